@@ -1,0 +1,406 @@
+"""CPU oracle for the FitHuBERT distillation step.  TEST INFRASTRUCTURE ONLY.
+
+A plain-PyTorch fp32, *functional* restatement (state-dict in, tensors out) of the
+reference arithmetic on the hot path.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module; the product
+package fithubert_b200/ never does (it fails loudly without its CUDA library).
+
+Parity pin: the reference ships no tests or golden vectors, so
+this oracle is pinned against the *reference's own files executed unmodified* through
+oracle/fairseq_stub (oracle/gen_golden.py -> tests/golden/*.pt, and the live check in
+tests/test_oracle_vs_reference.py when /root/reference is present), and the teacher
+additionally against torchaudio.models.hubert_base.  The optimizer (s3prl, source not
+available anywhere in this image) is restated from its published algorithm:
+"parity unpinned" for that one function.
+
+Every function cites the reference file:line it follows (paths relative to the
+reference root; [EXT] = fairseq @1b61bbad / s3prl @185e4b06, not vendored).
+"""
+from __future__ import annotations
+
+import ast
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+State = Dict[str, Tensor]
+
+FITHUBERT_CONV = "[(128, 10, 5)] + [(256, 1, 1)] + [(256, 3, 2)] * 4 + [(512, 1, 1)] + [(512, 2, 2)] * 2"
+HUBERT_CONV = "[(512,10,5)] + [(512,3,2)] * 4 + [(512,2,2)] * 2"
+
+
+# --------------------------------------------------------------------------- config
+def parse_conv_layers(spec) -> List[Tuple[int, int, int]]:
+    """The reference eval()s this string (modules/model.py:267,384); we evaluate the
+    same list arithmetic ('+' and '*' on list literals) without eval."""
+    if not isinstance(spec, str):
+        return [tuple(x) for x in spec]
+
+    def ev(node):
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Add):
+            return ev(node.left) + ev(node.right)
+        if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Mult):
+            return ev(node.left) * ev(node.right)
+        return ast.literal_eval(node)
+
+    return [tuple(int(v) for v in t) for t in ev(ast.parse(spec, mode="eval"))]
+
+
+def student_config(**over) -> dict:
+    """Defaults = data/conf/fithubert.yaml:27-89 (the `distiller:` group)."""
+    cfg = dict(
+        conv_feature_layers=FITHUBERT_CONV, conv_pos=128, conv_pos_groups=16,
+        encoder_layers=12, encoder_embed_dim=480, encoder_ffn_embed_dim=480,
+        encoder_attention_heads=12, pred_head_final_dim=768, tr_reduce_factor=2,
+        enable_tr_layer=True, layerwise_proj=True,
+    )
+    cfg.update(over)
+    return cfg
+
+
+def teacher_config(**over) -> dict:
+    """HuBERT-Base / wav2vec2-Base ([EXT] fairseq HubertConfig / Wav2Vec2Config defaults)."""
+    cfg = dict(
+        conv_feature_layers=HUBERT_CONV, conv_pos=128, conv_pos_groups=16,
+        encoder_layers=12, encoder_embed_dim=768, encoder_ffn_embed_dim=3072,
+        encoder_attention_heads=12, kind="hubert",
+    )
+    cfg.update(over)
+    return cfg
+
+
+# --------------------------------------------------------------------------- masks (integer, bit-exact)
+def conv_out_lengths(lengths: Tensor, conv_layers) -> Tensor:
+    """modules/model.py:376-391: per layer floor((len - k)/s + 1) in *float* arithmetic,
+    then .long().  Restated with the same float ops so ties round identically."""
+    x = lengths
+    for (_, k, s) in conv_layers:
+        x = torch.floor((x - k) / s + 1)
+    return x.to(torch.long)
+
+
+def mask_m1(padding_mask: Optional[Tensor], T: int, conv_layers) -> Optional[Tensor]:
+    """Student / wav2vec2 frame mask, modules/model.py:449-472.  Returns None when no
+    sample is padded.  Frame j is padding iff j >= conv_out_len(len_i)."""
+    if padding_mask is None or not bool(padding_mask.any()):
+        return None
+    input_lengths = (1 - padding_mask.long()).sum(-1)
+    out_len = conv_out_lengths(input_lengths, conv_layers)
+    m = torch.zeros(padding_mask.shape[0], T, dtype=torch.float32)
+    m[torch.arange(m.shape[0]), out_len - 1] = 1
+    return (1 - m.flip([-1]).cumsum(-1).flip([-1])).bool()
+
+
+def mask_m2(mask: Optional[Tensor], factor: int = 2) -> Optional[Tensor]:
+    """Time-reduction of the mask, modules/module.py:324-328: pairs, drop odd tail, any()."""
+    if mask is None:
+        return None
+    sp = mask.split(factor, 1)
+    if mask.shape[-1] % factor != 0:
+        sp = sp[:-1]
+    return torch.stack(sp).any(-1).transpose(0, 1)
+
+
+def mask_m3(padding_mask: Optional[Tensor], T: int) -> Optional[Tensor]:
+    """[EXT] HubertModel.forward_padding_mask: crop to a multiple of T, view
+    [B, T, L//T], all(-1).  Applied whenever a mask is passed (even all-False)."""
+    if padding_mask is None:
+        return None
+    extra = padding_mask.size(1) % T
+    if extra > 0:
+        padding_mask = padding_mask[:, :-extra]
+    return padding_mask.view(padding_mask.size(0), T, -1).all(-1)
+
+
+def valid_lengths(mask: Optional[Tensor], T: int, B: int) -> Tensor:
+    """Every mask above is a suffix mask; its per-sample valid length describes it fully."""
+    if mask is None:
+        return torch.full((B,), T, dtype=torch.long)
+    return (~mask).long().sum(-1)
+
+
+# --------------------------------------------------------------------------- blocks
+def conv_extractor(sd: State, prefix: str, x: Tensor, conv_layers) -> Tensor:
+    """modules/module.py:94-102 with mode='default', conv_bias=False: layer 0 is
+    conv -> Fp32GroupNorm(C, C) -> GELU (:65-71), the others conv -> GELU (:72-73)."""
+    x = x.unsqueeze(1)
+    for i, (c, k, s) in enumerate(conv_layers):
+        x = F.conv1d(x, sd[f"{prefix}conv_layers.{i}.0.weight"], None, stride=s)
+        if i == 0:
+            x = F.group_norm(x.float(), c, sd[f"{prefix}conv_layers.0.2.weight"],
+                             sd[f"{prefix}conv_layers.0.2.bias"], 1e-5)
+        x = F.gelu(x)
+    return x  # [B, C, T]
+
+
+def pos_conv(sd: State, prefix: str, x_btc: Tensor, k: int, groups: int) -> Tensor:
+    """modules/module.py:186-200,276-278: weight_norm(dim=2) grouped conv, pad k//2,
+    SamePad drops the last frame (k even), GELU.  Returns the conv branch [B,T,C]."""
+    v, g = sd[f"{prefix}weight_v"], sd[f"{prefix}weight_g"]
+    w = g * v / v.norm(dim=(0, 1), keepdim=True)
+    y = F.conv1d(x_btc.transpose(1, 2), w, sd[f"{prefix}bias"], padding=k // 2, groups=groups)
+    if k % 2 == 0:
+        y = y[:, :, :-1]
+    return F.gelu(y).transpose(1, 2)
+
+
+def mha(sd: State, p: str, x_tbc: Tensor, key_mask: Optional[Tensor], H: int) -> Tensor:
+    """[EXT] fairseq MultiheadAttention manual path: q scaled after
+    bias, -inf on padded keys, fp32 softmax, out_proj."""
+    T, B, E = x_tbc.shape
+    d = E // H
+    q = F.linear(x_tbc, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"]) * d ** -0.5
+    k = F.linear(x_tbc, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])
+    v = F.linear(x_tbc, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"])
+    q, k, v = (t.reshape(T, B * H, d).transpose(0, 1) for t in (q, k, v))
+    w = torch.bmm(q, k.transpose(1, 2))
+    if key_mask is not None:
+        w = w.view(B, H, T, T).masked_fill(key_mask[:, None, None, :], float("-inf")).view(B * H, T, T)
+    a = torch.bmm(torch.softmax(w.float(), -1), v)
+    a = a.transpose(0, 1).reshape(T, B, E)
+    return F.linear(a, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+
+
+def encoder_layer(sd: State, p: str, x: Tensor, key_mask, H: int) -> Tuple[Tensor, Tensor]:
+    """modules/module.py:557-580, post-LN branch, dropout = identity."""
+    E = x.shape[-1]
+    x = x + mha(sd, p + "self_attn.", x, key_mask, H)
+    x = F.layer_norm(x, (E,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], 1e-5)
+    h = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+    lr = F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+    x = F.layer_norm(x + lr, (E,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5)
+    return x, lr
+
+
+def encoder_prologue(sd: State, x: Tensor, mask: Optional[Tensor], cfg: dict) -> Tensor:
+    """modules/module.py:273-281: zero padded frames, x + pos_conv(x), LayerNorm."""
+    if mask is not None:
+        x = x.masked_fill(mask.unsqueeze(-1), 0.0)
+    x = x + pos_conv(sd, "encoder.pos_conv.0.", x, cfg["conv_pos"], cfg["conv_pos_groups"])
+    E = x.shape[-1]
+    return F.layer_norm(x, (E,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], 1e-5)
+
+
+# --------------------------------------------------------------------------- student
+def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional[Tensor] = None,
+                    heads: bool = True) -> dict:
+    """CustomStudentModel.forward, modules/model.py:420-552 (n_mels=0, transformer,
+    layerwise_proj=True, conv1d TR layer at index 0, dropout identity).
+    heads=False mirrors the state after _disable_projection_heads() (:393-399,500-502):
+    final_proj = proj_head[-1] applied to the last layer only."""
+    conv_layers = parse_conv_layers(cfg["conv_feature_layers"])
+    H = cfg["encoder_attention_heads"]
+    feats = conv_extractor(sd, "feature_extractor.", source, conv_layers).transpose(1, 2)
+    B, T, C = feats.shape
+    feats = F.layer_norm(feats, (C,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
+    mask = mask_m1(padding_mask, T, conv_layers)
+    feats = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
+    features_to_distill = feats
+    x = encoder_prologue(sd, feats, mask, cfg).transpose(0, 1)  # [T,B,C]
+    # time-reduction conv, modules/module.py:317-321 (drops the last frame when T is odd)
+    x = F.conv1d(x.permute(1, 2, 0), sd["encoder.layers.0.weight"], sd["encoder.layers.0.bias"],
+                 stride=cfg["tr_reduce_factor"]).permute(2, 0, 1)
+    tr_layer_results = [x]
+    rmask = mask_m2(mask, cfg["tr_reduce_factor"])
+    layer_results = []
+    for i in range(1, cfg["encoder_layers"] + 1):
+        x, lr = encoder_layer(sd, f"encoder.layers.{i}.", x, rmask, H)
+        layer_results.append((x, None, lr))
+
+    def head(i, h_tbc):  # LayerWiseProjHead.forward, modules/module.py:649-661
+        y = F.conv_transpose1d(h_tbc.permute(1, 2, 0), sd[f"proj_head.{i}.upsampler.weight"],
+                               sd[f"proj_head.{i}.upsampler.bias"], stride=cfg["tr_reduce_factor"])
+        return F.linear(y.transpose(1, 2), sd[f"proj_head.{i}.lin_proj.weight"], sd[f"proj_head.{i}.lin_proj.bias"])
+
+    if heads:
+        projections = [head(i, layer_results[i][0]) for i in range(cfg["encoder_layers"])]
+        out = projections[-1]
+    else:
+        projections = None
+        out = head(cfg["encoder_layers"] - 1, x)
+    return {"x": out, "padding_mask": mask, "features": features_to_distill,
+            "layer_results": layer_results, "tr_layer_results": tr_layer_results,
+            "projections": projections}
+
+
+# --------------------------------------------------------------------------- teacher
+def teacher_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional[Tensor] = None) -> dict:
+    """TeacherWrapper.extract_features (utils/utils.py:80-99) around [EXT]
+    HubertModel / Wav2Vec2Model.extract_features(mask=None), eval mode."""
+    conv_layers = parse_conv_layers(cfg["conv_feature_layers"])
+    H = cfg["encoder_attention_heads"]
+    feats = conv_extractor(sd, "feature_extractor.", source, conv_layers).transpose(1, 2)
+    B, T, C = feats.shape
+    feats = F.layer_norm(feats, (C,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
+    if cfg.get("kind", "hubert") == "hubert":
+        mask = mask_m3(padding_mask, T)
+    else:
+        mask = mask_m1(padding_mask, T, conv_layers)
+    feats = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
+    x = encoder_prologue(sd, feats, mask, cfg).transpose(0, 1)
+    layer_results = []
+    for i in range(cfg["encoder_layers"]):
+        x, lr = encoder_layer(sd, f"encoder.layers.{i}.", x, mask, H)
+        layer_results.append((x, (None, lr)))
+    return {"layer_results": layer_results, "x": layer_results[-1][0].transpose(0, 1),
+            "features": [feats], "padding_mask": mask}
+
+
+# --------------------------------------------------------------------------- loss
+def layer_weights(n_layers: int, random_layer_weight: float = 0.1) -> List[float]:
+    """train.py:90-91,290-291 with distil_random_layer = n_layers-1: every lower layer
+    is selected (a permutation), each weighted random_layer_weight; last layer 1.0."""
+    return [random_layer_weight] * (n_layers - 1) + [1.0]
+
+
+def distill_loss(projections: Sequence[Tensor], teacher_layer_results, weights: Sequence[float],
+                 rec_loss_type: str = "mse") -> Tuple[Tensor, Tensor]:
+    """W2V2Distil.calculate_loss rec branch, train.py:250-267,282-293,372-378
+    (rec_loss_weight 1, all other weights 0).  Returns (total, per-layer weighted means)
+    in *layer order* (the reference logs them in permuted order, train.py:319-321)."""
+    pred = torch.stack(list(projections), dim=1)  # B x N x T' x D
+    tgt = torch.stack([lr[0].transpose(0, 1) for lr in teacher_layer_results], dim=1)
+    tgt = tgt.narrow(2, 0, pred.shape[2])
+    if rec_loss_type == "mse":
+        e = F.mse_loss(pred.float(), tgt.float(), reduction="none")
+    elif rec_loss_type == "l1":
+        e = F.l1_loss(pred.float(), tgt.float(), reduction="none")
+    else:
+        raise NotImplementedError("rec_loss_type must be one of 'l1', 'mse'.")
+    w = torch.tensor(list(weights), dtype=e.dtype).view(1, -1, 1, 1)
+    per_layer = (e * w).mean((0, 2, 3))
+    return per_layer.sum(), per_layer
+
+
+# --------------------------------------------------------------------------- optimizer (parity unpinned)
+def lr_schedule(step: int, total_steps: int, warmup: float) -> float:
+    """[EXT] s3prl warmup_linear: x/w for x < w, else max((x-1)/(w-1), 0)."""
+    x = step / total_steps
+    return x / warmup if x < warmup else max((x - 1.0) / (warmup - 1.0), 0.0)
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float,
+               betas=(0.9, 0.98), eps=1e-6, weight_decay=1e-6, mode: str = "s3prl") -> None:
+    """In-place Adam step.  mode='s3prl': SURVEY App. B.3 ([EXT] Lamb(adam=True,
+    correct_bias=True)); eps on the un-corrected sqrt(v), decay inside the corrected
+    step.  mode='torch': torch.optim.AdamW semantics.  `step` is 1-based."""
+    b1, b2 = betas
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    if mode == "s3prl":
+        step_size = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        p.add_(m / (v.sqrt() + eps) + weight_decay * p, alpha=-step_size)
+    else:
+        p.mul_(1 - lr * weight_decay)
+        denom = (v.sqrt() / math.sqrt(1 - b2 ** step)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / (1 - b1 ** step))
+
+
+# --------------------------------------------------------------------------- init
+def init_encoder_state(cfg: dict, gen: torch.Generator, n_layers_offset: int) -> State:
+    E, Fd, k, G = cfg["encoder_embed_dim"], cfg["encoder_ffn_embed_dim"], cfg["conv_pos"], cfg["conv_pos_groups"]
+    sd: State = {}
+
+    def normal(*shape, std):
+        return torch.empty(*shape).normal_(0.0, std, generator=gen)
+
+    # modules/module.py:194-199
+    wv = normal(E, E // G, k, std=math.sqrt(4.0 / (k * E)))
+    sd["encoder.pos_conv.0.bias"] = torch.zeros(E)
+    sd["encoder.pos_conv.0.weight_g"] = wv.norm(dim=(0, 1), keepdim=True)
+    sd["encoder.pos_conv.0.weight_v"] = wv
+    for i in range(cfg["encoder_layers"]):
+        p = f"encoder.layers.{i + n_layers_offset}."
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):  # init_bert_params
+            sd[p + f"self_attn.{nm}.weight"] = normal(E, E, std=0.02)
+            sd[p + f"self_attn.{nm}.bias"] = torch.zeros(E)
+        sd[p + "self_attn_layer_norm.weight"] = torch.ones(E)
+        sd[p + "self_attn_layer_norm.bias"] = torch.zeros(E)
+        sd[p + "fc1.weight"] = normal(Fd, E, std=0.02)
+        sd[p + "fc1.bias"] = torch.zeros(Fd)
+        sd[p + "fc2.weight"] = normal(E, Fd, std=0.02)
+        sd[p + "fc2.bias"] = torch.zeros(E)
+        sd[p + "final_layer_norm.weight"] = torch.ones(E)
+        sd[p + "final_layer_norm.bias"] = torch.zeros(E)
+    sd["encoder.layer_norm.weight"] = torch.ones(E)
+    sd["encoder.layer_norm.bias"] = torch.zeros(E)
+    return sd
+
+
+def _init_frontend(cfg: dict, gen: torch.Generator) -> State:
+    sd: State = {}
+    cin = 1
+    conv_layers = parse_conv_layers(cfg["conv_feature_layers"])
+    for i, (c, k, s) in enumerate(conv_layers):  # kaiming_normal_, modules/module.py:47
+        sd[f"feature_extractor.conv_layers.{i}.0.weight"] = torch.empty(c, cin, k).normal_(
+            0.0, math.sqrt(2.0 / (cin * k)), generator=gen)
+        cin = c
+    c0 = conv_layers[0][0]
+    sd["feature_extractor.conv_layers.0.2.weight"] = torch.ones(c0)
+    sd["feature_extractor.conv_layers.0.2.bias"] = torch.zeros(c0)
+    sd["layer_norm.weight"] = torch.ones(cin)
+    sd["layer_norm.bias"] = torch.zeros(cin)
+    E = cfg["encoder_embed_dim"]
+    b = 1 / math.sqrt(cin)  # nn.Linear default init
+    sd["post_extract_proj.weight"] = torch.empty(E, cin).uniform_(-b, b, generator=gen)
+    sd["post_extract_proj.bias"] = torch.empty(E).uniform_(-b, b, generator=gen)
+    return sd
+
+
+def init_student_state(cfg: dict, seed: int = 0, perturb: bool = False) -> State:
+    """Random student weights with the reference's parameter names
+    and init distributions.  perturb=True randomises the biases and norm
+    affine parameters too (they are 0/1 at init) so parity tests exercise them."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = _init_frontend(cfg, gen)
+    sd.update(init_encoder_state(cfg, gen, 1))
+    E, D = cfg["encoder_embed_dim"], cfg["pred_head_final_dim"]
+    f = cfg["tr_reduce_factor"]
+
+    def uni(*shape, bound):
+        return torch.empty(*shape).uniform_(-bound, bound, generator=gen)
+
+    bt = 1 / math.sqrt(E * f)
+    sd["encoder.layers.0.weight"] = uni(E, E, f, bound=bt)
+    sd["encoder.layers.0.bias"] = uni(E, bound=bt)
+    sd["upsampler.weight"] = uni(E, E, f, bound=bt)  # dead when layerwise_proj
+    sd["upsampler.bias"] = uni(E, bound=bt)
+    for i in range(cfg["encoder_layers"]):
+        sd[f"proj_head.{i}.upsampler.weight"] = uni(E, E, f, bound=bt)
+        sd[f"proj_head.{i}.upsampler.bias"] = uni(E, bound=bt)
+        sd[f"proj_head.{i}.lin_proj.weight"] = uni(D, E, bound=1 / math.sqrt(E))
+        sd[f"proj_head.{i}.lin_proj.bias"] = uni(D, bound=1 / math.sqrt(E))
+    if perturb:
+        _perturb(sd, gen)
+    return sd
+
+
+def init_teacher_state(cfg: dict, seed: int = 1, perturb: bool = False) -> State:
+    gen = torch.Generator().manual_seed(seed)
+    sd = _init_frontend(cfg, gen)
+    sd.update(init_encoder_state(cfg, gen, 0))
+    if perturb:
+        _perturb(sd, gen)
+    return sd
+
+
+def _perturb(sd: State, gen: torch.Generator) -> None:
+    for k, t in sd.items():
+        if k.endswith(".bias") or "layer_norm.weight" in k or k.endswith("conv_layers.0.2.weight"):
+            t.add_(torch.empty_like(t).normal_(0.0, 0.05, generator=gen))
+
+
+def synth_batch(B: int, Lmax: int, lengths: Sequence[int], seed: int = 1234) -> Tuple[Tensor, Tensor]:
+    """Input contract of utils/dataset.py:63-74: fp32 [B, L] zero-padded waveforms and a
+    bool padding mask (True = pad).  Waveform = 0.1*randn."""
+    gen = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(B, Lmax, generator=gen)
+    ar = torch.arange(Lmax).unsqueeze(0)
+    pm = ~(ar < torch.tensor(list(lengths)).unsqueeze(1))
+    x = x.masked_fill(pm, 0.0)
+    return x, pm

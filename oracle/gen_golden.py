@@ -1,0 +1,152 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference files.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+It imports reference modules/model.py + modules/module.py through oracle/fairseq_stub,
+builds (a) a *tiny* student (same architecture family as data/conf/fithubert.yaml with
+small widths so the weights fit in a fixture) and (b) a tiny HuBERT-style teacher
+composed from the reference's own ConvFeatureExtractionModel / TransformerEncoder
+classes (they are copies of fairseq wav2vec2.py; top-level wiring per SURVEY App. B.2),
+runs them on seeded synthetic waveforms with padding, and stores weights, inputs and
+outputs.  tests/test_oracle_golden.py replays the fixtures through oracle/fhb_oracle.py
+(CPU) and tests/test_gpu_parity.py through the CUDA path.
+"""
+import os
+import sys
+import types
+import warnings
+
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("FHB_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(HERE, "fairseq_stub"), REF]
+sys.path.insert(0, HERE)
+warnings.filterwarnings("ignore")
+
+from modules.model import CustomStudentModel, CustomStudentModelConfig  # noqa: E402  (reference)
+from modules.module import ConvFeatureExtractionModel, TransformerEncoder  # noqa: E402  (reference)
+import fhb_oracle as O  # noqa: E402
+
+TINY_STUDENT = dict(
+    conv_feature_layers="[(16, 10, 5)] + [(32, 1, 1)] + [(32, 3, 2)] * 4 + [(64, 1, 1)] + [(64, 2, 2)] * 2",
+    encoder_layers=3, encoder_embed_dim=48, encoder_ffn_embed_dim=48, encoder_attention_heads=4,
+    conv_pos=16, conv_pos_groups=4, pred_head_final_dim=64,
+)
+TINY_TEACHER = dict(
+    conv_feature_layers="[(32,10,5)] + [(32,3,2)] * 4 + [(32,2,2)] * 2",
+    encoder_layers=3, encoder_embed_dim=64, encoder_ffn_embed_dim=128, encoder_attention_heads=4,
+    conv_pos=16, conv_pos_groups=4,
+)
+
+
+def ref_student_cfg(yaml_distiller: dict, **over):
+    d = dict(yaml_distiller)
+    d.update(over)
+    return CustomStudentModelConfig(**d)
+
+
+class RefTeacher(nn.Module):
+    """HuBERT/wav2vec2 `features_only` top level wired from reference classes."""
+
+    def __init__(self, cfg: dict):
+        super().__init__()
+        layers = O.parse_conv_layers(cfg["conv_feature_layers"])
+        self.kind = cfg.get("kind", "hubert")
+        self.conv_layers = layers
+        self.feature_extractor = ConvFeatureExtractionModel(layers, 0.0, "default", False)
+        self.layer_norm = nn.LayerNorm(layers[-1][0])
+        self.post_extract_proj = nn.Linear(layers[-1][0], cfg["encoder_embed_dim"])
+        args = types.SimpleNamespace(
+            dropout=0.1, encoder_embed_dim=cfg["encoder_embed_dim"], required_seq_len_multiple=1,
+            pos_conv_depth=1, conv_pos=cfg["conv_pos"], conv_pos_groups=cfg["conv_pos_groups"],
+            enable_tr_layer=False, encoder_layers=cfg["encoder_layers"], layer_type="transformer",
+            encoder_ffn_embed_dim=cfg["encoder_ffn_embed_dim"],
+            encoder_attention_heads=cfg["encoder_attention_heads"], attention_dropout=0.1,
+            activation_dropout=0.0, activation_fn="gelu", layer_norm_first=False,
+            checkpoint_activations=False, encoder_layerdrop=0.0)
+        self.encoder = TransformerEncoder(args)
+
+    def forward(self, source, padding_mask):
+        f = self.feature_extractor(source).transpose(1, 2)
+        f = self.layer_norm(f)
+        T = f.shape[1]
+        if self.kind == "hubert":
+            mask = O.mask_m3(padding_mask, T)
+        else:
+            mask = O.mask_m1(padding_mask, T, self.conv_layers)
+        f = self.post_extract_proj(f)
+        x, layer_results, _ = self.encoder(f.clone(), padding_mask=mask)
+        return {"layer_results": [(lr[0], (None, lr[2])) for lr in layer_results],
+                "features": [f], "padding_mask": mask}
+
+
+def perturb_(module, seed):
+    """Biases / norm affines are 0/1 at reference init: randomise so they matter."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in module.named_parameters():
+            if n.endswith(".bias") or "layer_norm.weight" in n or n.endswith("conv_layers.0.2.weight"):
+                p.add_(torch.empty_like(p).normal_(0.0, 0.05, generator=g))
+
+
+def run_case(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, kind="hubert", grads=True):
+    torch.manual_seed(0)
+    student = CustomStudentModel(ref_student_cfg(yaml_distiller, **s_over))
+    tcfg = O.teacher_config(**t_over, kind=kind)
+    teacher = RefTeacher(tcfg)
+    perturb_(student, 11)
+    perturb_(teacher, 12)
+    student.eval()  # dropout = identity (parity runs use p = 0)
+    teacher.eval()
+    x, pm = O.synth_batch(B, Lmax, lengths, seed=1234)
+    with torch.no_grad():
+        t_res = teacher(x, pm)
+    s_res = student(source=x, padding_mask=pm)
+    n_layers = len(s_res["projections"])
+    w = O.layer_weights(n_layers, 0.1)
+    # calculate_loss rec branch restated inline from train.py:250-293 (train.py itself
+    # cannot be imported: pytorch_lightning / s3prl are absent)
+    pred = torch.stack(s_res["projections"], 1)
+    tgt = torch.stack([lr[0].transpose(0, 1) for lr in t_res["layer_results"]], 1).narrow(2, 0, pred.shape[2])
+    rec = torch.nn.functional.mse_loss(pred, tgt, reduction="none")
+    rec[:, :-1] = rec[:, :-1] * 0.1
+    per_layer = rec.mean((0, 2, 3))
+    loss = per_layer.sum()
+    out = {
+        "student_cfg": s_over, "teacher_cfg": dict(t_over, kind=kind),
+        "student_state": {k: v.detach().clone() for k, v in student.state_dict().items()},
+        "teacher_state": {k: v.detach().clone() for k, v in teacher.state_dict().items()},
+        "source": x, "padding_mask": pm, "layer_weights": w,
+        "student_mask": s_res["padding_mask"], "teacher_mask": t_res["padding_mask"],
+        "student_features": s_res["features"].detach(),
+        "student_layers": [lr[0].detach() for lr in s_res["layer_results"]],
+        "student_tr": s_res["tr_layer_results"][0].detach(),
+        "projections": [p.detach() for p in s_res["projections"]],
+        "teacher_layers": [lr[0].detach() for lr in t_res["layer_results"]],
+        "teacher_features": t_res["features"][0].detach(),
+        "loss": loss.detach(), "per_layer": per_layer.detach(),
+    }
+    if grads:
+        loss.backward()
+        out["grads"] = {n: p.grad.detach().clone() for n, p in student.named_parameters() if p.grad is not None}
+        out["no_grad_params"] = [n for n, p in student.named_parameters() if p.grad is None]
+    path = os.path.join(HERE, "..", "tests", "golden", name + ".pt")
+    torch.save(out, path)
+    print(name, "loss", float(loss), "bytes", os.path.getsize(path))
+
+
+def main():
+    import yaml
+    with open(os.path.join(REF, "data/conf/fithubert.yaml")) as f:
+        ycfg = yaml.safe_load(f)["distiller"]
+    run_case("tiny_hubert_pad", TINY_STUDENT, TINY_TEACHER, 3, 9000, [9000, 7411, 5000], ycfg)
+    run_case("tiny_hubert_nopad", TINY_STUDENT, TINY_TEACHER, 2, 6500, [6500, 6500], ycfg)
+    run_case("tiny_w2v2_pad_oddT", TINY_STUDENT, TINY_TEACHER, 2, 8100, [8100, 4321], ycfg, kind="wav2vec2")
+
+
+if __name__ == "__main__":
+    main()

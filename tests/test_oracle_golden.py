@@ -1,0 +1,71 @@
+"""Oracle (oracle/fhb_oracle.py) vs fixtures produced by the unmodified reference
+(oracle/gen_golden.py).  CPU, fp32, tolerance 1e-5 max-abs (observed ~1e-6)."""
+import glob
+import os
+
+import pytest
+import torch
+
+import fhb_oracle as O
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "tiny_*.pt")))
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(c) for c in CASES])
+def test_oracle_matches_reference_fixture(path):
+    g = torch.load(path)
+    scfg = O.student_config(**g["student_cfg"])
+    tcfg = O.teacher_config(**g["teacher_cfg"])
+    ssd = {k: v.clone().requires_grad_(True) for k, v in g["student_state"].items()}
+    s = O.student_forward(ssd, scfg, g["source"], g["padding_mask"])
+    with torch.no_grad():
+        t = O.teacher_forward(g["teacher_state"], tcfg, g["source"], g["padding_mask"])
+    # integer outputs: bit-exact
+    for mine, ref in ((s["padding_mask"], g["student_mask"]), (t["padding_mask"], g["teacher_mask"])):
+        assert (mine is None) == (ref is None)
+        if ref is not None:
+            assert torch.equal(mine, ref)
+    for i, ref in enumerate(g["teacher_layers"]):
+        assert relerr(t["layer_results"][i][0], ref) < 1e-5
+    for i, ref in enumerate(g["student_layers"]):
+        assert relerr(s["layer_results"][i][0], ref) < 1e-5
+    assert relerr(s["tr_layer_results"][0], g["student_tr"]) < 1e-5
+    for i, ref in enumerate(g["projections"]):
+        assert relerr(s["projections"][i], ref) < 1e-5
+    loss, per_layer = O.distill_loss(s["projections"], t["layer_results"], g["layer_weights"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert relerr(per_layer, g["per_layer"]) < 1e-5
+    loss.backward()
+    for n, ref in g["grads"].items():
+        assert ssd[n].grad is not None, n
+        # k_proj.bias has a mathematically zero gradient (softmax shift invariance): atol
+        assert float((ssd[n].grad - ref).abs().max()) < 2e-4 * float(ref.abs().max()) + 1e-8, n
+    for n in g["no_grad_params"]:
+        assert ssd[n].grad is None
+
+
+def test_conv_layer_string_parser():
+    assert O.parse_conv_layers(O.FITHUBERT_CONV) == [(128, 10, 5), (256, 1, 1)] + [(256, 3, 2)] * 4 + [(512, 1, 1)] + [(512, 2, 2)] * 2
+    assert len(O.parse_conv_layers(O.HUBERT_CONV)) == 7
+
+
+def test_mask_rules_suffix_and_lengths():
+    conv = O.parse_conv_layers(O.FITHUBERT_CONV)
+    L = 64000
+    for n in (64000, 61000, 40000, 63999, 63681, 63680, 63679):
+        pm = ~(torch.arange(L)[None] < torch.tensor([[L], [n]]))
+        T = int(O.conv_out_lengths(torch.tensor([L]), conv))
+        m1 = O.mask_m1(pm, T, conv)
+        if n == L:
+            assert m1 is None
+            continue
+        v = O.valid_lengths(m1, T, 2)
+        assert v.tolist() == [T, int(O.conv_out_lengths(torch.tensor([n]), conv))]
+        assert O.valid_lengths(O.mask_m2(m1), T // 2, 2).tolist() == [T // 2, v[1] // 2]
+        m3 = O.mask_m3(pm, T)
+        chunk = (L - L % T) // T
+        assert O.valid_lengths(m3, T, 2)[1] == min(T, -(-n // chunk))
