@@ -1,0 +1,304 @@
+// K1: waveform conv (1 -> C channels, k=10, s=5, no bias) + GroupNorm(C groups) + GELU, fused.
+// Reference: modules/module.py:46,65-71,99-100 layer 0 (Conv1d -> Fp32GroupNorm(dim,dim) -> GELU).
+//
+// HBM plan.  GroupNorm needs per-(sample, channel) mean/var of the conv output over ALL T0 frames
+// (zero padding included).  Because the conv has one input channel, those statistics are
+// a function of 65 numbers per sample: S_j = sum_t x[5t+j] and R_jj' = sum_t x[5t+j] x[5t+j']:
+//   mean_c = w_c . S / T0,   E[y^2]_c = w_c^T R w_c / T0.
+// So pass 1 reads only the waveform (1 MB/sample), never the C x T0 conv output; pass 2 reads the
+// waveform again and writes the bf16 channel-last output once.  Backward needs dW, dgamma, dbeta only
+// (the waveform has no gradient) and is ONE pass over dY using the same algebra (see bwd kernel).
+#include "fhb_common.cuh"
+
+namespace {
+
+constexpr int kK = 10, kS = 5;
+constexpr int kNR = 55;            // upper triangle of the 10x10 autocorrelation
+constexpr int kNStat = kK + kNR;   // 65
+
+// ---------------------------------------------------------------- pass 1: S_j and R_jj'
+__global__ void __launch_bounds__(256) conv0_stats_kernel(const float* __restrict__ wave, long long ld, int T0,
+                                                          int frames_per_block, double* __restrict__ stat) {
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(t_begin + frames_per_block, T0);
+  const float* x = wave + (long long)b * ld;
+  float acc[kNStat];
+#pragma unroll
+  for (int i = 0; i < kNStat; ++i) acc[i] = 0.f;
+  for (int t = t_begin + threadIdx.x; t < t_end; t += blockDim.x) {
+    float v[kK];
+#pragma unroll
+    for (int j = 0; j < kK; ++j) v[j] = __ldg(x + (long long)t * kS + j);
+    int r = kK;
+#pragma unroll
+    for (int j = 0; j < kK; ++j) {
+      acc[j] += v[j];
+#pragma unroll
+      for (int q = j; q < kK; ++q) acc[r++] += v[j] * v[q];
+    }
+  }
+  __shared__ float red[8][kNStat];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kNStat; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNStat) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += (double)red[w][threadIdx.x];
+    atomicAdd(stat + (long long)b * kNStat + threadIdx.x, s);
+  }
+}
+
+__device__ __forceinline__ double quad_form(const float* w, const double* R) {
+  // w^T R w with R stored as the packed upper triangle
+  double q = 0.0;
+  int r = 0;
+  for (int j = 0; j < kK; ++j)
+    for (int k2 = j; k2 < kK; ++k2) {
+      const double term = (double)w[j] * (double)w[k2] * R[r++];
+      q += (j == k2) ? term : 2.0 * term;
+    }
+  return q;
+}
+
+__global__ void conv0_finalize_stats_kernel(const double* __restrict__ stat, const float* __restrict__ weight, int C,
+                                            int T0, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* S = stat + (long long)b * kNStat;
+  float w[kK];
+  double m = 0.0;
+  for (int j = 0; j < kK; ++j) {
+    w[j] = weight[c * kK + j];
+    m += (double)w[j] * S[j];
+  }
+  m /= (double)T0;
+  const double ey2 = quad_form(w, S + kK) / (double)T0;
+  const double var = fmax(ey2 - m * m, 0.0);
+  mean[b * C + c] = (float)m;
+  rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------- pass 2: normalise + GELU + store
+template <int CPT>  // channels per thread (8 -> one 16-byte bf16 store)
+__global__ void __launch_bounds__(256)
+conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
+                 const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float xs[];  // frames_per_block*5 + 5 samples
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int nframes = min(frames_per_block, T0 - t_begin);
+  const float* x = wave + (long long)b * ld + (long long)t_begin * kS;
+  const int nsamp = nframes * kS + (kK - kS);
+  for (int i = threadIdx.x; i < nsamp; i += blockDim.x) xs[i] = __ldg(x + i);
+  const int tcols = C / CPT;
+  const int tx = threadIdx.x % tcols, ty = threadIdx.x / tcols, fy = blockDim.x / tcols;
+  const int c0 = tx * CPT;
+  float w[CPT][kK], sc[CPT], sh[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+    for (int j = 0; j < kK; ++j) w[i][j] = __ldg(weight + (c0 + i) * kK + j);
+    const float r = rstd[b * C + c0 + i], g = __ldg(gamma + c0 + i);
+    sc[i] = r * g;
+    sh[i] = __ldg(beta + c0 + i) - mean[b * C + c0 + i] * r * g;
+  }
+  __syncthreads();
+  if (ty >= fy) return;
+  __nv_bfloat16* o = out + ((long long)b * T0 + t_begin) * C + c0;
+  for (int t = ty; t < nframes; t += fy) {
+    float v[kK];
+#pragma unroll
+    for (int j = 0; j < kK; ++j) v[j] = xs[t * kS + j];
+    float y[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < kK; ++j) a = fmaf(w[i][j], v[j], a);
+      y[i] = gelu_erf(fmaf(a, sc[i], sh[i]));
+    }
+    uint32_t pk[CPT / 2];
+#pragma unroll
+    for (int i = 0; i < CPT / 2; ++i) pk[i] = pack_bf16(y[2 * i], y[2 * i + 1]);
+    if (CPT == 8) {
+      *reinterpret_cast<uint4*>(o + (long long)t * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    } else {
+      *reinterpret_cast<uint2*>(o + (long long)t * C) = make_uint2(pk[0], pk[1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward (single pass over dY)
+// Per (b, c) accumulate  A0 = sum_t dz,  A1 = sum_t dz*xhat,  P_j = sum_t dz*x[5t+j]   (dz = dY*gelu'(z)).
+constexpr int kNAcc = 2 + kK;  // 12
+template <int CPT>             // 4
+__global__ void __launch_bounds__(256)
+conv0_bwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
+                 const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dy,
+                 float* __restrict__ acc_out /*[B][C][12]*/) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int nframes = min(frames_per_block, T0 - t_begin);
+  const int nsamp = nframes * kS + (kK - kS);
+  float* xs = smem;
+  float* red = smem + frames_per_block * kS + (kK - kS);  // [C][12]
+  const float* x = wave + (long long)b * ld + (long long)t_begin * kS;
+  for (int i = threadIdx.x; i < nsamp; i += blockDim.x) xs[i] = __ldg(x + i);
+  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) red[i] = 0.f;
+  const int tcols = C / CPT;
+  const int tx = threadIdx.x % tcols, ty = threadIdx.x / tcols, fy = blockDim.x / tcols;
+  const int c0 = tx * CPT;
+  float w[CPT][kK], mu[CPT], rs[CPT], g[CPT], be[CPT], acc[CPT][kNAcc];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+#pragma unroll
+    for (int j = 0; j < kK; ++j) w[i][j] = __ldg(weight + (c0 + i) * kK + j);
+    mu[i] = mean[b * C + c0 + i];
+    rs[i] = rstd[b * C + c0 + i];
+    g[i] = __ldg(gamma + c0 + i);
+    be[i] = __ldg(beta + c0 + i);
+#pragma unroll
+    for (int q = 0; q < kNAcc; ++q) acc[i][q] = 0.f;
+  }
+  __syncthreads();
+  if (ty < fy) {
+    const __nv_bfloat16* d = dy + ((long long)b * T0 + t_begin) * C + c0;
+    for (int t = ty; t < nframes; t += fy) {
+      float v[kK];
+#pragma unroll
+      for (int j = 0; j < kK; ++j) v[j] = xs[t * kS + j];
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(d + (long long)t * C));
+      const float2 d01 = unpack_bf16(raw.x), d23 = unpack_bf16(raw.y);
+      const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < kK; ++j) a = fmaf(w[i][j], v[j], a);
+        const float xhat = (a - mu[i]) * rs[i];
+        const float dz = dv[i] * gelu_erf_grad(fmaf(xhat, g[i], be[i]));
+        acc[i][0] += dz;
+        acc[i][1] += dz * xhat;
+#pragma unroll
+        for (int j = 0; j < kK; ++j) acc[i][2 + j] = fmaf(dz, v[j], acc[i][2 + j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+      for (int q = 0; q < kNAcc; ++q) atomicAdd(&red[(c0 + i) * kNAcc + q], acc[i][q]);
+  }
+  __syncthreads();
+  float* o = acc_out + (long long)b * C * kNAcc;
+  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) atomicAdd(o + i, red[i]);
+}
+
+// dW[c][j], dgamma[c], dbeta[c] from the per-(b,c) accumulators (see header comment for the algebra)
+__global__ void conv0_bwd_finalize_kernel(const float* __restrict__ acc, const double* __restrict__ stat,
+                                          const float* __restrict__ weight, const float* __restrict__ gamma,
+                                          const float* __restrict__ mean, const float* __restrict__ rstd, int B, int C,
+                                          int T0, float* __restrict__ dW, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float w[kK];
+  for (int j = 0; j < kK; ++j) w[j] = weight[c * kK + j];
+  const double gm = gamma[c];
+  double dw[kK], dg = 0.0, db = 0.0;
+  for (int j = 0; j < kK; ++j) dw[j] = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* a = acc + ((long long)b * C + c) * kNAcc;
+    const double* S = stat + (long long)b * kNStat;
+    const double* R = S + kK;
+    const double r = rstd[b * C + c], m = mean[b * C + c];
+    const double a0 = a[0], a1 = a[1];
+    dg += a1;
+    db += a0;
+    for (int j = 0; j < kK; ++j) {
+      // sum_t y x_j = sum_j' w_j' R[j', j]
+      double yx = 0.0;
+      for (int q = 0; q < kK; ++q) {
+        const int lo = q < j ? q : j, hi = q < j ? j : q;
+        const int idx = lo * kK - lo * (lo - 1) / 2 + (hi - lo);
+        yx += (double)w[q] * R[idx];
+      }
+      const double xhat_x = r * (yx - m * S[j]);
+      dw[j] += r * gm * ((double)a[2 + j] - a0 / T0 * S[j] - a1 / T0 * xhat_x);
+    }
+  }
+  for (int j = 0; j < kK; ++j) dW[c * kK + j] = (accumulate ? dW[c * kK + j] : 0.f) + (float)dw[j];
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)dg;
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)db;
+}
+
+int check_common(const fhb_conv0_args* a) {
+  FHB_ARG_CHECK(a != nullptr, "conv0: null args");
+  FHB_ARG_CHECK(a->kernel == kK && a->stride == kS, "conv0: only k=10,s=5 is implemented (got k=%d,s=%d)", a->kernel,
+                a->stride);
+  FHB_ARG_CHECK(a->B > 0 && a->C > 0 && a->T0 > 0, "conv0: empty problem");
+  FHB_ARG_CHECK((long long)(a->T0 - 1) * kS + kK <= a->L, "conv0: T0=%d frames do not fit in L=%d samples", a->T0, a->L);
+  FHB_ARG_CHECK(a->C % 8 == 0 && 256 % (a->C / 8) == 0 && a->C <= 2048, "conv0: C=%d must be 8*2^k, <= 2048", a->C);
+  FHB_ARG_CHECK(a->wave && a->weight && a->gamma && a->beta && a->stat && a->mean && a->rstd, "conv0: null pointer");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* a, fhb_stream_t stream) {
+  int rc = check_common(a);
+  if (rc) return rc;
+  FHB_ARG_CHECK(a->out != nullptr, "conv0 fwd: null out");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FHB_CUDA_CHECK(cudaMemsetAsync(a->stat, 0, sizeof(double) * kNStat * a->B, s));
+  {
+    const int fpb = 2048;
+    dim3 grid((a->T0 + fpb - 1) / fpb, a->B);
+    conv0_stats_kernel<<<grid, 256, 0, s>>>(a->wave, a->wave_ld, a->T0, fpb, a->stat);
+    FHB_LAUNCH_CHECK();
+  }
+  {
+    dim3 grid((a->C + 127) / 128, a->B);
+    conv0_finalize_stats_kernel<<<grid, 128, 0, s>>>(a->stat, a->weight, a->C, a->T0, a->eps, a->mean, a->rstd);
+    FHB_LAUNCH_CHECK();
+  }
+  {
+    const int fpb = 64 * (256 / (a->C / 8)) / 4;  // 64 frames per thread-row group ... keeps ~16 frames/thread
+    const int frames = fpb < 16 ? 16 : fpb;
+    dim3 grid((a->T0 + frames - 1) / frames, a->B);
+    const size_t smem = sizeof(float) * (frames * kS + (kK - kS));
+    conv0_fwd_kernel<8><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
+                                                 a->mean, a->rstd, static_cast<__nv_bfloat16*>(a->out));
+    FHB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t stream) {
+  int rc = check_common(a);
+  if (rc) return rc;
+  FHB_ARG_CHECK(a->dy && a->acc && a->dweight && a->dgamma && a->dbeta, "conv0 bwd: null pointer");
+  FHB_ARG_CHECK(a->C % 4 == 0 && 256 % (a->C / 4) == 0, "conv0 bwd: C=%d must be 4*2^k, <= 1024", a->C);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FHB_CUDA_CHECK(cudaMemsetAsync(a->acc, 0, sizeof(float) * kNAcc * a->B * a->C, s));
+  const int fy = 256 / (a->C / 4);
+  const int frames = fy * 32;
+  dim3 grid((a->T0 + frames - 1) / frames, a->B);
+  const size_t smem = sizeof(float) * (frames * kS + (kK - kS) + a->C * kNAcc);
+  conv0_bwd_kernel<4><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
+                                              a->mean, a->rstd, static_cast<const __nv_bfloat16*>(a->dy), a->acc);
+  FHB_LAUNCH_CHECK();
+  conv0_bwd_finalize_kernel<<<(a->C + 63) / 64, 64, 0, s>>>(a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
+                                                           a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
+                                                           a->accumulate);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,104 @@
+"""ctypes binding of libfhb_sm100a.so (include/fhb.h).  There is NO fallback: if the
+library is missing or a call fails this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfhb_sm100a.so")
+
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROWZERO = 1, 2, 4, 8
+EPI_STORE_PREACT, EPI_MUL_DGELU, EPI_OUT_F32, EPI_ATOMIC_ADD, EPI_SQDIFF = 16, 32, 64, 128, 256
+
+
+class FhbError(RuntimeError):
+    pass
+
+
+class Tensor3(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dim", C.c_int64 * 3), ("stride", C.c_int64 * 2)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", Tensor3), ("b", Tensor3),
+        ("a_major", C.c_int32), ("b_major", C.c_int32),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("num_ob", C.c_int32), ("ob_mod", C.c_int32), ("num_cb", C.c_int32),
+        ("a_lo_c0", C.c_int32), ("a_hi_c2", C.c_int32), ("a_lo_c2", C.c_int32), ("a_cb_c2", C.c_int32),
+        ("b_lo_c0", C.c_int32), ("b_hi_c2", C.c_int32), ("b_lo_c2", C.c_int32), ("b_cb_c2", C.c_int32),
+        ("d", C.c_void_p),
+        ("d_ld", C.c_int64), ("d_hi_stride", C.c_int64), ("d_lo_stride", C.c_int64),
+        ("flags", C.c_int32), ("split_k", C.c_int32),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("aux_in", C.c_void_p), ("aux_out", C.c_void_p),
+        ("row_valid", C.c_void_p),
+        ("loss_target", C.c_void_p), ("loss_acc", C.c_void_p),
+        ("loss_weight", C.c_float), ("grad_scale", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FhbError(
+                f"{LIB_PATH} not found: build it with `python -m fithubert_b200.build` "
+                "(there is no CPU / PyTorch fallback for the FitHuBERT hot path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.fhb_last_error.restype = C.c_char_p
+        _declare(_lib)
+    return _lib
+
+
+def _declare(l):
+    for name in EXPORTS:
+        fn = getattr(l, name)
+        if name not in ("fhb_last_error",):
+            fn.restype = C.c_int
+
+
+# every symbol include/fhb.h declares (tests/test_abi.py checks the .so exports all of them)
+EXPORTS = [
+    "fhb_last_error", "fhb_abi_version", "fhb_gemm",
+]
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise FhbError(f"{what} failed (rc={rc}): {lib().fhb_last_error().decode()}")
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> C.c_void_p | None:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def tensor3(t: torch.Tensor | None = None, *, data_ptr=None, dim=None, stride=None) -> Tensor3:
+    """Describe a bf16 operand.  With `t` given (1-3 D, last dim contiguous) the description is
+    derived; otherwise dim/stride (elements, dim[0] contiguous) are taken verbatim."""
+    r = Tensor3()
+    if t is not None and dim is None:
+        assert t.dtype == torch.bfloat16 and t.stride(-1) == 1, (t.dtype, t.stride())
+        if t.dim() == 2:
+            dim = (t.shape[1], t.shape[0], 1)
+            stride = (t.stride(0), t.stride(0) * t.shape[0])
+        else:
+            assert t.dim() == 3
+            dim = (t.shape[2], t.shape[1], t.shape[0])
+            stride = (t.stride(1), t.stride(0))
+        data_ptr = t.data_ptr()
+    elif t is not None:
+        data_ptr = t.data_ptr()
+    r.ptr = data_ptr
+    r.dim = (C.c_int64 * 3)(*dim)
+    r.stride = (C.c_int64 * 2)(*stride)
+    return r
