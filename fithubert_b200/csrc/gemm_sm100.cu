@@ -32,6 +32,7 @@ struct GemmParams {
   int kb_per_cb, kb_total, kb_per_split;
   int a_lo_c0, a_hi_c2, a_lo_c2, a_cb_c2;
   int b_lo_c0, b_hi_c2, b_lo_c2, b_cb_c2;
+  int a_c1_off, b_c1_off;
   long long d_ld, d_hi_stride, d_lo_stride;
   void* d;
   const float* bias;
@@ -124,7 +125,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < kBM / 64; ++i)
-              tma_load_3d(&tm_a, &full[stage], sa + i * (kBK * 128), t.m0 + i * 64 + t.ob_lo * p.a_lo_c0, kr,
+              tma_load_3d(&tm_a, &full[stage], sa + i * (kBK * 128), t.m0 + i * 64 + t.ob_lo * p.a_lo_c0, kr + p.a_c1_off,
                           a_c2 + cb * p.a_cb_c2);
           } else {
             tma_load_3d(&tm_a, &full[stage], sa, kb * kBK + t.ob_lo * p.a_lo_c0, t.m0, a_c2);
@@ -132,7 +133,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (B_MN) {
             const int atoms = (p.bn + 63) >> 6;
             for (int i = 0; i < atoms; ++i)
-              tma_load_3d(&tm_b, &full[stage], sb + i * (kBK * 128), t.n0 + i * 64 + t.ob_lo * p.b_lo_c0, kr,
+              tma_load_3d(&tm_b, &full[stage], sb + i * (kBK * 128), t.n0 + i * 64 + t.ob_lo * p.b_lo_c0, kr + p.b_c1_off,
                           b_c2 + cb * p.b_cb_c2);
           } else {
             tma_load_3d(&tm_b, &full[stage], sb, kb * kBK + t.ob_lo * p.b_lo_c0, t.n0, b_c2);
@@ -419,6 +420,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.total_tiles = base_tiles * p.split_k;
   p.a_lo_c0 = a->a_lo_c0; p.a_hi_c2 = a->a_hi_c2; p.a_lo_c2 = a->a_lo_c2; p.a_cb_c2 = a->a_cb_c2;
   p.b_lo_c0 = a->b_lo_c0; p.b_hi_c2 = a->b_hi_c2; p.b_lo_c2 = a->b_lo_c2; p.b_cb_c2 = a->b_cb_c2;
+  p.a_c1_off = a->a_c1_off; p.b_c1_off = a->b_c1_off;
   p.d_ld = a->d_ld; p.d_hi_stride = a->d_hi_stride; p.d_lo_stride = a->d_lo_stride;
   p.d = a->d;
   p.bias = a->bias;

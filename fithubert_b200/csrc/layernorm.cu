@@ -1,0 +1,195 @@
+// K3: warp-per-row LayerNorm forward / backward (bf16 activations, fp32 statistics).
+// Reference call sites: modules/model.py:446-447; modules/module.py:251,281,513,518,569,580.
+// HBM-bound: one read of x (and dy) and one write per element; rows are 960-1536 bytes, each lane
+// moves 16-byte vectors; gamma/beta stay in L1/L2.
+#include "fhb_common.cuh"
+
+namespace {
+
+constexpr int kMaxVec = 3;  // C <= 3*32*8 = 768
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = C >> 3;
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const __nv_bfloat16* xr = x + row * C;
+    float v[kMaxVec][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        load8(xr + vi * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+    const float mu = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mu;
+          q += d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0 && mean_out) {
+      mean_out[row] = mu;
+      rstd_out[row] = rs;
+    }
+    __nv_bfloat16* yr = y + row * C;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float o[8];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)),
+                     g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)),
+                     b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+        store8(yr + vi * 8, o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)),  dxhat = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (per-warp register partials -> smem -> atomics)
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
+  extern __shared__ float sred[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = C >> 3;
+  float pg[kMaxVec][8], pb[kMaxVec][8], g[kMaxVec][8];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      pg[i][j] = 0.f;
+      pb[i][j] = 0.f;
+      g[i][j] = (vi < nvec) ? __ldg(gamma + vi * 8 + j) : 0.f;
+    }
+  }
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kMaxVec][8], dyv[kMaxVec][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        load8(x + row * C + vi * 8, xh[i]);
+        load8(dy + row * C + vi * 8, dyv[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          const float dxh = dyv[i][j] * g[i][j];
+          s1 += dxh;
+          s2 += dxh * xh[i][j];
+          pg[i][j] += dyv[i][j] * xh[i][j];
+          pb[i][j] += dyv[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float o[8];
+        if (dres) load8(dres + row * C + vi * 8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = rs * (dyv[i][j] * g[i][j] - s1 - xh[i][j] * s2);
+          o[j] = dres ? o[j] + d : d;
+        }
+        store8(dx + row * C + vi * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sred[vi * 8 + j], pg[i][j]);
+        atomicAdd(&sred[C + vi * 8 + j], pb[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, sred[i]);
+    atomicAdd(dbeta + i, sred[C + i]);
+  }
+}
+
+int ln_grid(long long rows, int rows_per_warp_target) {
+  long long blocks = (rows + 8LL * rows_per_warp_target - 1) / (8LL * rows_per_warp_target);
+  const long long cap = (long long)fhb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                 float* rstd, int64_t rows, int32_t C, float eps, fhb_stream_t stream) {
+  FHB_ARG_CHECK(x && gamma && beta && y, "layernorm_fwd: null pointer");
+  FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_fwd: C=%d must be a multiple of 8, <= %d",
+                C, kMaxVec * 256);
+  FHB_ARG_CHECK((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
+  if (rows == 0) return 0;
+  layernorm_fwd_kernel<<<ln_grid(rows, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 int64_t rows, int32_t C, fhb_stream_t stream) {
+  FHB_ARG_CHECK(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+  FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_bwd: bad C=%d", C);
+  if (rows == 0) return 0;
+  layernorm_bwd_kernel<<<ln_grid(rows, 4), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
+      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,276 @@
+// HBM-bound helpers: fused distillation loss + gradient (K10), multi-tensor AdamW (K11), multi-tensor
+// weight preparation (fp32 master -> bf16 GEMM layouts), bias-gradient column sums, mask lengths.
+#include <math.h>
+
+#include "fhb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ K10 loss + gradient
+// grid (chunks, n_layers).  pred [L][B][Tp][D], tgt [L][B][Tt][D] (first Tp frames used).
+__global__ void __launch_bounds__(256)
+distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt,
+                    const float* __restrict__ weights, float* __restrict__ layer_loss, __nv_bfloat16* __restrict__ dpred,
+                    int B, int Tp, int Tt, int D, int loss_type, float grad_scale) {
+  const int l = blockIdx.y;
+  const float w = weights[l];
+  const long long vec_per_row = D >> 3;
+  const long long nvec = (long long)B * Tp * vec_per_row;
+  const float inv_count = 1.0f / ((float)B * (float)Tp * (float)D);
+  const float gs = grad_scale * w * inv_count * (loss_type == 0 ? 2.f : 1.f);
+  const __nv_bfloat16* pl = pred + (long long)l * B * Tp * D;
+  const __nv_bfloat16* tl = tgt + (long long)l * B * Tt * D;
+  __nv_bfloat16* dl = dpred ? dpred + (long long)l * B * Tp * D : nullptr;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec_per_row;
+    const int cv = i - row * vec_per_row;
+    const int b = row / Tp, t = row - (long long)b * Tp;
+    const uint4 pu = *reinterpret_cast<const uint4*>(pl + row * D + cv * 8);
+    const uint4 tu = __ldg(reinterpret_cast<const uint4*>(tl + ((long long)b * Tt + t) * D + cv * 8));
+    const uint32_t pa[4] = {pu.x, pu.y, pu.z, pu.w}, ta[4] = {tu.x, tu.y, tu.z, tu.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16(pa[j]), q = unpack_bf16(ta[j]);
+      const float d0 = p.x - q.x, d1 = p.y - q.y;
+      if (loss_type == 0) {
+        acc += d0 * d0 + d1 * d1;
+        out[j] = pack_bf16(gs * d0, gs * d1);
+      } else {
+        acc += fabsf(d0) + fabsf(d1);
+        out[j] = pack_bf16(d0 > 0.f ? gs : (d0 < 0.f ? -gs : 0.f), d1 > 0.f ? gs : (d1 < 0.f ? -gs : 0.f));
+      }
+    }
+    if (dl) *reinterpret_cast<uint4*>(dl + row * D + cv * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(layer_loss + l, s * w * inv_count);
+  }
+}
+
+// ------------------------------------------------------------------ K11 AdamW over a tensor table
+struct AdamScalars {
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale;
+  int mode;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const fhb_adamw_tensor* __restrict__ table, AdamScalars s) {
+  const fhb_adamw_tensor e = table[blockIdx.y];
+  if (e.g == nullptr) return;
+  const long long d1 = e.dim[1], d2 = e.dim[2];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (long long)gridDim.x * blockDim.x) {
+    const long long i2 = i % d2, r = i / d2;
+    const long long i1 = r % d1, i0 = r / d1;
+    const float g = e.g[i0 * e.gstride[0] + i1 * e.gstride[1] + i2 * e.gstride[2]] * s.grad_scale;
+    float p = e.p[i];
+    const float m = s.b1 * e.m[i] + (1.f - s.b1) * g;
+    const float v = s.b2 * e.v[i] + (1.f - s.b2) * g * g;
+    e.m[i] = m;
+    e.v[i] = v;
+    if (s.mode == 0) {
+      // s3prl Lamb(adam=True, correct_bias=True): eps on the un-corrected sqrt(v), decay inside the step
+      const float step = s.lr * s.bc2_sqrt / s.bc1;
+      p -= step * (m / (sqrtf(v) + s.eps) + s.wd * p);
+    } else {
+      // torch.optim.AdamW
+      p *= 1.f - s.lr * s.wd;
+      p -= (s.lr / s.bc1) * m / (sqrtf(v) / s.bc2_sqrt + s.eps);
+    }
+    e.p[i] = p;
+  }
+}
+
+// ------------------------------------------------------------------ weight preparation
+// dst (bf16 or fp32, contiguous [d0][d1][d2]) = src_fp32[i0*s0 + i1*s1 + i2*s2]
+__global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* __restrict__ table) {
+  const fhb_prep_tensor e = table[blockIdx.y];
+  const long long d1 = e.dim[1], d2 = e.dim[2];
+  const long long n = e.dim[0] * d1 * d2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long i2 = i % d2, r = i / d2;
+    const long long i1 = r % d1, i0 = r / d1;
+    const float v = e.src[i0 * e.sstride[0] + i1 * e.sstride[1] + i2 * e.sstride[2]];
+    if (e.dst_is_f32)
+      static_cast<float*>(e.dst)[i] = e.accumulate ? static_cast<float*>(e.dst)[i] + v : v;
+    else
+      static_cast<__nv_bfloat16*>(e.dst)[i] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long long ld, int rows_per_block,
+              float* __restrict__ out) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, rows);
+  for (int cv = threadIdx.x; cv < (C >> 3); cv += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long r = r0; r < r1; ++r) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ld + cv * 8));
+      const uint32_t a[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(a[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + cv * 8 + j, acc[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y,
+                long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 ua = reinterpret_cast<const uint4*>(a)[i], ub = reinterpret_cast<const uint4*>(b)[i];
+    const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, bb[4] = {ub.x, ub.y, ub.z, ub.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(bb[j]);
+      o[j] = pack_bf16(p.x + q.x, p.y + q.y);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[b][i] = dy[b][i] * gelu'(u[b][i]) over B segments of n elements with independent batch strides
+__global__ void __launch_bounds__(256)
+mul_dgelu_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, const __nv_bfloat16* __restrict__ u, long long u_bs,
+                 __nv_bfloat16* __restrict__ out, long long out_bs, long long nvec) {
+  const int b = blockIdx.y;
+  const uint4* d4 = reinterpret_cast<const uint4*>(dy + b * dy_bs);
+  const uint4* u4 = reinterpret_cast<const uint4*>(u + b * u_bs);
+  uint4* o4 = reinterpret_cast<uint4*>(out + b * out_bs);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = d4[i], c = u4[i];
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, cc[4] = {c.x, c.y, c.z, c.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(cc[j]);
+      o[j] = pack_bf16(p.x * gelu_erf_grad(q.x), p.y * gelu_erf_grad(q.y));
+    }
+    o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// lengths[b] = number of zero bytes in mask[b][0..L)   (mask: 1 = padding)
+__global__ void __launch_bounds__(256) mask_lengths_kernel(const uint8_t* __restrict__ mask, long long L, int* __restrict__ lengths) {
+  const uint8_t* row = mask + (long long)blockIdx.x * L;
+  int cnt = 0;
+  for (long long i = threadIdx.x; i < L; i += blockDim.x) cnt += row[i] ? 0 : 1;
+  __shared__ int red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    lengths[blockIdx.x] = s;
+  }
+}
+
+int grid_x(long long work_items, int cap_mult) {
+  long long b = (work_items + 255) / 256;
+  const long long cap = (long long)fhb_num_sms() * cap_mult;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+extern "C" int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const float* weights, float* layer_loss,
+                                        void* dpred, int32_t n_layers, int32_t B, int32_t Tp, int32_t Tt, int32_t D,
+                                        int32_t loss_type, float grad_scale, fhb_stream_t stream) {
+  FHB_ARG_CHECK(pred && tgt && weights && layer_loss, "distill_loss: null pointer");
+  FHB_ARG_CHECK(n_layers > 0 && B > 0 && Tp > 0 && Tt >= Tp && D > 0 && D % 8 == 0,
+                "distill_loss: bad shape (layers=%d B=%d Tp=%d Tt=%d D=%d)", n_layers, B, Tp, Tt, D);
+  FHB_ARG_CHECK(loss_type == 0 || loss_type == 1, "rec_loss_type must be one of 'l1', 'mse'.");
+  const long long nvec = (long long)B * Tp * (D / 8);
+  int gx = grid_x(nvec, 8);
+  gx = (gx + n_layers - 1) / n_layers;
+  if (gx < 1) gx = 1;
+  distill_loss_kernel<<<dim3(gx, n_layers), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(tgt), weights, layer_loss,
+      static_cast<__nv_bfloat16*>(dpred), B, Tp, Tt, D, loss_type, grad_scale);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_adamw_multi(const fhb_adamw_tensor* table_dev, int32_t n_tensors, int64_t max_n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int32_t step, int32_t mode,
+                               float grad_scale, fhb_stream_t stream) {
+  FHB_ARG_CHECK(table_dev && n_tensors > 0 && max_n > 0, "adamw: empty table");
+  FHB_ARG_CHECK(step >= 1, "adamw: step is 1-based");
+  FHB_ARG_CHECK(mode == 0 || mode == 1, "adamw: mode must be 0 (s3prl) or 1 (torch)");
+  AdamScalars s;
+  s.lr = lr; s.b1 = beta1; s.b2 = beta2; s.eps = eps; s.wd = weight_decay; s.grad_scale = grad_scale; s.mode = mode;
+  s.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  s.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  int gx = grid_x(max_n, 2);
+  if (gx > 64) gx = 64;
+  adamw_multi_kernel<<<dim3(gx, n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, s);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_prep_multi(const fhb_prep_tensor* table_dev, int32_t n_tensors, int64_t max_n, fhb_stream_t stream) {
+  FHB_ARG_CHECK(table_dev && n_tensors > 0 && max_n > 0, "prep_multi: empty table");
+  int gx = grid_x(max_n, 2);
+  if (gx > 64) gx = 64;
+  prep_multi_kernel<<<dim3(gx, n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, float* out, fhb_stream_t stream) {
+  FHB_ARG_CHECK(x && out && C % 8 == 0 && ld % 8 == 0, "colsum: bad arguments");
+  if (rows == 0) return 0;
+  const int rpb = 64;
+  colsum_kernel<<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), rows, C, ld, rpb, out);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t stream) {
+  FHB_ARG_CHECK(a && b && y && n % 8 == 0, "add_bf16: n must be a multiple of 8");
+  if (n == 0) return 0;
+  add_bf16_kernel<<<grid_x(n / 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), n / 8);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_bstride, void* out,
+                             int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream) {
+  FHB_ARG_CHECK(dy && u && out && B > 0, "mul_dgelu: null pointer");
+  FHB_ARG_CHECK(n % 8 == 0 && dy_bstride % 8 == 0 && u_bstride % 8 == 0 && out_bstride % 8 == 0,
+                "mul_dgelu: sizes and strides must be multiples of 8 elements");
+  if (n == 0) return 0;
+  int gx = grid_x(n / 8, 8);
+  gx = (gx + B - 1) / B;
+  mul_dgelu_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), dy_bstride, static_cast<const __nv_bfloat16*>(u), u_bstride,
+      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_mask_lengths(const uint8_t* mask, int32_t B, int64_t L, int32_t* lengths, fhb_stream_t stream) {
+  FHB_ARG_CHECK(mask && lengths && B > 0 && L > 0, "mask_lengths: bad arguments");
+  mask_lengths_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, L, lengths);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}

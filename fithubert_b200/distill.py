@@ -1,0 +1,204 @@
+"""W2V2Distil: the reference's distillation module (train.py:26-446) without Lightning.
+
+Same surface for the hot path: forward(x, padding_mask) -> (student_results, teacher_results),
+calculate_loss(student_results, teacher_results, labels=None) -> (total_loss, losses),
+training_step(batch, batch_idx) -> loss, configure_optimizers().  training_step is the FUSED path:
+teacher forward -> student forward -> loss+gradient kernel -> explicit backward, no autograd.
+CTC / attention-map / value-relation / CNN losses are out of scope: requesting them
+raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+from . import kernels as K
+from .config import CustomStudentModelConfig
+from .model import CustomStudentModel, TeacherModel, TeacherWrapper, conv_out_lengths, freeze_model, _lengths_from_mask
+from .optim import FusedAdamW, GradAllReduce
+
+bf16 = torch.bfloat16
+
+
+def load_model_and_config(teacher_model: str, device=None):
+    """Reference utils/utils.py:102-149 loads a fairseq checkpoint.  fairseq pickles cannot be read
+    without fairseq (a 'next' row); here the name selects the architecture and weights are
+    random-init (BASELINE.json: 'random-init teacher'), or a plain state-dict file is loaded if it
+    exists and is one."""
+    kind = "wav2vec2" if ("wav2vec" in teacher_model or "w2v" in teacher_model) else "hubert"
+    model = TeacherModel(kind=kind)
+    try:
+        state = torch.load(teacher_model, map_location="cpu")
+        sd = state.get("model", state)
+        model.load_state_dict({k: v for k, v in sd.items() if k in model.state_dict()}, strict=False)
+    except (FileNotFoundError, OSError, AttributeError, RuntimeError, ModuleNotFoundError, ImportError):
+        pass
+    if device is not None:
+        model = model.to(device)
+    return TeacherWrapper(model), None, True
+
+
+class W2V2Distil(nn.Module):
+    def __init__(self, cfg: dict, teacher_model: Optional[TeacherWrapper] = None, device=None):
+        super().__init__()
+        self.yaml_cfg = cfg
+        self.train_cfg = cfg["train"]
+        dev = torch.device(device if device is not None else "cuda")
+        if teacher_model is None:
+            teacher_model, _, self.task_agnostic = load_model_and_config(cfg["teacher"]["teacher_model"], dev)
+        else:
+            self.task_agnostic = True
+        self.teacher_model = teacher_model.to(dev)
+        freeze_model(self.teacher_model)
+        self.model_cfg = cfg["distiller"]
+        student_config = CustomStudentModelConfig(**self.model_cfg)
+        student_config._teacher_task_agnostic = self.task_agnostic
+        student_config._cnn_weight = self.train_cfg["cnn_loss_weight"]
+        self.student_model = CustomStudentModel(cfg=student_config, teacher_model=self.teacher_model).to(dev)
+        t = self.train_cfg
+        self.cnn_loss_weight, self.rec_loss_weight = t["cnn_loss_weight"], t["rec_loss_weight"]
+        self.rec_loss_type, self.sim_loss_weight = t["rec_loss_type"], t["sim_loss_weight"]
+        self.attn_loss_weight, self.v_rel_loss_weight = t["attn_loss_weight"], t["v_rel_loss_weight"]
+        self.random_layer_weight = t["random_layer_weight"]
+        for name, w in (("cnn_loss_weight", self.cnn_loss_weight), ("sim_loss_weight", self.sim_loss_weight),
+                        ("attn_loss_weight", self.attn_loss_weight), ("v_rel_loss_weight", self.v_rel_loss_weight)):
+            if w:
+                raise NotImplementedError(f"{name} > 0 is outside the B200 hot path (SURVEY 2.1 / 8f)")
+        if self.rec_loss_type not in ("mse", "l1"):
+            raise NotImplementedError("rec_loss_type must be one of 'l1', 'mse'.")
+        if t.get("delete_projections"):
+            raise NotImplementedError("delete_projections=True leaves nothing to distil on this path")
+        self.num_encoders = self.model_cfg["encoder_layers"]
+        n = self.num_encoders
+        if t["distil_random_layer"] > 0:
+            # train.py:88-91: a random subset of the lower layers, each weighted random_layer_weight
+            self.all_enc = range(n - 1)
+            self.rand_l = random.sample(self.all_enc, t["distil_random_layer"])
+            w = [0.0] * n
+            for l in self.rand_l:
+                w[l] = float(self.random_layer_weight)
+            w[n - 1] = 1.0
+            self.mean_over_layers = False
+        else:
+            assert t["random_layer_weight"] == 0
+            # train.py:294-297: plain mean over the pred_layer_id layers
+            ids = self.student_model.pred_layer_id
+            w = [0.0] * n
+            for l in ids:
+                w[l] = 1.0 / len(ids)
+            self.rand_l = []
+            self.mean_over_layers = True
+        self.layer_weights_host = w
+        self.layer_weights = torch.tensor(w, dtype=torch.float32, device=dev)
+        self.batch_size = t["batch_size"]
+        self.num_gpus = t["gpus"] if not isinstance(t["gpus"], list) else len(t["gpus"])
+        self.accumulate = int(t.get("accumulate_grad_batches", 1))
+        self.optimizer: Optional[FusedAdamW] = None
+        self.reducer: Optional[GradAllReduce] = None
+        self._micro = 0
+        self._tgt_buf = None
+
+    # ------------------------------------------------------------------ reference-style API (autograd)
+    def forward(self, x, padding_mask=None):
+        self.teacher_model.eval()
+        teacher_results = self.teacher_model.extract_features(source=x, padding_mask=padding_mask)
+        student_results = self.student_model(source=x, padding_mask=padding_mask)
+        return student_results, teacher_results
+
+    def calculate_loss(self, student_results, teacher_results, labels=None):
+        from .autograd import _DistillLossFn
+        if labels is not None or not self.task_agnostic:
+            raise NotImplementedError("task-specific (CTC) teacher path is dead code in the reference and not built")
+        preds = torch.stack(student_results["projections"], 0) if not isinstance(
+            student_results["projections"], torch.Tensor) else student_results["projections"]
+        base = student_results["projections"][0]
+        if isinstance(student_results["projections"], list) and base._base is not None and \
+                base._base.shape[0] == len(student_results["projections"]):
+            preds = base._base  # the engine's stacked [n, B, T', D] buffer: no copy
+        total, per_layer = _DistillLossFn.apply(preds, teacher_results["_stacked"], self.layer_weights,
+                                                0 if self.rec_loss_type == "mse" else 1)
+        losses = self._loss_dict(per_layer)
+        return self.rec_loss_weight * total, losses
+
+    def _loss_dict(self, per_layer: torch.Tensor) -> Dict[str, torch.Tensor]:
+        losses = {}
+        n = self.num_encoders
+        if self.train_cfg["distil_random_layer"] > 0:
+            for i, l in enumerate(self.rand_l):
+                losses[f"rand_l{i}"] = per_layer[l]
+            losses[f"l{n - 1}"] = per_layer[n - 1]
+        else:
+            for pred_id in self.student_model.pred_layer_id:
+                losses[f"layer{pred_id}"] = per_layer[pred_id] * len(self.student_model.pred_layer_id)
+        return losses
+
+    # ------------------------------------------------------------------ fused training path
+    def configure_optimizers(self, total_steps: int = 0):
+        o = self.yaml_cfg["optimizer"]
+        lr = float(o["lr"]) if not isinstance(o["lr"], str) else float(eval(o["lr"], {"__builtins__": {}}))
+        self.optimizer = FusedAdamW(self.student_model, lr=lr, betas=tuple(o.get("betas", (0.9, 0.999))),
+                                    eps=float(o.get("eps", 1e-8)), weight_decay=float(o.get("weight_decay", 0.0)),
+                                    total_steps=total_steps, warmup_proportion=float(o.get("warmup_proportion", 0.05)))
+        self.reducer = GradAllReduce()
+        return {"optimizer": self.optimizer}
+
+    def fused_forward_backward(self, x, padding_mask=None, lengths: Optional[List[int]] = None, grad_scale=1.0):
+        """teacher fwd + student fwd + loss + student bwd for one micro-batch.  Gradients accumulate in the
+        flat buffer.  Returns (total_loss [1] fp32 tensor on device, per-layer losses [n] fp32)."""
+        sm, tm = self.student_model, self.teacher_model.model
+        dev = sm.post_extract_proj.weight.device
+        x = x.to(dev, non_blocking=True).float().contiguous()
+        if lengths is None:
+            lengths = _lengths_from_mask(padding_mask)
+        elif all(n == x.shape[1] for n in lengths):
+            lengths = None
+        Ld = x.shape[1]
+        T = E.conv_frames(Ld, tm._conv_layers)[-1]
+        # teacher mask (M3 for HuBERT: applied whenever a mask exists; M1 for wav2vec2)
+        if padding_mask is None and lengths is None:
+            t_valid = None
+        elif tm.kind == "hubert":
+            from .model import hubert_mask_lengths
+            t_valid = hubert_mask_lengths(lengths if lengths is not None else [Ld] * x.shape[0], Ld, T)
+        else:
+            t_valid = None if lengths is None else conv_out_lengths(lengths, tm._conv_layers)
+        s_valid = None if lengths is None else conv_out_lengths(lengths, sm._conv_layers)
+        n, B, D = self.num_encoders, x.shape[0], sm._geom.d_out
+        Pt, Wt = tm.engine_state()
+        if self._tgt_buf is None or self._tgt_buf.shape[1:3] != (B, T):
+            self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=bf16)
+        tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf)
+        P, W, G = sm.engine_state(True)
+        c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all")
+        layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
+        # gradient written in place over the projections (they are not needed again)
+        K.distill_loss(c.preds, tgt, self.layer_weights, layer_loss, c.preds, n, B, c.Tq, T, D,
+                       0 if self.rec_loss_type == "mse" else 1, grad_scale * self.rec_loss_weight)
+        E.student_backward(P, W, sm._geom, G, c, c.preds)
+        return layer_loss
+
+    def training_step(self, batch, batch_idx=0):
+        """One micro-batch (reference train.py:158-170); every `accumulate_grad_batches`-th call also runs
+        the gradient all-reduce and the fused AdamW step (what Lightning's automatic optimisation does)."""
+        if self.optimizer is None:
+            self.configure_optimizers()
+        if self._micro == 0:
+            self.optimizer.zero_grad()
+        layer_loss = self.fused_forward_backward(batch["x"], batch.get("padding_mask"), batch.get("lengths"),
+                                                 grad_scale=1.0 / self.accumulate)
+        self._micro += 1
+        if self._micro == self.accumulate:
+            self._micro = 0
+            self.optimizer_step()
+        self.last_layer_losses = layer_loss
+        return layer_loss.sum() * self.rec_loss_weight
+
+    def optimizer_step(self):
+        _, _, G = self.student_model.engine_state(True)
+        self.reducer.reduce_all(G.flat)
+        self.reducer.wait()
+        self.optimizer.step(grad_scale=1.0 / self.reducer.world)

@@ -1,0 +1,626 @@
+"""Execution engine: orchestrates the hand-written sm_100a kernels (kernels.py -> libfhb_sm100a.so)
+into the teacher forward, the student forward and the student backward.
+
+Layout decisions:
+  * activations bf16 channel-last [B, T, C]; every contraction is a tcgen05 GEMM over a (possibly
+    overlapping-row) strided view - no im2col, no permute copies;
+  * fp32 master parameters live in the nn.Module; bf16 GEMM-layout shadows are re-derived by ONE
+    multi-tensor kernel whenever the parameters change;
+  * parameter gradients accumulate in ONE flat fp32 buffer, in the layout the wgrad GEMM produces
+    (the fused AdamW kernel reads them through a 3-D stride; the buffer is what NCCL all-reduces).
+There is no autograd inside: backward is written out explicitly (SURVEY App. F backward inventory).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import kernels as K
+from . import lib as L
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def conv_frames(n: int, layers) -> List[int]:
+    out = []
+    for (_, k, s) in layers:
+        n = (n - k) // s + 1
+        out.append(n)
+    return out
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Geometry:
+    def __init__(self, conv_layers, E, F, H, G, kpos, n_layers, d_out=0, student=True):
+        self.conv_layers = [tuple(c) for c in conv_layers]
+        self.E, self.F, self.H, self.G, self.kpos, self.n_layers = E, F, H, G, kpos, n_layers
+        self.d = E // H
+        self.cg = E // G
+        self.cp = round_up(self.cg, 16)
+        self.d_out = d_out
+        self.student = student
+        self.c_feat = self.conv_layers[-1][0]
+
+
+# =============================================================================================
+# bf16 / fp32 shadows of the master parameters
+# =============================================================================================
+class WeightSet:
+    """GEMM-layout shadows for one model on one device."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], g: Geometry, train: bool):
+        self.params, self.g, self.train = params, g, train
+        self.device = next(iter(params.values())).device
+        self._sig = None
+        self._table = None
+        self.views: Dict[str, torch.Tensor] = {}
+        self._plan()
+
+    # ---- plan: (shadow name, dtype, dst dims3, [(param, src_off, sstride3, dst_off_elems)])
+    def _plan(self):
+        g = self.g
+        spec = []
+
+        def add(name, dtype, dims, parts):
+            spec.append((name, dtype, tuple(dims), parts))
+
+        cin = self.g.conv_layers[0][0]
+        for i, (c, k, s) in enumerate(g.conv_layers):
+            if i == 0:
+                continue
+            pn = f"feature_extractor.conv_layers.{i}.0.weight"
+            add(f"conv{i}.w", bf16, (c, k, cin), [(pn, 0, (cin * k, 1, k), 0)])
+            if self.train and (k, s) == (3, 2):
+                add(f"conv{i}.wd_even", bf16, (cin, 2, c), [(pn, 2, (k, -2, cin * k), 0)])
+                add(f"conv{i}.wd_odd", bf16, (cin, 1, c), [(pn, 1, (k, 0, cin * k), 0)])
+            cin = c
+        E, F = g.E, g.F
+
+        def lin(name, pn, n, kd):
+            add(name, bf16, (n, 1, kd), [(pn, 0, (kd, 0, 1), 0)])
+
+        lin("pp.w", "post_extract_proj.weight", E, g.c_feat)
+        off = 0
+        if g.student:
+            add("tr.w", bf16, (E, 2, E), [("encoder.layers.0.weight", 0, (2 * E, 1, 2), 0)])
+            off = 1
+        for l in range(g.n_layers):
+            p = f"encoder.layers.{l + off}."
+            add(f"l{l}.wqkv", bf16, (3 * E, 1, E),
+                [(p + f"self_attn.{nm}_proj.weight", 0, (E, 0, 1), j * E * E) for j, nm in enumerate("qkv")])
+            add(f"l{l}.bqkv", f32, (3 * E, 1, 1),
+                [(p + f"self_attn.{nm}_proj.bias", 0, (1, 0, 0), j * E) for j, nm in enumerate("qkv")])
+            lin(f"l{l}.wo", p + "self_attn.out_proj.weight", E, E)
+            lin(f"l{l}.w1", p + "fc1.weight", F, E)
+            lin(f"l{l}.w2", p + "fc2.weight", E, F)
+        if g.student:
+            for i in range(g.n_layers):
+                p = f"proj_head.{i}."
+                if p + "upsampler.weight" not in self.params:
+                    if i == g.n_layers - 1 and "final_proj.upsampler.weight" in self.params:
+                        p = "final_proj."
+                    else:
+                        continue
+                add(f"h{i}.wup", bf16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
+                add(f"h{i}.bup", f32, (2, E, 1), [(p + "upsampler.bias", 0, (0, 1, 0), 0)])
+                lin(f"h{i}.wlin", p + "lin_proj.weight", g.d_out, E)
+        self.spec = spec
+        nb = sum(math.prod(d) for (_, t, d, _) in spec if t == bf16)
+        nf = sum(math.prod(d) for (_, t, d, _) in spec if t == f32)
+        pc = g.G * g.cp * g.kpos * g.cp
+        self.buf16 = torch.empty(round_up(nb, 64) + 64 * len(spec) + 2 * pc + 128, device=self.device, dtype=bf16)
+        self.buf32 = torch.empty(nf + 8 * len(spec) + g.kpos + 64, device=self.device, dtype=f32)
+        o16 = o32 = 0
+        for (name, t, dims, _) in spec:
+            n = math.prod(dims)
+            if t == bf16:
+                self.views[name] = self.buf16[o16:o16 + n]
+                o16 += round_up(n, 64)  # keep every shadow 128-byte aligned (TMA base alignment)
+            else:
+                self.views[name] = self.buf32[o32:o32 + n]
+                o32 += round_up(n, 8)
+        self.views["pc.w"] = self.buf16[o16:o16 + pc]
+        o16 += round_up(pc, 64)
+        self.views["pc.wt"] = self.buf16[o16:o16 + pc]
+        self.views["pc.inv"] = self.buf32[o32:o32 + g.kpos]
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+    def signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.params.values())
+
+    def mark_stale(self):
+        self._sig = None
+
+    def ensure_fresh(self):
+        sig = self.signature()
+        if sig == self._sig:
+            return
+        ptrs = tuple(s[0] for s in sig)
+        if self._table is None or ptrs != self._ptrs:
+            entries = []
+            self._max_n = 1
+            for (name, t, dims, parts) in self.spec:
+                per = math.prod(dims) // len(parts)
+                pd = (dims[0] // len(parts), dims[1], dims[2])
+                for (pn, soff, sstr, doff) in parts:
+                    src = self.params[pn]
+                    assert src.dtype == f32 and src.is_contiguous(), pn
+                    e = L.PrepTensor()
+                    e.src = src.data_ptr() + 4 * soff
+                    e.dst = self.views[name].data_ptr() + doff * self.views[name].element_size()
+                    e.dim = (L.C.c_int64 * 3)(*pd)
+                    e.sstride = (L.C.c_int64 * 3)(*sstr)
+                    e.dst_is_f32 = int(t == f32)
+                    e.accumulate = 0
+                    entries.append(e)
+                    self._max_n = max(self._max_n, per)
+            self._table = L.table_to_device(entries, self.device)
+            self._n_entries = len(entries)
+            self._ptrs = ptrs
+        K.prep_multi(self._table, self._n_entries, self._max_n)
+        g = self.g
+        v, gn = self.params["encoder.pos_conv.0.weight_v"], self.params["encoder.pos_conv.0.weight_g"]
+        K.posconv_wn_prep(v, gn, self.views["pc.w"], self.views["pc.inv"], g.E, g.G, g.kpos, g.cp, 0)
+        if self.train:
+            K.posconv_wn_prep(v, gn, self.views["pc.wt"], None, g.E, g.G, g.kpos, g.cp, 1)
+        self._sig = sig
+
+
+# =============================================================================================
+# flat gradient buffer (student)
+# =============================================================================================
+class GradStore:
+    """One flat fp32 buffer holding every parameter gradient in wgrad-GEMM layout.
+    entry: name -> (offset, numel, param dims3, gstride3)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], g: Geometry):
+        self.params, self.g = params, g
+        self.device = next(iter(params.values())).device
+        E = g.E
+        order: List[Tuple[str, Tuple[int, int, int], Tuple[int, int, int]]] = []
+
+        def plain(pn):
+            n = params[pn].numel()
+            order.append((pn, (1, 1, n), (0, 0, 1)))
+
+        cin = g.conv_layers[0][0]
+        for pn in ("feature_extractor.conv_layers.0.0.weight", "feature_extractor.conv_layers.0.2.weight",
+                   "feature_extractor.conv_layers.0.2.bias"):
+            plain(pn)
+        for i, (c, k, s) in enumerate(g.conv_layers):
+            if i == 0:
+                continue
+            # grad stored as dW2[co][j][ci]; param element (co, ci, j)
+            order.append((f"feature_extractor.conv_layers.{i}.0.weight", (c, cin, k), (k * cin, 1, cin)))
+            cin = c
+        for pn in ("layer_norm.weight", "layer_norm.bias", "post_extract_proj.weight", "post_extract_proj.bias",
+                   "encoder.pos_conv.0.bias", "encoder.pos_conv.0.weight_g", "encoder.pos_conv.0.weight_v",
+                   "encoder.layer_norm.weight", "encoder.layer_norm.bias"):
+            plain(pn)
+        order.append(("encoder.layers.0.weight", (E, E, 2), (2 * E, 1, E)))
+        plain("encoder.layers.0.bias")
+        for l in range(1, g.n_layers + 1):
+            p = f"encoder.layers.{l}."
+            for nm in "qkv":
+                plain(p + f"self_attn.{nm}_proj.weight")
+            for nm in "qkv":
+                plain(p + f"self_attn.{nm}_proj.bias")
+            for pn in ("self_attn.out_proj.weight", "self_attn.out_proj.bias", "self_attn_layer_norm.weight",
+                       "self_attn_layer_norm.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias",
+                       "final_layer_norm.weight", "final_layer_norm.bias"):
+                plain(p + pn)
+        for i in range(g.n_layers):
+            p = f"proj_head.{i}."
+            if p + "upsampler.weight" not in params:
+                continue
+            # grad stored as dWup[(j, co)][ci]; param element (ci, co, j)
+            order.append((p + "upsampler.weight", (E, E, 2), (1, E, E * E)))
+            plain(p + "upsampler.bias")
+            plain(p + "lin_proj.weight")
+            plain(p + "lin_proj.bias")
+        self.entries = {}
+        off = 0
+        for (pn, dims, gs) in order:
+            n = params[pn].numel()
+            assert math.prod(dims) == n, pn
+            self.entries[pn] = (off, n, dims, gs)
+            off += round_up(n, 4)  # 16-byte alignment for vector / TMA-free fp32 stores
+        self.numel = off
+        self.flat = torch.zeros(off, device=self.device, dtype=f32)
+        self.no_grad = [pn for pn in params if pn not in self.entries]  # the dead `upsampler.*`
+
+    def view(self, pn) -> torch.Tensor:
+        off, n, _, _ = self.entries[pn]
+        return self.flat[off:off + n]
+
+    def span(self, first, last) -> torch.Tensor:
+        a = self.entries[first][0]
+        b = self.entries[last][0] + self.entries[last][1]
+        return self.flat[a:b]
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def export(self, accumulate=False) -> Dict[str, torch.Tensor]:
+        """Gradients in PARAMETER layout (what autograd would have produced)."""
+        out = {}
+        entries = []
+        mx = 1
+        for pn, (off, n, dims, gs) in self.entries.items():
+            dst = torch.empty_like(self.params[pn]) if not accumulate else self.params[pn].grad
+            out[pn] = dst
+            e = L.PrepTensor()
+            e.src = self.flat.data_ptr() + 4 * off
+            e.dst = dst.data_ptr()
+            e.dim = (L.C.c_int64 * 3)(*dims)
+            e.sstride = (L.C.c_int64 * 3)(*gs)
+            e.dst_is_f32, e.accumulate = 1, int(accumulate)
+            entries.append(e)
+            mx = max(mx, n)
+        table = L.table_to_device(entries, self.device)
+        K.prep_multi(table, len(entries), mx)
+        self._keepalive = table
+        return out
+
+
+# =============================================================================================
+# forward building blocks
+# =============================================================================================
+def _valid_tensor(valid: Optional[List[int]], device) -> Optional[torch.Tensor]:
+    if valid is None:
+        return None
+    return torch.tensor(valid, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool):
+    """Conv feature extractor (reference modules/module.py:94-102).  Returns ctx with the last
+    activation [B, T, C] (contiguous view) and, when `save`, everything backward needs.
+    When saving for backward, the output of every k=3,s=2 layer is stored as [B, T_i + 2, C_i] with one
+    halo row on each side: its gradient buffer shares that layout and the zero halo rows turn the k=3,s=2
+    dgrad into two plain overlapped-view GEMMs (even / odd input frames)."""
+    B, Ld = wave.shape
+    dev = wave.device
+    frames = conv_frames(Ld, g.conv_layers)
+    C0 = g.conv_layers[0][0]
+    T0 = frames[0]
+    halos = [1 if (save and i > 0 and (k, s) == (3, 2)) else 0 for i, (_, k, s) in enumerate(g.conv_layers)]
+    c = SimpleNamespace(B=B, L=Ld, frames=frames, halos=halos, wave=wave)
+    c.stat = torch.empty(B, 65, device=dev, dtype=torch.float64)
+    c.mean0 = torch.empty(B, C0, device=dev, dtype=f32)
+    c.rstd0 = torch.empty(B, C0, device=dev, dtype=f32)
+    y = torch.empty(B, T0, C0, device=dev, dtype=bf16)
+    K.conv0_fwd(wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
+                P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat, c.mean0, c.rstd0, y)
+    c.y = [y]
+    c.u = [None]
+    # (buffer, rows allocated per sample, first data row)
+    x_buf, x_rows, x_row0, cin, T = y, T0, 0, C0, T0
+    for i, (co, k, s) in enumerate(g.conv_layers):
+        if i == 0:
+            continue
+        To = frames[i]
+        halo = halos[i]
+        rows = To + 2 * halo
+        yb = torch.empty(B, rows, co, device=dev, dtype=bf16)
+        ub = torch.empty(B, rows, co, device=dev, dtype=bf16) if save else None
+        a3 = L.tensor3(data_ptr=x_buf.data_ptr() + 2 * x_row0 * cin, dim=(k * cin, To, B), stride=(s * cin, x_rows * cin))
+        b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
+        K.gemm_raw(a3, b3, yb, To, co, k * cin, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=co, d_hi_stride=rows * co,
+                   d_offset_elems=halo * co, flags=L.EPI_GELU | (L.EPI_STORE_PREACT if save else 0), aux_out=ub)
+        c.y.append(yb)
+        c.u.append(ub)
+        x_buf, x_rows, x_row0, cin, T = yb, rows, halo, co, To
+    c.T = T
+    assert halos[-1] == 0, "the last conv layer must not be k=3,s=2 (its output feeds a dense LayerNorm)"
+    c.out = x_buf
+    return c
+
+
+def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Tensor], save: bool):
+    """conv stack -> LayerNorm -> post_extract_proj -> (mask, pos-conv, +x, LayerNorm)
+    = reference modules/model.py:428-489 + modules/module.py:273-281."""
+    c = conv_stack_fwd(P, W, g, wave, save)
+    B, T, dev = c.B, c.T, wave.device
+    E, Cf = g.E, g.c_feat
+    feat = c.out
+    f_ln = torch.empty(B, T, Cf, device=dev, dtype=bf16)
+    c.mean_f = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    c.rstd_f = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    K.layernorm_fwd(feat, P["layer_norm.weight"], P["layer_norm.bias"], f_ln, c.mean_f, c.rstd_f)
+    c.f_ln = f_ln
+    feats = K.linear(f_ln.view(B * T, Cf), W["pp.w"].view(E, Cf), P["post_extract_proj.bias"])
+    c.feats = feats  # [B*T, E], padded frames NOT zeroed (reference `features_to_distill`)
+    # positional conv as one batched GEMM per (sample, group)
+    G, cp, kp = g.G, g.cp, g.kpos
+    Tp = T + kp
+    xg = torch.empty(B * G, Tp, cp, device=dev, dtype=bf16)
+    K.posconv_pack(feats, valid_t, xg, B, T, E, G, cp, kp // 2, Tp)
+    conv = torch.empty(B * T, G * cp, device=dev, dtype=bf16)
+    a3 = L.tensor3(data_ptr=xg.data_ptr(), dim=(kp * cp, T, B * G), stride=(cp, Tp * cp))
+    b3 = L.tensor3(data_ptr=W["pc.w"].data_ptr(), dim=(kp * cp, cp, G), stride=(kp * cp, cp * kp * cp))
+    K.gemm_raw(a3, b3, conv, T, cp, kp * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
+               d_ld=G * cp, d_hi_stride=T * G * cp, d_lo_stride=cp)
+    c.xg, c.conv = (xg, conv) if save else (None, conv)
+    enc = torch.empty(B * T, E, device=dev, dtype=bf16)
+    c.h = torch.empty(B * T, E, device=dev, dtype=bf16) if save else None
+    c.mean_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    c.rstd_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    K.posconv_finish_fwd(feats, valid_t, conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"],
+                         P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp)
+    c.enc_in = enc
+    return c
+
+
+def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, T, save: bool, want_lr: bool,
+              out: Optional[torch.Tensor] = None):
+    """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E]."""
+    E, F, H, d = g.E, g.F, g.H, g.d
+    dev = x.device
+    s = SimpleNamespace(x=x)
+    qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
+    attn = torch.empty(B * T, E, device=dev, dtype=bf16)
+    lse = torch.empty(B, H, T, device=dev, dtype=f32) if save else None
+    K.attn_fwd(qkv, valid_t, attn, lse, B, T, H, d, d ** -0.5)
+    y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"], residual=x)
+    x1 = torch.empty_like(y1)
+    s.mean1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    s.rstd1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    K.layernorm_fwd(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1,
+                    s.mean1, s.rstd1)
+    u = torch.empty(B * T, F, device=dev, dtype=bf16) if save else None
+    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, preact_out=u)
+    lr = torch.empty(B * T, E, device=dev, dtype=bf16) if want_lr else None
+    y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr)
+    x2 = out if out is not None else torch.empty_like(y2)
+    s.mean2 = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    s.rstd2 = torch.empty(B * T, device=dev, dtype=f32) if save else None
+    K.layernorm_fwd(y2, P[prefix + "final_layer_norm.weight"], P[prefix + "final_layer_norm.bias"], x2, s.mean2, s.rstd2)
+    if save:
+        s.qkv, s.attn, s.lse, s.y1, s.x1, s.u, s.h, s.y2 = qkv, attn, lse, y1, x1, u, h, y2
+    s.out, s.lr = x2, lr
+    return s
+
+
+# =============================================================================================
+# teacher
+# =============================================================================================
+def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None):
+    """Frozen teacher forward (reference utils/utils.py:80-99 around fairseq HubertModel /
+    Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] bf16, features [B, T, E])."""
+    W.ensure_fresh()
+    valid_t = _valid_tensor(valid, wave.device)
+    c = frontend_fwd(P, W, g, wave, valid_t, save=False)
+    B, T, E = c.B, c.T, g.E
+    if out_buf is None:
+        out_buf = torch.empty(g.n_layers, B, T, E, device=wave.device, dtype=bf16)
+    x = c.enc_in
+    lrs = []
+    for l in range(g.n_layers):
+        s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=False,
+                      out=out_buf[l].view(B * T, E))
+        x = s.out
+    return out_buf, c.feats.view(B, T, E)
+
+
+# =============================================================================================
+# student
+# =============================================================================================
+def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], *, train: bool,
+                    heads: str = "all", want_lr: bool = False, pred_buf=None):
+    """Student forward (reference modules/model.py:420-552).  heads: 'all' (12 LayerWiseProjHeads),
+    'last' (after _disable_projection_heads: final_proj on the last layer), 'none'.
+    Returns ctx: .layers [n_layers][B*Ts, E], .tr [B*Ts, E], .preds [n_layers or 1, B, T', D], .feats."""
+    W.ensure_fresh()
+    dev = wave.device
+    valid_t = _valid_tensor(valid, dev)
+    valid_s = _valid_tensor(None if valid is None else [v // 2 for v in valid], dev)
+    c = frontend_fwd(P, W, g, wave, valid_t, save=train)
+    B, T, E = c.B, c.T, g.E
+    Ts = T // 2
+    c.Ts, c.valid_t, c.valid_s = Ts, valid_t, valid_s
+    # time-reduction Conv1d(k=2, s=2) (modules/module.py:317-321): reshaped-view GEMM, drops an odd tail frame
+    tr = torch.empty(B * Ts, E, device=dev, dtype=bf16)
+    a3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
+    b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
+    K.gemm_raw(a3, b3, tr, Ts, E, 2 * E, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=Ts * E,
+               flags=L.EPI_BIAS, bias=P["encoder.layers.0.bias"])
+    c.tr = tr
+    x = tr
+    c.layer_ctx = []
+    for l in range(g.n_layers):
+        s = layer_fwd(P, W, g, f"encoder.layers.{l + 1}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr)
+        c.layer_ctx.append(s)
+        x = s.out
+    c.layers = [s.out for s in c.layer_ctx]
+    c.lrs = [s.lr for s in c.layer_ctx]
+    # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E]
+    Tq = 2 * Ts
+    D = g.d_out
+    idx = list(range(g.n_layers)) if heads == "all" else ([g.n_layers - 1] if heads == "last" else [])
+    c.head_idx = idx
+    if idx:
+        if pred_buf is None:
+            pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=bf16)
+        c.z = []
+        for j, i in enumerate(idx):
+            z = K.linear(c.layers[i], W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"])
+            K.linear(z.view(B * Tq, E), W[f"h{i}.wlin"].view(D, E), P[_head_name(P, i) + "lin_proj.bias"],
+                     out=pred_buf[j].view(B * Tq, D))
+            c.z.append(z if train else None)
+    c.preds = pred_buf if idx else None
+    c.Tq = Tq
+    return c
+
+
+def _head_name(P, i):
+    return f"proj_head.{i}." if f"proj_head.{i}.lin_proj.bias" in P else "final_proj."
+
+
+def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc: int, num_cb=1, a_cb=0, b_cb=0,
+           a_c1_off=0, b_c1_off=0):
+    """out[M][N] (fp32, accumulated) += sum over contraction of dy^T x; both MN-major."""
+    K.gemm_raw(dy3, x3, out, M, N, Kc, a_major=1, b_major=1, num_cb=num_cb, a_coord=(0, 0, 0, a_cb),
+               b_coord=(0, 0, 0, b_cb), d_ld=N, flags=L.EPI_ATOMIC_ADD, a_c1_off=a_c1_off, b_c1_off=b_c1_off)
+
+
+def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torch.Tensor,
+                     dlayers: Optional[List[Optional[torch.Tensor]]] = None):
+    """Backward of student_forward(train=True, heads='all').  dpred: [n_layers, B, T', D] bf16 gradient of
+    the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer."""
+    E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
+    B, T, Ts, Tq = c.B, c.T, c.Ts, c.Tq
+    dev = dpred.device
+    gv = G_.view
+    dx = None  # gradient wrt the current layer's output [B*Ts, E]
+    for l in range(g.n_layers - 1, -1, -1):
+        s = c.layer_ctx[l]
+        p = f"encoder.layers.{l + 1}."
+        hp = f"proj_head.{l}."
+        if l in c.head_idx:
+            j = c.head_idx.index(l)
+            dp = dpred[j].view(B * Tq, D)
+            z = c.z[j].view(B * Tq, E)
+            K.colsum(dp, gv(hp + "lin_proj.bias"))
+            K.linear_wgrad(dp, z, out=gv(hp + "lin_proj.weight").view(D, E), accumulate=True)
+            dz = K.linear_dgrad(dp, W[f"h{l}.wlin"].view(D, E))  # [B*Tq, E] == [B*Ts, 2E]
+            K.colsum(dz, gv(hp + "upsampler.bias"))
+            dz2 = dz.view(B * Ts, 2 * E)
+            K.linear_wgrad(dz2, s.out, out=gv(hp + "upsampler.weight").view(2 * E, E), accumulate=True)
+            dx = K.linear_dgrad(dz2, W[f"h{l}.wup"].view(2 * E, E), residual=dx)
+        if dlayers is not None and dlayers[l] is not None:
+            dx = dlayers[l] if dx is None else K.add_bf16(dx, dlayers[l], torch.empty_like(dx))
+        if dx is None:
+            continue
+        # final LayerNorm
+        dy2 = torch.empty_like(dx)
+        K.layernorm_bwd(dx, s.y2, P[p + "final_layer_norm.weight"], s.mean2, s.rstd2, dy2,
+                        gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"))
+        # FFN
+        K.colsum(dy2, gv(p + "fc2.bias"))
+        K.linear_wgrad(dy2, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
+        du = K.linear_dgrad(dy2, W[f"l{l}.w2"].view(E, F), dgelu_of=s.u)
+        K.colsum(du, gv(p + "fc1.bias"))
+        K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
+        dx1 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2)
+        # attention LayerNorm
+        dy1 = torch.empty_like(dx1)
+        K.layernorm_bwd(dx1, s.y1, P[p + "self_attn_layer_norm.weight"], s.mean1, s.rstd1, dy1,
+                        gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"))
+        # attention block
+        K.colsum(dy1, gv(p + "self_attn.out_proj.bias"))
+        K.linear_wgrad(dy1, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
+        dattn = K.linear_dgrad(dy1, W[f"l{l}.wo"].view(E, E))
+        dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
+        delta = torch.empty(B, H, Ts, device=dev, dtype=f32)
+        K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5)
+        K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
+        K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
+                       accumulate=True)
+        dx = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1)
+    if dx is None:
+        return
+    # ---- time-reduction conv backward
+    K.colsum(dx, gv("encoder.layers.0.bias"))
+    dy3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
+    x3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
+    _wgrad(dy3, x3, gv("encoder.layers.0.weight").view(E, 2 * E), E, 2 * E, Ts, num_cb=B, a_cb=1, b_cb=1)
+    denc = torch.zeros(B * T, E, device=dev, dtype=bf16) if T % 2 else torch.empty(B * T, E, device=dev, dtype=bf16)
+    a3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
+    b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
+    K.gemm_raw(a3, b3, denc, Ts, 2 * E, E, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * E, d_hi_stride=T * E)
+    # ---- encoder prologue backward: LayerNorm, + pos-conv residual, GELU, grouped conv (dgrad + wgrad), mask
+    G, cp, kp = g.G, g.cp, g.kpos
+    Tp = T + kp
+    dh = torch.empty(B * T, E, device=dev, dtype=bf16)
+    dcg = torch.zeros(B * G, Tp, cp, device=dev, dtype=bf16)
+    pad_b = kp // 2 - 1
+    K.posconv_finish_bwd(denc, c.h, c.conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"], c.mean_e,
+                         c.rstd_e, dh, dcg, gv("encoder.layer_norm.weight"), gv("encoder.layer_norm.bias"),
+                         gv("encoder.pos_conv.0.bias"), B, T, E, G, cp, pad_b, Tp)
+    dxc = torch.empty(B * T, G * cp, device=dev, dtype=bf16)
+    a3 = L.tensor3(data_ptr=dcg.data_ptr(), dim=(kp * cp, T, B * G), stride=(cp, Tp * cp))
+    b3 = L.tensor3(data_ptr=W["pc.wt"].data_ptr(), dim=(kp * cp, cp, G), stride=(kp * cp, cp * kp * cp))
+    K.gemm_raw(a3, b3, dxc, T, cp, kp * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
+               d_ld=G * cp, d_hi_stride=T * G * cp, d_lo_stride=cp)
+    # wgrad: dwt[g][(j,ci)][co] = sum_{b,t} xg[b,g,t+j,ci] * dcg[b,g,t+pad_b,co]
+    dwt = torch.empty(G, kp * cp, cp, device=dev, dtype=f32)
+    a3 = L.tensor3(data_ptr=c.xg.data_ptr(), dim=(kp * cp, T, B * G), stride=(cp, Tp * cp))
+    b3 = L.tensor3(data_ptr=dcg.data_ptr(), dim=(cp, Tp, B * G), stride=(cp, Tp * cp))
+    K.gemm_raw(a3, b3, dwt, kp * cp, cp, T, a_major=1, b_major=1, num_ob=G, ob_mod=G, num_cb=B,
+               a_coord=(0, 0, 1, G), b_coord=(0, 0, 1, G), d_ld=cp, d_lo_stride=kp * cp * cp, b_c1_off=pad_b,
+               split_k=1)
+    K.posconv_wn_bwd(dwt, P["encoder.pos_conv.0.weight_v"], P["encoder.pos_conv.0.weight_g"], W["pc.inv"],
+                     gv("encoder.pos_conv.0.weight_v"), gv("encoder.pos_conv.0.weight_g"), E, G, kp, cp, True)
+    dfeat = torch.empty(B * T, E, device=dev, dtype=bf16)
+    K.posconv_unpack_bwd(dh, dxc, c.valid_t, dfeat, B, T, E, G, cp)
+    # ---- post_extract_proj + LayerNorm(C_feat)
+    Cf = g.c_feat
+    K.colsum(dfeat, gv("post_extract_proj.bias"))
+    K.linear_wgrad(dfeat, c.f_ln.view(B * T, Cf), out=gv("post_extract_proj.weight").view(E, Cf), accumulate=True)
+    dfl = K.linear_dgrad(dfeat, W["pp.w"].view(E, Cf))
+    n_conv = len(g.conv_layers)
+    last = n_conv - 1
+    dyl = torch.empty(B * T, Cf, device=dev, dtype=bf16)
+    K.layernorm_bwd(dfl, c.out, P["layer_norm.weight"], c.mean_f, c.rstd_f, dyl, gv("layer_norm.weight"),
+                    gv("layer_norm.bias"))
+    # dU_last = dY * gelu'(U_last)
+    du = torch.empty(B, T, Cf, device=dev, dtype=bf16)
+    K.mul_dgelu(dyl, T * Cf, c.u[last], T * Cf, du, T * Cf, B, T * Cf)
+    # ---- conv stack backward, layers last .. 1.  du: [B, To + 2*halo_i, C_i], data rows start at halo_i
+    for i in range(last, 0, -1):
+        co, k, s = g.conv_layers[i]
+        cin = g.conv_layers[i - 1][0]
+        To, Tin = c.frames[i], c.frames[i - 1]
+        halo, in_halo = c.halos[i], c.halos[i - 1]
+        rows, in_rows = To + 2 * halo, Tin + 2 * in_halo
+        xin = c.y[i - 1]
+        du_data = du.data_ptr() + 2 * halo * co
+        # wgrad: dW2[co][(j,ci)] += sum_{b,t} dU[b,t,co] * X[b, s*t + j, ci]
+        dy3 = L.tensor3(data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
+        x3 = L.tensor3(data_ptr=xin.data_ptr() + 2 * in_halo * cin, dim=(k * cin, To, B), stride=(s * cin, in_rows * cin))
+        _wgrad(dy3, x3, gv(f"feature_extractor.conv_layers.{i}.0.weight").view(co, k * cin), co, k * cin, To,
+               num_cb=B, a_cb=1, b_cb=1)
+        first = i == 1
+        if first:
+            # gradient wrt the GELU output of layer 0: no GELU derivative here (conv0 backward recomputes it)
+            assert (k, s) in ((1, 1), (2, 2)) or halo == 1
+            dprev = torch.empty(B, Tin, cin, device=dev, dtype=bf16) if (k, s) == (1, 1) else \
+                torch.zeros(B, Tin, cin, device=dev, dtype=bf16)
+            flags, uprev = 0, None
+        else:
+            # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1}); zero-filled so halo rows / an odd tail frame stay zero
+            dprev = torch.zeros(B, in_rows, cin, device=dev, dtype=bf16)
+            flags, uprev = L.EPI_MUL_DGELU, c.u[i - 1]
+        if (k, s) == (1, 1) or (k, s) == (2, 2):
+            # dA[b,t,(j,ci)] = dU[b,t,:] W2[:, (j,ci)]  ==  dX[b, s*t + j, ci]   (W2 consumed MN-major)
+            a3 = L.tensor3(data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
+            b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
+            K.gemm_raw(a3, b3, dprev, To, k * cin, co, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=k * cin,
+                       d_hi_stride=in_rows * cin, d_offset_elems=in_halo * cin, flags=flags, aux_in=uprev)
+        else:  # (3, 2): even input frames see taps (2, 0) of outputs (u-1, u); odd frames tap 1 of output u
+            n_even, n_odd = (Tin + 1) // 2, Tin // 2
+            a3 = L.tensor3(data_ptr=du.data_ptr(), dim=(2 * co, n_even, B), stride=(co, rows * co))
+            b3 = L.tensor3(data_ptr=W[f"conv{i}.wd_even"].data_ptr(), dim=(2 * co, cin, 1), stride=(2 * co, 2 * co * cin))
+            K.gemm_raw(a3, b3, dprev, n_even, cin, 2 * co, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * cin,
+                       d_hi_stride=in_rows * cin, d_offset_elems=in_halo * cin, flags=flags, aux_in=uprev)
+            a3 = L.tensor3(data_ptr=du_data, dim=(co, n_odd, B), stride=(co, rows * co))
+            b3 = L.tensor3(data_ptr=W[f"conv{i}.wd_odd"].data_ptr(), dim=(co, cin, 1), stride=(co, co * cin))
+            K.gemm_raw(a3, b3, dprev, n_odd, cin, co, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * cin,
+                       d_hi_stride=in_rows * cin, d_offset_elems=(in_halo + 1) * cin, flags=flags, aux_in=uprev)
+        du = dprev
+    # ---- layer 0: conv + GroupNorm + GELU backward (dW0, dgamma, dbeta) in one pass over dY0
+    C0 = g.conv_layers[0][0]
+    acc = torch.empty(B, C0, 12, device=dev, dtype=f32)
+    K.conv0_bwd(c.wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
+                P["feature_extractor.conv_layers.0.2.bias"], c.frames[0], c.stat, c.mean0, c.rstd0, du, acc,
+                gv("feature_extractor.conv_layers.0.0.weight"), gv("feature_extractor.conv_layers.0.2.weight"),
+                gv("feature_extractor.conv_layers.0.2.bias"), True)

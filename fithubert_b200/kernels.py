@@ -22,7 +22,7 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
              num_ob=1, ob_mod=1, num_cb=1, a_coord=(0, 0, 0, 0), b_coord=(0, 0, 0, 0),
              d_ld: int, d_hi_stride=0, d_lo_stride=0, flags=0, split_k=0, bias=None, residual=None,
              aux_in=None, aux_out=None, row_valid=None, loss_target=None, loss_acc=None,
-             loss_weight=0.0, grad_scale=0.0, d_offset_elems=0) -> None:
+             loss_weight=0.0, grad_scale=0.0, d_offset_elems=0, a_c1_off=0, b_c1_off=0) -> None:
     g = L.GemmArgs()
     g.a, g.b = a, b
     g.a_major, g.b_major = a_major, b_major
@@ -30,6 +30,7 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
     g.num_ob, g.ob_mod, g.num_cb = num_ob, ob_mod, num_cb
     g.a_lo_c0, g.a_hi_c2, g.a_lo_c2, g.a_cb_c2 = a_coord
     g.b_lo_c0, g.b_hi_c2, g.b_lo_c2, g.b_cb_c2 = b_coord
+    g.a_c1_off, g.b_c1_off = a_c1_off, b_c1_off
     g.d = d.data_ptr() + d_offset_elems * d.element_size()
     g.d_ld, g.d_hi_stride, g.d_lo_stride = d_ld, d_hi_stride, d_lo_stride
     if d.dtype == torch.float32:
@@ -37,9 +38,11 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
     else:
         assert d.dtype == bf16
     g.flags, g.split_k = flags, split_k
-    for name, t in (("bias", bias), ("residual", residual), ("aux_in", aux_in), ("aux_out", aux_out),
-                    ("row_valid", row_valid), ("loss_target", loss_target), ("loss_acc", loss_acc)):
+    for name, t in (("bias", bias), ("row_valid", row_valid), ("loss_acc", loss_acc)):
         setattr(g, name, None if t is None else t.data_ptr())
+    for name, t in (("residual", residual), ("aux_in", aux_in), ("aux_out", aux_out), ("loss_target", loss_target)):
+        # "laid out like D": same element offset as the output
+        setattr(g, name, None if t is None else t.data_ptr() + d_offset_elems * t.element_size())
     g.loss_weight, g.grad_scale = loss_weight, grad_scale
     L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
 
@@ -101,3 +104,126 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] 
     b3 = L.tensor3(data_ptr=x.data_ptr(), dim=(K, M, 1), stride=(x.stride(0), x.stride(0) * M))
     gemm_raw(a3, b3, out, N, K, M, a_major=1, b_major=1, d_ld=out.stride(0), flags=L.EPI_ATOMIC_ADD)
     return out
+
+
+# ----------------------------------------------------------------------------- non-GEMM kernels
+def _f(x):
+    return C.c_float(float(x))
+
+
+def conv0_fwd(wave, weight, gamma, beta, T0, stat, mean, rstd, out, eps=1e-5):
+    a = L.Conv0Args()
+    B, Ld = wave.shape
+    a.wave, a.wave_ld = wave.data_ptr(), wave.stride(0)
+    a.B, a.L, a.C, a.T0, a.kernel, a.stride, a.eps = B, Ld, weight.shape[0], T0, weight.shape[-1], 5, eps
+    a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    a.stat, a.mean, a.rstd, a.out = stat.data_ptr(), mean.data_ptr(), rstd.data_ptr(), out.data_ptr()
+    L.check(L.lib().fhb_conv0_gn_gelu_fwd(C.byref(a), L.stream_ptr()), "fhb_conv0_gn_gelu_fwd")
+
+
+def conv0_bwd(wave, weight, gamma, beta, T0, stat, mean, rstd, dy, acc, dweight, dgamma, dbeta,
+              accumulate=True, eps=1e-5):
+    a = L.Conv0Args()
+    B, Ld = wave.shape
+    a.wave, a.wave_ld = wave.data_ptr(), wave.stride(0)
+    a.B, a.L, a.C, a.T0, a.kernel, a.stride, a.eps = B, Ld, weight.shape[0], T0, weight.shape[-1], 5, eps
+    a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    a.stat, a.mean, a.rstd = stat.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.dy, a.acc = dy.data_ptr(), acc.data_ptr()
+    a.dweight, a.dgamma, a.dbeta, a.accumulate = dweight.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate)
+    L.check(L.lib().fhb_conv0_gn_gelu_bwd(C.byref(a), L.stream_ptr()), "fhb_conv0_gn_gelu_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
+    rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
+    L.check(L.lib().fhb_layernorm_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd),
+                                      C.c_int64(rows), Cd, _f(eps), L.stream_ptr()), "fhb_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+    rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
+    L.check(L.lib().fhb_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dres),
+                                      L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), C.c_int64(rows), Cd, L.stream_ptr()),
+            "fhb_layernorm_bwd")
+    return dx
+
+
+def posconv_pack(x, valid, xg, B, T, Cd, G, cp, pad_l, Tp):
+    L.check(L.lib().fhb_posconv_pack(L.ptr(x), L.ptr(valid), L.ptr(xg), B, T, Cd, G, cp, pad_l, Tp, L.stream_ptr()),
+            "fhb_posconv_pack")
+
+
+def posconv_wn_prep(v, g, w_out, inv_norm, Cd, G, Kt, cp, flip_transpose):
+    L.check(L.lib().fhb_posconv_wn_prep(L.ptr(v), L.ptr(g), L.ptr(w_out), L.ptr(inv_norm), Cd, G, Kt, cp,
+                                        int(flip_transpose), L.stream_ptr()), "fhb_posconv_wn_prep")
+
+
+def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5):
+    L.check(L.lib().fhb_posconv_finish_fwd(L.ptr(x), L.ptr(valid), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(beta),
+                                           L.ptr(h_out), L.ptr(y), L.ptr(mean), L.ptr(rstd), B, T, Cd, G, cp, _f(eps),
+                                           L.stream_ptr()), "fhb_posconv_finish_fwd")
+
+
+def posconv_finish_bwd(dy, h, conv, bias, gamma, mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, Cd, G, cp, pad_l, Tp):
+    L.check(L.lib().fhb_posconv_finish_bwd(L.ptr(dy), L.ptr(h), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(mean),
+                                           L.ptr(rstd), L.ptr(dh), L.ptr(dcg), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias),
+                                           B, T, Cd, G, cp, pad_l, Tp, L.stream_ptr()), "fhb_posconv_finish_bwd")
+
+
+def posconv_unpack_bwd(dh, dxc, valid, dx, B, T, Cd, G, cp):
+    L.check(L.lib().fhb_posconv_unpack_bwd(L.ptr(dh), L.ptr(dxc), L.ptr(valid), L.ptr(dx), B, T, Cd, G, cp,
+                                           L.stream_ptr()), "fhb_posconv_unpack_bwd")
+
+
+def posconv_wn_bwd(dwt, v, g, inv_norm, dv, dg, Cd, G, Kt, cp, accumulate=True):
+    L.check(L.lib().fhb_posconv_wn_bwd(L.ptr(dwt), L.ptr(v), L.ptr(g), L.ptr(inv_norm), L.ptr(dv), L.ptr(dg), Cd, G, Kt,
+                                       cp, int(accumulate), L.stream_ptr()), "fhb_posconv_wn_bwd")
+
+
+def attn_fwd(qkv, valid, out, lse, B, T, H, d, scale):
+    L.check(L.lib().fhb_attn_fwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(lse), B, T, H, d, _f(scale),
+                                 L.stream_ptr()), "fhb_attn_fwd")
+
+
+def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale):
+    L.check(L.lib().fhb_attn_bwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv),
+                                 L.ptr(delta_ws), B, T, H, d, _f(scale), L.stream_ptr()), "fhb_attn_bwd")
+
+
+def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0):
+    L.check(L.lib().fhb_distill_loss_fwd_bwd(L.ptr(pred), L.ptr(tgt), L.ptr(weights), L.ptr(layer_loss), L.ptr(dpred),
+                                             n_layers, B, Tp, Tt, D, loss_type, _f(grad_scale), L.stream_ptr()),
+            "fhb_distill_loss_fwd_bwd")
+
+
+def adamw_multi(table, n_tensors, max_n, lr, beta1, beta2, eps, wd, step, mode=0, grad_scale=1.0):
+    L.check(L.lib().fhb_adamw_multi(L.ptr(table), n_tensors, C.c_int64(max_n), _f(lr), _f(beta1), _f(beta2), _f(eps),
+                                    _f(wd), step, mode, _f(grad_scale), L.stream_ptr()), "fhb_adamw_multi")
+
+
+def prep_multi(table, n_tensors, max_n):
+    L.check(L.lib().fhb_prep_multi(L.ptr(table), n_tensors, C.c_int64(max_n), L.stream_ptr()), "fhb_prep_multi")
+
+
+def colsum(x2d, out):
+    rows, Cd = x2d.shape
+    L.check(L.lib().fhb_colsum(L.ptr(x2d), C.c_int64(rows), Cd, C.c_int64(x2d.stride(0)), L.ptr(out), L.stream_ptr()),
+            "fhb_colsum")
+
+
+def add_bf16(a, b, y):
+    L.check(L.lib().fhb_add_bf16(L.ptr(a), L.ptr(b), L.ptr(y), C.c_int64(a.numel()), L.stream_ptr()), "fhb_add_bf16")
+    return y
+
+
+def mul_dgelu(dy, dy_bs, u, u_bs, out, out_bs, B, n, *, u_off=0, out_off=0):
+    L.check(L.lib().fhb_mul_dgelu(L.ptr(dy), C.c_int64(dy_bs), C.c_void_p(u.data_ptr() + 2 * u_off), C.c_int64(u_bs),
+                                  C.c_void_p(out.data_ptr() + 2 * out_off), C.c_int64(out_bs), B, C.c_int64(n),
+                                  L.stream_ptr()), "fhb_mul_dgelu")
+
+
+def mask_lengths(mask_u8, lengths):
+    B, Ld = mask_u8.shape
+    L.check(L.lib().fhb_mask_lengths(L.ptr(mask_u8), B, C.c_int64(Ld), L.ptr(lengths), L.stream_ptr()),
+            "fhb_mask_lengths")

@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("num_ob", C.c_int32), ("ob_mod", C.c_int32), ("num_cb", C.c_int32),
         ("a_lo_c0", C.c_int32), ("a_hi_c2", C.c_int32), ("a_lo_c2", C.c_int32), ("a_cb_c2", C.c_int32),
         ("b_lo_c0", C.c_int32), ("b_hi_c2", C.c_int32), ("b_lo_c2", C.c_int32), ("b_cb_c2", C.c_int32),
+        ("a_c1_off", C.c_int32), ("b_c1_off", C.c_int32),
         ("d", C.c_void_p),
         ("d_ld", C.c_int64), ("d_hi_stride", C.c_int64), ("d_lo_stride", C.c_int64),
         ("flags", C.c_int32), ("split_k", C.c_int32),
@@ -38,6 +39,36 @@ class GemmArgs(C.Structure):
         ("loss_target", C.c_void_p), ("loss_acc", C.c_void_p),
         ("loss_weight", C.c_float), ("grad_scale", C.c_float),
     ]
+
+
+class Conv0Args(C.Structure):
+    _fields_ = [
+        ("wave", C.c_void_p), ("wave_ld", C.c_int64),
+        ("B", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("T0", C.c_int32),
+        ("kernel", C.c_int32), ("stride", C.c_int32), ("eps", C.c_float),
+        ("weight", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("stat", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("out", C.c_void_p), ("dy", C.c_void_p), ("acc", C.c_void_p),
+        ("dweight", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("accumulate", C.c_int32),
+    ]
+
+
+class AdamwTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n", C.c_int64), ("dim", C.c_int64 * 3), ("gstride", C.c_int64 * 3)]
+
+
+class PrepTensor(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dim", C.c_int64 * 3), ("sstride", C.c_int64 * 3),
+                ("dst_is_f32", C.c_int32), ("accumulate", C.c_int32)]
+
+
+def table_to_device(entries, device) -> torch.Tensor:
+    """Pack a list of ctypes structs into one device-resident byte tensor (a kernel argument table)."""
+    arr = (type(entries[0]) * len(entries))(*entries)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
 
 
 _lib = None
@@ -65,7 +96,11 @@ def _declare(l):
 
 # every symbol include/fhb.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "fhb_last_error", "fhb_abi_version", "fhb_gemm",
+    "fhb_last_error", "fhb_abi_version", "fhb_gemm", "fhb_conv0_gn_gelu_fwd", "fhb_conv0_gn_gelu_bwd",
+    "fhb_layernorm_fwd", "fhb_layernorm_bwd", "fhb_posconv_pack", "fhb_posconv_wn_prep",
+    "fhb_posconv_finish_fwd", "fhb_posconv_finish_bwd", "fhb_posconv_unpack_bwd", "fhb_posconv_wn_bwd",
+    "fhb_attn_fwd", "fhb_attn_bwd", "fhb_distill_loss_fwd_bwd", "fhb_adamw_multi", "fhb_prep_multi",
+    "fhb_colsum", "fhb_add_bf16", "fhb_mul_dgelu", "fhb_mask_lengths",
 ]
 
 

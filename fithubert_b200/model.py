@@ -1,0 +1,383 @@
+"""Reference-facing model classes.  Same constructor / forward signatures, attribute names, returned
+dict keys and state-dict keys as the reference (modules/model.py:253-588, modules/module.py,
+utils/utils.py:51-99), but the modules below are parameter
+CONTAINERS only: all arithmetic runs in engine.py on hand-written sm_100a kernels.  Calling them on
+CPU tensors raises - there is no fallback path."""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+from . import kernels as K
+from . import lib as L
+from .config import CustomStudentModelConfig, parse_int_list, parse_layer_spec
+
+bf16 = torch.bfloat16
+
+
+# --------------------------------------------------------------------------- parameter containers
+class _Weight(nn.Module):
+    def __init__(self, *shape, bias_shape=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(*shape))
+        if bias_shape is not None:
+            self.bias = nn.Parameter(torch.zeros(*bias_shape))
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise L.FhbError("parameter container: the computation runs in fithubert_b200.engine")
+
+
+class _Affine(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class ConvFeatureExtractionModel(nn.Module):
+    """conv_layers.{i}.0.weight [Cout, Cin, k]; conv_layers.0.2.{weight,bias} (GroupNorm).
+    Init: kaiming_normal_ (reference modules/module.py:45-48)."""
+
+    def __init__(self, conv_layers, dropout=0.0, mode="default", conv_bias=False):
+        super().__init__()
+        assert mode in {"default", "layer_norm"}
+        self.conv_layers = nn.ModuleList()
+        cin = 1
+        for i, cl in enumerate(conv_layers):
+            assert len(cl) == 3, "invalid conv definition: " + str(cl)
+            dim, k, stride = cl
+            conv = _Weight(dim, cin, k)
+            nn.init.kaiming_normal_(conv.weight)
+            mods = [conv, nn.Identity()]
+            if i == 0:
+                mods.append(_Affine(dim))
+            mods.append(nn.Identity())
+            self.conv_layers.append(nn.Sequential(*mods))
+            cin = dim
+
+
+class _PosConv(nn.Module):
+    """Old-style weight_norm(dim=2) parameters: bias, weight_g [1,1,k], weight_v [E, E/G, k]
+    (reference modules/module.py:186-200)."""
+
+    def __init__(self, e, k, g):
+        super().__init__()
+        v = torch.empty(e, e // g, k)
+        nn.init.normal_(v, mean=0, std=math.sqrt(4.0 / (k * e)))
+        self.bias = nn.Parameter(torch.zeros(e))
+        self.weight_g = nn.Parameter(v.norm(dim=(0, 1), keepdim=True).clone())
+        self.weight_v = nn.Parameter(v)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, e, heads):
+        super().__init__()
+        self.embed_dim, self.num_heads = e, heads
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            lin = nn.Linear(e, e, bias=True)
+            nn.init.normal_(lin.weight, 0.0, 0.02)  # init_bert_params
+            nn.init.zeros_(lin.bias)
+            setattr(self, nm, lin)
+
+
+class TransformerSentenceEncoderLayer(nn.Module):
+    def __init__(self, embedding_dim=768, ffn_embedding_dim=3072, num_attention_heads=8, **_):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.self_attn = _SelfAttention(embedding_dim, num_attention_heads)
+        self.self_attn_layer_norm = nn.LayerNorm(embedding_dim)
+        self.fc1 = nn.Linear(embedding_dim, ffn_embedding_dim)
+        self.fc2 = nn.Linear(ffn_embedding_dim, embedding_dim)
+        self.final_layer_norm = nn.LayerNorm(embedding_dim)
+        for lin in (self.fc1, self.fc2):
+            nn.init.normal_(lin.weight, 0.0, 0.02)
+            nn.init.zeros_(lin.bias)
+
+
+class TransformerEncoder(nn.Module):
+    """pos_conv.0.*, layers.{i}.* (layers[0] = time-reduction Conv1d when enabled), layer_norm.*"""
+
+    def __init__(self, embed_dim, ffn_dim, heads, n_layers, conv_pos, conv_pos_groups, tr_layer: bool):
+        super().__init__()
+        self.embedding_dim = embed_dim
+        self.pos_conv = nn.Sequential(_PosConv(embed_dim, conv_pos, conv_pos_groups), nn.Identity(), nn.Identity())
+        self.layers = nn.ModuleList(
+            [TransformerSentenceEncoderLayer(embed_dim, ffn_dim, heads) for _ in range(n_layers)])
+        if tr_layer:
+            tr = nn.Conv1d(embed_dim, embed_dim, kernel_size=2, stride=2)  # default torch init, as the reference
+            self.layers.insert(0, tr)
+        self.layer_norm = nn.LayerNorm(embed_dim)
+
+
+class LayerWiseProjHead(nn.Module):
+    def __init__(self, in_dim, out_dim, enable_tr_layer=True, tr_reduce_factor=2):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.upsampler = nn.ConvTranspose1d(in_dim, in_dim, kernel_size=tr_reduce_factor, stride=tr_reduce_factor)
+        self.lin_proj = nn.Linear(in_dim, out_dim)
+
+
+def _named_param_dict(module: nn.Module):
+    # detach() shares the version counter with the Parameter (unlike .data), so in-place updates by any
+    # optimizer / load_state_dict are seen by WeightSet.signature()
+    return {n: p.detach() for n, p in module.named_parameters()}
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise L.FhbError(f"{what}: parameters must live on a CUDA device (no CPU fallback for the hot path)")
+
+
+# --------------------------------------------------------------------------- mask rules (host integers)
+def conv_out_lengths(lengths: List[int], conv_layers) -> List[int]:
+    """Rule M1 (reference modules/model.py:376-391): per layer floor((n - k)/s + 1)."""
+    out = []
+    for n in lengths:
+        for (_, k, s) in conv_layers:
+            n = (n - k) // s + 1
+        out.append(int(n))
+    return out
+
+
+def hubert_mask_lengths(lengths: List[int], Lmax: int, T: int) -> List[int]:
+    """Rule M3 (fairseq HubertModel.forward_padding_mask): a frame is padding iff all its samples are;
+    valid = min(T, ceil(len / chunk)), chunk = (Lmax - Lmax % T) / T."""
+    chunk = (Lmax - Lmax % T) // T
+    return [min(T, -(-int(n) // chunk)) for n in lengths]
+
+
+def _lengths_from_mask(padding_mask: Optional[torch.Tensor]) -> Optional[List[int]]:
+    """Per-sample un-padded length, or None when there is no padding (the reference then runs mask-free,
+    modules/model.py:449,471-472)."""
+    if padding_mask is None:
+        return None
+    if padding_mask.is_cuda:
+        out = torch.empty(padding_mask.shape[0], device=padding_mask.device, dtype=torch.int32)
+        K.mask_lengths(padding_mask.contiguous().view(torch.uint8), out)
+        lengths = out.tolist()
+    else:
+        lengths = (~padding_mask).sum(-1).tolist()
+    if all(n == padding_mask.shape[1] for n in lengths):
+        return None
+    return lengths
+
+
+def _frame_mask(valid: Optional[List[int]], T: int, device) -> Optional[torch.Tensor]:
+    if valid is None:
+        return None
+    m = torch.arange(T).unsqueeze(0) >= torch.tensor(valid).unsqueeze(1)
+    return m.to(device)
+
+
+# --------------------------------------------------------------------------- student
+class CustomStudentModel(nn.Module):
+    def __init__(self, cfg: CustomStudentModelConfig, teacher_model=None, **kwargs):
+        super().__init__()
+        self.cfg = cfg
+        cfg.validate_hot_path()
+        self.n_mels = cfg.n_mels
+        layers = parse_layer_spec(cfg.conv_feature_layers)
+        self.embed = layers[-1][0]
+        self.feature_extractor = ConvFeatureExtractionModel(layers, 0.0, cfg.extractor_mode, cfg.conv_bias)
+        self.post_extract_proj = nn.Linear(self.embed, cfg.encoder_embed_dim)
+        self.cnn_proj_head = None
+        self.crop_seq_to_multiple = cfg.crop_seq_to_multiple
+        self.feature_grad_mult = cfg.feature_grad_mult
+        self.encoder = TransformerEncoder(cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim,
+                                          cfg.encoder_attention_heads, cfg.encoder_layers, cfg.conv_pos,
+                                          cfg.conv_pos_groups, cfg.enable_tr_layer)
+        self.layer_norm = nn.LayerNorm(self.embed)
+        self.init_conv_layers = cfg.init_conv_layers
+        self.init_encoder_layers = cfg.init_encoder_layers
+        self._teacher_task_agnostic = cfg._teacher_task_agnostic
+        self.pred_layer_id = parse_int_list(cfg.pred_layer_id)
+        self.n_tasks = len(self.pred_layer_id)
+        self.enable_tr_layer = cfg.enable_tr_layer
+        self.upsampler = nn.ConvTranspose1d(cfg.encoder_embed_dim, cfg.encoder_embed_dim,
+                                            kernel_size=cfg.tr_reduce_factor, stride=cfg.tr_reduce_factor)
+        self.layerwise_proj = cfg.layerwise_proj
+        self.proj_head = nn.ModuleList([
+            LayerWiseProjHead(cfg.encoder_embed_dim, cfg.pred_head_final_dim, cfg.enable_tr_layer, cfg.tr_reduce_factor)
+            for _ in range(cfg.encoder_layers)])
+        self.final_proj = None
+        self.specaug = None
+        if self.init_conv_layers:
+            assert teacher_model is not None
+            self.init_from_teacher_conv(teacher_model)
+        if self.init_encoder_layers > 0:
+            assert teacher_model is not None
+            self.init_from_teacher_enc(teacher_model, self.init_encoder_layers)
+        self._geom = E.Geometry(layers, cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads,
+                                cfg.conv_pos_groups, cfg.conv_pos, cfg.encoder_layers, cfg.pred_head_final_dim, True)
+        self._weights = None
+        self._grads = None
+        self._conv_layers = layers
+
+    # ---- reference API -------------------------------------------------------------------
+    def add_specaug(self, specaug):
+        self.specaug = specaug
+
+    def _get_feat_extract_output_lengths(self, input_lengths: torch.LongTensor):
+        return torch.tensor(conv_out_lengths(input_lengths.tolist(), self._conv_layers), dtype=torch.long,
+                            device=input_lengths.device)
+
+    def _disable_projection_heads(self):
+        if self.layerwise_proj:
+            self.final_proj = self.proj_head[-1]
+        self.proj_head = None
+        self.cnn_proj_head = None
+        self._weights = None
+        self._grads = None
+
+    def init_from_teacher_conv(self, teacher_model):
+        self.feature_extractor.load_state_dict(teacher_model.model.feature_extractor.state_dict())
+        try:
+            self.post_extract_proj.load_state_dict(teacher_model.model.post_extract_proj.state_dict())
+        except Exception:
+            pass
+
+    def init_from_teacher_enc(self, teacher_model, n_layers):
+        assert n_layers <= self.cfg.encoder_layers
+        self.encoder.pos_conv.load_state_dict(teacher_model.model.encoder.pos_conv.state_dict())
+        for i in range(n_layers):
+            self.encoder.layers[i].load_state_dict(teacher_model.model.encoder.layers[i].state_dict())
+
+    # ---- engine plumbing -----------------------------------------------------------------
+    def engine_state(self, train: bool):
+        P = _named_param_dict(self)
+        _require_cuda(next(iter(P.values())), "CustomStudentModel")
+        if self._weights is None or self._weights.train != train or self._weights.device != next(iter(P.values())).device \
+                or any(self._weights.params[k] is not v and self._weights.params[k].data_ptr() != v.data_ptr()
+                       for k, v in P.items()):
+            self._weights = E.WeightSet(P, self._geom, train)
+            self._grads = None
+        if train and self._grads is None:
+            self._grads = E.GradStore(P, self._geom)
+        return P, self._weights, self._grads
+
+    def forward(self, source, padding_mask=None, layer=None):
+        if layer is not None:
+            raise NotImplementedError("`layer` early exit is not implemented on the B200 path")
+        dev = self.post_extract_proj.weight.device
+        _require_cuda(self.post_extract_proj.weight, "CustomStudentModel")
+        source = source.to(dev, non_blocking=True).float().contiguous()
+        lengths = _lengths_from_mask(padding_mask)
+        valid = None if lengths is None else conv_out_lengths(lengths, self._conv_layers)
+        heads = "all" if self.proj_head is not None else ("last" if self.final_proj is not None else "none")
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad:
+            if heads != "all":
+                raise NotImplementedError("training without the layer-wise projection heads is not implemented")
+            from .autograd import student_apply
+            c, preds, layers_out = student_apply(self, source, valid)
+        else:
+            P, W, _ = self.engine_state(False)
+            c = E.student_forward(P, W, self._geom, source, valid, train=False, heads=heads, want_lr=True)
+            preds, layers_out = c.preds, c.layers
+        B, T, Ts, Em = c.B, c.T, c.Ts, self._geom.E
+        mask = _frame_mask(valid, T, dev)
+        layer_results = [(lo.view(B, Ts, Em).transpose(0, 1), None,
+                          None if lr is None else lr.view(B, Ts, Em).transpose(0, 1))
+                         for lo, lr in zip(layers_out, c.lrs)]
+        if heads == "all":
+            projections = [preds[i] for i in range(preds.shape[0])]
+            x = projections[-1]
+        elif heads == "last":
+            projections, x = None, preds[0]
+        else:
+            projections, x = None, layers_out[-1].view(B, Ts, Em)
+        return {
+            "x": x,
+            "padding_mask": mask,
+            "features": c.feats.view(B, T, Em),
+            "layer_results": layer_results,
+            "tr_layer_results": [c.tr.view(B, Ts, Em).transpose(0, 1)],
+            "projections": projections,
+        }
+
+    def extract_features(self, source, padding_mask, layer=None):
+        return self.forward(source, padding_mask, layer=layer)
+
+
+# --------------------------------------------------------------------------- teacher
+class TeacherModel(nn.Module):
+    """HuBERT-Base / wav2vec 2.0-Base `features_only` trunk with fairseq's parameter names
+    (feature_extractor.*, layer_norm.*, post_extract_proj.*, encoder.*); SURVEY App. B.2, B.4."""
+
+    def __init__(self, kind="hubert", conv_feature_layers="[(512,10,5)] + [(512,3,2)] * 4 + [(512,2,2)] * 2",
+                 encoder_embed_dim=768, encoder_ffn_embed_dim=3072, encoder_attention_heads=12, encoder_layers=12,
+                 conv_pos=128, conv_pos_groups=16):
+        super().__init__()
+        assert kind in ("hubert", "wav2vec2")
+        self.kind = kind
+        layers = parse_layer_spec(conv_feature_layers)
+        self._conv_layers = layers
+        self.feature_extractor = ConvFeatureExtractionModel(layers)
+        self.layer_norm = nn.LayerNorm(layers[-1][0])
+        self.post_extract_proj = nn.Linear(layers[-1][0], encoder_embed_dim)
+        self.encoder = TransformerEncoder(encoder_embed_dim, encoder_ffn_embed_dim, encoder_attention_heads,
+                                          encoder_layers, conv_pos, conv_pos_groups, tr_layer=False)
+        self._geom = E.Geometry(layers, encoder_embed_dim, encoder_ffn_embed_dim, encoder_attention_heads,
+                                conv_pos_groups, conv_pos, encoder_layers, 0, False)
+        self._weights = None
+
+    def engine_state(self):
+        P = _named_param_dict(self)
+        first = next(iter(P.values()))
+        _require_cuda(first, "TeacherModel")
+        if self._weights is None or any(self._weights.params[k].data_ptr() != v.data_ptr() for k, v in P.items()):
+            self._weights = E.WeightSet(P, self._geom, False)
+        return P, self._weights
+
+    def frame_valid(self, padding_mask, Lmax: int, T: int) -> Optional[List[int]]:
+        if padding_mask is None:
+            return None
+        if self.kind == "hubert":  # applied whenever a mask is passed, even an all-False one
+            if padding_mask.is_cuda:
+                out = torch.empty(padding_mask.shape[0], device=padding_mask.device, dtype=torch.int32)
+                K.mask_lengths(padding_mask.contiguous().view(torch.uint8), out)
+                lengths = out.tolist()
+            else:
+                lengths = (~padding_mask).sum(-1).tolist()
+            return hubert_mask_lengths(lengths, Lmax, T)
+        lengths = _lengths_from_mask(padding_mask)  # wav2vec2: rule M1, only if mask.any()
+        return None if lengths is None else conv_out_lengths(lengths, self._conv_layers)
+
+    @torch.no_grad()
+    def extract_features(self, source, padding_mask=None, mask=None, out_buf=None):
+        dev = self.post_extract_proj.weight.device
+        source = source.to(dev, non_blocking=True).float().contiguous()
+        P, W = self.engine_state()
+        T = E.conv_frames(source.shape[1], self._conv_layers)[-1]
+        valid = self.frame_valid(padding_mask, source.shape[1], T)
+        layers, feats = E.teacher_forward(P, W, self._geom, source, valid, out_buf=out_buf)
+        return layers, feats, valid
+
+
+class TeacherWrapper(nn.Module):
+    """Same contract as reference utils/utils.py:51-99: extract_features(source, padding_mask) ->
+    {'layer_results': [(x [T,B,C], (None, None))] * n_layers, 'x': [B,T,C], 'features': [post_extract_proj out]}."""
+
+    def __init__(self, model: TeacherModel):
+        super().__init__()
+        self.model = model
+
+    def extract_features(self, source, padding_mask=None, out_buf=None):
+        layers, feats, valid = self.model.extract_features(source, padding_mask, out_buf=out_buf)
+        res = {
+            "layer_results": [(layers[i].transpose(0, 1), (None, None)) for i in range(layers.shape[0])],
+            "x": layers[-1],
+            "features": [feats],
+        }
+        res["_stacked"] = layers  # [n_layers, B, T, C] bf16, the fused loss kernel's target operand
+        res["_valid"] = valid
+        return res
+
+
+def freeze_model(model: nn.Module):
+    for p in model.parameters():
+        p.requires_grad = False

@@ -65,6 +65,7 @@ typedef struct {
   /* TMA coordinates: c0 += ob_lo*lo_c0 ; c2 = ob_hi*hi_c2 + ob_lo*lo_c2 + cb*cb_c2          */
   int32_t a_lo_c0, a_hi_c2, a_lo_c2, a_cb_c2;
   int32_t b_lo_c0, b_hi_c2, b_lo_c2, b_cb_c2;
+  int32_t a_c1_off, b_c1_off; /* added to the contraction-row coordinate of MN-major operands */
   void* d;
   int64_t d_ld, d_hi_stride, d_lo_stride; /* elements */
   int32_t flags;
@@ -81,6 +82,144 @@ typedef struct {
 } fhb_gemm_args;
 
 int fhb_gemm(const fhb_gemm_args* args, fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ conv0 + GroupNorm + GELU (K1)
+ * out[b][t][c] = gelu( GN_c( sum_j w[c][j] * wave[b][5t+j] ) ),  GroupNorm with C groups over all T0
+ * frames (zero padding included).  Replaces modules/module.py:46,65-71 (layer 0 of
+ * ConvFeatureExtractionModel: nn.Conv1d -> Fp32GroupNorm(dim, dim) -> nn.GELU), teacher and student.
+ * fwd writes stat/mean/rstd (needed by bwd).  bwd produces dweight/dgamma/dbeta only (the waveform
+ * has no gradient, SURVEY App. F backward inventory). */
+typedef struct {
+  const float* wave;      /* [B][wave_ld] fp32, zero padded                                   */
+  int64_t wave_ld;
+  int32_t B, L, C, T0, kernel, stride;
+  float eps;
+  const float* weight;    /* [C][kernel] fp32                                                  */
+  const float* gamma;     /* [C]                                                               */
+  const float* beta;      /* [C]                                                               */
+  double* stat;           /* [B][65] workspace: S_j and packed R_jj' (fwd writes, bwd reads)   */
+  float* mean;            /* [B][C]                                                            */
+  float* rstd;            /* [B][C]                                                            */
+  void* out;              /* fwd: bf16 [B][T0][C]                                              */
+  const void* dy;         /* bwd: bf16 [B][T0][C]                                              */
+  float* acc;             /* bwd workspace [B][C][12]                                          */
+  float* dweight;         /* bwd: [C][kernel]                                                  */
+  float* dgamma;          /* bwd: [C]                                                          */
+  float* dbeta;           /* bwd: [C]                                                          */
+  int32_t accumulate;     /* bwd: add into dweight/dgamma/dbeta instead of overwriting         */
+} fhb_conv0_args;
+int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* args, fhb_stream_t stream);
+int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* args, fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ LayerNorm (K3)
+ * y = LN(x) * gamma + beta over the last dim C (eps 1e-5), rows = everything else; bf16 in/out, fp32
+ * statistics.  Replaces nn.LayerNorm at modules/model.py:446-447 and modules/module.py:251,281,513,
+ * 518,569,580.  fwd optionally saves mean/rstd; bwd: dx (bf16, optionally + dres), dgamma/dbeta
+ * (fp32, atomically ACCUMULATED: zero them first). */
+int fhb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      int64_t rows, int32_t C, float eps, fhb_stream_t stream);
+int fhb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                      fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ positional conv (K5) helpers
+ * The grouped Conv1d(k=128, pad=64, groups=16) of modules/module.py:186-200,276-278 runs as a batched
+ * fhb_gemm over a group-major, time-padded copy of x.  These kernels do the layout work around it:
+ *  pack:    xg[b][g][t+pad][cp] = (t < valid[b]) ? x[b][t][g*cg + c] : 0   (zeroes padded frames =
+ *           index_put at :273-274; cp = cg rounded up to 16; borders and channel padding zero)
+ *  wn_prep: w = g * v / ||v||_(0,1) (weight_norm dim=2, :199) -> bf16 [G][cp_out][k*cp_in]
+ *  finish:  h = xz + gelu(conv[..][:cg]) ; y = LN(h)  (SamePad + GELU + residual :276-278, LN :280-281)
+ * and their backward counterparts. */
+int fhb_posconv_pack(const void* x, const int32_t* valid, void* xg, int32_t B, int32_t T, int32_t C, int32_t G,
+                     int32_t cp, int32_t pad_l, int32_t Tp, fhb_stream_t stream);
+int fhb_posconv_wn_prep(const float* v, const float* g, void* w_out, float* inv_norm, int32_t C, int32_t G,
+                        int32_t K, int32_t cp, int32_t flip_transpose, fhb_stream_t stream);
+int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const void* conv, const float* bias,
+                           const float* gamma, const float* beta, void* h_out, void* y, float* mean, float* rstd,
+                           int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps, fhb_stream_t stream);
+/* dh = LN-bwd(dy) and dcg[b][g][t+pad_l][cp] = dh * gelu'(conv + bias) (group-major, time-padded: the
+ * A operand of the dgrad GEMM and the B operand of the wgrad GEMM) in one pass; dgamma/dbeta/dbias are
+ * ACCUMULATED atomically. */
+int fhb_posconv_finish_bwd(const void* dy, const void* h, const void* conv, const float* bias, const float* gamma,
+                           const float* mean, const float* rstd, void* dh, void* dcg, float* dgamma, float* dbeta,
+                           float* dbias, int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, int32_t pad_l,
+                           int32_t Tp, fhb_stream_t stream);
+/* dx[b][t][c] = (t < valid[b]) ? dh[b][t][c] + dxc[b][t][g][c'] : 0   (dxc = dgrad GEMM output) */
+int fhb_posconv_unpack_bwd(const void* dh, const void* dxc, const int32_t* valid, void* dx, int32_t B, int32_t T,
+                           int32_t C, int32_t G, int32_t cp, fhb_stream_t stream);
+/* dv, dg from dwt (fp32 [G][K*cp][cp], the wgrad GEMM output: dW[g*cg+co][ci][j] = dwt[g][j*cp+ci][co]) */
+int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, const float* inv_norm, float* dv,
+                       float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate,
+                       fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ masked attention (K7)
+ * o = softmax(scale * q k^T + keymask) v per (sample, head); replaces fairseq MultiheadAttention's
+ * bmm -> masked_fill(-inf) -> fp32 softmax -> bmm chain reached from modules/module.py:558-564.
+ * qkv: bf16 [B][T][3*H*d] (q | k | v column blocks, as written by the fused QKV GEMM); keys at
+ * t >= valid[b] are masked; padded QUERY rows are still computed.  lse: fp32 [B][H][T].
+ * d in {40 (student), 64 (teacher)} plus any multiple of 8 <= 64. */
+int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
+                 int32_t d, float scale, fhb_stream_t stream);
+int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const void* dout, const float* lse,
+                 void* dqkv, float* delta_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
+                 fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ distillation loss + gradient (K10)
+ * loss_l = w_l * mean_{b,t,d} (pred_l - tgt_l)^2 ; dpred_l = 2 w_l (pred_l - tgt_l) / (B*T'*D)
+ * Replaces train.py:250-267 (two torch.stack copies), :282-293 (mse, weighting, mean).  pred: bf16
+ * [n_layers][B][Tp][D] (Tp = T' frames); tgt: bf16 [n_layers][B][Tt][D] with Tt >= Tp (narrow, :282).
+ * layer_loss (fp32 [n_layers]) is ACCUMULATED: zero it first.  dpred may alias pred. */
+int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const float* weights, float* layer_loss,
+                             void* dpred, int32_t n_layers, int32_t B, int32_t Tp, int32_t Tt, int32_t D,
+                             int32_t loss_type /*0 mse, 1 l1*/, float grad_scale, fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ fused AdamW (K11)
+ * ONE launch over a device-resident table of tensors.  Replaces s3prl get_optimizer ->
+ * Lamb(adam=True, correct_bias=True) reached from train.py:416-420 (mode 0; source
+ * not available here: "parity unpinned") or torch.optim.AdamW semantics (mode 1).  Gradients are read
+ * through a 3-D stride so they may stay in the layout the wgrad GEMM produced them in
+ * (p is contiguous [dim0][dim1][dim2]; g index = i0*gstride0 + i1*gstride1 + i2*gstride2).
+ * Entries with g == NULL are skipped (the reference skips parameters whose .grad is None). */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+  int64_t dim[3];
+  int64_t gstride[3];
+} fhb_adamw_tensor;
+int fhb_adamw_multi(const fhb_adamw_tensor* table_dev, int32_t n_tensors, int64_t max_n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, int32_t mode, float grad_scale,
+                    fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ weight preparation
+ * ONE launch: dst (contiguous [dim0][dim1][dim2], bf16 or fp32) = src_fp32[i0*s0 + i1*s1 + i2*s2].
+ * Produces the bf16 GEMM-layout shadows of the fp32 master parameters (conv weights tap-major,
+ * ConvTranspose weights as [2*Cout][Cin], fused q|k|v) and, with dst_is_f32, strided fp32 copies
+ * (concatenated biases; gradients exported back to parameter layout, optionally accumulated). */
+typedef struct {
+  const float* src;
+  void* dst;
+  int64_t dim[3];
+  int64_t sstride[3];
+  int32_t dst_is_f32;
+  int32_t accumulate;
+} fhb_prep_tensor;
+int fhb_prep_multi(const fhb_prep_tensor* table_dev, int32_t n_tensors, int64_t max_n, fhb_stream_t stream);
+
+/* ------------------------------------------------------------------ small helpers */
+/* out[c] += sum_rows x[row][c]   (bias gradients); x bf16 [rows][ld], out fp32 accumulated atomically */
+int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, float* out, fhb_stream_t stream);
+/* y = a + b (bf16, n % 8 == 0), used where two gradient streams meet */
+int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t stream);
+/* out = dy * gelu'(u) over B segments of n bf16 elements (independent batch strides); the one place a
+ * GELU derivative is not a GEMM epilogue: LayerNorm(512)-backward -> last conv layer (module.py:73) */
+int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_bstride, void* out,
+                  int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
+/* lengths[b] = #(mask[b][:] == 0); mask is the reference's bool padding mask (True = pad),
+ * utils/dataset.py:63-74 / fithubert/expert.py:60-63; first step of modules/model.py:453 */
+int fhb_mask_lengths(const uint8_t* mask, int32_t B, int64_t L, int32_t* lengths, fhb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ import fhb_oracle as O  # noqa: E402
 
 TINY_STUDENT = dict(
     conv_feature_layers="[(16, 10, 5)] + [(32, 1, 1)] + [(32, 3, 2)] * 4 + [(64, 1, 1)] + [(64, 2, 2)] * 2",
-    encoder_layers=3, encoder_embed_dim=48, encoder_ffn_embed_dim=48, encoder_attention_heads=4,
+    encoder_layers=3, encoder_embed_dim=96, encoder_ffn_embed_dim=96, encoder_attention_heads=4,
     conv_pos=16, conv_pos_groups=4, pred_head_final_dim=64,
 )
 TINY_TEACHER = dict(
