@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py - FitHuBERT distillation-step throughput (audio-seconds / second) on B200.
+
+Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]
+One "step" = one full distillation step over one batch of synthetic 16 kHz waveforms:
+frozen HuBERT-Base teacher forward + student forward/backward + layer-wise loss + gradient
+all-reduce (N > 1) + fused AdamW.  Workload at every N: cfg-2 of BASELINE.json per GPU
+(32 x 15.6 s, LibriSpeech-bucket lengths, random-init teacher/student), i.e. weak scaling
+(global batch 32*N; at N = 8 this is BASELINE configs[2]'s global batch 256).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+CFG2 = dict(B=32, Lmax=249600)
+# algorithmic FLOPs per step / per audio-second: SURVEY 8d (408.0 GFLOP per 15.6 s utterance)
+FLOP_PER_UTT = 408.01e9
+
+
+def yaml_cfg():
+    """data/conf/fithubert.yaml of the reference, restated (the file itself is not on the GPU box)."""
+    return {
+        "teacher": {"teacher_model": "hubert_base_ls960.pt"},
+        "train": dict(num_epochs=100, gpus=1, batch_size=32, accumulate_grad_batches=1, use_fp16=True,
+                      monitor_losses=True, cnn_loss_weight=0, rec_loss_weight=1.0, rec_loss_type="mse",
+                      sim_loss_weight=0, attn_loss_weight=0, attn_loss_type="kldiv", v_rel_loss_weight=0,
+                      distil_random_layer=11, random_layer_weight=0.1, delete_projections=False, specaug=False),
+        "distiller": dict(
+            extractor_mode="default",
+            conv_feature_layers="[(128, 10, 5)] + [(256, 1, 1)] + [(256, 3, 2)] * 4 + [(512, 1, 1)] + [(512, 2, 2)] * 2",
+            feature_grad_mult=1.0, conv_bias=False, n_mels=0, enable_log_mel=False, conv_pos=128, conv_pos_groups=16,
+            pos_conv_depth=1, max_positions=100000, layer_type="transformer", encoder_layers=12, encoder_embed_dim=480,
+            encoder_ffn_embed_dim=480, encoder_attention_heads=12, activation_fn="gelu", layer_norm_first=False,
+            dropout=0.1, attention_dropout=0.1, activation_dropout=0.1, encoder_layerdrop=0.0, dropout_input=0.05,
+            final_dim=256, pred_head_final_dim=768, pred_head_inter_dim=0, layerwise_proj=True, pred_layer_id="[11]",
+            init_conv_layers=False, init_encoder_layers=0, enable_tr_layer=True, tr_conv1d_kernel=2, tr_layer_index=0,
+            tr_reduce_factor=2, tr_layer_type="conv1d", checkpoint_activations=False, required_seq_len_multiple=1,
+            crop_seq_to_multiple=1),
+        "optimizer": dict(name="AdamW_with_schedule", lr=5.e-4, warmup_proportion=0.05, betas=[0.9, 0.98], eps=1.e-6,
+                          weight_decay=1.e-6),
+    }
+
+
+def synth_lengths(B, Lmax, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    lens = Lmax - torch.randint(0, 8001, (B,), generator=g)
+    lens[0] = Lmax
+    return sorted(lens.tolist(), reverse=True)
+
+
+def synth_batch(B, Lmax, seed, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    lengths = synth_lengths(B, Lmax, seed)
+    x = 0.1 * torch.randn(B, Lmax, generator=g)
+    pm = ~(torch.arange(Lmax).unsqueeze(0) < torch.tensor(lengths).unsqueeze(1))
+    x.masked_fill_(pm, 0.0)
+    if pin:
+        x, pm = x.pin_memory(), pm.pin_memory()
+    return x, pm, lengths
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [s.strip() for s in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_fn(n_utts, Lmax, seed=1234):
+    """The reference's algorithm for this path, restated (oracle/fhb_oracle.py), fp32 on the host cores:
+    teacher fwd + student fwd/bwd + loss + AdamW for `n_utts` utterances of the cfg-2 length distribution."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fhb_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    scfg, tcfg = O.student_config(), O.teacher_config()
+    ssd = {k: v.requires_grad_(k not in ("upsampler.weight", "upsampler.bias")) for k, v in O.init_student_state(scfg, 0).items()}
+    tsd = O.init_teacher_state(tcfg, 1)
+    lengths = synth_lengths(CFG2["B"], Lmax, seed)[:n_utts]
+    lengths[0] = Lmax
+    x, pm = O.synth_batch(n_utts, Lmax, lengths, seed)
+    w = O.layer_weights(12, 0.1)
+    m = {k: torch.zeros_like(v) for k, v in ssd.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in ssd.items()}
+    state = {"step": 0}
+
+    def step():
+        with torch.no_grad():
+            t = O.teacher_forward(tsd, tcfg, x, pm)
+        s = O.student_forward(ssd, scfg, x, pm)
+        loss, _ = O.distill_loss(s["projections"], t["layer_results"], w)
+        loss.backward()
+        state["step"] += 1
+        with torch.no_grad():
+            for k, p in ssd.items():
+                if p.grad is None:
+                    continue
+                O.adamw_step(p, p.grad, m[k], v2[k], state["step"], 5e-4)
+                p.grad = None
+        return float(loss)
+
+    return step, sum(lengths) / SR, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_utts = 2
+    step, audio_s, cores = cpu_reference_step_fn(n_utts, CFG2["Lmax"])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = audio_s * args.steps / dt
+    sample = f"{n_utts} of the 32 cfg-2 utterances (15.6 s each) per step, fp32, {args.warmup} warm-up + {args.steps} timed full steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "distill-step audio-sec/sec", "value": val, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg-2: FitHuBERT distillation step, 32 x 15.6 s per GPU (bounded CPU sample)",
+                   "per_gpu_batch": 32, "utterance_s": 15.6},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fhb")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="2 device steps then exit (for ncu launch lists)")
+    ap.add_argument("--batch", type=int, default=CFG2["B"])
+    ap.add_argument("--lmax", type=int, default=CFG2["Lmax"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the FitHuBERT hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import fithubert_b200 as F
+    from fithubert_b200 import kernels as K
+
+    torch.manual_seed(0)
+    cfg = yaml_cfg()
+    cfg["train"]["batch_size"] = args.batch
+    step_obj = F.W2V2Distil(cfg, device=dev)
+    step_obj.configure_optimizers(total_steps=1000)
+    B, Lmax = args.batch, args.lmax
+    x_host, pm_host, lengths = synth_batch(B, Lmax, 1234 + rank, pin=True)
+    x_dev = x_host.to(dev)
+    audio_s = sum(lengths) / SR
+
+    def dev_step():
+        step_obj.optimizer.zero_grad()
+        ll = step_obj.fused_forward_backward(x_dev, None, lengths, grad_scale=1.0)
+        step_obj.optimizer_step()
+        return ll
+
+    def e2e_step():
+        loss = step_obj.training_step({"x": x_host, "padding_mask": pm_host})
+        return float(loss.detach())  # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.profile:
+        for _ in range(2):
+            dev_step()
+        torch.cuda.synchronize()
+        return
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.reset_counters()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(args.steps):
+        ll = dev_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = K.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(ll.sum())
+
+    # ---- same steps again with a CUDA-event pair around every GEMM launch: live kernel time + flops
+    K.enable_gemm_timing(True)
+    for _ in range(args.steps):
+        dev_step()
+    torch.cuda.synchronize()
+    gemm_ms, gemm_flops, gemm_calls = K.gemm_timing_summary()
+    K.enable_gemm_timing(False)
+
+    # ---- end to end through the public API with host buffers
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_src = "measured (MEASURED_PEAKS.json, bf16_tflops_sustained)"
+        peak = float(peaks["bf16_tflops_sustained"])
+    except (OSError, KeyError, ValueError):
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    value = audio_s * world * args.steps / (ms / 1e3)
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    out = {
+        "metric": "distill-step audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"cfg-2: FitHuBERT distillation step (HuBERT-Base teacher fwd + student fwd/bwd + "
+                               f"loss + allreduce + AdamW), {B} x {Lmax / SR:.1f} s per GPU, random-init weights",
+                   "per_gpu_batch": B, "global_batch": B * world, "utterance_s": Lmax / SR,
+                   "l2": "per-step working set is several GB (>> 126 MB L2); no explicit flush",
+                   "step_tflops_algorithmic": FLOP_PER_UTT * B * (Lmax / CFG2["Lmax"]) / 1e12},
+        "clocks": clocks,
+        "e2e": {"value": audio_s * world * args.steps / (e2e_ms / 1e3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": x_host.numel() * 4 + 4 * B, "d2h_bytes_per_step": 4,
+                "api": "W2V2Distil.training_step({'x','padding_mask'}) with pinned host tensors"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "fhb_gemm_kernel (tcgen05, all variants)", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": peak_src, "launches_per_step": gemm_calls / max(1, args.steps),
+                     "gemm_ms_per_step": gemm_ms / args.steps,
+                     "step_frac": (FLOP_PER_UTT * B * (Lmax / CFG2["Lmax"]) / (ms / args.steps / 1e3) / 1e12) / peak},
+        "loss": loss_val,
+    }
+    if not args.no_cpu_baseline:
+        n_utts = 2
+        stepf, a_s, cores = cpu_reference_step_fn(n_utts, Lmax)
+        stepf()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            stepf()
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": a_s * n / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                               "sample": f"{n_utts} of the {B} utterances ({Lmax / SR:.1f} s each), fp32 oracle, "
+                                         f"1 warm-up + {n} timed full steps"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

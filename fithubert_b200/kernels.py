@@ -18,6 +18,23 @@ def _cuda(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+_GEMM_TIMING = {"on": False, "events": []}
+reset_counters = L.reset_counters
+launch_count = L.launch_count
+
+
+def enable_gemm_timing(on: bool) -> None:
+    _GEMM_TIMING["on"] = on
+    _GEMM_TIMING["events"] = []
+
+
+def gemm_timing_summary():
+    """(total ms, total algorithmic flops, launches) of the fhb_gemm launches recorded since enable."""
+    torch.cuda.synchronize()
+    ev = _GEMM_TIMING["events"]
+    return sum(a.elapsed_time(b) for a, b, _ in ev), float(sum(f for _, _, f in ev)), len(ev)
+
+
 def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int, *, a_major=0, b_major=0,
              num_ob=1, ob_mod=1, num_cb=1, a_coord=(0, 0, 0, 0), b_coord=(0, 0, 0, 0),
              d_ld: int, d_hi_stride=0, d_lo_stride=0, flags=0, split_k=0, bias=None, residual=None,
@@ -44,6 +61,13 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
         # "laid out like D": same element offset as the output
         setattr(g, name, None if t is None else t.data_ptr() + d_offset_elems * t.element_size())
     g.loss_weight, g.grad_scale = loss_weight, grad_scale
+    if _GEMM_TIMING["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
+        e1.record()
+        _GEMM_TIMING["events"].append((e0, e1, 2.0 * m * n * k * max(1, num_ob) * max(1, num_cb)))
+        return
     L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
 
 

@@ -104,7 +104,21 @@ EXPORTS = [
 ]
 
 
+CALLS: dict = {}
+_KERNELS_PER_CALL = {"fhb_conv0_gn_gelu_fwd": 3, "fhb_conv0_gn_gelu_bwd": 2, "fhb_attn_bwd": 3}
+
+
+def reset_counters() -> None:
+    CALLS.clear()
+
+
+def launch_count() -> int:
+    """Kernels of libfhb_sm100a.so launched since reset_counters() (memsets not counted)."""
+    return sum(n * _KERNELS_PER_CALL.get(k, 1) for k, n in CALLS.items())
+
+
 def check(rc: int, what: str) -> None:
+    CALLS[what] = CALLS.get(what, 0) + 1
     if rc != 0:
         raise FhbError(f"{what} failed (rc={rc}): {lib().fhb_last_error().decode()}")
 
