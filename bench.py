@@ -102,8 +102,10 @@ class ClockSampler:
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
                 mx = float(f[2])
+                if float(f[3]) < 300.0:  # idle sample (before / after the timed region)
+                    continue
+                sm.append(float(f[1]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
@@ -237,12 +239,13 @@ def main():
             dev_step()
         torch.cuda.synchronize()
         return
+    sampler = ClockSampler(local)
     for _ in range(max(args.warmup, 3)):
         dev_step()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # let nvidia-smi come up; the rows kept are those taken under load (see stop())
     K.reset_counters()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()

@@ -1,15 +1,21 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma
-// (UMMA M=128, N<=256, K=16, accumulators in TMEM, double buffered) -> tcgen05.ld -> fused epilogue.
+// (UMMA M=128, N<=256, K=16, accumulators in TMEM, double buffered) -> tcgen05.ld -> fused epilogue
+// -> 128B-swizzled smem slab -> TMA store (TMA reduce-add for split-K).
 //
-// One CTA per SM, 192 threads:
-//   warps 0-3  epilogue (warp w owns TMEM lanes 32w..32w+31 = tile rows)
-//   warp  4    TMA producer (one elected lane)
-//   warp  5    MMA issuer (one elected lane) + TMEM allocation
+// One CTA per SM, 320 threads:
+//   warps 0-7  epilogue: warp w owns TMEM lanes 32(w%4)..+31 (= tile rows) and column half (w/4) of
+//              every 128-byte output slab
+//   warp  8    TMA producer (one elected lane)
+//   warp  9    MMA issuer (one elected lane) + TMEM allocation
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile schedule (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs of one wave
 // share the A tile in L2).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "fhb_common.cuh"
 
@@ -20,11 +26,15 @@ constexpr int kBK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int kMaxBN = 256;
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 64;
 constexpr uint32_t kABytes = kBM * kBK * 2;     // 16 KiB
 constexpr uint32_t kBBytes = kMaxBN * kBK * 2;  // 32 KiB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kThreads = 192;
+constexpr uint32_t kStoreBytes = kBM * 128;  // one output slab: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
+constexpr uint32_t kBiasBytes = 2 * kMaxBN * 4;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 2 * kStoreBytes + kBiasBytes + 128 /*barriers*/;
 
 struct GemmParams {
   int m, n, k, bn;
@@ -46,6 +56,7 @@ struct GemmParams {
   int flags;
   uint32_t stage_tx_bytes;
   int total_tiles;
+  int use_tma_store;
 };
 
 struct Tile {
@@ -69,15 +80,18 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
   return t;
 }
 
-template <int A_MN, int B_MN>
+// EPI_IN = 1: the epilogue may read [m][n] operands from global memory (residual / gelu' input / loss target)
+template <int A_MN, int B_MN, int EPI_IN>
 __global__ void __launch_bounds__(kThreads, 1)
 fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_aux,
                 const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* smem_out = smem + kStages * kStageBytes;  // 2 x 16 KiB staging for TMA stores
+  float* bias_s = reinterpret_cast<float*>(smem_out + 2 * kStoreBytes);  // [2][kMaxBN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 2 * kStoreBytes + kBiasBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
@@ -87,26 +101,28 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();  // 128B-swizzle atoms need a 1024-byte aligned base
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_d);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], kEpiThreads);
     }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
@@ -145,7 +161,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)p.bn, A_MN, B_MN);
@@ -184,36 +200,48 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0-3)
+    // ------------------------------------------------------------ epilogue (warps 0-7)
     const int flags = p.flags;
+    const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
+    const bool two_out = (flags & FHB_EPI_STORE_PREACT) != 0;
+    const int slab_cols = out_f32 ? 32 : 64;       // columns per 128-byte slab
+    const int my_cols = slab_cols >> 1;            // this warp's half of the slab: 16 (fp32) or 32 (bf16)
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t rsw = (uint32_t)(row_in_tile & 7);
+    const uint32_t out_u32 = smem_u32(smem_out);
     int it = 0;
+    uint32_t slab_ctr = 0;
     float loss_local = 0.f;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const Tile t = decode_tile(p, tile);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      // stage this tile's bias slice (double buffered by tile parity; the slab barriers order it)
+      float* bs = bias_s + as * kMaxBN;
+      if (flags & FHB_EPI_BIAS) {
+        const int c = threadIdx.x;
+        if (c < p.bn) bs[c] = (t.n0 + c < p.n) ? __ldg(p.bias + t.n0 + c) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      const int row = t.m0 + warp * 32 + lane;
+      const int row = t.m0 + row_in_tile;
       const bool row_ok = row < p.m;
       bool zero_row = false;
       if ((flags & FHB_EPI_ROWZERO) && row_ok) zero_row = row >= p.row_valid[t.ob_hi];
       const long long off = (long long)t.ob_hi * p.d_hi_stride + (long long)t.ob_lo * p.d_lo_stride +
                             (long long)row * p.d_ld + t.n0;
-      const uint32_t taddr = tmem_base + as * kMaxBN + ((uint32_t)(warp * 32) << 16);
-      for (int c = 0; c < p.bn; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      const uint32_t taddr = tmem_base + as * kMaxBN + ((uint32_t)(quarter * 32) << 16);
+      const int n_slabs = p.use_tma_store ? p.bn / slab_cols : 0;
+
+      // fused epilogue math on 16 consecutive columns starting at tile column c
+      auto math16 = [&](float* v, float* pre, int c) {
         if (flags & FHB_EPI_BIAS) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + t.n0 + c);
+          const float4* bp = reinterpret_cast<const float4*>(bs + c);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b4 = __ldg(bp + j);
+            const float4 b4 = bp[j];
             v[4 * j] += b4.x;
             v[4 * j + 1] += b4.y;
             v[4 * j + 2] += b4.z;
@@ -221,55 +249,139 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         if (flags & FHB_EPI_STORE_PREACT) {
-          uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off + c);
-          ap[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          ap[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                             pack_bf16(v[14], v[15]));
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pre[j] = v[j];
         }
         if (flags & FHB_EPI_GELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (flags & FHB_EPI_MUL_DGELU) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + off + c);
-          const uint4 u0 = __ldg(ap), u1 = __ldg(ap + 1);
-          const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        if (EPI_IN && row_ok) {
+          if (flags & FHB_EPI_MUL_DGELU) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + off + c);
+            const uint4 u0 = __ldg(ap), u1 = __ldg(ap + 1);
+            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16(uu[j]);
-            v[2 * j] *= gelu_erf_grad(f.x);
-            v[2 * j + 1] *= gelu_erf_grad(f.y);
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack_bf16(uu[j]);
+              v[2 * j] *= gelu_erf_grad(f.x);
+              v[2 * j + 1] *= gelu_erf_grad(f.y);
+            }
           }
-        }
-        if (flags & FHB_EPI_RESIDUAL) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
-          const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-          const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          if (flags & FHB_EPI_RESIDUAL) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+            const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16(uu[j]);
-            v[2 * j] += f.x;
-            v[2 * j + 1] += f.y;
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack_bf16(uu[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
           }
-        }
-        if (flags & FHB_EPI_SQDIFF) {
-          const uint4* tp = reinterpret_cast<const uint4*>(p.loss_target + off + c);
-          const uint4 u0 = __ldg(tp), u1 = __ldg(tp + 1);
-          const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          if (flags & FHB_EPI_SQDIFF) {
+            const uint4* tp = reinterpret_cast<const uint4*>(p.loss_target + off + c);
+            const uint4 u0 = __ldg(tp), u1 = __ldg(tp + 1);
+            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16(uu[j]);
-            const float d0 = v[2 * j] - f.x, d1 = v[2 * j + 1] - f.y;
-            loss_local += d0 * d0 + d1 * d1;
-            v[2 * j] = d0 * p.grad_scale;
-            v[2 * j + 1] = d1 * p.grad_scale;
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack_bf16(uu[j]);
+              const float d0 = v[2 * j] - f.x, d1 = v[2 * j + 1] - f.y;
+              loss_local += d0 * d0 + d1 * d1;
+              v[2 * j] = d0 * p.grad_scale;
+              v[2 * j + 1] = d1 * p.grad_scale;
+            }
           }
         }
         if (zero_row) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
-        if (flags & FHB_EPI_OUT_F32) {
+      };
+
+      // ---- full 128-byte slabs through shared memory + TMA
+      for (int sidx = 0; sidx < n_slabs; ++sidx) {
+        const uint32_t dbuf = out_u32 + (two_out ? 0u : (slab_ctr & 1u) * kStoreBytes);
+        const uint32_t abuf = out_u32 + kStoreBytes;
+        // the buffer we are about to overwrite must have been drained by its previous TMA store
+        if (threadIdx.x == 0) {
+          if (two_out)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int c0 = sidx * slab_cols + half * my_cols;  // first tile column of this warp's share
+        uint32_t r[32];
+        tmem_ld16(taddr + c0, r);
+        if (!out_f32) tmem_ld16(taddr + c0 + 16, r + 16);
+        tmem_ld_wait();
+        const uint32_t drow = dbuf + row_in_tile * 128;
+        const uint32_t arow = abuf + row_in_tile * 128;
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+          if (gq == 1 && out_f32) break;
+          float v[16], pre[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[gq * 16 + j]);
+          math16(v, pre, c0 + gq * 16);
+          if (out_f32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 4 chunks of 4 floats; chunk index within the 128-byte row
+              const uint32_t ch = (uint32_t)(half * 4 + q);
+              st_shared_v4(drow + ((ch ^ rsw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                           __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {  // 2 chunks of 8 bf16
+              const uint32_t ch = (uint32_t)(half * 4 + gq * 2 + q);
+              st_shared_v4(drow + ((ch ^ rsw) << 4), pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+              if (two_out)
+                st_shared_v4(arow + ((ch ^ rsw) << 4), pack_bf16(pre[8 * q], pre[8 * q + 1]),
+                             pack_bf16(pre[8 * q + 2], pre[8 * q + 3]), pack_bf16(pre[8 * q + 4], pre[8 * q + 5]),
+                             pack_bf16(pre[8 * q + 6], pre[8 * q + 7]));
+            }
+          }
+        }
+        fence_async_shared();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+          const int cc = t.n0 + sidx * slab_cols;
+          if (flags & FHB_EPI_ATOMIC_ADD) {
+            asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm_d), "r"(dbuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm_d), "r"(dbuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
+          }
+          if (two_out)
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm_aux), "r"(abuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++slab_ctr;
+      }
+
+      // ---- remaining columns (bn not a multiple of the slab width, or TMA store disabled): direct stores,
+      //      16-column groups dealt round-robin to the two warps of a lane quarter
+      for (int c = n_slabs * slab_cols + half * 16; c < p.bn; c += 32) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        float v[16], pre[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        math16(v, pre, c);
+        if (!row_ok || t.n0 + c >= p.n) continue;
+        if (flags & FHB_EPI_STORE_PREACT) {
+          uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off + c);
+          ap[0] = make_uint4(pack_bf16(pre[0], pre[1]), pack_bf16(pre[2], pre[3]), pack_bf16(pre[4], pre[5]), pack_bf16(pre[6], pre[7]));
+          ap[1] = make_uint4(pack_bf16(pre[8], pre[9]), pack_bf16(pre[10], pre[11]), pack_bf16(pre[12], pre[13]),
+                             pack_bf16(pre[14], pre[15]));
+        }
+        if (out_f32) {
           float* dp = reinterpret_cast<float*>(p.d) + off + c;
           if (flags & FHB_EPI_ATOMIC_ADD) {
 #pragma unroll
@@ -289,7 +401,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
-    if (flags & FHB_EPI_SQDIFF) {
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (EPI_IN && (flags & FHB_EPI_SQDIFF)) {
       loss_local = warp_sum(loss_local);
       if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_acc, loss_local * p.loss_weight);
     }
@@ -297,7 +410,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -320,7 +433,48 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs several microseconds of driver time; a training step issues the same few
+// hundred (pointer, shape) combinations every iteration (the caching allocator returns the same blocks), so
+// encoded maps are memoised.  Key = every input of the encode call.
+struct TmapKey {
+  const void* ptr;
+  long long d[4];
+  long long s[3];
+  unsigned box0, box1, kind;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&k);
+    unsigned long long h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmap_cache.find(k);
+  if (it == g_tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+void tmap_insert(const TmapKey& k, const CUtensorMap& v) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+  g_tmap_cache.emplace(k, v);
+}
+
 int make_tmap(CUtensorMap* tm, const fhb_tensor3& t, uint32_t box0, uint32_t box1, const char* name) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = t.ptr;
+  key.d[0] = t.dim[0]; key.d[1] = t.dim[1]; key.d[2] = t.dim[2];
+  key.s[0] = t.stride[0]; key.s[1] = t.stride[1];
+  key.box0 = box0; key.box1 = box1; key.kind = 1;
+  if (tmap_lookup(key, tm)) return 0;
   EncodeTiledFn enc = get_encode_fn();
   FHB_ARG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   FHB_ARG_CHECK(t.ptr != nullptr && (reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0, "gemm: %s pointer must be 16B aligned", name);
@@ -341,6 +495,34 @@ int make_tmap(CUtensorMap* tm, const fhb_tensor3& t, uint32_t box0, uint32_t box
   FHB_ARG_CHECK(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %lld,%lld,%lld strides %lld,%lld box %u,%u)",
                 name, (int)r, (long long)t.dim[0], (long long)t.dim[1], (long long)t.dim[2], (long long)t.stride[0],
                 (long long)s2, box0, box1);
+  tmap_insert(key, *tm);
+  return 0;
+}
+
+// Output tensor map: {columns, rows, ob_lo, ob_hi}; box = one 128-byte slab x 128 rows, 128B swizzle.
+int make_out_tmap(CUtensorMap* tm, void* base, bool f32, int n, int m, int ob_mod, int n_hi, long long ld,
+                  long long lo_stride, long long hi_stride, const char* name) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = base;
+  key.d[0] = n; key.d[1] = m; key.d[2] = ob_mod; key.d[3] = n_hi;
+  key.s[0] = ld; key.s[1] = lo_stride; key.s[2] = hi_stride;
+  key.kind = f32 ? 3 : 2;
+  if (tmap_lookup(key, tm)) return 0;
+  EncodeTiledFn enc = get_encode_fn();
+  FHB_ARG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const int elt = f32 ? 4 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)m, (cuuint64_t)ob_mod, (cuuint64_t)n_hi};
+  long long s1 = ld, s2 = lo_stride > 0 ? lo_stride : ld * m, s3 = hi_stride > 0 ? hi_stride : s2 * ob_mod;
+  cuuint64_t strides[3] = {(cuuint64_t)s1 * elt, (cuuint64_t)s2 * elt, (cuuint64_t)s3 * elt};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / elt), (cuuint32_t)kBM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FHB_ARG_CHECK(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d (n=%d m=%d ld=%lld lo=%lld hi=%lld)",
+                name, (int)r, n, m, ld, s2, s3);
+  tmap_insert(key, *tm);
   return 0;
 }
 
@@ -351,17 +533,26 @@ int pick_bn(int n) {
   return bn;
 }
 
-template <int A_MN, int B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+template <int A_MN, int B_MN, int EPI_IN>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
+            const GemmParams& p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytes));
     attr_set = true;
   }
   const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
-  fhb_gemm_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, p);
+  fhb_gemm_kernel<A_MN, B_MN, EPI_IN><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, tx, p);
   FHB_LAUNCH_CHECK();
   return 0;
+}
+
+template <int A_MN, int B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
+           const GemmParams& p, cudaStream_t s) {
+  if (p.flags & (FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_SQDIFF)) return launch2<A_MN, B_MN, 1>(ta, tb, td, tx, p, s);
+  return launch2<A_MN, B_MN, 0>(ta, tb, td, tx, p, s);
 }
 
 }  // namespace
@@ -407,9 +598,9 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   const int base_tiles = p.num_m_blk * p.num_n_blk * num_ob;
   if (split <= 0) {
     split = 1;
-    if (flags & FHB_EPI_ATOMIC_ADD) {  // fill the machine when the output is small (wgrad)
-      split = (2 * fhb_num_sms() + base_tiles - 1) / base_tiles;
-      if (split > p.kb_total / 4) split = p.kb_total / 4;
+    if (flags & FHB_EPI_ATOMIC_ADD) {  // wgrad: small output, long contraction -> about one wave of work,
+      split = fhb_num_sms() / base_tiles;  // each split long enough (>= 8 k-blocks) to amortise its reduce-add
+      if (split > p.kb_total / 8) split = p.kb_total / 8;
       if (split < 1) split = 1;
     }
   }
@@ -449,8 +640,31 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
     if ((rc = make_tmap(&tb, a->b, 64, kBK, "B")) != 0) return rc;
     p.stage_tx_bytes = kABytes + (uint32_t)b_atoms * 64 * kBK * 2;
   }
+  // TMA store path: needs 16B-aligned strides (already checked) and every (ob_lo, ob_hi) offset expressible as
+  // a tensor-map stride; otherwise (or when FHB_GEMM_DIRECT_STORE is set) the epilogue stores directly.
+  CUtensorMap td, tx;
+  memset(&td, 0, sizeof(td));
+  memset(&tx, 0, sizeof(tx));
+  static const bool force_direct = getenv("FHB_GEMM_DIRECT_STORE") != nullptr;
+  p.use_tma_store = force_direct ? 0 : 1;
+  if (p.use_tma_store) {
+    const int n_hi = (num_ob + ob_mod - 1) / ob_mod;
+    if ((rc = make_out_tmap(&td, a->d, (flags & FHB_EPI_OUT_F32) != 0, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride,
+                            a->d_hi_stride, "D")) != 0)
+      return rc;
+    if (flags & FHB_EPI_STORE_PREACT) {
+      if ((rc = make_out_tmap(&tx, a->aux_out, false, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride, a->d_hi_stride,
+                              "aux_out")) != 0)
+        return rc;
+    } else {
+      tx = td;
+    }
+  } else {
+    td = ta;
+    tx = ta;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->a_major == 0 && a->b_major == 0) return launch<0, 0>(ta, tb, p, s);
-  if (a->a_major == 0 && a->b_major == 1) return launch<0, 1>(ta, tb, p, s);
-  return launch<1, 1>(ta, tb, p, s);
+  if (a->a_major == 0 && a->b_major == 0) return launch<0, 0>(ta, tb, td, tx, p, s);
+  if (a->a_major == 0 && a->b_major == 1) return launch<0, 1>(ta, tb, td, tx, p, s);
+  return launch<1, 1>(ta, tb, td, tx, p, s);
 }

@@ -106,26 +106,50 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* 
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients)
+// Warp per row (lanes stride over 16-byte column vectors: 512 contiguous bytes per warp load), rows dealt
+// round-robin to all warps of the grid; per-lane partial sums -> block smem -> one atomic per column/block.
+constexpr int kColsumMaxVec = 8;  // C <= 8 * 32 * 8 = 2048
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long long ld, int rows_per_block,
-              float* __restrict__ out) {
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(r0 + rows_per_block, rows);
-  for (int cv = threadIdx.x; cv < (C >> 3); cv += blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long long r = r0; r < r1; ++r) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ld + cv * 8));
-      const uint32_t a[4] = {u.x, u.y, u.z, u.w};
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out) {
+  extern __shared__ float csum[];  // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) csum[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float acc[kColsumMaxVec][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(a[j]);
-        acc[2 * j] += f.x;
-        acc[2 * j + 1] += f.y;
+  for (int i = 0; i < kColsumMaxVec; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const __nv_bfloat16* xr = x + r * ld;
+#pragma unroll
+    for (int i = 0; i < kColsumMaxVec; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + vi * 8));
+        const uint32_t a[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(a[j]);
+          acc[i][2 * j] += f.x;
+          acc[i][2 * j + 1] += f.y;
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + cv * 8 + j, acc[j]);
   }
+#pragma unroll
+  for (int i = 0; i < kColsumMaxVec; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&csum[vi * 8 + j], acc[i][j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, csum[i]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -235,11 +259,13 @@ extern "C" int fhb_prep_multi(const fhb_prep_tensor* table_dev, int32_t n_tensor
 }
 
 extern "C" int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, float* out, fhb_stream_t stream) {
-  FHB_ARG_CHECK(x && out && C % 8 == 0 && ld % 8 == 0, "colsum: bad arguments");
+  FHB_ARG_CHECK(x && out && C % 8 == 0 && ld % 8 == 0 && C <= kColsumMaxVec * 256, "colsum: bad arguments (C=%d)", C);
   if (rows == 0) return 0;
-  const int rpb = 64;
-  colsum_kernel<<<(unsigned)((rows + rpb - 1) / rpb), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), rows, C, ld, rpb, out);
+  long long blocks = (rows + 8 * 8 - 1) / (8 * 8);  // >= 8 rows per warp
+  if (blocks > fhb_num_sms()) blocks = fhb_num_sms();
+  if (blocks < 1) blocks = 1;
+  colsum_kernel<<<(unsigned)blocks, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), rows, C, ld, out);
   FHB_LAUNCH_CHECK();
   return 0;
 }
