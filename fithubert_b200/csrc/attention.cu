@@ -8,6 +8,8 @@
 // Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16) with ldmatrix-fed fragments, 64-query x
 // 64-key tiles, 4 warps per CTA.  Attention is ~8 % of the step's FLOPs; moving it to
 // tcgen05 with S/P in TMEM is the planned next step.
+#include <stdlib.h>
+
 #include "fhb_common.cuh"
 
 namespace {
@@ -432,13 +434,18 @@ int check_shape(int B, int T, int H, int d) {
   else if (DPV <= 48) { constexpr int DP = 48; CALL; } \
   else { constexpr int DP = 64; CALL; }
 
+int fhb_attn_fwd_tc64(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
+                      float scale, cudaStream_t s);  // attention_tc.cu (tcgen05 path, head_dim 64)
+
 extern "C" int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T,
                             int32_t H, int32_t d, float scale, fhb_stream_t stream) {
   int rc = check_shape(B, T, H, d);
   if (rc) return rc;
   FHB_ARG_CHECK(qkv && out, "attn_fwd: null pointer");
-  dim3 grid((T + kTile - 1) / kTile, H, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool no_tc = getenv("FHB_ATTN_NO_TC") != nullptr;
+  if (d == 64 && !no_tc) return fhb_attn_fwd_tc64(qkv, valid, out, lse, B, T, H, scale, s);
+  dim3 grid((T + kTile - 1) / kTile, H, B);
   FHB_ATTN_DISPATCH(d, (attn_fwd_kernel<DP><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), valid,
                                                                    static_cast<__nv_bfloat16*>(out), lse, T, H, d, scale)));
   FHB_LAUNCH_CHECK();

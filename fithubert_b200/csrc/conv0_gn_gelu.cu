@@ -271,8 +271,9 @@ extern "C" int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* a, fhb_stream_t strea
     FHB_LAUNCH_CHECK();
   }
   {
-    const int fpb = 64 * (256 / (a->C / 8)) / 4;  // 64 frames per thread-row group ... keeps ~16 frames/thread
-    const int frames = fpb < 16 ? 16 : fpb;
+    // 512 frames per block: the 80 weight registers / affine terms of a thread are amortised over
+    // 512 / (256 / (C/8)) frames, and the 10 KB waveform slice is staged once
+    const int frames = 512;
     dim3 grid((a->T0 + frames - 1) / frames, a->B);
     const size_t smem = sizeof(float) * (frames * kS + (kK - kS));
     conv0_fwd_kernel<8><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
@@ -289,8 +290,8 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
   FHB_ARG_CHECK(a->C % 4 == 0 && 256 % (a->C / 4) == 0, "conv0 bwd: C=%d must be 4*2^k, <= 1024", a->C);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   FHB_CUDA_CHECK(cudaMemsetAsync(a->acc, 0, sizeof(float) * kNAcc * a->B * a->C, s));
-  const int fy = 256 / (a->C / 4);
-  const int frames = fy * 32;
+  // 2048 frames per block: few blocks per (sample, channel) -> few global atomics per accumulator
+  const int frames = 2048;
   dim3 grid((a->T0 + frames - 1) / frames, a->B);
   const size_t smem = sizeof(float) * (frames * kS + (kK - kS) + a->C * kNAcc);
   conv0_bwd_kernel<4><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,

@@ -27,6 +27,10 @@ void fhb_set_error(const char* fmt, ...);
   } while (0)
 #define FHB_LAUNCH_CHECK() FHB_CUDA_CHECK(cudaGetLastError())
 
+// memoised cuTensorMapEncodeTiled for a 3-D bf16 tensor (dim[0] contiguous, strides in elements), 128B swizzle
+int fhb_make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, const int64_t dim[3], const int64_t stride[2],
+                          uint32_t box0, uint32_t box1, const char* name);
+
 static inline int fhb_num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -57,6 +57,7 @@ struct GemmParams {
   uint32_t stage_tx_bytes;
   int total_tiles;
   int use_tma_store;
+  int stages;  // smem pipeline depth: 4, or 3 when a second output needs its own staging buffers
 };
 
 struct Tile {
@@ -87,11 +88,13 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_aux,
                 const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int nstages = p.stages;
+  const int n_out_bufs = (kStages - nstages) * 3 + 2;  // 2 (4 stages) or 5 (3 stages); 4 are used
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* smem_out = smem + kStages * kStageBytes;  // 2 x 16 KiB staging for TMA stores
-  float* bias_s = reinterpret_cast<float*>(smem_out + 2 * kStoreBytes);  // [2][kMaxBN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 2 * kStoreBytes + kBiasBytes);
+  uint8_t* smem_b = smem + nstages * kABytes;
+  uint8_t* smem_out = smem + nstages * kStageBytes;  // 16 KiB staging buffers for TMA stores
+  float* bias_s = reinterpret_cast<float*>(smem_out + n_out_bufs * kStoreBytes);  // [2][kMaxBN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + n_out_bufs * kStoreBytes + kBiasBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
@@ -154,7 +157,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           } else {
             tma_load_3d(&tm_b, &full[stage], sb, kb * kBK + t.ob_lo * p.b_lo_c0, t.n0, b_c2);
           }
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -191,7 +194,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             tc_mma_bf16(tmem_d, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -301,15 +304,12 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
       // ---- full 128-byte slabs through shared memory + TMA
       for (int sidx = 0; sidx < n_slabs; ++sidx) {
-        const uint32_t dbuf = out_u32 + (two_out ? 0u : (slab_ctr & 1u) * kStoreBytes);
-        const uint32_t abuf = out_u32 + kStoreBytes;
-        // the buffer we are about to overwrite must have been drained by its previous TMA store
-        if (threadIdx.x == 0) {
-          if (two_out)
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        }
+        // double-buffered staging: D in buffers {0,1}, the optional second output in {2,3}
+        const uint32_t dbuf = out_u32 + (slab_ctr & 1u) * kStoreBytes;
+        const uint32_t abuf = out_u32 + (2u + (slab_ctr & 1u)) * kStoreBytes;
+        // the buffers we are about to overwrite must have been drained by the TMA stores of slab - 2
+        // (one bulk group per slab, so at most one group may still be reading)
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int c0 = sidx * slab_cols + half * my_cols;  // first tile column of this warp's share
         uint32_t r[32];
@@ -557,6 +557,17 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
 
 }  // namespace
 
+// external-linkage wrapper for the other translation units (attention_tc.cu)
+int fhb_make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, const int64_t dim[3], const int64_t stride[2],
+                          uint32_t box0, uint32_t box1, const char* name) {
+  fhb_tensor3 t;
+  t.ptr = ptr;
+  for (int i = 0; i < 3; ++i) t.dim[i] = dim[i];
+  t.stride[0] = stride[0];
+  t.stride[1] = stride[1];
+  return make_tmap(tm, t, box0, box1, name);
+}
+
 extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   FHB_ARG_CHECK(a != nullptr, "gemm: null args");
   FHB_ARG_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "gemm: m,n,k must be positive (got %d,%d,%d)", a->m, a->n, a->k);
@@ -647,6 +658,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   memset(&tx, 0, sizeof(tx));
   static const bool force_direct = getenv("FHB_GEMM_DIRECT_STORE") != nullptr;
   p.use_tma_store = force_direct ? 0 : 1;
+  p.stages = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 3 : kStages;
   if (p.use_tma_store) {
     const int n_hi = (num_ob + ob_mod - 1) / ob_mod;
     if ((rc = make_out_tmap(&td, a->d, (flags & FHB_EPI_OUT_F32) != 0, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride,

@@ -294,6 +294,14 @@ extern "C" int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, 
   return 0;
 }
 
+extern "C" int fhb_memset2d(void* ptr, int64_t pitch_bytes, int64_t width_bytes, int64_t height, fhb_stream_t stream) {
+  FHB_ARG_CHECK(ptr && pitch_bytes >= width_bytes && width_bytes >= 0 && height >= 0, "memset2d: bad arguments");
+  if (width_bytes == 0 || height == 0) return 0;
+  FHB_CUDA_CHECK(cudaMemset2DAsync(ptr, (size_t)pitch_bytes, 0, (size_t)width_bytes, (size_t)height,
+                                   static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 extern "C" int fhb_mask_lengths(const uint8_t* mask, int32_t B, int64_t L, int32_t* lengths, fhb_stream_t stream) {
   FHB_ARG_CHECK(mask && lengths && B > 0 && L > 0, "mask_lengths: bad arguments");
   mask_lengths_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, L, lengths);

@@ -248,7 +248,7 @@ class GradStore:
         return self.flat[a:b]
 
     def zero_(self):
-        self.flat.zero_()
+        K.zero_(self.flat)
 
     def export(self, accumulate=False) -> Dict[str, torch.Tensor]:
         """Gradients in PARAMETER layout (what autograd would have produced)."""
@@ -533,7 +533,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     dy3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
     x3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
     _wgrad(dy3, x3, gv("encoder.layers.0.weight").view(E, 2 * E), E, 2 * E, Ts, num_cb=B, a_cb=1, b_cb=1)
-    denc = torch.zeros(B * T, E, device=dev, dtype=bf16) if T % 2 else torch.empty(B * T, E, device=dev, dtype=bf16)
+    denc = torch.empty(B * T, E, device=dev, dtype=bf16)
+    if T % 2:  # the odd tail frame was dropped by the TR conv: zero gradient
+        K.zero_rows(denc, (T - 1) * E, T * E, E, B)
     a3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
     b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
     K.gemm_raw(a3, b3, denc, Ts, 2 * E, E, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * E, d_hi_stride=T * E)
@@ -541,8 +543,10 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     G, cp, kp = g.G, g.cp, g.kpos
     Tp = T + kp
     dh = torch.empty(B * T, E, device=dev, dtype=bf16)
-    dcg = torch.zeros(B * G, Tp, cp, device=dev, dtype=bf16)
     pad_b = kp // 2 - 1
+    dcg = torch.empty(B * G, Tp, cp, device=dev, dtype=bf16)
+    K.zero_rows(dcg, 0, Tp * cp, pad_b * cp, B * G)  # borders only: rows [pad_b, pad_b + T) are written below
+    K.zero_rows(dcg, (pad_b + T) * cp, Tp * cp, (Tp - pad_b - T) * cp, B * G)
     K.posconv_finish_bwd(denc, c.h, c.conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"], c.mean_e,
                          c.rstd_e, dh, dcg, gv("encoder.layer_norm.weight"), gv("encoder.layer_norm.bias"),
                          gv("encoder.pos_conv.0.bias"), B, T, E, G, cp, pad_b, Tp)
@@ -593,13 +597,18 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         if first:
             # gradient wrt the GELU output of layer 0: no GELU derivative here (conv0 backward recomputes it)
             assert (k, s) in ((1, 1), (2, 2)) or halo == 1
-            dprev = torch.empty(B, Tin, cin, device=dev, dtype=bf16) if (k, s) == (1, 1) else \
-                torch.zeros(B, Tin, cin, device=dev, dtype=bf16)
+            dprev = torch.empty(B, Tin, cin, device=dev, dtype=bf16)
             flags, uprev = 0, None
         else:
-            # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1}); zero-filled so halo rows / an odd tail frame stay zero
-            dprev = torch.zeros(B, in_rows, cin, device=dev, dtype=bf16)
+            # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1})
+            dprev = torch.empty(B, in_rows, cin, device=dev, dtype=bf16)
             flags, uprev = L.EPI_MUL_DGELU, c.u[i - 1]
+        if in_halo:  # halo rows must read as zero in the overlapped-view dgrad of layer i-1
+            K.zero_rows(dprev, 0, in_rows * cin, cin, B)
+            K.zero_rows(dprev, (in_rows - 1) * cin, in_rows * cin, cin, B)
+        covered = Tin if (k, s) != (2, 2) else 2 * To
+        if covered < Tin:  # frames no output depends on (odd tail of a k=2,s=2 layer)
+            K.zero_rows(dprev, (in_halo + covered) * cin, in_rows * cin, (Tin - covered) * cin, B)
         if (k, s) == (1, 1) or (k, s) == (2, 2):
             # dA[b,t,(j,ci)] = dU[b,t,:] W2[:, (j,ci)]  ==  dX[b, s*t + j, ci]   (W2 consumed MN-major)
             a3 = L.tensor3(data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))

@@ -251,3 +251,16 @@ def mask_lengths(mask_u8, lengths):
     B, Ld = mask_u8.shape
     L.check(L.lib().fhb_mask_lengths(L.ptr(mask_u8), B, C.c_int64(Ld), L.ptr(lengths), L.stream_ptr()),
             "fhb_mask_lengths")
+
+
+def zero_rows(buf: torch.Tensor, elem_offset: int, pitch_elems: int, width_elems: int, height: int):
+    """Zero `height` runs of `width_elems` elements, `pitch_elems` apart, starting at `elem_offset`."""
+    es = buf.element_size()
+    L.check(L.lib().fhb_memset2d(C.c_void_p(buf.data_ptr() + elem_offset * es), C.c_int64(pitch_elems * es),
+                                 C.c_int64(width_elems * es), C.c_int64(height), L.stream_ptr()), "fhb_memset2d")
+
+
+def zero_(buf: torch.Tensor):
+    n = buf.numel() * buf.element_size()
+    L.check(L.lib().fhb_memset2d(L.ptr(buf), C.c_int64(n), C.c_int64(n), C.c_int64(1), L.stream_ptr()), "fhb_memset2d")
+    return buf

@@ -217,6 +217,9 @@ int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t 
  * GELU derivative is not a GEMM epilogue: LayerNorm(512)-backward -> last conv layer (module.py:73) */
 int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_bstride, void* out,
                   int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
+/* zero `height` runs of `width_bytes` bytes, `pitch_bytes` apart (halo rows / borders of strided buffers);
+ * a cudaMemset2DAsync, no kernel */
+int fhb_memset2d(void* ptr, int64_t pitch_bytes, int64_t width_bytes, int64_t height, fhb_stream_t stream);
 /* lengths[b] = #(mask[b][:] == 0); mask is the reference's bool padding mask (True = pad),
  * utils/dataset.py:63-74 / fithubert/expert.py:60-63; first step of modules/model.py:453 */
 int fhb_mask_lengths(const uint8_t* mask, int32_t B, int64_t L, int32_t* lengths, fhb_stream_t stream);
