@@ -434,8 +434,8 @@ int check_shape(int B, int T, int H, int d) {
   else if (DPV <= 48) { constexpr int DP = 48; CALL; } \
   else { constexpr int DP = 64; CALL; }
 
-int fhb_attn_fwd_tc64(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
-                      float scale, cudaStream_t s);  // attention_tc.cu (tcgen05 path, head_dim 64)
+int fhb_attn_fwd_tc(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
+                    int32_t d, float scale, cudaStream_t s);  // attention_tc.cu (tcgen05 path, head_dim 64 / 40)
 
 extern "C" int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T,
                             int32_t H, int32_t d, float scale, fhb_stream_t stream) {
@@ -444,7 +444,7 @@ extern "C" int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, fl
   FHB_ARG_CHECK(qkv && out, "attn_fwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static const bool no_tc = getenv("FHB_ATTN_NO_TC") != nullptr;
-  if (d == 64 && !no_tc) return fhb_attn_fwd_tc64(qkv, valid, out, lse, B, T, H, scale, s);
+  if ((d == 64 || d == 40) && !no_tc) return fhb_attn_fwd_tc(qkv, valid, out, lse, B, T, H, d, scale, s);
   dim3 grid((T + kTile - 1) / kTile, H, B);
   FHB_ATTN_DISPATCH(d, (attn_fwd_kernel<DP><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), valid,
                                                                    static_cast<__nv_bfloat16*>(out), lse, T, H, d, scale)));

@@ -34,7 +34,10 @@ constexpr uint32_t kBBytes = kMaxBN * kBK * 2;  // 32 KiB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kStoreBytes = kBM * 128;  // one output slab: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
 constexpr uint32_t kBiasBytes = 2 * kMaxBN * 4;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 2 * kStoreBytes + kBiasBytes + 128 /*barriers*/;
+constexpr int kInRing = 3;  // epilogue-input slabs in flight (prefetch distance 2)
+constexpr uint32_t kBarBytes = 256;
+// 14 units of 16 KiB: 3 per pipeline stage + 2 output slabs (+ 2 second-output slabs) (+ 3 epilogue-input slabs)
+constexpr uint32_t kSmemBytes = 14 * kStoreBytes + kBiasBytes + kBarBytes;
 
 struct GemmParams {
   int m, n, k, bn;
@@ -43,7 +46,7 @@ struct GemmParams {
   int a_lo_c0, a_hi_c2, a_lo_c2, a_cb_c2;
   int b_lo_c0, b_hi_c2, b_lo_c2, b_cb_c2;
   int a_c1_off, b_c1_off;
-  long long d_ld, d_hi_stride, d_lo_stride;
+  long long d_ld, d_hi_stride, d_lo_stride, bias_hi_stride;
   void* d;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -57,7 +60,9 @@ struct GemmParams {
   uint32_t stage_tx_bytes;
   int total_tiles;
   int use_tma_store;
-  int stages;  // smem pipeline depth: 4, or 3 when a second output needs its own staging buffers
+  int stages;    // smem pipeline depth: 4, 3 or 2 depending on how many epilogue staging buffers are needed
+  int n_auxout;  // 0 / 2 staging buffers for the second output
+  int n_in;      // 0 / kInRing staging buffers for the TMA-loaded epilogue input (residual or aux_in)
 };
 
 struct Tile {
@@ -81,25 +86,28 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
   return t;
 }
 
-// EPI_IN = 1: the epilogue may read [m][n] operands from global memory (residual / gelu' input / loss target)
+// EPI_IN = 1: the epilogue reads [m][n] operands (residual / aux_in / loss target) laid out like D
 template <int A_MN, int B_MN, int EPI_IN>
 __global__ void __launch_bounds__(kThreads, 1)
 fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_aux,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap tm_in, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nstages = p.stages;
-  const int n_out_bufs = (kStages - nstages) * 3 + 2;  // 2 (4 stages) or 5 (3 stages); 4 are used
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + nstages * kABytes;
-  uint8_t* smem_out = smem + nstages * kStageBytes;  // 16 KiB staging buffers for TMA stores
-  float* bias_s = reinterpret_cast<float*>(smem_out + n_out_bufs * kStoreBytes);  // [2][kMaxBN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + n_out_bufs * kStoreBytes + kBiasBytes);
+  uint8_t* smem_out = smem + nstages * kStageBytes;            // 2 x 16 KiB staging buffers for TMA stores of D
+  uint8_t* smem_auxo = smem_out + 2 * kStoreBytes;             // 0 / 2 buffers for the second output
+  uint8_t* smem_in = smem_auxo + p.n_auxout * kStoreBytes;     // 0 / 3 buffers for the TMA-loaded epilogue input
+  uint8_t* smem_tail = smem + 14 * kStoreBytes;
+  float* bias_s = reinterpret_cast<float*>(smem_tail);  // [2][kMaxBN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_tail + kBiasBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
   uint64_t* acc_empty = bars + 2 * kStages + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+  uint64_t* in_full = bars + 2 * kStages + 2 * kAccStages;  // [kInRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages + kInRing);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,6 +125,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kEpiThreads);
     }
+    for (int i = 0; i < kInRing; ++i) mbar_init(&in_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -167,7 +176,6 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)p.bn, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart (SBO); MN-major: 64-element atoms kBK*128 B apart (LBO),
       // 8-k-row groups 1024 B apart (SBO).
       const uint32_t a_lbo = A_MN ? kBK * 128 : 0, b_lbo = B_MN ? kBK * 128 : 0;
@@ -177,6 +185,9 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const Tile t = decode_tile(p, tile);
+        // the last n-block of a row may be narrower: issue only the columns that exist (multiple of 16)
+        const int n_eff = min(p.bn, (p.n - t.n0 + 15) & ~15);
+        const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)n_eff, A_MN, B_MN);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);
@@ -207,12 +218,46 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int flags = p.flags;
     const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
     const bool two_out = (flags & FHB_EPI_STORE_PREACT) != 0;
+    const bool in_tma = EPI_IN && p.n_in > 0;
+    // which [m][n] operand travels through the TMA input ring: aux_in if it is used, else the residual
+    const bool ring_is_aux = (flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) != 0;
     const int slab_cols = out_f32 ? 32 : 64;       // columns per 128-byte slab
     const int my_cols = slab_cols >> 1;            // this warp's half of the slab: 16 (fp32) or 32 (bf16)
     const int quarter = warp & 3, half = warp >> 2;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t rsw = (uint32_t)(row_in_tile & 7);
-    const uint32_t out_u32 = smem_u32(smem_out);
+    const uint32_t out_u32 = smem_u32(smem_out), auxo_u32 = smem_u32(smem_auxo), in_u32 = smem_u32(smem_in);
+    auto tile_slabs = [&](const Tile& t) {
+      return p.use_tma_store ? (min(p.bn, p.n - t.n0) + slab_cols - 1) / slab_cols : 0;
+    };
+    // ---- input-ring prefetcher (thread 0): walks the (tile, slab) sequence kInRing-1 slabs ahead
+    int pf_tile = blockIdx.x, pf_sidx = 0, pf_ns = 0;
+    uint32_t pf_ctr = 0;
+    Tile pf_t = {0, 0, 0, 0, 0, 0};
+    auto prefetch_one = [&]() {
+      if (pf_tile >= p.total_tiles) return;
+      const uint32_t slot = pf_ctr % kInRing;
+      mbar_expect_tx(&in_full[slot], kStoreBytes);
+      tma_load_4d(&tm_in, &in_full[slot], in_u32 + slot * kStoreBytes, pf_t.n0 + pf_sidx * slab_cols, pf_t.m0, pf_t.ob_lo,
+                  pf_t.ob_hi);
+      ++pf_ctr;
+      if (++pf_sidx == pf_ns) {
+        pf_sidx = 0;
+        pf_tile += gridDim.x;
+        if (pf_tile < p.total_tiles) {
+          pf_t = decode_tile(p, pf_tile);
+          pf_ns = tile_slabs(pf_t);
+        }
+      }
+    };
+    if (in_tma && threadIdx.x == 0) {
+      tma_prefetch_desc(&tm_in);
+      if (pf_tile < p.total_tiles) {
+        pf_t = decode_tile(p, pf_tile);
+        pf_ns = tile_slabs(pf_t);
+      }
+      for (int i = 0; i < kInRing - 1; ++i) prefetch_one();
+    }
     int it = 0;
     uint32_t slab_ctr = 0;
     float loss_local = 0.f;
@@ -224,7 +269,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       float* bs = bias_s + as * kMaxBN;
       if (flags & FHB_EPI_BIAS) {
         const int c = threadIdx.x;
-        if (c < p.bn) bs[c] = (t.n0 + c < p.n) ? __ldg(p.bias + t.n0 + c) : 0.f;
+        if (c < p.bn) bs[c] = (t.n0 + c < p.n) ? __ldg(p.bias + (long long)t.ob_hi * p.bias_hi_stride + t.n0 + c) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[as], aphase);
@@ -236,10 +281,12 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       const long long off = (long long)t.ob_hi * p.d_hi_stride + (long long)t.ob_lo * p.d_lo_stride +
                             (long long)row * p.d_ld + t.n0;
       const uint32_t taddr = tmem_base + as * kMaxBN + ((uint32_t)(quarter * 32) << 16);
-      const int n_slabs = p.use_tma_store ? p.bn / slab_cols : 0;
+      const int n_slabs = tile_slabs(t);
+      const int tile_cols = min(p.bn, p.n - t.n0);
 
-      // fused epilogue math on 16 consecutive columns starting at tile column c
-      auto math16 = [&](float* v, float* pre, int c) {
+      // fused epilogue math on 16 consecutive columns starting at tile column c.  `ring`: this thread's 16
+      // values of the TMA-staged input operand (nullptr = read every [m][n] operand from global memory).
+      auto math16 = [&](float* v, float* pre, int c, const uint32_t* ring) {
         if (flags & FHB_EPI_BIAS) {
           const float4* bp = reinterpret_cast<const float4*>(bs + c);
 #pragma unroll
@@ -252,29 +299,64 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         if (flags & FHB_EPI_STORE_PREACT) {
+          if (flags & FHB_EPI_AUX_DGELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pre[j] = v[j];
+            for (int j = 0; j < 16; ++j) pre[j] = gelu_erf_grad(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pre[j] = v[j];
+          }
         }
         if (flags & FHB_EPI_GELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (EPI_IN && row_ok) {
-          if (flags & FHB_EPI_MUL_DGELU) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + off + c);
-            const uint4 u0 = __ldg(ap), u1 = __ldg(ap + 1);
-            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        if (EPI_IN) {
+          const bool col_ok = row_ok && (t.n0 + c < p.n);
+          if (flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) {
+            uint32_t uu[8];
+            if (ring) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack_bf16(uu[j]);
-              v[2 * j] *= gelu_erf_grad(f.x);
-              v[2 * j + 1] *= gelu_erf_grad(f.y);
+              for (int j = 0; j < 8; ++j) uu[j] = ring[j];
+            } else if (col_ok) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + off + c);
+              const uint4 u0 = __ldg(ap), u1 = __ldg(ap + 1);
+              uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w;
+              uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) uu[j] = 0u;
+            }
+            if (flags & FHB_EPI_MUL_DGELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = unpack_bf16(uu[j]);
+                v[2 * j] *= gelu_erf_grad(f.x);
+                v[2 * j + 1] *= gelu_erf_grad(f.y);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = unpack_bf16(uu[j]);
+                v[2 * j] *= f.x;
+                v[2 * j + 1] *= f.y;
+              }
             }
           }
           if (flags & FHB_EPI_RESIDUAL) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
-            const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            uint32_t uu[8];
+            if (ring && !ring_is_aux) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) uu[j] = ring[j];
+            } else if (col_ok) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+              const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+              uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w;
+              uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) uu[j] = 0u;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float2 f = unpack_bf16(uu[j]);
@@ -282,7 +364,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               v[2 * j + 1] += f.y;
             }
           }
-          if (flags & FHB_EPI_SQDIFF) {
+          if ((flags & FHB_EPI_SQDIFF) && col_ok) {
             const uint4* tp = reinterpret_cast<const uint4*>(p.loss_target + off + c);
             const uint4 u0 = __ldg(tp), u1 = __ldg(tp + 1);
             const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -302,19 +384,36 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       };
 
-      // ---- full 128-byte slabs through shared memory + TMA
+      // ---- 128-byte slabs through shared memory + TMA (the last slab of a row of tiles may hang over the
+      //      tensor edge: TMA clips the store and zero-fills the load)
       for (int sidx = 0; sidx < n_slabs; ++sidx) {
-        // double-buffered staging: D in buffers {0,1}, the optional second output in {2,3}
+        // double-buffered staging: D in out[0..1], the optional second output in auxo[0..1]
         const uint32_t dbuf = out_u32 + (slab_ctr & 1u) * kStoreBytes;
-        const uint32_t abuf = out_u32 + (2u + (slab_ctr & 1u)) * kStoreBytes;
+        const uint32_t abuf = auxo_u32 + (slab_ctr & 1u) * kStoreBytes;
         // the buffers we are about to overwrite must have been drained by the TMA stores of slab - 2
         // (one bulk group per slab, so at most one group may still be reading)
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (threadIdx.x == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          // every thread has finished reading ring slot (slab_ctr - 1) % kInRing (barrier at the end of the
+          // previous slab): refill it with the slab kInRing - 1 ahead
+          if (in_tma) prefetch_one();
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int c0 = sidx * slab_cols + half * my_cols;  // first tile column of this warp's share
         uint32_t r[32];
         tmem_ld16(taddr + c0, r);
         if (!out_f32) tmem_ld16(taddr + c0 + 16, r + 16);
+        uint32_t ring[16];
+        if (in_tma) {
+          const uint32_t slot = slab_ctr % kInRing;
+          mbar_wait(&in_full[slot], (slab_ctr / kInRing) & 1u);
+          const uint32_t irow = in_u32 + slot * kStoreBytes + row_in_tile * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t ch = (uint32_t)(half * 4 + q);
+            ld_shared_v4(irow + ((ch ^ rsw) << 4), ring[4 * q], ring[4 * q + 1], ring[4 * q + 2], ring[4 * q + 3]);
+          }
+        }
         tmem_ld_wait();
         const uint32_t drow = dbuf + row_in_tile * 128;
         const uint32_t arow = abuf + row_in_tile * 128;
@@ -324,7 +423,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           float v[16], pre[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[gq * 16 + j]);
-          math16(v, pre, c0 + gq * 16);
+          math16(v, pre, c0 + gq * 16, in_tma ? ring + gq * 8 : nullptr);
           if (out_f32) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 4 chunks of 4 floats; chunk index within the 128-byte row
@@ -364,16 +463,16 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         ++slab_ctr;
       }
 
-      // ---- remaining columns (bn not a multiple of the slab width, or TMA store disabled): direct stores,
-      //      16-column groups dealt round-robin to the two warps of a lane quarter
-      for (int c = n_slabs * slab_cols + half * 16; c < p.bn; c += 32) {
+      // ---- TMA store disabled (FHB_GEMM_DIRECT_STORE): direct stores, 16-column groups dealt round-robin to
+      //      the two warps of a lane quarter
+      for (int c = n_slabs * slab_cols + half * 16; c < tile_cols; c += 32) {
         uint32_t r[16];
         tmem_ld16(taddr + c, r);
         tmem_ld_wait();
         float v[16], pre[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        math16(v, pre, c);
+        math16(v, pre, c, nullptr);
         if (!row_ok || t.n0 + c >= p.n) continue;
         if (flags & FHB_EPI_STORE_PREACT) {
           uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off + c);
@@ -526,16 +625,34 @@ int make_out_tmap(CUtensorMap* tm, void* base, bool f32, int n, int m, int ob_mo
   return 0;
 }
 
-int pick_bn(int n) {
-  const int parts = (n + kMaxBN - 1) / kMaxBN;
-  int bn = (n + parts - 1) / parts;
-  bn = (bn + 15) / 16 * 16;
-  return bn;
+// Tile width.  One n-block when the row fits (any multiple of 16); otherwise a multiple of 64 so that the
+// 128-byte store slabs of neighbouring n-blocks never overlap (only the last block of a row is clipped by
+// TMA).  Among {64,128,192,256} pick the width that minimises (rounds over the SMs) x (tile width + a fixed
+// per-tile cost worth ~48 columns): N = 480 on 98 row blocks runs as 192+192+96 (294 tiles, 2 rounds)
+// instead of 256+224 (196 tiles, still 2 rounds of wider tiles).
+int pick_bn(int n, long long row_tiles, bool split_k) {
+  const int n16 = (n + 15) / 16 * 16;
+  if (n16 <= 64) return n16;
+  const int sms = fhb_num_sms();
+  int best = kMaxBN;
+  double best_cost = 1e30;
+  for (int bn = kMaxBN; bn >= 64; bn -= 64) {
+    const int nblk = (n + bn - 1) / bn;
+    const int w = nblk == 1 ? n16 : bn;
+    const long long tiles = row_tiles * nblk;
+    const double rounds = split_k ? (double)nblk : (double)((tiles + sms - 1) / sms);
+    const double cost = rounds * (w + 48);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = w;
+    }
+  }
+  return best;
 }
 
 template <int A_MN, int B_MN, int EPI_IN>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
-            const GemmParams& p, cudaStream_t s) {
+            const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -543,16 +660,17 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
     attr_set = true;
   }
   const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
-  fhb_gemm_kernel<A_MN, B_MN, EPI_IN><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, tx, p);
+  fhb_gemm_kernel<A_MN, B_MN, EPI_IN><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, tx, ti, p);
   FHB_LAUNCH_CHECK();
   return 0;
 }
 
 template <int A_MN, int B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
-           const GemmParams& p, cudaStream_t s) {
-  if (p.flags & (FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_SQDIFF)) return launch2<A_MN, B_MN, 1>(ta, tb, td, tx, p, s);
-  return launch2<A_MN, B_MN, 0>(ta, tb, td, tx, p, s);
+           const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
+  if (p.flags & (FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX | FHB_EPI_SQDIFF))
+    return launch2<A_MN, B_MN, 1>(ta, tb, td, tx, ti, p, s);
+  return launch2<A_MN, B_MN, 0>(ta, tb, td, tx, ti, p, s);
 }
 
 }  // namespace
@@ -585,7 +703,10 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   FHB_ARG_CHECK(!(flags & FHB_EPI_RESIDUAL) || a->residual, "gemm: FHB_EPI_RESIDUAL without residual");
   FHB_ARG_CHECK(!(flags & FHB_EPI_ROWZERO) || a->row_valid, "gemm: FHB_EPI_ROWZERO without row_valid");
   FHB_ARG_CHECK(!(flags & FHB_EPI_STORE_PREACT) || a->aux_out, "gemm: FHB_EPI_STORE_PREACT without aux_out");
-  FHB_ARG_CHECK(!(flags & FHB_EPI_MUL_DGELU) || a->aux_in, "gemm: FHB_EPI_MUL_DGELU without aux_in");
+  FHB_ARG_CHECK(!(flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) || a->aux_in, "gemm: FHB_EPI_MUL_DGELU/MUL_AUX without aux_in");
+  FHB_ARG_CHECK((flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) != (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX),
+                "gemm: FHB_EPI_MUL_DGELU and FHB_EPI_MUL_AUX are exclusive");
+  FHB_ARG_CHECK(!(flags & FHB_EPI_AUX_DGELU) || (flags & FHB_EPI_STORE_PREACT), "gemm: FHB_EPI_AUX_DGELU needs FHB_EPI_STORE_PREACT");
   FHB_ARG_CHECK(!(flags & FHB_EPI_SQDIFF) || (a->loss_target && a->loss_acc), "gemm: FHB_EPI_SQDIFF without target/acc");
   FHB_ARG_CHECK(!(flags & FHB_EPI_ATOMIC_ADD) || (flags & FHB_EPI_OUT_F32), "gemm: atomic accumulate needs fp32 output");
   const int elt = (flags & FHB_EPI_OUT_F32) ? 4 : 2;
@@ -598,8 +719,8 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.m = a->m;
   p.n = a->n;
   p.k = a->k;
-  p.bn = pick_bn(a->n);
   p.num_m_blk = (a->m + kBM - 1) / kBM;
+  p.bn = pick_bn(a->n, (long long)p.num_m_blk * num_ob, (flags & FHB_EPI_ATOMIC_ADD) != 0);
   p.num_n_blk = (a->n + p.bn - 1) / p.bn;
   p.num_ob = num_ob;
   p.ob_mod = ob_mod;
@@ -625,6 +746,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.a_c1_off = a->a_c1_off; p.b_c1_off = a->b_c1_off;
   p.d_ld = a->d_ld; p.d_hi_stride = a->d_hi_stride; p.d_lo_stride = a->d_lo_stride;
   p.d = a->d;
+  p.bias_hi_stride = a->bias_hi_stride;
   p.bias = a->bias;
   p.residual = static_cast<const __nv_bfloat16*>(a->residual);
   p.aux_in = static_cast<const __nv_bfloat16*>(a->aux_in);
@@ -653,30 +775,44 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   }
   // TMA store path: needs 16B-aligned strides (already checked) and every (ob_lo, ob_hi) offset expressible as
   // a tensor-map stride; otherwise (or when FHB_GEMM_DIRECT_STORE is set) the epilogue stores directly.
-  CUtensorMap td, tx;
+  CUtensorMap td, tx, ti;
   memset(&td, 0, sizeof(td));
   memset(&tx, 0, sizeof(tx));
+  memset(&ti, 0, sizeof(ti));
   static const bool force_direct = getenv("FHB_GEMM_DIRECT_STORE") != nullptr;
   p.use_tma_store = force_direct ? 0 : 1;
-  p.stages = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 3 : kStages;
+  const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
+  // the [m][n] epilogue input (aux_in if used, else the residual) is staged through a TMA ring when D is bf16
+  const void* ring_src = (flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) ? a->aux_in
+                         : ((flags & FHB_EPI_RESIDUAL) ? a->residual : nullptr);
+  p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 2 : 0;
+  p.n_in = (p.use_tma_store && ring_src && !out_f32) ? kInRing : 0;
+  p.stages = (14 - 2 - p.n_auxout - p.n_in) / 3;
+  if (p.stages > kStages) p.stages = kStages;
   if (p.use_tma_store) {
     const int n_hi = (num_ob + ob_mod - 1) / ob_mod;
-    if ((rc = make_out_tmap(&td, a->d, (flags & FHB_EPI_OUT_F32) != 0, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride,
-                            a->d_hi_stride, "D")) != 0)
+    if ((rc = make_out_tmap(&td, a->d, out_f32, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride, a->d_hi_stride,
+                            "D")) != 0)
       return rc;
+    tx = td;
+    ti = td;
     if (flags & FHB_EPI_STORE_PREACT) {
       if ((rc = make_out_tmap(&tx, a->aux_out, false, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride, a->d_hi_stride,
                               "aux_out")) != 0)
         return rc;
-    } else {
-      tx = td;
+    }
+    if (p.n_in) {
+      if ((rc = make_out_tmap(&ti, const_cast<void*>(ring_src), false, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride,
+                              a->d_hi_stride, "epilogue input")) != 0)
+        return rc;
     }
   } else {
     td = ta;
     tx = ta;
+    ti = ta;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->a_major == 0 && a->b_major == 0) return launch<0, 0>(ta, tb, td, tx, p, s);
-  if (a->a_major == 0 && a->b_major == 1) return launch<0, 1>(ta, tb, td, tx, p, s);
-  return launch<1, 1>(ta, tb, td, tx, p, s);
+  if (a->a_major == 0 && a->b_major == 0) return launch<0, 0>(ta, tb, td, tx, ti, p, s);
+  if (a->a_major == 0 && a->b_major == 1) return launch<0, 1>(ta, tb, td, tx, ti, p, s);
+  return launch<1, 1>(ta, tb, td, tx, ti, p, s);
 }

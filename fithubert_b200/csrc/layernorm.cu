@@ -78,76 +78,91 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 }
 
 // dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)),  dxhat = dy * gamma
-// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (per-warp register partials -> smem -> atomics)
-__global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; optionally dxsum += sum_rows dx (the bias gradient of
+// the linear layer that produced x: saves a separate column-sum pass over dx).
+// Per-lane register partials -> block smem -> one atomic per column per block.  NV = 16-byte vectors per lane.
+template <int NV, bool DXSUM>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
-  extern __shared__ float sred[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows,
+                     int C) {
+  extern __shared__ float sred[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = C >> 3;
-  float pg[kMaxVec][8], pb[kMaxVec][8], g[kMaxVec][8];
+  float pg[NV][8], pb[NV][8], pd[DXSUM ? NV : 1][8];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = lane + 32 * i;
+  for (int i = 0; i < NV; ++i) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       pg[i][j] = 0.f;
       pb[i][j] = 0.f;
-      g[i][j] = (vi < nvec) ? __ldg(gamma + vi * 8 + j) : 0.f;
+      if (DXSUM) pd[i][j] = 0.f;
     }
   }
   for (long long row = warp_global; row < rows; row += nwarps) {
     const float mu = mean[row], rs = rstd[row];
-    float xh[kMaxVec][8], dyv[kMaxVec][8];
+    float xh[NV][8], dxh[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         load8(x + row * C + vi * 8, xh[i]);
-        load8(dy + row * C + vi * 8, dyv[i]);
+        load8(dy + row * C + vi * 8, dxh[i]);
+        if (dy2) {  // two gradient streams meet here (layer above + this layer's projection head)
+          float t2[8];
+          load8(dy2 + row * C + vi * 8, t2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dxh[i][j] += t2[j];
+        }
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)),
+                     g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xh[i][j] - mu) * rs;
-          const float dxh = dyv[i][j] * g[i][j];
-          s1 += dxh;
-          s2 += dxh * xh[i][j];
-          pg[i][j] += dyv[i][j] * xh[i][j];
-          pb[i][j] += dyv[i][j];
+          const float d = dxh[i][j];
+          pg[i][j] += d * xh[i][j];
+          pb[i][j] += d;
+          dxh[i][j] = d * g[j];
+          s1 += dxh[i][j];
+          s2 += dxh[i][j] * xh[i][j];
         }
       }
     }
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         float o[8];
         if (dres) load8(dres + row * C + vi * 8, o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = rs * (dyv[i][j] * g[i][j] - s1 - xh[i][j] * s2);
+          const float d = rs * (dxh[i][j] - s1 - xh[i][j] * s2);
           o[j] = dres ? o[j] + d : d;
+          if (DXSUM) pd[i][j] += o[j];
         }
         store8(dx + row * C + vi * 8, o);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&sred[vi * 8 + j], pg[i][j]);
         atomicAdd(&sred[C + vi * 8 + j], pb[i][j]);
+        if (DXSUM) atomicAdd(&sred[2 * C + vi * 8 + j], pd[i][j]);
       }
     }
   }
@@ -155,6 +170,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(dgamma + i, sred[i]);
     atomicAdd(dbeta + i, sred[C + i]);
+    if (DXSUM) atomicAdd(dxsum + i, sred[2 * C + i]);
   }
 }
 
@@ -181,15 +197,29 @@ extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float*
   return 0;
 }
 
-extern "C" int fhb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x, const float* gamma, const float* mean,
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                                 int64_t rows, int32_t C, fhb_stream_t stream) {
+                                 float* dxsum, int64_t rows, int32_t C, fhb_stream_t stream) {
   FHB_ARG_CHECK(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
   FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_bwd: bad C=%d", C);
   if (rows == 0) return 0;
-  layernorm_bwd_kernel<<<ln_grid(rows, 4), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
-      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C);
+  // ~2 blocks per SM (register-limited), every warp streams several rows
+  long long blocks = (rows + 15) / 16;
+  if (blocks > 2LL * fhb_num_sms()) blocks = 2LL * fhb_num_sms();
+  const int nv = (C / 8 + 31) / 32;
+  const size_t sm = 3 * C * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define FHB_LN_BWD(NV, DX)                                                                                          \
+  layernorm_bwd_kernel<NV, DX><<<(unsigned)blocks, 256, sm, s>>>(                                                   \
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dy2),                               \
+      static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,                                                      \
+      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum, rows, C)
+  if (dxsum) {
+    if (nv == 1) FHB_LN_BWD(1, true); else if (nv == 2) FHB_LN_BWD(2, true); else FHB_LN_BWD(3, true);
+  } else {
+    if (nv == 1) FHB_LN_BWD(1, false); else if (nv == 2) FHB_LN_BWD(2, false); else FHB_LN_BWD(3, false);
+  }
+#undef FHB_LN_BWD
   FHB_LAUNCH_CHECK();
   return 0;
 }

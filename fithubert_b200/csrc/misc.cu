@@ -8,10 +8,14 @@ namespace {
 
 // ------------------------------------------------------------------ K10 loss + gradient
 // grid (chunks, n_layers).  pred [L][B][Tp][D], tgt [L][B][Tt][D] (first Tp frames used).
+// The grid stride (gridDim.x * 256 vectors) is a multiple of D/8, so a thread always sees the same 8 columns:
+// the column sums of the gradient (= bias gradient of the head's final Linear) accumulate in registers.
 __global__ void __launch_bounds__(256)
 distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt,
                     const float* __restrict__ weights, float* __restrict__ layer_loss, __nv_bfloat16* __restrict__ dpred,
-                    int B, int Tp, int Tt, int D, int loss_type, float grad_scale) {
+                    float* __restrict__ dbias, long long dbias_stride, int B, int Tp, int Tt, int D, int loss_type,
+                    float grad_scale) {
+  extern __shared__ float csum[];  // [D] (only when dbias)
   const int l = blockIdx.y;
   const float w = weights[l];
   const long long vec_per_row = D >> 3;
@@ -21,8 +25,14 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
   const __nv_bfloat16* pl = pred + (long long)l * B * Tp * D;
   const __nv_bfloat16* tl = tgt + (long long)l * B * Tt * D;
   __nv_bfloat16* dl = dpred ? dpred + (long long)l * B * Tp * D : nullptr;
+  if (dbias) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) csum[i] = 0.f;
+    __syncthreads();
+  }
   float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / vec_per_row;
     const int cv = i - row * vec_per_row;
     const int b = row / Tp, t = row - (long long)b * Tp;
@@ -34,15 +44,27 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
     for (int j = 0; j < 4; ++j) {
       const float2 p = unpack_bf16(pa[j]), q = unpack_bf16(ta[j]);
       const float d0 = p.x - q.x, d1 = p.y - q.y;
+      float g0, g1;
       if (loss_type == 0) {
         acc += d0 * d0 + d1 * d1;
-        out[j] = pack_bf16(gs * d0, gs * d1);
+        g0 = gs * d0;
+        g1 = gs * d1;
       } else {
         acc += fabsf(d0) + fabsf(d1);
-        out[j] = pack_bf16(d0 > 0.f ? gs : (d0 < 0.f ? -gs : 0.f), d1 > 0.f ? gs : (d1 < 0.f ? -gs : 0.f));
+        g0 = d0 > 0.f ? gs : (d0 < 0.f ? -gs : 0.f);
+        g1 = d1 > 0.f ? gs : (d1 < 0.f ? -gs : 0.f);
       }
+      out[j] = pack_bf16(g0, g1);
+      const float2 gr = unpack_bf16(out[j]);  // sum what the downstream GEMMs will read
+      cs[2 * j] += gr.x;
+      cs[2 * j + 1] += gr.y;
     }
     if (dl) *reinterpret_cast<uint4*>(dl + row * D + cv * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+  if (dbias && i0 < nvec) {
+    const int cv = (int)(i0 % vec_per_row);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&csum[cv * 8 + j], cs[j]);
   }
   __shared__ float red[8];
   acc = warp_sum(acc);
@@ -52,6 +74,10 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i];
     atomicAdd(layer_loss + l, s * w * inv_count);
+  }
+  if (dbias) {
+    float* db = dbias + (long long)l * dbias_stride;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(db + i, csum[i]);
   }
 }
 
@@ -110,8 +136,11 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* 
 // round-robin to all warps of the grid; per-lane partial sums -> block smem -> one atomic per column/block.
 constexpr int kColsumMaxVec = 8;  // C <= 8 * 32 * 8 = 2048
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out) {
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out,
+              long long x_bstride, long long out_bstride) {
   extern __shared__ float csum[];  // [C]
+  x += (long long)blockIdx.y * x_bstride;
+  out += (long long)blockIdx.y * out_bstride;
   for (int i = threadIdx.x; i < C; i += blockDim.x) csum[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -123,6 +152,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long l
   for (int i = 0; i < kColsumMaxVec; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
   for (long long r = warp_global; r < rows; r += nwarps) {
     const __nv_bfloat16* xr = x + r * ld;
 #pragma unroll
@@ -189,6 +219,27 @@ mul_dgelu_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, const __
   }
 }
 
+// out[b][i] = a[b][i] * m[b][i] (m = a saved multiplier, e.g. gelu' from FHB_EPI_AUX_DGELU)
+__global__ void __launch_bounds__(256)
+mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_bfloat16* __restrict__ m, long long m_bs,
+                __nv_bfloat16* __restrict__ out, long long out_bs, long long nvec) {
+  const int b = blockIdx.y;
+  const uint4* a4 = reinterpret_cast<const uint4*>(a + b * a_bs);
+  const uint4* m4 = reinterpret_cast<const uint4*>(m + b * m_bs);
+  uint4* o4 = reinterpret_cast<uint4*>(out + b * out_bs);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 x = a4[i], c = m4[i];
+    const uint32_t aa[4] = {x.x, x.y, x.z, x.w}, cc[4] = {c.x, c.y, c.z, c.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(cc[j]);
+      o[j] = pack_bf16(p.x * q.x, p.y * q.y);
+    }
+    o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // lengths[b] = number of zero bytes in mask[b][0..L)   (mask: 1 = padding)
 __global__ void __launch_bounds__(256) mask_lengths_kernel(const uint8_t* __restrict__ mask, long long L, int* __restrict__ lengths) {
   const uint8_t* row = mask + (long long)blockIdx.x * L;
@@ -215,19 +266,26 @@ int grid_x(long long work_items, int cap_mult) {
 }  // namespace
 
 extern "C" int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const float* weights, float* layer_loss,
-                                        void* dpred, int32_t n_layers, int32_t B, int32_t Tp, int32_t Tt, int32_t D,
-                                        int32_t loss_type, float grad_scale, fhb_stream_t stream) {
+                                        void* dpred, float* dbias, int64_t dbias_layer_stride, int32_t n_layers,
+                                        int32_t B, int32_t Tp, int32_t Tt, int32_t D, int32_t loss_type,
+                                        float grad_scale, fhb_stream_t stream) {
   FHB_ARG_CHECK(pred && tgt && weights && layer_loss, "distill_loss: null pointer");
   FHB_ARG_CHECK(n_layers > 0 && B > 0 && Tp > 0 && Tt >= Tp && D > 0 && D % 8 == 0,
                 "distill_loss: bad shape (layers=%d B=%d Tp=%d Tt=%d D=%d)", n_layers, B, Tp, Tt, D);
   FHB_ARG_CHECK(loss_type == 0 || loss_type == 1, "rec_loss_type must be one of 'l1', 'mse'.");
+  FHB_ARG_CHECK(!dbias || dpred, "distill_loss: dbias needs dpred");
   const long long nvec = (long long)B * Tp * (D / 8);
   int gx = grid_x(nvec, 8);
   gx = (gx + n_layers - 1) / n_layers;
   if (gx < 1) gx = 1;
-  distill_loss_kernel<<<dim3(gx, n_layers), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  // make the grid stride a multiple of the row length in vectors: gx * 256 % (D/8) == 0
+  long long vpr = D / 8, g = vpr, a = 256;
+  while (a) { const long long t2 = g % a; g = a; a = t2; }  // g = gcd(vpr, 256)
+  const int unit = (int)(vpr / g);
+  gx = (gx + unit - 1) / unit * unit;
+  distill_loss_kernel<<<dim3(gx, n_layers), 256, dbias ? D * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(tgt), weights, layer_loss,
-      static_cast<__nv_bfloat16*>(dpred), B, Tp, Tt, D, loss_type, grad_scale);
+      static_cast<__nv_bfloat16*>(dpred), dbias, dbias_layer_stride, B, Tp, Tt, D, loss_type, grad_scale);
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -258,16 +316,23 @@ extern "C" int fhb_prep_multi(const fhb_prep_tensor* table_dev, int32_t n_tensor
   return 0;
 }
 
-extern "C" int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, float* out, fhb_stream_t stream) {
-  FHB_ARG_CHECK(x && out && C % 8 == 0 && ld % 8 == 0 && C <= kColsumMaxVec * 256, "colsum: bad arguments (C=%d)", C);
+extern "C" int fhb_colsum_batched(const void* x, int64_t rows, int32_t C, int64_t ld, int64_t x_bstride, float* out,
+                                  int64_t out_bstride, int32_t batches, fhb_stream_t stream) {
+  FHB_ARG_CHECK(x && out && C % 8 == 0 && ld % 8 == 0 && C <= kColsumMaxVec * 256 && batches > 0 && x_bstride % 8 == 0,
+                "colsum: bad arguments (C=%d)", C);
   if (rows == 0) return 0;
   long long blocks = (rows + 8 * 8 - 1) / (8 * 8);  // >= 8 rows per warp
-  if (blocks > fhb_num_sms()) blocks = fhb_num_sms();
+  const long long cap = (2LL * fhb_num_sms() + batches - 1) / batches;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  colsum_kernel<<<(unsigned)blocks, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), rows, C, ld, out);
+  colsum_kernel<<<dim3((unsigned)blocks, batches), 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), rows, C, ld, out, x_bstride, out_bstride);
   FHB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, float* out, fhb_stream_t stream) {
+  return fhb_colsum_batched(x, rows, C, ld, 0, out, 0, 1, stream);
 }
 
 extern "C" int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t stream) {
@@ -289,6 +354,21 @@ extern "C" int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, 
   gx = (gx + B - 1) / B;
   mul_dgelu_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), dy_bstride, static_cast<const __nv_bfloat16*>(u), u_bstride,
+      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstride, void* out,
+                            int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream) {
+  FHB_ARG_CHECK(a && m && out && B > 0, "mul_bf16: null pointer");
+  FHB_ARG_CHECK(n % 8 == 0 && a_bstride % 8 == 0 && m_bstride % 8 == 0 && out_bstride % 8 == 0,
+                "mul_bf16: sizes and strides must be multiples of 8 elements");
+  if (n == 0) return 0;
+  int gx = grid_x(n / 8, 8);
+  gx = (gx + B - 1) / B;
+  mul_bf16_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_bstride, static_cast<const __nv_bfloat16*>(m), m_bstride,
       static_cast<__nv_bfloat16*>(out), out_bstride, n / 8);
   FHB_LAUNCH_CHECK();
   return 0;

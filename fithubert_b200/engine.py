@@ -111,6 +111,7 @@ class WeightSet:
                 add(f"h{i}.wup", bf16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
                 add(f"h{i}.bup", f32, (2, E, 1), [(p + "upsampler.bias", 0, (0, 1, 0), 0)])
                 lin(f"h{i}.wlin", p + "lin_proj.weight", g.d_out, E)
+                add(f"h{i}.blin", f32, (g.d_out, 1, 1), [(p + "lin_proj.bias", 0, (1, 0, 0), 0)])
         self.spec = spec
         nb = sum(math.prod(d) for (_, t, d, _) in spec if t == bf16)
         nf = sum(math.prod(d) for (_, t, d, _) in spec if t == f32)
@@ -133,6 +134,22 @@ class WeightSet:
 
     def __getitem__(self, name):
         return self.views[name]
+
+    def head_stride(self, name: str) -> Optional[int]:
+        """Element stride between consecutive projection heads' shadow `name` (wup / bup / wlin / blin) if every
+        head 0..n-1 has its own parameters at a uniform stride (then the 12 heads run as ONE batched GEMM)."""
+        n = self.g.n_layers
+        if any(f"h{i}.{name}" not in self.views for i in range(n)) or "proj_head.0.lin_proj.bias" not in self.params \
+                or f"proj_head.{n - 1}.lin_proj.bias" not in self.params:
+            return None
+        es = self.views[f"h0.{name}"].element_size()
+        ptrs = [self.views[f"h{i}.{name}"].data_ptr() for i in range(n)]
+        if n == 1:
+            return self.views[f"h0.{name}"].numel()
+        d = ptrs[1] - ptrs[0]
+        if d <= 0 or any(ptrs[i + 1] - ptrs[i] != d for i in range(n - 1)):
+            return None
+        return d // es
 
     def signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.params.values())
@@ -250,6 +267,25 @@ class GradStore:
     def zero_(self):
         K.zero_(self.flat)
 
+    def head_stride(self) -> Optional[int]:
+        """Float stride between consecutive projection heads' gradient blocks, if uniform."""
+        n = self.g.n_layers
+        names = ("upsampler.weight", "upsampler.bias", "lin_proj.weight", "lin_proj.bias")
+        if any(f"proj_head.{i}.{nm}" not in self.entries for i in range(n) for nm in names):
+            return None
+        if n == 1:
+            return self.numel
+        d = self.entries["proj_head.1.lin_proj.bias"][0] - self.entries["proj_head.0.lin_proj.bias"][0]
+        for nm in names:
+            offs = [self.entries[f"proj_head.{i}.{nm}"][0] for i in range(n)]
+            if any(offs[i + 1] - offs[i] != d for i in range(n - 1)):
+                return None
+        return d
+
+    def from_(self, pn) -> torch.Tensor:
+        """Flat view from the start of `pn` to the end of the buffer (base pointer of a strided batch)."""
+        return self.flat[self.entries[pn][0]:]
+
     def export(self, accumulate=False) -> Dict[str, torch.Tensor]:
         """Gradients in PARAMETER layout (what autograd would have produced)."""
         out = {}
@@ -301,7 +337,7 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool)
     K.conv0_fwd(wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
                 P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat, c.mean0, c.rstd0, y)
     c.y = [y]
-    c.u = [None]
+    c.u = [None]  # per layer: gelu'(pre-activation), saved by the forward epilogue (the backward multiplier)
     # (buffer, rows allocated per sample, first data row)
     x_buf, x_rows, x_row0, cin, T = y, T0, 0, C0, T0
     for i, (co, k, s) in enumerate(g.conv_layers):
@@ -315,7 +351,8 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool)
         a3 = L.tensor3(data_ptr=x_buf.data_ptr() + 2 * x_row0 * cin, dim=(k * cin, To, B), stride=(s * cin, x_rows * cin))
         b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
         K.gemm_raw(a3, b3, yb, To, co, k * cin, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=co, d_hi_stride=rows * co,
-                   d_offset_elems=halo * co, flags=L.EPI_GELU | (L.EPI_STORE_PREACT if save else 0), aux_out=ub)
+                   d_offset_elems=halo * co,
+                   flags=L.EPI_GELU | ((L.EPI_STORE_PREACT | L.EPI_AUX_DGELU) if save else 0), aux_out=ub)
         c.y.append(yb)
         c.u.append(ub)
         x_buf, x_rows, x_row0, cin, T = yb, rows, halo, co, To
@@ -377,7 +414,7 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
     K.layernorm_fwd(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1,
                     s.mean1, s.rstd1)
     u = torch.empty(B * T, F, device=dev, dtype=bf16) if save else None
-    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, preact_out=u)
+    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u)
     lr = torch.empty(B * T, E, device=dev, dtype=bf16) if want_lr else None
     y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr)
     x2 = out if out is not None else torch.empty_like(y2)
@@ -436,26 +473,45 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     c.tr = tr
     x = tr
     c.layer_ctx = []
+    lay = torch.empty(g.n_layers, B * Ts, E, device=dev, dtype=bf16)  # stacked layer outputs (batched heads)
     for l in range(g.n_layers):
-        s = layer_fwd(P, W, g, f"encoder.layers.{l + 1}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr)
+        s = layer_fwd(P, W, g, f"encoder.layers.{l + 1}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l])
         c.layer_ctx.append(s)
         x = s.out
+    c.lay = lay
     c.layers = [s.out for s in c.layer_ctx]
     c.lrs = [s.lr for s in c.layer_ctx]
     # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E]
     Tq = 2 * Ts
     D = g.d_out
-    idx = list(range(g.n_layers)) if heads == "all" else ([g.n_layers - 1] if heads == "last" else [])
+    n = g.n_layers
+    idx = list(range(n)) if heads == "all" else ([n - 1] if heads == "last" else [])
     c.head_idx = idx
+    hs = {k: W.head_stride(k) for k in ("wup", "bup", "wlin", "blin")} if heads == "all" else {}
+    c.heads_batched = bool(idx) and heads == "all" and all(v is not None for v in hs.values())
     if idx:
         if pred_buf is None:
             pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=bf16)
-        c.z = []
-        for j, i in enumerate(idx):
-            z = K.linear(c.layers[i], W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"])
-            K.linear(z.view(B * Tq, E), W[f"h{i}.wlin"].view(D, E), P[_head_name(P, i) + "lin_proj.bias"],
-                     out=pred_buf[j].view(B * Tq, D))
-            c.z.append(z if train else None)
+        if c.heads_batched:
+            # all n heads as TWO batched GEMMs (ob = head): 12x the tiles per launch, no per-head launch tails
+            z = torch.empty(n, B * Tq, E, device=dev, dtype=bf16)
+            a3 = L.tensor3(data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
+            b3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
+            K.gemm_raw(a3, b3, z, B * Ts, 2 * E, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=2 * E,
+                       d_hi_stride=B * Ts * 2 * E, flags=L.EPI_BIAS, bias=W["h0.bup"], bias_hi_stride=hs["bup"])
+            a3 = L.tensor3(data_ptr=z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
+            b3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+            K.gemm_raw(a3, b3, pred_buf, B * Tq, D, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=D,
+                       d_hi_stride=B * Tq * D, flags=L.EPI_BIAS, bias=W["h0.blin"], bias_hi_stride=hs["blin"])
+            c.z = z if train else None
+            c.head_strides = hs
+        else:
+            c.z = []
+            for j, i in enumerate(idx):
+                z = K.linear(c.layers[i], W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"])
+                K.linear(z.view(B * Tq, E), W[f"h{i}.wlin"].view(D, E), P[_head_name(P, i) + "lin_proj.bias"],
+                         out=pred_buf[j].view(B * Tq, D))
+                c.z.append(z if train else None)
     c.preds = pred_buf if idx else None
     c.Tq = Tq
     return c
@@ -473,23 +529,57 @@ def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc:
 
 
 def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torch.Tensor,
-                     dlayers: Optional[List[Optional[torch.Tensor]]] = None):
+                     dlayers: Optional[List[Optional[torch.Tensor]]] = None, lin_bias_done: bool = False):
     """Backward of student_forward(train=True, heads='all').  dpred: [n_layers, B, T', D] bf16 gradient of
-    the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer."""
+    the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer.
+    lin_bias_done: the lin_proj bias gradients (column sums of dpred) were already accumulated by the loss kernel."""
     E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
     B, T, Ts, Tq = c.B, c.T, c.Ts, c.Tq
     dev = dpred.device
     gv = G_.view
     dx = None  # gradient wrt the current layer's output [B*Ts, E]
+    n = g.n_layers
+    gs = G_.head_stride() if getattr(c, "heads_batched", False) else None
+    dx_head = None
+    if gs is not None:
+        # ---- all n projection heads at once (ob = head): 2 wgrad + 2 dgrad batched GEMMs, 1-2 column sums
+        hs = c.head_strides
+        dp3 = dpred.view(n, B * Tq, D)
+        if not lin_bias_done:
+            K.colsum_batched(dp3, G_.from_("proj_head.0.lin_proj.bias"), gs)
+        a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, B * Tq, n), stride=(D, B * Tq * D))
+        z3 = L.tensor3(data_ptr=c.z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
+        K.gemm_raw(a3, z3, G_.from_("proj_head.0.lin_proj.weight"), D, E, B * Tq, a_major=1, b_major=1, num_ob=n,
+                   a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD)
+        dz = torch.empty(n, B * Tq, E, device=dev, dtype=bf16)
+        b3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+        K.gemm_raw(a3, b3, dz, B * Tq, E, D, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E,
+                   d_hi_stride=B * Tq * E)
+        K.colsum_batched(dz, G_.from_("proj_head.0.upsampler.bias"), gs)
+        a3 = L.tensor3(data_ptr=dz.data_ptr(), dim=(2 * E, B * Ts, n), stride=(2 * E, B * Ts * 2 * E))
+        x3 = L.tensor3(data_ptr=c.lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
+        K.gemm_raw(a3, x3, G_.from_("proj_head.0.upsampler.weight"), 2 * E, E, B * Ts, a_major=1, b_major=1, num_ob=n,
+                   a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD)
+        dx_head = torch.empty(n, B * Ts, E, device=dev, dtype=bf16)
+        b3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
+        K.gemm_raw(a3, b3, dx_head, B * Ts, E, 2 * E, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
+                   d_ld=E, d_hi_stride=B * Ts * E)
     for l in range(g.n_layers - 1, -1, -1):
         s = c.layer_ctx[l]
         p = f"encoder.layers.{l + 1}."
         hp = f"proj_head.{l}."
-        if l in c.head_idx:
+        dx2 = None  # second gradient stream into this layer's output (summed inside the LayerNorm backward)
+        if dx_head is not None:
+            if dx is None:
+                dx = dx_head[l]
+            else:
+                dx2 = dx_head[l]
+        elif l in c.head_idx:
             j = c.head_idx.index(l)
             dp = dpred[j].view(B * Tq, D)
             z = c.z[j].view(B * Tq, E)
-            K.colsum(dp, gv(hp + "lin_proj.bias"))
+            if not lin_bias_done:
+                K.colsum(dp, gv(hp + "lin_proj.bias"))
             K.linear_wgrad(dp, z, out=gv(hp + "lin_proj.weight").view(D, E), accumulate=True)
             dz = K.linear_dgrad(dp, W[f"h{l}.wlin"].view(D, E))  # [B*Tq, E] == [B*Ts, 2E]
             K.colsum(dz, gv(hp + "upsampler.bias"))
@@ -497,26 +587,31 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.linear_wgrad(dz2, s.out, out=gv(hp + "upsampler.weight").view(2 * E, E), accumulate=True)
             dx = K.linear_dgrad(dz2, W[f"h{l}.wup"].view(2 * E, E), residual=dx)
         if dlayers is not None and dlayers[l] is not None:
-            dx = dlayers[l] if dx is None else K.add_bf16(dx, dlayers[l], torch.empty_like(dx))
+            if dx is None:
+                dx = dlayers[l]
+            elif dx2 is None:
+                dx2 = dlayers[l]
+            else:
+                dx2 = K.add_bf16(dx2, dlayers[l], torch.empty_like(dx))
         if dx is None:
             continue
         # final LayerNorm
         dy2 = torch.empty_like(dx)
         K.layernorm_bwd(dx, s.y2, P[p + "final_layer_norm.weight"], s.mean2, s.rstd2, dy2,
-                        gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"))
-        # FFN
-        K.colsum(dy2, gv(p + "fc2.bias"))
+                        gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"), dxsum=gv(p + "fc2.bias"),
+                        dy2=dx2)
+        # FFN (fc2 bias gradient = column sums of dy2: accumulated by the LayerNorm backward above)
         K.linear_wgrad(dy2, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
-        du = K.linear_dgrad(dy2, W[f"l{l}.w2"].view(E, F), dgelu_of=s.u)
+        du = K.linear_dgrad(dy2, W[f"l{l}.w2"].view(E, F), mul_aux=s.u)
         K.colsum(du, gv(p + "fc1.bias"))
         K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
         dx1 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2)
         # attention LayerNorm
         dy1 = torch.empty_like(dx1)
         K.layernorm_bwd(dx1, s.y1, P[p + "self_attn_layer_norm.weight"], s.mean1, s.rstd1, dy1,
-                        gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"))
-        # attention block
-        K.colsum(dy1, gv(p + "self_attn.out_proj.bias"))
+                        gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"),
+                        dxsum=gv(p + "self_attn.out_proj.bias"))
+        # attention block (out_proj bias gradient: accumulated by the LayerNorm backward above)
         K.linear_wgrad(dy1, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
         dattn = K.linear_dgrad(dy1, W[f"l{l}.wo"].view(E, E))
         dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
@@ -576,9 +671,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     dyl = torch.empty(B * T, Cf, device=dev, dtype=bf16)
     K.layernorm_bwd(dfl, c.out, P["layer_norm.weight"], c.mean_f, c.rstd_f, dyl, gv("layer_norm.weight"),
                     gv("layer_norm.bias"))
-    # dU_last = dY * gelu'(U_last)
+    # dU_last = dY * gelu'(U_last)   (c.u holds the saved gelu' values)
     du = torch.empty(B, T, Cf, device=dev, dtype=bf16)
-    K.mul_dgelu(dyl, T * Cf, c.u[last], T * Cf, du, T * Cf, B, T * Cf)
+    K.mul_bf16(dyl, T * Cf, c.u[last], T * Cf, du, T * Cf, B, T * Cf)
     # ---- conv stack backward, layers last .. 1.  du: [B, To + 2*halo_i, C_i], data rows start at halo_i
     for i in range(last, 0, -1):
         co, k, s = g.conv_layers[i]
@@ -602,7 +697,7 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         else:
             # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1})
             dprev = torch.empty(B, in_rows, cin, device=dev, dtype=bf16)
-            flags, uprev = L.EPI_MUL_DGELU, c.u[i - 1]
+            flags, uprev = L.EPI_MUL_AUX, c.u[i - 1]
         if in_halo:  # halo rows must read as zero in the overlapped-view dgrad of layer i-1
             K.zero_rows(dprev, 0, in_rows * cin, cin, B)
             K.zero_rows(dprev, (in_rows - 1) * cin, in_rows * cin, cin, B)

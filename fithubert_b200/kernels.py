@@ -39,7 +39,7 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
              num_ob=1, ob_mod=1, num_cb=1, a_coord=(0, 0, 0, 0), b_coord=(0, 0, 0, 0),
              d_ld: int, d_hi_stride=0, d_lo_stride=0, flags=0, split_k=0, bias=None, residual=None,
              aux_in=None, aux_out=None, row_valid=None, loss_target=None, loss_acc=None,
-             loss_weight=0.0, grad_scale=0.0, d_offset_elems=0, a_c1_off=0, b_c1_off=0) -> None:
+             loss_weight=0.0, grad_scale=0.0, d_offset_elems=0, a_c1_off=0, b_c1_off=0, bias_hi_stride=0) -> None:
     g = L.GemmArgs()
     g.a, g.b = a, b
     g.a_major, g.b_major = a_major, b_major
@@ -61,6 +61,7 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
         # "laid out like D": same element offset as the output
         setattr(g, name, None if t is None else t.data_ptr() + d_offset_elems * t.element_size())
     g.loss_weight, g.grad_scale = loss_weight, grad_scale
+    g.bias_hi_stride = bias_hi_stride
     if _GEMM_TIMING["on"]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -72,9 +73,11 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, gelu=False,
-           residual=None, row_valid=None, rows_per_batch=0, preact_out=None, out_dtype=bf16,
+           residual=None, row_valid=None, rows_per_batch=0, preact_out=None, dgelu_out=None, out_dtype=bf16,
            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y[M,N] = epi(x[M,K] @ w[N,K]^T).  x, w bf16 row-major (x may be a strided 2-D view)."""
+    """y[M,N] = epi(x[M,K] @ w[N,K]^T).  x, w bf16 row-major (x may be a strided 2-D view).
+    preact_out: also store the value before GELU / residual; dgelu_out: store gelu'(that value) instead
+    (what the backward epilogue multiplies by: FHB_EPI_MUL_AUX)."""
     _cuda(x)
     M, K = x.shape
     N = w.shape[0]
@@ -86,7 +89,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         flags |= L.EPI_GELU
     if residual is not None:
         flags |= L.EPI_RESIDUAL
-    if preact_out is not None:
+    if dgelu_out is not None:
+        assert preact_out is None
+        flags |= L.EPI_STORE_PREACT | L.EPI_AUX_DGELU
+        preact_out = dgelu_out
+    elif preact_out is not None:
         flags |= L.EPI_STORE_PREACT
     if row_valid is not None:
         # rows are [batch, rows_per_batch] flattened: run as a batched problem so ob_hi = sample
@@ -102,16 +109,19 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return y
 
 
-def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, dgelu_of=None, residual=None,
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, dgelu_of=None, mul_aux=None, residual=None,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dx[M,K] = dy[M,N] @ w[N,K]  (w consumed MN-major: no transposed copy)."""
+    """dx[M,K] = dy[M,N] @ w[N,K]  (w consumed MN-major: no transposed copy), optionally * gelu'(dgelu_of)
+    or * mul_aux (a saved gelu'), + residual."""
     M, N = dy.shape
     K = w.shape[1]
     dx = out if out is not None else torch.empty(M, K, device=dy.device, dtype=bf16)
-    flags = (L.EPI_MUL_DGELU if dgelu_of is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0)
+    assert dgelu_of is None or mul_aux is None
+    flags = (L.EPI_MUL_DGELU if dgelu_of is not None else 0) | (L.EPI_MUL_AUX if mul_aux is not None else 0) | \
+        (L.EPI_RESIDUAL if residual is not None else 0)
     b3 = L.tensor3(data_ptr=w.data_ptr(), dim=(K, N, 1), stride=(w.stride(0), w.stride(0) * N))
-    gemm_raw(L.tensor3(dy), b3, dx, M, K, N, b_major=1, d_ld=dx.stride(0), flags=flags, aux_in=dgelu_of,
-             residual=residual)
+    gemm_raw(L.tensor3(dy), b3, dx, M, K, N, b_major=1, d_ld=dx.stride(0), flags=flags,
+             aux_in=dgelu_of if dgelu_of is not None else mul_aux, residual=residual)
     return dx
 
 
@@ -165,11 +175,13 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=None, dy2=None):
+    """dxsum (fp32 [C], accumulated): column sums of dx = bias gradient of the linear layer that produced x.
+    dy2: optional second gradient stream, summed with dy on load."""
     rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
-    L.check(L.lib().fhb_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dres),
-                                      L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), C.c_int64(rows), Cd, L.stream_ptr()),
-            "fhb_layernorm_bwd")
+    L.check(L.lib().fhb_layernorm_bwd(L.ptr(dy), L.ptr(dy2), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dres),
+                                      L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dxsum), C.c_int64(rows), Cd,
+                                      L.stream_ptr()), "fhb_layernorm_bwd")
     return dx
 
 
@@ -215,10 +227,11 @@ def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale):
                                  L.ptr(delta_ws), B, T, H, d, _f(scale), L.stream_ptr()), "fhb_attn_bwd")
 
 
-def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0):
+def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0,
+                 dbias=None, dbias_layer_stride=0):
     L.check(L.lib().fhb_distill_loss_fwd_bwd(L.ptr(pred), L.ptr(tgt), L.ptr(weights), L.ptr(layer_loss), L.ptr(dpred),
-                                             n_layers, B, Tp, Tt, D, loss_type, _f(grad_scale), L.stream_ptr()),
-            "fhb_distill_loss_fwd_bwd")
+                                             L.ptr(dbias), C.c_int64(dbias_layer_stride), n_layers, B, Tp, Tt, D,
+                                             loss_type, _f(grad_scale), L.stream_ptr()), "fhb_distill_loss_fwd_bwd")
 
 
 def adamw_multi(table, n_tensors, max_n, lr, beta1, beta2, eps, wd, step, mode=0, grad_scale=1.0):
@@ -236,6 +249,14 @@ def colsum(x2d, out):
             "fhb_colsum")
 
 
+def colsum_batched(x3d, out, out_bstride):
+    """x3d [n, rows, C] (contiguous), out: fp32 view whose batch b lives at out + b * out_bstride elements."""
+    n, rows, Cd = x3d.shape
+    L.check(L.lib().fhb_colsum_batched(L.ptr(x3d), C.c_int64(rows), Cd, C.c_int64(x3d.stride(1)),
+                                       C.c_int64(x3d.stride(0)), L.ptr(out), C.c_int64(out_bstride), n, L.stream_ptr()),
+            "fhb_colsum_batched")
+
+
 def add_bf16(a, b, y):
     L.check(L.lib().fhb_add_bf16(L.ptr(a), L.ptr(b), L.ptr(y), C.c_int64(a.numel()), L.stream_ptr()), "fhb_add_bf16")
     return y
@@ -245,6 +266,11 @@ def mul_dgelu(dy, dy_bs, u, u_bs, out, out_bs, B, n, *, u_off=0, out_off=0):
     L.check(L.lib().fhb_mul_dgelu(L.ptr(dy), C.c_int64(dy_bs), C.c_void_p(u.data_ptr() + 2 * u_off), C.c_int64(u_bs),
                                   C.c_void_p(out.data_ptr() + 2 * out_off), C.c_int64(out_bs), B, C.c_int64(n),
                                   L.stream_ptr()), "fhb_mul_dgelu")
+
+
+def mul_bf16(a, a_bs, m, m_bs, out, out_bs, B, n):
+    L.check(L.lib().fhb_mul_bf16(L.ptr(a), C.c_int64(a_bs), L.ptr(m), C.c_int64(m_bs), L.ptr(out), C.c_int64(out_bs), B,
+                                 C.c_int64(n), L.stream_ptr()), "fhb_mul_bf16")
 
 
 def mask_lengths(mask_u8, lengths):

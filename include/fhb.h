@@ -52,7 +52,9 @@ enum {
   FHB_EPI_MUL_DGELU = 32,   /* * gelu'(aux_in[m][n])  (backward through a fused GELU)        */
   FHB_EPI_OUT_F32 = 64,     /* D is fp32 (default bf16)                                      */
   FHB_EPI_ATOMIC_ADD = 128, /* D += (fp32 atomics; required when split_k > 1)                */
-  FHB_EPI_SQDIFF = 256      /* fused distillation loss, see fhb_gemm_args.loss_*             */
+  FHB_EPI_SQDIFF = 256,     /* fused distillation loss, see fhb_gemm_args.loss_*             */
+  FHB_EPI_AUX_DGELU = 512,  /* with STORE_PREACT: aux_out = gelu'(value before GELU) instead  */
+  FHB_EPI_MUL_AUX = 1024    /* * aux_in[m][n] (e.g. a gelu' saved by FHB_EPI_AUX_DGELU)       */
 };
 
 typedef struct {
@@ -79,6 +81,7 @@ typedef struct {
   const void* loss_target;  /* bf16, laid out like D                                         */
   float* loss_acc;
   float loss_weight, grad_scale;
+  int64_t bias_hi_stride;   /* elements: batch ob_hi reads bias + ob_hi * bias_hi_stride (0 = shared bias)  */
 } fhb_gemm_args;
 
 int fhb_gemm(const fhb_gemm_args* args, fhb_stream_t stream);
@@ -118,9 +121,10 @@ int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* args, fhb_stream_t stream);
  * (fp32, atomically ACCUMULATED: zero them first). */
 int fhb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                       int64_t rows, int32_t C, float eps, fhb_stream_t stream);
-int fhb_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C,
-                      fhb_stream_t stream);
+int fhb_layernorm_bwd(const void* dy, const void* dy2 /* optional: gradient = dy + dy2 */, const void* x,
+                      const float* gamma, const float* mean, const float* rstd,
+                      const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows,
+                      int32_t C, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ positional conv (K5) helpers
  * The grouped Conv1d(k=128, pad=64, groups=16) of modules/module.py:186-200,276-278 runs as a batched
@@ -168,10 +172,13 @@ int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const v
  * loss_l = w_l * mean_{b,t,d} (pred_l - tgt_l)^2 ; dpred_l = 2 w_l (pred_l - tgt_l) / (B*T'*D)
  * Replaces train.py:250-267 (two torch.stack copies), :282-293 (mse, weighting, mean).  pred: bf16
  * [n_layers][B][Tp][D] (Tp = T' frames); tgt: bf16 [n_layers][B][Tt][D] with Tt >= Tp (narrow, :282).
- * layer_loss (fp32 [n_layers]) is ACCUMULATED: zero it first.  dpred may alias pred. */
+ * layer_loss (fp32 [n_layers]) is ACCUMULATED: zero it first.  dpred may alias pred.  dbias (optional):
+ * dbias[l * dbias_layer_stride + d] += sum_{b,t} dpred_l[b][t][d], the gradient of the bias of the Linear that
+ * produced pred_l (LayerWiseProjHead.lin_proj, modules/module.py:661). */
 int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const float* weights, float* layer_loss,
-                             void* dpred, int32_t n_layers, int32_t B, int32_t Tp, int32_t Tt, int32_t D,
-                             int32_t loss_type /*0 mse, 1 l1*/, float grad_scale, fhb_stream_t stream);
+                             void* dpred, float* dbias, int64_t dbias_layer_stride, int32_t n_layers, int32_t B,
+                             int32_t Tp, int32_t Tt, int32_t D, int32_t loss_type /*0 mse, 1 l1*/, float grad_scale,
+                             fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ fused AdamW (K11)
  * ONE launch over a device-resident table of tensors.  Replaces s3prl get_optimizer ->
@@ -211,12 +218,18 @@ int fhb_prep_multi(const fhb_prep_tensor* table_dev, int32_t n_tensors, int64_t 
 /* ------------------------------------------------------------------ small helpers */
 /* out[c] += sum_rows x[row][c]   (bias gradients); x bf16 [rows][ld], out fp32 accumulated atomically */
 int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, float* out, fhb_stream_t stream);
+/* the same over `batches` matrices: x + b * x_bstride (elements) -> out + b * out_bstride */
+int fhb_colsum_batched(const void* x, int64_t rows, int32_t C, int64_t ld, int64_t x_bstride, float* out,
+                       int64_t out_bstride, int32_t batches, fhb_stream_t stream);
 /* y = a + b (bf16, n % 8 == 0), used where two gradient streams meet */
 int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t stream);
 /* out = dy * gelu'(u) over B segments of n bf16 elements (independent batch strides); the one place a
  * GELU derivative is not a GEMM epilogue: LayerNorm(512)-backward -> last conv layer (module.py:73) */
 int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_bstride, void* out,
                   int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
+/* out = a * m elementwise (bf16), same batching; m is a multiplier saved by FHB_EPI_AUX_DGELU */
+int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstride, void* out,
+                 int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
 /* zero `height` runs of `width_bytes` bytes, `pitch_bytes` apart (halo rows / borders of strided buffers);
  * a cudaMemset2DAsync, no kernel */
 int fhb_memset2d(void* ptr, int64_t pitch_bytes, int64_t width_bytes, int64_t height, fhb_stream_t stream);

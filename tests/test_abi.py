@@ -39,8 +39,8 @@ def test_arg_errors_do_not_need_a_gpu(lib):
     assert rc == -1 and b"m,n,k" in lib.fhb_last_error()
     rc = lib.fhb_layernorm_fwd(None, None, None, None, None, None, C.c_int64(4), 480, C.c_float(1e-5), None)
     assert rc == -1 and b"null" in lib.fhb_last_error()
-    rc = lib.fhb_distill_loss_fwd_bwd(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), None, 12, 2, 10, 11, 768, 7,
-                                      C.c_float(1.0), None)
+    rc = lib.fhb_distill_loss_fwd_bwd(C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), None, None, C.c_int64(0),
+                                      12, 2, 10, 11, 768, 7, C.c_float(1.0), None)
     assert rc == -1 and b"rec_loss_type must be one of 'l1', 'mse'." in lib.fhb_last_error()
 
 

@@ -77,6 +77,20 @@ def test_gemm_variants(F):
     uu = u.float().requires_grad_(True)
     Fn.gelu(uu).backward(dy.float() @ w2.float())
     assert rel(K.linear_dgrad(dy, w2, dgelu_of=u, residual=rr), uu.grad + rr.float()) < 1e-2
+    assert rel(K.linear_dgrad(dy, w2, dgelu_of=u), uu.grad) < 1e-2
+    assert rel(K.linear_dgrad(dy, w2, residual=rr), dy.float() @ w2.float() + rr.float()) < 1e-2
+    # forward epilogue saves gelu'(pre-activation); backward epilogue multiplies by it (TMA-staged input ring)
+    for (M, N, Kd) in [(700, 480, 480), (300, 1440, 96), (257, 48, 128), (1000, 256, 768)]:
+        x, w, b = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev)
+        pre = (x.float() @ w.float().t() + b).requires_grad_(True)
+        gp = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        y = K.linear(x, w, b, gelu=True, dgelu_out=gp)
+        Fn.gelu(pre).sum().backward()
+        assert rel(y, Fn.gelu(pre)) < 1e-2 and rel(gp, pre.grad) < 1e-2
+        dy2, w3, r2 = rnd(M, 192), rnd(192, N, sc=0.05), rnd(M, N)
+        ref = (dy2.float() @ w3.float()) * gp.float()
+        assert rel(K.linear_dgrad(dy2, w3, mul_aux=gp), ref) < 1e-2
+        assert rel(K.linear_dgrad(dy2, w3, mul_aux=gp, residual=r2), ref + r2.float()) < 1e-2
     dy, xx = rnd(5000, 480, sc=0.1), rnd(5000, 960)
     assert rel(K.linear_wgrad(dy, xx), dy.float().t() @ xx.float()) < 2e-3
     # k=3,s=2 convolution as an overlapping-row TMA view
@@ -109,6 +123,13 @@ def test_layernorm_fwd_bwd(F):
         dx, dg, db = torch.empty_like(x), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
         K.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db)
         assert rel(dx, xr.grad) < 1e-2 and rel(dg, gr.grad) < 1e-3 and rel(db, br.grad) < 1e-3
+        # two gradient streams summed on load + fused column sums of dx (bias gradient of the producer of x)
+        dya, dyb = (0.5 * dy.float() + 1).bfloat16(), (0.5 * dy.float() - 1).bfloat16()
+        dx2, dg2, db2, dsum = torch.empty_like(x), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), \
+            torch.zeros(C, device="cuda")
+        K.layernorm_bwd(dya, x, g, mean, rstd, dx2, dg2, db2, dxsum=dsum, dy2=dyb)
+        assert rel(dx2, xr.grad) < 1.5e-2 and rel(dg2, gr.grad) < 5e-3 and rel(db2, br.grad) < 5e-3
+        assert rel(dsum, xr.grad.sum(0)) < 5e-3  # fp32 sums of the un-rounded dx
 
 
 def test_conv0_groupnorm_gelu_fwd_bwd(F):
@@ -135,13 +156,16 @@ def test_conv0_groupnorm_gelu_fwd_bwd(F):
     assert rel(dw, w.grad.view(C, 10)) < 1e-2 and rel(dg, g.grad) < 1e-2 and rel(db, b.grad) < 1e-2
 
 
-@pytest.mark.parametrize("d,T", [(40, 389), (64, 779), (24, 50), (16, 13)])
-def test_attention_fwd_bwd(F, d, T):
+@pytest.mark.parametrize("d,T,amp,short", [(40, 389, 1.0, 37), (64, 779, 1.0, 37), (24, 50, 1.0, 37), (16, 13, 1.0, 37),
+                                           (64, 779, 3.0, 600), (40, 389, 3.0, 300), (64, 130, 1.0, 129), (40, 128, 2.0, 1)])
+def test_attention_fwd_bwd(F, d, T, amp, short):
+    """d = 64 / 40 run the tcgen05 forward (lazy-rescale online softmax: amp = 3 makes the running maximum move by
+    far more than the 2^8 rescale threshold between key tiles); `short` leaves whole key tiles masked."""
     from fithubert_b200 import kernels as K
     torch.manual_seed(3)
     B, H = 2, 3
-    qkv = torch.randn(B, T, 3 * H * d, device="cuda").bfloat16()
-    valid = [T, max(1, T - 37)]
+    qkv = (amp * torch.randn(B, T, 3 * H * d, device="cuda")).bfloat16()
+    valid = [T, max(1, T - short)]
     vt = torch.tensor(valid, device="cuda", dtype=torch.int32)
     out = torch.empty(B * T, H * d, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(B, H, T, device="cuda")
@@ -149,10 +173,11 @@ def test_attention_fwd_bwd(F, d, T):
     q3 = qkv.float().requires_grad_(True)
     q, k, v = (t.reshape(B, T, H, d).transpose(1, 2) for t in q3.chunk(3, dim=-1))
     mask = (torch.arange(T, device="cuda")[None] >= vt[:, None])[:, None, None, :]
-    s = (q @ k.transpose(-1, -2)) * d ** -0.5
-    p = torch.softmax(s.masked_fill(mask, float("-inf")), -1)
+    s = ((q @ k.transpose(-1, -2)) * d ** -0.5).masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, -1)
     ref = (p @ v).transpose(1, 2).reshape(B, T, H * d)
     assert rel(out.view(B, T, -1), ref) < 1e-2
+    assert float((lse - torch.logsumexp(s, -1)).abs().max()) < 2e-2
     do = torch.randn(B, T, H * d, device="cuda").bfloat16()
     ref.backward(do.float())
     dqkv = torch.empty_like(qkv)
@@ -175,6 +200,11 @@ def test_distill_loss_and_adamw(F):
     ll, dp = torch.zeros(n, device="cuda"), torch.empty_like(pred)
     K.distill_loss(pred, tgt, torch.tensor(w, device="cuda"), ll, dp, n, B, Tp, Tt, D, 0, 1.0)
     assert rel(ll, per) < 1e-5 and rel(dp, pr.grad) < 1e-2
+    # fused bias gradient: per-layer column sums of the gradient, written at a layer stride
+    ll2, dp2, db = torch.zeros(n, device="cuda"), torch.empty_like(pred), torch.zeros(n, D + 24, device="cuda")
+    K.distill_loss(pred, tgt, torch.tensor(w, device="cuda"), ll2, dp2, n, B, Tp, Tt, D, 0, 1.0, dbias=db,
+                   dbias_layer_stride=D + 24)
+    assert torch.equal(dp2, dp) and rel(db[:, :D], dp.float().sum((1, 2))) < 1e-3 and float(db[:, D:].abs().max()) == 0
     # AdamW, both modes, with a strided gradient view, vs the oracle's restatement
     for mode in ("s3prl", "torch"):
         p0 = torch.randn(6, 5, 2)
@@ -266,10 +296,15 @@ def test_fused_step_equals_autograd_path_and_updates_weights(F):
             continue
         pr = before[n].cpu().clone()
         O.adamw_step(pr, g["grads"][n], torch.zeros_like(pr), torch.zeros_like(pr), 1, lr)
-        # Adam's first step is lr * sign(g) (+eps): compare the update, tolerance on its scale
+        # Adam's first step is lr * g / (|g| + eps), i.e. a sign function: it can only be compared where the
+        # bf16 gradient error (<= GTOL * max|g|, checked above) cannot flip the sign; everywhere the step is
+        # bounded by lr (+ the decoupled decay).
         upd, upd_ref = (p.detach().cpu() - before[n].cpu()), (pr - before[n].cpu())
-        big = g["grads"][n].abs() > 1e-3 * g["grads"][n].abs().max()
-        assert float((upd - upd_ref)[big].abs().max()) < 0.25 * lr + 1e-9, n
+        gmax = g["grads"][n].abs().max()
+        big = g["grads"][n].abs() > 2 * GTOL * gmax
+        if bool(big.any()) and gmax > 1e-4:
+            assert float((upd - upd_ref)[big].abs().max()) < 0.25 * lr + 1e-9, n
+        assert float(upd.abs().max()) <= lr * (1 + 1e-3) + 1e-9, n
     # the reference-style calculate_loss API gives the same loss dict structure
     s_res, t_res = step(g["source"].cuda(), g["padding_mask"])
     total, losses = step.calculate_loss(s_res, t_res)

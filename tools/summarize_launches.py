@@ -17,7 +17,13 @@ def main(path, skip=0):
         unit = r.get("Metric Unit", "ns")
         v = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
         rows.append((int(r["ID"]), r["Kernel Name"], v))
-    rows = rows[skip:]
+    if skip == "step":
+        # keep the last full step: from just after the second-to-last adamw launch to the last one (inclusive)
+        idx = [i for i, r in enumerate(rows) if "adamw" in r[1]]
+        if len(idx) >= 2:
+            rows = rows[idx[-2] + 1:idx[-1] + 1]
+    else:
+        rows = rows[int(skip):]
     tot = defaultdict(float)
     cnt = defaultdict(int)
     for _, k, v in rows:
@@ -33,4 +39,4 @@ def main(path, skip=0):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else 0)
