@@ -12,7 +12,8 @@ class _StudentFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, source, valid, *params):
         P, W, G = model.engine_state(True)
-        c = E.student_forward(P, W, model._geom, source, valid, train=True, heads="all", want_lr=False)
+        c = E.student_forward(P, W, model._geom, source, valid, train=True, heads="all", want_lr=False,
+                              drop=model.drop_cfg())
         ctx.model, ctx.c, ctx.names = model, c, [n for n, _ in model.named_parameters()]
         model._last_ctx = c
         return (c.preds, *c.layers)

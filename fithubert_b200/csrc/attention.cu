@@ -119,7 +119,8 @@ __device__ __forceinline__ void acc_to_frags(const float (*s)[4], uint32_t (*pf)
 template <int DP>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ valid, __nv_bfloat16* __restrict__ out,
-                float* __restrict__ lse, int T, int H, int d, float scale) {
+                float* __restrict__ lse, int T, int H, int d, float scale, uint32_t drop_seed, uint32_t drop_thr,
+                float drop_scale) {
   __shared__ __align__(16) __nv_bfloat16 Qs[kTile * (DP + 8)];
   __shared__ __align__(16) __nv_bfloat16 Ks[kTile * (DP + 8)];
   __shared__ __align__(16) __nv_bfloat16 Vs[kTile * (DP + 8)];
@@ -172,7 +173,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ v
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_i[r], mx[r]);
-      alpha[r] = exp2f(m_i[r] - m_new);
+      alpha[r] = ex2_approx(m_i[r] - m_new);
       m_i[r] = m_new;
       l_i[r] *= alpha[r];
     }
@@ -180,8 +181,22 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ v
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        s[i][e] = exp2f(s[i][e] - m_i[e >> 1]);
+        s[i][e] = ex2_approx(s[i][e] - m_i[e >> 1]);
         l_i[e >> 1] += s[i][e];
+      }
+    }
+    if (drop_thr) {  // attention dropout on the probabilities (l stays un-dropped); pairs = adjacent keys
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t q = (uint32_t)((b * H + h) * T + q0 + warp * 16 + g + r * 8);
+          float m0, m1;
+          dropout_pair(drop_seed, q * (uint32_t)((T + 1) >> 1) + (uint32_t)((k0 + i * 8 + 2 * tq) >> 1), drop_thr, drop_scale,
+                       m0, m1);
+          s[i][2 * r] *= m0;
+          s[i][2 * r + 1] *= m1;
+        }
       }
     }
 #pragma unroll
@@ -245,7 +260,8 @@ template <int DP>
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ valid,
                     const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int d, float scale) {
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int d, float scale,
+                    uint32_t drop_seed, uint32_t drop_thr, float drop_scale) {
   __shared__ __align__(16) __nv_bfloat16 Ks[kTile * (DP + 8)];
   __shared__ __align__(16) __nv_bfloat16 Vs[kTile * (DP + 8)];
   __shared__ __align__(16) __nv_bfloat16 Qs[kTile * (DP + 8)];
@@ -308,9 +324,14 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict
         for (int e = 0; e < 4; ++e) {
           const int qc = i * 8 + 2 * tq + (e & 1);
           const bool ok = key_row[e >> 1] < nvalid;
-          const float p = ok ? exp2f(st[i][e] * sc - lse_s[qc]) : 0.f;
-          st[i][e] = p;
-          dp[i][e] = p * (dp[i][e] - delta_s[qc]) * scale;
+          const float p = ok ? ex2_approx(st[i][e] * sc - lse_s[qc]) : 0.f;
+          float mk = 1.f;  // dropout multiplier of P[q][key] (0 or 1/(1-p)); same hash as the forward
+          if (drop_thr) {
+            const uint32_t q = (uint32_t)((b * H + h) * T + q0 + qc);
+            mk = dropout_one(drop_seed, q * (uint32_t)(2 * ((T + 1) >> 1)) + (uint32_t)key_row[e >> 1], drop_thr, drop_scale);
+          }
+          st[i][e] = p * mk;                                        // dropped P -> dV
+          dp[i][e] = p * (dp[i][e] * mk - delta_s[qc]) * scale;   // dS = P o (dP_dropped o mask - delta)
         }
       }
       uint32_t pf[4][4];
@@ -342,7 +363,8 @@ template <int DP>
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ valid,
                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int d, float scale) {
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int H, int d, float scale,
+                   uint32_t drop_seed, uint32_t drop_thr, float drop_scale) {
   __shared__ __align__(16) __nv_bfloat16 Qs[kTile * (DP + 8)];
   __shared__ __align__(16) __nv_bfloat16 Ds[kTile * (DP + 8)];
   __shared__ __align__(16) __nv_bfloat16 Ks[kTile * (DP + 8)];
@@ -398,8 +420,14 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict_
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const bool ok = (k0 + i * 8 + 2 * tq + (e & 1)) < nvalid;
-        const float p = ok ? exp2f(s[i][e] * sc - lse_r[e >> 1]) : 0.f;
-        dp[i][e] = p * (dp[i][e] - delta_r[e >> 1]) * scale;
+        const float p = ok ? ex2_approx(s[i][e] * sc - lse_r[e >> 1]) : 0.f;
+        float mk = 1.f;
+        if (drop_thr) {
+          const uint32_t q = (uint32_t)((b * H + h) * T + q0 + warp * 16 + g + (e >> 1) * 8);
+          mk = dropout_one(drop_seed, q * (uint32_t)(2 * ((T + 1) >> 1)) + (uint32_t)(k0 + i * 8 + 2 * tq + (e & 1)), drop_thr,
+                           drop_scale);
+        }
+        dp[i][e] = p * (dp[i][e] * mk - delta_r[e >> 1]) * scale;
       }
     }
     uint32_t pf[4][4];
@@ -435,28 +463,41 @@ int check_shape(int B, int T, int H, int d) {
   else { constexpr int DP = 64; CALL; }
 
 int fhb_attn_fwd_tc(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
-                    int32_t d, float scale, cudaStream_t s);  // attention_tc.cu (tcgen05 path, head_dim 64 / 40)
+                    int32_t d, float scale, uint32_t drop_seed, float drop_p, cudaStream_t s);  // attention_tc.cu (tcgen05 path, head_dim 64 / 40)
+
+int check_drop(int32_t B, int32_t T, int32_t H, float drop_p) {
+  FHB_ARG_CHECK(drop_p >= 0.f && drop_p < 1.f, "attention: drop_p=%f must be in [0, 1)", (double)drop_p);
+  FHB_ARG_CHECK(drop_p == 0.f || (long long)B * H * T * (T + 1) < (1LL << 32), "attention: dropout index space exceeds 32 bits");
+  return 0;
+}
 
 extern "C" int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T,
-                            int32_t H, int32_t d, float scale, fhb_stream_t stream) {
+                            int32_t H, int32_t d, float scale, uint32_t drop_seed, float drop_p, fhb_stream_t stream) {
   int rc = check_shape(B, T, H, d);
   if (rc) return rc;
+  if ((rc = check_drop(B, T, H, drop_p)) != 0) return rc;
+  const uint32_t thr = drop_p > 0.f ? fhb_dropout_thr16(drop_p) : 0u;
+  const float dsc = fhb_dropout_scale(drop_p);
   FHB_ARG_CHECK(qkv && out, "attn_fwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static const bool no_tc = getenv("FHB_ATTN_NO_TC") != nullptr;
-  if ((d == 64 || d == 40) && !no_tc) return fhb_attn_fwd_tc(qkv, valid, out, lse, B, T, H, d, scale, s);
+  if ((d == 64 || d == 40) && !no_tc) return fhb_attn_fwd_tc(qkv, valid, out, lse, B, T, H, d, scale, drop_seed, drop_p, s);
   dim3 grid((T + kTile - 1) / kTile, H, B);
   FHB_ATTN_DISPATCH(d, (attn_fwd_kernel<DP><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), valid,
-                                                                   static_cast<__nv_bfloat16*>(out), lse, T, H, d, scale)));
+                                                                   static_cast<__nv_bfloat16*>(out), lse, T, H, d, scale,
+                                                                   drop_seed, thr, dsc)));
   FHB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const void* dout, const float* lse,
                             void* dqkv, float* delta_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
-                            fhb_stream_t stream) {
+                            uint32_t drop_seed, float drop_p, fhb_stream_t stream) {
   int rc = check_shape(B, T, H, d);
   if (rc) return rc;
+  if ((rc = check_drop(B, T, H, drop_p)) != 0) return rc;
+  const uint32_t thr = drop_p > 0.f ? fhb_dropout_thr16(drop_p) : 0u;
+  const float dsc = fhb_dropout_scale(drop_p);
   FHB_ARG_CHECK(qkv && out && dout && lse && dqkv && delta_ws, "attn_bwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n = (long long)B * T * H;
@@ -466,11 +507,11 @@ extern "C" int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* o
   dim3 grid((T + kTile - 1) / kTile, H, B);
   FHB_ATTN_DISPATCH(d, (attn_bwd_dkv_kernel<DP><<<grid, 128, 0, s>>>(
                            static_cast<const __nv_bfloat16*>(qkv), valid, static_cast<const __nv_bfloat16*>(dout), lse,
-                           delta_ws, static_cast<__nv_bfloat16*>(dqkv), T, H, d, scale)));
+                           delta_ws, static_cast<__nv_bfloat16*>(dqkv), T, H, d, scale, drop_seed, thr, dsc)));
   FHB_LAUNCH_CHECK();
   FHB_ATTN_DISPATCH(d, (attn_bwd_dq_kernel<DP><<<grid, 128, 0, s>>>(
                            static_cast<const __nv_bfloat16*>(qkv), valid, static_cast<const __nv_bfloat16*>(dout), lse,
-                           delta_ws, static_cast<__nv_bfloat16*>(dqkv), T, H, d, scale)));
+                           delta_ws, static_cast<__nv_bfloat16*>(dqkv), T, H, d, scale, drop_seed, thr, dsc)));
   FHB_LAUNCH_CHECK();
   return 0;
 }

@@ -49,10 +49,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // HD: logical head dim (64 or 40); DK = HD rounded up to the UMMA k-step / n-step of 16
-template <int HD>
+template <int HD, bool DROP>
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __restrict__ valid,
-                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale) {
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale,
+                   uint32_t drop_seed, uint32_t drop_thr, float drop_scale) {
   constexpr int DK = (HD + 15) / 16 * 16;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -166,6 +167,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
     const float sc = scale * kLog2e;
     float m_i = -INFINITY, l_i = 0.f;
     const uint32_t prow = smem_u32(sP) + row_in_tile * 128;
+    // dropout pair index of (b, h, q, k): ((b*H + h)*T + q) * ceil(T/2) + (k >> 1)
+    const uint32_t drop_row = (uint32_t)(((b * H + h) * T + q0 + row_in_tile) * ((T + 1) >> 1));
     for (int j = 0; j < nt; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -231,6 +234,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) ls4[i & 3] += pv[i];
+        if (DROP) {  // attention dropout on the probabilities (the row sum l stays un-dropped)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float m0, m1;
+            dropout_pair(drop_seed, drop_row + (uint32_t)((j * kTK + c) >> 1) + i, drop_thr, drop_scale, m0, m1);
+            pv[2 * i] *= m0;
+            pv[2 * i + 1] *= m1;
+          }
+        }
         const uint32_t atom = (uint32_t)(c >> 6) * kTileBytes;
         const uint32_t ch = (uint32_t)((c & 63) >> 3);
         st_shared_v4(prow + atom + (((ch) ^ rsw) << 4), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]),
@@ -275,7 +287,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
 
 template <int HD>
 int launch_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H, float scale,
-               cudaStream_t s) {
+               uint32_t drop_seed, float drop_p, cudaStream_t s) {
   CUtensorMap tm;
   const int64_t dim[3] = {3LL * H * HD, T, B};
   const int64_t stride[2] = {3LL * H * HD, 3LL * H * HD * T};
@@ -283,11 +295,17 @@ int launch_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   dim3 grid((T + kTQ - 1) / kTQ, H, B);
-  attn_fwd_tc_kernel<HD><<<grid, 160, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale);
+  if (drop_p > 0.f)
+    attn_fwd_tc_kernel<HD, true><<<grid, 160, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale,
+                                                          drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p));
+  else
+    attn_fwd_tc_kernel<HD, false><<<grid, 160, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale, 0u,
+                                                           0u, 1.f);
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -296,7 +314,7 @@ int launch_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int
 
 // Called by fhb_attn_fwd (attention.cu) for head_dim 64 / 40.
 int fhb_attn_fwd_tc(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
-                    int32_t d, float scale, cudaStream_t s) {
-  if (d == 64) return launch_fwd<64>(qkv, valid, out, lse, B, T, H, scale, s);
-  return launch_fwd<40>(qkv, valid, out, lse, B, T, H, scale, s);
+                    int32_t d, float scale, uint32_t drop_seed, float drop_p, cudaStream_t s) {
+  if (d == 64) return launch_fwd<64>(qkv, valid, out, lse, B, T, H, scale, drop_seed, drop_p, s);
+  return launch_fwd<40>(qkv, valid, out, lse, B, T, H, scale, drop_seed, drop_p, s);
 }

@@ -44,33 +44,81 @@ static inline int fhb_num_sms() {
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- small math
-// Exact (erf-based) GELU.  Phi(x) = 1 - 0.5 erfc(x/sqrt2) with erfc(z) = exp(-z q(z)), q a degree-6
-// minimax fit of -ln(erfc(z))/z on [0, 6] (fitted offline with numpy/scipy; relative error of erfc
-// <= 1.2e-4 everywhere incl. the tails, |gelu error| <= 2e-6: far below bf16 resolution).  One MUFU
-// (ex2) + ~13 FP32 ops instead of erff's ~40: the GELU epilogues (3.5 G evaluations per distillation
-// step, 8 epilogue warps per SM) are issue-bound otherwise.
+// Exact (erf-based) GELU, written for issue-bound GEMM epilogues (3.5 G evaluations per distillation step on
+// 8 epilogue warps per SM):  gelu(x) = max(x, 0) - |x| * T(|x|),  T(a) = 0.5 erfc(a / sqrt2) = 2^t(a), t a
+// degree-4 polynomial without constant term (fitted offline with scipy: -ln erfc(z) / z as a cubic in z,
+// folded with the 1/sqrt2, log2 e and 0.5 factors).  |gelu error| <= 1.3e-5, |gelu' error| <= 2.1e-5 over all
+// x (bf16 resolution near 1 is 4e-3).  gelu: FMNMX, 4 FFMA, MUFU.EX2, FMNMX, FFMA = 8 instructions;
+// gelu' (one more MUFU): phi + x * pdf = step(x) + sign(x) * (|x| pdf(|x|) - T(|x|)).
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float phi_cdf(float x) {
-  const float z = fminf(fabsf(x) * 0.70710678118654752f, 6.0f);
-  float q = fmaf(1.054685981e-05f, z, -2.824920404e-04f);
-  q = fmaf(q, z, 3.301705543e-03f);
-  q = fmaf(q, z, -2.262040308e-02f);
-  q = fmaf(q, z, 1.044878894e-01f);
-  q = fmaf(q, z, 6.363186673e-01f);
-  q = fmaf(q, z, 1.128385771e+00f);
-  const float half_tail = ex2_approx(fmaf(z * q, -1.4426950408889634f, -1.0f));  // 0.5 * erfc(z)
-  return x >= 0.f ? 1.0f - half_tail : half_tail;
+// a = min(|x|, 6 sqrt2) -> 0.5 * erfc(a / sqrt2)
+__device__ __forceinline__ float gelu_tail(float a) {
+  float t = fmaf(4.389107953e-03f, a, -4.677256044e-02f);
+  t = fmaf(t, a, -4.635094653e-01f);
+  t = fmaf(t, a, -1.150136897e+00f);
+  t = fmaf(t, a, -1.0f);
+  return ex2_approx(t);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return x * phi_cdf(x); }
+__device__ __forceinline__ float gelu_abs_clamp(float x) { return fminf(fabsf(x), 8.4852814f); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float a = gelu_abs_clamp(x);
+  return fmaf(-a, gelu_tail(a), fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float gelu_grad_from(float x, float a, float tail) {
+  const float ak = a * 0.8493218003f;                              // a * sqrt(log2(e) / 2)
+  const float w = ex2_approx(-ak * ak);                           // exp(-a^2 / 2)
+  const float h = fmaf(a * 0.3989422804f, w, -tail);              // a * pdf(a) - T(a)
+  return x >= 0.f ? 1.0f + h : -h;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  // d/dx [x * Phi(x)] = Phi(x) + x * phi(x),  phi(x) = exp(-x^2/2) / sqrt(2 pi)
-  const float e = ex2_approx(x * x * -0.72134752044448170f);
-  return fmaf(x * 0.39894228040143268f, e, phi_cdf(x));
+  const float a = gelu_abs_clamp(x);
+  return gelu_grad_from(x, a, gelu_tail(a));
 }
+// y = gelu(x), g = gelu'(x) sharing the tail evaluation
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& g) {
+  const float a = gelu_abs_clamp(x);
+  const float tail = gelu_tail(a);
+  y = fmaf(-a, tail, fmaxf(x, 0.f));
+  g = gelu_grad_from(x, a, tail);
+}
+// ---------------------------------------------------------------- dropout (K13)
+// Counter-based masks: forward and backward kernels regenerate the same bits from (seed, element index), so no
+// mask tensor is ever stored.  One 32-bit hash (murmur3 finaliser) serves the element pair (2i, 2i+1): each
+// element keeps iff its 16-bit half >= thr16 = round(p * 65536).  nn.Dropout semantics: kept values are
+// scaled by 1 / (1 - p).  (torch's Philox stream cannot be reproduced; parity runs use p = 0)
+__device__ __forceinline__ uint32_t fhb_hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t dropout_pair_bits(uint32_t seed, uint32_t pair_idx) {
+  return fhb_hash32(pair_idx * 0x9E3779B1u + seed);
+}
+// multipliers (0 or scale) for elements 2*pair_idx and 2*pair_idx + 1
+__device__ __forceinline__ void dropout_pair(uint32_t seed, uint32_t pair_idx, uint32_t thr16, float scale, float& m0,
+                                             float& m1) {
+  const uint32_t bits = dropout_pair_bits(seed, pair_idx);
+  m0 = (bits & 0xFFFFu) >= thr16 ? scale : 0.f;
+  m1 = (bits >> 16) >= thr16 ? scale : 0.f;
+}
+__device__ __forceinline__ float dropout_one(uint32_t seed, uint32_t idx, uint32_t thr16, float scale) {
+  const uint32_t bits = dropout_pair_bits(seed, idx >> 1);
+  return ((idx & 1u) ? (bits >> 16) : (bits & 0xFFFFu)) >= thr16 ? scale : 0.f;
+}
+#endif  // __CUDACC__
+static inline uint32_t fhb_dropout_thr16(float p) {
+  const float t = p * 65536.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
+}
+static inline float fhb_dropout_scale(float p) { return 1.0f / (1.0f - (float)fhb_dropout_thr16(p) / 65536.0f); }
+#ifdef __CUDACC__
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -56,6 +56,8 @@ struct GemmParams {
   const __nv_bfloat16* loss_target;
   float* loss_acc;
   float loss_weight, grad_scale;
+  uint32_t drop_seed, drop_thr;
+  float drop_scale;
   int flags;
   uint32_t stage_tx_bytes;
   int total_tiles;
@@ -298,18 +300,38 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             v[4 * j + 3] += b4.w;
           }
         }
-        if (flags & FHB_EPI_STORE_PREACT) {
-          if (flags & FHB_EPI_AUX_DGELU) {
+        if ((flags & (FHB_EPI_GELU | FHB_EPI_AUX_DGELU)) == (FHB_EPI_GELU | FHB_EPI_AUX_DGELU)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pre[j] = gelu_erf_grad(v[j]);
-          } else {
+          for (int j = 0; j < 16; ++j) gelu_erf_both(v[j], v[j], pre[j]);
+        } else {
+          if (flags & FHB_EPI_STORE_PREACT) {
+            if (flags & FHB_EPI_AUX_DGELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pre[j] = v[j];
+              for (int j = 0; j < 16; ++j) pre[j] = gelu_erf_grad(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pre[j] = v[j];
+            }
+          }
+          if (flags & FHB_EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
           }
         }
-        if (flags & FHB_EPI_GELU) {
+        if (flags & FHB_EPI_DROPOUT) {
+          // element index = ((ob * m) + row) * n + column; one hash per column pair
+          const uint32_t pair0 = (uint32_t)((((long long)(t.ob_hi * p.ob_mod + t.ob_lo) * p.m + row) * p.n + t.n0 + c) >> 1);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 8; ++j) {
+            float m0, m1;
+            dropout_pair(p.drop_seed, pair0 + j, p.drop_thr, p.drop_scale, m0, m1);
+            v[2 * j] *= m0;
+            v[2 * j + 1] *= m1;
+            if (flags & FHB_EPI_AUX_DGELU) {
+              pre[2 * j] *= m0;
+              pre[2 * j + 1] *= m1;
+            }
+          }
         }
         if (EPI_IN) {
           const bool col_ok = row_ok && (t.n0 + c < p.n);
@@ -756,6 +778,13 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.loss_acc = a->loss_acc;
   p.loss_weight = a->loss_weight;
   p.grad_scale = a->grad_scale;
+  if (flags & FHB_EPI_DROPOUT) {
+    FHB_ARG_CHECK(a->drop_p >= 0.f && a->drop_p < 1.f, "gemm: drop_p=%f must be in [0, 1)", (double)a->drop_p);
+    FHB_ARG_CHECK((long long)num_ob * a->m * a->n < (1LL << 32) && a->n % 2 == 0, "gemm: dropout index space exceeds 32 bits");
+    p.drop_seed = a->drop_seed;
+    p.drop_thr = fhb_dropout_thr16(a->drop_p);
+    p.drop_scale = fhb_dropout_scale(a->drop_p);
+  }
   p.flags = flags;
 
   CUtensorMap ta, tb;

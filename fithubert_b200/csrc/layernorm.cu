@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                      const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows,
-                     int C) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
+                     __nv_bfloat16* __restrict__ dx_drop, uint32_t drop_seed, uint32_t drop_thr, float drop_scale,
+                     long long rows, int C) {
   extern __shared__ float sred[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
@@ -148,9 +149,25 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int j = 0; j < 8; ++j) {
           const float d = rs * (dxh[i][j] - s1 - xh[i][j] * s2);
           o[j] = dres ? o[j] + d : d;
-          if (DXSUM) pd[i][j] += o[j];
         }
         store8(dx + row * C + vi * 8, o);
+        if (dx_drop) {
+          // gradient through nn.Dropout on the branch that produced x (residual + dropout(branch)): the masked
+          // copy feeds the branch's dgrad / wgrad / bias gradient, the plain dx continues down the residual
+          const uint32_t pair0 = (uint32_t)((row * C + vi * 8) >> 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float m0, m1;
+            dropout_pair(drop_seed, pair0 + j, drop_thr, drop_scale, m0, m1);
+            o[2 * j] *= m0;
+            o[2 * j + 1] *= m1;
+          }
+          store8(dx_drop + row * C + vi * 8, o);
+        }
+        if (DXSUM) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pd[i][j] += o[j];
+        }
       }
     }
   }
@@ -199,8 +216,10 @@ extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float*
 
 extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x, const float* gamma, const float* mean,
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                                 float* dxsum, int64_t rows, int32_t C, fhb_stream_t stream) {
+                                 float* dxsum, void* dx_drop, uint32_t drop_seed, float drop_p, int64_t rows, int32_t C,
+                                 fhb_stream_t stream) {
   FHB_ARG_CHECK(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+  FHB_ARG_CHECK(!dx_drop || (drop_p >= 0.f && drop_p < 1.f && rows * C < (1LL << 32)), "layernorm_bwd: bad dropout arguments");
   FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_bwd: bad C=%d", C);
   if (rows == 0) return 0;
   // ~2 blocks per SM (register-limited), every warp streams several rows
@@ -213,7 +232,8 @@ extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x,
   layernorm_bwd_kernel<NV, DX><<<(unsigned)blocks, 256, sm, s>>>(                                                   \
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dy2),                               \
       static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,                                                      \
-      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum, rows, C)
+      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum,              \
+      static_cast<__nv_bfloat16*>(dx_drop), drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p), rows, C)
   if (dxsum) {
     if (nv == 1) FHB_LN_BWD(1, true); else if (nv == 2) FHB_LN_BWD(2, true); else FHB_LN_BWD(3, true);
   } else {

@@ -240,6 +240,24 @@ mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_
   }
 }
 
+__global__ void __launch_bounds__(256)
+dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long nvec, uint32_t seed,
+               uint32_t thr, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float m0, m1;
+      dropout_pair(seed, (uint32_t)(i * 4 + j), thr, scale, m0, m1);
+      const float2 p = unpack_bf16(aa[j]);
+      o[j] = pack_bf16(p.x * m0, p.y * m1);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // lengths[b] = number of zero bytes in mask[b][0..L)   (mask: 1 = padding)
 __global__ void __launch_bounds__(256) mask_lengths_kernel(const uint8_t* __restrict__ mask, long long L, int* __restrict__ lengths) {
   const uint8_t* row = mask + (long long)blockIdx.x * L;
@@ -370,6 +388,17 @@ extern "C" int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int
   mul_bf16_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(a), a_bstride, static_cast<const __nv_bfloat16*>(m), m_bstride,
       static_cast<__nv_bfloat16*>(out), out_bstride, n / 8);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, float p, fhb_stream_t stream) {
+  FHB_ARG_CHECK(x && y && n % 8 == 0 && n < (1LL << 32), "dropout: n must be a multiple of 8 and < 2^32");
+  FHB_ARG_CHECK(p >= 0.f && p < 1.f, "dropout: p=%f must be in [0, 1)", (double)p);
+  if (n == 0) return 0;
+  dropout_kernel<<<grid_x(n / 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n / 8, seed, fhb_dropout_thr16(p),
+      fhb_dropout_scale(p));
   FHB_LAUNCH_CHECK();
   return 0;
 }

@@ -174,6 +174,11 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
         dcg[(((long long)b * G + g) * Tp + t + pad_l) * cp + cc] = __float2bfloat16(dc);
       }
     }
+    // channel padding cg..cp-1 of every group: must read as zero in the dgrad GEMM (0-weight x garbage = NaN)
+    for (int i = lane; i < G * (cp - cg); i += 32) {
+      const int g = i / (cp - cg), cc = cg + i % (cp - cg);
+      dcg[(((long long)b * G + g) * Tp + t + pad_l) * cp + cc] = __float2bfloat16(0.f);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 24; ++i) {

@@ -173,7 +173,7 @@ class W2V2Distil(nn.Module):
             self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=bf16)
         tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf)
         P, W, G = sm.engine_state(True)
-        c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all")
+        c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
         # gradient written in place over the projections (they are not needed again)
         # the loss kernel also accumulates the lin_proj bias gradients (column sums of the gradient it writes)

@@ -37,6 +37,41 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _fmix32(x: int) -> int:
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+class DropCfg:
+    """Dropout probabilities of one training forward/backward (reference modules/model.py:489,
+    modules/module.py:294,566,573,578 + fairseq MultiheadAttention) and the seed its counter-based masks derive
+    from.  Each dropout site gets its own 32-bit seed; forward and backward kernels regenerate identical masks."""
+    SITE_INPUT, SITE_PROLOGUE, SITE_LAYER0 = 0, 1, 16
+    ATTN, DROP1, ACT, DROP3 = 0, 1, 2, 3
+
+    def __init__(self, seed: int, p_input=0.0, p_drop=0.0, p_attn=0.0, p_act=0.0):
+        self.seed = _fmix32(seed)
+        self.p_input, self.p_drop, self.p_attn, self.p_act = float(p_input), float(p_drop), float(p_attn), float(p_act)
+
+    def any(self) -> bool:
+        return max(self.p_input, self.p_drop, self.p_attn, self.p_act) > 0.0
+
+    def site(self, site_id: int, p: float):
+        """(seed, p) for one dropout site, or None when that site is inactive."""
+        if p <= 0.0:
+            return None
+        return (_fmix32(self.seed + 0x632BE5AB * (site_id + 1)), p)
+
+    def layer(self, l: int, which: int):
+        p = (self.p_attn, self.p_drop, self.p_act, self.p_drop)[which]
+        return self.site(self.SITE_LAYER0 + 4 * l + which, p)
+
+
 class Geometry:
     def __init__(self, conv_layers, E, F, H, G, kpos, n_layers, d_out=0, student=True):
         self.conv_layers = [tuple(c) for c in conv_layers]
@@ -362,7 +397,8 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool)
     return c
 
 
-def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Tensor], save: bool):
+def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Tensor], save: bool,
+                 drop: Optional[DropCfg] = None):
     """conv stack -> LayerNorm -> post_extract_proj -> (mask, pos-conv, +x, LayerNorm)
     = reference modules/model.py:428-489 + modules/module.py:273-281."""
     c = conv_stack_fwd(P, W, g, wave, save)
@@ -376,6 +412,9 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Ten
     c.f_ln = f_ln
     feats = K.linear(f_ln.view(B * T, Cf), W["pp.w"].view(E, Cf), P["post_extract_proj.bias"])
     c.feats = feats  # [B*T, E], padded frames NOT zeroed (reference `features_to_distill`)
+    d_in = drop.site(DropCfg.SITE_INPUT, drop.p_input) if drop is not None else None
+    if d_in is not None:  # dropout_input (modules/model.py:489); `features_to_distill` above stays un-dropped
+        feats = K.dropout(feats, torch.empty_like(feats), *d_in)
     # positional conv as one batched GEMM per (sample, group)
     G, cp, kp = g.G, g.cp, g.kpos
     Tp = T + kp
@@ -393,12 +432,15 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Ten
     c.rstd_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
     K.posconv_finish_fwd(feats, valid_t, conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"],
                          P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp)
+    d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
+    if d_pro is not None:  # F.dropout after the encoder LayerNorm (modules/module.py:294)
+        K.dropout(enc, enc, *d_pro)
     c.enc_in = enc
     return c
 
 
 def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, T, save: bool, want_lr: bool,
-              out: Optional[torch.Tensor] = None):
+              out: Optional[torch.Tensor] = None, drop: Optional[DropCfg] = None):
     """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E]."""
     E, F, H, d = g.E, g.F, g.H, g.d
     dev = x.device
@@ -406,17 +448,18 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
     qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
     attn = torch.empty(B * T, E, device=dev, dtype=bf16)
     lse = torch.empty(B, H, T, device=dev, dtype=f32) if save else None
-    K.attn_fwd(qkv, valid_t, attn, lse, B, T, H, d, d ** -0.5)
-    y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"], residual=x)
+    dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
+    K.attn_fwd(qkv, valid_t, attn, lse, B, T, H, d, d ** -0.5, drop=dl(DropCfg.ATTN))
+    y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"], residual=x, drop=dl(DropCfg.DROP1))
     x1 = torch.empty_like(y1)
     s.mean1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
     s.rstd1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
     K.layernorm_fwd(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1,
                     s.mean1, s.rstd1)
     u = torch.empty(B * T, F, device=dev, dtype=bf16) if save else None
-    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u)
+    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u, drop=dl(DropCfg.ACT))
     lr = torch.empty(B * T, E, device=dev, dtype=bf16) if want_lr else None
-    y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr)
+    y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr, drop=dl(DropCfg.DROP3))
     x2 = out if out is not None else torch.empty_like(y2)
     s.mean2 = torch.empty(B * T, device=dev, dtype=f32) if save else None
     s.rstd2 = torch.empty(B * T, device=dev, dtype=f32) if save else None
@@ -452,7 +495,7 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
 # student
 # =============================================================================================
 def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], *, train: bool,
-                    heads: str = "all", want_lr: bool = False, pred_buf=None):
+                    heads: str = "all", want_lr: bool = False, pred_buf=None, drop: Optional[DropCfg] = None):
     """Student forward (reference modules/model.py:420-552).  heads: 'all' (12 LayerWiseProjHeads),
     'last' (after _disable_projection_heads: final_proj on the last layer), 'none'.
     Returns ctx: .layers [n_layers][B*Ts, E], .tr [B*Ts, E], .preds [n_layers or 1, B, T', D], .feats."""
@@ -460,10 +503,12 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     dev = wave.device
     valid_t = _valid_tensor(valid, dev)
     valid_s = _valid_tensor(None if valid is None else [v // 2 for v in valid], dev)
-    c = frontend_fwd(P, W, g, wave, valid_t, save=train)
+    if drop is not None and not drop.any():
+        drop = None
+    c = frontend_fwd(P, W, g, wave, valid_t, save=train, drop=drop)
     B, T, E = c.B, c.T, g.E
     Ts = T // 2
-    c.Ts, c.valid_t, c.valid_s = Ts, valid_t, valid_s
+    c.Ts, c.valid_t, c.valid_s, c.drop = Ts, valid_t, valid_s, drop
     # time-reduction Conv1d(k=2, s=2) (modules/module.py:317-321): reshaped-view GEMM, drops an odd tail frame
     tr = torch.empty(B * Ts, E, device=dev, dtype=bf16)
     a3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
@@ -475,7 +520,8 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     c.layer_ctx = []
     lay = torch.empty(g.n_layers, B * Ts, E, device=dev, dtype=bf16)  # stacked layer outputs (batched heads)
     for l in range(g.n_layers):
-        s = layer_fwd(P, W, g, f"encoder.layers.{l + 1}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l])
+        s = layer_fwd(P, W, g, f"encoder.layers.{l + 1}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l],
+                      drop=drop)
         c.layer_ctx.append(s)
         x = s.out
     c.lay = lay
@@ -595,28 +641,36 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
                 dx2 = K.add_bf16(dx2, dlayers[l], torch.empty_like(dx))
         if dx is None:
             continue
-        # final LayerNorm
+        # final LayerNorm.  With dropout3 active the LayerNorm backward also writes dy2 * mask: that copy feeds the
+        # fc2 branch (wgrad, dgrad, bias gradient), the plain dy2 continues down the residual.
+        drop = getattr(c, "drop", None)
+        dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
         dy2 = torch.empty_like(dx)
+        d3 = dl(DropCfg.DROP3)
+        dy2m = torch.empty_like(dx) if d3 is not None else dy2
         K.layernorm_bwd(dx, s.y2, P[p + "final_layer_norm.weight"], s.mean2, s.rstd2, dy2,
                         gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"), dxsum=gv(p + "fc2.bias"),
-                        dy2=dx2)
-        # FFN (fc2 bias gradient = column sums of dy2: accumulated by the LayerNorm backward above)
-        K.linear_wgrad(dy2, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
-        du = K.linear_dgrad(dy2, W[f"l{l}.w2"].view(E, F), mul_aux=s.u)
+                        dy2=dx2, dx_drop=dy2m if d3 is not None else None, drop=d3)
+        # FFN (fc2 bias gradient = column sums of dy2m: accumulated by the LayerNorm backward above; the saved
+        # s.u = gelu'(u) * activation-dropout mask, s.h = dropped activations)
+        K.linear_wgrad(dy2m, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
+        du = K.linear_dgrad(dy2m, W[f"l{l}.w2"].view(E, F), mul_aux=s.u)
         K.colsum(du, gv(p + "fc1.bias"))
         K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
         dx1 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2)
-        # attention LayerNorm
+        # attention LayerNorm (same scheme for dropout1 on the out_proj branch)
         dy1 = torch.empty_like(dx1)
+        d1 = dl(DropCfg.DROP1)
+        dy1m = torch.empty_like(dx1) if d1 is not None else dy1
         K.layernorm_bwd(dx1, s.y1, P[p + "self_attn_layer_norm.weight"], s.mean1, s.rstd1, dy1,
                         gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"),
-                        dxsum=gv(p + "self_attn.out_proj.bias"))
+                        dxsum=gv(p + "self_attn.out_proj.bias"), dx_drop=dy1m if d1 is not None else None, drop=d1)
         # attention block (out_proj bias gradient: accumulated by the LayerNorm backward above)
-        K.linear_wgrad(dy1, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
-        dattn = K.linear_dgrad(dy1, W[f"l{l}.wo"].view(E, E))
+        K.linear_wgrad(dy1m, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
+        dattn = K.linear_dgrad(dy1m, W[f"l{l}.wo"].view(E, E))
         dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
         delta = torch.empty(B, H, Ts, device=dev, dtype=f32)
-        K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5)
+        K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5, drop=dl(DropCfg.ATTN))
         K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
         K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
                        accumulate=True)
@@ -634,7 +688,11 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     a3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
     b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
     K.gemm_raw(a3, b3, denc, Ts, 2 * E, E, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * E, d_hi_stride=T * E)
-    # ---- encoder prologue backward: LayerNorm, + pos-conv residual, GELU, grouped conv (dgrad + wgrad), mask
+    # ---- encoder prologue backward: (dropout,) LayerNorm, + pos-conv residual, GELU, grouped conv, mask
+    drop = getattr(c, "drop", None)
+    d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
+    if d_pro is not None:
+        K.dropout(denc, denc, *d_pro)
     G, cp, kp = g.G, g.cp, g.kpos
     Tp = T + kp
     dh = torch.empty(B * T, E, device=dev, dtype=bf16)
@@ -661,6 +719,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
                      gv("encoder.pos_conv.0.weight_v"), gv("encoder.pos_conv.0.weight_g"), E, G, kp, cp, True)
     dfeat = torch.empty(B * T, E, device=dev, dtype=bf16)
     K.posconv_unpack_bwd(dh, dxc, c.valid_t, dfeat, B, T, E, G, cp)
+    d_in = drop.site(DropCfg.SITE_INPUT, drop.p_input) if drop is not None else None
+    if d_in is not None:
+        K.dropout(dfeat, dfeat, *d_in)
     # ---- post_extract_proj + LayerNorm(C_feat)
     Cf = g.c_feat
     K.colsum(dfeat, gv("post_extract_proj.bias"))

@@ -39,7 +39,8 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
              num_ob=1, ob_mod=1, num_cb=1, a_coord=(0, 0, 0, 0), b_coord=(0, 0, 0, 0),
              d_ld: int, d_hi_stride=0, d_lo_stride=0, flags=0, split_k=0, bias=None, residual=None,
              aux_in=None, aux_out=None, row_valid=None, loss_target=None, loss_acc=None,
-             loss_weight=0.0, grad_scale=0.0, d_offset_elems=0, a_c1_off=0, b_c1_off=0, bias_hi_stride=0) -> None:
+             loss_weight=0.0, grad_scale=0.0, d_offset_elems=0, a_c1_off=0, b_c1_off=0, bias_hi_stride=0,
+             drop=None) -> None:
     g = L.GemmArgs()
     g.a, g.b = a, b
     g.a_major, g.b_major = a_major, b_major
@@ -62,6 +63,10 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
         setattr(g, name, None if t is None else t.data_ptr() + d_offset_elems * t.element_size())
     g.loss_weight, g.grad_scale = loss_weight, grad_scale
     g.bias_hi_stride = bias_hi_stride
+    if drop is not None and drop[1] > 0.0:  # (seed, p)
+        flags |= L.EPI_DROPOUT
+        g.flags = flags
+        g.drop_seed, g.drop_p = drop[0] & 0xFFFFFFFF, drop[1]
     if _GEMM_TIMING["on"]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -74,7 +79,7 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, gelu=False,
            residual=None, row_valid=None, rows_per_batch=0, preact_out=None, dgelu_out=None, out_dtype=bf16,
-           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, drop=None) -> torch.Tensor:
     """y[M,N] = epi(x[M,K] @ w[N,K]^T).  x, w bf16 row-major (x may be a strided 2-D view).
     preact_out: also store the value before GELU / residual; dgelu_out: store gelu'(that value) instead
     (what the backward epilogue multiplies by: FHB_EPI_MUL_AUX)."""
@@ -102,10 +107,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         a3 = L.tensor3(x.view(nb, rows_per_batch, K))
         gemm_raw(a3, L.tensor3(w), y, rows_per_batch, N, K, num_ob=nb, a_coord=(0, 1, 0, 0),
                  d_ld=y.stride(0), d_hi_stride=rows_per_batch * y.stride(0), flags=flags, bias=bias,
-                 residual=residual, aux_out=preact_out, row_valid=row_valid)
+                 residual=residual, aux_out=preact_out, row_valid=row_valid, drop=drop)
         return y
     gemm_raw(L.tensor3(x), L.tensor3(w), y, M, N, K, d_ld=y.stride(0), flags=flags, bias=bias,
-             residual=residual, aux_out=preact_out)
+             residual=residual, aux_out=preact_out, drop=drop)
     return y
 
 
@@ -175,13 +180,16 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=None, dy2=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=None, dy2=None, dx_drop=None,
+                  drop=None):
     """dxsum (fp32 [C], accumulated): column sums of dx = bias gradient of the linear layer that produced x.
-    dy2: optional second gradient stream, summed with dy on load."""
+    dy2: optional second gradient stream, summed with dy on load.  dx_drop + drop=(seed, p): also write
+    dx * dropout-mask (the gradient entering a `residual + dropout(branch)` branch; dxsum then sums that)."""
     rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
+    seed, p = (drop[0] & 0xFFFFFFFF, drop[1]) if (drop is not None and dx_drop is not None) else (0, 0.0)
     L.check(L.lib().fhb_layernorm_bwd(L.ptr(dy), L.ptr(dy2), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dres),
-                                      L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dxsum), C.c_int64(rows), Cd,
-                                      L.stream_ptr()), "fhb_layernorm_bwd")
+                                      L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dxsum), L.ptr(dx_drop),
+                                      C.c_uint32(seed), _f(p), C.c_int64(rows), Cd, L.stream_ptr()), "fhb_layernorm_bwd")
     return dx
 
 
@@ -217,14 +225,19 @@ def posconv_wn_bwd(dwt, v, g, inv_norm, dv, dg, Cd, G, Kt, cp, accumulate=True):
                                        cp, int(accumulate), L.stream_ptr()), "fhb_posconv_wn_bwd")
 
 
-def attn_fwd(qkv, valid, out, lse, B, T, H, d, scale):
-    L.check(L.lib().fhb_attn_fwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(lse), B, T, H, d, _f(scale),
+def _drop(drop):
+    return (C.c_uint32(drop[0] & 0xFFFFFFFF), _f(drop[1])) if drop is not None else (C.c_uint32(0), _f(0.0))
+
+
+def attn_fwd(qkv, valid, out, lse, B, T, H, d, scale, drop=None):
+    """drop = (seed, p): attention dropout on the probabilities (same pair passed to attn_bwd)."""
+    L.check(L.lib().fhb_attn_fwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(lse), B, T, H, d, _f(scale), *_drop(drop),
                                  L.stream_ptr()), "fhb_attn_fwd")
 
 
-def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale):
+def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale, drop=None):
     L.check(L.lib().fhb_attn_bwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv),
-                                 L.ptr(delta_ws), B, T, H, d, _f(scale), L.stream_ptr()), "fhb_attn_bwd")
+                                 L.ptr(delta_ws), B, T, H, d, _f(scale), *_drop(drop), L.stream_ptr()), "fhb_attn_bwd")
 
 
 def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0,
@@ -271,6 +284,13 @@ def mul_dgelu(dy, dy_bs, u, u_bs, out, out_bs, B, n, *, u_off=0, out_off=0):
 def mul_bf16(a, a_bs, m, m_bs, out, out_bs, B, n):
     L.check(L.lib().fhb_mul_bf16(L.ptr(a), C.c_int64(a_bs), L.ptr(m), C.c_int64(m_bs), L.ptr(out), C.c_int64(out_bs), B,
                                  C.c_int64(n), L.stream_ptr()), "fhb_mul_bf16")
+
+
+def dropout(x, y, seed, p):
+    """y = nn.Dropout(p)(x) with the library's counter-based mask (also its own backward); y may alias x."""
+    L.check(L.lib().fhb_dropout(L.ptr(x), L.ptr(y), C.c_int64(x.numel()), C.c_uint32(seed & 0xFFFFFFFF), _f(p),
+                                L.stream_ptr()), "fhb_dropout")
+    return y
 
 
 def mask_lengths(mask_u8, lengths):

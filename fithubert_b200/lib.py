@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfhb_sm100a.so")
 
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROWZERO = 1, 2, 4, 8
 EPI_STORE_PREACT, EPI_MUL_DGELU, EPI_OUT_F32, EPI_ATOMIC_ADD, EPI_SQDIFF = 16, 32, 64, 128, 256
-EPI_AUX_DGELU, EPI_MUL_AUX = 512, 1024
+EPI_AUX_DGELU, EPI_MUL_AUX, EPI_DROPOUT = 512, 1024, 2048
 
 
 class FhbError(RuntimeError):
@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
         ("loss_target", C.c_void_p), ("loss_acc", C.c_void_p),
         ("loss_weight", C.c_float), ("grad_scale", C.c_float),
         ("bias_hi_stride", C.c_int64),
+        ("drop_seed", C.c_uint32), ("drop_p", C.c_float),
     ]
 
 
@@ -102,7 +103,7 @@ EXPORTS = [
     "fhb_layernorm_fwd", "fhb_layernorm_bwd", "fhb_posconv_pack", "fhb_posconv_wn_prep",
     "fhb_posconv_finish_fwd", "fhb_posconv_finish_bwd", "fhb_posconv_unpack_bwd", "fhb_posconv_wn_bwd",
     "fhb_attn_fwd", "fhb_attn_bwd", "fhb_distill_loss_fwd_bwd", "fhb_adamw_multi", "fhb_prep_multi",
-    "fhb_colsum", "fhb_colsum_batched", "fhb_add_bf16", "fhb_mul_dgelu", "fhb_mul_bf16", "fhb_mask_lengths", "fhb_memset2d",
+    "fhb_colsum", "fhb_colsum_batched", "fhb_add_bf16", "fhb_mul_dgelu", "fhb_mul_bf16", "fhb_dropout", "fhb_mask_lengths", "fhb_memset2d",
 ]
 
 

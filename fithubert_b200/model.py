@@ -216,6 +216,21 @@ class CustomStudentModel(nn.Module):
         self._weights = None
         self._grads = None
         self._conv_layers = layers
+        self._drop_p = dict(p_input=cfg.dropout_input, p_drop=cfg.dropout, p_attn=cfg.attention_dropout,
+                            p_act=cfg.activation_dropout)
+        self._drop_calls = 0
+
+    def drop_cfg(self):
+        """Dropout configuration of the next training forward (None in eval mode or when every p is 0).  nn.Dropout
+        semantics: active iff the module is in training mode.  Masks are counter-based (engine.DropCfg): the seed
+        mixes torch's initial seed, the data-parallel rank and a per-model call counter."""
+        if not self.training or max(self._drop_p.values()) <= 0.0:
+            return None
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self._drop_calls += 1
+        return E.DropCfg((torch.initial_seed() & 0xFFFFFFFF) ^ (rank * 0x9E3779B1) ^ (self._drop_calls * 0x7F4A7C15),
+                         **self._drop_p)
 
     # ---- reference API -------------------------------------------------------------------
     def add_specaug(self, specaug):
@@ -276,7 +291,8 @@ class CustomStudentModel(nn.Module):
             c, preds, layers_out = student_apply(self, source, valid)
         else:
             P, W, _ = self.engine_state(False)
-            c = E.student_forward(P, W, self._geom, source, valid, train=False, heads=heads, want_lr=True)
+            c = E.student_forward(P, W, self._geom, source, valid, train=False, heads=heads, want_lr=True,
+                                  drop=self.drop_cfg())
             preds, layers_out = c.preds, c.layers
         B, T, Ts, Em = c.B, c.T, c.Ts, self._geom.E
         mask = _frame_mask(valid, T, dev)

@@ -54,7 +54,10 @@ enum {
   FHB_EPI_ATOMIC_ADD = 128, /* D += (fp32 atomics; required when split_k > 1)                */
   FHB_EPI_SQDIFF = 256,     /* fused distillation loss, see fhb_gemm_args.loss_*             */
   FHB_EPI_AUX_DGELU = 512,  /* with STORE_PREACT: aux_out = gelu'(value before GELU) instead  */
-  FHB_EPI_MUL_AUX = 1024    /* * aux_in[m][n] (e.g. a gelu' saved by FHB_EPI_AUX_DGELU)       */
+  FHB_EPI_MUL_AUX = 1024,   /* * aux_in[m][n] (e.g. a gelu' saved by FHB_EPI_AUX_DGELU)       */
+  FHB_EPI_DROPOUT = 2048    /* nn.Dropout(drop_p) after bias/GELU, before the residual; the    */
+                            /* mask of element (ob, m, n) is a hash of (drop_seed, index), see  */
+                            /* fhb_dropout; with AUX_DGELU the saved gelu' is masked the same   */
 };
 
 typedef struct {
@@ -82,6 +85,8 @@ typedef struct {
   float* loss_acc;
   float loss_weight, grad_scale;
   int64_t bias_hi_stride;   /* elements: batch ob_hi reads bias + ob_hi * bias_hi_stride (0 = shared bias)  */
+  uint32_t drop_seed;       /* FHB_EPI_DROPOUT                                                 */
+  float drop_p;
 } fhb_gemm_args;
 
 int fhb_gemm(const fhb_gemm_args* args, fhb_stream_t stream);
@@ -123,8 +128,8 @@ int fhb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
                       int64_t rows, int32_t C, float eps, fhb_stream_t stream);
 int fhb_layernorm_bwd(const void* dy, const void* dy2 /* optional: gradient = dy + dy2 */, const void* x,
                       const float* gamma, const float* mean, const float* rstd,
-                      const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int64_t rows,
-                      int32_t C, fhb_stream_t stream);
+                      const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, void* dx_drop,
+                      uint32_t drop_seed, float drop_p, int64_t rows, int32_t C, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ positional conv (K5) helpers
  * The grouped Conv1d(k=128, pad=64, groups=16) of modules/module.py:186-200,276-278 runs as a batched
@@ -161,12 +166,14 @@ int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, const f
  * bmm -> masked_fill(-inf) -> fp32 softmax -> bmm chain reached from modules/module.py:558-564.
  * qkv: bf16 [B][T][3*H*d] (q | k | v column blocks, as written by the fused QKV GEMM); keys at
  * t >= valid[b] are masked; padded QUERY rows are still computed.  lse: fp32 [B][H][T].
- * d in {40 (student), 64 (teacher)} plus any multiple of 8 <= 64. */
+ * d in {40 (student), 64 (teacher)} run on tcgen05 (forward); any multiple of 8 <= 64 is supported.
+ * drop_p > 0: attention dropout (fairseq MultiheadAttention dropout_module on the probabilities) with the
+ * counter-based mask of fhb_dropout over index ((b*H + h)*T + q) * 2*ceil(T/2) + k; backward regenerates it. */
 int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
-                 int32_t d, float scale, fhb_stream_t stream);
+                 int32_t d, float scale, uint32_t drop_seed, float drop_p, fhb_stream_t stream);
 int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const void* dout, const float* lse,
                  void* dqkv, float* delta_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
-                 fhb_stream_t stream);
+                 uint32_t drop_seed, float drop_p, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ distillation loss + gradient (K10)
  * loss_l = w_l * mean_{b,t,d} (pred_l - tgt_l)^2 ; dpred_l = 2 w_l (pred_l - tgt_l) / (B*T'*D)
@@ -230,6 +237,12 @@ int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_b
 /* out = a * m elementwise (bf16), same batching; m is a multiplier saved by FHB_EPI_AUX_DGELU */
 int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstride, void* out,
                  int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
+/* nn.Dropout(p) forward AND backward (the op is its own adjoint): y[i] = x[i] * mask(i) / (1 - p) for a flat
+ * tensor of n bf16 elements (y may alias x).  mask(i): element pair (2j, 2j+1) shares the 32-bit murmur3-finalised
+ * hash of (j * 0x9E3779B1 + seed); element keeps iff its 16-bit half >= round(p * 65536).  Every fused dropout
+ * in this library (GEMM epilogue, LayerNorm backward, attention) generates the same mask for the same index.
+ * Replaces nn.Dropout / F.dropout at modules/model.py:489, modules/module.py:294,566,573,578. */
+int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, float p, fhb_stream_t stream);
 /* zero `height` runs of `width_bytes` bytes, `pitch_bytes` apart (halo rows / borders of strided buffers);
  * a cudaMemset2DAsync, no kernel */
 int fhb_memset2d(void* ptr, int64_t pitch_bytes, int64_t width_bytes, int64_t height, fhb_stream_t stream);

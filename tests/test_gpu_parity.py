@@ -48,7 +48,7 @@ def build_pair(F, g):
     teacher.load_state_dict(g["teacher_state"])
     student = F.CustomStudentModel(full_student_cfg(F, g["student_cfg"]))
     student.load_state_dict(g["student_state"])
-    return F.TeacherWrapper(teacher.cuda()), student.cuda()
+    return F.TeacherWrapper(teacher.cuda()), student.cuda().eval()  # eval: dropout = identity, like the fixtures
 
 
 # ----------------------------------------------------------------------------- kernels vs torch fp32
@@ -186,6 +186,137 @@ def test_attention_fwd_bwd(F, d, T, amp, short):
     assert rel(dqkv, q3.grad) < 2e-2
 
 
+# ----------------------------------------------------------------------------- dropout (K13)
+def _fmix32(x):
+    x = x & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def drop_mask(seed, n, p):
+    """Restatement of the library's counter-based dropout mask (include/fhb.h: fhb_dropout) in int64 torch
+    arithmetic: multipliers (0 or 1/(1-p')) for a flat tensor of n elements."""
+    j = torch.arange((n + 1) // 2, dtype=torch.int64)
+    h = _fmix32(j * 0x9E3779B1 + seed)
+    thr = int(p * 65536.0 + 0.5)
+    keep = torch.stack([(h & 0xFFFF) >= thr, (h >> 16) >= thr], -1).reshape(-1)[:n]
+    return keep.float() / (1.0 - thr / 65536.0)
+
+
+def test_dropout_sites_match_the_mask_restatement(F):
+    from fithubert_b200 import kernels as K
+    torch.manual_seed(11)
+    dev = "cuda"
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc).bfloat16()
+    seed, p = 0xC0FFEE11, 0.1
+    # elementwise kernel (dropout_input, encoder prologue) + keep fraction
+    x = rnd(1000, 480)
+    m = drop_mask(seed, x.numel(), p).view_as(x).cuda()
+    assert abs(float((m > 0).float().mean()) - (1 - p)) < 5e-3
+    y = K.dropout(x, torch.empty_like(x), seed, p)
+    assert torch.equal(y, (x.float() * m).bfloat16())
+    # GEMM epilogues: fc1 (GELU -> dropout, saved gelu' carries the mask), out_proj / fc2 (dropout -> + residual)
+    M, N, Kd = 700, 480, 480
+    xx, w, b, r = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev), rnd(M, N)
+    m = drop_mask(seed, M * N, p).view(M, N).cuda()
+    pre = (xx.float() @ w.float().t() + b).requires_grad_(True)
+    Fn.gelu(pre).sum().backward()
+    gp = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    y = K.linear(xx, w, b, gelu=True, dgelu_out=gp, drop=(seed, p))
+    assert rel(y, Fn.gelu(pre) * m) < 1e-2 and rel(gp, pre.grad * m) < 1e-2
+    assert torch.equal(y == 0, m == 0) or float(((y == 0) != (m == 0)).float().mean()) < 1e-3
+    lr = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    y = K.linear(xx, w, b, residual=r, preact_out=lr, drop=(seed, p))
+    assert rel(y, pre.detach() * m + r.float()) < 1e-2 and rel(lr, pre.detach()) < 1e-2  # layer_result is pre-dropout
+    # LayerNorm backward: second, masked copy of dx and its column sums
+    C = 480
+    xl, dy = rnd(M, C), rnd(M, C)
+    g_, b_ = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    yl, mean, rstd = torch.empty_like(xl), torch.empty(M, device=dev), torch.empty(M, device=dev)
+    K.layernorm_fwd(xl, g_, b_, yl, mean, rstd)
+    dx, dxm = torch.empty_like(xl), torch.empty_like(xl)
+    dg, db, ds = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    K.layernorm_bwd(dy, xl, g_, mean, rstd, dx, dg, db, dxsum=ds, dx_drop=dxm, drop=(seed, p))
+    xr = xl.float().requires_grad_(True)
+    Fn.layer_norm(xr, (C,), g_, b_, 1e-5).backward(dy.float())
+    assert rel(dx, xr.grad) < 1e-2 and rel(dxm, xr.grad * m) < 1e-2 and rel(ds, (xr.grad * m).sum(0)) < 5e-3
+
+
+@pytest.mark.parametrize("d,T", [(40, 389), (24, 70), (64, 200)])
+def test_attention_dropout_fwd_bwd(F, d, T):
+    """Attention-probability dropout: the tcgen05 forward (d = 40 / 64), the mma.sync forward (d = 24) and both
+    backward kernels regenerate the same counter-based mask; compare with torch using the restated mask."""
+    from fithubert_b200 import kernels as K
+    torch.manual_seed(5)
+    B, H, seed, p = 2, 3, 0x1234ABCD, 0.1
+    qkv = torch.randn(B, T, 3 * H * d, device="cuda").bfloat16()
+    valid = [T, T - 21]
+    vt = torch.tensor(valid, device="cuda", dtype=torch.int32)
+    T2 = 2 * ((T + 1) // 2)
+    m = drop_mask(seed, B * H * T * T2, p).view(B, H, T, T2)[..., :T].cuda()
+    out, lse = torch.empty(B * T, H * d, device="cuda", dtype=torch.bfloat16), torch.empty(B, H, T, device="cuda")
+    K.attn_fwd(qkv, vt, out, lse, B, T, H, d, d ** -0.5, drop=(seed, p))
+    q3 = qkv.float().requires_grad_(True)
+    q, k, v = (t.reshape(B, T, H, d).transpose(1, 2) for t in q3.chunk(3, dim=-1))
+    mask = (torch.arange(T, device="cuda")[None] >= vt[:, None])[:, None, None, :]
+    s = ((q @ k.transpose(-1, -2)) * d ** -0.5).masked_fill(mask, float("-inf"))
+    pr = torch.softmax(s, -1)
+    ref = ((pr * m) @ v).transpose(1, 2).reshape(B, T, H * d)
+    assert rel(out.view(B, T, -1), ref) < 1.5e-2
+    assert float((lse - torch.logsumexp(s, -1)).abs().max()) < 2e-2  # statistics are those of the un-dropped softmax
+    do = torch.randn(B, T, H * d, device="cuda").bfloat16()
+    ref.backward(do.float())
+    dqkv, delta = torch.empty_like(qkv), torch.empty(B, H, T, device="cuda")
+    K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5, drop=(seed, p))
+    assert rel(dqkv, q3.grad) < 2.5e-2
+
+
+def test_training_mode_dropout_paths_agree(F):
+    """With the module in training mode the yaml's dropout probabilities are live.  The fused step (no autograd)
+    and the autograd-facing path must produce the same gradients when they draw the same masks (same call
+    counter), and differ from the eval-mode (p = 0) result."""
+    g = torch.load(GOLDEN[1])
+    import bench
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"]["pred_layer_id"] = "[2]"
+    cfg["train"]["distil_random_layer"] = 2
+    teacher, _ = build_pair(F, g)
+    step = F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+    sm = step.student_model
+    sm.load_state_dict(g["student_state"])
+    step.configure_optimizers(total_steps=100)
+    x, pm = g["source"].cuda(), g["padding_mask"]
+    sm.eval()
+    step.optimizer.zero_grad()
+    loss_eval = float(step.fused_forward_backward(x, pm).sum())
+    sm.train()
+    assert sm.drop_cfg() is not None
+    sm._drop_calls = 40
+    step.optimizer.zero_grad()
+    loss_fused = float(step.fused_forward_backward(x, pm).sum())
+    _, _, G = sm.engine_state(True)
+    g_fused = {k: v.clone() for k, v in G.export().items()}
+    sm._drop_calls = 40
+    sm.zero_grad()
+    s_res, t_res = step(x, pm)
+    total, _ = step.calculate_loss(s_res, t_res)
+    total.backward()
+    assert abs(float(total) - loss_fused) < 1e-3 * abs(loss_fused)
+    assert abs(loss_fused - loss_eval) > 1e-4 * abs(loss_eval)  # dropout really changed the forward
+    for n, p in sm.named_parameters():
+        if p.grad is None:
+            continue
+        assert rel(p.grad, g_fused[n]) < 1e-3, n
+    sm._drop_calls = 41
+    step.optimizer.zero_grad()
+    assert float(step.fused_forward_backward(x, pm).sum()) != loss_fused  # a new call draws new masks
+
+
 def test_distill_loss_and_adamw(F):
     from fithubert_b200 import kernels as K, lib as L
     torch.manual_seed(4)
@@ -285,6 +416,7 @@ def test_fused_step_equals_autograd_path_and_updates_weights(F):
     teacher, _ = build_pair(F, g)
     step = F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
     step.student_model.load_state_dict(g["student_state"])
+    step.student_model.eval()  # parity at p = 0 (the fixtures were produced in eval mode)
     step.configure_optimizers(total_steps=100)
     before = {n: p.detach().clone() for n, p in step.student_model.named_parameters()}
     loss = step.training_step({"x": g["source"], "padding_mask": g["padding_mask"]})
@@ -316,7 +448,7 @@ def test_expert_forward_contract(F):
     cfg = {"distiller": dict(extractor_mode="default", layerwise_proj=True, enable_tr_layer=True, tr_layer_index=0,
                              tr_layer_type="conv1d", required_seq_len_multiple=1, pred_layer_id="[2]", **g["student_cfg"])}
     ck = {"state_dict": {"student_model." + k: v for k, v in g["student_state"].items()}}
-    ex = F.UpstreamExpert(ck, cfg).cuda()
+    ex = F.UpstreamExpert(ck, cfg).cuda().eval()  # s3prl extracts features in eval mode
     lens = (~g["padding_mask"]).sum(-1).tolist()
     wavs = [g["source"][i, :n].cuda() for i, n in enumerate(lens)]
     out = ex(wavs)
@@ -336,6 +468,7 @@ def test_full_size_properties(F):
     step = F.W2V2Distil(cfg, device="cuda")
     step.configure_optimizers(total_steps=1000)
     x, pm, lengths = bench.synth_batch(4, 249600, 1234)
+    step.student_model.eval()
     with torch.no_grad():
         full = step.student_model(x.cuda(), pm)
         one = step.student_model(x[2:3].cuda(), pm[2:3])
@@ -343,6 +476,7 @@ def test_full_size_properties(F):
     conv = O.parse_conv_layers(O.FITHUBERT_CONV)
     assert (~full["padding_mask"]).sum(-1).tolist() == O.conv_out_lengths(torch.tensor(lengths), conv).tolist()
     assert rel(full["x"][2:3], one["x"]) < 1e-2  # same kernels, same data: only tile-position effects
+    step.student_model.train()  # the yaml's dropout probabilities are live from here on
     losses = []
     for _ in range(4):
         losses.append(float(step.training_step({"x": x, "padding_mask": pm})))
