@@ -490,9 +490,13 @@ extern "C" int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, fl
   return 0;
 }
 
+int fhb_attn_bwd_tc(const void* qkv, const int32_t* valid, const void* dout, const float* lse, const float* delta,
+                    void* dqkv, float* dq_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale, uint32_t drop_seed,
+                    float drop_p, cudaStream_t s);  // attention_bwd_tc.cu (tcgen05 path, head_dim 40 / 64)
+
 extern "C" int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const void* dout, const float* lse,
-                            void* dqkv, float* delta_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
-                            uint32_t drop_seed, float drop_p, fhb_stream_t stream) {
+                            void* dqkv, float* delta_ws, float* dq_ws, int32_t B, int32_t T, int32_t H, int32_t d,
+                            float scale, uint32_t drop_seed, float drop_p, fhb_stream_t stream) {
   int rc = check_shape(B, T, H, d);
   if (rc) return rc;
   if ((rc = check_drop(B, T, H, drop_p)) != 0) return rc;
@@ -504,6 +508,9 @@ extern "C" int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* o
   attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(out),
                                                                 static_cast<const __nv_bfloat16*>(dout), delta_ws, B, T, H, d);
   FHB_LAUNCH_CHECK();
+  static const bool no_tc = getenv("FHB_ATTN_NO_TC") != nullptr;
+  if ((d == 64 || d == 40) && dq_ws && !no_tc)
+    return fhb_attn_bwd_tc(qkv, valid, dout, lse, delta_ws, dqkv, dq_ws, B, T, H, d, scale, drop_seed, drop_p, s);
   dim3 grid((T + kTile - 1) / kTile, H, B);
   FHB_ATTN_DISPATCH(d, (attn_bwd_dkv_kernel<DP><<<grid, 128, 0, s>>>(
                            static_cast<const __nv_bfloat16*>(qkv), valid, static_cast<const __nv_bfloat16*>(dout), lse,

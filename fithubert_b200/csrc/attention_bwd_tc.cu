@@ -1,0 +1,396 @@
+// K7 backward on 5th-gen tensor cores (head_dim 40: FitHuBERT student; 64 also instantiated).
+// Gradient of fairseq MultiheadAttention's bmm -> masked softmax -> (dropout) -> bmm chain
+// (modules/module.py:558-564), one fused kernel for dQ, dK and dV:
+//
+// One CTA per (128-key tile, head, sample), 288 threads, 1 CTA per SM, loop over 128-query tiles i:
+//   warp 8 (one elected lane): TMA loads (K, V once; Q_i, dO_i double buffered) and every tcgen05.mma:
+//        S^T_i  = K  Q_i^T      (128 keys x 128 queries, contraction over d)        -> TMEM
+//        dP^T_i = V  dO_i^T                                                          -> TMEM
+//        dV    += Pd^T_i dO_i   (A = Pd^T from smem, K-major; B = dO_i MN-major)     -> TMEM, accumulates over i
+//        dK    += dS^T_i Q_i                                                         -> TMEM, accumulates over i
+//        dQ_i   = dS_i K        (A = the SAME dS^T smem tile read MN-major)          -> TMEM, fresh per i
+//   warps 0-7: thread = (key row, 64-query half).  S^T / dP^T out of TMEM in one batch, then
+//        P^T = 2^(S^T*scale*log2e - lse_q), Pd^T = P^T o dropmask, dS^T = P^T o (dP^T o dropmask - delta_q) * scale,
+//        both written as bf16 A operands (128B-swizzled);  dQ_i is drained TMEM -> smem -> TMA reduce-add (fp32)
+//        into a [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to bf16 afterwards.
+// S^T_{i+1} / dP^T_{i+1} are issued as soon as the compute warps hold tile i in registers, so the tensor pipe
+// works ahead of the exponentials.  Keys >= valid[b] give P = 0; key tiles beyond valid[b] write zeros and exit;
+// out-of-range query rows are zero-filled by TMA and carry lse = +inf.  Dropout masks are regenerated from the
+// forward's (seed, index) hash.  head_dim 40: the 8 pad columns of K and V are zeroed in smem once per CTA.
+#include "fhb_common.cuh"
+
+int fhb_make_tmap_f32_3d(CUtensorMap* tm, void* ptr, const int64_t dim[3], const int64_t stride[2], uint32_t box0,
+                         uint32_t box1, const char* name);
+
+namespace {
+
+constexpr int kT = 128;
+constexpr uint32_t kTileBytes = kT * 64 * 2;  // 16 KiB
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void tmem_ld32b(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int HD>
+struct Smem {
+  static constexpr uint32_t kK = 0, kV = kTileBytes, kQ = 2 * kTileBytes, kDO = 4 * kTileBytes, kP = 6 * kTileBytes,
+                            kDS = 8 * kTileBytes, kDQ = 10 * kTileBytes;
+  static constexpr uint32_t kDQBytes = kT * HD * 4;
+  static constexpr uint32_t kStats = kDQ + kDQBytes;   // lse[2][128], delta[2][128] floats
+  static constexpr uint32_t kBars = kStats + 4 * kT * 4;
+  static constexpr uint32_t kTotal = kBars + 128;
+};
+
+template <int HD, bool DROP>
+__global__ void __launch_bounds__(288, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dq, const int* __restrict__ valid,
+                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                   int T, int H, float scale, uint32_t drop_seed, uint32_t drop_thr, float drop_scale) {
+  constexpr int DK = (HD + 15) / 16 * 16;
+  using S = Smem<HD>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
+  uint64_t* kv_full = bars;         // TMA: K, V landed
+  uint64_t* kv_ready = bars + 1;    // 256: pad columns zeroed (HD % 16 != 0)
+  uint64_t* qd_full = bars + 2;     // [2] TMA: Q_i, dO_i landed
+  uint64_t* s_full = bars + 4;      // S^T_i, dP^T_i in TMEM
+  uint64_t* s_free = bars + 5;      // 256: both copied to registers
+  uint64_t* p_full = bars + 6;      // 256: Pd^T_i, dS^T_i in smem
+  uint64_t* mma_done = bars + 7;    // dV, dK, dQ_i MMAs of tile i retired (smem P/dS + Q/dO stage reusable, dQ_i ready)
+  uint64_t* dq_free = bars + 8;     // 256: dQ_i copied out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* lse_s = reinterpret_cast<float*>(smem + S::kStats);
+  float* delta_s = lse_s + 2 * kT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
+  const int HDall = H * HD;
+  const long long ld = 3LL * HDall;
+  int nvalid = valid ? valid[b] : T;
+  nvalid = max(1, min(nvalid, T));
+  const int nq = (T + kT - 1) / kT;
+
+  if (k0 >= nvalid) {
+    // every key of this tile is masked: P = 0 -> dK = dV = 0 (block-uniform early exit, no TMEM needed)
+    for (int i = threadIdx.x; i < kT * (HD / 8); i += blockDim.x) {
+      const int r = i / (HD / 8), c = i - r * (HD / 8);
+      if (k0 + r < T) {
+        __nv_bfloat16* base = dqkv + ((long long)b * T + k0 + r) * ld + h * HD + c * 8;
+        *reinterpret_cast<uint4*>(base + HDall) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(base + 2 * HDall) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    return;
+  }
+
+  if (warp == 8 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_ready, 256);
+    mbar_init(&qd_full[0], 1);
+    mbar_init(&qd_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
+    mbar_init(mma_done, 1);
+    mbar_init(dq_free, 256);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
+                 tm_dqa = tmem_base + 384;
+
+  if (warp == 8) {
+    if (elect_one()) {
+      auto load_qd = [&](int i) {
+        const int st = i & 1;
+        mbar_expect_tx(&qd_full[st], 2 * kTileBytes);
+        tma_load_3d(&tm_qkv, &qd_full[st], smem + S::kQ + st * kTileBytes, h * HD, i * kT, b);
+        tma_load_3d(&tm_do, &qd_full[st], smem + S::kDO + st * kTileBytes, h * HD, i * kT, b);
+      };
+      mbar_expect_tx(kv_full, 2 * kTileBytes);
+      tma_load_3d(&tm_qkv, kv_full, smem + S::kK, HDall + h * HD, k0, b);
+      tma_load_3d(&tm_qkv, kv_full, smem + S::kV, 2 * HDall + h * HD, k0, b);
+      load_qd(0);
+      if (nq > 1) load_qd(1);
+      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T / dP^T: both operands K-major over d
+      const uint32_t id_kv = umma_idesc_bf16(128, DK, 0, 1);   // dV / dK: A K-major (queries), B MN-major
+      const uint32_t id_dq = umma_idesc_bf16(128, DK, 1, 1);   // dQ: A = dS^T read MN-major, B = K MN-major
+      const uint32_t ka = smem_u32(smem + S::kK), va = smem_u32(smem + S::kV);
+      const uint32_t pa = smem_u32(smem + S::kP), dsa = smem_u32(smem + S::kDS);
+      auto issue_s = [&](int i) {
+        const uint32_t qa = smem_u32(smem + S::kQ + (i & 1) * kTileBytes);
+        const uint32_t da = smem_u32(smem + S::kDO + (i & 1) * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k)
+          tc_mma_bf16(tm_s, umma_desc_sw128(ka + k * 32, 0, 1024), umma_desc_sw128(qa + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k)
+          tc_mma_bf16(tm_dp, umma_desc_sw128(va + k * 32, 0, 1024), umma_desc_sw128(da + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
+        tc_commit(s_full);
+      };
+      if (HD % 16) mbar_wait(kv_ready, 0); else mbar_wait(kv_full, 0);
+      mbar_wait(&qd_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        if (i + 1 < nq) {
+          mbar_wait(&qd_full[st ^ 1], ((i + 1) >> 1) & 1);
+          mbar_wait(s_free, i & 1);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + S::kQ + st * kTileBytes);
+        const uint32_t da = smem_u32(smem + S::kDO + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kT / 16; ++k) {  // contraction over the 128 queries: A atoms of 64 queries, B 16 rows = 2 KiB
+          const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
+          tc_mma_bf16(tm_dv, umma_desc_sw128(pa + aoff, 0, 1024), umma_desc_sw128(da + k * 2048, 0, 1024), id_kv,
+                      (i > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < kT / 16; ++k) {
+          const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
+          tc_mma_bf16(tm_dk, umma_desc_sw128(dsa + aoff, 0, 1024), umma_desc_sw128(qa + k * 2048, 0, 1024), id_kv,
+                      (i > 0 || k > 0) ? 1u : 0u);
+        }
+        if (i > 0) {
+          mbar_wait(dq_free, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < kT / 16; ++k)  // contraction over the 128 keys: dS^T rows are the K rows (MN-major A)
+          tc_mma_bf16(tm_dqa, umma_desc_sw128(dsa + k * 2048, kTileBytes, 1024), umma_desc_sw128(ka + k * 2048, 0, 1024),
+                      id_dq, k > 0 ? 1u : 0u);
+        tc_commit(mma_done);
+        if (i + 2 < nq) {
+          mbar_wait(mma_done, i & 1);
+          load_qd(i + 2);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ compute warps
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;         // key row of this thread within the tile
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const int key = k0 + row;
+    const float keymask = key < nvalid ? 1.f : 0.f;
+    if (HD % 16) {
+      // pad columns HD..DK-1 of K (threads 0-127) and V (128-255) hold the next head's values: zero them
+      mbar_wait(kv_full, 0);
+      const uint32_t tile = smem_u32(smem + (half ? S::kV : S::kK));
+      st_shared_v4(tile + row * 128 + ((((uint32_t)HD >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+      fence_async_shared();
+      mbar_arrive(kv_ready);
+    }
+    const float sc = scale * kLog2e;
+    const uint32_t prow = smem_u32(smem + S::kP) + half * kTileBytes + row * 128;
+    const uint32_t dsrow = smem_u32(smem + S::kDS) + half * kTileBytes + row * 128;
+    const uint32_t T2 = 2u * (uint32_t)((T + 1) >> 1);
+    const int tid = threadIdx.x;
+    // dQ drain geometry: thread owns query row `row` of the tile; warps 0-3 take columns [0, 32), warps 4-7 the rest
+    float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ);
+    auto drain_dq = [&](int j) {
+      // staging buffer must have been read by the previous TMA reduce
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      bar_compute();
+      tc_fence_after();
+      const int c_begin = half ? 32 : 0, c_end = half ? DK : 32;
+      for (int c = c_begin; c < c_end; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tm_dqa + lane_off + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (c + 4 * q4 < HD)
+            *reinterpret_cast<float4*>(dq_stage + row * HD + c + 4 * q4) =
+                make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
+                            __uint_as_float(r[4 * q4 + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_free);
+      fence_async_shared();
+      bar_compute();
+      if (tid == 0) {
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(&tm_dq), "r"(smem_u32(dq_stage)), "r"(h * HD), "r"(j * kT), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    for (int i = 0; i < nq; ++i) {
+      const int q0 = i * kT;
+      float* ls = lse_s + (i & 1) * kT;
+      float* dl = delta_s + (i & 1) * kT;
+      {
+        const int q = q0 + (tid & 127);
+        const long long off = ((long long)b * H + h) * T + q;
+        if (tid < 128) ls[tid] = q < T ? lse[off] * kLog2e : INFINITY;
+        else dl[tid - 128] = q < T ? delta[off] : 0.f;
+      }
+      bar_compute();
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint32_t sr[64], dr[64];
+      tmem_ld32b(tm_s + lane_off + half * 64, sr);
+      tmem_ld32b(tm_s + lane_off + half * 64 + 32, sr + 32);
+      tmem_ld32b(tm_dp + lane_off + half * 64, dr);
+      tmem_ld32b(tm_dp + lane_off + half * 64 + 32, dr + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      if (i > 0) mbar_wait(mma_done, (i - 1) & 1);  // smem P / dS free again
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        float pd[8], ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ql = half * 64 + c + e;  // query within the tile
+          const float p = ex2_approx(fmaf(__uint_as_float(sr[c + e]), sc, -ls[ql])) * keymask;
+          float mk = 1.f;
+          if (DROP) {
+            const uint32_t qid = (uint32_t)((b * H + h) * T + q0 + ql);
+            mk = dropout_one(drop_seed, qid * T2 + (uint32_t)key, drop_thr, drop_scale);
+          }
+          pd[e] = p * mk;
+          ds[e] = p * (__uint_as_float(dr[c + e]) * mk - dl[ql]) * scale;
+        }
+        const uint32_t ch = (uint32_t)(c >> 3);
+        st_shared_v4(prow + ((ch ^ rsw) << 4), pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]),
+                     pack_bf16(pd[6], pd[7]));
+        st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                     pack_bf16(ds[6], ds[7]));
+      }
+      tc_fence_before();
+      fence_async_shared();
+      mbar_arrive(p_full);
+      if (i > 0) drain_dq(i - 1);
+    }
+    mbar_wait(mma_done, (nq - 1) & 1);
+    drain_dq(nq - 1);
+    // ---- dK, dV: TMEM -> bf16 -> global.  Thread = key row; warps 0-3 columns [0, 32), warps 4-7 [32, HD)
+    tc_fence_after();
+    {
+      __nv_bfloat16* krow = dqkv + ((long long)b * T + key) * ld + HDall + h * HD;
+      __nv_bfloat16* vrow = krow + HDall;
+      const int c_begin = half ? 32 : 0, c_end = half ? DK : 32;
+      for (int c = c_begin; c < c_end; c += 16) {
+        uint32_t rk[16], rv[16];
+        tmem_ld16(tm_dk + lane_off + c, rk);  // warp-collective: every lane takes part, stores are predicated
+        tmem_ld16(tm_dv + lane_off + c, rv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q8 = 0; q8 < 2; ++q8) {
+          if (key < T && c + 8 * q8 < HD) {
+            const uint32_t* a = rk + 8 * q8;
+            const uint32_t* v = rv + 8 * q8;
+            *reinterpret_cast<uint4*>(krow + c + 8 * q8) =
+                make_uint4(pack_bf16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                           pack_bf16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16(__uint_as_float(a[6]), __uint_as_float(a[7])));
+            *reinterpret_cast<uint4*>(vrow + c + 8 * q8) =
+                make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                           pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
+          }
+        }
+      }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dqkv[row][0:E] = bf16(dq_acc[row][0:E])
+__global__ void __launch_bounds__(256)
+dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int E8, long long ld) {
+  const long long total = rows * E8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / E8;
+    const int c = (int)(i - r * E8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(acc + r * (E8 * 8) + c);
+    const float4 b2 = *reinterpret_cast<const float4*>(acc + r * (E8 * 8) + c + 4);
+    *reinterpret_cast<uint4*>(dqkv + r * ld + c) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b2.x, b2.y), pack_bf16(b2.z, b2.w));
+  }
+}
+
+template <int HD>
+int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const float* lse, const float* delta, void* dqkv,
+               float* dq_ws, int32_t B, int32_t T, int32_t H, float scale, uint32_t drop_seed, float drop_p,
+               cudaStream_t s) {
+  using S = Smem<HD>;
+  const int64_t E = (int64_t)H * HD;
+  CUtensorMap tq, td, ta;
+  {
+    const int64_t dim[3] = {3 * E, T, B}, stride[2] = {3 * E, 3 * E * T};
+    int rc = fhb_make_tmap_bf16_3d(&tq, qkv, dim, stride, 64, kT, "qkv");
+    if (rc) return rc;
+  }
+  {
+    const int64_t dim[3] = {E, T, B}, stride[2] = {E, E * T};
+    int rc = fhb_make_tmap_bf16_3d(&td, dout, dim, stride, 64, kT, "dout");
+    if (rc) return rc;
+    rc = fhb_make_tmap_f32_3d(&ta, dq_ws, dim, stride, HD, kT, "dq workspace");
+    if (rc) return rc;
+  }
+  FHB_CUDA_CHECK(cudaMemsetAsync(dq_ws, 0, sizeof(float) * (size_t)B * T * E, s));
+  static bool attr_set = false;
+  if (!attr_set) {
+    FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  dim3 grid((T + kT - 1) / kT, H, B);
+  if (drop_p > 0.f)
+    attn_bwd_tc_kernel<HD, true><<<grid, 288, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
+                                                             H, scale, drop_seed, fhb_dropout_thr16(drop_p),
+                                                             fhb_dropout_scale(drop_p));
+  else
+    attn_bwd_tc_kernel<HD, false><<<grid, 288, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
+                                                              T, H, scale, 0u, 0u, 1.f);
+  FHB_LAUNCH_CHECK();
+  const long long rows = (long long)B * T;
+  long long blocks = (rows * (E / 8) + 255) / 256;
+  if (blocks > 8LL * fhb_num_sms()) blocks = 8LL * fhb_num_sms();
+  dq_convert_kernel<<<(unsigned)blocks, 256, 0, s>>>(dq_ws, static_cast<__nv_bfloat16*>(dqkv), rows, (int)(E / 8), 3 * E);
+  FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// Called by fhb_attn_bwd (attention.cu) for head_dim 40 / 64 when a dQ workspace is supplied.
+int fhb_attn_bwd_tc(const void* qkv, const int32_t* valid, const void* dout, const float* lse, const float* delta,
+                    void* dqkv, float* dq_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale, uint32_t drop_seed,
+                    float drop_p, cudaStream_t s) {
+  if (d == 64) return launch_bwd<64>(qkv, valid, dout, lse, delta, dqkv, dq_ws, B, T, H, scale, drop_seed, drop_p, s);
+  return launch_bwd<40>(qkv, valid, dout, lse, delta, dqkv, dq_ws, B, T, H, scale, drop_seed, drop_p, s);
+}

@@ -670,7 +670,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         dattn = K.linear_dgrad(dy1m, W[f"l{l}.wo"].view(E, E))
         dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
         delta = torch.empty(B, H, Ts, device=dev, dtype=f32)
-        K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5, drop=dl(DropCfg.ATTN))
+        dq_ws = torch.empty(B * Ts, E, device=dev, dtype=f32) if d in (40, 64) else None
+        K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5, drop=dl(DropCfg.ATTN),
+                   dq_ws=dq_ws)
         K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
         K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
                        accumulate=True)

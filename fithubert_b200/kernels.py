@@ -235,9 +235,11 @@ def attn_fwd(qkv, valid, out, lse, B, T, H, d, scale, drop=None):
                                  L.stream_ptr()), "fhb_attn_fwd")
 
 
-def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale, drop=None):
+def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale, drop=None, dq_ws=None):
+    """dq_ws (fp32 [B, T, H*d]): enables the fused tcgen05 backward for d in {40, 64}."""
     L.check(L.lib().fhb_attn_bwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv),
-                                 L.ptr(delta_ws), B, T, H, d, _f(scale), *_drop(drop), L.stream_ptr()), "fhb_attn_bwd")
+                                 L.ptr(delta_ws), L.ptr(dq_ws), B, T, H, d, _f(scale), *_drop(drop), L.stream_ptr()),
+            "fhb_attn_bwd")
 
 
 def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0,

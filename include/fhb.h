@@ -171,8 +171,11 @@ int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, const f
  * counter-based mask of fhb_dropout over index ((b*H + h)*T + q) * 2*ceil(T/2) + k; backward regenerates it. */
 int fhb_attn_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int32_t B, int32_t T, int32_t H,
                  int32_t d, float scale, uint32_t drop_seed, float drop_p, fhb_stream_t stream);
+/* delta_ws: fp32 [B][H][T] workspace.  dq_ws: fp32 [B][T][H*d] workspace (optional): with it, d in {40, 64}
+ * runs the fused tcgen05 backward (dQ partials of every key tile are TMA-reduce-added into dq_ws, then converted);
+ * without it the two-kernel mma.sync backward is used. */
 int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const void* dout, const float* lse,
-                 void* dqkv, float* delta_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
+                 void* dqkv, float* delta_ws, float* dq_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
                  uint32_t drop_seed, float drop_p, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ distillation loss + gradient (K10)

@@ -182,8 +182,13 @@ def test_attention_fwd_bwd(F, d, T, amp, short):
     ref.backward(do.float())
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, H, T, device="cuda")
-    K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5)
+    K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5)  # two-kernel mma.sync backward
     assert rel(dqkv, q3.grad) < 2e-2
+    if d in (40, 64):  # fused tcgen05 backward (needs the fp32 dQ workspace)
+        dqkv2 = torch.full_like(qkv, float("nan"))
+        K.attn_bwd(qkv, vt, out, do, lse, dqkv2, delta, B, T, H, d, d ** -0.5,
+                   dq_ws=torch.empty(B * T, H * d, device="cuda"))
+        assert rel(dqkv2, q3.grad) < 2e-2
 
 
 # ----------------------------------------------------------------------------- dropout (K13)
@@ -273,6 +278,11 @@ def test_attention_dropout_fwd_bwd(F, d, T):
     dqkv, delta = torch.empty_like(qkv), torch.empty(B, H, T, device="cuda")
     K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5, drop=(seed, p))
     assert rel(dqkv, q3.grad) < 2.5e-2
+    if d in (40, 64):
+        dqkv2 = torch.full_like(qkv, float("nan"))
+        K.attn_bwd(qkv, vt, out, do, lse, dqkv2, delta, B, T, H, d, d ** -0.5, drop=(seed, p),
+                   dq_ws=torch.empty(B * T, H * d, device="cuda"))
+        assert rel(dqkv2, q3.grad) < 2.5e-2
 
 
 def test_training_mode_dropout_paths_agree(F):
