@@ -242,10 +242,10 @@ def main():
     sampler = ClockSampler(local)
     for _ in range(max(args.warmup, 3)):
         dev_step()
-    barrier()
     if rank == 0:
         sampler.start()
         time.sleep(0.3)  # let nvidia-smi come up; the rows kept are those taken under load (see stop())
+    barrier()  # after rank 0's sleep: no rank may enter the timed region while another is still outside it
     K.reset_counters()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()

@@ -2,19 +2,21 @@
 // Gradient of fairseq MultiheadAttention's bmm -> masked softmax -> (dropout) -> bmm chain
 // (modules/module.py:558-564), one fused kernel for dQ, dK and dV:
 //
-// One CTA per (128-key tile, head, sample), 288 threads, 1 CTA per SM, loop over 128-query tiles i:
-//   warp 8 (one elected lane): TMA loads (K, V once; Q_i, dO_i double buffered) and every tcgen05.mma:
+// One CTA per (128-key tile, head, sample), 544 threads, 1 CTA per SM, loop over 128-query tiles i:
+//   warp 16 (one elected lane): TMA loads (K, V once; Q_i, dO_i double buffered) and every tcgen05.mma:
 //        S^T_i  = K  Q_i^T      (128 keys x 128 queries, contraction over d)        -> TMEM
 //        dP^T_i = V  dO_i^T                                                          -> TMEM
 //        dV    += Pd^T_i dO_i   (A = Pd^T from smem, K-major; B = dO_i MN-major)     -> TMEM, accumulates over i
 //        dK    += dS^T_i Q_i                                                         -> TMEM, accumulates over i
 //        dQ_i   = dS_i K        (A = the SAME dS^T smem tile read MN-major)          -> TMEM, fresh per i
-//   warps 0-7: thread = (key row, 64-query half).  S^T / dP^T out of TMEM in one batch, then
+//   warps 0-15: thread = (key row, 32-query quarter).  S^T / dP^T out of TMEM in one batch, then
 //        P^T = 2^(S^T*scale*log2e - lse_q), Pd^T = P^T o dropmask, dS^T = P^T o (dP^T o dropmask - delta_q) * scale,
 //        both written as bf16 A operands (128B-swizzled);  dQ_i is drained TMEM -> smem -> TMA reduce-add (fp32)
 //        into a [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to bf16 afterwards.
 // S^T_{i+1} / dP^T_{i+1} are issued as soon as the compute warps hold tile i in registers, so the tensor pipe
-// works ahead of the exponentials.  Keys >= valid[b] give P = 0; key tiles beyond valid[b] write zeros and exit;
+// works ahead of the exponentials.  Ragged edges are trimmed: the last query tile issues N = ceil16(valid
+// queries) and contracts over that many queries only; warps whose queries or keys are all out of range skip
+// the exponentials (they write the zeros the MMAs need).  Keys >= valid[b] give P = 0; key tiles beyond valid[b] write zeros and exit;
 // out-of-range query rows are zero-filled by TMA and carry lse = +inf.  Dropout masks are regenerated from the
 // forward's (seed, index) hash.  head_dim 40: the 8 pad columns of K and V are zeroed in smem once per CTA.
 #include "fhb_common.cuh"
@@ -40,7 +42,8 @@ __device__ __forceinline__ void tmem_ld32b(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+constexpr int kCT = 512;  // compute threads (16 warps)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <int HD>
 struct Smem {
@@ -53,7 +56,7 @@ struct Smem {
 };
 
 template <int HD, bool DROP>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(kCT + 32, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dq, const int* __restrict__ valid,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -63,7 +66,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
   uint64_t* kv_full = bars;         // TMA: K, V landed
-  uint64_t* kv_ready = bars + 1;    // 256: pad columns zeroed (HD % 16 != 0)
+  uint64_t* kv_ready = bars + 1;    // kCT: pad columns zeroed (HD % 16 != 0)
   uint64_t* qd_full = bars + 2;     // [2] TMA: Q_i, dO_i landed
   uint64_t* s_full = bars + 4;      // S^T_i, dP^T_i in TMEM
   uint64_t* s_free = bars + 5;      // 256: both copied to registers
@@ -95,23 +98,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     return;
   }
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
     mbar_init(kv_full, 1);
-    mbar_init(kv_ready, 256);
+    mbar_init(kv_ready, kCT);
     mbar_init(&qd_full[0], 1);
     mbar_init(&qd_full[1], 1);
     mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(p_full, 256);
+    mbar_init(s_free, kCT);
+    mbar_init(p_full, kCT);
     mbar_init(mma_done, 1);
-    mbar_init(dq_free, 256);
+    mbar_init(dq_free, kCT);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -119,7 +122,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
                  tm_dqa = tmem_base + 384;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (elect_one()) {
       auto load_qd = [&](int i) {
         const int st = i & 1;
@@ -132,14 +135,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_load_3d(&tm_qkv, kv_full, smem + S::kV, 2 * HDall + h * HD, k0, b);
       load_qd(0);
       if (nq > 1) load_qd(1);
-      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T / dP^T: both operands K-major over d
       const uint32_t id_kv = umma_idesc_bf16(128, DK, 0, 1);   // dV / dK: A K-major (queries), B MN-major
       const uint32_t id_dq = umma_idesc_bf16(128, DK, 1, 1);   // dQ: A = dS^T read MN-major, B = K MN-major
       const uint32_t ka = smem_u32(smem + S::kK), va = smem_u32(smem + S::kV);
       const uint32_t pa = smem_u32(smem + S::kP), dsa = smem_u32(smem + S::kDS);
+      auto nq16 = [&](int i) { return (min(kT, T - i * kT) + 15) & ~15; };  // valid queries of tile i, rounded to 16
       auto issue_s = [&](int i) {
         const uint32_t qa = smem_u32(smem + S::kQ + (i & 1) * kTileBytes);
         const uint32_t da = smem_u32(smem + S::kDO + (i & 1) * kTileBytes);
+        const uint32_t id_s = umma_idesc_bf16(128, (uint32_t)nq16(i), 0, 0);  // both operands K-major over d
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k)
           tc_mma_bf16(tm_s, umma_desc_sw128(ka + k * 32, 0, 1024), umma_desc_sw128(qa + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
@@ -164,14 +168,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tc_fence_after();
         const uint32_t qa = smem_u32(smem + S::kQ + st * kTileBytes);
         const uint32_t da = smem_u32(smem + S::kDO + st * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kT / 16; ++k) {  // contraction over the 128 queries: A atoms of 64 queries, B 16 rows = 2 KiB
+        const int ksteps = nq16(i) / 16;  // contraction over the valid queries of this tile only
+        for (int k = 0; k < ksteps; ++k) {  // A atoms of 64 queries, B 16 query rows = 2 KiB per step
           const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
           tc_mma_bf16(tm_dv, umma_desc_sw128(pa + aoff, 0, 1024), umma_desc_sw128(da + k * 2048, 0, 1024), id_kv,
                       (i > 0 || k > 0) ? 1u : 0u);
         }
-#pragma unroll
-        for (int k = 0; k < kT / 16; ++k) {
+        for (int k = 0; k < ksteps; ++k) {
           const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
           tc_mma_bf16(tm_dk, umma_desc_sw128(dsa + aoff, 0, 1024), umma_desc_sw128(qa + k * 2048, 0, 1024), id_kv,
                       (i > 0 || k > 0) ? 1u : 0u);
@@ -193,41 +196,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------ compute warps
-    const int quarter = warp & 3, half = warp >> 2;
-    const int row = quarter * 32 + lane;         // key row of this thread within the tile
+    const int quarter = warp & 3, quad = warp >> 2;  // TMEM lane quarter (key rows), 32-query column group
+    const int row = quarter * 32 + lane;              // key row of this thread within the tile
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t rsw = (uint32_t)(row & 7);
     const int key = k0 + row;
     const float keymask = key < nvalid ? 1.f : 0.f;
+    const bool warp_keys_live = (k0 + quarter * 32) < nvalid;  // warp-uniform: any valid key in this warp's rows
+    const int tid = threadIdx.x;
     if (HD % 16) {
       // pad columns HD..DK-1 of K (threads 0-127) and V (128-255) hold the next head's values: zero them
       mbar_wait(kv_full, 0);
-      const uint32_t tile = smem_u32(smem + (half ? S::kV : S::kK));
-      st_shared_v4(tile + row * 128 + ((((uint32_t)HD >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
-      fence_async_shared();
+      if (tid < 256) {
+        const uint32_t tile = smem_u32(smem + (tid >= 128 ? S::kV : S::kK));
+        st_shared_v4(tile + row * 128 + ((((uint32_t)HD >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+        fence_async_shared();
+      }
       mbar_arrive(kv_ready);
     }
     const float sc = scale * kLog2e;
-    const uint32_t prow = smem_u32(smem + S::kP) + half * kTileBytes + row * 128;
-    const uint32_t dsrow = smem_u32(smem + S::kDS) + half * kTileBytes + row * 128;
+    const uint32_t col_off = (uint32_t)(quad >> 1) * kTileBytes + row * 128;  // atom of 64 queries + this row
+    const uint32_t prow = smem_u32(smem + S::kP) + col_off;
+    const uint32_t dsrow = smem_u32(smem + S::kDS) + col_off;
+    const uint32_t ch0 = (uint32_t)(quad & 1) * 4;  // first 16-byte chunk of this thread's 32 queries inside the atom
     const uint32_t T2 = 2u * (uint32_t)((T + 1) >> 1);
-    const int tid = threadIdx.x;
-    // dQ drain geometry: thread owns query row `row` of the tile; warps 0-3 take columns [0, 32), warps 4-7 the rest
+    // dQ drain / final dK, dV store geometry: thread owns tile row `row`, column group [16 quad, 16 quad + 16)
+    const int c16 = quad * 16;
     float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ);
     auto drain_dq = [&](int j) {
       // staging buffer must have been read by the previous TMA reduce
       if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       bar_compute();
       tc_fence_after();
-      const int c_begin = half ? 32 : 0, c_end = half ? DK : 32;
-      for (int c = c_begin; c < c_end; c += 16) {
+      if (c16 < DK) {
         uint32_t r[16];
-        tmem_ld16(tm_dqa + lane_off + c, r);
+        tmem_ld16(tm_dqa + lane_off + c16, r);
         tmem_ld_wait();
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          if (c + 4 * q4 < HD)
-            *reinterpret_cast<float4*>(dq_stage + row * HD + c + 4 * q4) =
+          if (c16 + 4 * q4 < HD)
+            *reinterpret_cast<float4*>(dq_stage + row * HD + c16 + 4 * q4) =
                 make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
                             __uint_as_float(r[4 * q4 + 3]));
         }
@@ -246,44 +254,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int q0 = i * kT;
       float* ls = lse_s + (i & 1) * kT;
       float* dl = delta_s + (i & 1) * kT;
-      {
+      if (tid < 256) {
         const int q = q0 + (tid & 127);
         const long long off = ((long long)b * H + h) * T + q;
         if (tid < 128) ls[tid] = q < T ? lse[off] * kLog2e : INFINITY;
         else dl[tid - 128] = q < T ? delta[off] : 0.f;
       }
       bar_compute();
+      const int nq16v = (min(kT, T - q0) + 15) & ~15;      // query columns the MMAs of this tile touch
+      const bool cols_live = quad * 32 < nq16v;             // warp-uniform: this warp's queries exist
+      const bool work = cols_live && warp_keys_live;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      uint32_t sr[64], dr[64];
-      tmem_ld32b(tm_s + lane_off + half * 64, sr);
-      tmem_ld32b(tm_s + lane_off + half * 64 + 32, sr + 32);
-      tmem_ld32b(tm_dp + lane_off + half * 64, dr);
-      tmem_ld32b(tm_dp + lane_off + half * 64 + 32, dr + 32);
-      tmem_ld_wait();
+      uint32_t sr[32], dr[32];
+      if (work) {
+        tmem_ld32b(tm_s + lane_off + quad * 32, sr);
+        tmem_ld32b(tm_dp + lane_off + quad * 32, dr);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(s_free);
       if (i > 0) mbar_wait(mma_done, (i - 1) & 1);  // smem P / dS free again
+      if (work) {
 #pragma unroll
-      for (int c = 0; c < 64; c += 8) {
-        float pd[8], ds[8];
+        for (int c = 0; c < 32; c += 8) {
+          float pd[8], ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ql = half * 64 + c + e;  // query within the tile
-          const float p = ex2_approx(fmaf(__uint_as_float(sr[c + e]), sc, -ls[ql])) * keymask;
-          float mk = 1.f;
-          if (DROP) {
-            const uint32_t qid = (uint32_t)((b * H + h) * T + q0 + ql);
-            mk = dropout_one(drop_seed, qid * T2 + (uint32_t)key, drop_thr, drop_scale);
+          for (int e = 0; e < 8; ++e) {
+            const int ql = quad * 32 + c + e;  // query within the tile
+            const float p = ex2_approx(fmaf(__uint_as_float(sr[c + e]), sc, -ls[ql])) * keymask;
+            float mk = 1.f;
+            if (DROP) {
+              const uint32_t qid = (uint32_t)((b * H + h) * T + q0 + ql);
+              mk = dropout_one(drop_seed, qid * T2 + (uint32_t)key, drop_thr, drop_scale);
+            }
+            pd[e] = p * mk;
+            ds[e] = p * (__uint_as_float(dr[c + e]) * mk - dl[ql]) * scale;
           }
-          pd[e] = p * mk;
-          ds[e] = p * (__uint_as_float(dr[c + e]) * mk - dl[ql]) * scale;
+          const uint32_t ch = ch0 + (uint32_t)(c >> 3);
+          st_shared_v4(prow + ((ch ^ rsw) << 4), pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]),
+                       pack_bf16(pd[6], pd[7]));
+          st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                       pack_bf16(ds[6], ds[7]));
         }
-        const uint32_t ch = (uint32_t)(c >> 3);
-        st_shared_v4(prow + ((ch ^ rsw) << 4), pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]),
-                     pack_bf16(pd[6], pd[7]));
-        st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
-                     pack_bf16(ds[6], ds[7]));
+      } else if (cols_live) {
+        // every key of this warp is masked: P = dS = 0 (the dQ contraction reads these rows)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          st_shared_v4(prow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+          st_shared_v4(dsrow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+        }
       }
       tc_fence_before();
       fence_async_shared();
@@ -292,29 +312,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     mbar_wait(mma_done, (nq - 1) & 1);
     drain_dq(nq - 1);
-    // ---- dK, dV: TMEM -> bf16 -> global.  Thread = key row; warps 0-3 columns [0, 32), warps 4-7 [32, HD)
+    // ---- dK, dV: TMEM -> bf16 -> global.  Thread = key row, columns [16 quad, 16 quad + 16)
     tc_fence_after();
-    {
+    if (c16 < DK) {
       __nv_bfloat16* krow = dqkv + ((long long)b * T + key) * ld + HDall + h * HD;
       __nv_bfloat16* vrow = krow + HDall;
-      const int c_begin = half ? 32 : 0, c_end = half ? DK : 32;
-      for (int c = c_begin; c < c_end; c += 16) {
-        uint32_t rk[16], rv[16];
-        tmem_ld16(tm_dk + lane_off + c, rk);  // warp-collective: every lane takes part, stores are predicated
-        tmem_ld16(tm_dv + lane_off + c, rv);
-        tmem_ld_wait();
+      uint32_t rk[16], rv[16];
+      tmem_ld16(tm_dk + lane_off + c16, rk);  // warp-collective: every lane takes part, stores are predicated
+      tmem_ld16(tm_dv + lane_off + c16, rv);
+      tmem_ld_wait();
+      if (key >= nvalid) {  // masked keys: exact zeros (their P rows were never computed)
 #pragma unroll
-        for (int q8 = 0; q8 < 2; ++q8) {
-          if (key < T && c + 8 * q8 < HD) {
-            const uint32_t* a = rk + 8 * q8;
-            const uint32_t* v = rv + 8 * q8;
-            *reinterpret_cast<uint4*>(krow + c + 8 * q8) =
-                make_uint4(pack_bf16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16(__uint_as_float(a[2]), __uint_as_float(a[3])),
-                           pack_bf16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16(__uint_as_float(a[6]), __uint_as_float(a[7])));
-            *reinterpret_cast<uint4*>(vrow + c + 8 * q8) =
-                make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
-                           pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
-          }
+        for (int e = 0; e < 16; ++e) rk[e] = rv[e] = 0u;
+      }
+#pragma unroll
+      for (int q8 = 0; q8 < 2; ++q8) {
+        if (key < T && c16 + 8 * q8 < HD) {
+          const uint32_t* a = rk + 8 * q8;
+          const uint32_t* v = rv + 8 * q8;
+          *reinterpret_cast<uint4*>(krow + c16 + 8 * q8) =
+              make_uint4(pack_bf16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                         pack_bf16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16(__uint_as_float(a[6]), __uint_as_float(a[7])));
+          *reinterpret_cast<uint4*>(vrow + c16 + 8 * q8) =
+              make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                         pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
         }
       }
     }
@@ -322,7 +343,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -370,11 +391,11 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
   }
   dim3 grid((T + kT - 1) / kT, H, B);
   if (drop_p > 0.f)
-    attn_bwd_tc_kernel<HD, true><<<grid, 288, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
+    attn_bwd_tc_kernel<HD, true><<<grid, kCT + 32, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
                                                              H, scale, drop_seed, fhb_dropout_thr16(drop_p),
                                                              fhb_dropout_scale(drop_p));
   else
-    attn_bwd_tc_kernel<HD, false><<<grid, 288, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
+    attn_bwd_tc_kernel<HD, false><<<grid, kCT + 32, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
                                                               T, H, scale, 0u, 0u, 1.f);
   FHB_LAUNCH_CHECK();
   const long long rows = (long long)B * T;

@@ -3,13 +3,16 @@
 // Replaces the bmm -> masked_fill(-inf) -> fp32 softmax -> bmm chain of fairseq MultiheadAttention
 // (reached from modules/module.py:558-564; the teacher runs the same code in fairseq).
 //
-// One CTA per (128-query tile, head, sample), 160 threads, 2 CTAs per SM (112 KB smem, 256 TMEM columns
+// One CTA per (128-query tile, head, sample), 288 threads, 2 CTAs per SM (113 KB smem, 256 TMEM columns
 // each) so one CTA's softmax overlaps the other's MMAs:
-//   warp 4 (one elected lane): TMA loads of Q / K_j / V_j (128B swizzle, double-buffered K/V) and all
+//   warp 8 (one elected lane): TMA loads of Q / K_j / V_j (128B swizzle, double-buffered K/V) and all
 //                              tcgen05.mma issue:  S_j = Q K_j^T (128x128xd)  and  O += P_j V_j (128xdx128)
-//   warps 0-3: one query row per thread.  S_j is pulled out of TMEM in one batch of tcgen05.ld (which frees
-//              the S columns for S_{j+1} while the exponentials run), online softmax in registers with no
-//              cross-thread reductions, P_j -> bf16 -> swizzled smem (A operand of the second MMA).
+//   warps 0-7: thread = (query row, 64-key half).  S_j is pulled out of TMEM in one batch of tcgen05.ld (which
+//              frees the S columns for S_{j+1} while the exponentials run), online softmax in registers - the two
+//              halves of a row only exchange their maxima through smem once per key tile - and P_j -> bf16 ->
+//              swizzled smem (A operand of the second MMA).  16 softmax warps per SM hide the TMEM / MUFU latency.
+//   Ragged edges are trimmed: the last key tile issues N = ceil16(valid keys) and contracts over that many keys
+//   only; warps whose 32 query rows are all >= T skip the exponentials.
 //   O stays in TMEM for the whole key loop (accumulating MMAs).  The running maximum is only moved - and O
 //   rescaled in TMEM (tcgen05.ld / st) - when it grows by more than 2^8, so the rescale is off the
 //   steady-state path; l and the LSE stay exact because P, l and O share the same reference maximum.
@@ -21,7 +24,7 @@ namespace {
 
 constexpr int kTQ = 128, kTK = 128;
 constexpr uint32_t kTileBytes = kTQ * 64 * 2;  // 16 KiB: 128 rows x 64 bf16 (one 128-byte swizzle row each)
-constexpr uint32_t kSmem = kTileBytes /*Q*/ + 2 * kTileBytes /*K*/ + 2 * kTileBytes /*V*/ + 2 * kTileBytes /*P*/ + 128;
+constexpr uint32_t kSmem = kTileBytes /*Q*/ + 2 * kTileBytes /*K*/ + 2 * kTileBytes /*V*/ + 2 * kTileBytes /*P*/ + 512 /*xch*/ + 128;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -50,7 +53,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // HD: logical head dim (64 or 40); DK = HD rounded up to the UMMA k-step / n-step of 16
 template <int HD, bool DROP>
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(288, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __restrict__ valid,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale,
                    uint32_t drop_seed, uint32_t drop_thr, float drop_scale) {
@@ -60,15 +63,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
   uint8_t* sK = smem + kTileBytes;
   uint8_t* sV = smem + 3 * kTileBytes;
   uint8_t* sP = smem + 5 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+  // [2][128] row maxima of the two halves, exchanged as bf16: both halves use the same ROUNDED pair, so they agree
+  // exactly on the reference maximum (which only has to stay within 2^8 of the true one)
+  __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(smem + 7 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes + 512);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
   uint64_t* q_full = bars + 4;
   uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;     // 128 arrivals: S_j has been copied to registers
-  uint64_t* p_full = bars + 7;     // 128 arrivals: P_j is in smem (and O has been rescaled if needed)
+  uint64_t* s_free = bars + 6;     // 256 arrivals: S_j has been copied to registers
+  uint64_t* p_full = bars + 7;     // 256 arrivals: P_j is in smem (and O has been rescaled if needed)
   uint64_t* o_done = bars + 8;     // PV_j retired: P smem reusable, O readable
-  uint64_t* q_ready = bars + 9;    // 128 arrivals: pad columns of Q zeroed (HD % 16 != 0 only)
+  uint64_t* q_ready = bars + 9;    // 256 arrivals: pad columns of Q zeroed (HD % 16 != 0 only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,7 +83,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
   nvalid = max(1, min(nvalid, T));
   const int nt = (nvalid + kTK - 1) / kTK;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tm_qkv);
     for (int i = 0; i < 2; ++i) {
@@ -86,13 +92,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
     }
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
     mbar_init(o_done, 1);
-    mbar_init(q_ready, 128);
+    mbar_init(q_ready, 256);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,7 +106,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
   const uint32_t tmem_s = tmem_base;        // 128 fp32 columns
   const uint32_t tmem_o = tmem_base + 128;  // DK fp32 columns
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       const int HD_all = H * HD;
       auto load_kv = [&](int j) {
@@ -113,11 +119,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
       tma_load_3d(&tm_qkv, q_full, sQ, h * HD, q0, b);
       load_kv(0);
       if (nt > 1) load_kv(1);
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S: A = Q (K-major), B = K (K-major)
       const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);   // O: A = P (K-major), B = V (MN-major)
       const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
+      auto nk16 = [&](int j) { return (min(kTK, nvalid - j * kTK) + 15) & ~15; };  // valid keys of tile j, rounded
       auto issue_s = [&](int j) {
         const uint32_t ka = smem_u32(sK + (j & 1) * kTileBytes);
+        const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk16(j), 0, 0);  // S: A = Q, B = K, both K-major
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k)
           tc_mma_bf16(tmem_s, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024), idesc_s,
@@ -139,8 +146,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         const uint32_t va = smem_u32(sV + st * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kTK / 16; ++k)  // P: two 64-key atoms of 16 KiB; V: 16 key rows = 2 KiB per step
+        const int ksteps = nk16(j) / 16;
+        for (int k = 0; k < ksteps; ++k)  // P: two 64-key atoms of 16 KiB; V: 16 key rows = 2 KiB per step
           tc_mma_bf16(tmem_o, umma_desc_sw128(pa + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
                       umma_desc_sw128(va + k * 2048, 0, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(o_done);
@@ -152,48 +159,69 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax (one query row per thread)
-    const int row_in_tile = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // ------------------------------------------------------------ softmax: thread = (query row, 64-key half)
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t rsw = (uint32_t)(row_in_tile & 7);
+    const bool warp_live = q0 + quarter * 32 < T;  // warp-uniform: some query row of this warp exists
     if constexpr (HD % 16 != 0) {
       // columns HD..DK-1 of this Q row hold the next head's values: zero them so they drop out of Q K^T
       mbar_wait(q_full, 0);
       static_assert(HD % 8 == 0 && DK - HD == 8, "pad is one 16-byte chunk");
-      st_shared_v4(smem_u32(sQ) + row_in_tile * 128 + ((((uint32_t)HD >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
-      fence_async_shared();
+      if (half == 0) {
+        st_shared_v4(smem_u32(sQ) + row_in_tile * 128 + ((((uint32_t)HD >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+        fence_async_shared();
+      }
       mbar_arrive(q_ready);
     }
     const float sc = scale * kLog2e;
-    float m_i = -INFINITY, l_i = 0.f;
-    const uint32_t prow = smem_u32(sP) + row_in_tile * 128;
+    float m_i = -INFINITY, l_i = 0.f;  // m_i: reference maximum of the whole row (shared by both halves), l_i: this half
+    const uint32_t prow = smem_u32(sP) + half * kTileBytes + row_in_tile * 128;
     // dropout pair index of (b, h, q, k): ((b*H + h)*T + q) * ceil(T/2) + (k >> 1)
     const uint32_t drop_row = (uint32_t)(((b * H + h) * T + q0 + row_in_tile) * ((T + 1) >> 1));
+    // O columns owned by this thread for rescale / final store: half 0 -> [0, 32), half 1 -> [32, DK)
+    const int oc_begin = half ? 32 : 0, oc_end = half ? DK : 32;
     for (int j = 0; j < nt; ++j) {
+      const int nk = nvalid - j * kTK;             // valid keys in this tile (>= 1; >= 128 for all but the last tile)
+      const int nkh = nk - half * 64;              // ... of which fall after this half's first column
+      const int n16 = ((min(kTK, nk) + 15) & ~15) - half * 64;  // columns of this half the MMAs touch (<= 0: none)
+      const bool work = warp_live && n16 > 0;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t r[kTK];
-#pragma unroll
-      for (int c = 0; c < kTK; c += 32) tmem_ld32(tmem_s + lane_off + c, r + c);
-      tmem_ld_wait();
+      uint32_t r[64];
+      if (work) {
+        tmem_ld32(tmem_s + lane_off + half * 64, r);
+        if (n16 > 32) tmem_ld32(tmem_s + lane_off + half * 64 + 32, r + 32);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(s_free);
-      const int nk = nvalid - j * kTK;  // valid keys in this tile (>= 1; >= 128 for all but the last tile)
-      // 8 independent max chains (a single 128-long dependent chain costs ~500 cycles of latency)
-      float mx8[8];
-      if (nk >= kTK) {
+      // 8 independent max chains over this half's columns
+      float mx = -INFINITY;
+      if (work) {
+        float mx8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 8; ++i) mx8[i] = -INFINITY;
 #pragma unroll
-        for (int i = 8; i < kTK; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(r[i]));
-      } else {
+        for (int c = 0; c < 64; c += 16) {
+          if (c < n16) {
+            if (c + 16 <= nkh) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = i < nk ? __uint_as_float(r[i]) : -INFINITY;
+              for (int i = 0; i < 16; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(r[c + i]));
+            } else {
 #pragma unroll
-        for (int i = 8; i < kTK; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], i < nk ? __uint_as_float(r[i]) : -INFINITY);
+              for (int i = 0; i < 16; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], c + i < nkh ? __uint_as_float(r[c + i]) : -INFINITY);
+            }
+          }
+        }
+        mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       }
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      // the two halves of a row agree on the row maximum through smem (one named barrier per key tile)
+      const __nv_bfloat16 mxr = __float2bfloat16_ru(mx);
+      xch[half * kTQ + row_in_tile] = mxr;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(__bfloat162float(mxr), __bfloat162float(xch[(half ^ 1) * kTQ + row_in_tile]));
       const float m_new = fmaxf(m_i, mx * sc);
       if (j == 0) {
         m_i = m_new;
@@ -206,8 +234,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
           const float alpha = need ? ex2_approx(m_i - m_new) : 1.f;
           if (need) m_i = m_new;
           l_i *= alpha;
-#pragma unroll
-          for (int c = 0; c < DK; c += 16) {
+          for (int c = oc_begin; c < oc_end; c += 16) {
             uint32_t o[16];
             tmem_ld16(tmem_o + lane_off + c, o);
             tmem_ld_wait();
@@ -218,50 +245,59 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
           tmem_st_wait();
         }
       }
-      // probabilities -> bf16 -> swizzled smem (K-major A operand: two 64-key atoms)
-      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float neg_m = -m_i;
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // xch may be rewritten by the next tile only after both halves read it
+      // probabilities -> bf16 -> swizzled smem (K-major A operand: this half's 64-key atom)
+      if (work) {
+        float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float neg_m = -m_i;
 #pragma unroll
-      for (int c = 0; c < kTK; c += 16) {
-        float pv[16];
-        if (nk >= kTK) {
+        for (int c = 0; c < 64; c += 16) {
+          if (c < n16) {
+            float pv[16];
+            if (c + 16 <= nkh) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[c + i]), sc, neg_m));
-        } else {
+              for (int i = 0; i < 16; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[c + i]), sc, neg_m));
+            } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pv[i] = (c + i < nk) ? ex2_approx(fmaf(__uint_as_float(r[c + i]), sc, neg_m)) : 0.f;
-        }
+              for (int i = 0; i < 16; ++i)
+                pv[i] = (c + i < nkh) ? ex2_approx(fmaf(__uint_as_float(r[c + i]), sc, neg_m)) : 0.f;
+            }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ls4[i & 3] += pv[i];
-        if (DROP) {  // attention dropout on the probabilities (the row sum l stays un-dropped)
+            for (int i = 0; i < 16; ++i) ls4[i & 3] += pv[i];
+            if (DROP) {  // attention dropout on the probabilities (the row sum l stays un-dropped)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float m0, m1;
-            dropout_pair(drop_seed, drop_row + (uint32_t)((j * kTK + c) >> 1) + i, drop_thr, drop_scale, m0, m1);
-            pv[2 * i] *= m0;
-            pv[2 * i + 1] *= m1;
+              for (int i = 0; i < 8; ++i) {
+                float m0, m1;
+                dropout_pair(drop_seed, drop_row + (uint32_t)((j * kTK + half * 64 + c) >> 1) + i, drop_thr, drop_scale, m0,
+                             m1);
+                pv[2 * i] *= m0;
+                pv[2 * i + 1] *= m1;
+              }
+            }
+            const uint32_t ch = (uint32_t)(c >> 3);
+            st_shared_v4(prow + (((ch) ^ rsw) << 4), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]),
+                         pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
+            st_shared_v4(prow + (((ch + 1) ^ rsw) << 4), pack_bf16(pv[8], pv[9]), pack_bf16(pv[10], pv[11]),
+                         pack_bf16(pv[12], pv[13]), pack_bf16(pv[14], pv[15]));
           }
         }
-        const uint32_t atom = (uint32_t)(c >> 6) * kTileBytes;
-        const uint32_t ch = (uint32_t)((c & 63) >> 3);
-        st_shared_v4(prow + atom + (((ch) ^ rsw) << 4), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]),
-                     pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
-        st_shared_v4(prow + atom + (((ch + 1) ^ rsw) << 4), pack_bf16(pv[8], pv[9]), pack_bf16(pv[10], pv[11]),
-                     pack_bf16(pv[12], pv[13]), pack_bf16(pv[14], pv[15]));
+        l_i += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       }
-      l_i += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       tc_fence_before();
       fence_async_shared();
       mbar_arrive(p_full);
     }
     mbar_wait(o_done, (nt - 1) & 1);
     tc_fence_after();
+    // row sum of both halves, exchanged through the (now idle) P tile
+    float* lx = reinterpret_cast<float*>(sP);
+    lx[half * kTQ + row_in_tile] = l_i;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_row = l_i + lx[(half ^ 1) * kTQ + row_in_tile];
     const int row = q0 + row_in_tile;
-    const float inv = 1.f / l_i;
+    const float inv = 1.f / l_row;
     __nv_bfloat16* orow = out + ((long long)b * T + row) * (H * HD) + h * HD;
-#pragma unroll
-    for (int c = 0; c < DK; c += 16) {
+    for (int c = oc_begin; c < oc_end; c += 16) {
       uint32_t o[16];
       tmem_ld16(tmem_o + lane_off + c, o);
       tmem_ld_wait();
@@ -275,11 +311,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
           op[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
       }
     }
-    if (lse && row < T) lse[((long long)b * H + h) * T + row] = (m_i + log2f(l_i)) * kLn2;
+    if (lse && half == 0 && row < T) lse[((long long)b * H + h) * T + row] = (m_i + log2f(l_row)) * kLn2;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -301,10 +337,10 @@ int launch_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int
   }
   dim3 grid((T + kTQ - 1) / kTQ, H, B);
   if (drop_p > 0.f)
-    attn_fwd_tc_kernel<HD, true><<<grid, 160, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale,
+    attn_fwd_tc_kernel<HD, true><<<grid, 288, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale,
                                                           drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p));
   else
-    attn_fwd_tc_kernel<HD, false><<<grid, 160, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale, 0u,
+    attn_fwd_tc_kernel<HD, false><<<grid, 288, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale, 0u,
                                                            0u, 1.f);
   FHB_LAUNCH_CHECK();
   return 0;

@@ -160,7 +160,11 @@ def _lengths_from_mask(padding_mask: Optional[torch.Tensor]) -> Optional[List[in
         K.mask_lengths(padding_mask.contiguous().view(torch.uint8), out)
         lengths = out.tolist()
     else:
-        lengths = (~padding_mask).sum(-1).tolist()
+        # host mask (what utils/dataset.py:63-74 hands over): SIMD byte count, ~1 ms for 32 x 250k samples
+        # (torch's bool sum goes through int64 and costs several ms on one thread)
+        import numpy as np
+        m = padding_mask.contiguous().view(torch.uint8).numpy()
+        lengths = (padding_mask.shape[1] - np.count_nonzero(m, axis=1)).tolist()
     if all(n == padding_mask.shape[1] for n in lengths):
         return None
     return lengths

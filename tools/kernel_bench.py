@@ -101,8 +101,11 @@ for (d, T, H) in ((64, 779, 12), (40, 389, 12)):
     do = rnd(B, T, H * d)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, H, T, device=dev)
-    timeit(f"attn bwd d={d} T={T}", lambda: K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5),
+    ws = torch.empty(B * T, H * d, device=dev)
+    timeit(f"attn bwd d={d} T={T} (tcgen05)", lambda: K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5, dq_ws=ws),
            flops=10.0 * B * H * T * T * d)
+    timeit(f"attn bwd d={d} T={T} +dropout", lambda: K.attn_bwd(qkv, vt, out, do, lse, dqkv, delta, B, T, H, d, d ** -0.5, dq_ws=ws,
+                                                              drop=(123, 0.1)), flops=10.0 * B * H * T * T * d)
 
 for (rows, C) in ((Mt, 768), (Ms, 480)):
     x = rnd(rows, C)
