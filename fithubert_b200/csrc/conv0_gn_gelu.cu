@@ -89,7 +89,8 @@ template <int CPT>  // channels per thread (8 -> one 16-byte bf16 store)
 __global__ void __launch_bounds__(256)
 conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
                  const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ out) {
+                 const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ out,
+                 __nv_bfloat16* __restrict__ gp_out) {
   extern __shared__ float xs[];  // frames_per_block*5 + 5 samples
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * frames_per_block;
@@ -116,13 +117,14 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
     float v[kK];
 #pragma unroll
     for (int j = 0; j < kK; ++j) v[j] = xs[t * kS + j];
-    float y[CPT];
+    float y[CPT], gp[CPT];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
       float a = 0.f;
 #pragma unroll
       for (int j = 0; j < kK; ++j) a = fmaf(w[i][j], v[j], a);
-      y[i] = gelu_erf(fmaf(a, sc[i], sh[i]));
+      if (gp_out) gelu_erf_both(fmaf(a, sc[i], sh[i]), y[i], gp[i]);
+      else y[i] = gelu_erf(fmaf(a, sc[i], sh[i]));
     }
     uint32_t pk[CPT / 2];
 #pragma unroll
@@ -131,6 +133,13 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
       *reinterpret_cast<uint4*>(o + (long long)t * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     } else {
       *reinterpret_cast<uint2*>(o + (long long)t * C) = make_uint2(pk[0], pk[1]);
+    }
+    if (gp_out) {  // gelu'(z): the backward multiplier (applied by the dgrad epilogue of the next layer)
+#pragma unroll
+      for (int i = 0; i < CPT / 2; ++i) pk[i] = pack_bf16(gp[2 * i], gp[2 * i + 1]);
+      __nv_bfloat16* og = gp_out + ((long long)b * T0 + t_begin) * C + c0 + (long long)t * C;
+      if (CPT == 8) *reinterpret_cast<uint4*>(og) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      else *reinterpret_cast<uint2*>(og) = make_uint2(pk[0], pk[1]);
     }
   }
 }
@@ -143,7 +152,7 @@ __global__ void __launch_bounds__(256)
 conv0_bwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
                  const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dy,
-                 float* __restrict__ acc_out /*[B][C][12]*/) {
+                 float* __restrict__ acc_out /*[B][C][12]*/, int dy_is_dz) {
   extern __shared__ float smem[];
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * frames_per_block;
@@ -179,23 +188,113 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
       const uint2 raw = __ldg(reinterpret_cast<const uint2*>(d + (long long)t * C));
       const float2 d01 = unpack_bf16(raw.x), d23 = unpack_bf16(raw.y);
       const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+      if (dy_is_dz) {
+        // dy already carries gelu'(z) (saved by the forward, multiplied in by the producing dgrad epilogue):
+        // only A0 and P_j are accumulated; A1 = rstd * (w . P - mean * A0) follows algebraically below
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          acc[i][0] += dv[i];
+#pragma unroll
+          for (int j = 0; j < kK; ++j) acc[i][2 + j] = fmaf(dv[i], v[j], acc[i][2 + j]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int j = 0; j < kK; ++j) a = fmaf(w[i][j], v[j], a);
+          const float xhat = (a - mu[i]) * rs[i];
+          const float dz = dv[i] * gelu_erf_grad(fmaf(xhat, g[i], be[i]));
+          acc[i][0] += dz;
+          acc[i][1] += dz * xhat;
+#pragma unroll
+          for (int j = 0; j < kK; ++j) acc[i][2 + j] = fmaf(dz, v[j], acc[i][2 + j]);
+        }
+      }
+    }
+    if (dy_is_dz) {
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
-        float a = 0.f;
+        float wp = 0.f;
 #pragma unroll
-        for (int j = 0; j < kK; ++j) a = fmaf(w[i][j], v[j], a);
-        const float xhat = (a - mu[i]) * rs[i];
-        const float dz = dv[i] * gelu_erf_grad(fmaf(xhat, g[i], be[i]));
-        acc[i][0] += dz;
-        acc[i][1] += dz * xhat;
-#pragma unroll
-        for (int j = 0; j < kK; ++j) acc[i][2 + j] = fmaf(dz, v[j], acc[i][2 + j]);
+        for (int j = 0; j < kK; ++j) wp = fmaf(w[i][j], acc[i][2 + j], wp);
+        acc[i][1] = rs[i] * (wp - mu[i] * acc[i][0]);
       }
     }
 #pragma unroll
     for (int i = 0; i < CPT; ++i)
 #pragma unroll
       for (int q = 0; q < kNAcc; ++q) atomicAdd(&red[(c0 + i) * kNAcc + q], acc[i][q]);
+  }
+  __syncthreads();
+  float* o = acc_out + (long long)b * C * kNAcc;
+  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) atomicAdd(o + i, red[i]);
+}
+
+// Training path: dy already carries gelu'(z) (saved by the forward as gp_out and multiplied in by the dgrad
+// epilogue that produced dy), so per (b, c) only A0 = sum_t dz and P_j = sum_t dz x[5t+j] are streamed
+// (11 FMAs per element, HBM-bound read of dz); A1 = rstd (w . P - mean A0) follows algebraically.
+// 4 frames are loaded ahead of the FMAs so that every thread keeps 4 x 8-byte loads in flight.
+template <int CPT>  // 4
+__global__ void __launch_bounds__(256)
+conv0_bwd_dz_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
+                    const float* __restrict__ weight, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const __nv_bfloat16* __restrict__ dz, float* __restrict__ acc_out /*[B][C][12]*/) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int nframes = min(frames_per_block, T0 - t_begin);
+  const int nsamp = nframes * kS + (kK - kS);
+  float* xs = smem;
+  float* red = smem + frames_per_block * kS + (kK - kS);  // [C][12]
+  const float* x = wave + (long long)b * ld + (long long)t_begin * kS;
+  for (int i = threadIdx.x; i < nsamp; i += blockDim.x) xs[i] = __ldg(x + i);
+  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) red[i] = 0.f;
+  const int tcols = C / CPT;
+  const int tx = threadIdx.x % tcols, ty = threadIdx.x / tcols, fy = blockDim.x / tcols;
+  const int c0 = tx * CPT;
+  float acc[CPT][kNAcc];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i)
+#pragma unroll
+    for (int q = 0; q < kNAcc; ++q) acc[i][q] = 0.f;
+  __syncthreads();
+  if (ty < fy) {
+    const __nv_bfloat16* d = dz + ((long long)b * T0 + t_begin) * C + c0;
+    constexpr int U = 4;
+    for (int t0 = ty; t0 < nframes; t0 += U * fy) {
+      uint2 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * fy;
+        raw[u] = t < nframes ? __ldg(reinterpret_cast<const uint2*>(d + (long long)t * C)) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = min(t0 + u * fy, nframes - 1);  // out-of-range frames carry dz = 0
+        float v[kK];
+#pragma unroll
+        for (int j = 0; j < kK; ++j) v[j] = xs[t * kS + j];
+        const float2 d01 = unpack_bf16(raw[u].x), d23 = unpack_bf16(raw[u].y);
+        const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          acc[i][0] += dv[i];
+#pragma unroll
+          for (int j = 0; j < kK; ++j) acc[i][2 + j] = fmaf(dv[i], v[j], acc[i][2 + j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      float wp = 0.f;
+#pragma unroll
+      for (int j = 0; j < kK; ++j) wp = fmaf(__ldg(weight + (c0 + i) * kK + j), acc[i][2 + j], wp);
+      const float mu = mean[b * C + c0 + i], rs = rstd[b * C + c0 + i];
+      acc[i][1] = rs * (wp - mu * acc[i][0]);
+#pragma unroll
+      for (int q = 0; q < kNAcc; ++q) atomicAdd(&red[(c0 + i) * kNAcc + q], acc[i][q]);
+    }
   }
   __syncthreads();
   float* o = acc_out + (long long)b * C * kNAcc;
@@ -277,7 +376,8 @@ extern "C" int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* a, fhb_stream_t strea
     dim3 grid((a->T0 + frames - 1) / frames, a->B);
     const size_t smem = sizeof(float) * (frames * kS + (kK - kS));
     conv0_fwd_kernel<8><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
-                                                 a->mean, a->rstd, static_cast<__nv_bfloat16*>(a->out));
+                                                 a->mean, a->rstd, static_cast<__nv_bfloat16*>(a->out),
+                                                 static_cast<__nv_bfloat16*>(a->gp_out));
     FHB_LAUNCH_CHECK();
   }
   return 0;
@@ -290,12 +390,26 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
   FHB_ARG_CHECK(a->C % 4 == 0 && 256 % (a->C / 4) == 0, "conv0 bwd: C=%d must be 4*2^k, <= 1024", a->C);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   FHB_CUDA_CHECK(cudaMemsetAsync(a->acc, 0, sizeof(float) * kNAcc * a->B * a->C, s));
+  if (a->dy_is_dz) {
+    const int frames = 1024;
+    dim3 grid((a->T0 + frames - 1) / frames, a->B);
+    const size_t smem = sizeof(float) * (frames * kS + (kK - kS) + a->C * kNAcc);
+    conv0_bwd_dz_kernel<4><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->mean, a->rstd,
+                                                   static_cast<const __nv_bfloat16*>(a->dy), a->acc);
+    FHB_LAUNCH_CHECK();
+    conv0_bwd_finalize_kernel<<<(a->C + 63) / 64, 64, 0, s>>>(a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
+                                                             a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
+                                                             a->accumulate);
+    FHB_LAUNCH_CHECK();
+    return 0;
+  }
   // 2048 frames per block: few blocks per (sample, channel) -> few global atomics per accumulator
   const int frames = 2048;
   dim3 grid((a->T0 + frames - 1) / frames, a->B);
   const size_t smem = sizeof(float) * (frames * kS + (kK - kS) + a->C * kNAcc);
   conv0_bwd_kernel<4><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
-                                              a->mean, a->rstd, static_cast<const __nv_bfloat16*>(a->dy), a->acc);
+                                              a->mean, a->rstd, static_cast<const __nv_bfloat16*>(a->dy), a->acc,
+                                              a->dy_is_dz);
   FHB_LAUNCH_CHECK();
   conv0_bwd_finalize_kernel<<<(a->C + 63) / 64, 64, 0, s>>>(a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
                                                            a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,

@@ -79,6 +79,9 @@ class Geometry:
         self.d = E // H
         self.cg = E // G
         self.cp = round_up(self.cg, 16)
+        # pos-conv time blocking: one GEMM row = pdelta consecutive frames (N = pdelta * cp fills the 128 x N UMMA)
+        self.pdelta = 4 if (kpos + 4) * self.cp % 64 == 0 else 1
+        self.kpx = kpos + (self.pdelta if self.pdelta > 1 else 0)  # taps of the blocked weight operand
         self.d_out = d_out
         self.student = student
         self.c_feat = self.conv_layers[-1][0]
@@ -150,8 +153,8 @@ class WeightSet:
         self.spec = spec
         nb = sum(math.prod(d) for (_, t, d, _) in spec if t == bf16)
         nf = sum(math.prod(d) for (_, t, d, _) in spec if t == f32)
-        pc = g.G * g.cp * g.kpos * g.cp
-        self.buf16 = torch.empty(round_up(nb, 64) + 64 * len(spec) + 2 * pc + 128, device=self.device, dtype=bf16)
+        pc = g.G * g.pdelta * g.cp * g.kpx * g.cp
+        self.buf16 = torch.empty(round_up(nb, 64) + 64 * len(spec) + 2 * round_up(pc, 64) + 128, device=self.device, dtype=bf16)
         self.buf32 = torch.empty(nf + 8 * len(spec) + g.kpos + 64, device=self.device, dtype=f32)
         o16 = o32 = 0
         for (name, t, dims, _) in spec:
@@ -165,6 +168,8 @@ class WeightSet:
         self.views["pc.w"] = self.buf16[o16:o16 + pc]
         o16 += round_up(pc, 64)
         self.views["pc.wt"] = self.buf16[o16:o16 + pc]
+        self.views["pc.w"].zero_()   # the blocked layout keeps structural zeros the prep kernel never touches
+        self.views["pc.wt"].zero_()
         self.views["pc.inv"] = self.buf32[o32:o32 + g.kpos]
 
     def __getitem__(self, name):
@@ -221,9 +226,9 @@ class WeightSet:
         K.prep_multi(self._table, self._n_entries, self._max_n)
         g = self.g
         v, gn = self.params["encoder.pos_conv.0.weight_v"], self.params["encoder.pos_conv.0.weight_g"]
-        K.posconv_wn_prep(v, gn, self.views["pc.w"], self.views["pc.inv"], g.E, g.G, g.kpos, g.cp, 0)
+        K.posconv_wn_prep(v, gn, self.views["pc.w"], self.views["pc.inv"], g.E, g.G, g.kpos, g.cp, 0, g.pdelta)
         if self.train:
-            K.posconv_wn_prep(v, gn, self.views["pc.wt"], None, g.E, g.G, g.kpos, g.cp, 1)
+            K.posconv_wn_prep(v, gn, self.views["pc.wt"], None, g.E, g.G, g.kpos, g.cp, 1, g.pdelta)
         self._sig = sig
 
 
@@ -369,10 +374,11 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool)
     c.mean0 = torch.empty(B, C0, device=dev, dtype=f32)
     c.rstd0 = torch.empty(B, C0, device=dev, dtype=f32)
     y = torch.empty(B, T0, C0, device=dev, dtype=bf16)
+    gp0 = torch.empty(B, T0, C0, device=dev, dtype=bf16) if save else None
     K.conv0_fwd(wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
-                P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat, c.mean0, c.rstd0, y)
+                P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat, c.mean0, c.rstd0, y, gp_out=gp0)
     c.y = [y]
-    c.u = [None]  # per layer: gelu'(pre-activation), saved by the forward epilogue (the backward multiplier)
+    c.u = [gp0]  # per layer: gelu'(pre-activation), saved by the forward epilogue (the backward multiplier)
     # (buffer, rows allocated per sample, first data row)
     x_buf, x_rows, x_row0, cin, T = y, T0, 0, C0, T0
     for i, (co, k, s) in enumerate(g.conv_layers):
@@ -416,22 +422,24 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Ten
     if d_in is not None:  # dropout_input (modules/model.py:489); `features_to_distill` above stays un-dropped
         feats = K.dropout(feats, torch.empty_like(feats), *d_in)
     # positional conv as one batched GEMM per (sample, group)
-    G, cp, kp = g.G, g.cp, g.kpos
-    Tp = T + kp
+    G, cp, kp, dl = g.G, g.cp, g.kpos, g.pdelta
+    R = (T + dl - 1) // dl                   # GEMM rows per (sample, group): one row = dl consecutive frames
+    Tp = dl * R + g.kpx                      # padded time extent every overlapped row window stays inside
     xg = torch.empty(B * G, Tp, cp, device=dev, dtype=bf16)
     K.posconv_pack(feats, valid_t, xg, B, T, E, G, cp, kp // 2, Tp)
-    conv = torch.empty(B * T, G * cp, device=dev, dtype=bf16)
-    a3 = L.tensor3(data_ptr=xg.data_ptr(), dim=(kp * cp, T, B * G), stride=(cp, Tp * cp))
-    b3 = L.tensor3(data_ptr=W["pc.w"].data_ptr(), dim=(kp * cp, cp, G), stride=(kp * cp, cp * kp * cp))
-    K.gemm_raw(a3, b3, conv, T, cp, kp * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
-               d_ld=G * cp, d_hi_stride=T * G * cp, d_lo_stride=cp)
+    conv = torch.empty(B * R, G * dl * cp, device=dev, dtype=bf16)  # [b][r][g][dl][cp]
+    a3 = L.tensor3(data_ptr=xg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    b3 = L.tensor3(data_ptr=W["pc.w"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))
+    K.gemm_raw(a3, b3, conv, R, dl * cp, g.kpx * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
+               d_ld=G * dl * cp, d_hi_stride=R * G * dl * cp, d_lo_stride=dl * cp)
     c.xg, c.conv = (xg, conv) if save else (None, conv)
     enc = torch.empty(B * T, E, device=dev, dtype=bf16)
     c.h = torch.empty(B * T, E, device=dev, dtype=bf16) if save else None
     c.mean_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
     c.rstd_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
     K.posconv_finish_fwd(feats, valid_t, conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"],
-                         P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp)
+                         P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp, delta=dl)
+    c.Tp, c.R = Tp, R
     d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
     if d_pro is not None:  # F.dropout after the encoder LayerNorm (modules/module.py:294)
         K.dropout(enc, enc, *d_pro)
@@ -695,8 +703,8 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
     if d_pro is not None:
         K.dropout(denc, denc, *d_pro)
-    G, cp, kp = g.G, g.cp, g.kpos
-    Tp = T + kp
+    G, cp, kp, dl = g.G, g.cp, g.kpos, g.pdelta
+    Tp, R = c.Tp, c.R
     dh = torch.empty(B * T, E, device=dev, dtype=bf16)
     pad_b = kp // 2 - 1
     dcg = torch.empty(B * G, Tp, cp, device=dev, dtype=bf16)
@@ -704,23 +712,23 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     K.zero_rows(dcg, (pad_b + T) * cp, Tp * cp, (Tp - pad_b - T) * cp, B * G)
     K.posconv_finish_bwd(denc, c.h, c.conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"], c.mean_e,
                          c.rstd_e, dh, dcg, gv("encoder.layer_norm.weight"), gv("encoder.layer_norm.bias"),
-                         gv("encoder.pos_conv.0.bias"), B, T, E, G, cp, pad_b, Tp)
-    dxc = torch.empty(B * T, G * cp, device=dev, dtype=bf16)
-    a3 = L.tensor3(data_ptr=dcg.data_ptr(), dim=(kp * cp, T, B * G), stride=(cp, Tp * cp))
-    b3 = L.tensor3(data_ptr=W["pc.wt"].data_ptr(), dim=(kp * cp, cp, G), stride=(kp * cp, cp * kp * cp))
-    K.gemm_raw(a3, b3, dxc, T, cp, kp * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
-               d_ld=G * cp, d_hi_stride=T * G * cp, d_lo_stride=cp)
-    # wgrad: dwt[g][(j,ci)][co] = sum_{b,t} xg[b,g,t+j,ci] * dcg[b,g,t+pad_b,co]
-    dwt = torch.empty(G, kp * cp, cp, device=dev, dtype=f32)
-    a3 = L.tensor3(data_ptr=c.xg.data_ptr(), dim=(kp * cp, T, B * G), stride=(cp, Tp * cp))
-    b3 = L.tensor3(data_ptr=dcg.data_ptr(), dim=(cp, Tp, B * G), stride=(cp, Tp * cp))
-    K.gemm_raw(a3, b3, dwt, kp * cp, cp, T, a_major=1, b_major=1, num_ob=G, ob_mod=G, num_cb=B,
-               a_coord=(0, 0, 1, G), b_coord=(0, 0, 1, G), d_ld=cp, d_lo_stride=kp * cp * cp, b_c1_off=pad_b,
-               split_k=1)
+                         gv("encoder.pos_conv.0.bias"), B, T, E, G, cp, pad_b, Tp, delta=dl)
+    dxc = torch.empty(B * R, G * dl * cp, device=dev, dtype=bf16)  # [b][r][g][dl][cp], like the forward output
+    a3 = L.tensor3(data_ptr=dcg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    b3 = L.tensor3(data_ptr=W["pc.wt"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))
+    K.gemm_raw(a3, b3, dxc, R, dl * cp, g.kpx * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
+               d_ld=G * dl * cp, d_hi_stride=R * G * dl * cp, d_lo_stride=dl * cp)
+    # wgrad, time-blocked like the forward: dwt'[g][(j',ci)][(dl,co)] = sum_{b,r} xg[b,g,dl_*r + j',ci] *
+    # dcg[b,g,dl_*r + dl + pad_b,co]  (N = dl_*cp instead of cp); posconv_wn_bwd folds the dl_ shifted partials
+    dwt = torch.empty(G, g.kpx * cp, dl * cp, device=dev, dtype=f32)
+    a3 = L.tensor3(data_ptr=c.xg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    b3 = L.tensor3(data_ptr=dcg.data_ptr() + 2 * pad_b * cp, dim=(dl * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    K.gemm_raw(a3, b3, dwt, g.kpx * cp, dl * cp, R, a_major=1, b_major=1, num_ob=G, ob_mod=G, num_cb=B,
+               a_coord=(0, 0, 1, G), b_coord=(0, 0, 1, G), d_ld=dl * cp, d_lo_stride=g.kpx * cp * dl * cp, split_k=1)
     K.posconv_wn_bwd(dwt, P["encoder.pos_conv.0.weight_v"], P["encoder.pos_conv.0.weight_g"], W["pc.inv"],
-                     gv("encoder.pos_conv.0.weight_v"), gv("encoder.pos_conv.0.weight_g"), E, G, kp, cp, True)
+                     gv("encoder.pos_conv.0.weight_v"), gv("encoder.pos_conv.0.weight_g"), E, G, kp, cp, True, delta=dl)
     dfeat = torch.empty(B * T, E, device=dev, dtype=bf16)
-    K.posconv_unpack_bwd(dh, dxc, c.valid_t, dfeat, B, T, E, G, cp)
+    K.posconv_unpack_bwd(dh, dxc, c.valid_t, dfeat, B, T, E, G, cp, delta=dl)
     d_in = drop.site(DropCfg.SITE_INPUT, drop.p_input) if drop is not None else None
     if d_in is not None:
         K.dropout(dfeat, dfeat, *d_in)
@@ -751,16 +759,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         x3 = L.tensor3(data_ptr=xin.data_ptr() + 2 * in_halo * cin, dim=(k * cin, To, B), stride=(s * cin, in_rows * cin))
         _wgrad(dy3, x3, gv(f"feature_extractor.conv_layers.{i}.0.weight").view(co, k * cin), co, k * cin, To,
                num_cb=B, a_cb=1, b_cb=1)
-        first = i == 1
-        if first:
-            # gradient wrt the GELU output of layer 0: no GELU derivative here (conv0 backward recomputes it)
-            assert (k, s) in ((1, 1), (2, 2)) or halo == 1
-            dprev = torch.empty(B, Tin, cin, device=dev, dtype=bf16)
-            flags, uprev = 0, None
-        else:
-            # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1})
-            dprev = torch.empty(B, in_rows, cin, device=dev, dtype=bf16)
-            flags, uprev = L.EPI_MUL_AUX, c.u[i - 1]
+        # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1}) (layer 0 included: its forward saved gelu' of the GroupNorm output)
+        dprev = torch.empty(B, in_rows, cin, device=dev, dtype=bf16)
+        flags, uprev = L.EPI_MUL_AUX, c.u[i - 1]
         if in_halo:  # halo rows must read as zero in the overlapped-view dgrad of layer i-1
             K.zero_rows(dprev, 0, in_rows * cin, cin, B)
             K.zero_rows(dprev, (in_rows - 1) * cin, in_rows * cin, cin, B)
@@ -790,4 +791,4 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     K.conv0_bwd(c.wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
                 P["feature_extractor.conv_layers.0.2.bias"], c.frames[0], c.stat, c.mean0, c.rstd0, du, acc,
                 gv("feature_extractor.conv_layers.0.0.weight"), gv("feature_extractor.conv_layers.0.2.weight"),
-                gv("feature_extractor.conv_layers.0.2.bias"), True)
+                gv("feature_extractor.conv_layers.0.2.bias"), True, dy_is_dz=True)

@@ -150,25 +150,26 @@ def _f(x):
     return C.c_float(float(x))
 
 
-def conv0_fwd(wave, weight, gamma, beta, T0, stat, mean, rstd, out, eps=1e-5):
+def conv0_fwd(wave, weight, gamma, beta, T0, stat, mean, rstd, out, eps=1e-5, gp_out=None):
     a = L.Conv0Args()
     B, Ld = wave.shape
     a.wave, a.wave_ld = wave.data_ptr(), wave.stride(0)
     a.B, a.L, a.C, a.T0, a.kernel, a.stride, a.eps = B, Ld, weight.shape[0], T0, weight.shape[-1], 5, eps
     a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
     a.stat, a.mean, a.rstd, a.out = stat.data_ptr(), mean.data_ptr(), rstd.data_ptr(), out.data_ptr()
+    a.gp_out = None if gp_out is None else gp_out.data_ptr()
     L.check(L.lib().fhb_conv0_gn_gelu_fwd(C.byref(a), L.stream_ptr()), "fhb_conv0_gn_gelu_fwd")
 
 
 def conv0_bwd(wave, weight, gamma, beta, T0, stat, mean, rstd, dy, acc, dweight, dgamma, dbeta,
-              accumulate=True, eps=1e-5):
+              accumulate=True, eps=1e-5, dy_is_dz=False):
     a = L.Conv0Args()
     B, Ld = wave.shape
     a.wave, a.wave_ld = wave.data_ptr(), wave.stride(0)
     a.B, a.L, a.C, a.T0, a.kernel, a.stride, a.eps = B, Ld, weight.shape[0], T0, weight.shape[-1], 5, eps
     a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
     a.stat, a.mean, a.rstd = stat.data_ptr(), mean.data_ptr(), rstd.data_ptr()
-    a.dy, a.acc = dy.data_ptr(), acc.data_ptr()
+    a.dy, a.acc, a.dy_is_dz = dy.data_ptr(), acc.data_ptr(), int(dy_is_dz)
     a.dweight, a.dgamma, a.dbeta, a.accumulate = dweight.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate)
     L.check(L.lib().fhb_conv0_gn_gelu_bwd(C.byref(a), L.stream_ptr()), "fhb_conv0_gn_gelu_bwd")
 
@@ -198,31 +199,32 @@ def posconv_pack(x, valid, xg, B, T, Cd, G, cp, pad_l, Tp):
             "fhb_posconv_pack")
 
 
-def posconv_wn_prep(v, g, w_out, inv_norm, Cd, G, Kt, cp, flip_transpose):
+def posconv_wn_prep(v, g, w_out, inv_norm, Cd, G, Kt, cp, flip_transpose, delta=1):
     L.check(L.lib().fhb_posconv_wn_prep(L.ptr(v), L.ptr(g), L.ptr(w_out), L.ptr(inv_norm), Cd, G, Kt, cp,
-                                        int(flip_transpose), L.stream_ptr()), "fhb_posconv_wn_prep")
+                                        int(flip_transpose), delta, L.stream_ptr()), "fhb_posconv_wn_prep")
 
 
-def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5):
+def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5, delta=1):
     L.check(L.lib().fhb_posconv_finish_fwd(L.ptr(x), L.ptr(valid), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(beta),
                                            L.ptr(h_out), L.ptr(y), L.ptr(mean), L.ptr(rstd), B, T, Cd, G, cp, _f(eps),
-                                           L.stream_ptr()), "fhb_posconv_finish_fwd")
+                                           delta, L.stream_ptr()), "fhb_posconv_finish_fwd")
 
 
-def posconv_finish_bwd(dy, h, conv, bias, gamma, mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, Cd, G, cp, pad_l, Tp):
+def posconv_finish_bwd(dy, h, conv, bias, gamma, mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, Cd, G, cp, pad_l, Tp,
+                       delta=1):
     L.check(L.lib().fhb_posconv_finish_bwd(L.ptr(dy), L.ptr(h), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(mean),
                                            L.ptr(rstd), L.ptr(dh), L.ptr(dcg), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias),
-                                           B, T, Cd, G, cp, pad_l, Tp, L.stream_ptr()), "fhb_posconv_finish_bwd")
+                                           B, T, Cd, G, cp, pad_l, Tp, delta, L.stream_ptr()), "fhb_posconv_finish_bwd")
 
 
-def posconv_unpack_bwd(dh, dxc, valid, dx, B, T, Cd, G, cp):
-    L.check(L.lib().fhb_posconv_unpack_bwd(L.ptr(dh), L.ptr(dxc), L.ptr(valid), L.ptr(dx), B, T, Cd, G, cp,
+def posconv_unpack_bwd(dh, dxc, valid, dx, B, T, Cd, G, cp, delta=1):
+    L.check(L.lib().fhb_posconv_unpack_bwd(L.ptr(dh), L.ptr(dxc), L.ptr(valid), L.ptr(dx), B, T, Cd, G, cp, delta,
                                            L.stream_ptr()), "fhb_posconv_unpack_bwd")
 
 
-def posconv_wn_bwd(dwt, v, g, inv_norm, dv, dg, Cd, G, Kt, cp, accumulate=True):
+def posconv_wn_bwd(dwt, v, g, inv_norm, dv, dg, Cd, G, Kt, cp, accumulate=True, delta=1):
     L.check(L.lib().fhb_posconv_wn_bwd(L.ptr(dwt), L.ptr(v), L.ptr(g), L.ptr(inv_norm), L.ptr(dv), L.ptr(dg), Cd, G, Kt,
-                                       cp, int(accumulate), L.stream_ptr()), "fhb_posconv_wn_bwd")
+                                       cp, int(accumulate), delta, L.stream_ptr()), "fhb_posconv_wn_bwd")
 
 
 def _drop(drop):

@@ -54,6 +54,7 @@ class Conv0Args(C.Structure):
         ("out", C.c_void_p), ("dy", C.c_void_p), ("acc", C.c_void_p),
         ("dweight", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("accumulate", C.c_int32),
+        ("gp_out", C.c_void_p), ("dy_is_dz", C.c_int32),
     ]
 
 

@@ -115,6 +115,9 @@ typedef struct {
   float* dgamma;          /* bwd: [C]                                                          */
   float* dbeta;           /* bwd: [C]                                                          */
   int32_t accumulate;     /* bwd: add into dweight/dgamma/dbeta instead of overwriting         */
+  void* gp_out;           /* fwd, optional: bf16 [B][T0][C] gelu'(GroupNorm output), the backward multiplier */
+  int32_t dy_is_dz;       /* bwd: dy was already multiplied by gp_out (e.g. FHB_EPI_MUL_AUX of the next
+                             layer's dgrad GEMM): no conv / GroupNorm / gelu' recompute                */
 } fhb_conv0_args;
 int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* args, fhb_stream_t stream);
 int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* args, fhb_stream_t stream);
@@ -138,27 +141,34 @@ int fhb_layernorm_bwd(const void* dy, const void* dy2 /* optional: gradient = dy
  *           index_put at :273-274; cp = cg rounded up to 16; borders and channel padding zero)
  *  wn_prep: w = g * v / ||v||_(0,1) (weight_norm dim=2, :199) -> bf16 [G][cp_out][k*cp_in]
  *  finish:  h = xz + gelu(conv[..][:cg]) ; y = LN(h)  (SamePad + GELU + residual :276-278, LN :280-281)
- * and their backward counterparts. */
+ * and their backward counterparts.
+ * Time blocking: with delta > 1 one GEMM row produces delta consecutive frames (N = delta * cp instead of a
+ * 30-48 column sliver): wn_prep then writes delta shifted weight copies W'[g][(dl, n)][(j + dl, k)] over K + delta
+ * taps into a buffer the caller zeroed once, and the GEMM output / dgrad output is laid out
+ * [b][ceil(T / delta)][g][delta][cp] (what finish_fwd / finish_bwd / unpack_bwd index when given delta). */
 int fhb_posconv_pack(const void* x, const int32_t* valid, void* xg, int32_t B, int32_t T, int32_t C, int32_t G,
                      int32_t cp, int32_t pad_l, int32_t Tp, fhb_stream_t stream);
 int fhb_posconv_wn_prep(const float* v, const float* g, void* w_out, float* inv_norm, int32_t C, int32_t G,
-                        int32_t K, int32_t cp, int32_t flip_transpose, fhb_stream_t stream);
+                        int32_t K, int32_t cp, int32_t flip_transpose, int32_t delta, fhb_stream_t stream);
 int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const void* conv, const float* bias,
                            const float* gamma, const float* beta, void* h_out, void* y, float* mean, float* rstd,
-                           int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps, fhb_stream_t stream);
+                           int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps, int32_t delta,
+                           fhb_stream_t stream);
 /* dh = LN-bwd(dy) and dcg[b][g][t+pad_l][cp] = dh * gelu'(conv + bias) (group-major, time-padded: the
  * A operand of the dgrad GEMM and the B operand of the wgrad GEMM) in one pass; dgamma/dbeta/dbias are
  * ACCUMULATED atomically. */
 int fhb_posconv_finish_bwd(const void* dy, const void* h, const void* conv, const float* bias, const float* gamma,
                            const float* mean, const float* rstd, void* dh, void* dcg, float* dgamma, float* dbeta,
                            float* dbias, int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, int32_t pad_l,
-                           int32_t Tp, fhb_stream_t stream);
+                           int32_t Tp, int32_t delta, fhb_stream_t stream);
 /* dx[b][t][c] = (t < valid[b]) ? dh[b][t][c] + dxc[b][t][g][c'] : 0   (dxc = dgrad GEMM output) */
 int fhb_posconv_unpack_bwd(const void* dh, const void* dxc, const int32_t* valid, void* dx, int32_t B, int32_t T,
-                           int32_t C, int32_t G, int32_t cp, fhb_stream_t stream);
-/* dv, dg from dwt (fp32 [G][K*cp][cp], the wgrad GEMM output: dW[g*cg+co][ci][j] = dwt[g][j*cp+ci][co]) */
+                           int32_t C, int32_t G, int32_t cp, int32_t delta, fhb_stream_t stream);
+/* dv, dg from dwt (fp32 [G][K*cp][cp], the wgrad GEMM output: dW[g*cg+co][ci][j] = dwt[g][j*cp+ci][co]).
+ * delta > 1: dwt is the time-blocked wgrad output [G][(K+delta)*cp][delta*cp] and
+ * dW[g*cg+co][ci][j] = sum_dl dwt[g][(j+dl)*cp+ci][dl*cp+co]. */
 int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, const float* inv_norm, float* dv,
-                       float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate,
+                       float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate, int32_t delta,
                        fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ masked attention (K7)

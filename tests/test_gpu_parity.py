@@ -154,6 +154,18 @@ def test_conv0_groupnorm_gelu_fwd_bwd(F):
     dw, dg, db = torch.zeros(C, 10, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     K.conv0_bwd(x, w.detach(), g.detach(), b.detach(), T0, stat, mean, rstd, dy, acc, dw, dg, db, accumulate=False)
     assert rel(dw, w.grad.view(C, 10)) < 1e-2 and rel(dg, g.grad) < 1e-2 and rel(db, b.grad) < 1e-2
+    # training path: the forward also saves gelu'(GroupNorm output); the backward then consumes dz = dy * gelu'
+    gp, out2 = torch.empty_like(out), torch.empty_like(out)
+    K.conv0_fwd(x, w.detach(), g.detach(), b.detach(), T0, stat, mean, rstd, out2, gp_out=gp)
+    z = Fn.group_norm(Fn.conv1d(x.unsqueeze(1), w.detach(), stride=5), C, g.detach(), b.detach(), 1e-5).transpose(1, 2)
+    zr = z.clone().requires_grad_(True)
+    Fn.gelu(zr).sum().backward()
+    assert torch.equal(out2, out) and rel(gp, zr.grad) < 1e-2
+    dz = (dy.float() * gp.float()).bfloat16()
+    dw2, dg2, db2 = torch.zeros(C, 10, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    K.conv0_bwd(x, w.detach(), g.detach(), b.detach(), T0, stat, mean, rstd, dz, acc, dw2, dg2, db2, accumulate=False,
+                dy_is_dz=True)
+    assert rel(dw2, w.grad.view(C, 10)) < 1.5e-2 and rel(dg2, g.grad) < 1.5e-2 and rel(db2, b.grad) < 1.5e-2
 
 
 @pytest.mark.parametrize("d,T,amp,short", [(40, 389, 1.0, 37), (64, 779, 1.0, 37), (24, 50, 1.0, 37), (16, 13, 1.0, 37),
