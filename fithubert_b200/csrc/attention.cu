@@ -234,6 +234,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ v
 // ------------------------------------------------------------------ backward
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                   float* __restrict__ delta, int B, int T, int H, int d) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, t, h)
   if (idx >= (long long)B * T * H) return;
   const int h = idx % H;
@@ -505,8 +506,8 @@ extern "C" int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* o
   FHB_ARG_CHECK(qkv && out && dout && lse && dqkv && delta_ws, "attn_bwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n = (long long)B * T * H;
-  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(out),
-                                                                static_cast<const __nv_bfloat16*>(dout), delta_ws, B, T, H, d);
+  FHB_CUDA_CHECK(fhb_launch(attn_delta_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(out),
+                                                                static_cast<const __nv_bfloat16*>(dout), delta_ws, B, T, H, d));
   FHB_LAUNCH_CHECK();
   static const bool no_tc = getenv("FHB_ATTN_NO_TC") != nullptr;
   if ((d == 64 || d == 40) && dq_ws && !no_tc)

@@ -81,6 +81,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int k0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
   const int HDall = H * HD;
   const long long ld = 3LL * HDall;
+  pdl_sync();  // before the first global read (valid[]) and before the early exit below
   int nvalid = valid ? valid[b] : T;
   nvalid = max(1, min(nvalid, T));
   const int nq = (T + kT - 1) / kT;
@@ -352,6 +353,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 // dqkv[row][0:E] = bf16(dq_acc[row][0:E])
 __global__ void __launch_bounds__(256)
 dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int E8, long long ld) {
+  pdl_sync();
   const long long total = rows * E8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / E8;
@@ -391,17 +393,17 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
   }
   dim3 grid((T + kT - 1) / kT, H, B);
   if (drop_p > 0.f)
-    attn_bwd_tc_kernel<HD, true><<<grid, kCT + 32, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
+    FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, true>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
                                                              H, scale, drop_seed, fhb_dropout_thr16(drop_p),
-                                                             fhb_dropout_scale(drop_p));
+                                                             fhb_dropout_scale(drop_p)));
   else
-    attn_bwd_tc_kernel<HD, false><<<grid, kCT + 32, S::kTotal, s>>>(tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
-                                                              T, H, scale, 0u, 0u, 1.f);
+    FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, false>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
+                                                              T, H, scale, 0u, 0u, 1.f));
   FHB_LAUNCH_CHECK();
   const long long rows = (long long)B * T;
   long long blocks = (rows * (E / 8) + 255) / 256;
   if (blocks > 8LL * fhb_num_sms()) blocks = 8LL * fhb_num_sms();
-  dq_convert_kernel<<<(unsigned)blocks, 256, 0, s>>>(dq_ws, static_cast<__nv_bfloat16*>(dqkv), rows, (int)(E / 8), 3 * E);
+  FHB_CUDA_CHECK(fhb_launch(dq_convert_kernel, dim3((unsigned)blocks), dim3(256), 0, s, dq_ws, static_cast<__nv_bfloat16*>(dqkv), rows, (int)(E / 8), 3 * E));
   FHB_LAUNCH_CHECK();
   return 0;
 }

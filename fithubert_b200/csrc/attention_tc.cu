@@ -79,9 +79,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTQ, h = blockIdx.y, b = blockIdx.z;
-  int nvalid = valid ? valid[b] : T;
-  nvalid = max(1, min(nvalid, T));
-  const int nt = (nvalid + kTK - 1) / kTK;
 
   if (warp == 8 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -105,6 +102,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;        // 128 fp32 columns
   const uint32_t tmem_o = tmem_base + 128;  // DK fp32 columns
+  pdl_sync();  // the prologue above overlapped the previous kernel's tail; global memory only from here on
+  int nvalid = valid ? valid[b] : T;
+  nvalid = max(1, min(nvalid, T));
+  const int nt = (nvalid + kTK - 1) / kTK;
 
   if (warp == 8) {
     if (elect_one()) {
@@ -337,11 +338,11 @@ int launch_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int
   }
   dim3 grid((T + kTQ - 1) / kTQ, H, B);
   if (drop_p > 0.f)
-    attn_fwd_tc_kernel<HD, true><<<grid, 288, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale,
-                                                          drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p));
+    FHB_CUDA_CHECK(fhb_launch((attn_fwd_tc_kernel<HD, true>), dim3(grid), dim3(288), kSmem, s, tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale,
+                                                          drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p)));
   else
-    attn_fwd_tc_kernel<HD, false><<<grid, 288, kSmem, s>>>(tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale, 0u,
-                                                           0u, 1.f);
+    FHB_CUDA_CHECK(fhb_launch((attn_fwd_tc_kernel<HD, false>), dim3(grid), dim3(288), kSmem, s, tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale, 0u,
+                                                           0u, 1.f));
   FHB_LAUNCH_CHECK();
   return 0;
 }

@@ -19,6 +19,7 @@ constexpr int kNStat = kK + kNR;   // 65
 // ---------------------------------------------------------------- pass 1: S_j and R_jj'
 __global__ void __launch_bounds__(256) conv0_stats_kernel(const float* __restrict__ wave, long long ld, int T0,
                                                           int frames_per_block, double* __restrict__ stat) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * frames_per_block;
   const int t_end = min(t_begin + frames_per_block, T0);
@@ -67,6 +68,7 @@ __device__ __forceinline__ double quad_form(const float* w, const double* R) {
 
 __global__ void conv0_finalize_stats_kernel(const double* __restrict__ stat, const float* __restrict__ weight, int C,
                                             int T0, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -91,6 +93,7 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
                  const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ gp_out) {
+  pdl_sync();
   extern __shared__ float xs[];  // frames_per_block*5 + 5 samples
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * frames_per_block;
@@ -153,6 +156,7 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
                  const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dy,
                  float* __restrict__ acc_out /*[B][C][12]*/, int dy_is_dz) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * frames_per_block;
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(256)
 conv0_bwd_dz_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
                     const float* __restrict__ weight, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const __nv_bfloat16* __restrict__ dz, float* __restrict__ acc_out /*[B][C][12]*/) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * frames_per_block;
@@ -307,6 +312,7 @@ __global__ void conv0_bwd_finalize_kernel(const float* __restrict__ acc, const d
                                           const float* __restrict__ mean, const float* __restrict__ rstd, int B, int C,
                                           int T0, float* __restrict__ dW, float* __restrict__ dgamma,
                                           float* __restrict__ dbeta, int accumulate) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float w[kK];
@@ -361,12 +367,12 @@ extern "C" int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* a, fhb_stream_t strea
   {
     const int fpb = 2048;
     dim3 grid((a->T0 + fpb - 1) / fpb, a->B);
-    conv0_stats_kernel<<<grid, 256, 0, s>>>(a->wave, a->wave_ld, a->T0, fpb, a->stat);
+    FHB_CUDA_CHECK(fhb_launch(conv0_stats_kernel, dim3(grid), dim3(256), 0, s, a->wave, a->wave_ld, a->T0, fpb, a->stat));
     FHB_LAUNCH_CHECK();
   }
   {
     dim3 grid((a->C + 127) / 128, a->B);
-    conv0_finalize_stats_kernel<<<grid, 128, 0, s>>>(a->stat, a->weight, a->C, a->T0, a->eps, a->mean, a->rstd);
+    FHB_CUDA_CHECK(fhb_launch(conv0_finalize_stats_kernel, dim3(grid), dim3(128), 0, s, a->stat, a->weight, a->C, a->T0, a->eps, a->mean, a->rstd));
     FHB_LAUNCH_CHECK();
   }
   {
@@ -375,9 +381,9 @@ extern "C" int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* a, fhb_stream_t strea
     const int frames = 512;
     dim3 grid((a->T0 + frames - 1) / frames, a->B);
     const size_t smem = sizeof(float) * (frames * kS + (kK - kS));
-    conv0_fwd_kernel<8><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
+    FHB_CUDA_CHECK(fhb_launch((conv0_fwd_kernel<8>), dim3(grid), dim3(256), smem, s, a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
                                                  a->mean, a->rstd, static_cast<__nv_bfloat16*>(a->out),
-                                                 static_cast<__nv_bfloat16*>(a->gp_out));
+                                                 static_cast<__nv_bfloat16*>(a->gp_out)));
     FHB_LAUNCH_CHECK();
   }
   return 0;
@@ -394,12 +400,12 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
     const int frames = 1024;
     dim3 grid((a->T0 + frames - 1) / frames, a->B);
     const size_t smem = sizeof(float) * (frames * kS + (kK - kS) + a->C * kNAcc);
-    conv0_bwd_dz_kernel<4><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->mean, a->rstd,
-                                                   static_cast<const __nv_bfloat16*>(a->dy), a->acc);
+    FHB_CUDA_CHECK(fhb_launch((conv0_bwd_dz_kernel<4>), dim3(grid), dim3(256), smem, s, a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->mean, a->rstd,
+                                                   static_cast<const __nv_bfloat16*>(a->dy), a->acc));
     FHB_LAUNCH_CHECK();
-    conv0_bwd_finalize_kernel<<<(a->C + 63) / 64, 64, 0, s>>>(a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
+    FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize_kernel, dim3((a->C + 63) / 64), dim3(64), 0, s, a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
                                                              a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
-                                                             a->accumulate);
+                                                             a->accumulate));
     FHB_LAUNCH_CHECK();
     return 0;
   }
@@ -407,13 +413,13 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
   const int frames = 2048;
   dim3 grid((a->T0 + frames - 1) / frames, a->B);
   const size_t smem = sizeof(float) * (frames * kS + (kK - kS) + a->C * kNAcc);
-  conv0_bwd_kernel<4><<<grid, 256, smem, s>>>(a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
+  FHB_CUDA_CHECK(fhb_launch((conv0_bwd_kernel<4>), dim3(grid), dim3(256), smem, s, a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->gamma, a->beta,
                                               a->mean, a->rstd, static_cast<const __nv_bfloat16*>(a->dy), a->acc,
-                                              a->dy_is_dz);
+                                              a->dy_is_dz));
   FHB_LAUNCH_CHECK();
-  conv0_bwd_finalize_kernel<<<(a->C + 63) / 64, 64, 0, s>>>(a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
+  FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize_kernel, dim3((a->C + 63) / 64), dim3(64), 0, s, a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
                                                            a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
-                                                           a->accumulate);
+                                                           a->accumulate));
   FHB_LAUNCH_CHECK();
   return 0;
 }

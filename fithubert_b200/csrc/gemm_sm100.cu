@@ -135,6 +135,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
@@ -682,7 +683,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
     attr_set = true;
   }
   const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
-  fhb_gemm_kernel<A_MN, B_MN, EPI_IN><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, tx, ti, p);
+  FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
   FHB_LAUNCH_CHECK();
   return 0;
 }

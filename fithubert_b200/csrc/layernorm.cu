@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -89,6 +90,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
                      __nv_bfloat16* __restrict__ dx_drop, uint32_t drop_seed, uint32_t drop_thr, float drop_scale,
                      long long rows, int C) {
+  pdl_sync();
   extern __shared__ float sred[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
@@ -208,8 +210,8 @@ extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float*
                 C, kMaxVec * 256);
   FHB_ARG_CHECK((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
   if (rows == 0) return 0;
-  layernorm_fwd_kernel<<<ln_grid(rows, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps);
+  FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel, dim3(ln_grid(rows, 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -229,11 +231,11 @@ extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x,
   const size_t sm = 3 * C * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define FHB_LN_BWD(NV, DX)                                                                                          \
-  layernorm_bwd_kernel<NV, DX><<<(unsigned)blocks, 256, sm, s>>>(                                                   \
+  FHB_CUDA_CHECK(fhb_launch((layernorm_bwd_kernel<NV, DX>), dim3((unsigned)blocks), dim3(256), sm, s,                                                    \
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dy2),                               \
       static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,                                                      \
       static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum,              \
-      static_cast<__nv_bfloat16*>(dx_drop), drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p), rows, C)
+      static_cast<__nv_bfloat16*>(dx_drop), drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p), rows, C))
   if (dxsum) {
     if (nv == 1) FHB_LN_BWD(1, true); else if (nv == 2) FHB_LN_BWD(2, true); else FHB_LN_BWD(3, true);
   } else {

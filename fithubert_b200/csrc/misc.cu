@@ -15,6 +15,7 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
                     const float* __restrict__ weights, float* __restrict__ layer_loss, __nv_bfloat16* __restrict__ dpred,
                     float* __restrict__ dbias, long long dbias_stride, int B, int Tp, int Tt, int D, int loss_type,
                     float grad_scale) {
+  pdl_sync();
   extern __shared__ float csum[];  // [D] (only when dbias)
   const int l = blockIdx.y;
   const float w = weights[l];
@@ -89,6 +90,7 @@ struct AdamScalars {
 
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const fhb_adamw_tensor* __restrict__ table, AdamScalars s) {
+  pdl_sync();
   const fhb_adamw_tensor e = table[blockIdx.y];
   if (e.g == nullptr) return;
   const long long d1 = e.dim[1], d2 = e.dim[2];
@@ -117,6 +119,7 @@ adamw_multi_kernel(const fhb_adamw_tensor* __restrict__ table, AdamScalars s) {
 // ------------------------------------------------------------------ weight preparation
 // dst (bf16 or fp32, contiguous [d0][d1][d2]) = src_fp32[i0*s0 + i1*s1 + i2*s2]
 __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* __restrict__ table) {
+  pdl_sync();
   const fhb_prep_tensor e = table[blockIdx.y];
   const long long d1 = e.dim[1], d2 = e.dim[2];
   const long long n = e.dim[0] * d1 * d2;
@@ -132,59 +135,87 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* 
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients)
-// Warp per row (lanes stride over 16-byte column vectors: 512 contiguous bytes per warp load), rows dealt
-// round-robin to all warps of the grid; per-lane partial sums -> block smem -> one atomic per column/block.
-constexpr int kColsumMaxVec = 8;  // C <= 8 * 32 * 8 = 2048
+// Block = (64-column slice, row chunk): 256 threads = 32 row lanes x 8 sixteen-byte column chunks, so a warp
+// load covers 4 rows x 128 contiguous bytes and a thread carries only 8 accumulators (deep unrolling, many
+// loads in flight).  Row lanes are folded through shared memory; one atomic per column per block, and only
+// `row chunks` blocks ever hit the same address (a flat row-striped grid made every block hit every column).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out,
-              long long x_bstride, long long out_bstride) {
-  extern __shared__ float csum[];  // [C]
-  x += (long long)blockIdx.y * x_bstride;
-  out += (long long)blockIdx.y * out_bstride;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) csum[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int nvec = C >> 3;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  float acc[kColsumMaxVec][8];
+              long long x_bstride, long long out_bstride, int rows_per_chunk) {
+  pdl_sync();
+  __shared__ float red[32][65];
+  x += (long long)blockIdx.z * x_bstride;
+  out += (long long)blockIdx.z * out_bstride;
+  const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col = blockIdx.x * 64 + cl * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < C) {
+    const __nv_bfloat16* xp = x + col;
+#pragma unroll 8
+    for (long long r = r0 + rl; r < r1; r += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xp + r * ld));
+      const uint32_t a[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int i = 0; i < kColsumMaxVec; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (long long r = warp_global; r < rows; r += nwarps) {
-    const __nv_bfloat16* xr = x + r * ld;
-#pragma unroll
-    for (int i = 0; i < kColsumMaxVec; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + vi * 8));
-        const uint32_t a[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16(a[j]);
-          acc[i][2 * j] += f.x;
-          acc[i][2 * j + 1] += f.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(a[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < kColsumMaxVec; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
+  for (int j = 0; j < 8; ++j) red[rl][cl * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
+    float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&csum[vi * 8 + j], acc[i][j]);
-    }
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    atomicAdd(out + blockIdx.x * 64 + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------ projection-head bias gradients
+// dz = dpred @ Wlin has no bias term, so the column sums of dz (the gradient of the ConvTranspose1d bias) follow
+// from the column sums of dpred the loss kernel already produced:  colsum(dz)[e] = sum_d colsum(dpred)[d] Wlin[d][e]
+// - a [1 x D] x [D x E] product per head instead of another pass over the n x B x T' x E tensor dz.
+// grid (D / 64, heads), block = E / 2 threads (two columns each); also folds colsum(dpred) into the lin_proj bias
+// gradient (each element owned by exactly one block).
+__global__ void __launch_bounds__(512)
+head_bias_grads_kernel(const float* __restrict__ cs, long long cs_stride, const __nv_bfloat16* __restrict__ wlin,
+                       long long wlin_stride, float* __restrict__ dlin_bias, float* __restrict__ dup_bias,
+                       long long grad_stride, int D, int E) {
+  pdl_sync();
+  __shared__ float cs_s[64];
+  const int h = blockIdx.y, d0 = blockIdx.x * 64;
+  const int nd = min(64, D - d0);
+  const float* csh = cs + (long long)h * cs_stride + d0;
+  if ((int)threadIdx.x < nd) {
+    const float v = csh[threadIdx.x];
+    cs_s[threadIdx.x] = v;
+    if (dlin_bias) dlin_bias[(long long)h * grad_stride + d0 + threadIdx.x] += v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, csum[i]);
+  const int e = threadIdx.x * 2;
+  if (e >= E) return;
+  const __nv_bfloat16* w = wlin + (long long)h * wlin_stride + (long long)d0 * E + e;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll 16
+  for (int d = 0; d < nd; ++d) {
+    const float2 f = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(w + (long long)d * E)));
+    a0 = fmaf(cs_s[d], f.x, a0);
+    a1 = fmaf(cs_s[d], f.y, a1);
+  }
+  float* o = dup_bias + (long long)h * grad_stride + e;
+  atomicAdd(o, a0);
+  atomicAdd(o + 1, a1);
 }
 
 __global__ void __launch_bounds__(256)
 add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y,
                 long long nvec) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 ua = reinterpret_cast<const uint4*>(a)[i], ub = reinterpret_cast<const uint4*>(b)[i];
     const uint32_t aa[4] = {ua.x, ua.y, ua.z, ua.w}, bb[4] = {ub.x, ub.y, ub.z, ub.w};
@@ -202,6 +233,7 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 mul_dgelu_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, const __nv_bfloat16* __restrict__ u, long long u_bs,
                  __nv_bfloat16* __restrict__ out, long long out_bs, long long nvec) {
+  pdl_sync();
   const int b = blockIdx.y;
   const uint4* d4 = reinterpret_cast<const uint4*>(dy + b * dy_bs);
   const uint4* u4 = reinterpret_cast<const uint4*>(u + b * u_bs);
@@ -223,6 +255,7 @@ mul_dgelu_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, const __
 __global__ void __launch_bounds__(256)
 mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_bfloat16* __restrict__ m, long long m_bs,
                 __nv_bfloat16* __restrict__ out, long long out_bs, long long nvec) {
+  pdl_sync();
   const int b = blockIdx.y;
   const uint4* a4 = reinterpret_cast<const uint4*>(a + b * a_bs);
   const uint4* m4 = reinterpret_cast<const uint4*>(m + b * m_bs);
@@ -243,6 +276,7 @@ mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_
 __global__ void __launch_bounds__(256)
 dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long nvec, uint32_t seed,
                uint32_t thr, float scale) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 a = reinterpret_cast<const uint4*>(x)[i];
     const uint32_t aa[4] = {a.x, a.y, a.z, a.w};
@@ -260,6 +294,7 @@ dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
 
 // lengths[b] = number of zero bytes in mask[b][0..L)   (mask: 1 = padding)
 __global__ void __launch_bounds__(256) mask_lengths_kernel(const uint8_t* __restrict__ mask, long long L, int* __restrict__ lengths) {
+  pdl_sync();
   const uint8_t* row = mask + (long long)blockIdx.x * L;
   int cnt = 0;
   for (long long i = threadIdx.x; i < L; i += blockDim.x) cnt += row[i] ? 0 : 1;
@@ -301,9 +336,9 @@ extern "C" int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const
   while (a) { const long long t2 = g % a; g = a; a = t2; }  // g = gcd(vpr, 256)
   const int unit = (int)(vpr / g);
   gx = (gx + unit - 1) / unit * unit;
-  distill_loss_kernel<<<dim3(gx, n_layers), 256, dbias ? D * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(distill_loss_kernel, dim3(dim3(gx, n_layers)), dim3(256), dbias ? D * sizeof(float) : 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(tgt), weights, layer_loss,
-      static_cast<__nv_bfloat16*>(dpred), dbias, dbias_layer_stride, B, Tp, Tt, D, loss_type, grad_scale);
+      static_cast<__nv_bfloat16*>(dpred), dbias, dbias_layer_stride, B, Tp, Tt, D, loss_type, grad_scale));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -320,7 +355,7 @@ extern "C" int fhb_adamw_multi(const fhb_adamw_tensor* table_dev, int32_t n_tens
   s.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   int gx = grid_x(max_n, 2);
   if (gx > 64) gx = 64;
-  adamw_multi_kernel<<<dim3(gx, n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, s);
+  FHB_CUDA_CHECK(fhb_launch(adamw_multi_kernel, dim3(dim3(gx, n_tensors)), dim3(256), 0, static_cast<cudaStream_t>(stream), table_dev, s));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -329,23 +364,28 @@ extern "C" int fhb_prep_multi(const fhb_prep_tensor* table_dev, int32_t n_tensor
   FHB_ARG_CHECK(table_dev && n_tensors > 0 && max_n > 0, "prep_multi: empty table");
   int gx = grid_x(max_n, 2);
   if (gx > 64) gx = 64;
-  prep_multi_kernel<<<dim3(gx, n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev);
+  FHB_CUDA_CHECK(fhb_launch(prep_multi_kernel, dim3(dim3(gx, n_tensors)), dim3(256), 0, static_cast<cudaStream_t>(stream), table_dev));
   FHB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int fhb_colsum_batched(const void* x, int64_t rows, int32_t C, int64_t ld, int64_t x_bstride, float* out,
                                   int64_t out_bstride, int32_t batches, fhb_stream_t stream) {
-  FHB_ARG_CHECK(x && out && C % 8 == 0 && ld % 8 == 0 && C <= kColsumMaxVec * 256 && batches > 0 && x_bstride % 8 == 0,
+  FHB_ARG_CHECK(x && out && C > 0 && C % 8 == 0 && ld % 8 == 0 && batches > 0 && x_bstride % 8 == 0,
                 "colsum: bad arguments (C=%d)", C);
   if (rows == 0) return 0;
-  long long blocks = (rows + 8 * 8 - 1) / (8 * 8);  // >= 8 rows per warp
-  const long long cap = (2LL * fhb_num_sms() + batches - 1) / batches;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  colsum_kernel<<<dim3((unsigned)blocks, batches), 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), rows, C, ld, out, x_bstride, out_bstride);
-  FHB_LAUNCH_CHECK();
+  const int slices = (C + 63) / 64;
+  // about 4 blocks per SM in total, at least 64 rows (2 per row lane) per chunk
+  long long chunks = (4LL * fhb_num_sms() + (long long)slices * batches - 1) / ((long long)slices * batches);
+  const long long max_chunks = (rows + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  const int rpc = (int)((rows + chunks - 1) / chunks);
+  chunks = (rows + rpc - 1) / rpc;
+  FHB_CUDA_CHECK(fhb_launch(colsum_kernel, dim3(slices, (unsigned)chunks, batches), dim3(256), 0,
+                            static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), rows, C, ld, out,
+                            x_bstride, out_bstride, rpc));
   return 0;
 }
 
@@ -353,11 +393,23 @@ extern "C" int fhb_colsum(const void* x, int64_t rows, int32_t C, int64_t ld, fl
   return fhb_colsum_batched(x, rows, C, ld, 0, out, 0, 1, stream);
 }
 
+extern "C" int fhb_head_bias_grads(const float* colsum_dpred, int64_t cs_stride, const void* wlin, int64_t wlin_stride,
+                                   float* dlin_bias, float* dup_bias, int64_t grad_stride, int32_t n_heads, int32_t D,
+                                   int32_t E, fhb_stream_t stream) {
+  FHB_ARG_CHECK(colsum_dpred && wlin && dup_bias && n_heads > 0 && D > 0, "head_bias_grads: bad arguments");
+  FHB_ARG_CHECK(E > 0 && E % 2 == 0 && E <= 1024, "head_bias_grads: E=%d must be even and <= 1024", E);
+  FHB_CUDA_CHECK(fhb_launch(head_bias_grads_kernel, dim3((D + 63) / 64, n_heads), dim3((E / 2 + 31) / 32 * 32 < 64 ? 64 : (E / 2 + 31) / 32 * 32), 0,
+                            static_cast<cudaStream_t>(stream), colsum_dpred, (long long)cs_stride,
+                            static_cast<const __nv_bfloat16*>(wlin), (long long)wlin_stride, dlin_bias, dup_bias,
+                            (long long)grad_stride, D, E));
+  return 0;
+}
+
 extern "C" int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t stream) {
   FHB_ARG_CHECK(a && b && y && n % 8 == 0, "add_bf16: n must be a multiple of 8");
   if (n == 0) return 0;
-  add_bf16_kernel<<<grid_x(n / 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), n / 8);
+  FHB_CUDA_CHECK(fhb_launch(add_bf16_kernel, dim3(grid_x(n / 8, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), n / 8));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -370,9 +422,9 @@ extern "C" int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, 
   if (n == 0) return 0;
   int gx = grid_x(n / 8, 8);
   gx = (gx + B - 1) / B;
-  mul_dgelu_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(mul_dgelu_kernel, dim3(dim3(gx < 1 ? 1 : gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), dy_bstride, static_cast<const __nv_bfloat16*>(u), u_bstride,
-      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8);
+      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -385,9 +437,9 @@ extern "C" int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int
   if (n == 0) return 0;
   int gx = grid_x(n / 8, 8);
   gx = (gx + B - 1) / B;
-  mul_bf16_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(mul_bf16_kernel, dim3(dim3(gx < 1 ? 1 : gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(a), a_bstride, static_cast<const __nv_bfloat16*>(m), m_bstride,
-      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8);
+      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -396,9 +448,9 @@ extern "C" int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, flo
   FHB_ARG_CHECK(x && y && n % 8 == 0 && n < (1LL << 32), "dropout: n must be a multiple of 8 and < 2^32");
   FHB_ARG_CHECK(p >= 0.f && p < 1.f, "dropout: p=%f must be in [0, 1)", (double)p);
   if (n == 0) return 0;
-  dropout_kernel<<<grid_x(n / 8, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(dropout_kernel, dim3(grid_x(n / 8, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n / 8, seed, fhb_dropout_thr16(p),
-      fhb_dropout_scale(p));
+      fhb_dropout_scale(p)));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -413,7 +465,7 @@ extern "C" int fhb_memset2d(void* ptr, int64_t pitch_bytes, int64_t width_bytes,
 
 extern "C" int fhb_mask_lengths(const uint8_t* mask, int32_t B, int64_t L, int32_t* lengths, fhb_stream_t stream) {
   FHB_ARG_CHECK(mask && lengths && B > 0 && L > 0, "mask_lengths: bad arguments");
-  mask_lengths_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, L, lengths);
+  FHB_CUDA_CHECK(fhb_launch(mask_lengths_kernel, dim3(B), dim3(256), 0, static_cast<cudaStream_t>(stream), mask, L, lengths));
   FHB_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 posconv_pack_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ valid, __nv_bfloat16* __restrict__ xg,
                     int T, int C, int G, int cp, int pad_l, int Tp, long long total) {
+  pdl_sync();
   const int cg = C / G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % cp;
@@ -36,6 +37,7 @@ posconv_pack_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__
 __global__ void __launch_bounds__(256)
 posconv_wn_prep_kernel(const float* __restrict__ v, const float* __restrict__ gain, __nv_bfloat16* __restrict__ w_out,
                        float* __restrict__ inv_norm, int C, int G, int K, int cp, int flip_transpose, int delta) {
+  pdl_sync();
   const int j = blockIdx.x;
   const int cg = C / G;
   const int n = C * cg;
@@ -75,6 +77,7 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                           float* __restrict__ rstd_out, int B, int T, int C, int G, int cp, float eps, int delta) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * T) return;
@@ -132,6 +135,7 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
                           __nv_bfloat16* __restrict__ dcg, float* __restrict__ dgamma, float* __restrict__ dbeta,
                           float* __restrict__ dbias, int B, int T, int C, int G, int cp, int pad_l, int Tp,
                           int rows_per_warp, int delta) {
+  pdl_sync();
   extern __shared__ float sred[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(256)
 posconv_unpack_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ dxc,
                           const int* __restrict__ valid, __nv_bfloat16* __restrict__ dx, int T, int C, int G, int cp,
                           long long total, int delta) {
+  pdl_sync();
   const int cg = C / G;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % C;
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__(256)
 posconv_wn_bwd_kernel(const float* __restrict__ dwt, const float* __restrict__ v, const float* __restrict__ gain,
                       const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg, int C, int G,
                       int K, int cp, int accumulate, int delta) {
+  pdl_sync();
   const int j = blockIdx.x;
   const int cg = C / G;
   const int n = C * cg;
@@ -282,8 +288,8 @@ extern "C" int fhb_posconv_pack(const void* x, const int32_t* valid, void* xg, i
   FHB_ARG_CHECK(x && xg, "posconv_pack: null pointer");
   FHB_ARG_CHECK(C % G == 0 && cp >= C / G && cp % 16 == 0 && Tp >= T + pad_l, "posconv_pack: bad geometry");
   const long long total = (long long)B * G * Tp * cp;
-  posconv_pack_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), valid, static_cast<__nv_bfloat16*>(xg), T, C, G, cp, pad_l, Tp, total);
+  FHB_CUDA_CHECK(fhb_launch(posconv_pack_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(x), valid, static_cast<__nv_bfloat16*>(xg), T, C, G, cp, pad_l, Tp, total));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -292,8 +298,8 @@ extern "C" int fhb_posconv_wn_prep(const float* v, const float* g, void* w_out, 
                                    int32_t K, int32_t cp, int32_t flip_transpose, int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(v && g && w_out, "posconv_wn_prep: null pointer");
   FHB_ARG_CHECK(C % G == 0 && cp >= C / G && delta >= 1, "posconv_wn_prep: bad geometry");
-  posconv_wn_prep_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, static_cast<__nv_bfloat16*>(w_out),
-                                                                         inv_norm, C, G, K, cp, flip_transpose, delta);
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_prep_kernel, dim3(K), dim3(256), 0, static_cast<cudaStream_t>(stream), v, g, static_cast<__nv_bfloat16*>(w_out),
+                                                                         inv_norm, C, G, K, cp, flip_transpose, delta));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -305,9 +311,9 @@ extern "C" int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const
   FHB_ARG_CHECK(x && conv && bias && gamma && beta && y && delta >= 1, "posconv_finish_fwd: null pointer");
   FHB_ARG_CHECK(C <= 768 && C % G == 0, "posconv_finish_fwd: C=%d must be <= 768", C);
   const long long rows = (long long)B * T;
-  posconv_finish_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(posconv_finish_fwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), valid, static_cast<const __nv_bfloat16*>(conv), bias, gamma, beta,
-      static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta);
+      static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -323,10 +329,10 @@ extern "C" int fhb_posconv_finish_bwd(const void* dy, const void* h, const void*
   const long long rows = (long long)B * T;
   const int rpw = 4;
   const long long warps = (rows + rpw - 1) / rpw;
-  posconv_finish_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(posconv_finish_bwd_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 3 * C * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(conv),
       bias, gamma, mean, rstd, static_cast<__nv_bfloat16*>(dh), static_cast<__nv_bfloat16*>(dcg), dgamma, dbeta, dbias, B,
-      T, C, G, cp, pad_l, Tp, rpw, delta);
+      T, C, G, cp, pad_l, Tp, rpw, delta));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -335,9 +341,9 @@ extern "C" int fhb_posconv_unpack_bwd(const void* dh, const void* dxc, const int
                                       int32_t T, int32_t C, int32_t G, int32_t cp, int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(dh && dxc && dx && delta >= 1, "posconv_unpack_bwd: null pointer");
   const long long total = (long long)B * T * C;
-  posconv_unpack_bwd_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FHB_CUDA_CHECK(fhb_launch(posconv_unpack_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dh), static_cast<const __nv_bfloat16*>(dxc), valid,
-      static_cast<__nv_bfloat16*>(dx), T, C, G, cp, total, delta);
+      static_cast<__nv_bfloat16*>(dx), T, C, G, cp, total, delta));
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -346,8 +352,8 @@ extern "C" int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float*
                                   float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate,
                                   int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(dwt && v && g && inv_norm && dv && dg && delta >= 1, "posconv_wn_bwd: null pointer");
-  posconv_wn_bwd_kernel<<<K, 256, 0, static_cast<cudaStream_t>(stream)>>>(dwt, v, g, inv_norm, dv, dg, C, G, K, cp,
-                                                                        accumulate, delta);
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel, dim3(K), dim3(256), 0, static_cast<cudaStream_t>(stream), dwt, v, g, inv_norm, dv, dg, C, G, K, cp,
+                                                                        accumulate, delta));
   FHB_LAUNCH_CHECK();
   return 0;
 }

@@ -176,12 +176,14 @@ class W2V2Distil(nn.Module):
         c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
         # gradient written in place over the projections (they are not needed again)
-        # the loss kernel also accumulates the lin_proj bias gradients (column sums of the gradient it writes)
-        gs = G.head_stride() if len(c.head_idx) == n else None
+        # the loss kernel also produces the column sums of the gradient it writes: both head bias gradients follow
+        # (batched heads only; the per-head fallback path computes its own column sums)
+        fused = getattr(c, "heads_batched", False) and G.head_stride() is not None
+        dcs = torch.zeros(n, D, device=dev, dtype=torch.float32) if fused else None
         K.distill_loss(c.preds, tgt, self.layer_weights, layer_loss, c.preds, n, B, c.Tq, T, D,
                        0 if self.rec_loss_type == "mse" else 1, grad_scale * self.rec_loss_weight,
-                       dbias=None if gs is None else G.from_("proj_head.0.lin_proj.bias"), dbias_layer_stride=gs or 0)
-        E.student_backward(P, W, sm._geom, G, c, c.preds, lin_bias_done=gs is not None)
+                       dbias=dcs, dbias_layer_stride=D if fused else 0)
+        E.student_backward(P, W, sm._geom, G, c, c.preds, dpred_colsum=dcs)
         return layer_loss
 
     def training_step(self, batch, batch_idx=0):

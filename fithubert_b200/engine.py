@@ -583,10 +583,12 @@ def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc:
 
 
 def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torch.Tensor,
-                     dlayers: Optional[List[Optional[torch.Tensor]]] = None, lin_bias_done: bool = False):
+                     dlayers: Optional[List[Optional[torch.Tensor]]] = None,
+                     dpred_colsum: Optional[torch.Tensor] = None):
     """Backward of student_forward(train=True, heads='all').  dpred: [n_layers, B, T', D] bf16 gradient of
     the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer.
-    lin_bias_done: the lin_proj bias gradients (column sums of dpred) were already accumulated by the loss kernel."""
+    dpred_colsum: fp32 [n_layers, D] column sums of dpred over (B, T') if the loss kernel already produced them
+    (batched-heads path only); both head bias gradients are derived from them (fhb_head_bias_grads)."""
     E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
     B, T, Ts, Tq = c.B, c.T, c.Ts, c.Tq
     dev = dpred.device
@@ -599,8 +601,12 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         # ---- all n projection heads at once (ob = head): 2 wgrad + 2 dgrad batched GEMMs, 1-2 column sums
         hs = c.head_strides
         dp3 = dpred.view(n, B * Tq, D)
-        if not lin_bias_done:
-            K.colsum_batched(dp3, G_.from_("proj_head.0.lin_proj.bias"), gs)
+        if dpred_colsum is None:
+            dpred_colsum = torch.zeros(n, D, device=dev, dtype=f32)
+            K.colsum_batched(dp3, dpred_colsum, D)
+        # lin_proj.bias += colsum(dpred); upsampler.bias += colsum(dpred) @ Wlin (= colsum of dz below, never re-read)
+        K.head_bias_grads(dpred_colsum, W["h0.wlin"], hs["wlin"], G_.from_("proj_head.0.lin_proj.bias"),
+                          G_.from_("proj_head.0.upsampler.bias"), gs, n, D, E)
         a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, B * Tq, n), stride=(D, B * Tq * D))
         z3 = L.tensor3(data_ptr=c.z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
         K.gemm_raw(a3, z3, G_.from_("proj_head.0.lin_proj.weight"), D, E, B * Tq, a_major=1, b_major=1, num_ob=n,
@@ -609,7 +615,6 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         b3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
         K.gemm_raw(a3, b3, dz, B * Tq, E, D, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E,
                    d_hi_stride=B * Tq * E)
-        K.colsum_batched(dz, G_.from_("proj_head.0.upsampler.bias"), gs)
         a3 = L.tensor3(data_ptr=dz.data_ptr(), dim=(2 * E, B * Ts, n), stride=(2 * E, B * Ts * 2 * E))
         x3 = L.tensor3(data_ptr=c.lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
         K.gemm_raw(a3, x3, G_.from_("proj_head.0.upsampler.weight"), 2 * E, E, B * Ts, a_major=1, b_major=1, num_ob=n,
@@ -632,8 +637,7 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             j = c.head_idx.index(l)
             dp = dpred[j].view(B * Tq, D)
             z = c.z[j].view(B * Tq, E)
-            if not lin_bias_done:
-                K.colsum(dp, gv(hp + "lin_proj.bias"))
+            K.colsum(dp, gv(hp + "lin_proj.bias"))
             K.linear_wgrad(dp, z, out=gv(hp + "lin_proj.weight").view(D, E), accumulate=True)
             dz = K.linear_dgrad(dp, W[f"h{l}.wlin"].view(D, E))  # [B*Tq, E] == [B*Ts, 2E]
             K.colsum(dz, gv(hp + "upsampler.bias"))

@@ -24,6 +24,12 @@ launch_count = L.launch_count
 
 
 def enable_gemm_timing(on: bool) -> None:
+    """Bracket every fhb_gemm launch with a CUDA-event pair.  Programmatic dependent launch is switched off
+    while timing so that each pair covers the whole kernel (prologue included), not just its un-overlapped part."""
+    if on:
+        _GEMM_TIMING["pdl"] = L.lib().fhb_set_pdl(0)
+    elif "pdl" in _GEMM_TIMING:
+        L.lib().fhb_set_pdl(_GEMM_TIMING.pop("pdl"))
     _GEMM_TIMING["on"] = on
     _GEMM_TIMING["events"] = []
 
@@ -272,6 +278,13 @@ def colsum_batched(x3d, out, out_bstride):
     L.check(L.lib().fhb_colsum_batched(L.ptr(x3d), C.c_int64(rows), Cd, C.c_int64(x3d.stride(1)),
                                        C.c_int64(x3d.stride(0)), L.ptr(out), C.c_int64(out_bstride), n, L.stream_ptr()),
             "fhb_colsum_batched")
+
+
+def head_bias_grads(cs, wlin, wlin_stride, dlin_bias, dup_bias, grad_stride, n_heads, D, Ed):
+    """cs: fp32 [n, D] column sums of dpred.  dlin_bias (or None) += cs; dup_bias += cs @ Wlin per head."""
+    L.check(L.lib().fhb_head_bias_grads(L.ptr(cs), C.c_int64(cs.stride(0)), L.ptr(wlin), C.c_int64(wlin_stride),
+                                        L.ptr(dlin_bias), L.ptr(dup_bias), C.c_int64(grad_stride), n_heads, D, Ed,
+                                        L.stream_ptr()), "fhb_head_bias_grads")
 
 
 def add_bf16(a, b, y):

@@ -23,6 +23,10 @@ typedef void* fhb_stream_t; /* cudaStream_t */
 
 const char* fhb_last_error(void);
 int fhb_abi_version(void);
+/* Programmatic dependent launch (off by default; FHB_PDL=1 in the environment or fhb_set_pdl(1) enables it): kernels
+ * are then launched so that their prologue overlaps the previous kernel's tail; each waits (griddepcontrol.wait)
+ * before its first global-memory access.  Returns the previous setting.  Per-kernel event timing switches it off. */
+int fhb_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
  * D[ob][m][n] = epilogue( sum_{cb,k} A[ob,cb][m][k] * B[ob,cb][n][k] )        bf16 x bf16 -> fp32
@@ -247,6 +251,13 @@ int fhb_add_bf16(const void* a, const void* b, void* y, int64_t n, fhb_stream_t 
  * GELU derivative is not a GEMM epilogue: LayerNorm(512)-backward -> last conv layer (module.py:73) */
 int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_bstride, void* out,
                   int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
+/* Bias gradients of the n LayerWiseProjHeads (modules/module.py:649-661) from the column sums of dpred alone:
+ * dlin_bias[h][d] += cs[h][d] (may be NULL) and dup_bias[h][e] += sum_d cs[h][d] * wlin[h][d][e]  (the column sums
+ * of dz = dpred @ Wlin, i.e. the ConvTranspose1d bias gradient, without a pass over dz).  cs: fp32 [n][D] at
+ * cs_stride; wlin: bf16 [n][D][E] at wlin_stride; both gradient blocks at grad_stride floats per head. */
+int fhb_head_bias_grads(const float* colsum_dpred, int64_t cs_stride, const void* wlin, int64_t wlin_stride,
+                        float* dlin_bias, float* dup_bias, int64_t grad_stride, int32_t n_heads, int32_t D, int32_t E,
+                        fhb_stream_t stream);
 /* out = a * m elementwise (bf16), same batching; m is a multiplier saved by FHB_EPI_AUX_DGELU */
 int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstride, void* out,
                  int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
