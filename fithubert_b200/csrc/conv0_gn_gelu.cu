@@ -147,6 +147,23 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
   }
 }
 
+// Fold the per-thread accumulators of the fy frame lanes (same channels, different frames) into red[(i, q)][tx]
+// (bank-conflict free, zero-initialised by the caller) one lane at a time: plain read-modify-writes between
+// barriers - shared-memory float atomics are CAS spin loops and the lanes collide on every address.
+template <int CPT>
+__device__ __forceinline__ void block_fold(float* red, const float (&acc)[CPT][2 + kK], int tx, int ty, int fy, int tcols) {
+  __syncthreads();
+  for (int w = 0; w < fy; ++w) {
+    if (ty == w) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int q = 0; q < 2 + kK; ++q) red[(i * (2 + kK) + q) * tcols + tx] += acc[i][q];
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- backward (single pass over dY)
 // Per (b, c) accumulate  A0 = sum_t dz,  A1 = sum_t dz*xhat,  P_j = sum_t dz*x[5t+j]   (dz = dY*gelu'(z)).
 constexpr int kNAcc = 2 + kK;  // 12
@@ -225,14 +242,13 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
         acc[i][1] = rs[i] * (wp - mu[i] * acc[i][0]);
       }
     }
-#pragma unroll
-    for (int i = 0; i < CPT; ++i)
-#pragma unroll
-      for (int q = 0; q < kNAcc; ++q) atomicAdd(&red[(c0 + i) * kNAcc + q], acc[i][q]);
   }
-  __syncthreads();
+  block_fold<CPT>(red, acc, tx, ty, fy, tcols);
   float* o = acc_out + (long long)b * C * kNAcc;
-  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) atomicAdd(o + i, red[i]);
+  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) {
+    const int c = i / kNAcc, q = i - c * kNAcc;
+    atomicAdd(o + i, red[((c % CPT) * kNAcc + q) * tcols + c / CPT]);
+  }
 }
 
 // Training path: dy already carries gelu'(z) (saved by the forward as gp_out and multiplied in by the dgrad
@@ -297,29 +313,37 @@ conv0_bwd_dz_kernel(const float* __restrict__ wave, long long ld, int T0, int C,
       for (int j = 0; j < kK; ++j) wp = fmaf(__ldg(weight + (c0 + i) * kK + j), acc[i][2 + j], wp);
       const float mu = mean[b * C + c0 + i], rs = rstd[b * C + c0 + i];
       acc[i][1] = rs * (wp - mu * acc[i][0]);
-#pragma unroll
-      for (int q = 0; q < kNAcc; ++q) atomicAdd(&red[(c0 + i) * kNAcc + q], acc[i][q]);
     }
   }
-  __syncthreads();
+  block_fold<CPT>(red, acc, tx, ty, fy, tcols);
   float* o = acc_out + (long long)b * C * kNAcc;
-  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) atomicAdd(o + i, red[i]);
+  for (int i = threadIdx.x; i < C * kNAcc; i += blockDim.x) {
+    const int c = i / kNAcc, q = i - c * kNAcc;
+    atomicAdd(o + i, red[((c % CPT) * kNAcc + q) * tcols + c / CPT]);
+  }
 }
 
-// dW[c][j], dgamma[c], dbeta[c] from the per-(b,c) accumulators (see header comment for the algebra)
+// dW[c][j], dgamma[c], dbeta[c] from the per-(b,c) accumulators (see header comment for the algebra).
+// One thread per (channel, tap); the tap-0 thread also owns dgamma / dbeta.
 __global__ void conv0_bwd_finalize_kernel(const float* __restrict__ acc, const double* __restrict__ stat,
                                           const float* __restrict__ weight, const float* __restrict__ gamma,
                                           const float* __restrict__ mean, const float* __restrict__ rstd, int B, int C,
                                           int T0, float* __restrict__ dW, float* __restrict__ dgamma,
                                           float* __restrict__ dbeta, int accumulate) {
   pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float w[kK];
-  for (int j = 0; j < kK; ++j) w[j] = weight[c * kK + j];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * kK) return;
+  const int c = idx / kK, j = idx - c * kK;
+  double w[kK];
+  int ridx[kK];  // packed-upper-triangle index of R[q][j]
+#pragma unroll
+  for (int q = 0; q < kK; ++q) {
+    w[q] = (double)weight[c * kK + q];
+    const int lo = q < j ? q : j, hi = q < j ? j : q;
+    ridx[q] = lo * kK - lo * (lo - 1) / 2 + (hi - lo);
+  }
   const double gm = gamma[c];
-  double dw[kK], dg = 0.0, db = 0.0;
-  for (int j = 0; j < kK; ++j) dw[j] = 0.0;
+  double dw = 0.0, dg = 0.0, db = 0.0;
   for (int b = 0; b < B; ++b) {
     const float* a = acc + ((long long)b * C + c) * kNAcc;
     const double* S = stat + (long long)b * kNStat;
@@ -328,21 +352,17 @@ __global__ void conv0_bwd_finalize_kernel(const float* __restrict__ acc, const d
     const double a0 = a[0], a1 = a[1];
     dg += a1;
     db += a0;
-    for (int j = 0; j < kK; ++j) {
-      // sum_t y x_j = sum_j' w_j' R[j', j]
-      double yx = 0.0;
-      for (int q = 0; q < kK; ++q) {
-        const int lo = q < j ? q : j, hi = q < j ? j : q;
-        const int idx = lo * kK - lo * (lo - 1) / 2 + (hi - lo);
-        yx += (double)w[q] * R[idx];
-      }
-      const double xhat_x = r * (yx - m * S[j]);
-      dw[j] += r * gm * ((double)a[2 + j] - a0 / T0 * S[j] - a1 / T0 * xhat_x);
-    }
+    double yx = 0.0;  // sum_t y x_j = sum_q w_q R[q, j]
+#pragma unroll
+    for (int q = 0; q < kK; ++q) yx += w[q] * R[ridx[q]];
+    const double xhat_x = r * (yx - m * S[j]);
+    dw += r * gm * ((double)a[2 + j] - a0 / T0 * S[j] - a1 / T0 * xhat_x);
   }
-  for (int j = 0; j < kK; ++j) dW[c * kK + j] = (accumulate ? dW[c * kK + j] : 0.f) + (float)dw[j];
-  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)dg;
-  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)db;
+  dW[idx] = (accumulate ? dW[idx] : 0.f) + (float)dw;
+  if (j == 0) {
+    dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)dg;
+    dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)db;
+  }
 }
 
 int check_common(const fhb_conv0_args* a) {
@@ -403,7 +423,7 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
     FHB_CUDA_CHECK(fhb_launch((conv0_bwd_dz_kernel<4>), dim3(grid), dim3(256), smem, s, a->wave, a->wave_ld, a->T0, a->C, frames, a->weight, a->mean, a->rstd,
                                                    static_cast<const __nv_bfloat16*>(a->dy), a->acc));
     FHB_LAUNCH_CHECK();
-    FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize_kernel, dim3((a->C + 63) / 64), dim3(64), 0, s, a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
+    FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize_kernel, dim3((a->C * kK + 127) / 128), dim3(128), 0, s, a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
                                                              a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
                                                              a->accumulate));
     FHB_LAUNCH_CHECK();
@@ -417,7 +437,7 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
                                               a->mean, a->rstd, static_cast<const __nv_bfloat16*>(a->dy), a->acc,
                                               a->dy_is_dz));
   FHB_LAUNCH_CHECK();
-  FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize_kernel, dim3((a->C + 63) / 64), dim3(64), 0, s, a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
+  FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize_kernel, dim3((a->C * kK + 127) / 128), dim3(128), 0, s, a->acc, a->stat, a->weight, a->gamma, a->mean, a->rstd,
                                                            a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
                                                            a->accumulate));
   FHB_LAUNCH_CHECK();

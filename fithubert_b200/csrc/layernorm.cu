@@ -91,9 +91,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      __nv_bfloat16* __restrict__ dx_drop, uint32_t drop_seed, uint32_t drop_thr, float drop_scale,
                      long long rows, int C) {
   pdl_sync();
-  extern __shared__ float sred[];  // [3][C]
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float sred[];  // [warps][NS][C]: per-warp column partials (no shared-memory float atomics:
+                                   // they compile to CAS spin loops and eight warps collide on every column)
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -173,23 +172,32 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       }
     }
   }
+  constexpr int NS = DXSUM ? 3 : 2;
+  float* mine = sred + (threadIdx.x >> 5) * NS * C;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sred[vi * 8 + j], pg[i][j]);
-        atomicAdd(&sred[C + vi * 8 + j], pb[i][j]);
-        if (DXSUM) atomicAdd(&sred[2 * C + vi * 8 + j], pd[i][j]);
+      float4* g4 = reinterpret_cast<float4*>(mine + vi * 8);
+      float4* b4 = reinterpret_cast<float4*>(mine + C + vi * 8);
+      g4[0] = make_float4(pg[i][0], pg[i][1], pg[i][2], pg[i][3]);
+      g4[1] = make_float4(pg[i][4], pg[i][5], pg[i][6], pg[i][7]);
+      b4[0] = make_float4(pb[i][0], pb[i][1], pb[i][2], pb[i][3]);
+      b4[1] = make_float4(pb[i][4], pb[i][5], pb[i][6], pb[i][7]);
+      if (DXSUM) {
+        float4* d4 = reinterpret_cast<float4*>(mine + 2 * C + vi * 8);
+        d4[0] = make_float4(pd[i][0], pd[i][1], pd[i][2], pd[i][3]);
+        d4[1] = make_float4(pd[i][4], pd[i][5], pd[i][6], pd[i][7]);
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, sred[i]);
-    atomicAdd(dbeta + i, sred[C + i]);
-    if (DXSUM) atomicAdd(dxsum + i, sred[2 * C + i]);
+  const int nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < NS * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += sred[w * NS * C + i];
+    float* dst = i < C ? dgamma + i : (i < 2 * C ? dbeta + (i - C) : dxsum + (i - 2 * C));
+    atomicAdd(dst, t);
   }
 }
 
@@ -228,14 +236,22 @@ extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x,
   long long blocks = (rows + 15) / 16;
   if (blocks > 2LL * fhb_num_sms()) blocks = 2LL * fhb_num_sms();
   const int nv = (C / 8 + 31) / 32;
-  const size_t sm = 3 * C * sizeof(float);
+  const size_t sm = 8 * (dxsum ? 3 : 2) * C * sizeof(float);  // [8 warps][NS][C]
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define FHB_LN_BWD(NV, DX)                                                                                          \
-  FHB_CUDA_CHECK(fhb_launch((layernorm_bwd_kernel<NV, DX>), dim3((unsigned)blocks), dim3(256), sm, s,                                                    \
+  do {                                                                                                              \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      FHB_CUDA_CHECK(cudaFuncSetAttribute(layernorm_bwd_kernel<NV, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          8 * 3 * kMaxVec * 256 * (int)sizeof(float)));                             \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    FHB_CUDA_CHECK(fhb_launch((layernorm_bwd_kernel<NV, DX>), dim3((unsigned)blocks), dim3(256), sm, s,             \
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dy2),                               \
       static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,                                                      \
       static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum,              \
-      static_cast<__nv_bfloat16*>(dx_drop), drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p), rows, C))
+      static_cast<__nv_bfloat16*>(dx_drop), drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p), rows, C)); \
+  } while (0)
   if (dxsum) {
     if (nv == 1) FHB_LN_BWD(1, true); else if (nv == 2) FHB_LN_BWD(2, true); else FHB_LN_BWD(3, true);
   } else {

@@ -6,127 +6,240 @@
 
 namespace {
 
-// xg[b][g][tp][c'] = x[b][tp - pad_l][g*cg + c'] if 0 <= tp - pad_l < valid[b] and c' < cg else 0
+// bf16 vectors of VEC = 2 (one 32-bit word) or 8 (one 16-byte word) elements <-> fp32 registers
+template <int VEC>
+__device__ __forceinline__ void ldv(const __nv_bfloat16* p, float* f) {
+  if constexpr (VEC == 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t a[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_bf16(a[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
+    }
+  } else {
+    const float2 t = unpack_bf16(*reinterpret_cast<const uint32_t*>(p));
+    f[0] = t.x;
+    f[1] = t.y;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const float* f) {
+  if constexpr (VEC == 8) {
+    *reinterpret_cast<uint4*>(p) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16(f[0], f[1]);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void ldf(const float* p, float* f) {
+#pragma unroll
+  for (int j = 0; j < VEC; j += 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p + j));
+    f[j] = t.x;
+    f[j + 1] = t.y;
+  }
+}
+
+// xg[b][g][tp][c'] = x[b][tp - pad_l][g*cg + c'] if 0 <= tp - pad_l < valid[b] and c' < cg else 0.
+// One thread per 16-byte output chunk (8 channels); the source is read as one 16-byte word (cg % 8 == 0, VEC = 8)
+// or as 32-bit words (cg even, VEC = 2: FitHuBERT's 30 channels per group start on 4-byte boundaries only).
+template <int VEC>
 __global__ void __launch_bounds__(256)
 posconv_pack_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ valid, __nv_bfloat16* __restrict__ xg,
-                    int T, int C, int G, int cp, int pad_l, int Tp, long long total) {
+                    int T, int C, int G, int cp, int pad_l, int Tp, long long total_chunks) {
   pdl_sync();
-  const int cg = C / G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = i % cp;
-    long long r = i / cp;
+  const int cg = C / G, cpv = cp >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cpv) * 8;
+    long long r = i / cpv;
     const int tp = r % Tp;
     r /= Tp;
     const int g = r % G;
     const int b = r / G;
     const int t = tp - pad_l;
     const int nv = valid ? min(valid[b], T) : T;
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    if (c < cg && t >= 0 && t < nv) v = x[((long long)b * T + t) * C + g * cg + c];
-    xg[i] = v;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < nv && c0 < cg) {
+      const __nv_bfloat16* src = x + ((long long)b * T + t) * C + g * cg + c0;
+      if constexpr (VEC == 8) {
+        o = __ldg(reinterpret_cast<const uint4*>(src));
+      } else if constexpr (VEC == 2) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (c0 + 2 * q < cg) ? __ldg(reinterpret_cast<const uint32_t*>(src + 2 * q)) : 0u;
+        o = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t lo = (c0 + 2 * q < cg) ? (uint32_t)reinterpret_cast<const uint16_t*>(src)[2 * q] : 0u;
+          const uint32_t hi = (c0 + 2 * q + 1 < cg) ? (uint32_t)reinterpret_cast<const uint16_t*>(src)[2 * q + 1] : 0u;
+          w[q] = lo | (hi << 16);
+        }
+        o = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    reinterpret_cast<uint4*>(xg)[i] = o;
   }
 }
 
-// One block per tap j: n_j = ||v[:,:,j]||, w = g_j * v / n_j written in GEMM layout (bf16).
-//  flip_transpose = 0: W[g][co][(j, ci)]           (forward B operand, K-major over (j,ci))
-//  flip_transpose = 1: W[g][ci][(127 - j, co)]     (dgrad B operand)
-// Time blocking (delta > 1): one GEMM row produces `delta` consecutive frames, so the B operand holds delta
-// shifted copies of W:  W'[g][(dl, n)][(j + dl, k)] = W[g][n][(j, k)],  K' = (K + delta) taps, zero elsewhere
-// (the buffer is zeroed once; the nonzero pattern never changes).  N grows from cp (30-48: a sliver of the
-// 128 x N UMMA) to delta * cp at +delta/K extra flops.
+// Weight norm (reference modules/module.py:199: nn.utils.weight_norm(dim=2)) in two launches.
+//  (1) per-tap sums of squares of v [C*cg][K] (tap fastest): coalesced row reads, one atomic per tap per block
 __global__ void __launch_bounds__(256)
-posconv_wn_prep_kernel(const float* __restrict__ v, const float* __restrict__ gain, __nv_bfloat16* __restrict__ w_out,
-                       float* __restrict__ inv_norm, int C, int G, int K, int cp, int flip_transpose, int delta) {
+posconv_wn_sumsq_kernel(const float* __restrict__ v, long long n_rows, int K, int rows_per_block, float* __restrict__ sumsq) {
   pdl_sync();
-  const int j = blockIdx.x;
-  const int cg = C / G;
-  const int n = C * cg;
+  __shared__ float red[256];
+  const int lanes = blockDim.x / K;            // row lanes (host guarantees K <= 256 and K divides 256)
+  const int j = threadIdx.x % K, rl = threadIdx.x / K;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(n_rows, r0 + rows_per_block);
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float t = v[(long long)i * K + j];
-    s += t * t;
+#pragma unroll 8
+  for (long long r = r0 + rl; r < r1; r += lanes) {
+    const float t = __ldg(v + r * K + j);
+    s = fmaf(t, t, s);
   }
-  __shared__ float red[8];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  red[threadIdx.x] = s;
   __syncthreads();
-  float tot = 0.f;
-  for (int w = 0; w < 8; ++w) tot += red[w];
-  const float inv = rsqrtf(tot);
-  if (threadIdx.x == 0 && inv_norm) inv_norm[j] = inv;
-  const float sc = gain[j] * inv;
-  // padded entries are zero
-  const int total = G * cp * cp;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int ci = i % cp;
-    const int co = (i / cp) % cp;
-    const int g = i / (cp * cp);
-    float val = 0.f;
-    if (ci < cg && co < cg) val = sc * v[((long long)(g * cg + co) * cg + ci) * K + j];
-    const int n = flip_transpose ? ci : co, kk = flip_transpose ? co : ci, jj = flip_transpose ? K - 1 - j : j;
-    const __nv_bfloat16 bv = __float2bfloat16(val);
-    for (int dl = 0; dl < delta; ++dl)
-      w_out[((long long)((g * delta + dl) * cp + n) * (K + (delta > 1 ? delta : 0)) + jj + dl) * cp + kk] = bv;
+  if (rl == 0) {
+    for (int q = 1; q < lanes; ++q) s += red[q * K + j];
+    atomicAdd(sumsq + j, s);
   }
 }
 
-// Warp per (b, t) row:  h = xz + gelu(conv + bias);  y = LN(h).   conv is [B*T][G][cp] (bf16, raw GEMM output)
+//  (2) w = g_j * v / ||v_j|| written in GEMM layout (bf16).  Block (r, g, z): z = 0 forward operand
+//      W[g][co = r][(j, ci)], z = 1 dgrad operand W[g][ci = r][(K - 1 - j, co)]; the [kk][tap] source tile
+//      (kk = the operand's inner channel index) is read with coalesced 4*K-byte rows and transposed through smem.
+//  Time blocking (delta > 1): one GEMM row produces `delta` consecutive frames, so the B operand holds delta
+//  shifted copies of W:  W'[g][(dl, n)][(j + dl, k)] = W[g][n][(j, k)],  K' = (K + delta) taps, zero elsewhere
+//  (the buffer is zeroed once; the nonzero pattern never changes).  N grows from cp (30-48: a sliver of the
+//  128 x N UMMA) to delta * cp at +delta/K extra flops.
+__global__ void __launch_bounds__(256)
+posconv_wn_layout_kernel(const float* __restrict__ v, const float* __restrict__ gain, const float* __restrict__ sumsq,
+                         __nv_bfloat16* __restrict__ w_fwd, __nv_bfloat16* __restrict__ w_bwd,
+                         float* __restrict__ inv_norm, int C, int G, int K, int cp, int delta) {
+  pdl_sync();
+  extern __shared__ float tile[];  // [cg][K + 1] then sc[K]
+  const int cg = C / G;
+  const int r = blockIdx.x, g = blockIdx.y, flip = blockIdx.z;
+  __nv_bfloat16* w_out = flip ? w_bwd : w_fwd;
+  float* sc = tile + cg * (K + 1);
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    const float inv = rsqrtf(sumsq[j]);
+    sc[j] = gain[j] * inv;
+    if (r == 0 && g == 0 && flip == 0 && inv_norm) inv_norm[j] = inv;
+  }
+  if (w_out == nullptr) return;
+  for (int i = threadIdx.x; i < cg * K; i += blockDim.x) {
+    const int kk = i / K, j = i - kk * K;
+    const long long row = flip ? (long long)(g * cg + kk) * cg + r : (long long)(g * cg + r) * cg + kk;
+    tile[kk * (K + 1) + j] = __ldg(v + row * K + j);
+  }
+  __syncthreads();
+  const int Kx = K + (delta > 1 ? delta : 0);
+  const int half = cg >> 1;  // cg is even (host check): consecutive threads write consecutive bf16 pairs of one tap row
+  for (int i = threadIdx.x; i < K * half; i += blockDim.x) {
+    const int j = i / half, kk = (i - j * half) * 2;
+    const uint32_t pk = pack_bf16(sc[j] * tile[kk * (K + 1) + j], sc[j] * tile[(kk + 1) * (K + 1) + j]);
+    const int jj = flip ? K - 1 - j : j;
+    for (int dl = 0; dl < delta; ++dl)
+      *reinterpret_cast<uint32_t*>(w_out + ((long long)((g * delta + dl) * cp + r) * Kx + jj + dl) * cp + kk) = pk;
+  }
+}
+
+// Warp per (b, t) row:  h = xz + gelu(conv + bias);  y = LN(h).   conv is [B*T][G][cp] (bf16, raw GEMM output).
+// Lane owns NV vectors of VEC channels (a vector never straddles a group: cg % VEC == 0); the group offsets are
+// computed once per lane, each warp walks `rows_per_warp` rows.
+template <int VEC, int NV>
 __global__ void __launch_bounds__(256)
 posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ valid,
                           const __nv_bfloat16* __restrict__ conv, const float* __restrict__ bias,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                          float* __restrict__ rstd_out, int B, int T, int C, int G, int cp, float eps, int delta) {
+                          float* __restrict__ rstd_out, int B, int T, int C, int G, int cp, float eps, int delta,
+                          int rows_per_warp) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= (long long)B * T) return;
-  const int b = row / T, t = row % T;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long rows = (long long)B * T;
   const int cg = C / G;
-  const bool live = valid ? t < valid[b] : true;
-  // conv GEMM output layout: [b][r = t / delta][g][dl = t % delta][cp]
-  const long long crow = ((long long)b * ((T + delta - 1) / delta) + t / delta) * G * delta + (t % delta);
-  float hv[24];  // C <= 768
-  float s = 0.f;
+  const int R = (T + delta - 1) / delta;
+  int coff[NV];  // offset of this lane's i-th vector inside a conv row block [g][dl][cp]; -1: beyond C
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + 32 * i;
-    hv[i] = 0.f;
-    if (c < C) {
-      const int g = c / cg, cc = c - g * cg;
-      const float xv = live ? __bfloat162float(x[row * C + c]) : 0.f;
-      const float cv = __bfloat162float(conv[(crow + (long long)g * delta) * cp + cc]) + bias[c];
-      hv[i] = xv + gelu_erf(cv);
-      s += hv[i];
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * VEC;
+    const int g = c / cg;
+    coff[i] = c < C ? g * delta * cp + (c - g * cg) : -1;
+  }
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const long long row = warp_global * rows_per_warp + rr;
+    if (row >= rows) break;
+    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+    const bool live = valid ? t < valid[b] : true;
+    // conv GEMM output layout: [b][r = t / delta][g][dl = t % delta][cp]
+    const __nv_bfloat16* cbase = conv + (((long long)b * R + t / delta) * G * delta + (t % delta)) * cp;
+    float hv[NV][VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (coff[i] >= 0) {
+        const int c = (lane + 32 * i) * VEC;
+        float xv[VEC], cv[VEC], bv[VEC];
+        if (live) {
+          ldv<VEC>(x + row * C + c, xv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) xv[j] = 0.f;
+        }
+        ldv<VEC>(cbase + coff[i], cv);
+        ldf<VEC>(bias + c, bv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          hv[i][j] = xv[j] + gelu_erf(cv[j] + bv[j]);
+          s += hv[i][j];
+        }
+      }
     }
-  }
-  const float mu = warp_sum(s) / (float)C;
-  float q = 0.f;
+    const float mu = warp_sum(s) / (float)C;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) {
-      const float dlt = hv[i] - mu;
-      q += dlt * dlt;
+    for (int i = 0; i < NV; ++i) {
+      if (coff[i] >= 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float dlt = hv[i][j] - mu;
+          q = fmaf(dlt, dlt, q);
+        }
+      }
     }
-  }
-  const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
-  if (lane == 0 && mean_out) {
-    mean_out[row] = mu;
-    rstd_out[row] = rs;
-  }
+    const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0 && mean_out) {
+      mean_out[row] = mu;
+      rstd_out[row] = rs;
+    }
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) {
-      if (h_out) h_out[row * C + c] = __float2bfloat16(hv[i]);
-      y[row * C + c] = __float2bfloat16((hv[i] - mu) * rs * gamma[c] + beta[c]);
+    for (int i = 0; i < NV; ++i) {
+      if (coff[i] >= 0) {
+        const int c = (lane + 32 * i) * VEC;
+        if (h_out) stv<VEC>(h_out + row * C + c, hv[i]);
+        float gv[VEC], bv[VEC], o[VEC];
+        ldf<VEC>(gamma + c, gv);
+        ldf<VEC>(beta + c, bv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = (hv[i][j] - mu) * rs * gv[j] + bv[j];
+        stv<VEC>(y + row * C + c, o);
+      }
     }
   }
 }
 
 // Backward of the above.  dh = LNbwd(dy); dconv = dh * gelu'(conv + bias) written group-major, time-padded:
 // dcg[b][g][t + pad_l][cc] (pad channels written as 0); dgamma/dbeta/dbias accumulated atomically.
+template <int VEC, int NV>
 __global__ void __launch_bounds__(256)
 posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
                           const __nv_bfloat16* __restrict__ conv, const float* __restrict__ bias,
@@ -136,96 +249,130 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
                           float* __restrict__ dbias, int B, int T, int C, int G, int cp, int pad_l, int Tp,
                           int rows_per_warp, int delta) {
   pdl_sync();
-  extern __shared__ float sred[];  // [3][C]
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float sred[];  // [warps][3][C] per-warp column partials (shared float atomics are CAS spin loops)
   const int lane = threadIdx.x & 31;
   const int cg = C / G;
+  const int R = (T + delta - 1) / delta;
   const long long rows = (long long)B * T;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  float pg[24], pb[24], pc[24];
+  int coff[NV], goff[NV];  // conv-row offset and dcg offset (g * Tp * cp + cc) of this lane's vectors
+  float pg[NV][VEC], pb[NV][VEC], pc[NV][VEC];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) pg[i] = pb[i] = pc[i] = 0.f;
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * VEC;
+    const int g = c / cg, cc = c - g * cg;
+    coff[i] = c < C ? g * delta * cp + cc : -1;
+    goff[i] = g * Tp * cp + cc;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) pg[i][j] = pb[i][j] = pc[i][j] = 0.f;
+  }
+  const int npad = G * (cp - cg) / 2;  // zero pad channel PAIRS per row (cp, cg even)
   for (int rr = 0; rr < rows_per_warp; ++rr) {
     const long long row = warp_global * rows_per_warp + rr;
     if (row >= rows) break;
-    const int b = row / T, t = row % T;
-    const long long crow = ((long long)b * ((T + delta - 1) / delta) + t / delta) * G * delta + (t % delta);
+    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+    const __nv_bfloat16* cbase = conv + (((long long)b * R + t / delta) * G * delta + (t % delta)) * cp;
+    __nv_bfloat16* dbase = dcg + ((long long)b * G * Tp + t + pad_l) * cp;
     const float mu = mean[row], rs = rstd[row];
-    float xh[24], dv[24];
+    float xh[NV][VEC], dv[NV][VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-      const int c = lane + 32 * i;
-      xh[i] = dv[i] = 0.f;
-      if (c < C) {
-        xh[i] = (__bfloat162float(h[row * C + c]) - mu) * rs;
-        dv[i] = __bfloat162float(dy[row * C + c]);
-        const float dxh = dv[i] * gamma[c];
-        s1 += dxh;
-        s2 += dxh * xh[i];
-        pg[i] += dv[i] * xh[i];
-        pb[i] += dv[i];
+    for (int i = 0; i < NV; ++i) {
+      if (coff[i] >= 0) {
+        const int c = (lane + 32 * i) * VEC;
+        float gv[VEC];
+        ldv<VEC>(h + row * C + c, xh[i]);
+        ldv<VEC>(dy + row * C + c, dv[i]);
+        ldf<VEC>(gamma + c, gv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          pg[i][j] = fmaf(dv[i][j], xh[i][j], pg[i][j]);
+          pb[i][j] += dv[i][j];
+          dv[i][j] *= gv[j];  // dxhat
+          s1 += dv[i][j];
+          s2 = fmaf(dv[i][j], xh[i][j], s2);
+        }
       }
     }
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-      const int c = lane + 32 * i;
-      if (c < C) {
-        const float d = rs * (dv[i] * gamma[c] - s1 - xh[i] * s2);
-        dh[row * C + c] = __float2bfloat16(d);
-        const int g = c / cg, cc = c - g * cg;
-        const float cv = __bfloat162float(conv[(crow + (long long)g * delta) * cp + cc]) + bias[c];
-        const float dc = d * gelu_erf_grad(cv);
-        pc[i] += dc;
-        dcg[(((long long)b * G + g) * Tp + t + pad_l) * cp + cc] = __float2bfloat16(dc);
+    for (int i = 0; i < NV; ++i) {
+      if (coff[i] >= 0) {
+        const int c = (lane + 32 * i) * VEC;
+        float cv[VEC], bv[VEC], d[VEC], dc[VEC];
+        ldv<VEC>(cbase + coff[i], cv);
+        ldf<VEC>(bias + c, bv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          d[j] = rs * (dv[i][j] - s1 - xh[i][j] * s2);
+          dc[j] = d[j] * gelu_erf_grad(cv[j] + bv[j]);
+        }
+        stv<VEC>(dh + row * C + c, d);
+        stv<VEC>(dbase + goff[i], dc);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) pc[i][j] += dc[j];
       }
     }
     // channel padding cg..cp-1 of every group: must read as zero in the dgrad GEMM (0-weight x garbage = NaN)
-    for (int i = lane; i < G * (cp - cg); i += 32) {
-      const int g = i / (cp - cg), cc = cg + i % (cp - cg);
-      dcg[(((long long)b * G + g) * Tp + t + pad_l) * cp + cc] = __float2bfloat16(0.f);
+    for (int i = lane; i < npad; i += 32) {
+      const int g = i / ((cp - cg) / 2), cc = cg + 2 * (i % ((cp - cg) / 2));
+      *reinterpret_cast<uint32_t*>(dbase + (long long)g * Tp * cp + cc) = 0u;
     }
   }
+  float* mine = sred + (threadIdx.x >> 5) * 3 * C;
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) {
-      atomicAdd(&sred[c], pg[i]);
-      atomicAdd(&sred[C + c], pb[i]);
-      atomicAdd(&sred[2 * C + c], pc[i]);
+  for (int i = 0; i < NV; ++i) {
+    if (coff[i] >= 0) {
+      const int c = (lane + 32 * i) * VEC;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        mine[c + j] = pg[i][j];
+        mine[C + c + j] = pb[i][j];
+        mine[2 * C + c + j] = pc[i][j];
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, sred[i]);
-    atomicAdd(dbeta + i, sred[C + i]);
-    atomicAdd(dbias + i, sred[2 * C + i]);
+  const int nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += sred[w * 3 * C + i];
+    float* dst = i < C ? dgamma + i : (i < 2 * C ? dbeta + (i - C) : dbias + (i - 2 * C));
+    atomicAdd(dst, t);
   }
 }
 
 // dx[b][t][c] = (t < valid[b]) ? dh[b][t][c] + dxc[b][t][g][cc] : 0      (dxc = dgrad GEMM output)
+template <int VEC>
 __global__ void __launch_bounds__(256)
 posconv_unpack_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ dxc,
                           const int* __restrict__ valid, __nv_bfloat16* __restrict__ dx, int T, int C, int G, int cp,
-                          long long total, int delta) {
+                          long long total_vec, int delta) {
   pdl_sync();
-  const int cg = C / G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = i % C;
-    const long long row = i / C;
+  const int cg = C / G, cv = C / VEC;
+  const int R = (T + delta - 1) / delta;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    const long long row = i / cv;
     const int t = row % T;
     const int b = row / T;
     const bool live = valid ? t < valid[b] : true;
-    float v = 0.f;
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     if (live) {
       const int g = c / cg, cc = c - g * cg;
-      const long long crow = (((long long)b * ((T + delta - 1) / delta) + t / delta) * G + g) * delta + (t % delta);
-      v = __bfloat162float(dh[i]) + __bfloat162float(dxc[crow * cp + cc]);
+      const long long crow = (((long long)b * R + t / delta) * G + g) * delta + (t % delta);
+      float a[VEC], d[VEC];
+      ldv<VEC>(dh + i * VEC, a);
+      ldv<VEC>(dxc + crow * cp + cc, d);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = a[j] + d[j];
     }
-    dx[i] = __float2bfloat16(v);
+    stv<VEC>(dx + i * VEC, o);
   }
 }
 
@@ -242,7 +389,9 @@ __device__ __forceinline__ float wn_dw(const float* __restrict__ dwt, int g, int
   return s;
 }
 
-__global__ void __launch_bounds__(256)
+// One block (1024 threads) per tap j.  Threads walk (g, ci, co) with co fastest: the dwt reads are contiguous runs
+// of cg floats; v / dv are touched at stride K either way (tap-fastest parameter layout).
+__global__ void __launch_bounds__(1024)
 posconv_wn_bwd_kernel(const float* __restrict__ dwt, const float* __restrict__ v, const float* __restrict__ gain,
                       const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg, int C, int G,
                       int K, int cp, int accumulate, int delta) {
@@ -251,26 +400,26 @@ posconv_wn_bwd_kernel(const float* __restrict__ dwt, const float* __restrict__ v
   const int cg = C / G;
   const int n = C * cg;
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int ci = i % cg, co_full = i / cg;
-    const int g = co_full / cg, co = co_full - g * cg;
-    const float dw = wn_dw(dwt, g, j, ci, co, K, cp, delta);
-    s += dw * v[(long long)i * K + j];
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int co = idx % cg, rest = idx / cg;
+    const int ci = rest % cg, g = rest / cg;
+    const long long i = (long long)(g * cg + co) * cg + ci;
+    s += wn_dw(dwt, g, j, ci, co, K, cp, delta) * __ldg(v + i * K + j);
   }
-  __shared__ float red[8];
+  __shared__ float red[32];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   float tot = 0.f;
-  for (int w = 0; w < 8; ++w) tot += red[w];
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
   const float inv = inv_norm[j], gj = gain[j];
   if (threadIdx.x == 0) dg[j] = (accumulate ? dg[j] : 0.f) + tot * inv;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int ci = i % cg, co_full = i / cg;
-    const int g = co_full / cg, co = co_full - g * cg;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int co = idx % cg, rest = idx / cg;
+    const int ci = rest % cg, g = rest / cg;
+    const long long vi = ((long long)(g * cg + co) * cg + ci) * K + j;
     const float dw = wn_dw(dwt, g, j, ci, co, K, cp, delta);
-    const long long vi = (long long)i * K + j;
-    const float val = gj * inv * (dw - v[vi] * tot * inv * inv);
+    const float val = gj * inv * (dw - __ldg(v + vi) * tot * inv * inv);
     dv[vi] = (accumulate ? dv[vi] : 0.f) + val;
   }
 }
@@ -287,20 +436,52 @@ extern "C" int fhb_posconv_pack(const void* x, const int32_t* valid, void* xg, i
                                 int32_t G, int32_t cp, int32_t pad_l, int32_t Tp, fhb_stream_t stream) {
   FHB_ARG_CHECK(x && xg, "posconv_pack: null pointer");
   FHB_ARG_CHECK(C % G == 0 && cp >= C / G && cp % 16 == 0 && Tp >= T + pad_l, "posconv_pack: bad geometry");
-  const long long total = (long long)B * G * Tp * cp;
-  FHB_CUDA_CHECK(fhb_launch(posconv_pack_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), valid, static_cast<__nv_bfloat16*>(xg), T, C, G, cp, pad_l, Tp, total));
-  FHB_LAUNCH_CHECK();
+  const long long total = (long long)B * G * Tp * (cp / 8);
+  const int cg = C / G;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(xg);
+  if (cg % 8 == 0 && C % 8 == 0)
+    FHB_CUDA_CHECK(fhb_launch(posconv_pack_kernel<8>, dim3(grid_for(total)), dim3(256), 0, s, xp, valid, op, T, C, G, cp, pad_l, Tp, total));
+  else if (cg % 2 == 0)
+    FHB_CUDA_CHECK(fhb_launch(posconv_pack_kernel<2>, dim3(grid_for(total)), dim3(256), 0, s, xp, valid, op, T, C, G, cp, pad_l, Tp, total));
+  else
+    FHB_CUDA_CHECK(fhb_launch(posconv_pack_kernel<1>, dim3(grid_for(total)), dim3(256), 0, s, xp, valid, op, T, C, G, cp, pad_l, Tp, total));
   return 0;
 }
 
-extern "C" int fhb_posconv_wn_prep(const float* v, const float* g, void* w_out, float* inv_norm, int32_t C, int32_t G,
-                                   int32_t K, int32_t cp, int32_t flip_transpose, int32_t delta, fhb_stream_t stream) {
-  FHB_ARG_CHECK(v && g && w_out, "posconv_wn_prep: null pointer");
-  FHB_ARG_CHECK(C % G == 0 && cp >= C / G && delta >= 1, "posconv_wn_prep: bad geometry");
-  FHB_CUDA_CHECK(fhb_launch(posconv_wn_prep_kernel, dim3(K), dim3(256), 0, static_cast<cudaStream_t>(stream), v, g, static_cast<__nv_bfloat16*>(w_out),
-                                                                         inv_norm, C, G, K, cp, flip_transpose, delta));
-  FHB_LAUNCH_CHECK();
+extern "C" int fhb_posconv_wn_prep(const float* v, const float* g, void* w_fwd, void* w_bwd, float* ws, int32_t C,
+                                   int32_t G, int32_t K, int32_t cp, int32_t delta, fhb_stream_t stream) {
+  FHB_ARG_CHECK(v && g && ws && (w_fwd || w_bwd), "posconv_wn_prep: null pointer");
+  FHB_ARG_CHECK(C % G == 0 && cp >= C / G && delta >= 1 && (C / G) % 2 == 0, "posconv_wn_prep: bad geometry");
+  FHB_ARG_CHECK(K > 0 && K <= 256 && 256 % K == 0, "posconv_wn_prep: K=%d must divide 256", K);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cg = C / G;
+  const long long n_rows = (long long)C * cg;
+  FHB_CUDA_CHECK(cudaMemsetAsync(ws, 0, K * sizeof(float), s));
+  const int rpb = 64;
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_sumsq_kernel, dim3((unsigned)((n_rows + rpb - 1) / rpb)), dim3(256), 0, s, v, n_rows, K, rpb, ws));
+  const size_t smem = ((size_t)cg * (K + 1) + K) * sizeof(float);
+  FHB_ARG_CHECK(smem <= 48 * 1024, "posconv_wn_prep: cg=%d x K=%d tile does not fit 48 KB of shared memory", cg, K);
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_layout_kernel, dim3(cg, G, w_bwd ? 2 : 1), dim3(256), smem, s, v, g,
+                            static_cast<const float*>(ws), static_cast<__nv_bfloat16*>(w_fwd),
+                            static_cast<__nv_bfloat16*>(w_bwd), ws + K, C, G, K, cp, delta));
+  return 0;
+}
+
+template <int VEC>
+int launch_finish_fwd(int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, const int32_t* valid, const __nv_bfloat16* conv,
+                      const float* bias, const float* gamma, const float* beta, __nv_bfloat16* h_out, __nv_bfloat16* y,
+                      float* mean, float* rstd, int B, int T, int C, int G, int cp, float eps, int delta, int rpw) {
+#define FHB_FF(NV)                                                                                                        \
+  FHB_CUDA_CHECK(fhb_launch((posconv_finish_fwd_kernel<VEC, NV>), grid, dim3(256), 0, s, x, valid, conv, bias, gamma, beta, \
+                            h_out, y, mean, rstd, B, T, C, G, cp, eps, delta, rpw))
+  if constexpr (VEC == 8) {
+    if (nv <= 1) FHB_FF(1); else if (nv == 2) FHB_FF(2); else FHB_FF(3);
+  } else {
+    if (nv <= 4) FHB_FF(4); else if (nv <= 8) FHB_FF(8); else FHB_FF(12);
+  }
+#undef FHB_FF
   return 0;
 }
 
@@ -309,12 +490,39 @@ extern "C" int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const
                                       float* rstd, int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps,
                                       int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(x && conv && bias && gamma && beta && y && delta >= 1, "posconv_finish_fwd: null pointer");
-  FHB_ARG_CHECK(C <= 768 && C % G == 0, "posconv_finish_fwd: C=%d must be <= 768", C);
+  FHB_ARG_CHECK(C <= 768 && C % G == 0 && (C / G) % 2 == 0, "posconv_finish_fwd: C=%d must be <= 768 with an even group width", C);
   const long long rows = (long long)B * T;
-  FHB_CUDA_CHECK(fhb_launch(posconv_finish_fwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), valid, static_cast<const __nv_bfloat16*>(conv), bias, gamma, beta,
-      static_cast<__nv_bfloat16*>(h_out), static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta));
-  FHB_LAUNCH_CHECK();
+  const int rpw = 2;
+  const dim3 grid((unsigned)((rows + 8 * rpw - 1) / (8 * rpw)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cg = C / G;
+  if (cg % 8 == 0)
+    return launch_finish_fwd<8>((C / 8 + 31) / 32, grid, s, static_cast<const __nv_bfloat16*>(x), valid,
+                                static_cast<const __nv_bfloat16*>(conv), bias, gamma, beta, static_cast<__nv_bfloat16*>(h_out),
+                                static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta, rpw);
+  return launch_finish_fwd<2>((C / 2 + 31) / 32, grid, s, static_cast<const __nv_bfloat16*>(x), valid,
+                              static_cast<const __nv_bfloat16*>(conv), bias, gamma, beta, static_cast<__nv_bfloat16*>(h_out),
+                              static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta, rpw);
+}
+
+template <int VEC>
+int launch_finish_bwd(int nv, dim3 grid, size_t smem, cudaStream_t s, const __nv_bfloat16* dy, const __nv_bfloat16* h,
+                      const __nv_bfloat16* conv, const float* bias, const float* gamma, const float* mean, const float* rstd,
+                      __nv_bfloat16* dh, __nv_bfloat16* dcg, float* dgamma, float* dbeta, float* dbias, int B, int T, int C,
+                      int G, int cp, int pad_l, int Tp, int rpw, int delta) {
+#define FHB_FB(NV)                                                                                                       \
+  do {                                                                                                                   \
+    FHB_CUDA_CHECK(cudaFuncSetAttribute(posconv_finish_bwd_kernel<VEC, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                        8 * 3 * 768 * (int)sizeof(float)));                                              \
+    FHB_CUDA_CHECK(fhb_launch((posconv_finish_bwd_kernel<VEC, NV>), grid, dim3(256), smem, s, dy, h, conv, bias, gamma,   \
+                              mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, C, G, cp, pad_l, Tp, rpw, delta));         \
+  } while (0)
+  if constexpr (VEC == 8) {
+    if (nv <= 1) FHB_FB(1); else if (nv == 2) FHB_FB(2); else FHB_FB(3);
+  } else {
+    if (nv <= 4) FHB_FB(4); else if (nv <= 8) FHB_FB(8); else FHB_FB(12);
+  }
+#undef FHB_FB
   return 0;
 }
 
@@ -325,26 +533,44 @@ extern "C" int fhb_posconv_finish_bwd(const void* dy, const void* h, const void*
                                       fhb_stream_t stream) {
   FHB_ARG_CHECK(dy && h && conv && bias && gamma && mean && rstd && dh && dcg && dgamma && dbeta && dbias && delta >= 1,
                 "posconv_finish_bwd: null pointer");
-  FHB_ARG_CHECK(C <= 768 && C % G == 0, "posconv_finish_bwd: C=%d must be <= 768", C);
+  FHB_ARG_CHECK(C <= 768 && C % G == 0 && (C / G) % 2 == 0 && cp % 2 == 0,
+                "posconv_finish_bwd: C=%d must be <= 768 with an even group width", C);
   const long long rows = (long long)B * T;
-  const int rpw = 4;
-  const long long warps = (rows + rpw - 1) / rpw;
-  FHB_CUDA_CHECK(fhb_launch(posconv_finish_bwd_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 3 * C * sizeof(float), static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(conv),
-      bias, gamma, mean, rstd, static_cast<__nv_bfloat16*>(dh), static_cast<__nv_bfloat16*>(dcg), dgamma, dbeta, dbias, B,
-      T, C, G, cp, pad_l, Tp, rpw, delta));
-  FHB_LAUNCH_CHECK();
-  return 0;
+  // ~4 blocks per SM; every warp walks a contiguous run of rows and carries its column partial sums in registers
+  long long blocks = 4LL * fhb_num_sms();
+  if (blocks > (rows + 7) / 8) blocks = (rows + 7) / 8;
+  const int rpw = (int)((rows + blocks * 8 - 1) / (blocks * 8));
+  blocks = (rows + 8LL * rpw - 1) / (8LL * rpw);
+  const dim3 grid((unsigned)blocks);
+  const size_t smem = 8 * 3 * C * sizeof(float);  // [8 warps][3][C]
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cg = C / G;
+  if (cg % 8 == 0)
+    return launch_finish_bwd<8>((C / 8 + 31) / 32, grid, smem, s, static_cast<const __nv_bfloat16*>(dy),
+                                static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(conv), bias, gamma,
+                                mean, rstd, static_cast<__nv_bfloat16*>(dh), static_cast<__nv_bfloat16*>(dcg), dgamma, dbeta,
+                                dbias, B, T, C, G, cp, pad_l, Tp, rpw, delta);
+  return launch_finish_bwd<2>((C / 2 + 31) / 32, grid, smem, s, static_cast<const __nv_bfloat16*>(dy),
+                              static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(conv), bias, gamma,
+                              mean, rstd, static_cast<__nv_bfloat16*>(dh), static_cast<__nv_bfloat16*>(dcg), dgamma, dbeta,
+                              dbias, B, T, C, G, cp, pad_l, Tp, rpw, delta);
 }
 
 extern "C" int fhb_posconv_unpack_bwd(const void* dh, const void* dxc, const int32_t* valid, void* dx, int32_t B,
                                       int32_t T, int32_t C, int32_t G, int32_t cp, int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(dh && dxc && dx && delta >= 1, "posconv_unpack_bwd: null pointer");
-  const long long total = (long long)B * T * C;
-  FHB_CUDA_CHECK(fhb_launch(posconv_unpack_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(dh), static_cast<const __nv_bfloat16*>(dxc), valid,
-      static_cast<__nv_bfloat16*>(dx), T, C, G, cp, total, delta));
-  FHB_LAUNCH_CHECK();
+  FHB_ARG_CHECK(C % G == 0 && (C / G) % 2 == 0, "posconv_unpack_bwd: the group width must be even");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cg = C / G;
+  const __nv_bfloat16 *a = static_cast<const __nv_bfloat16*>(dh), *b = static_cast<const __nv_bfloat16*>(dxc);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dx);
+  if (cg % 8 == 0) {
+    const long long total = (long long)B * T * C / 8;
+    FHB_CUDA_CHECK(fhb_launch(posconv_unpack_bwd_kernel<8>, dim3(grid_for(total)), dim3(256), 0, s, a, b, valid, o, T, C, G, cp, total, delta));
+  } else {
+    const long long total = (long long)B * T * C / 2;
+    FHB_CUDA_CHECK(fhb_launch(posconv_unpack_bwd_kernel<2>, dim3(grid_for(total)), dim3(256), 0, s, a, b, valid, o, T, C, G, cp, total, delta));
+  }
   return 0;
 }
 
@@ -352,8 +578,7 @@ extern "C" int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float*
                                   float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate,
                                   int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(dwt && v && g && inv_norm && dv && dg && delta >= 1, "posconv_wn_bwd: null pointer");
-  FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel, dim3(K), dim3(256), 0, static_cast<cudaStream_t>(stream), dwt, v, g, inv_norm, dv, dg, C, G, K, cp,
-                                                                        accumulate, delta));
-  FHB_LAUNCH_CHECK();
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel, dim3(K), dim3(1024), 0, static_cast<cudaStream_t>(stream), dwt, v, g,
+                            inv_norm, dv, dg, C, G, K, cp, accumulate, delta));
   return 0;
 }

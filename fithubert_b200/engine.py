@@ -155,7 +155,7 @@ class WeightSet:
         nf = sum(math.prod(d) for (_, t, d, _) in spec if t == f32)
         pc = g.G * g.pdelta * g.cp * g.kpx * g.cp
         self.buf16 = torch.empty(round_up(nb, 64) + 64 * len(spec) + 2 * round_up(pc, 64) + 128, device=self.device, dtype=bf16)
-        self.buf32 = torch.empty(nf + 8 * len(spec) + g.kpos + 64, device=self.device, dtype=f32)
+        self.buf32 = torch.empty(nf + 8 * len(spec) + 2 * g.kpos + 64, device=self.device, dtype=f32)
         o16 = o32 = 0
         for (name, t, dims, _) in spec:
             n = math.prod(dims)
@@ -170,7 +170,8 @@ class WeightSet:
         self.views["pc.wt"] = self.buf16[o16:o16 + pc]
         self.views["pc.w"].zero_()   # the blocked layout keeps structural zeros the prep kernel never touches
         self.views["pc.wt"].zero_()
-        self.views["pc.inv"] = self.buf32[o32:o32 + g.kpos]
+        self.views["pc.ws"] = self.buf32[o32:o32 + 2 * g.kpos]   # [sum of squares | 1 / norm] per tap
+        self.views["pc.inv"] = self.views["pc.ws"][g.kpos:]
 
     def __getitem__(self, name):
         return self.views[name]
@@ -226,9 +227,8 @@ class WeightSet:
         K.prep_multi(self._table, self._n_entries, self._max_n)
         g = self.g
         v, gn = self.params["encoder.pos_conv.0.weight_v"], self.params["encoder.pos_conv.0.weight_g"]
-        K.posconv_wn_prep(v, gn, self.views["pc.w"], self.views["pc.inv"], g.E, g.G, g.kpos, g.cp, 0, g.pdelta)
-        if self.train:
-            K.posconv_wn_prep(v, gn, self.views["pc.wt"], None, g.E, g.G, g.kpos, g.cp, 1, g.pdelta)
+        K.posconv_wn_prep(v, gn, self.views["pc.w"], self.views["pc.wt"] if self.train else None, self.views["pc.ws"],
+                          g.E, g.G, g.kpos, g.cp, g.pdelta)
         self._sig = sig
 
 

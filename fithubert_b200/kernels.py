@@ -205,9 +205,10 @@ def posconv_pack(x, valid, xg, B, T, Cd, G, cp, pad_l, Tp):
             "fhb_posconv_pack")
 
 
-def posconv_wn_prep(v, g, w_out, inv_norm, Cd, G, Kt, cp, flip_transpose, delta=1):
-    L.check(L.lib().fhb_posconv_wn_prep(L.ptr(v), L.ptr(g), L.ptr(w_out), L.ptr(inv_norm), Cd, G, Kt, cp,
-                                        int(flip_transpose), delta, L.stream_ptr()), "fhb_posconv_wn_prep")
+def posconv_wn_prep(v, g, w_fwd, w_bwd, ws, Cd, G, Kt, cp, delta=1):
+    """ws: fp32 [2 * Kt] workspace; ws[Kt:] receives 1 / ||v[:, :, j]|| (posconv_wn_bwd's inv_norm)."""
+    L.check(L.lib().fhb_posconv_wn_prep(L.ptr(v), L.ptr(g), L.ptr(w_fwd), L.ptr(w_bwd), L.ptr(ws), Cd, G, Kt, cp, delta,
+                                        L.stream_ptr()), "fhb_posconv_wn_prep")
 
 
 def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5, delta=1):

@@ -109,7 +109,7 @@ EXPORTS = [
 
 
 CALLS: dict = {}
-_KERNELS_PER_CALL = {"fhb_conv0_gn_gelu_fwd": 3, "fhb_conv0_gn_gelu_bwd": 2, "fhb_attn_bwd": 3}
+_KERNELS_PER_CALL = {"fhb_conv0_gn_gelu_fwd": 3, "fhb_conv0_gn_gelu_bwd": 2, "fhb_attn_bwd": 3, "fhb_posconv_wn_prep": 2}
 
 
 def reset_counters() -> None:

@@ -152,8 +152,11 @@ int fhb_layernorm_bwd(const void* dy, const void* dy2 /* optional: gradient = dy
  * [b][ceil(T / delta)][g][delta][cp] (what finish_fwd / finish_bwd / unpack_bwd index when given delta). */
 int fhb_posconv_pack(const void* x, const int32_t* valid, void* xg, int32_t B, int32_t T, int32_t C, int32_t G,
                      int32_t cp, int32_t pad_l, int32_t Tp, fhb_stream_t stream);
-int fhb_posconv_wn_prep(const float* v, const float* g, void* w_out, float* inv_norm, int32_t C, int32_t G,
-                        int32_t K, int32_t cp, int32_t flip_transpose, int32_t delta, fhb_stream_t stream);
+/* wn_prep writes the forward operand w_fwd = W[g][co][(j, ci)] and (if non-NULL) the dgrad operand
+ * w_bwd = W[g][ci][(K - 1 - j, co)] in one call.  ws: 2*K floats of workspace; on return ws[K..2K) holds
+ * 1 / ||v[:, :, j]|| (the inv_norm argument of fhb_posconv_wn_bwd).  Group width C / G must be even, K | 256. */
+int fhb_posconv_wn_prep(const float* v, const float* g, void* w_fwd, void* w_bwd, float* ws, int32_t C, int32_t G,
+                        int32_t K, int32_t cp, int32_t delta, fhb_stream_t stream);
 int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const void* conv, const float* bias,
                            const float* gamma, const float* beta, void* h_out, void* y, float* mean, float* rstd,
                            int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps, int32_t delta,

@@ -426,6 +426,49 @@ def test_model_matches_reference_fixture(F, path):
         assert rel(p.grad, ref) < GTOL, n
 
 
+def test_oracle_parity_fithubert_group_geometry(F):
+    """Seeded oracle comparison at FitHuBERT's own positional-conv geometry (30 channels per group -> 4-byte
+    vector path, cp = 32, time-blocked GEMM) and head dim 40 (tcgen05 attention), which the reference fixtures
+    (24 / 16 channels per group) do not reach: hidden states, loss and every parameter gradient."""
+    from fithubert_b200.autograd import _DistillLossFn
+    s_over = dict(conv_feature_layers="[(16, 10, 5)] + [(32, 1, 1)] + [(32, 3, 2)] * 4 + [(64, 1, 1)] + [(64, 2, 2)] * 2",
+                  encoder_layers=2, encoder_embed_dim=240, encoder_ffn_embed_dim=240, encoder_attention_heads=6,
+                  conv_pos=128, conv_pos_groups=8, pred_head_final_dim=64)
+    t_over = dict(conv_feature_layers="[(32,10,5)] + [(32,3,2)] * 4 + [(32,2,2)] * 2", encoder_layers=2,
+                  encoder_embed_dim=64, encoder_ffn_embed_dim=128, encoder_attention_heads=4, conv_pos=16,
+                  conv_pos_groups=4)
+    scfg, tcfg = O.student_config(**s_over), O.teacher_config(**t_over)
+    ssd, tsd = O.init_student_state(scfg, 3, perturb=True), O.init_teacher_state(tcfg, 4, perturb=True)
+    x, pm = O.synth_batch(3, 12000, [12000, 9100, 7000], seed=11)
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+    with torch.no_grad():
+        t_ref = O.teacher_forward(tsd, tcfg, x, pm)
+    s_ref = O.student_forward(ref_sd, scfg, x, pm)
+    w = O.layer_weights(2, 0.1)
+    loss_ref, _ = O.distill_loss(s_ref["projections"], t_ref["layer_results"], w)
+    loss_ref.backward()
+    teacher = F.TeacherModel(kind="hubert", **t_over)
+    teacher.load_state_dict(tsd)
+    teacher = F.TeacherWrapper(teacher.cuda())
+    student = F.CustomStudentModel(full_student_cfg(F, dict(s_over, pred_layer_id="[1]")))
+    student.load_state_dict(ssd)
+    student = student.cuda().eval()
+    assert student._geom.cg == 30 and student._geom.cp == 32 and student._geom.d == 40
+    tr = teacher.extract_features(x.cuda(), pm)
+    sr = student(x.cuda(), pm)
+    assert torch.equal(sr["padding_mask"].cpu(), s_ref["padding_mask"])
+    for i in range(2):
+        assert rel(sr["layer_results"][i][0], s_ref["layer_results"][i][0]) < TOL
+        assert rel(sr["projections"][i], s_ref["projections"][i]) < TOL
+    loss, _ = _DistillLossFn.apply(sr["projections"][0]._base, tr["_stacked"], torch.tensor(w, device="cuda"), 0)
+    assert abs(float(loss) - float(loss_ref)) < 1e-2 * float(loss_ref)
+    loss.backward()
+    for n, p in student.named_parameters():
+        if p.grad is None or ref_sd[n].grad is None or ref_sd[n].grad.abs().max() < 1e-8:
+            continue
+        assert rel(p.grad, ref_sd[n].grad) < 6e-2, n
+
+
 def test_fused_step_equals_autograd_path_and_updates_weights(F):
     """W2V2Distil.training_step (fused, no autograd) vs the autograd-facing path on the same batch, then one
     optimizer step vs the oracle's AdamW restatement."""
