@@ -81,7 +81,15 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 // dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)),  dxhat = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; optionally dxsum += sum_rows dx (the bias gradient of
 // the linear layer that produced x: saves a separate column-sum pass over dx).
-// Per-lane register partials -> block smem -> one atomic per column per block.  NV = 16-byte vectors per lane.
+// Column partial sums live in a per-warp shared-memory slab [NS][C] (every lane owns its columns: plain
+// read-modify-writes; shared float atomics would be CAS spin loops), folded across the warps at the end: one
+// global atomic per column per block.  All 16-byte loads of a row are issued before the first use.
+// NV = 16-byte vectors per lane.
+__device__ __forceinline__ void cvt8(const uint4& u, float* f) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 template <int NV, bool DXSUM>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
@@ -91,23 +99,29 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      __nv_bfloat16* __restrict__ dx_drop, uint32_t drop_seed, uint32_t drop_thr, float drop_scale,
                      long long rows, int C) {
   pdl_sync();
-  extern __shared__ float sred[];  // [warps][NS][C]: per-warp column partials (no shared-memory float atomics:
-                                   // they compile to CAS spin loops and eight warps collide on every column)
+  extern __shared__ float sred[];  // [warps][NS][C]
+  constexpr int NS = DXSUM ? 3 : 2;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = C >> 3;
-  float pg[NV][8], pb[NV][8], pd[DXSUM ? NV : 1][8];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      pg[i][j] = 0.f;
-      pb[i][j] = 0.f;
-      if (DXSUM) pd[i][j] = 0.f;
-    }
-  }
+  float* mine = sred + (threadIdx.x >> 5) * NS * C;
+  for (int i = lane; i < NS * C; i += 32) mine[i] = 0.f;
+  __syncwarp();
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   for (long long row = warp_global; row < rows; row += nwarps) {
+    uint4 rx[NV], rd[NV], rd2[NV], rr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      rx[i] = rd[i] = rd2[i] = rr[i] = zero4;
+      if (vi < nvec) {
+        rx[i] = *reinterpret_cast<const uint4*>(x + row * C + vi * 8);
+        rd[i] = *reinterpret_cast<const uint4*>(dy + row * C + vi * 8);
+        if (dy2) rd2[i] = *reinterpret_cast<const uint4*>(dy2 + row * C + vi * 8);
+        if (dres) rr[i] = *reinterpret_cast<const uint4*>(dres + row * C + vi * 8);
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
     float xh[NV][8], dxh[NV][8];
     float s1 = 0.f, s2 = 0.f;
@@ -115,26 +129,28 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        load8(x + row * C + vi * 8, xh[i]);
-        load8(dy + row * C + vi * 8, dxh[i]);
+        cvt8(rx[i], xh[i]);
+        cvt8(rd[i], dxh[i]);
         if (dy2) {  // two gradient streams meet here (layer above + this layer's projection head)
           float t2[8];
-          load8(dy2 + row * C + vi * 8, t2);
+          cvt8(rd2[i], t2);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dxh[i][j] += t2[j];
         }
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)),
                      g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float* mg = mine + vi;       // slab layout [NS][8][nvec]: lanes hit consecutive banks
+        float* mb = mine + C + vi;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xh[i][j] - mu) * rs;
           const float d = dxh[i][j];
-          pg[i][j] += d * xh[i][j];
-          pb[i][j] += d;
+          mg[j * nvec] = fmaf(d, xh[i][j], mg[j * nvec]);
+          mb[j * nvec] += d;
           dxh[i][j] = d * g[j];
           s1 += dxh[i][j];
-          s2 += dxh[i][j] * xh[i][j];
+          s2 = fmaf(dxh[i][j], xh[i][j], s2);
         }
       }
     }
@@ -145,12 +161,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         float o[8];
-        if (dres) load8(dres + row * C + vi * 8, o);
+        cvt8(rr[i], o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = rs * (dxh[i][j] - s1 - xh[i][j] * s2);
-          o[j] = dres ? o[j] + d : d;
-        }
+        for (int j = 0; j < 8; ++j) o[j] += rs * (dxh[i][j] - s1 - xh[i][j] * s2);
         store8(dx + row * C + vi * 8, o);
         if (dx_drop) {
           // gradient through nn.Dropout on the branch that produced x (residual + dropout(branch)): the masked
@@ -166,38 +179,21 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           store8(dx_drop + row * C + vi * 8, o);
         }
         if (DXSUM) {
+          float* md = mine + 2 * C + vi;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pd[i][j] += o[j];
+          for (int j = 0; j < 8; ++j) md[j * nvec] += o[j];
         }
-      }
-    }
-  }
-  constexpr int NS = DXSUM ? 3 : 2;
-  float* mine = sred + (threadIdx.x >> 5) * NS * C;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
-      float4* g4 = reinterpret_cast<float4*>(mine + vi * 8);
-      float4* b4 = reinterpret_cast<float4*>(mine + C + vi * 8);
-      g4[0] = make_float4(pg[i][0], pg[i][1], pg[i][2], pg[i][3]);
-      g4[1] = make_float4(pg[i][4], pg[i][5], pg[i][6], pg[i][7]);
-      b4[0] = make_float4(pb[i][0], pb[i][1], pb[i][2], pb[i][3]);
-      b4[1] = make_float4(pb[i][4], pb[i][5], pb[i][6], pb[i][7]);
-      if (DXSUM) {
-        float4* d4 = reinterpret_cast<float4*>(mine + 2 * C + vi * 8);
-        d4[0] = make_float4(pd[i][0], pd[i][1], pd[i][2], pd[i][3]);
-        d4[1] = make_float4(pd[i][4], pd[i][5], pd[i][6], pd[i][7]);
       }
     }
   }
   __syncthreads();
   const int nw = blockDim.x >> 5;
   for (int i = threadIdx.x; i < NS * C; i += blockDim.x) {
+    const int ns = i / C, c = i - ns * C;
+    const int slot = ns * C + (c & 7) * nvec + (c >> 3);
     float t = 0.f;
-    for (int w = 0; w < nw; ++w) t += sred[w * NS * C + i];
-    float* dst = i < C ? dgamma + i : (i < 2 * C ? dbeta + (i - C) : dxsum + (i - 2 * C));
-    atomicAdd(dst, t);
+    for (int w = 0; w < nw; ++w) t += sred[w * NS * C + slot];
+    atomicAdd((ns == 0 ? dgamma : (ns == 1 ? dbeta : dxsum)) + c, t);
   }
 }
 
@@ -232,7 +228,7 @@ extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x,
   FHB_ARG_CHECK(!dx_drop || (drop_p >= 0.f && drop_p < 1.f && rows * C < (1LL << 32)), "layernorm_bwd: bad dropout arguments");
   FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_bwd: bad C=%d", C);
   if (rows == 0) return 0;
-  // ~2 blocks per SM (register-limited), every warp streams several rows
+  // 2 blocks per SM (register-limited), every warp streams several rows
   long long blocks = (rows + 15) / 16;
   if (blocks > 2LL * fhb_num_sms()) blocks = 2LL * fhb_num_sms();
   const int nv = (C / 8 + 31) / 32;

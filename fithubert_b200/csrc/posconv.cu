@@ -43,6 +43,33 @@ __device__ __forceinline__ void ldf(const float* p, float* f) {
   }
 }
 
+// raw (unconverted) vector loads: issuing every load of a row into its own registers before the first use keeps
+// them all in flight (the compiler otherwise recycles one destination register and serialises the row on L2 latency)
+template <int VEC>
+struct RawVec {
+  uint32_t w[VEC / 2];
+};
+template <int VEC>
+__device__ __forceinline__ RawVec<VEC> ldraw(const __nv_bfloat16* p) {
+  RawVec<VEC> r;
+  if constexpr (VEC == 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    r.w[0] = u.x; r.w[1] = u.y; r.w[2] = u.z; r.w[3] = u.w;
+  } else {
+    r.w[0] = *reinterpret_cast<const uint32_t*>(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void cvtraw(const RawVec<VEC>& r, float* f) {
+#pragma unroll
+  for (int j = 0; j < VEC / 2; ++j) {
+    const float2 t = unpack_bf16(r.w[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
 // xg[b][g][tp][c'] = x[b][tp - pad_l][g*cg + c'] if 0 <= tp - pad_l < valid[b] and c' < cg else 0.
 // One thread per 16-byte output chunk (8 channels); the source is read as one 16-byte word (cg % 8 == 0, VEC = 8)
 // or as 32-bit words (cg even, VEC = 2: FitHuBERT's 30 channels per group start on 4-byte boundaries only).
@@ -182,6 +209,17 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
     const bool live = valid ? t < valid[b] : true;
     // conv GEMM output layout: [b][r = t / delta][g][dl = t % delta][cp]
     const __nv_bfloat16* cbase = conv + (((long long)b * R + t / delta) * G * delta + (t % delta)) * cp;
+    RawVec<VEC> rx[NV], rc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (coff[i] >= 0) {
+        const int c = (lane + 32 * i) * VEC;
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) rx[i].w[j] = 0u;
+        if (live) rx[i] = ldraw<VEC>(x + row * C + c);
+        rc[i] = ldraw<VEC>(cbase + coff[i]);
+      }
+    }
     float hv[NV][VEC];
     float s = 0.f;
 #pragma unroll
@@ -189,13 +227,8 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
       if (coff[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
         float xv[VEC], cv[VEC], bv[VEC];
-        if (live) {
-          ldv<VEC>(x + row * C + c, xv);
-        } else {
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) xv[j] = 0.f;
-        }
-        ldv<VEC>(cbase + coff[i], cv);
+        cvtraw<VEC>(rx[i], xv);
+        cvtraw<VEC>(rc[i], cv);
         ldf<VEC>(bias + c, bv);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -239,8 +272,10 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
 
 // Backward of the above.  dh = LNbwd(dy); dconv = dh * gelu'(conv + bias) written group-major, time-padded:
 // dcg[b][g][t + pad_l][cc] (pad channels written as 0); dgamma/dbeta/dbias accumulated atomically.
+// Column partial sums live in a per-warp shared-memory slab [3][C] (each lane owns its columns: plain
+// read-modify-writes, no atomics), which keeps the register budget at two blocks per SM.
 template <int VEC, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
                           const __nv_bfloat16* __restrict__ conv, const float* __restrict__ bias,
                           const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -249,22 +284,21 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
                           float* __restrict__ dbias, int B, int T, int C, int G, int cp, int pad_l, int Tp,
                           int rows_per_warp, int delta) {
   pdl_sync();
-  extern __shared__ float sred[];  // [warps][3][C] per-warp column partials (shared float atomics are CAS spin loops)
+  extern __shared__ float sred[];  // [warps][3][C]
   const int lane = threadIdx.x & 31;
   const int cg = C / G;
   const int R = (T + delta - 1) / delta;
   const long long rows = (long long)B * T;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int coff[NV], goff[NV];  // conv-row offset and dcg offset (g * Tp * cp + cc) of this lane's vectors
-  float pg[NV][VEC], pb[NV][VEC], pc[NV][VEC];
+  float* mine = sred + (threadIdx.x >> 5) * 3 * C;
+  for (int i = lane; i < 3 * C; i += 32) mine[i] = 0.f;
+  __syncwarp();
+  int gcc[NV];  // (group << 16) | channel-in-group of this lane's i-th vector; -1: beyond C
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * VEC;
-    const int g = c / cg, cc = c - g * cg;
-    coff[i] = c < C ? g * delta * cp + cc : -1;
-    goff[i] = g * Tp * cp + cc;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) pg[i][j] = pb[i][j] = pc[i][j] = 0.f;
+    const int g = c / cg;
+    gcc[i] = c < C ? ((g << 16) | (c - g * cg)) : -1;
   }
   const int npad = G * (cp - cg) / 2;  // zero pad channel PAIRS per row (cp, cg even)
   for (int rr = 0; rr < rows_per_warp; ++rr) {
@@ -274,21 +308,31 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     const __nv_bfloat16* cbase = conv + (((long long)b * R + t / delta) * G * delta + (t % delta)) * cp;
     __nv_bfloat16* dbase = dcg + ((long long)b * G * Tp + t + pad_l) * cp;
     const float mu = mean[row], rs = rstd[row];
+    RawVec<VEC> rh[NV], rd[NV], rc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (gcc[i] >= 0) {
+        const int c = (lane + 32 * i) * VEC;
+        rh[i] = ldraw<VEC>(h + row * C + c);
+        rd[i] = ldraw<VEC>(dy + row * C + c);
+        rc[i] = ldraw<VEC>(cbase + (gcc[i] >> 16) * delta * cp + (gcc[i] & 0xFFFF));
+      }
+    }
     float xh[NV][VEC], dv[NV][VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (coff[i] >= 0) {
+      if (gcc[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
         float gv[VEC];
-        ldv<VEC>(h + row * C + c, xh[i]);
-        ldv<VEC>(dy + row * C + c, dv[i]);
+        cvtraw<VEC>(rh[i], xh[i]);
+        cvtraw<VEC>(rd[i], dv[i]);
         ldf<VEC>(gamma + c, gv);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           xh[i][j] = (xh[i][j] - mu) * rs;
-          pg[i][j] = fmaf(dv[i][j], xh[i][j], pg[i][j]);
-          pb[i][j] += dv[i][j];
+          mine[c + j] = fmaf(dv[i][j], xh[i][j], mine[c + j]);
+          mine[C + c + j] += dv[i][j];
           dv[i][j] *= gv[j];  // dxhat
           s1 += dv[i][j];
           s2 = fmaf(dv[i][j], xh[i][j], s2);
@@ -299,39 +343,25 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     s2 = warp_sum(s2) / (float)C;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (coff[i] >= 0) {
+      if (gcc[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
         float cv[VEC], bv[VEC], d[VEC], dc[VEC];
-        ldv<VEC>(cbase + coff[i], cv);
+        cvtraw<VEC>(rc[i], cv);
         ldf<VEC>(bias + c, bv);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           d[j] = rs * (dv[i][j] - s1 - xh[i][j] * s2);
           dc[j] = d[j] * gelu_erf_grad(cv[j] + bv[j]);
+          mine[2 * C + c + j] += dc[j];
         }
         stv<VEC>(dh + row * C + c, d);
-        stv<VEC>(dbase + goff[i], dc);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) pc[i][j] += dc[j];
+        stv<VEC>(dbase + (long long)(gcc[i] >> 16) * Tp * cp + (gcc[i] & 0xFFFF), dc);
       }
     }
     // channel padding cg..cp-1 of every group: must read as zero in the dgrad GEMM (0-weight x garbage = NaN)
     for (int i = lane; i < npad; i += 32) {
       const int g = i / ((cp - cg) / 2), cc = cg + 2 * (i % ((cp - cg) / 2));
       *reinterpret_cast<uint32_t*>(dbase + (long long)g * Tp * cp + cc) = 0u;
-    }
-  }
-  float* mine = sred + (threadIdx.x >> 5) * 3 * C;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (coff[i] >= 0) {
-      const int c = (lane + 32 * i) * VEC;
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        mine[c + j] = pg[i][j];
-        mine[C + c + j] = pb[i][j];
-        mine[2 * C + c + j] = pc[i][j];
-      }
     }
   }
   __syncthreads();
