@@ -15,6 +15,9 @@ def __getattr__(name):  # lazy: importing the package must not need CUDA
     if name in ("UpstreamExpert", "fithubert"):
         from . import expert
         return getattr(expert, name)
+    if name in ("load_fairseq_teacher", "load_student_state_dict", "load_checkpoint_to_cpu", "student_checkpoint"):
+        from . import checkpoint
+        return getattr(checkpoint, name)
     if name in ("FusedAdamW", "GradAllReduce", "warmup_linear"):
         from . import optim
         return getattr(optim, name)

@@ -25,21 +25,21 @@ bf16 = torch.bfloat16
 
 
 def load_model_and_config(teacher_model: str, device=None):
-    """Reference utils/utils.py:102-149 loads a fairseq checkpoint.  fairseq pickles cannot be read
-    without fairseq (a 'next' row); here the name selects the architecture and weights are
-    random-init (BASELINE.json: 'random-init teacher'), or a plain state-dict file is loaded if it
-    exists and is one."""
-    kind = "wav2vec2" if ("wav2vec" in teacher_model or "w2v" in teacher_model) else "hubert"
-    model = TeacherModel(kind=kind)
-    try:
-        state = torch.load(teacher_model, map_location="cpu")
-        sd = state.get("model", state)
-        model.load_state_dict({k: v for k, v in sd.items() if k in model.state_dict()}, strict=False)
-    except (FileNotFoundError, OSError, AttributeError, RuntimeError, ModuleNotFoundError, ImportError):
-        pass
+    """Reference utils/utils.py:102-149: (TeacherWrapper, model_cfg, task_agnostic).  An existing file is read as a
+    fairseq checkpoint WITHOUT fairseq (checkpoint.load_fairseq_teacher: tolerant unpickler + the reference's own
+    parameter names) and must supply every teacher tensor.  A name that is not a file selects the architecture
+    (HuBERT-Base / wav2vec 2.0-Base) with random-init weights - the BASELINE.json benchmark configuration, where
+    no checkpoint can be downloaded."""
+    import os
+    if isinstance(teacher_model, str) and os.path.isfile(teacher_model):
+        from .checkpoint import load_fairseq_teacher
+        model, _, model_cfg = load_fairseq_teacher(teacher_model)
+    else:
+        kind = "wav2vec2" if ("wav2vec" in str(teacher_model) or "w2v" in str(teacher_model)) else "hubert"
+        model, model_cfg = TeacherModel(kind=kind), None
     if device is not None:
         model = model.to(device)
-    return TeacherWrapper(model), None, True
+    return TeacherWrapper(model), model_cfg, True
 
 
 class W2V2Distil(nn.Module):

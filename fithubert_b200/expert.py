@@ -1,8 +1,6 @@
 """s3prl upstream plug-in, same surface as reference fithubert/expert.py:9-75 and hubconf.py:3-13."""
 from __future__ import annotations
 
-from collections import OrderedDict
-
 import torch
 import torch.nn as nn
 import yaml
@@ -26,9 +24,10 @@ class UpstreamExpert(nn.Module):
         self.model_config = CustomStudentModelConfig(**model_config)
         self.model = CustomStudentModel(self.model_config)
         if ckpt is not None:
-            state = torch.load(ckpt, map_location="cpu") if not isinstance(ckpt, dict) else ckpt
-            state_dict = OrderedDict({k[14:]: v for k, v in state["state_dict"].items() if "student_model" in k})
-            self.model.load_state_dict(state_dict)
+            # Lightning checkpoint (or an already loaded dict): keys under `student_model.` with the prefix cut,
+            # read without pytorch_lightning installed (checkpoint.py)
+            from .checkpoint import load_student_state_dict
+            self.model.load_state_dict(load_student_state_dict(ckpt))
         self.model._disable_projection_heads()
 
     def get_downsample_rates(self, key: str):
