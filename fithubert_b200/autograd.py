@@ -39,30 +39,46 @@ def student_apply(model, source, valid):
 
 
 class _DistillLossFn(torch.autograd.Function):
-    """Fused K10: per-layer weighted MSE/L1 between projections and teacher layers + d(loss)/d(pred)
-    in one pass (reference train.py:250-293)."""
+    """Fused K10: per-layer weighted MSE/L1 (+ optional cosine, train.py:302-314) between projections and teacher
+    layers + d(loss)/d(pred) in one pass (reference train.py:250-314).
+    apply(preds, tgt, weights, loss_type[, rec_weight=1, sim_weight=0]) -> (total, per-layer rec[, per-layer sim]);
+    total = rec_weight * sum(rec) + sim_weight * sum(sim)."""
 
     @staticmethod
-    def forward(ctx, preds, tgt, weights, loss_type):
-        from . import kernels as K
+    def forward(ctx, preds, tgt, weights, loss_type, *extra):
+        rec_weight, sim_weight = (tuple(extra) + (1.0, 0.0)[len(extra):])[:2]
         n, B, Tq, D = preds.shape
         Tt = tgt.shape[2]
-        layer_loss = torch.zeros(n, device=preds.device, dtype=torch.float32)
+        ctx.n_in = 4 + len(extra)
+        rec = torch.zeros(n, device=preds.device, dtype=torch.float32)
         dpred = torch.empty_like(preds)
-        K.distill_loss(preds, tgt, weights, layer_loss, dpred, n, B, Tq, Tt, D, loss_type, 1.0)
+        ctx.args = (preds, tgt, weights, n, B, Tq, Tt, D, loss_type, float(rec_weight), float(sim_weight))
+        sim = _run_loss(ctx.args, rec, dpred, 1.0)
         ctx.save_for_backward(dpred)
-        ctx.args = (preds, tgt, weights, n, B, Tq, Tt, D, loss_type)
-        ctx.mark_non_differentiable(layer_loss)
-        total = layer_loss.sum()  # 12-element reduction; the heavy lifting is the kernel above
-        return total, layer_loss
+        total = rec.sum() * rec_weight  # 12-element reductions; the heavy lifting is the kernel above
+        if sim is None:
+            ctx.mark_non_differentiable(rec)
+            return total, rec
+        ctx.mark_non_differentiable(rec, sim)
+        return total + sim.sum() * sim_weight, rec, sim
 
     @staticmethod
-    def backward(ctx, gtotal, _glayers):
-        from . import kernels as K
+    def backward(ctx, gtotal, *_glayers):
         (dpred,) = ctx.saved_tensors
         scale = float(gtotal)  # one scalar D2H; 1.0 unless the caller rescales the loss (grad accumulation)
         if scale != 1.0:
-            preds, tgt, weights, n, B, Tq, Tt, D, loss_type = ctx.args
-            scratch = torch.zeros(n, device=preds.device, dtype=torch.float32)
-            K.distill_loss(preds, tgt, weights, scratch, dpred, n, B, Tq, Tt, D, loss_type, scale)
-        return dpred, None, None, None
+            scratch = torch.zeros(ctx.args[3], device=dpred.device, dtype=torch.float32)
+            _run_loss(ctx.args, scratch, dpred, scale)
+        return (dpred,) + (None,) * (ctx.n_in - 1)
+
+
+def _run_loss(args, rec, dpred, scale):
+    """Launch the loss kernel; returns the per-layer cosine term (or None when sim_weight == 0)."""
+    from . import kernels as K
+    preds, tgt, weights, n, B, Tq, Tt, D, loss_type, rec_w, sim_w = args
+    if not sim_w:
+        K.distill_loss(preds, tgt, weights, rec, dpred, n, B, Tq, Tt, D, loss_type, scale * rec_w)
+        return None
+    sim = torch.zeros(n, device=preds.device, dtype=torch.float32)
+    K.distill_loss_sim(preds, tgt, weights, rec, sim, dpred, n, B, Tq, Tt, D, loss_type, scale * rec_w, scale * sim_w)
+    return sim

@@ -82,6 +82,146 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------ K10b reconstruction + cosine-similarity loss
+// Reference train.py:282-314 with sim_loss_weight > 0 (the `distil_random_layer == 0` branch - the other one
+// indexes a 3-D tensor with dim 3 and cannot run): per row r = (layer, b, t) of D features
+//   rec = sum_d (p - q)^2 or |p - q|,   c = p.q / (max(|p|, eps) max(|q|, eps)),   sim = -logsigmoid(c)
+//   dpred = gr * d rec/dp + gs * (-sigmoid(-c)) * (q / (|p||q|) - c p / |p|^2)
+// Warp per row (16-byte vectors, NV per lane), rows dealt round-robin to the warps of blockIdx.y's layer; each
+// lane owns fixed columns so the column sums of the gradient (bias gradient of the head's Linear) stay in
+// registers until the block folds them through shared memory.
+template <int NV>
+__global__ void __launch_bounds__(256)
+distill_loss_sim_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16* __restrict__ tgt,
+                        const float* __restrict__ weights, float* __restrict__ rec_loss, float* __restrict__ sim_loss,
+                        __nv_bfloat16* __restrict__ dpred, float* __restrict__ dbias, long long dbias_stride, int B,
+                        int Tp, int Tt, int D, int loss_type, float rec_grad_scale, float sim_grad_scale) {
+  pdl_sync();
+  extern __shared__ float csum[];  // [warps][D] (only when dbias)
+  const int l = blockIdx.y;
+  const float w = weights[l];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  const long long rows = (long long)B * Tp;
+  const float inv_rows = 1.0f / (float)rows, inv_elems = inv_rows / (float)D;
+  const float gr = rec_grad_scale * w * inv_elems * (loss_type == 0 ? 2.f : 1.f);
+  const float gs = sim_grad_scale * w * inv_rows;
+  const __nv_bfloat16* pl = pred + (long long)l * rows * D;
+  const __nv_bfloat16* tl = tgt + (long long)l * B * Tt * D;
+  __nv_bfloat16* dl = dpred ? dpred + (long long)l * rows * D : nullptr;
+  float cs[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[i][j] = 0.f;
+  float acc_rec = 0.f, acc_sim = 0.f;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
+    const int b = (int)(r / Tp), t = (int)(r - (long long)b * Tp);
+    const __nv_bfloat16* pr = pl + r * D;
+    const __nv_bfloat16* qr = tl + ((long long)b * Tt + t) * D;
+    uint4 pu[NV], qu[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      pu[i] = qu[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (vi < nvec) {
+        pu[i] = *reinterpret_cast<const uint4*>(pr + vi * 8);
+        qu[i] = __ldg(reinterpret_cast<const uint4*>(qr + vi * 8));
+      }
+    }
+    float p[NV][8], q[NV][8];
+    float dot = 0.f, pp = 0.f, qq = 0.f, rec = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t pa[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w}, qa[4] = {qu[i].x, qu[i].y, qu[i].z, qu[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(pa[j]), c = unpack_bf16(qa[j]);
+        p[i][2 * j] = a.x; p[i][2 * j + 1] = a.y;
+        q[i][2 * j] = c.x; q[i][2 * j + 1] = c.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dot = fmaf(p[i][j], q[i][j], dot);
+        pp = fmaf(p[i][j], p[i][j], pp);
+        qq = fmaf(q[i][j], q[i][j], qq);
+        const float d = p[i][j] - q[i][j];
+        rec += loss_type == 0 ? d * d : fabsf(d);
+      }
+    }
+    dot = warp_sum(dot);
+    pp = warp_sum(pp);
+    qq = warp_sum(qq);
+    rec = warp_sum(rec);
+    const float eps = 1e-8f;
+    const float np = fmaxf(sqrtf(pp), eps), nq = fmaxf(sqrtf(qq), eps);
+    const float c = dot / (np * nq);
+    // -logsigmoid(c) = softplus(-c), evaluated the overflow-safe way
+    const float sim = fmaxf(-c, 0.f) + log1pf(expf(-fabsf(c)));
+    const float dsim = -1.0f / (1.0f + expf(c));          // d sim / d c
+    const float k_q = gs * dsim / (np * nq);              // coefficient of q
+    const float k_p = sqrtf(pp) > eps ? -gs * dsim * c / (np * np) : 0.f;  // coefficient of p (0 in the clamped regime)
+    acc_rec += rec;
+    acc_sim += sim;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float g2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = p[i][2 * j + e], qv = q[i][2 * j + e];
+            const float d = pv - qv;
+            const float grec = loss_type == 0 ? gr * d : (d > 0.f ? gr : (d < 0.f ? -gr : 0.f));
+            g2[e] = grec + k_q * qv + k_p * pv;
+          }
+          o[j] = pack_bf16(g2[0], g2[1]);
+          const float2 gb = unpack_bf16(o[j]);  // sum what the downstream GEMMs will read
+          cs[i][2 * j] += gb.x;
+          cs[i][2 * j + 1] += gb.y;
+        }
+        if (dl) *reinterpret_cast<uint4*>(dl + r * D + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  __shared__ float red[2][8];
+  if (lane == 0) {  // acc_* are already warp-uniform (built from warp_sum results)
+    red[0][warp] = acc_rec;
+    red[1][warp] = acc_sim;
+  }
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) csum[warp * D + vi * 8 + j] = cs[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c2 = 0.f;
+    for (int i = 0; i < nw; ++i) {
+      a += red[0][i];
+      c2 += red[1][i];
+    }
+    atomicAdd(rec_loss + l, a * w * inv_elems);
+    atomicAdd(sim_loss + l, c2 * w * inv_rows);
+  }
+  if (dbias) {
+    float* db = dbias + (long long)l * dbias_stride;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float t2 = 0.f;
+      for (int w2 = 0; w2 < nw; ++w2) t2 += csum[w2 * D + i];
+      atomicAdd(db + i, t2);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ K11 AdamW over a tensor table
 struct AdamScalars {
   float lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale;
@@ -340,6 +480,33 @@ extern "C" int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const
       static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(tgt), weights, layer_loss,
       static_cast<__nv_bfloat16*>(dpred), dbias, dbias_layer_stride, B, Tp, Tt, D, loss_type, grad_scale));
   FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_distill_loss_sim_fwd_bwd(const void* pred, const void* tgt, const float* weights, float* rec_layer_loss,
+                                            float* sim_layer_loss, void* dpred, float* dbias, int64_t dbias_layer_stride,
+                                            int32_t n_layers, int32_t B, int32_t Tp, int32_t Tt, int32_t D,
+                                            int32_t loss_type, float rec_grad_scale, float sim_grad_scale,
+                                            fhb_stream_t stream) {
+  FHB_ARG_CHECK(pred && tgt && weights && rec_layer_loss && sim_layer_loss, "distill_loss_sim: null pointer");
+  FHB_ARG_CHECK(n_layers > 0 && B > 0 && Tp > 0 && Tt >= Tp && D > 0 && D % 8 == 0 && D <= 1024,
+                "distill_loss_sim: bad shape (layers=%d B=%d Tp=%d Tt=%d D=%d)", n_layers, B, Tp, Tt, D);
+  FHB_ARG_CHECK(loss_type == 0 || loss_type == 1, "rec_loss_type must be one of 'l1', 'mse'.");
+  FHB_ARG_CHECK(!dbias || dpred, "distill_loss_sim: dbias needs dpred");
+  const long long rows = (long long)B * Tp;
+  long long gx = (4LL * fhb_num_sms() + n_layers - 1) / n_layers;
+  if (gx > (rows + 7) / 8) gx = (rows + 7) / 8;
+  if (gx < 1) gx = 1;
+  const int nv = (D / 8 + 31) / 32;
+  const size_t smem = dbias ? 8 * (size_t)D * sizeof(float) : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define FHB_SIM(NV)                                                                                                    \
+  FHB_CUDA_CHECK(fhb_launch(distill_loss_sim_kernel<NV>, dim3((unsigned)gx, n_layers), dim3(256), smem, s,             \
+                            static_cast<const __nv_bfloat16*>(pred), static_cast<const __nv_bfloat16*>(tgt), weights, \
+                            rec_layer_loss, sim_layer_loss, static_cast<__nv_bfloat16*>(dpred), dbias,                 \
+                            (long long)dbias_layer_stride, B, Tp, Tt, D, loss_type, rec_grad_scale, sim_grad_scale))
+  if (nv <= 1) FHB_SIM(1); else if (nv == 2) FHB_SIM(2); else if (nv == 3) FHB_SIM(3); else FHB_SIM(4);
+#undef FHB_SIM
   return 0;
 }
 

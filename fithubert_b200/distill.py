@@ -64,10 +64,17 @@ class W2V2Distil(nn.Module):
         self.rec_loss_type, self.sim_loss_weight = t["rec_loss_type"], t["sim_loss_weight"]
         self.attn_loss_weight, self.v_rel_loss_weight = t["attn_loss_weight"], t["v_rel_loss_weight"]
         self.random_layer_weight = t["random_layer_weight"]
-        for name, w in (("cnn_loss_weight", self.cnn_loss_weight), ("sim_loss_weight", self.sim_loss_weight),
-                        ("attn_loss_weight", self.attn_loss_weight), ("v_rel_loss_weight", self.v_rel_loss_weight)):
+        for name, w in (("cnn_loss_weight", self.cnn_loss_weight), ("attn_loss_weight", self.attn_loss_weight),
+                        ("v_rel_loss_weight", self.v_rel_loss_weight)):
             if w:
                 raise NotImplementedError(f"{name} > 0 is outside the B200 hot path (SURVEY 2.1 / 8f)")
+        if self.sim_loss_weight and t["distil_random_layer"] > 0:
+            # train.py:304-306 reduces the 3-D cosine loss over dim 3 in this branch and cannot execute
+            raise NotImplementedError("sim_loss_weight > 0 needs distil_random_layer = 0 (the reference's random-layer "
+                                      "branch of the cosine loss, train.py:304-306, indexes a dimension that does not exist)")
+        if self.sim_loss_weight and not self.rec_loss_weight:
+            raise NotImplementedError("sim_loss_weight > 0 with rec_loss_weight = 0 reads `pred` before assignment "
+                                      "in the reference (train.py:249,303)")
         if self.rec_loss_type not in ("mse", "l1"):
             raise NotImplementedError("rec_loss_type must be one of 'l1', 'mse'.")
         if t.get("delete_projections"):
@@ -119,10 +126,16 @@ class W2V2Distil(nn.Module):
         if isinstance(student_results["projections"], list) and base._base is not None and \
                 base._base.shape[0] == len(student_results["projections"]):
             preds = base._base  # the engine's stacked [n, B, T', D] buffer: no copy
-        total, per_layer = _DistillLossFn.apply(preds, teacher_results["_stacked"], self.layer_weights,
-                                                0 if self.rec_loss_type == "mse" else 1)
+        lt = 0 if self.rec_loss_type == "mse" else 1
+        if self.sim_loss_weight:
+            total, rec, sim = _DistillLossFn.apply(preds, teacher_results["_stacked"], self.layer_weights, lt,
+                                                   float(self.rec_loss_weight), float(self.sim_loss_weight))
+            per_layer = rec + sim  # train.py:316 feat_loss = rec_layer_loss + sim_layer_loss (un-weighted sum)
+        else:
+            total, per_layer = _DistillLossFn.apply(preds, teacher_results["_stacked"], self.layer_weights, lt,
+                                                    float(self.rec_loss_weight))
         losses = self._loss_dict(per_layer)
-        return self.rec_loss_weight * total, losses
+        return total, losses
 
     def _loss_dict(self, per_layer: torch.Tensor) -> Dict[str, torch.Tensor]:
         losses = {}
@@ -148,7 +161,8 @@ class W2V2Distil(nn.Module):
 
     def fused_forward_backward(self, x, padding_mask=None, lengths: Optional[List[int]] = None, grad_scale=1.0):
         """teacher fwd + student fwd + loss + student bwd for one micro-batch.  Gradients accumulate in the
-        flat buffer.  Returns (total_loss [1] fp32 tensor on device, per-layer losses [n] fp32)."""
+        flat buffer.  Returns the per-layer loss contributions [n] fp32 on the device, already weighted
+        (rec_loss_weight * rec + sim_loss_weight * sim per layer): their sum is the step's total loss."""
         sm, tm = self.student_model, self.teacher_model.model
         dev = sm.post_extract_proj.weight.device
         x = x.to(dev, non_blocking=True).float().contiguous()
@@ -180,9 +194,18 @@ class W2V2Distil(nn.Module):
         # (batched heads only; the per-head fallback path computes its own column sums)
         fused = getattr(c, "heads_batched", False) and G.head_stride() is not None
         dcs = torch.zeros(n, D, device=dev, dtype=torch.float32) if fused else None
-        K.distill_loss(c.preds, tgt, self.layer_weights, layer_loss, c.preds, n, B, c.Tq, T, D,
-                       0 if self.rec_loss_type == "mse" else 1, grad_scale * self.rec_loss_weight,
-                       dbias=dcs, dbias_layer_stride=D if fused else 0)
+        lt = 0 if self.rec_loss_type == "mse" else 1
+        if self.sim_loss_weight:
+            sim_loss = torch.zeros(n, device=dev, dtype=torch.float32)
+            K.distill_loss_sim(c.preds, tgt, self.layer_weights, layer_loss, sim_loss, c.preds, n, B, c.Tq, T, D, lt,
+                               grad_scale * self.rec_loss_weight, grad_scale * self.sim_loss_weight,
+                               dbias=dcs, dbias_layer_stride=D if fused else 0)
+            layer_loss = layer_loss * self.rec_loss_weight + sim_loss * self.sim_loss_weight
+        else:
+            K.distill_loss(c.preds, tgt, self.layer_weights, layer_loss, c.preds, n, B, c.Tq, T, D, lt,
+                           grad_scale * self.rec_loss_weight, dbias=dcs, dbias_layer_stride=D if fused else 0)
+            if self.rec_loss_weight != 1.0:
+                layer_loss = layer_loss * self.rec_loss_weight
         E.student_backward(P, W, sm._geom, G, c, c.preds, dpred_colsum=dcs)
         return layer_loss
 
@@ -200,7 +223,7 @@ class W2V2Distil(nn.Module):
             self._micro = 0
             self.optimizer_step()
         self.last_layer_losses = layer_loss
-        return layer_loss.sum() * self.rec_loss_weight
+        return layer_loss.sum()
 
     def optimizer_step(self):
         _, _, G = self.student_model.engine_state(True)

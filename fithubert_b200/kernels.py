@@ -258,6 +258,16 @@ def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, 
                                              loss_type, _f(grad_scale), L.stream_ptr()), "fhb_distill_loss_fwd_bwd")
 
 
+def distill_loss_sim(pred, tgt, weights, rec_layer_loss, sim_layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0,
+                     rec_grad_scale=1.0, sim_grad_scale=1.0, dbias=None, dbias_layer_stride=0):
+    """Reconstruction (mse / l1) + cosine (-logsigmoid(cos)) hint loss and its gradient in one pass (train.py:282-314)."""
+    L.check(L.lib().fhb_distill_loss_sim_fwd_bwd(L.ptr(pred), L.ptr(tgt), L.ptr(weights), L.ptr(rec_layer_loss),
+                                                 L.ptr(sim_layer_loss), L.ptr(dpred), L.ptr(dbias),
+                                                 C.c_int64(dbias_layer_stride), n_layers, B, Tp, Tt, D, loss_type,
+                                                 _f(rec_grad_scale), _f(sim_grad_scale), L.stream_ptr()),
+            "fhb_distill_loss_sim_fwd_bwd")
+
+
 def adamw_multi(table, n_tensors, max_n, lr, beta1, beta2, eps, wd, step, mode=0, grad_scale=1.0):
     L.check(L.lib().fhb_adamw_multi(L.ptr(table), n_tensors, C.c_int64(max_n), _f(lr), _f(beta1), _f(beta2), _f(eps),
                                     _f(wd), step, mode, _f(grad_scale), L.stream_ptr()), "fhb_adamw_multi")

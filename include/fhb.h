@@ -206,6 +206,14 @@ int fhb_distill_loss_fwd_bwd(const void* pred, const void* tgt, const float* wei
                              void* dpred, float* dbias, int64_t dbias_layer_stride, int32_t n_layers, int32_t B,
                              int32_t Tp, int32_t Tt, int32_t D, int32_t loss_type /*0 mse, 1 l1*/, float grad_scale,
                              fhb_stream_t stream);
+/* Same with the cosine term of train.py:302-314 (sim_loss_weight > 0; only the `distil_random_layer == 0` branch of the
+ * reference can execute): per row of D features sim = -logsigmoid(cos(pred, tgt)), cos with F.cosine_similarity's
+ * per-norm eps = 1e-8.  rec_layer_loss[l] += w_l * mean_{b,t,d} rec, sim_layer_loss[l] += w_l * mean_{b,t} sim,
+ * dpred = rec_grad_scale * w_l * d mean(rec)/dp + sim_grad_scale * w_l * d mean(sim)/dp.  D <= 1024. */
+int fhb_distill_loss_sim_fwd_bwd(const void* pred, const void* tgt, const float* weights, float* rec_layer_loss,
+                                 float* sim_layer_loss, void* dpred, float* dbias, int64_t dbias_layer_stride,
+                                 int32_t n_layers, int32_t B, int32_t Tp, int32_t Tt, int32_t D, int32_t loss_type,
+                                 float rec_grad_scale, float sim_grad_scale, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ fused AdamW (K11)
  * ONE launch over a device-resident table of tensors.  Replaces s3prl get_optimizer ->

@@ -277,6 +277,31 @@ def distill_loss(projections: Sequence[Tensor], teacher_layer_results, weights: 
     return per_layer.sum(), per_layer
 
 
+def distill_loss_sim(projections: Sequence[Tensor], teacher_layer_results, pred_layer_id: Sequence[int],
+                     rec_loss_type: str = "l1", rec_loss_weight: float = 1.0,
+                     sim_loss_weight: float = 1.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """W2V2Distil.calculate_loss with the cosine term, `distil_random_layer == 0` branch:
+    train.py:268-281 (pred_layer_id selection), :282-288 (rec), :294-297 (plain means), :302-303,309-312 (cosine),
+    :316,322-324 (per-layer log = rec + sim), :372-378 (total).  The random-layer branch (:304-306) calls
+    `.mean((0, 2, 3))` on the 3-D cosine loss and cannot run, so it has no restatement.
+    Returns (total, per-layer rec means, per-layer sim means), the last two in pred_layer_id order."""
+    ids = list(pred_layer_id)
+    pred = torch.stack([projections[i] for i in ids], dim=1).float()  # B x N x T' x D
+    tgt = torch.stack([teacher_layer_results[i][0].transpose(0, 1) for i in ids], dim=1).float()
+    tgt = tgt.narrow(2, 0, pred.shape[2])
+    if rec_loss_type == "l1":
+        rec = F.l1_loss(pred, tgt, reduction="none")
+    elif rec_loss_type == "mse":
+        rec = F.mse_loss(pred, tgt, reduction="none")
+    else:
+        raise NotImplementedError("rec_loss_type must be one of 'l1', 'mse'.")
+    rec_layer = rec.mean((0, 2, 3))
+    sim = -F.logsigmoid(F.cosine_similarity(pred, tgt, dim=-1))
+    sim_layer = sim.mean((0, 2))
+    total = rec_loss_weight * rec.mean() + sim_loss_weight * sim.mean()
+    return total, rec_layer, sim_layer
+
+
 # --------------------------------------------------------------------------- optimizer (parity unpinned)
 def lr_schedule(step: int, total_steps: int, warmup: float) -> float:
     """[EXT] s3prl warmup_linear: x/w for x < w, else max((x-1)/(w-1), 0)."""

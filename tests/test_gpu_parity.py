@@ -469,6 +469,71 @@ def test_oracle_parity_fithubert_group_geometry(F):
         assert rel(p.grad, ref_sd[n].grad) < 6e-2, n
 
 
+@pytest.mark.parametrize("loss_type", ["l1", "mse"])
+def test_cosine_plus_reconstruction_loss(F, loss_type):
+    """train.py:282-314 with sim_loss_weight > 0 (the ex.yaml recipe's l1 + cosine): fused loss + gradient + column
+    sums vs autograd on the oracle restatement; a zero row exercises F.cosine_similarity's eps clamp."""
+    from fithubert_b200 import kernels as K
+    torch.manual_seed(3)
+    n, B, Tq, Tt, D = 3, 2, 37, 38, 768
+    pred = torch.randn(n, B, Tq, D).to(torch.bfloat16)
+    pred[1, 0, 5] = 0
+    tgt = (0.7 * pred.float().mean() + torch.randn(n, B, Tt, D)).to(torch.bfloat16)
+    tgt[:, :, :Tq] += (0.5 * pred.float()).to(torch.bfloat16)
+    ids, rw, sw = [0, 1, 2], 0.8, 1.3
+    pr = pred.float().requires_grad_(True)
+    total_ref, rec_ref, sim_ref = O.distill_loss_sim([pr[i] for i in range(n)],
+                                                     [(tgt[i].float().transpose(0, 1), None) for i in range(n)],
+                                                     ids, loss_type, rw, sw)
+    total_ref.backward()
+    w = torch.full((n,), 1.0 / n, device="cuda")
+    rec, sim = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    dpred, dbias = torch.empty(n, B, Tq, D, device="cuda", dtype=torch.bfloat16), torch.zeros(n, D, device="cuda")
+    K.distill_loss_sim(pred.cuda(), tgt.cuda(), w, rec, sim, dpred, n, B, Tq, Tt, D, 0 if loss_type == "mse" else 1,
+                       rw, sw, dbias=dbias, dbias_layer_stride=D)
+    assert rel(rec * n, rec_ref) < 1e-4 and rel(sim * n, sim_ref) < 1e-4  # kernel returns w_l * mean_l
+    assert abs(float(rw * rec.sum() + sw * sim.sum()) - float(total_ref)) < 1e-4 * abs(float(total_ref))
+    assert rel(dpred, pr.grad) < 1e-2  # bf16 rounding of the stored gradient
+    assert rel(dbias, dpred.float().sum((1, 2))) < 1e-4
+    assert torch.isfinite(dpred.float()).all()
+    # autograd-facing wrapper (what W2V2Distil.calculate_loss uses)
+    from fithubert_b200.autograd import _DistillLossFn
+    pc = pred.cuda().requires_grad_(True)
+    total, rec2, sim2 = _DistillLossFn.apply(pc, tgt.cuda(), w, 0 if loss_type == "mse" else 1, rw, sw)
+    (2.0 * total).backward()
+    assert abs(float(total) - float(total_ref)) < 1e-4 * abs(float(total_ref))
+    assert rel(pc.grad, 2.0 * pr.grad) < 1e-2
+
+
+def test_distil_module_with_cosine_loss(F):
+    """W2V2Distil with the ex.yaml loss setting (rec l1 + cosine on pred_layer_id, no random layers): the fused
+    training step and the reference-style forward -> calculate_loss path agree with each other and with the
+    oracle on the fixture's own student / teacher outputs."""
+    g = torch.load(GOLDEN[1])
+    import bench
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"]["pred_layer_id"] = "[0, 2]"
+    cfg["train"].update(distil_random_layer=0, random_layer_weight=0, rec_loss_type="l1", rec_loss_weight=1.0,
+                        sim_loss_weight=1.0)
+    teacher, _ = build_pair(F, g)
+    step = F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+    step.student_model.load_state_dict(g["student_state"])
+    step.student_model.eval()
+    s_res, t_res = step(g["source"].cuda(), g["padding_mask"])
+    total, losses = step.calculate_loss(s_res, t_res)
+    assert set(losses) == {"layer0", "layer2"}
+    ref_total, rec_ref, sim_ref = O.distill_loss_sim(g["projections"], [(t, None) for t in g["teacher_layers"]], [0, 2], "l1")
+    assert abs(float(total) - float(ref_total)) < 2e-2 * float(ref_total)
+    assert abs(float(losses["layer2"]) - float(rec_ref[1] + sim_ref[1])) < 2e-2 * float(rec_ref[1] + sim_ref[1])
+    step.configure_optimizers(total_steps=100)
+    loss = step.training_step({"x": g["source"], "padding_mask": g["padding_mask"]})
+    assert abs(float(loss) - float(total)) < 1e-3 * float(total)
+    cfg["train"]["distil_random_layer"] = 2
+    with pytest.raises(NotImplementedError):
+        F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+
+
 def test_fused_step_equals_autograd_path_and_updates_weights(F):
     """W2V2Distil.training_step (fused, no autograd) vs the autograd-facing path on the same batch, then one
     optimizer step vs the oracle's AdamW restatement."""
