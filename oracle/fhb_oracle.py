@@ -11,7 +11,10 @@ oracle/fairseq_stub (oracle/gen_golden.py -> tests/golden/*.pt, and the live che
 tests/test_oracle_vs_reference.py when /root/reference is present), and the teacher
 additionally against torchaudio.models.hubert_base.  The optimizer (s3prl, source not
 available anywhere in this image) is restated from its published algorithm:
-"parity unpinned" for that one function.
+"parity unpinned" for that one function.  calculate_loss (train.py:236-405) cannot be
+executed either (train.py imports Lightning and s3prl at module level): distill_loss /
+distill_loss_sim are line-by-line transcriptions of its live branches built from the
+same torch calls (F.mse_loss, F.l1_loss, F.cosine_similarity, F.logsigmoid).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root; [EXT] = fairseq @1b61bbad / s3prl @185e4b06, not vendored).
