@@ -8,6 +8,8 @@
 // So pass 1 reads only the waveform (1 MB/sample), never the C x T0 conv output; pass 2 reads the
 // waveform again and writes the bf16 channel-last output once.  Backward needs dW, dgamma, dbeta only
 // (the waveform has no gradient) and is ONE pass over dY using the same algebra (see bwd kernel).
+#include <stdlib.h>
+
 #include "fhb_common.cuh"
 
 namespace {
@@ -143,6 +145,152 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
       __nv_bfloat16* og = gp_out + ((long long)b * T0 + t_begin) * C + c0 + (long long)t * C;
       if (CPT == 8) *reinterpret_cast<uint4*>(og) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       else *reinterpret_cast<uint2*>(og) = make_uint2(pk[0], pk[1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- pass 2 on the tensor pipe (C = 64 * 2^k <= 512)
+// The direct kernel above spends 10 of its ~23 instructions per output on the convolution FMAs and is FP32-issue
+// bound at 2 TB/s (ncu r01n_ncu_full_conv0_fwd_t).  Here the k = 10 taps become the contraction of a
+// mma.sync.m16n8k8 TF32 product (16 frames x 8 channels per instruction, K = 10 padded to 16), with
+//   * the waveform split into two TF32 terms (x = hi + lo, both multiplied in): exact in the samples; the scaled
+//     weights are rounded to TF32 once (2^-11 relative - the fp16 the reference's own AMP conv uses has the same
+//     mantissa, and the bf16 rounding of the output is 4x coarser),
+//   * the GroupNorm scale folded into the B operand and the shift used as the accumulator's initial value,
+//   * channels permuted inside each group of 4 n-tiles so that a thread ends up with 8 CONSECUTIVE channels of
+//     a frame: one 16-byte store per (thread, frame), 64 contiguous bytes per quad.
+// What is left per output is the GELU (8 instructions), half a pack and 1/8 of a store.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void mma_tf32_k4(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+// first product of a chain: D = A B + C with C in its own registers (no accumulator-initialising MOVs)
+__device__ __forceinline__ void mma_tf32_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %11, %10, %11};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+}
+
+template <bool GP>
+__global__ void __launch_bounds__(256, 2)
+conv0_fwd_mma_kernel(const float* __restrict__ wave, long long ld, int T0, int C, int frames_per_block,
+                     const float* __restrict__ weight, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ out,
+                     __nv_bfloat16* __restrict__ gp_out) {
+  pdl_sync();
+  extern __shared__ float xs[];  // frames_per_block * 5 + 16 samples (tail zero-filled: the padded taps read it)
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int nframes = min(frames_per_block, T0 - t_begin);
+  const float* x = wave + (long long)b * ld + (long long)t_begin * kS;
+  const int nsamp = nframes * kS + (kK - kS);
+  const int nsm = frames_per_block * kS + 16;
+  for (int i0 = threadIdx.x; i0 < nsm; i0 += 4 * blockDim.x) {  // 4 loads in flight per thread
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < nsamp ? __ldg(x + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < nsm) xs[i] = v[u];
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int ngroups = C >> 6;            // 64-channel groups: 1, 2, 4 or 8
+  const int wpg = 8 / ngroups;           // warps sharing a channel group (they split the frames)
+  const int cbase = (warp % ngroups) * 64;
+  const int flane = warp / ngroups;
+  // B operand: n-tile j (0..7), column n = g  <->  channel cbase + 32 (j >> 2) + 8 (g >> 1) + 2 (j & 3) + (g & 1);
+  // k-step 0 (m16n8k8) holds taps t and t + 4, k-step 1 (m16n8k4) tap t + 8 (< 10 for t < 2, else padding)
+  uint32_t bh[8][3];
+  float sh[8][2];  // accumulator start = GroupNorm shift of this thread's two output columns (2t, 2t + 1) per n-tile
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cbase + 32 * (j >> 2) + 8 * (g >> 1) + 2 * (j & 3) + (g & 1);
+    const float sc = rstd[b * C + ch] * __ldg(gamma + ch);
+    const float w0 = __ldg(weight + ch * kK + t) * sc, w1 = __ldg(weight + ch * kK + t + 4) * sc;
+    const float w2 = t < 2 ? __ldg(weight + ch * kK + t + 8) * sc : 0.f;
+    bh[j][0] = to_tf32(w0);
+    bh[j][1] = to_tf32(w1);
+    bh[j][2] = to_tf32(w2);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int co = cbase + 32 * (j >> 2) + 8 * t + 2 * (j & 3) + e;  // output column 2t + e of n-tile j
+      sh[j][e] = __ldg(beta + co) - mean[b * C + co] * rstd[b * C + co] * __ldg(gamma + co);
+    }
+  }
+  __syncthreads();
+  // this thread's output pointer for frame f0 + g; rows g + 8 sit `row8` elements further, the next m-tile `step`
+  const long long row8 = 8LL * C, step = (long long)wpg * 16 * C;
+  __nv_bfloat16* op = out + ((long long)b * T0 + t_begin + flane * 16 + g) * C + cbase + 8 * t;
+  __nv_bfloat16* gpp = GP ? gp_out + ((long long)b * T0 + t_begin + flane * 16 + g) * C + cbase + 8 * t : nullptr;
+  for (int f0 = flane * 16; f0 < nframes; f0 += wpg * 16, op += step, gpp += GP ? step : 0) {
+    // A fragments (frames f0 + g and f0 + g + 8): k-step 0 = taps (t, t + 4), k-step 1 = tap t + 8
+    const float* x0 = xs + (f0 + g) * kS;
+    const float* x1 = x0 + 8 * kS;
+    const float av[6] = {x0[t], x1[t], x0[t + 4], x1[t + 4], t < 2 ? x0[t + 8] : 0.f, t < 2 ? x1[t + 8] : 0.f};
+    // x = hi + lo: hi keeps the 10 mantissa bits the tensor pipe reads (the low 13 bits are ignored by the MMA),
+    // lo = x - hi is exact in fp32 and itself truncated to TF32 by the hardware (error 2^-21 |x|)
+    uint32_t ah0[4], al0[4], ah1[2], al1[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ah0[i] = __float_as_uint(av[i]) & 0xFFFFE000u;
+      al0[i] = __float_as_uint(av[i] - __uint_as_float(ah0[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ah1[i] = __float_as_uint(av[4 + i]) & 0xFFFFE000u;
+      al1[i] = __float_as_uint(av[4 + i] - __uint_as_float(ah1[i]));
+    }
+    const bool r0 = f0 + g < nframes, r1 = f0 + g + 8 < nframes;
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+      float y[2][8], gp[2][8];  // [row g / g + 8][8 consecutive channels]
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = grp * 4 + jj;
+        float d[4];
+        mma_tf32_c(d, al0, bh[j][0], bh[j][1], sh[j][0], sh[j][1]);
+        mma_tf32_k4(d, al1[0], al1[1], bh[j][2]);
+        mma_tf32(d, ah0, bh[j][0], bh[j][1]);
+        mma_tf32_k4(d, ah1[0], ah1[1], bh[j][2]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = e >> 1, col = 2 * jj + (e & 1);
+          if (GP) gelu_erf_both(d[e], y[row][col], gp[row][col]);
+          else y[row][col] = gelu_erf(d[e]);
+        }
+      }
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        if (row == 0 ? r0 : r1) {
+          const long long off = row * row8 + 32 * grp;
+          *reinterpret_cast<uint4*>(op + off) = make_uint4(pack_bf16(y[row][0], y[row][1]), pack_bf16(y[row][2], y[row][3]),
+                                                              pack_bf16(y[row][4], y[row][5]), pack_bf16(y[row][6], y[row][7]));
+          if (GP)
+            *reinterpret_cast<uint4*>(gpp + off) = make_uint4(pack_bf16(gp[row][0], gp[row][1]), pack_bf16(gp[row][2], gp[row][3]),
+                                                                pack_bf16(gp[row][4], gp[row][5]), pack_bf16(gp[row][6], gp[row][7]));
+        }
+      }
     }
   }
 }
@@ -396,6 +544,22 @@ extern "C" int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* a, fhb_stream_t strea
     FHB_LAUNCH_CHECK();
   }
   {
+    static const bool direct_only = getenv("FHB_CONV0_DIRECT") != nullptr;
+    if (!direct_only && a->C % 64 == 0 && a->C <= 512 && 8 % (a->C / 64) == 0) {
+      // tensor-pipe path: 1024 frames per block (the 64 B-operand registers of a thread are set up once per block)
+      const int frames = 1024;
+      dim3 grid((a->T0 + frames - 1) / frames, a->B);
+      const size_t smem = sizeof(float) * (frames * kS + 16);
+      if (a->gp_out)
+        FHB_CUDA_CHECK(fhb_launch(conv0_fwd_mma_kernel<true>, grid, dim3(256), smem, s, a->wave, a->wave_ld, a->T0, a->C, frames,
+                                  a->weight, a->gamma, a->beta, a->mean, a->rstd, static_cast<__nv_bfloat16*>(a->out),
+                                  static_cast<__nv_bfloat16*>(a->gp_out)));
+      else
+        FHB_CUDA_CHECK(fhb_launch(conv0_fwd_mma_kernel<false>, grid, dim3(256), smem, s, a->wave, a->wave_ld, a->T0, a->C, frames,
+                                  a->weight, a->gamma, a->beta, a->mean, a->rstd, static_cast<__nv_bfloat16*>(a->out),
+                                  static_cast<__nv_bfloat16*>(a->gp_out)));
+      return 0;
+    }
     // 512 frames per block: the 80 weight registers / affine terms of a thread are amortised over
     // 512 / (256 / (C/8)) frames, and the 10 KB waveform slice is staged once
     const int frames = 512;
