@@ -14,6 +14,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 # erff/expf precision matters for GELU parity: no --use_fast_math
 FLAGS.remove("--use_fast_math")
+FLAGS += os.environ.get("NVCC_EXTRA", "").split()  # e.g. -DFHB_ATTN_TIMELINE for tools/attn_timeline.py
 
 
 def sources():

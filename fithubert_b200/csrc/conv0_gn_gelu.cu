@@ -274,10 +274,9 @@ conv0_fwd_mma_kernel(const float* __restrict__ wave, long long ld, int T0, int C
         mma_tf32(d, ah0, bh[j][0], bh[j][1]);
         mma_tf32_k4(d, ah1[0], ah1[1], bh[j][2]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int row = e >> 1, col = 2 * jj + (e & 1);
-          if (GP) gelu_erf_both(d[e], y[row][col], gp[row][col]);
-          else y[row][col] = gelu_erf(d[e]);
+        for (int row = 0; row < 2; ++row) {  // (d[0], d[1]) = row g, (d[2], d[3]) = row g + 8: adjacent channels
+          if (GP) gelu_erf_both2(d[2 * row], d[2 * row + 1], y[row][2 * jj], y[row][2 * jj + 1], gp[row][2 * jj], gp[row][2 * jj + 1]);
+          else gelu_erf2(d[2 * row], d[2 * row + 1], y[row][2 * jj], y[row][2 * jj + 1]);
         }
       }
 #pragma unroll

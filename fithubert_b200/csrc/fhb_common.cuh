@@ -76,6 +76,38 @@ static inline cudaError_t fhb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cfg.numAttrs = fhb_pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// ---------------------------------------------------------------- packed fp32x2 math (sm_100: FFMA2 / FADD2 / FMNMX3)
+// Blackwell issues two fp32 FMAs / adds per instruction on an aligned register pair and a three-input max; the
+// issue-bound inner loops (softmax, GELU epilogues) use them to halve their FFMA / FADD / FMNMX counts.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 // ---------------------------------------------------------------- small math
 // Exact (erf-based) GELU, written for issue-bound GEMM epilogues (3.5 G evaluations per distillation step on
 // 8 epilogue warps per SM):  gelu(x) = max(x, 0) - |x| * T(|x|),  T(a) = 0.5 erfc(a / sqrt2) = 2^t(a), t a
@@ -117,6 +149,30 @@ __device__ __forceinline__ void gelu_erf_both(float x, float& y, float& g) {
   const float tail = gelu_tail(a);
   y = fmaf(-a, tail, fmaxf(x, 0.f));
   g = gelu_grad_from(x, a, tail);
+}
+// Two GELUs at once: the degree-4 polynomial runs as 4 FFMA2 instead of 8 FFMA (6 instead of 8 issue slots per value)
+__device__ __forceinline__ f32x2_t gelu_tail_poly2(f32x2_t a) {
+  f32x2_t t = fma2(pack2(4.389107953e-03f, 4.389107953e-03f), a, pack2(-4.677256044e-02f, -4.677256044e-02f));
+  t = fma2(t, a, pack2(-4.635094653e-01f, -4.635094653e-01f));
+  t = fma2(t, a, pack2(-1.150136897e+00f, -1.150136897e+00f));
+  return fma2(t, a, pack2(-1.0f, -1.0f));
+}
+__device__ __forceinline__ void gelu_erf2(float x0, float x1, float& y0, float& y1) {
+  const float a0 = gelu_abs_clamp(x0), a1 = gelu_abs_clamp(x1);
+  float t0, t1;
+  unpack2(gelu_tail_poly2(pack2(a0, a1)), t0, t1);
+  y0 = fmaf(-a0, ex2_approx(t0), fmaxf(x0, 0.f));
+  y1 = fmaf(-a1, ex2_approx(t1), fmaxf(x1, 0.f));
+}
+__device__ __forceinline__ void gelu_erf_both2(float x0, float x1, float& y0, float& y1, float& g0, float& g1) {
+  const float a0 = gelu_abs_clamp(x0), a1 = gelu_abs_clamp(x1);
+  float t0, t1;
+  unpack2(gelu_tail_poly2(pack2(a0, a1)), t0, t1);
+  const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+  y0 = fmaf(-a0, e0, fmaxf(x0, 0.f));
+  y1 = fmaf(-a1, e1, fmaxf(x1, 0.f));
+  g0 = gelu_grad_from(x0, a0, e0);
+  g1 = gelu_grad_from(x1, a1, e1);
 }
 // ---------------------------------------------------------------- dropout (K13)
 // Counter-based masks: forward and backward kernels regenerate the same bits from (seed, element index), so no

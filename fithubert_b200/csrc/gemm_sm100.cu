@@ -303,7 +303,11 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         if ((flags & (FHB_EPI_GELU | FHB_EPI_AUX_DGELU)) == (FHB_EPI_GELU | FHB_EPI_AUX_DGELU)) {
 #pragma unroll
+#ifdef FHB_GELU_SCALAR
           for (int j = 0; j < 16; ++j) gelu_erf_both(v[j], v[j], pre[j]);
+#else
+          for (int j = 0; j < 16; j += 2) gelu_erf_both2(v[j], v[j + 1], v[j], v[j + 1], pre[j], pre[j + 1]);
+#endif
         } else {
           if (flags & FHB_EPI_STORE_PREACT) {
             if (flags & FHB_EPI_AUX_DGELU) {
@@ -316,7 +320,11 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           if (flags & FHB_EPI_GELU) {
 #pragma unroll
+#ifdef FHB_GELU_SCALAR
             for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+#else
+            for (int j = 0; j < 16; j += 2) gelu_erf2(v[j], v[j + 1], v[j], v[j + 1]);
+#endif
           }
         }
         if (flags & FHB_EPI_DROPOUT) {
@@ -656,6 +664,8 @@ int make_out_tmap(CUtensorMap* tm, void* base, bool f32, int n, int m, int ob_mo
 int pick_bn(int n, long long row_tiles, bool split_k) {
   const int n16 = (n + 15) / 16 * 16;
   if (n16 <= 64) return n16;
+  static const int forced = getenv("FHB_GEMM_BN") ? atoi(getenv("FHB_GEMM_BN")) : 0;  // tuning sweeps only
+  if (forced >= 64 && forced % 64 == 0 && forced <= kMaxBN) return n16 <= forced ? n16 : forced;
   const int sms = fhb_num_sms();
   int best = kMaxBN;
   double best_cost = 1e30;

@@ -38,6 +38,12 @@ elif case == "sfc":
     x, w, b = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev)
     out = torch.empty(M, N, device=dev, dtype=bf)
     fn = lambda: K.linear(x, w, b, out=out)
+elif case == "sfc_res":
+    M, N, Kd = 32 * 389, 480, 480
+    x, w, b = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev)
+    res = rnd(M, N)
+    out = torch.empty(M, N, device=dev, dtype=bf)
+    fn = lambda: K.linear(x, w, b, out=out, residual=res)
 elif case == "tqkv":
     M, N, Kd = 32 * 779, 2304, 768
     x, w, b = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev)
