@@ -512,6 +512,78 @@ __global__ void conv0_bwd_finalize_kernel(const float* __restrict__ acc, const d
   }
 }
 
+// ---------------------------------------------------------------- backward on the tensor pipe
+// P_j[b][c] = sum_t dz[b][t][c] x[b][5t + j] and A0[b][c] = sum_t dz[b][t][c] are one contraction over the frames:
+// [C x T0] . [T0 x 32] per sample, i.e. a wgrad-shaped fhb_gemm (both operands MN-major, split-K) against this
+// im2col of the waveform:  xcol[b][t][0..9] = bf16(x[5t + j]),  [10] = 1,  [16..25] = bf16(x - float(hi)) (the
+// low half of a two-term bf16 split: together 16 mantissa bits), everything else 0.
+__global__ void __launch_bounds__(256)
+conv0_im2col_kernel(const float* __restrict__ wave, long long ld, int T0, __nv_bfloat16* __restrict__ xcol) {
+  pdl_sync();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T0) return;
+  const float* x = wave + (long long)b * ld + (long long)t * kS;
+  float hi[kK], lo[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    const float v = __ldg(x + j);
+    hi[j] = __bfloat162float(__float2bfloat16(v));
+    lo[j] = v - hi[j];
+  }
+  uint4* o = reinterpret_cast<uint4*>(xcol + ((long long)b * T0 + t) * 32);
+  o[0] = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+  o[1] = make_uint4(pack_bf16(hi[8], hi[9]), pack_bf16(1.0f, 0.f), 0u, 0u);
+  o[2] = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+  o[3] = make_uint4(pack_bf16(lo[8], lo[9]), 0u, 0u, 0u);
+}
+
+// dW[c][j], dgamma[c], dbeta[c] from the GEMM accumulators acc32[b][c][32] (layout of xcol's columns); same algebra
+// as conv0_bwd_finalize_kernel with A1 = rstd (w . P - mean A0) formed here.
+__global__ void conv0_bwd_finalize32_kernel(const float* __restrict__ acc32, const double* __restrict__ stat,
+                                            const float* __restrict__ weight, const float* __restrict__ gamma,
+                                            const float* __restrict__ mean, const float* __restrict__ rstd, int B, int C,
+                                            int T0, float* __restrict__ dW, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int accumulate) {
+  pdl_sync();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * kK) return;
+  const int c = idx / kK, j = idx - c * kK;
+  double w[kK];
+  int ridx[kK];
+#pragma unroll
+  for (int q = 0; q < kK; ++q) {
+    w[q] = (double)weight[c * kK + q];
+    const int lo = q < j ? q : j, hi = q < j ? j : q;
+    ridx[q] = lo * kK - lo * (lo - 1) / 2 + (hi - lo);
+  }
+  const double gm = gamma[c];
+  double dw = 0.0, dg = 0.0, db = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* a = acc32 + ((long long)b * C + c) * 32;
+    const double* S = stat + (long long)b * kNStat;
+    const double* R = S + kK;
+    const double r = rstd[b * C + c], m = mean[b * C + c];
+    const double a0 = a[10];
+    double wp = 0.0, yx = 0.0;
+#pragma unroll
+    for (int q = 0; q < kK; ++q) {
+      wp += w[q] * ((double)a[q] + (double)a[16 + q]);
+      yx += w[q] * R[ridx[q]];
+    }
+    const double a1 = r * (wp - m * a0);
+    dg += a1;
+    db += a0;
+    const double xhat_x = r * (yx - m * S[j]);
+    dw += r * gm * ((double)a[j] + (double)a[16 + j] - a0 / T0 * S[j] - a1 / T0 * xhat_x);
+  }
+  dW[idx] = (accumulate ? dW[idx] : 0.f) + (float)dw;
+  if (j == 0) {
+    dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)dg;
+    dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)db;
+  }
+}
+
 int check_common(const fhb_conv0_args* a) {
   FHB_ARG_CHECK(a != nullptr, "conv0: null args");
   FHB_ARG_CHECK(a->kernel == kK && a->stride == kS, "conv0: only k=10,s=5 is implemented (got k=%d,s=%d)", a->kernel,
@@ -604,5 +676,24 @@ extern "C" int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* a, fhb_stream_t strea
                                                            a->B, a->C, a->T0, a->dweight, a->dgamma, a->dbeta,
                                                            a->accumulate));
   FHB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fhb_conv0_im2col(const float* wave, int64_t wave_ld, int32_t B, int32_t L, int32_t T0, void* xcol,
+                                fhb_stream_t stream) {
+  FHB_ARG_CHECK(wave && xcol && B > 0 && T0 > 0, "conv0_im2col: bad arguments");
+  FHB_ARG_CHECK((long long)(T0 - 1) * kS + kK <= L, "conv0_im2col: T0=%d frames do not fit in L=%d samples", T0, L);
+  FHB_CUDA_CHECK(fhb_launch(conv0_im2col_kernel, dim3((T0 + 255) / 256, B), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            wave, (long long)wave_ld, T0, static_cast<__nv_bfloat16*>(xcol)));
+  return 0;
+}
+
+extern "C" int fhb_conv0_bwd_finalize(const float* acc32, const fhb_conv0_args* a, fhb_stream_t stream) {
+  int rc = check_common(a);
+  if (rc) return rc;
+  FHB_ARG_CHECK(acc32 && a->dweight && a->dgamma && a->dbeta, "conv0_bwd_finalize: null pointer");
+  FHB_CUDA_CHECK(fhb_launch(conv0_bwd_finalize32_kernel, dim3((a->C * kK + 127) / 128), dim3(128), 0,
+                            static_cast<cudaStream_t>(stream), acc32, a->stat, a->weight, a->gamma, a->mean, a->rstd, a->B,
+                            a->C, a->T0, a->dweight, a->dgamma, a->dbeta, a->accumulate));
   return 0;
 }

@@ -263,10 +263,24 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* 
   const fhb_prep_tensor e = table[blockIdx.y];
   const long long d1 = e.dim[1], d2 = e.dim[2];
   const long long n = e.dim[0] * d1 * d2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  // fast path (most entries: Linear weights, biases): the source is already laid out like the destination, so the
+  // entry is a plain fp32 -> bf16 cast - 16-byte loads, 8-byte stores, no index arithmetic
+  const bool contiguous = e.sstride[2] == 1 && (d1 == 1 || e.sstride[1] == d2) && (e.dim[0] == 1 || e.sstride[0] == d1 * d2);
+  if (contiguous && !e.dst_is_f32 && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(e.src) & 15) == 0) &&
+      ((reinterpret_cast<uintptr_t>(e.dst) & 7) == 0)) {
+    const float4* s4 = reinterpret_cast<const float4*>(e.src);
+    uint2* d2p = reinterpret_cast<uint2*>(e.dst);
+    for (long long i = i0; i < (n >> 2); i += step) {
+      const float4 v = __ldg(s4 + i);
+      d2p[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    return;
+  }
+  for (long long i = i0; i < n; i += step) {
     const long long i2 = i % d2, r = i / d2;
-    const long long i1 = r % d1, i0 = r / d1;
-    const float v = e.src[i0 * e.sstride[0] + i1 * e.sstride[1] + i2 * e.sstride[2]];
+    const long long i1 = r % d1, i0b = r / d1;
+    const float v = e.src[i0b * e.sstride[0] + i1 * e.sstride[1] + i2 * e.sstride[2]];
     if (e.dst_is_f32)
       static_cast<float*>(e.dst)[i] = e.accumulate ? static_cast<float*>(e.dst)[i] + v : v;
     else

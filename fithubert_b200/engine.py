@@ -789,10 +789,24 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.gemm_raw(a3, b3, dprev, n_odd, cin, co, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * cin,
                        d_hi_stride=in_rows * cin, d_offset_elems=(in_halo + 1) * cin, flags=flags, aux_in=uprev)
         du = dprev
-    # ---- layer 0: conv + GroupNorm + GELU backward (dW0, dgamma, dbeta) in one pass over dY0
+    # ---- layer 0: conv + GroupNorm + GELU backward (dW0, dgamma, dbeta).  du already carries gelu'(z) (dz): the sums
+    # over frames sum_t dz x[5t+j] and sum_t dz are a wgrad-shaped GEMM against a bf16 im2col of the waveform
+    # (C a multiple of 64: the MN-major A operand is loaded in 64-channel atoms); other widths take the direct kernel.
     C0 = g.conv_layers[0][0]
-    acc = torch.empty(B, C0, 12, device=dev, dtype=f32)
-    K.conv0_bwd(c.wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
-                P["feature_extractor.conv_layers.0.2.bias"], c.frames[0], c.stat, c.mean0, c.rstd0, du, acc,
-                gv("feature_extractor.conv_layers.0.0.weight"), gv("feature_extractor.conv_layers.0.2.weight"),
-                gv("feature_extractor.conv_layers.0.2.bias"), True, dy_is_dz=True)
+    wv, gm, bt = (P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
+                  P["feature_extractor.conv_layers.0.2.bias"])
+    gw, gg, gb = (gv("feature_extractor.conv_layers.0.0.weight"), gv("feature_extractor.conv_layers.0.2.weight"),
+                  gv("feature_extractor.conv_layers.0.2.bias"))
+    T0 = c.frames[0]
+    if C0 % 64 == 0:
+        xcol = torch.empty(B, T0, 32, device=dev, dtype=bf16)
+        K.conv0_im2col(c.wave, T0, xcol)
+        acc32 = torch.zeros(B, C0, 32, device=dev, dtype=f32)
+        a3 = L.tensor3(data_ptr=du.data_ptr(), dim=(C0, T0, B), stride=(C0, T0 * C0))
+        b3 = L.tensor3(data_ptr=xcol.data_ptr(), dim=(32, T0, B), stride=(32, T0 * 32))
+        K.gemm_raw(a3, b3, acc32, C0, 32, T0, a_major=1, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
+                   d_ld=32, d_hi_stride=C0 * 32, flags=L.EPI_ATOMIC_ADD)
+        K.conv0_bwd_finalize(acc32, c.wave, wv, gm, bt, T0, c.stat, c.mean0, c.rstd0, gw, gg, gb, True)
+    else:
+        acc = torch.empty(B, C0, 12, device=dev, dtype=f32)
+        K.conv0_bwd(c.wave, wv, gm, bt, T0, c.stat, c.mean0, c.rstd0, du, acc, gw, gg, gb, True, dy_is_dz=True)

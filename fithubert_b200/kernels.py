@@ -180,6 +180,25 @@ def conv0_bwd(wave, weight, gamma, beta, T0, stat, mean, rstd, dy, acc, dweight,
     L.check(L.lib().fhb_conv0_gn_gelu_bwd(C.byref(a), L.stream_ptr()), "fhb_conv0_gn_gelu_bwd")
 
 
+def conv0_im2col(wave, T0, xcol):
+    """xcol bf16 [B, T0, 32]: two-term bf16 split of the 10 taps of every frame + a ones column (conv0 backward GEMM)."""
+    B, Ld = wave.shape
+    L.check(L.lib().fhb_conv0_im2col(L.ptr(wave), C.c_int64(wave.stride(0)), B, Ld, T0, L.ptr(xcol), L.stream_ptr()),
+            "fhb_conv0_im2col")
+
+
+def conv0_bwd_finalize(acc32, wave, weight, gamma, beta, T0, stat, mean, rstd, dweight, dgamma, dbeta, accumulate=True,
+                       eps=1e-5):
+    a = L.Conv0Args()
+    B, Ld = wave.shape
+    a.wave, a.wave_ld = wave.data_ptr(), wave.stride(0)
+    a.B, a.L, a.C, a.T0, a.kernel, a.stride, a.eps = B, Ld, weight.shape[0], T0, weight.shape[-1], 5, eps
+    a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    a.stat, a.mean, a.rstd = stat.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.dweight, a.dgamma, a.dbeta, a.accumulate = dweight.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate)
+    L.check(L.lib().fhb_conv0_bwd_finalize(L.ptr(acc32), C.byref(a), L.stream_ptr()), "fhb_conv0_bwd_finalize")
+
+
 def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
     L.check(L.lib().fhb_layernorm_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd),

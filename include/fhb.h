@@ -125,6 +125,15 @@ typedef struct {
 } fhb_conv0_args;
 int fhb_conv0_gn_gelu_fwd(const fhb_conv0_args* args, fhb_stream_t stream);
 int fhb_conv0_gn_gelu_bwd(const fhb_conv0_args* args, fhb_stream_t stream);
+/* Training-path backward of layer 0 on the tensor pipe.  fhb_conv0_im2col writes xcol bf16 [B][T0][32]:
+ * columns 0-9 = bf16(x[5t+j]), 10 = 1, 16-25 = the bf16 remainder x - hi, the rest 0.  A wgrad-shaped fhb_gemm
+ * (A = dz [B][T0][C] MN-major, B = xcol MN-major, one output block [C][32] fp32 per sample, split-K accumulate) then
+ * yields sum_t dz x[5t+j] (hi + lo columns) and sum_t dz (column 10); fhb_conv0_bwd_finalize turns those
+ * accumulators acc32 [B][C][32] into dW / dgamma / dbeta (args: weight, gamma, stat, mean, rstd, dweight, dgamma,
+ * dbeta, accumulate, B, C, T0 as in fhb_conv0_gn_gelu_bwd; dz = dy * gelu'(z) as saved by the forward). */
+int fhb_conv0_im2col(const float* wave, int64_t wave_ld, int32_t B, int32_t L, int32_t T0, void* xcol,
+                     fhb_stream_t stream);
+int fhb_conv0_bwd_finalize(const float* acc32, const fhb_conv0_args* a, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ LayerNorm (K3)
  * y = LN(x) * gamma + beta over the last dim C (eps 1e-5), rows = everything else; bf16 in/out, fp32

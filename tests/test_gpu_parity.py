@@ -166,6 +166,25 @@ def test_conv0_groupnorm_gelu_fwd_bwd(F):
     K.conv0_bwd(x, w.detach(), g.detach(), b.detach(), T0, stat, mean, rstd, dz, acc, dw2, dg2, db2, accumulate=False,
                 dy_is_dz=True)
     assert rel(dw2, w.grad.view(C, 10)) < 1.5e-2 and rel(dg2, g.grad) < 1.5e-2 and rel(db2, b.grad) < 1.5e-2
+    # the engine's route for C % 64 == 0: bf16 im2col of the waveform + wgrad-shaped tcgen05 GEMM + finalize
+    from fithubert_b200 import lib as L
+    xcol = torch.empty(B, T0, 32, device="cuda", dtype=torch.bfloat16)
+    K.conv0_im2col(x, T0, xcol)
+    fr = x.unfold(1, 10, 5)[:, :T0]  # [B, T0, 10]
+    hi = xcol[..., :10].float()
+    assert torch.equal(hi, fr.bfloat16().float()) and bool((xcol[..., 10] == 1).all())
+    assert rel(hi + xcol[..., 16:26].float(), fr) < 2e-5 and float(xcol[..., 11:16].abs().max()) == 0.0
+    acc32 = torch.zeros(B, C, 32, device="cuda")
+    a3 = L.tensor3(data_ptr=dz.data_ptr(), dim=(C, T0, B), stride=(C, T0 * C))
+    b3 = L.tensor3(data_ptr=xcol.data_ptr(), dim=(32, T0, B), stride=(32, T0 * 32))
+    K.gemm_raw(a3, b3, acc32, C, 32, T0, a_major=1, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
+               d_ld=32, d_hi_stride=C * 32, flags=L.EPI_ATOMIC_ADD)
+    ref_p = torch.einsum("btc,btj->bcj", dz.float(), fr)
+    assert rel(acc32[..., :10] + acc32[..., 16:26], ref_p) < 1e-4 and rel(acc32[..., 10], dz.float().sum(1)) < 1e-4
+    dw3, dg3, db3 = torch.zeros(C, 10, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    K.conv0_bwd_finalize(acc32, x, w.detach(), g.detach(), b.detach(), T0, stat, mean, rstd, dw3, dg3, db3, accumulate=False)
+    assert rel(dw3, w.grad.view(C, 10)) < 1.5e-2 and rel(dg3, g.grad) < 1.5e-2 and rel(db3, b.grad) < 1.5e-2
+    assert rel(dw3, dw2) < 2e-3 and rel(dg3, dg2) < 2e-3  # same dz: only the summation route differs
 
 
 @pytest.mark.parametrize("d,T,amp,short", [(40, 389, 1.0, 37), (64, 779, 1.0, 37), (24, 50, 1.0, 37), (16, 13, 1.0, 37),
