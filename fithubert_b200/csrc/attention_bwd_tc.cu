@@ -10,7 +10,8 @@
 //        dK    += dS^T_i Q_i                                                         -> TMEM, accumulates over i
 //        dQ_i   = dS_i K        (A = the SAME dS^T smem tile read MN-major)          -> TMEM, fresh per i
 //   warps 0-15: thread = (key row, 32-query quarter).  S^T / dP^T out of TMEM in one batch, then
-//        P^T = 2^(S^T*scale*log2e - lse_q), Pd^T = P^T o dropmask, dS^T = P^T o (dP^T o dropmask - delta_q) * scale,
+//        P^T = 2^(S^T*scale*log2e - lse_q), Pd^T = P^T o dropmask, dS^T = P^T o (dP^T o dropmask - delta_q)  [the
+//        softmax scale is applied once to dK at the final store and to dQ in dq_convert, not per element],
 //        both written as bf16 A operands (128B-swizzled);  dQ_i is drained TMEM -> smem -> TMA reduce-add (fp32)
 //        into a [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to bf16 afterwards.
 // S^T_{i+1} / dP^T_{i+1} are issued as soon as the compute warps hold tile i in registers, so the tensor pipe
@@ -204,6 +205,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const int key = k0 + row;
     const float keymask = key < nvalid ? 1.f : 0.f;
     const bool warp_keys_live = (k0 + quarter * 32) < nvalid;  // warp-uniform: any valid key in this warp's rows
+    const bool masked_keys = (k0 + quarter * 32 + 32) > nvalid;  // warp-uniform: some key row of this warp is masked
     const int tid = threadIdx.x;
     if (HD % 16) {
       // pad columns HD..DK-1 of K (threads 0-127) and V (128-255) hold the next head's values: zero them
@@ -258,8 +260,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       if (tid < 256) {
         const int q = q0 + (tid & 127);
         const long long off = ((long long)b * H + h) * T + q;
-        if (tid < 128) ls[tid] = q < T ? lse[off] * kLog2e : INFINITY;
-        else dl[tid - 128] = q < T ? delta[off] : 0.f;
+        // stored NEGATED: the inner loop then reads them straight into packed FFMA2 addends
+        if (tid < 128) ls[tid] = q < T ? -lse[off] * kLog2e : -INFINITY;
+        else dl[tid - 128] = q < T ? -delta[off] : 0.f;
       }
       bar_compute();
       const int nq16v = (min(kT, T - q0) + 15) & ~15;      // query columns the MMAs of this tile touch
@@ -277,20 +280,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       mbar_arrive(s_free);
       if (i > 0) mbar_wait(mma_done, (i - 1) & 1);  // smem P / dS free again
       if (work) {
+        // P^T = 2^(S^T sc - lse), Pd^T = P^T o mask, dS^T = P^T o (dP^T o mask - delta)   (x scale folded into the dQ
+        // conversion and the dK store).  Two queries per FFMA2 / FMUL2; lse and delta come as 16-byte smem vectors.
+        const f32x2_t sc2 = pack2(sc, sc);
+        const float4* ls4 = reinterpret_cast<const float4*>(ls + quad * 32);
+        const float4* dl4 = reinterpret_cast<const float4*>(dl + quad * 32);
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
+          const float4 la = ls4[c >> 2], lb = ls4[(c >> 2) + 1], da = dl4[c >> 2], db = dl4[(c >> 2) + 1];
+          const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+          const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
           float pd[8], ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ql = quad * 32 + c + e;  // query within the tile
-            const float p = ex2_approx(fmaf(__uint_as_float(sr[c + e]), sc, -ls[ql])) * keymask;
-            float mk = 1.f;
+          for (int e = 0; e < 8; e += 2) {
+            float t0, t1;
+            unpack2(fma2(pack2(__uint_as_float(sr[c + e]), __uint_as_float(sr[c + e + 1])), sc2, pack2(nl[e], nl[e + 1])), t0, t1);
+            f32x2_t p2 = pack2(ex2_approx(t0), ex2_approx(t1));
+            if (masked_keys) p2 = mul2(p2, pack2(keymask, keymask));
+            f32x2_t dp2 = pack2(__uint_as_float(dr[c + e]), __uint_as_float(dr[c + e + 1]));
+            f32x2_t pd2 = p2;
             if (DROP) {
+              const int ql = quad * 32 + c + e;  // query within the tile
               const uint32_t qid = (uint32_t)((b * H + h) * T + q0 + ql);
-              mk = dropout_one(drop_seed, qid * T2 + (uint32_t)key, drop_thr, drop_scale);
+              const f32x2_t mk2 = pack2(dropout_one(drop_seed, qid * T2 + (uint32_t)key, drop_thr, drop_scale),
+                                        dropout_one(drop_seed, (qid + 1) * T2 + (uint32_t)key, drop_thr, drop_scale));
+              pd2 = mul2(p2, mk2);
+              dp2 = mul2(dp2, mk2);
             }
-            pd[e] = p * mk;
-            ds[e] = p * (__uint_as_float(dr[c + e]) * mk - dl[ql]) * scale;
+            unpack2(pd2, pd[e], pd[e + 1]);
+            unpack2(mul2(p2, add2(dp2, pack2(nd[e], nd[e + 1]))), ds[e], ds[e + 1]);
           }
           const uint32_t ch = ch0 + (uint32_t)(c >> 3);
           st_shared_v4(prow + ((ch ^ rsw) << 4), pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]),
@@ -322,6 +340,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tmem_ld16(tm_dk + lane_off + c16, rk);  // warp-collective: every lane takes part, stores are predicated
       tmem_ld16(tm_dv + lane_off + c16, rv);
       tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) rk[e] = __float_as_uint(__uint_as_float(rk[e]) * scale);  // dS^T was kept un-scaled
       if (key >= nvalid) {  // masked keys: exact zeros (their P rows were never computed)
 #pragma unroll
         for (int e = 0; e < 16; ++e) rk[e] = rv[e] = 0u;
@@ -350,9 +370,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
 }
 
-// dqkv[row][0:E] = bf16(dq_acc[row][0:E])
+// dqkv[row][0:E] = bf16(scale * dq_acc[row][0:E])   (the softmax scale the fused kernel left out of dS)
 __global__ void __launch_bounds__(256)
-dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int E8, long long ld) {
+dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int E8, long long ld,
+                  float scale) {
   pdl_sync();
   const long long total = rows * E8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -361,7 +382,8 @@ dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqk
     const float4 a = *reinterpret_cast<const float4*>(acc + r * (E8 * 8) + c);
     const float4 b2 = *reinterpret_cast<const float4*>(acc + r * (E8 * 8) + c + 4);
     *reinterpret_cast<uint4*>(dqkv + r * ld + c) =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b2.x, b2.y), pack_bf16(b2.z, b2.w));
+        make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale),
+                   pack_bf16(b2.x * scale, b2.y * scale), pack_bf16(b2.z * scale, b2.w * scale));
   }
 }
 
@@ -403,7 +425,7 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
   const long long rows = (long long)B * T;
   long long blocks = (rows * (E / 8) + 255) / 256;
   if (blocks > 8LL * fhb_num_sms()) blocks = 8LL * fhb_num_sms();
-  FHB_CUDA_CHECK(fhb_launch(dq_convert_kernel, dim3((unsigned)blocks), dim3(256), 0, s, dq_ws, static_cast<__nv_bfloat16*>(dqkv), rows, (int)(E / 8), 3 * E));
+  FHB_CUDA_CHECK(fhb_launch(dq_convert_kernel, dim3((unsigned)blocks), dim3(256), 0, s, dq_ws, static_cast<__nv_bfloat16*>(dqkv), rows, (int)(E / 8), 3 * E, scale));
   FHB_LAUNCH_CHECK();
   return 0;
 }
