@@ -190,30 +190,59 @@ def encoder_prologue(sd: State, x: Tensor, mask: Optional[Tensor], cfg: dict) ->
 
 
 # --------------------------------------------------------------------------- student
+def grad_multiply(x: Tensor, scale: float) -> Tensor:
+    """[EXT] fairseq GradMultiply (modules/model.py:428-431): identity forward, gradient x scale."""
+    if scale == 1.0:
+        return x
+    return x * scale + (x * (1.0 - scale)).detach()
+
+
 def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional[Tensor] = None,
                     heads: bool = True) -> dict:
-    """CustomStudentModel.forward, modules/model.py:420-552 (n_mels=0, transformer,
-    layerwise_proj=True, conv1d TR layer at index 0, dropout identity).
-    heads=False mirrors the state after _disable_projection_heads() (:393-399,500-502):
-    final_proj = proj_head[-1] applied to the last layer only."""
+    """CustomStudentModel.forward, modules/model.py:420-552 (n_mels=0, transformer, dropout identity) for the two
+    shipped recipes:
+      * fithubert.yaml: layerwise_proj=True, conv1d TR layer at index 0 -> 12 LayerWiseProjHeads, x = last projection;
+      * ex.yaml: layerwise_proj=False, enable_tr_layer=False, feature_grad_mult < 1 -> DistilHuBERT head
+        Linear -> GELU -> SplitLinear on the last layer (:504-518, modules/module.py:585-619), projections a
+        [B, N, T, D] tensor, x = the encoder output.
+    heads=False mirrors the state after _disable_projection_heads() (:393-399,500-502)."""
     conv_layers = parse_conv_layers(cfg["conv_feature_layers"])
     H = cfg["encoder_attention_heads"]
-    feats = conv_extractor(sd, "feature_extractor.", source, conv_layers).transpose(1, 2)
+    feats = conv_extractor(sd, "feature_extractor.", source, conv_layers)
+    feats = grad_multiply(feats, float(cfg.get("feature_grad_mult", 1.0))).transpose(1, 2)
     B, T, C = feats.shape
     feats = F.layer_norm(feats, (C,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
     mask = mask_m1(padding_mask, T, conv_layers)
     feats = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
     features_to_distill = feats
     x = encoder_prologue(sd, feats, mask, cfg).transpose(0, 1)  # [T,B,C]
-    # time-reduction conv, modules/module.py:317-321 (drops the last frame when T is odd)
-    x = F.conv1d(x.permute(1, 2, 0), sd["encoder.layers.0.weight"], sd["encoder.layers.0.bias"],
-                 stride=cfg["tr_reduce_factor"]).permute(2, 0, 1)
-    tr_layer_results = [x]
-    rmask = mask_m2(mask, cfg["tr_reduce_factor"])
+    tr = bool(cfg.get("enable_tr_layer", True))
+    tr_layer_results = []
+    rmask = mask
+    if tr:
+        # time-reduction conv, modules/module.py:317-321 (drops the last frame when T is odd)
+        x = F.conv1d(x.permute(1, 2, 0), sd["encoder.layers.0.weight"], sd["encoder.layers.0.bias"],
+                     stride=cfg["tr_reduce_factor"]).permute(2, 0, 1)
+        tr_layer_results = [x]
+        rmask = mask_m2(mask, cfg["tr_reduce_factor"])
     layer_results = []
-    for i in range(1, cfg["encoder_layers"] + 1):
-        x, lr = encoder_layer(sd, f"encoder.layers.{i}.", x, rmask, H)
+    off = 1 if tr else 0
+    for i in range(cfg["encoder_layers"]):
+        x, lr = encoder_layer(sd, f"encoder.layers.{i + off}.", x, rmask, H)
         layer_results.append((x, None, lr))
+
+    if not cfg.get("layerwise_proj", True):
+        assert not tr, "the shared-upsampler variant (layerwise_proj=False with a TR layer) is not restated"
+        out = x.transpose(0, 1)  # [B, T, E]
+        projections = None
+        if heads:
+            n = sd["proj_head.2.weight"].shape[0]
+            h = F.gelu(F.linear(out, sd["proj_head.0.weight"], sd["proj_head.0.bias"]))
+            h = h.reshape(B, T, n, 1, -1)
+            pred = torch.einsum("...klm,kmn->...kln", h, sd["proj_head.2.weight"]).squeeze(3) + sd["proj_head.2.bias"]
+            projections = pred.reshape(B, T, n, -1).permute(0, 2, 1, 3)  # B x N x T x D
+        return {"x": out, "padding_mask": mask, "features": features_to_distill,
+                "layer_results": layer_results, "tr_layer_results": tr_layer_results, "projections": projections}
 
     def head(i, h_tbc):  # LayerWiseProjHead.forward, modules/module.py:649-661
         y = F.conv_transpose1d(h_tbc.permute(1, 2, 0), sd[f"proj_head.{i}.upsampler.weight"],
@@ -386,7 +415,8 @@ def init_student_state(cfg: dict, seed: int = 0, perturb: bool = False) -> State
     affine parameters too (they are 0/1 at init) so parity tests exercise them."""
     gen = torch.Generator().manual_seed(seed)
     sd = _init_frontend(cfg, gen)
-    sd.update(init_encoder_state(cfg, gen, 1))
+    tr = bool(cfg.get("enable_tr_layer", True))
+    sd.update(init_encoder_state(cfg, gen, 1 if tr else 0))
     E, D = cfg["encoder_embed_dim"], cfg["pred_head_final_dim"]
     f = cfg["tr_reduce_factor"]
 
@@ -394,15 +424,25 @@ def init_student_state(cfg: dict, seed: int = 0, perturb: bool = False) -> State
         return torch.empty(*shape).uniform_(-bound, bound, generator=gen)
 
     bt = 1 / math.sqrt(E * f)
-    sd["encoder.layers.0.weight"] = uni(E, E, f, bound=bt)
-    sd["encoder.layers.0.bias"] = uni(E, bound=bt)
-    sd["upsampler.weight"] = uni(E, E, f, bound=bt)  # dead when layerwise_proj
-    sd["upsampler.bias"] = uni(E, bound=bt)
-    for i in range(cfg["encoder_layers"]):
-        sd[f"proj_head.{i}.upsampler.weight"] = uni(E, E, f, bound=bt)
-        sd[f"proj_head.{i}.upsampler.bias"] = uni(E, bound=bt)
-        sd[f"proj_head.{i}.lin_proj.weight"] = uni(D, E, bound=1 / math.sqrt(E))
-        sd[f"proj_head.{i}.lin_proj.bias"] = uni(D, bound=1 / math.sqrt(E))
+    if tr:
+        sd["encoder.layers.0.weight"] = uni(E, E, f, bound=bt)
+        sd["encoder.layers.0.bias"] = uni(E, bound=bt)
+        sd["upsampler.weight"] = uni(E, E, f, bound=bt)  # dead when layerwise_proj
+        sd["upsampler.bias"] = uni(E, bound=bt)
+    if not cfg.get("layerwise_proj", True):
+        # DistilHuBERT head (modules/model.py:362-368, modules/module.py:585-604): Linear(E, inter * N), SplitLinear
+        n = len(cfg["pred_layer_id"])
+        inter = cfg.get("pred_head_inter_dim", 0) or E
+        sd["proj_head.0.weight"] = uni(inter * n, E, bound=1 / math.sqrt(E))
+        sd["proj_head.0.bias"] = uni(inter * n, bound=1 / math.sqrt(E))
+        sd["proj_head.2.weight"] = uni(n, inter, D, bound=inter ** -0.5)
+        sd["proj_head.2.bias"] = uni(1, 1, n, D, bound=inter ** -0.5)
+    else:
+        for i in range(cfg["encoder_layers"]):
+            sd[f"proj_head.{i}.upsampler.weight"] = uni(E, E, f, bound=bt)
+            sd[f"proj_head.{i}.upsampler.bias"] = uni(E, bound=bt)
+            sd[f"proj_head.{i}.lin_proj.weight"] = uni(D, E, bound=1 / math.sqrt(E))
+            sd[f"proj_head.{i}.lin_proj.bias"] = uni(D, bound=1 / math.sqrt(E))
     if perturb:
         _perturb(sd, gen)
     return sd

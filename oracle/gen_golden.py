@@ -139,6 +139,58 @@ def run_case(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, kind="huber
     print(name, "loss", float(loss), "bytes", os.path.getsize(path))
 
 
+TINY_SPLIT_STUDENT = dict(  # data/conf/ex.yaml family: teacher-shaped conv stack, no TR layer, DistilHuBERT head
+    conv_feature_layers="[(32,10,5)] + [(32,3,2)] * 4 + [(32,2,2)] * 2",
+    encoder_layers=2, encoder_embed_dim=64, encoder_ffn_embed_dim=128, encoder_attention_heads=4,
+    conv_pos=16, conv_pos_groups=4, pred_head_final_dim=64, pred_layer_id="[0, 2]",
+    init_conv_layers=False, init_encoder_layers=0,
+)
+
+
+def run_case_split(name, s_over, t_over, B, Lmax, lengths, yaml_distiller):
+    """ex.yaml recipe: layerwise_proj False, enable_tr_layer False, feature_grad_mult 0.1; loss = L1 + cosine over
+    pred_layer_id (train.py:268-314, `distil_random_layer == 0` branch, restated inline like run_case's)."""
+    torch.manual_seed(0)
+    cfg = ref_student_cfg(yaml_distiller, **s_over)
+    assert not cfg.layerwise_proj and not cfg.enable_tr_layer and cfg.feature_grad_mult == 0.1
+    student = CustomStudentModel(cfg)
+    teacher = RefTeacher(O.teacher_config(**t_over, kind="hubert"))
+    perturb_(student, 21)
+    perturb_(teacher, 22)
+    student.eval()
+    teacher.eval()
+    x, pm = O.synth_batch(B, Lmax, lengths, seed=4321)
+    with torch.no_grad():
+        t_res = teacher(x, pm)
+    s_res = student(source=x, padding_mask=pm)
+    ids = eval(cfg.pred_layer_id)
+    tgt = torch.stack([t_res["layer_results"][i][0].transpose(0, 1) for i in ids], 1)
+    pred = s_res["projections"]
+    tgt = tgt.narrow(2, 0, pred.shape[2])
+    rec = torch.nn.functional.l1_loss(pred, tgt, reduction="none")
+    sim = -torch.nn.functional.logsigmoid(torch.nn.functional.cosine_similarity(pred, tgt, dim=-1))
+    loss = 1.0 * rec.mean() + 1.0 * sim.mean()
+    loss.backward()
+    out = {
+        "student_cfg": dict(s_over, layerwise_proj=False, enable_tr_layer=False, feature_grad_mult=0.1),
+        "teacher_cfg": dict(t_over, kind="hubert"),
+        "student_state": {k: v.detach().clone() for k, v in student.state_dict().items()},
+        "teacher_state": {k: v.detach().clone() for k, v in teacher.state_dict().items()},
+        "source": x, "padding_mask": pm, "pred_layer_id": ids,
+        "student_mask": s_res["padding_mask"], "teacher_mask": t_res["padding_mask"],
+        "student_features": s_res["features"].detach(),
+        "student_layers": [lr[0].detach() for lr in s_res["layer_results"]],
+        "x": s_res["x"].detach(), "projections": pred.detach(),
+        "teacher_layers": [lr[0].detach() for lr in t_res["layer_results"]],
+        "loss": loss.detach(), "rec_layer": rec.mean((0, 2, 3)).detach(), "sim_layer": sim.mean((0, 2)).detach(),
+        "grads": {n: p.grad.detach().clone() for n, p in student.named_parameters() if p.grad is not None},
+        "no_grad_params": [n for n, p in student.named_parameters() if p.grad is None],
+    }
+    path = os.path.join(HERE, "..", "tests", "golden", name + ".pt")
+    torch.save(out, path)
+    print(name, "loss", float(loss), "bytes", os.path.getsize(path))
+
+
 def main():
     import yaml
     with open(os.path.join(REF, "data/conf/fithubert.yaml")) as f:
@@ -146,6 +198,9 @@ def main():
     run_case("tiny_hubert_pad", TINY_STUDENT, TINY_TEACHER, 3, 9000, [9000, 7411, 5000], ycfg)
     run_case("tiny_hubert_nopad", TINY_STUDENT, TINY_TEACHER, 2, 6500, [6500, 6500], ycfg)
     run_case("tiny_w2v2_pad_oddT", TINY_STUDENT, TINY_TEACHER, 2, 8100, [8100, 4321], ycfg, kind="wav2vec2")
+    with open(os.path.join(REF, "data/conf/ex.yaml")) as f:
+        ecfg = yaml.safe_load(f)["distiller"]
+    run_case_split("split_hubert_pad", TINY_SPLIT_STUDENT, TINY_TEACHER, 3, 9000, [9000, 7411, 5000], ecfg)
 
 
 if __name__ == "__main__":

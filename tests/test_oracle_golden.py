@@ -48,6 +48,40 @@ def test_oracle_matches_reference_fixture(path):
         assert ssd[n].grad is None
 
 
+def test_oracle_matches_reference_fixture_split_head():
+    """ex.yaml recipe (DistilHuBERT head, no TR layer, feature_grad_mult 0.1, L1 + cosine loss) - the fixture was produced
+    by the unmodified reference through oracle/fairseq_stub (oracle/gen_golden.py::run_case_split)."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "split_hubert_pad.pt"))
+    scfg = O.student_config(**g["student_cfg"])
+    tcfg = O.teacher_config(**g["teacher_cfg"])
+    ssd = {k: v.clone().requires_grad_(True) for k, v in g["student_state"].items()}
+    assert set(ssd) == set(O.init_student_state(dict(scfg, pred_layer_id=g["pred_layer_id"])))
+    s = O.student_forward(ssd, scfg, g["source"], g["padding_mask"])
+    with torch.no_grad():
+        t = O.teacher_forward(g["teacher_state"], tcfg, g["source"], g["padding_mask"])
+    assert torch.equal(s["padding_mask"], g["student_mask"]) and s["tr_layer_results"] == []
+    for i, ref in enumerate(g["student_layers"]):
+        assert relerr(s["layer_results"][i][0], ref) < 1e-5
+    assert relerr(s["x"], g["x"]) < 1e-5 and relerr(s["projections"], g["projections"]) < 1e-5
+    ids = g["pred_layer_id"]
+    # the restated loss takes per-layer lists: unstack the [B, N, T, D] tensor, index the teacher by pred_layer_id
+    preds = {i: s["projections"][:, n] for n, i in enumerate(ids)}
+    loss, rec, sim = O.distill_loss_sim(preds, t["layer_results"], ids, "l1", 1.0, 1.0)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert relerr(rec, g["rec_layer"]) < 1e-5 and relerr(sim, g["sim_layer"]) < 1e-5
+    loss.backward()
+    for n, ref in g["grads"].items():
+        assert ssd[n].grad is not None, n
+        assert float((ssd[n].grad - ref).abs().max()) < 2e-4 * float(ref.abs().max()) + 1e-8, n
+    # feature_grad_mult really is 0.1: the conv gradients are one tenth of what an un-scaled run gives
+    ssd2 = {k: v.clone().requires_grad_(True) for k, v in g["student_state"].items()}
+    s2 = O.student_forward(ssd2, dict(scfg, feature_grad_mult=1.0), g["source"], g["padding_mask"])
+    l2, _, _ = O.distill_loss_sim({i: s2["projections"][:, n] for n, i in enumerate(ids)}, t["layer_results"], ids, "l1")
+    l2.backward()
+    k = "feature_extractor.conv_layers.3.0.weight"
+    assert relerr(ssd2[k].grad * 0.1, g["grads"][k]) < 1e-4
+
+
 def test_conv_layer_string_parser():
     assert O.parse_conv_layers(O.FITHUBERT_CONV) == [(128, 10, 5), (256, 1, 1)] + [(256, 3, 2)] * 4 + [(512, 1, 1)] + [(512, 2, 2)] * 2
     assert len(O.parse_conv_layers(O.HUBERT_CONV)) == 7
