@@ -93,8 +93,17 @@ class CustomStudentModelConfig:
             raise NotImplementedError("only activation_fn='gelu' is implemented")
         if self.pos_conv_depth != 1:
             raise NotImplementedError("pos_conv_depth > 1 is not implemented")
-        if not self.layerwise_proj:
-            raise NotImplementedError("DistilHuBERT-style SplitLinear head (layerwise_proj=False) is a 'next' row")
+        if self.layerwise_proj:
+            # FitHuBERT recipe (data/conf/fithubert.yaml): 12 LayerWiseProjHeads behind a conv1d TR layer at index 0
+            if not self.enable_tr_layer:
+                raise NotImplementedError("layerwise_proj=True without a time-reduction layer is not implemented")
+        else:
+            # DistilHuBERT-style recipe (data/conf/ex.yaml): Linear -> GELU -> SplitLinear on the last layer, no TR layer
+            if self.enable_tr_layer:
+                raise NotImplementedError("layerwise_proj=False with a TR layer (shared upsampler, modules/model.py:"
+                                          "504-505) is not implemented")
+            if len(parse_int_list(self.pred_layer_id)) < 2:
+                raise NotImplementedError("the SplitLinear head needs at least two pred_layer_id entries")
         if self.enable_tr_layer:
             if self.tr_layer_type != "conv1d":
                 raise NotImplementedError(
@@ -104,14 +113,12 @@ class CustomStudentModelConfig:
                     "fc1/fc2 time-reduction layers are broken in the reference (SURVEY 2.1) and not implemented")
             if self.tr_layer_index != 0 or self.tr_reduce_factor != 2:
                 raise NotImplementedError("time-reduction layer must be conv1d, index 0, factor 2")
-        else:
-            raise NotImplementedError("enable_tr_layer=False is not implemented on the student path")
         if self.required_seq_len_multiple != 1 or self.crop_seq_to_multiple != 1:
             raise NotImplementedError("required_seq_len_multiple / crop_seq_to_multiple must be 1")
         if self.encoder_layerdrop != 0.0:
             raise NotImplementedError("encoder_layerdrop must be 0")
-        if self.feature_grad_mult != 1.0:
-            raise NotImplementedError("feature_grad_mult must be 1.0")
+        if not (0.0 < self.feature_grad_mult <= 1.0):
+            raise NotImplementedError("feature_grad_mult must be in (0, 1] (0 freezes the extractor: not implemented)")
         layers = parse_layer_spec(self.conv_feature_layers)
         assert all(len(cl) == 3 for cl in layers), "invalid conv definition"
         if layers[0][1:] != (10, 5):

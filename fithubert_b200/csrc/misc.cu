@@ -408,7 +408,7 @@ mul_dgelu_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, const __
 // out[b][i] = a[b][i] * m[b][i] (m = a saved multiplier, e.g. gelu' from FHB_EPI_AUX_DGELU)
 __global__ void __launch_bounds__(256)
 mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_bfloat16* __restrict__ m, long long m_bs,
-                __nv_bfloat16* __restrict__ out, long long out_bs, long long nvec) {
+                __nv_bfloat16* __restrict__ out, long long out_bs, long long nvec, float alpha) {
   pdl_sync();
   const int b = blockIdx.y;
   const uint4* a4 = reinterpret_cast<const uint4*>(a + b * a_bs);
@@ -421,7 +421,7 @@ mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(cc[j]);
-      o[j] = pack_bf16(p.x * q.x, p.y * q.y);
+      o[j] = pack_bf16(alpha * p.x * q.x, alpha * p.y * q.y);
     }
     o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -611,7 +611,7 @@ extern "C" int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, 
 }
 
 extern "C" int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstride, void* out,
-                            int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream) {
+                            int64_t out_bstride, int32_t B, int64_t n, float alpha, fhb_stream_t stream) {
   FHB_ARG_CHECK(a && m && out && B > 0, "mul_bf16: null pointer");
   FHB_ARG_CHECK(n % 8 == 0 && a_bstride % 8 == 0 && m_bstride % 8 == 0 && out_bstride % 8 == 0,
                 "mul_bf16: sizes and strides must be multiples of 8 elements");
@@ -620,7 +620,7 @@ extern "C" int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int
   gx = (gx + B - 1) / B;
   FHB_CUDA_CHECK(fhb_launch(mul_bf16_kernel, dim3(dim3(gx < 1 ? 1 : gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(a), a_bstride, static_cast<const __nv_bfloat16*>(m), m_bstride,
-      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8));
+      static_cast<__nv_bfloat16*>(out), out_bstride, n / 8, alpha));
   FHB_LAUNCH_CHECK();
   return 0;
 }

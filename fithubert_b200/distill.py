@@ -81,7 +81,23 @@ class W2V2Distil(nn.Module):
             raise NotImplementedError("delete_projections=True leaves nothing to distil on this path")
         self.num_encoders = self.model_cfg["encoder_layers"]
         n = self.num_encoders
-        if t["distil_random_layer"] > 0:
+        self.split_head = not self.student_model.layerwise_proj
+        self.tgt_slots = None  # teacher layer -> row of the stacked target buffer (split head only)
+        if self.split_head:
+            # ex.yaml recipe (train.py:268-281 with layerwise_proj False): task k of the SplitLinear head is matched with
+            # teacher layer pred_layer_id[k]; plain means over all tasks (train.py:294-297)
+            if t["distil_random_layer"] > 0:
+                raise NotImplementedError("distil_random_layer > 0 indexes a list of per-layer projections; the "
+                                          "SplitLinear head returns one tensor (train.py:258-267)")
+            ids = self.student_model.pred_layer_id
+            n_teacher = len(self.teacher_model.model.encoder.layers)
+            assert max(ids) < n_teacher, "pred_layer_id exceeds the teacher depth"
+            self.tgt_slots = [ids.index(l) if l in ids else None for l in range(n_teacher)]
+            n = len(ids)
+            w = [1.0 / n] * n
+            self.rand_l = []
+            self.mean_over_layers = True
+        elif t["distil_random_layer"] > 0:
             # train.py:88-91: a random subset of the lower layers, each weighted random_layer_weight
             self.all_enc = range(n - 1)
             self.rand_l = random.sample(self.all_enc, t["distil_random_layer"])
@@ -99,6 +115,7 @@ class W2V2Distil(nn.Module):
                 w[l] = 1.0 / len(ids)
             self.rand_l = []
             self.mean_over_layers = True
+        self.n_pred = n  # rows of the stacked prediction / target buffers
         self.layer_weights_host = w
         self.layer_weights = torch.tensor(w, dtype=torch.float32, device=dev)
         self.batch_size = t["batch_size"]
@@ -120,20 +137,26 @@ class W2V2Distil(nn.Module):
         from .autograd import _DistillLossFn
         if labels is not None or not self.task_agnostic:
             raise NotImplementedError("task-specific (CTC) teacher path is dead code in the reference and not built")
-        preds = torch.stack(student_results["projections"], 0) if not isinstance(
-            student_results["projections"], torch.Tensor) else student_results["projections"]
-        base = student_results["projections"][0]
-        if isinstance(student_results["projections"], list) and base._base is not None and \
-                base._base.shape[0] == len(student_results["projections"]):
-            preds = base._base  # the engine's stacked [n, B, T', D] buffer: no copy
+        tgt = teacher_results["_stacked"]
+        if self.split_head:
+            # projections is ONE [B, N, T, D] tensor (a view of the engine's [N, B, T, D] buffer); targets are the
+            # teacher layers pred_layer_id (train.py:268-281)
+            preds = student_results["projections"].permute(1, 0, 2, 3).contiguous()
+            tgt = tgt[self.student_model.pred_layer_id]
+        else:
+            preds = torch.stack(student_results["projections"], 0) if not isinstance(
+                student_results["projections"], torch.Tensor) else student_results["projections"]
+            base = student_results["projections"][0]
+            if isinstance(student_results["projections"], list) and base._base is not None and \
+                    base._base.shape[0] == len(student_results["projections"]):
+                preds = base._base  # the engine's stacked [n, B, T', D] buffer: no copy
         lt = 0 if self.rec_loss_type == "mse" else 1
         if self.sim_loss_weight:
-            total, rec, sim = _DistillLossFn.apply(preds, teacher_results["_stacked"], self.layer_weights, lt,
+            total, rec, sim = _DistillLossFn.apply(preds, tgt, self.layer_weights, lt,
                                                    float(self.rec_loss_weight), float(self.sim_loss_weight))
             per_layer = rec + sim  # train.py:316 feat_loss = rec_layer_loss + sim_layer_loss (un-weighted sum)
         else:
-            total, per_layer = _DistillLossFn.apply(preds, teacher_results["_stacked"], self.layer_weights, lt,
-                                                    float(self.rec_loss_weight))
+            total, per_layer = _DistillLossFn.apply(preds, tgt, self.layer_weights, lt, float(self.rec_loss_weight))
         losses = self._loss_dict(per_layer)
         return total, losses
 
@@ -145,8 +168,9 @@ class W2V2Distil(nn.Module):
                 losses[f"rand_l{i}"] = per_layer[l]
             losses[f"l{n - 1}"] = per_layer[n - 1]
         else:
-            for pred_id in self.student_model.pred_layer_id:
-                losses[f"layer{pred_id}"] = per_layer[pred_id] * len(self.student_model.pred_layer_id)
+            ids = self.student_model.pred_layer_id
+            for k, pred_id in enumerate(ids):  # split head: row k of the stacked buffers; layer-wise heads: row pred_id
+                losses[f"layer{pred_id}"] = per_layer[k if self.split_head else pred_id] * len(ids)
         return losses
 
     # ------------------------------------------------------------------ fused training path
@@ -181,11 +205,11 @@ class W2V2Distil(nn.Module):
         else:
             t_valid = None if lengths is None else conv_out_lengths(lengths, tm._conv_layers)
         s_valid = None if lengths is None else conv_out_lengths(lengths, sm._conv_layers)
-        n, B, D = self.num_encoders, x.shape[0], sm._geom.d_out
+        n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
         Pt, Wt = tm.engine_state()
         if self._tgt_buf is None or self._tgt_buf.shape[1:3] != (B, T):
             self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=bf16)
-        tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf)
+        tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots)
         P, W, G = sm.engine_state(True)
         c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -194,6 +218,8 @@ class W2V2Distil(nn.Module):
         # (batched heads only; the per-head fallback path computes its own column sums)
         fused = getattr(c, "heads_batched", False) and G.head_stride() is not None
         dcs = torch.zeros(n, D, device=dev, dtype=torch.float32) if fused else None
+        if self.split_head:  # column sums of dpred = SplitLinear bias gradient [1, 1, N, D]: accumulate it in place
+            fused, dcs = True, G.view("proj_head.2.bias")
         lt = 0 if self.rec_loss_type == "mse" else 1
         if self.sim_loss_weight:
             sim_loss = torch.zeros(n, device=dev, dtype=torch.float32)

@@ -73,7 +73,8 @@ class DropCfg:
 
 
 class Geometry:
-    def __init__(self, conv_layers, E, F, H, G, kpos, n_layers, d_out=0, student=True):
+    def __init__(self, conv_layers, E, F, H, G, kpos, n_layers, d_out=0, student=True, tr=None, n_split=0, inter=0,
+                 grad_mult=1.0):
         self.conv_layers = [tuple(c) for c in conv_layers]
         self.E, self.F, self.H, self.G, self.kpos, self.n_layers = E, F, H, G, kpos, n_layers
         self.d = E // H
@@ -84,6 +85,10 @@ class Geometry:
         self.kpx = kpos + (self.pdelta if self.pdelta > 1 else 0)  # taps of the blocked weight operand
         self.d_out = d_out
         self.student = student
+        self.tr = student if tr is None else bool(tr)  # time-reduction conv at encoder.layers[0]
+        self.n_split = n_split                          # > 0: DistilHuBERT head (Linear -> GELU -> SplitLinear), N tasks
+        self.inter = inter or E
+        self.grad_mult = float(grad_mult)               # feature_grad_mult (GradMultiply on the conv features)
         self.c_feat = self.conv_layers[-1][0]
 
 
@@ -126,7 +131,7 @@ class WeightSet:
 
         lin("pp.w", "post_extract_proj.weight", E, g.c_feat)
         off = 0
-        if g.student:
+        if g.tr:
             add("tr.w", bf16, (E, 2, E), [("encoder.layers.0.weight", 0, (2 * E, 1, 2), 0)])
             off = 1
         for l in range(g.n_layers):
@@ -138,7 +143,12 @@ class WeightSet:
             lin(f"l{l}.wo", p + "self_attn.out_proj.weight", E, E)
             lin(f"l{l}.w1", p + "fc1.weight", F, E)
             lin(f"l{l}.w2", p + "fc2.weight", E, F)
-        if g.student:
+        if g.student and g.n_split and "proj_head.2.weight" in self.params:
+            # DistilHuBERT head (modules/module.py:585-619): Linear(E, N * inter) and the SplitLinear weight
+            # [N][inter][D] transposed per task to the K-major [D][inter] the forward GEMM consumes
+            lin("sp.w1", "proj_head.0.weight", g.n_split * g.inter, E)
+            add("sp.w2", bf16, (g.n_split, g.d_out, g.inter), [("proj_head.2.weight", 0, (g.inter * g.d_out, 1, g.d_out), 0)])
+        elif g.student:
             for i in range(g.n_layers):
                 p = f"proj_head.{i}."
                 if p + "upsampler.weight" not in self.params:
@@ -263,9 +273,12 @@ class GradStore:
                    "encoder.pos_conv.0.bias", "encoder.pos_conv.0.weight_g", "encoder.pos_conv.0.weight_v",
                    "encoder.layer_norm.weight", "encoder.layer_norm.bias"):
             plain(pn)
-        order.append(("encoder.layers.0.weight", (E, E, 2), (2 * E, 1, E)))
-        plain("encoder.layers.0.bias")
-        for l in range(1, g.n_layers + 1):
+        off = 0
+        if g.tr:
+            order.append(("encoder.layers.0.weight", (E, E, 2), (2 * E, 1, E)))
+            plain("encoder.layers.0.bias")
+            off = 1
+        for l in range(off, g.n_layers + off):
             p = f"encoder.layers.{l}."
             for nm in "qkv":
                 plain(p + f"self_attn.{nm}_proj.weight")
@@ -275,7 +288,10 @@ class GradStore:
                        "self_attn_layer_norm.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias",
                        "final_layer_norm.weight", "final_layer_norm.bias"):
                 plain(p + pn)
-        for i in range(g.n_layers):
+        if g.n_split and "proj_head.2.weight" in params:
+            for pn in ("proj_head.0.weight", "proj_head.0.bias", "proj_head.2.weight", "proj_head.2.bias"):
+                plain(pn)
+        for i in range(g.n_layers if not g.n_split else 0):
             p = f"proj_head.{i}."
             if p + "upsampler.weight" not in params:
                 continue
@@ -481,20 +497,29 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
 # =============================================================================================
 # teacher
 # =============================================================================================
-def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None):
+def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None, slots=None):
     """Frozen teacher forward (reference utils/utils.py:80-99 around fairseq HubertModel /
-    Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] bf16, features [B, T, E])."""
+    Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] bf16, features [B, T, E]).
+    slots: optional list mapping teacher layer -> row of out_buf (None = not a distillation target: that layer's
+    output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather."""
     W.ensure_fresh()
     valid_t = _valid_tensor(valid, wave.device)
     c = frontend_fwd(P, W, g, wave, valid_t, save=False)
     B, T, E = c.B, c.T, g.E
     if out_buf is None:
-        out_buf = torch.empty(g.n_layers, B, T, E, device=wave.device, dtype=bf16)
+        n_out = g.n_layers if slots is None else 1 + max(s for s in slots if s is not None)
+        out_buf = torch.empty(n_out, B, T, E, device=wave.device, dtype=bf16)
     x = c.enc_in
-    lrs = []
-    for l in range(g.n_layers):
-        s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=False,
-                      out=out_buf[l].view(B * T, E))
+    scratch = None
+    last = g.n_layers if slots is None else 1 + max(l for l, s in enumerate(slots) if s is not None)
+    for l in range(last):  # layers above the highest target are never needed
+        slot = l if slots is None else slots[l]
+        if slot is None:
+            scratch = [torch.empty(B * T, E, device=wave.device, dtype=bf16) for _ in range(2)] if scratch is None else scratch
+            dst = scratch[l & 1]
+        else:
+            dst = out_buf[slot].view(B * T, E)
+        s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=False, out=dst)
         x = s.out
     return out_buf, c.feats.view(B, T, E)
 
@@ -515,30 +540,50 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         drop = None
     c = frontend_fwd(P, W, g, wave, valid_t, save=train, drop=drop)
     B, T, E = c.B, c.T, g.E
-    Ts = T // 2
+    if g.tr:
+        Ts = T // 2
+        # time-reduction Conv1d(k=2, s=2) (modules/module.py:317-321): reshaped-view GEMM, drops an odd tail frame
+        tr = torch.empty(B * Ts, E, device=dev, dtype=bf16)
+        a3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
+        b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
+        K.gemm_raw(a3, b3, tr, Ts, E, 2 * E, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=Ts * E,
+                   flags=L.EPI_BIAS, bias=P["encoder.layers.0.bias"])
+        off = 1
+    else:  # ex.yaml: enable_tr_layer False - the layers run at the full frame rate, mask rule M1 un-reduced
+        Ts, tr, valid_s, off = T, None, valid_t, 0
     c.Ts, c.valid_t, c.valid_s, c.drop = Ts, valid_t, valid_s, drop
-    # time-reduction Conv1d(k=2, s=2) (modules/module.py:317-321): reshaped-view GEMM, drops an odd tail frame
-    tr = torch.empty(B * Ts, E, device=dev, dtype=bf16)
-    a3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
-    b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
-    K.gemm_raw(a3, b3, tr, Ts, E, 2 * E, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=Ts * E,
-               flags=L.EPI_BIAS, bias=P["encoder.layers.0.bias"])
     c.tr = tr
-    x = tr
+    x = tr if tr is not None else c.enc_in
     c.layer_ctx = []
     lay = torch.empty(g.n_layers, B * Ts, E, device=dev, dtype=bf16)  # stacked layer outputs (batched heads)
     for l in range(g.n_layers):
-        s = layer_fwd(P, W, g, f"encoder.layers.{l + 1}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l],
+        s = layer_fwd(P, W, g, f"encoder.layers.{l + off}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l],
                       drop=drop)
         c.layer_ctx.append(s)
         x = s.out
     c.lay = lay
     c.layers = [s.out for s in c.layer_ctx]
     c.lrs = [s.lr for s in c.layer_ctx]
-    # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E]
-    Tq = 2 * Ts
     D = g.d_out
     n = g.n_layers
+    if g.n_split:
+        # DistilHuBERT head on the last layer (modules/model.py:504-518): Linear(E, N * inter) -> GELU -> SplitLinear
+        # (modules/module.py:585-619) = one GEMM + one GEMM batched over the N tasks; preds [N, B, T, D]
+        c.Tq, c.head_idx, c.heads_batched, c.preds = Ts, [], False, None
+        if heads == "all":
+            N, inter = g.n_split, g.inter
+            c.sp_u = torch.empty(B * Ts, N * inter, device=dev, dtype=bf16) if train else None
+            c.sp_h = K.linear(c.layers[-1], W["sp.w1"].view(N * inter, E), P["proj_head.0.bias"], gelu=True, dgelu_out=c.sp_u)
+            if pred_buf is None:
+                pred_buf = torch.empty(N, B, Ts, D, device=dev, dtype=bf16)
+            a3 = L.tensor3(data_ptr=c.sp_h.data_ptr(), dim=(inter, B * Ts, N), stride=(N * inter, inter))
+            b3 = L.tensor3(data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
+            K.gemm_raw(a3, b3, pred_buf, B * Ts, D, inter, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=D,
+                       d_hi_stride=B * Ts * D, flags=L.EPI_BIAS, bias=P["proj_head.2.bias"], bias_hi_stride=D)
+            c.preds = pred_buf
+        return c
+    # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E]
+    Tq = 2 * Ts
     idx = list(range(n)) if heads == "all" else ([n - 1] if heads == "last" else [])
     c.head_idx = idx
     hs = {k: W.head_stride(k) for k in ("wup", "bup", "wlin", "blin")} if heads == "all" else {}
@@ -597,6 +642,24 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     n = g.n_layers
     gs = G_.head_stride() if getattr(c, "heads_batched", False) else None
     dx_head = None
+    if g.n_split:
+        # ---- DistilHuBERT head backward: SplitLinear (batched over the N tasks), GELU, Linear.  dpred [N, B, T, D];
+        #      the SplitLinear bias gradient (column sums of dpred) was accumulated by the loss kernel or is summed here
+        N, inter, rows = g.n_split, g.inter, B * Ts
+        if dpred_colsum is None:
+            K.colsum_batched(dpred.view(N, rows, D), gv("proj_head.2.bias"), D)
+        a3 = L.tensor3(data_ptr=c.sp_h.data_ptr(), dim=(inter, rows, N), stride=(N * inter, inter))
+        b3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, rows, N), stride=(D, rows * D))
+        K.gemm_raw(a3, b3, gv("proj_head.2.weight"), inter, D, rows, a_major=1, b_major=1, num_ob=N, a_coord=(0, 1, 0, 0),
+                   b_coord=(0, 1, 0, 0), d_ld=D, d_hi_stride=inter * D, flags=L.EPI_ATOMIC_ADD)
+        dh = torch.empty(rows, N * inter, device=dev, dtype=bf16)  # d(pre-GELU): x gelu'(u) in the epilogue
+        a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, rows, N), stride=(D, rows * D))
+        b3 = L.tensor3(data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
+        K.gemm_raw(a3, b3, dh, rows, inter, D, b_major=1, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
+                   d_ld=N * inter, d_hi_stride=inter, flags=L.EPI_MUL_AUX, aux_in=c.sp_u)
+        K.colsum(dh, gv("proj_head.0.bias"))
+        K.linear_wgrad(dh, c.layers[-1], out=gv("proj_head.0.weight").view(N * inter, E), accumulate=True)
+        dx = K.linear_dgrad(dh, W["sp.w1"].view(N * inter, E))
     if gs is not None:
         # ---- all n projection heads at once (ob = head): 2 wgrad + 2 dgrad batched GEMMs, 1-2 column sums
         hs = c.head_strides
@@ -623,9 +686,10 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         b3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
         K.gemm_raw(a3, b3, dx_head, B * Ts, E, 2 * E, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=E, d_hi_stride=B * Ts * E)
+    off = 1 if g.tr else 0
     for l in range(g.n_layers - 1, -1, -1):
         s = c.layer_ctx[l]
-        p = f"encoder.layers.{l + 1}."
+        p = f"encoder.layers.{l + off}."
         hp = f"proj_head.{l}."
         dx2 = None  # second gradient stream into this layer's output (summed inside the LayerNorm backward)
         if dx_head is not None:
@@ -691,17 +755,20 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         dx = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1)
     if dx is None:
         return
-    # ---- time-reduction conv backward
-    K.colsum(dx, gv("encoder.layers.0.bias"))
-    dy3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
-    x3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
-    _wgrad(dy3, x3, gv("encoder.layers.0.weight").view(E, 2 * E), E, 2 * E, Ts, num_cb=B, a_cb=1, b_cb=1)
-    denc = torch.empty(B * T, E, device=dev, dtype=bf16)
-    if T % 2:  # the odd tail frame was dropped by the TR conv: zero gradient
-        K.zero_rows(denc, (T - 1) * E, T * E, E, B)
-    a3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
-    b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
-    K.gemm_raw(a3, b3, denc, Ts, 2 * E, E, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * E, d_hi_stride=T * E)
+    if g.tr:
+        # ---- time-reduction conv backward
+        K.colsum(dx, gv("encoder.layers.0.bias"))
+        dy3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
+        x3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
+        _wgrad(dy3, x3, gv("encoder.layers.0.weight").view(E, 2 * E), E, 2 * E, Ts, num_cb=B, a_cb=1, b_cb=1)
+        denc = torch.empty(B * T, E, device=dev, dtype=bf16)
+        if T % 2:  # the odd tail frame was dropped by the TR conv: zero gradient
+            K.zero_rows(denc, (T - 1) * E, T * E, E, B)
+        a3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
+        b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
+        K.gemm_raw(a3, b3, denc, Ts, 2 * E, E, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * E, d_hi_stride=T * E)
+    else:
+        denc = dx  # no TR layer: the first transformer layer reads the prologue output directly
     # ---- encoder prologue backward: (dropout,) LayerNorm, + pos-conv residual, GELU, grouped conv, mask
     drop = getattr(c, "drop", None)
     d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
@@ -748,7 +815,7 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
                     gv("layer_norm.bias"))
     # dU_last = dY * gelu'(U_last)   (c.u holds the saved gelu' values)
     du = torch.empty(B, T, Cf, device=dev, dtype=bf16)
-    K.mul_bf16(dyl, T * Cf, c.u[last], T * Cf, du, T * Cf, B, T * Cf)
+    K.mul_bf16(dyl, T * Cf, c.u[last], T * Cf, du, T * Cf, B, T * Cf, alpha=g.grad_mult)  # x feature_grad_mult
     # ---- conv stack backward, layers last .. 1.  du: [B, To + 2*halo_i, C_i], data rows start at halo_i
     for i in range(last, 0, -1):
         co, k, s = g.conv_layers[i]

@@ -328,9 +328,10 @@ def mul_dgelu(dy, dy_bs, u, u_bs, out, out_bs, B, n, *, u_off=0, out_off=0):
                                   L.stream_ptr()), "fhb_mul_dgelu")
 
 
-def mul_bf16(a, a_bs, m, m_bs, out, out_bs, B, n):
+def mul_bf16(a, a_bs, m, m_bs, out, out_bs, B, n, alpha=1.0):
+    """out = alpha * a * m (alpha: fairseq GradMultiply's scale, modules/model.py:428-431)."""
     L.check(L.lib().fhb_mul_bf16(L.ptr(a), C.c_int64(a_bs), L.ptr(m), C.c_int64(m_bs), L.ptr(out), C.c_int64(out_bs), B,
-                                 C.c_int64(n), L.stream_ptr()), "fhb_mul_bf16")
+                                 C.c_int64(n), _f(alpha), L.stream_ptr()), "fhb_mul_bf16")
 
 
 def dropout(x, y, seed, p):

@@ -121,6 +121,16 @@ class LayerWiseProjHead(nn.Module):
         self.lin_proj = nn.Linear(in_dim, out_dim)
 
 
+class SplitLinear(nn.Module):
+    """Parameter container of reference modules/module.py:585-604: weight [N, Din, Dout], bias [1, 1, N, Dout]."""
+
+    def __init__(self, in_dim, in_split, out_dim):
+        super().__init__()
+        self.in_dim, self.in_split, self.out_dim = in_dim, in_split, out_dim
+        self.weight = nn.Parameter(torch.empty(in_split, in_dim, out_dim).uniform_(-(in_dim ** -0.5), in_dim ** -0.5))
+        self.bias = nn.Parameter(torch.empty(1, 1, in_split, out_dim).uniform_(-(in_dim ** -0.5), in_dim ** -0.5))
+
+
 def _named_param_dict(module: nn.Module):
     # detach() shares the version counter with the Parameter (unlike .data), so in-place updates by any
     # optimizer / load_state_dict are seen by WeightSet.signature().  Cached on the module (walking 264 parameters
@@ -218,12 +228,19 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
         self.pred_layer_id = parse_int_list(cfg.pred_layer_id)
         self.n_tasks = len(self.pred_layer_id)
         self.enable_tr_layer = cfg.enable_tr_layer
-        self.upsampler = nn.ConvTranspose1d(cfg.encoder_embed_dim, cfg.encoder_embed_dim,
-                                            kernel_size=cfg.tr_reduce_factor, stride=cfg.tr_reduce_factor)
+        self.upsampler = None
+        if cfg.enable_tr_layer:
+            self.upsampler = nn.ConvTranspose1d(cfg.encoder_embed_dim, cfg.encoder_embed_dim,
+                                                kernel_size=cfg.tr_reduce_factor, stride=cfg.tr_reduce_factor)
         self.layerwise_proj = cfg.layerwise_proj
-        self.proj_head = nn.ModuleList([
-            LayerWiseProjHead(cfg.encoder_embed_dim, cfg.pred_head_final_dim, cfg.enable_tr_layer, cfg.tr_reduce_factor)
-            for _ in range(cfg.encoder_layers)])
+        inter = cfg.pred_head_inter_dim if cfg.pred_head_inter_dim > 0 else cfg.encoder_embed_dim
+        if cfg.layerwise_proj:
+            self.proj_head = nn.ModuleList([
+                LayerWiseProjHead(cfg.encoder_embed_dim, cfg.pred_head_final_dim, cfg.enable_tr_layer, cfg.tr_reduce_factor)
+                for _ in range(cfg.encoder_layers)])
+        else:  # DistilHuBERT style projection (reference modules/model.py:362-368)
+            self.proj_head = nn.Sequential(nn.Linear(cfg.encoder_embed_dim, inter * self.n_tasks), nn.GELU(),
+                                           SplitLinear(inter, self.n_tasks, cfg.pred_head_final_dim))
         self.final_proj = None
         self.specaug = None
         if self.init_conv_layers:
@@ -233,7 +250,9 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             assert teacher_model is not None
             self.init_from_teacher_enc(teacher_model, self.init_encoder_layers)
         self._geom = E.Geometry(layers, cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads,
-                                cfg.conv_pos_groups, cfg.conv_pos, cfg.encoder_layers, cfg.pred_head_final_dim, True)
+                                cfg.conv_pos_groups, cfg.conv_pos, cfg.encoder_layers, cfg.pred_head_final_dim, True,
+                                tr=cfg.enable_tr_layer, n_split=0 if cfg.layerwise_proj else self.n_tasks, inter=inter,
+                                grad_mult=cfg.feature_grad_mult)
         self._weights = None
         self._grads = None
         self._conv_layers = layers
@@ -321,7 +340,11 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
         layer_results = [(lo.view(B, Ts, Em).transpose(0, 1), None,
                           None if lr is None else lr.view(B, Ts, Em).transpose(0, 1))
                          for lo, lr in zip(layers_out, c.lrs)]
-        if heads == "all":
+        if not self.layerwise_proj:
+            # reference modules/model.py:504-518: x stays the encoder output, projections is ONE [B, N, T, D] tensor
+            projections = None if preds is None else preds.permute(1, 0, 2, 3)
+            x = layers_out[-1].view(B, Ts, Em)
+        elif heads == "all":
             projections = [preds[i] for i in range(preds.shape[0])]
             x = projections[-1]
         elif heads == "last":
@@ -333,7 +356,7 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             "padding_mask": mask,
             "features": c.feats.view(B, T, Em),
             "layer_results": layer_results,
-            "tr_layer_results": [c.tr.view(B, Ts, Em).transpose(0, 1)],
+            "tr_layer_results": [] if c.tr is None else [c.tr.view(B, Ts, Em).transpose(0, 1)],
             "projections": projections,
         }
 

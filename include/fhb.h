@@ -278,9 +278,10 @@ int fhb_mul_dgelu(const void* dy, int64_t dy_bstride, const void* u, int64_t u_b
 int fhb_head_bias_grads(const float* colsum_dpred, int64_t cs_stride, const void* wlin, int64_t wlin_stride,
                         float* dlin_bias, float* dup_bias, int64_t grad_stride, int32_t n_heads, int32_t D, int32_t E,
                         fhb_stream_t stream);
-/* out = a * m elementwise (bf16), same batching; m is a multiplier saved by FHB_EPI_AUX_DGELU */
+/* out = alpha * a * m elementwise (bf16), same batching; m is a multiplier saved by FHB_EPI_AUX_DGELU, alpha the
+ * feature_grad_mult of fairseq's GradMultiply (modules/model.py:428-431; 1 for the FitHuBERT recipe) */
 int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstride, void* out,
-                 int64_t out_bstride, int32_t B, int64_t n, fhb_stream_t stream);
+                 int64_t out_bstride, int32_t B, int64_t n, float alpha, fhb_stream_t stream);
 /* nn.Dropout(p) forward AND backward (the op is its own adjoint): y[i] = x[i] * mask(i) / (1 - p) for a flat
  * tensor of n bf16 elements (y may alias x).  mask(i): element pair (2j, 2j+1) shares the 32-bit murmur3-finalised
  * hash of (j * 0x9E3779B1 + seed); element keeps iff its 16-bit half >= round(p * 65536).  Every fused dropout

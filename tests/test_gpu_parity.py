@@ -553,6 +553,61 @@ def test_distil_module_with_cosine_loss(F):
         F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
 
 
+def test_split_head_recipe_matches_reference_fixture(F):
+    """data/conf/ex.yaml recipe (DistilHuBERT Linear -> GELU -> SplitLinear head on the last layer, no TR layer,
+    feature_grad_mult 0.1, L1 + cosine loss over pred_layer_id) against the fixture the unmodified reference produced:
+    hidden states, the [B, N, T, D] projections, loss, every parameter gradient, and the fused training step."""
+    import bench
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "split_hubert_pad.pt"))
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"].update(init_conv_layers=False, init_encoder_layers=0, dropout_input=0.1)
+    cfg["train"].update(distil_random_layer=0, random_layer_weight=0, rec_loss_type="l1", rec_loss_weight=1.0,
+                        sim_loss_weight=1.0)
+    tc = dict(g["teacher_cfg"])
+    teacher = F.TeacherModel(kind=tc.pop("kind"), **tc)
+    teacher.load_state_dict(g["teacher_state"])
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    student = step.student_model
+    assert set(student.state_dict()) == set(g["student_state"])  # no upsampler / TR conv, proj_head.{0,2}.*
+    student.load_state_dict(g["student_state"])
+    student.eval()
+    x, pm = g["source"], g["padding_mask"]
+    with torch.no_grad():
+        sr = student(x.cuda(), pm)
+    assert torch.equal(sr["padding_mask"].cpu(), g["student_mask"]) and sr["tr_layer_results"] == []
+    for i, ref in enumerate(g["student_layers"]):
+        assert sr["layer_results"][i][0].shape == ref.shape and rel(sr["layer_results"][i][0], ref) < TOL
+    assert sr["projections"].shape == g["projections"].shape and rel(sr["projections"], g["projections"]) < TOL
+    assert rel(sr["x"], g["x"]) < TOL
+    # reference-style API: forward -> calculate_loss -> backward
+    s_res, t_res = step(x.cuda(), pm)
+    total, losses = step.calculate_loss(s_res, t_res)
+    ids = g["pred_layer_id"]
+    assert set(losses) == {f"layer{i}" for i in ids}
+    assert abs(float(total) - float(g["loss"])) < 2e-2 * float(g["loss"])
+    for k, i in enumerate(ids):
+        ref = float(g["rec_layer"][k] + g["sim_layer"][k])
+        assert abs(float(losses[f"layer{i}"]) - ref) < 2e-2 * ref
+    total.backward()
+    for n, p in student.named_parameters():
+        ref = g["grads"][n]
+        if ref.abs().max() < 1e-9:
+            continue
+        assert p.grad is not None and rel(p.grad, ref) < 6e-2, n  # L1's sign gradient is bf16-noise sensitive
+    # fused training step: same loss, parameters move
+    step.configure_optimizers(total_steps=100)
+    before = student.state_dict()["proj_head.2.weight"].clone()
+    loss = step.training_step({"x": x, "padding_mask": pm})
+    assert abs(float(loss) - float(total)) < 1e-3 * float(total)
+    assert not torch.equal(student.state_dict()["proj_head.2.weight"], before)
+    # after _disable_projection_heads the expert-style forward returns the encoder output
+    student._disable_projection_heads()
+    with torch.no_grad():
+        out = student(x.cuda(), pm)
+    assert out["projections"] is None and out["x"].shape == g["x"].shape
+
+
 def test_fused_step_equals_autograd_path_and_updates_weights(F):
     """W2V2Distil.training_step (fused, no autograd) vs the autograd-facing path on the same batch, then one
     optimizer step vs the oracle's AdamW restatement."""
