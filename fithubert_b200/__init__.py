@@ -18,6 +18,12 @@ def __getattr__(name):  # lazy: importing the package must not need CUDA
     if name in ("load_fairseq_teacher", "load_student_state_dict", "load_checkpoint_to_cpu", "student_checkpoint"):
         from . import checkpoint
         return getattr(checkpoint, name)
+    if name in ("LibriDataset", "SyntheticBuckets", "BucketLoader", "shard_indices", "load_audio"):
+        from . import data
+        return getattr(data, name)
+    if name in ("fit", "total_training_steps", "TopKCheckpoints", "EarlyStopping"):
+        from . import trainer
+        return getattr(trainer, name)
     if name in ("FusedAdamW", "GradAllReduce", "warmup_linear"):
         from . import optim
         return getattr(optim, name)

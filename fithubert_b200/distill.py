@@ -251,6 +251,59 @@ class W2V2Distil(nn.Module):
         self.last_layer_losses = layer_loss
         return layer_loss.sum()
 
+    def training_epoch_end(self, training_step_outputs=None):
+        """train.py:172-178: a fresh random subset of the lower layers every epoch (distil_random_layer > 0)."""
+        t = self.train_cfg
+        if t["distil_random_layer"] > 0 and not self.split_head:
+            n = self.num_encoders
+            self.rand_l = random.sample(self.all_enc, t["distil_random_layer"])
+            w = [0.0] * n
+            for l in self.rand_l:
+                w[l] = float(self.random_layer_weight)
+            w[n - 1] = 1.0
+            self.layer_weights_host = w
+            self.layer_weights.copy_(torch.tensor(w, dtype=torch.float32))
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx=0):
+        """train.py:180-203: teacher + student forward and the loss, no gradient; with random-layer distillation the
+        monitored value is the last layer's term only (train.py:198-199)."""
+        sm, tm = self.student_model, self.teacher_model.model
+        dev = sm.post_extract_proj.weight.device
+        x = batch["x"].to(dev, non_blocking=True).float().contiguous()
+        lengths = batch.get("lengths")
+        if lengths is None:
+            lengths = _lengths_from_mask(batch.get("padding_mask"))
+        Ld = x.shape[1]
+        T = E.conv_frames(Ld, tm._conv_layers)[-1]
+        if lengths is None and batch.get("padding_mask") is None:
+            t_valid = None
+        elif tm.kind == "hubert":
+            from .model import hubert_mask_lengths
+            t_valid = hubert_mask_lengths(lengths if lengths is not None else [Ld] * x.shape[0], Ld, T)
+        else:
+            t_valid = None if lengths is None else conv_out_lengths(lengths, tm._conv_layers)
+        s_valid = None if lengths is None else conv_out_lengths(lengths, sm._conv_layers)
+        n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
+        Pt, Wt = tm.engine_state()
+        tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, slots=self.tgt_slots)
+        was_training = sm.training
+        sm.eval()
+        P, W, _ = sm.engine_state(sm._weights.train if sm._weights is not None else False)
+        c = E.student_forward(P, W, sm._geom, x, s_valid, train=False, heads="all")
+        sm.train(was_training)
+        rec = torch.zeros(n, device=dev, dtype=torch.float32)
+        lt = 0 if self.rec_loss_type == "mse" else 1
+        if self.sim_loss_weight:
+            sim = torch.zeros(n, device=dev, dtype=torch.float32)
+            K.distill_loss_sim(c.preds, tgt, self.layer_weights, rec, sim, None, n, B, c.Tq, T, D, lt, 0.0, 0.0)
+            per = rec * self.rec_loss_weight + sim * self.sim_loss_weight
+        else:
+            K.distill_loss(c.preds, tgt, self.layer_weights, rec, None, n, B, c.Tq, T, D, lt, 0.0)
+            per = rec * self.rec_loss_weight
+        loss = per[n - 1] if (self.train_cfg["distil_random_layer"] > 0 and not self.split_head) else per.sum()
+        return {"v_loss": loss}
+
     def optimizer_step(self):
         _, _, G = self.student_model.engine_state(True)
         self.reducer.reduce_all(G.flat)

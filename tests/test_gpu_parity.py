@@ -608,6 +608,46 @@ def test_split_head_recipe_matches_reference_fixture(F):
     assert out["projections"] is None and out["x"].shape == g["x"].shape
 
 
+def test_fit_loop_trains_checkpoints_and_resumes(F, tmp_path):
+    """trainer.fit (the Lightning Trainer features the reference uses, train.py:475-509) on a tiny student / teacher and
+    synthetic length-bucketed data: the loss goes down, validation runs, Lightning-shaped checkpoints are written,
+    UpstreamExpert loads them, and resuming continues from the saved epoch with the saved optimizer state."""
+    import bench
+    from fithubert_b200 import trainer as TR
+    g = torch.load(GOLDEN[1])
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"]["pred_layer_id"] = "[2]"
+    cfg["train"].update(distil_random_layer=2, num_epochs=3, accumulate_grad_batches=2, batch_size=3)
+    cfg["optimizer"]["lr"] = 2e-3
+    torch.manual_seed(0)
+    teacher, _ = build_pair(F, g)
+    step = F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+    step.student_model.load_state_dict(g["student_state"])
+    train = F.BucketLoader(F.SyntheticBuckets(6, 3, 9000, seed=3), shuffle=True, seed=1)
+    val = F.BucketLoader(F.SyntheticBuckets(2, 3, 8000, seed=4), shuffle=False)
+    out = str(tmp_path / "run")
+    rand0 = list(step.rand_l)
+    res = F.fit(step, train, val, num_epochs=3, output_dir=out)
+    assert res["epochs_run"] == 3 and res["global_step"] == 9 and not res["stopped_early"]
+    assert step.optimizer.total_steps == F.total_training_steps(6, 1, 3, 2) == 9
+    hist = res["history"]
+    assert all(v == v for _, _, v in hist) and hist[-1][1] < hist[0][1] and hist[-1][2] < hist[0][2]
+    assert sorted(os.listdir(out)) == ["checkpoint-epoch=00.ckpt", "checkpoint-epoch=01.ckpt", "checkpoint-epoch=02.ckpt", "last.ckpt"]
+    assert len(step.rand_l) == len(rand0)
+    # the reference's own expert reads what we wrote
+    d = dict(cfg["distiller"])
+    expert = F.UpstreamExpert(os.path.join(out, "last.ckpt"), {"distiller": d}).cuda()
+    hs = expert([torch.randn(5000), torch.randn(4000)])["hidden_states"]
+    assert len(hs) == 3 and torch.isfinite(hs[-1][0].float()).all()
+    # resume: a fresh module continues at epoch 3 with the saved moments
+    torch.manual_seed(0)
+    step2 = F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+    res2 = F.fit(step2, train, val, num_epochs=4, output_dir=out, ckpt_path=os.path.join(out, "last.ckpt"))
+    assert res2["epochs_run"] == 1 and res2["history"][0][0] == 3 and res2["global_step"] == 12
+    assert res2["history"][0][2] < hist[0][2]
+
+
 def test_fused_step_equals_autograd_path_and_updates_weights(F):
     """W2V2Distil.training_step (fused, no autograd) vs the autograd-facing path on the same batch, then one
     optimizer step vs the oracle's AdamW restatement."""
