@@ -264,6 +264,21 @@ def main():
         dev_step()
     torch.cuda.synchronize()
     gemm_ms, gemm_flops, gemm_calls = K.gemm_timing_summary()
+    # where the aggregate comes from: the teacher's encoder GEMMs (24 928 rows, K = 768 / 3072) are tensor-bound, the
+    # student's 12 448 x 480 GEMMs are launch / tail-bound, the student conv stack (K = 128 .. 768 over 1.6 M rows) and
+    # the wgrads are HBM-bound
+    Tt = step_obj.teacher_model.model._geom
+    rows_t = B * (((Lmax - 400) // 320) + 1)
+
+    def classify(shape):
+        rows, n, k = shape
+        if rows == rows_t and {n, k} <= {Tt.E, 3 * Tt.E, Tt.F}:
+            return "teacher_encoder"
+        if rows >= 4 * rows_t:
+            return "conv_stacks"
+        return "student_and_rest"
+
+    groups = K.gemm_timing_groups(classify)
     K.enable_gemm_timing(False)
 
     # ---- end to end through the public API with host buffers
@@ -312,6 +327,10 @@ def main():
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": peak_src, "launches_per_step": gemm_calls / max(1, args.steps),
                      "gemm_ms_per_step": gemm_ms / args.steps,
+                     "groups": {g: {"tflops": (f / (ms / 1e3) / 1e12) if ms > 0 else 0.0,
+                                    "frac": (f / (ms / 1e3) / 1e12 / peak) if ms > 0 and peak else None,
+                                    "ms_per_step": ms / args.steps, "launches_per_step": c / args.steps}
+                                for g, (ms, f, c) in sorted(groups.items())},
                      "step_frac": (FLOP_PER_UTT * B * (Lmax / CFG2["Lmax"]) / (ms / args.steps / 1e3) / 1e12) / peak},
         "loss": loss_val,
     }

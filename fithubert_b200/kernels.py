@@ -38,7 +38,18 @@ def gemm_timing_summary():
     """(total ms, total algorithmic flops, launches) of the fhb_gemm launches recorded since enable."""
     torch.cuda.synchronize()
     ev = _GEMM_TIMING["events"]
-    return sum(a.elapsed_time(b) for a, b, _ in ev), float(sum(f for _, _, f in ev)), len(ev)
+    return sum(e[0].elapsed_time(e[1]) for e in ev), float(sum(e[2] for e in ev)), len(ev)
+
+
+def gemm_timing_groups(classify):
+    """{group: (ms, flops, launches)} of the recorded fhb_gemm launches; classify((rows, n, k)) -> group name."""
+    torch.cuda.synchronize()
+    out = {}
+    for e0, e1, fl, shape in _GEMM_TIMING["events"]:
+        g = classify(shape)
+        ms, f, c = out.get(g, (0.0, 0.0, 0))
+        out[g] = (ms + e0.elapsed_time(e1), f + fl, c + 1)
+    return out
 
 
 def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int, *, a_major=0, b_major=0,
@@ -78,7 +89,8 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
         e0.record()
         L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
         e1.record()
-        _GEMM_TIMING["events"].append((e0, e1, 2.0 * m * n * k * max(1, num_ob) * max(1, num_cb)))
+        _GEMM_TIMING["events"].append((e0, e1, 2.0 * m * n * k * max(1, num_ob) * max(1, num_cb),
+                                       (m * max(1, num_ob), n, k * max(1, num_cb))))
         return
     L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
 
