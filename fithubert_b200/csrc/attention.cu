@@ -506,6 +506,7 @@ extern "C" int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* o
   FHB_ARG_CHECK(qkv && out && dout && lse && dqkv && delta_ws, "attn_bwd: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n = (long long)B * T * H;
+  fhb_pdl_hint(true);
   FHB_CUDA_CHECK(fhb_launch(attn_delta_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(out),
                                                                 static_cast<const __nv_bfloat16*>(dout), delta_ws, B, T, H, d));
   FHB_LAUNCH_CHECK();

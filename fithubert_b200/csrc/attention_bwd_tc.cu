@@ -425,6 +425,7 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
   const long long rows = (long long)B * T;
   long long blocks = (rows * (E / 8) + 255) / 256;
   if (blocks > 8LL * fhb_num_sms()) blocks = 8LL * fhb_num_sms();
+  fhb_pdl_hint(true);
   FHB_CUDA_CHECK(fhb_launch(dq_convert_kernel, dim3((unsigned)blocks), dim3(256), 0, s, dq_ws, static_cast<__nv_bfloat16*>(dqkv), rows, (int)(E / 8), 3 * E, scale));
   FHB_LAUNCH_CHECK();
   return 0;

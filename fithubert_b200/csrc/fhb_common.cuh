@@ -45,14 +45,16 @@ static inline int fhb_num_sms() {
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
-// Opt-in (FHB_PDL=1 or fhb_set_pdl(1)): kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization,
-// so their CTAs may be scheduled while the previous kernel of the stream is still draining and the prologue
-// (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail.  Contract: EVERY thread
-// executes pdl_wait() before its first global-memory access and before any exit (it returns once the whole
-// predecessor grid has completed and its writes are visible; a no-op for a normally launched kernel);
-// pdl_trigger() right after it lets the successor's CTAs queue up behind this grid's last wave.
-// Measured on B200 (profiles/r01k_pdl_ab.log, interleaved A/B of the full step): 25.96 ms with, 25.60 ms without -
-// the step is a back-to-back sum of kernel times with no launch gaps to hide, so it stays OFF by default.
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may have their CTAs scheduled while the
+// previous kernel of the stream is still draining, so the launch latency and the prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) overlap the predecessor's tail.  Contract: EVERY thread executes pdl_wait() before
+// its first global-memory access and before any exit (it returns once the whole predecessor grid has completed and
+// its writes are visible; a no-op for a normally launched kernel); pdl_trigger() right after it lets the successor's
+// CTAs queue up behind this grid's last wave.
+// Modes (fhb_set_pdl / FHB_PDL): 0 off, 1 every kernel, 2 (default) only launches the host code hints as a few
+// microseconds long (the student's 12 448-row GEMMs, LayerNorms, column sums ...).  Interleaved A/B of the full step
+// on B200 (profiles/r01y_pdl_ab.log): 23.82 ms off, 23.70 ms all, 23.56 ms small-only - for the long kernels the early
+// co-residency costs more than the hidden latency is worth.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() {
@@ -60,6 +62,7 @@ __device__ __forceinline__ void pdl_sync() {
   pdl_trigger();
 }
 bool fhb_pdl_enabled();
+void fhb_pdl_hint(bool small);
 template <typename... KArgs, typename... Args>
 static inline cudaError_t fhb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args&&... args) {

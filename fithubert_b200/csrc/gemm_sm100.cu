@@ -693,6 +693,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
     attr_set = true;
   }
   const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
+  fhb_pdl_hint((long long)p.total_tiles * (p.kb_per_split < 1 ? 1 : p.kb_per_split) <= 16LL * 3 * fhb_num_sms());
   FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
   FHB_LAUNCH_CHECK();
   return 0;

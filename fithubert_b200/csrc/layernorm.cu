@@ -214,6 +214,7 @@ extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float*
                 C, kMaxVec * 256);
   FHB_ARG_CHECK((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
   if (rows == 0) return 0;
+  fhb_pdl_hint(rows * C <= 16LL << 20);
   FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel, dim3(ln_grid(rows, 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps));
   FHB_LAUNCH_CHECK();
@@ -228,6 +229,7 @@ extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x,
   FHB_ARG_CHECK(!dx_drop || (drop_p >= 0.f && drop_p < 1.f && rows * C < (1LL << 32)), "layernorm_bwd: bad dropout arguments");
   FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_bwd: bad C=%d", C);
   if (rows == 0) return 0;
+  fhb_pdl_hint(rows * C <= 16LL << 20);
   // 2 blocks per SM (register-limited), every warp streams several rows
   long long blocks = (rows + 15) / 16;
   if (blocks > 2LL * fhb_num_sms()) blocks = 2LL * fhb_num_sms();

@@ -564,6 +564,7 @@ extern "C" int fhb_colsum_batched(const void* x, int64_t rows, int32_t C, int64_
   if (chunks > 65535) chunks = 65535;
   const int rpc = (int)((rows + chunks - 1) / chunks);
   chunks = (rows + rpc - 1) / rpc;
+  fhb_pdl_hint(rows * C * batches <= 32LL << 20);
   FHB_CUDA_CHECK(fhb_launch(colsum_kernel, dim3(slices, (unsigned)chunks, batches), dim3(256), 0,
                             static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), rows, C, ld, out,
                             x_bstride, out_bstride, rpc));
@@ -629,6 +630,7 @@ extern "C" int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, flo
   FHB_ARG_CHECK(x && y && n % 8 == 0 && n < (1LL << 32), "dropout: n must be a multiple of 8 and < 2^32");
   FHB_ARG_CHECK(p >= 0.f && p < 1.f, "dropout: p=%f must be in [0, 1)", (double)p);
   if (n == 0) return 0;
+  fhb_pdl_hint(n <= 16LL << 20);
   FHB_CUDA_CHECK(fhb_launch(dropout_kernel, dim3(grid_x(n / 8, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n / 8, seed, fhb_dropout_thr16(p),
       fhb_dropout_scale(p)));

@@ -23,10 +23,11 @@ typedef void* fhb_stream_t; /* cudaStream_t */
 
 const char* fhb_last_error(void);
 int fhb_abi_version(void);
-/* Programmatic dependent launch (off by default; FHB_PDL=1 in the environment or fhb_set_pdl(1) enables it): kernels
- * are then launched so that their prologue overlaps the previous kernel's tail; each waits (griddepcontrol.wait)
- * before its first global-memory access.  Returns the previous setting.  Per-kernel event timing switches it off. */
-int fhb_set_pdl(int enabled);
+/* Programmatic dependent launch.  mode 0 off; 1 every kernel; 2 (default) only kernels the library knows to be a few
+ * microseconds long (FHB_PDL=0 / 1 / 2 in the environment select the initial mode).  A kernel launched this way
+ * overlaps its prologue with the previous kernel's tail and waits (griddepcontrol.wait) before its first global-memory
+ * access.  Returns the previous mode.  Per-kernel event timing switches it off. */
+int fhb_set_pdl(int mode);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
  * D[ob][m][n] = epilogue( sum_{cb,k} A[ob,cb][m][k] * B[ob,cb][n][k] )        bf16 x bf16 -> fp32
