@@ -693,7 +693,10 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
     attr_set = true;
   }
   const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
-  fhb_pdl_hint((long long)p.total_tiles * (p.kb_per_split < 1 ? 1 : p.kb_per_split) <= 16LL * 3 * fhb_num_sms());
+  // "small" = at most ~200 k-blocks per SM: the student's GEMMs and the teacher's encoder GEMMs, not the conv stacks
+  // (swept on B200, profiles/r01y_pdl_ab.log: 7 104 -> 23.61 ms, 30 000 -> 23.55 ms, 150 000 -> 23.68 ms, none -> 23.94 ms)
+  static const long long pdl_limit = getenv("FHB_PDL_GEMM_LIMIT") ? atoll(getenv("FHB_PDL_GEMM_LIMIT")) : 30000;
+  fhb_pdl_hint((long long)p.total_tiles * (p.kb_per_split < 1 ? 1 : p.kb_per_split) <= pdl_limit);
   FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
   FHB_LAUNCH_CHECK();
   return 0;
