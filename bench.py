@@ -26,6 +26,9 @@ SR = 16000
 CFG2 = dict(B=32, Lmax=249600)
 # algorithmic FLOPs per step / per audio-second: SURVEY 8d (408.0 GFLOP per 15.6 s utterance)
 FLOP_PER_UTT = 408.01e9
+# the other BASELINE.json configurations: not the default bench line, selected with --workload
+CFG4 = dict(B=64, Lmax=160000, Lmin=80000, flop_per_utt=35.23e9)    # s3prl UpstreamExpert forward, heads removed
+CFG5 = dict(B=16, Lmax=480000, Lmin=160000, flop_per_utt=843.48e9)  # FitW2V2: wav2vec 2.0 Base teacher, 30 s, mixed
 
 
 def yaml_cfg():
@@ -60,10 +63,20 @@ def synth_lengths(B, Lmax, seed):
     return sorted(lens.tolist(), reverse=True)
 
 
-def synth_batch(B, Lmax, seed, pin=False):
+def synth_lengths_uniform(B, Lmin, Lmax, seed):
+    """cfg-4 / cfg-5: lengths U[Lmin, Lmax] sorted descending, the longest pinned to Lmax."""
     import torch
     g = torch.Generator().manual_seed(seed)
-    lengths = synth_lengths(B, Lmax, seed)
+    lens = torch.randint(Lmin, Lmax + 1, (B,), generator=g)
+    lens[0] = Lmax
+    return sorted(lens.tolist(), reverse=True)
+
+
+def synth_batch(B, Lmax, seed, pin=False, lengths=None):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    if lengths is None:
+        lengths = synth_lengths(B, Lmax, seed)
     x = 0.1 * torch.randn(B, Lmax, generator=g)
     pm = ~(torch.arange(Lmax).unsqueeze(0) < torch.tensor(lengths).unsqueeze(1))
     x.masked_fill_(pm, 0.0)
@@ -180,6 +193,70 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def measure_student_fwd(dev, B, Lmax, Lmin, steps, warmup, seed, world):
+    """cfg-4 of BASELINE.json: the s3prl UpstreamExpert forward (fithubert/expert.py:52-75) - list of B variable-length
+    wavs in, all hidden states out, projection heads removed, no_grad.  `value`: wavs resident in HBM; `e2e`: the same
+    call with pinned HOST wavs (pad + mask on the host, H2D inside the timed region) and a D2H read of the
+    last frame of last_hidden_state."""
+    import torch
+    import torch.distributed as dist
+    import fithubert_b200 as F
+    from fithubert_b200 import kernels as K
+    torch.manual_seed(0)
+    ex = F.UpstreamExpert(None, {"distiller": yaml_cfg()["distiller"]}).to(dev).eval()
+    lengths = synth_lengths_uniform(B, Lmin, Lmax, seed)
+    g = torch.Generator().manual_seed(seed)
+    host = [(0.1 * torch.randn(n, generator=g)).pin_memory() for n in lengths]
+    wavs = [w.to(dev) for w in host]
+    audio_s = sum(lengths) / SR
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        out = ex(wavs)
+    barrier()
+    K.reset_counters()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(steps):
+        out = ex(wavs)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = K.launch_count()
+    assert out["last_hidden_state"].shape[0] == B and len(out["hidden_states"]) == 12
+    for _ in range(2):
+        float(ex(host)["last_hidden_state"][0, -1, 0])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        float(ex(host)["last_hidden_state"][0, -1, 0])
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    flops = CFG4["flop_per_utt"] * (Lmax / CFG4["Lmax"]) * B
+    return {
+        "metric": "student fwd audio-sec/sec", "value": audio_s * world * steps / (ms / 1e3), "unit": "audio-s/s",
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "config": {"workload": f"cfg-4: UpstreamExpert.forward (student inference, all hidden states), {B} wavs "
+                               f"U[{Lmin / SR:.0f} s, {Lmax / SR:.0f} s] per GPU, random-init weights",
+                   "per_gpu_batch": B, "global_batch": B * world, "utterance_s": Lmax / SR,
+                   "l2": "working set > 1 GB (>> 126 MB L2); no explicit flush",
+                   "step_tflops_algorithmic": flops / 1e12},
+        "e2e": {"value": audio_s * world * steps / (e2e_ms / 1e3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": 4 * B * Lmax, "d2h_bytes_per_step": 2,
+                "api": "UpstreamExpert.forward(list of pinned host wavs)"},
+        "gpu_launches": launches,
+        "step_tflops_per_s": flops / (ms / steps / 1e3) / 1e12,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,10 +264,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fhb")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-student-fwd", action="store_true")
     ap.add_argument("--profile", action="store_true", help="2 device steps then exit (for ncu launch lists)")
-    ap.add_argument("--batch", type=int, default=CFG2["B"])
-    ap.add_argument("--lmax", type=int, default=CFG2["Lmax"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+                    help="cfg2 (default, the bench line): distillation step 32 x 15.6 s; cfg4: UpstreamExpert "
+                         "inference forward 64 x <=10 s; cfg5: FitW2V2 distillation step 16 x <=30 s")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--lmax", type=int, default=None)
     args = ap.parse_args()
+    wl = {"cfg2": CFG2, "cfg4": CFG4, "cfg5": CFG5}[args.workload]
+    args.batch = args.batch or wl["B"]
+    args.lmax = args.lmax or wl["Lmax"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -212,10 +296,27 @@ def main():
     torch.manual_seed(0)
     cfg = yaml_cfg()
     cfg["train"]["batch_size"] = args.batch
+    B, Lmax = args.batch, args.lmax
+    if args.workload == "cfg4":
+        out = measure_student_fwd(dev, B, Lmax, CFG4["Lmin"], args.steps, max(args.warmup, 3), 1234 + rank, world)
+        if rank == 0:
+            out.update({"n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                        "dtype": "bf16", "data": "synthetic"})
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    flop_per_utt = FLOP_PER_UTT * (Lmax / CFG2["Lmax"])
+    wl_name = "cfg-2: FitHuBERT distillation step (HuBERT-Base teacher fwd"
+    fixed_lengths = None
+    if args.workload == "cfg5":
+        cfg["teacher"]["teacher_model"] = "wav2vec_small.pt"  # data/conf/fitwav2vec2.yaml: the only recipe difference
+        flop_per_utt = CFG5["flop_per_utt"] * (Lmax / CFG5["Lmax"])
+        wl_name = "cfg-5: FitW2V2 distillation step, mixed lengths U[10 s, 30 s] (wav2vec 2.0 Base teacher fwd"
+        fixed_lengths = synth_lengths_uniform(B, min(CFG5["Lmin"], Lmax), Lmax, 1234 + rank)
     step_obj = F.W2V2Distil(cfg, device=dev)
     step_obj.configure_optimizers(total_steps=1000)
-    B, Lmax = args.batch, args.lmax
-    x_host, pm_host, lengths = synth_batch(B, Lmax, 1234 + rank, pin=True)
+    x_host, pm_host, lengths = synth_batch(B, Lmax, 1234 + rank, pin=True, lengths=fixed_lengths)
     x_dev = x_host.to(dev)
     audio_s = sum(lengths) / SR
 
@@ -313,11 +414,11 @@ def main():
         "metric": "distill-step audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"cfg-2: FitHuBERT distillation step (HuBERT-Base teacher fwd + student fwd/bwd + "
+        "config": {"workload": f"{wl_name} + student fwd/bwd + "
                                f"loss + allreduce + AdamW), {B} x {Lmax / SR:.1f} s per GPU, random-init weights",
                    "per_gpu_batch": B, "global_batch": B * world, "utterance_s": Lmax / SR,
                    "l2": "per-step working set is several GB (>> 126 MB L2); no explicit flush",
-                   "step_tflops_algorithmic": FLOP_PER_UTT * B * (Lmax / CFG2["Lmax"]) / 1e12},
+                   "step_tflops_algorithmic": flop_per_utt * B / 1e12},
         "clocks": clocks,
         "e2e": {"value": audio_s * world * args.steps / (e2e_ms / 1e3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": x_host.numel() * 4 + 4 * B, "d2h_bytes_per_step": 4,
@@ -331,9 +432,14 @@ def main():
                                     "frac": (f / (ms / 1e3) / 1e12 / peak) if ms > 0 and peak else None,
                                     "ms_per_step": ms / args.steps, "launches_per_step": c / args.steps}
                                 for g, (ms, f, c) in sorted(groups.items())},
-                     "step_frac": (FLOP_PER_UTT * B * (Lmax / CFG2["Lmax"]) / (ms / args.steps / 1e3) / 1e12) / peak},
+                     "step_frac": (flop_per_utt * B / (ms / args.steps / 1e3) / 1e12) / peak},
         "loss": loss_val,
     }
+    if args.workload == "cfg2" and world == 1 and not args.no_student_fwd:
+        # the second half of BASELINE.json's metric: student inference forward (cfg-4, s3prl UpstreamExpert)
+        sf = measure_student_fwd(dev, CFG4["B"], CFG4["Lmax"], CFG4["Lmin"], args.steps, 3, 1234, 1)
+        out["student_fwd"] = {k: sf[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+        out["student_fwd"]["workload"] = sf["config"]["workload"]
     if not args.no_cpu_baseline:
         n_utts = 2
         stepf, a_s, cores = cpu_reference_step_fn(n_utts, Lmax)

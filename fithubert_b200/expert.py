@@ -35,10 +35,19 @@ class UpstreamExpert(nn.Module):
 
     @torch.no_grad()
     def forward(self, wavs):
-        wav_lens = torch.LongTensor([len(wav) for wav in wavs])
-        src = pad_sequence(wavs, batch_first=True)
-        padding_mask = ~torch.lt(torch.arange(int(max(wav_lens))).unsqueeze(0), wav_lens.unsqueeze(1))
-        results = self.model(source=src, padding_mask=padding_mask)
+        """fithubert/expert.py:52-75.  The reference pads the wavs and builds `padding_mask = ~(arange(Lmax) < len)`, from
+        which the model recovers `len` again (modules/model.py:449-472); here the lengths go to the model directly and
+        the zero-padded batch is assembled in HBM (one async copy per wav - DMA straight from the caller's buffer when
+        it is pinned or already on the device), so no [B, Lmax] mask or padded host copy is ever made."""
+        wav_lens = [len(wav) for wav in wavs]
+        dev = self.model.post_extract_proj.weight.device
+        if all(w.is_cuda for w in wavs):
+            src = pad_sequence(wavs, batch_first=True)
+        else:
+            src = torch.zeros(len(wavs), max(wav_lens), device=dev, dtype=torch.float32)
+            for i, (w, n) in enumerate(zip(wavs, wav_lens)):
+                src[i, :n].copy_(w, non_blocking=True)
+        results = self.model(source=src, lengths=wav_lens)
         return {"last_hidden_state": results["x"], "hidden_states": results["layer_results"]}
 
 

@@ -315,13 +315,23 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             self._grads = E.GradStore(P, self._geom)
         return P, self._weights, self._grads
 
-    def forward(self, source, padding_mask=None, layer=None):
+    def forward(self, source, padding_mask=None, layer=None, lengths: Optional[List[int]] = None):
+        """Reference modules/model.py:420-552.  `lengths` (not in the reference signature, optional): the per-sample
+        un-padded lengths the caller already knows, i.e. (~padding_mask).sum(-1); when given, the [B, L] mask is
+        neither needed nor scanned (UpstreamExpert builds its mask from these very numbers)."""
         if layer is not None:
             raise NotImplementedError("`layer` early exit is not implemented on the B200 path")
         dev = self.post_extract_proj.weight.device
         _require_cuda(self.post_extract_proj.weight, "CustomStudentModel")
         source = source.to(dev, non_blocking=True).float().contiguous()
-        lengths = _lengths_from_mask(padding_mask)
+        if lengths is None:
+            lengths = _lengths_from_mask(padding_mask)
+        else:
+            lengths = [int(n) for n in lengths]
+            if len(lengths) != source.shape[0] or max(lengths) > source.shape[1] or min(lengths) < 0:
+                raise ValueError("lengths must hold one value in [0, L] per sample")
+            if all(n == source.shape[1] for n in lengths):
+                lengths = None  # no sample is padded: the reference runs mask-free (modules/model.py:449,471-472)
         valid = None if lengths is None else conv_out_lengths(lengths, self._conv_layers)
         heads = "all" if self.proj_head is not None else ("last" if self.final_proj is not None else "none")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
