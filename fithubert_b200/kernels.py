@@ -45,7 +45,7 @@ def gemm_timing_groups(classify):
     """{group: (ms, flops, launches)} of the recorded fhb_gemm launches; classify((rows, n, k)) -> group name."""
     torch.cuda.synchronize()
     out = {}
-    for e0, e1, fl, shape in _GEMM_TIMING["events"]:
+    for e0, e1, fl, shape, _ in _GEMM_TIMING["events"]:
         g = classify(shape)
         ms, f, c = out.get(g, (0.0, 0.0, 0))
         out[g] = (ms + e0.elapsed_time(e1), f + fl, c + 1)
@@ -90,7 +90,8 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
         L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
         e1.record()
         _GEMM_TIMING["events"].append((e0, e1, 2.0 * m * n * k * max(1, num_ob) * max(1, num_cb),
-                                       (m * max(1, num_ob), n, k * max(1, num_cb))))
+                                       (m * max(1, num_ob), n, k * max(1, num_cb)),
+                                       (a_major, b_major, flags, split_k, num_ob)))
         return
     L.check(L.lib().fhb_gemm(C.byref(g), L.stream_ptr()), "fhb_gemm")
 
