@@ -360,10 +360,17 @@ def main():
     loss_val = float(ll.sum())
 
     # ---- same steps again with a CUDA-event pair around every GEMM launch: live kernel time + flops
+    # (single stream for this pass: an event pair only brackets its own kernel when nothing else runs beside it)
+    streams_env = os.environ.get("FHB_STREAMS")
+    os.environ["FHB_STREAMS"] = "0"
     K.enable_gemm_timing(True)
     for _ in range(args.steps):
         dev_step()
     torch.cuda.synchronize()
+    if streams_env is None:
+        del os.environ["FHB_STREAMS"]
+    else:
+        os.environ["FHB_STREAMS"] = streams_env
     gemm_ms, gemm_flops, gemm_calls = K.gemm_timing_summary()
     # where the aggregate comes from: the teacher's encoder GEMMs (24 928 rows, K = 768 / 3072) are tensor-bound, the
     # student's 12 448 x 480 GEMMs are launch / tail-bound, the student conv stack (K = 128 .. 768 over 1.6 M rows) and

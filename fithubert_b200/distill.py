@@ -209,9 +209,19 @@ class W2V2Distil(nn.Module):
         Pt, Wt = tm.engine_state()
         if self._tgt_buf is None or self._tgt_buf.shape[1:3] != (B, T):
             self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=bf16)
-        tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots)
         P, W, G = sm.engine_state(True)
-        c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
+        if E.stream_mode() & 1:
+            # the frozen teacher's forward and the student's forward only meet in the loss: run them on two streams so
+            # that each one's launch tails and HBM-bound kernels fill under the other's GEMMs
+            main, side = torch.cuda.current_stream(), E.side_stream(dev)
+            side.wait_stream(main)  # the H2D copy of x, the previous step's readers of the target buffer
+            with torch.cuda.stream(side):
+                tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots)
+            c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
+            main.wait_stream(side)
+        else:
+            tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots)
+            c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
         # gradient written in place over the projections (they are not needed again)
         # the loss kernel also produces the column sums of the gradient it writes: both head bias gradients follow

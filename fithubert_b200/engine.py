@@ -158,6 +158,7 @@ class WeightSet:
                         continue
                 add(f"h{i}.wup", bf16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
                 add(f"h{i}.bup", f32, (2, E, 1), [(p + "upsampler.bias", 0, (0, 1, 0), 0)])
+                add(f"h{i}.bup16", bf16, (E, 1, 1), [(p + "upsampler.bias", 0, (1, 0, 0), 0)])  # A operand of the bias fold
                 lin(f"h{i}.wlin", p + "lin_proj.weight", g.d_out, E)
                 add(f"h{i}.blin", f32, (g.d_out, 1, 1), [(p + "lin_proj.bias", 0, (1, 0, 0), 0)])
         self.spec = spec
@@ -527,6 +528,38 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
 # =============================================================================================
 # student
 # =============================================================================================
+def head_compose_enabled() -> bool:
+    """Run each LayerWiseProjHead as ONE GEMM against the folded weight (see _compose_heads); FHB_HEAD_COMPOSE=0 keeps
+    the two-GEMM form (A/B on B200, profiles/r01z_streams_ab.log: 22.96 / 23.26 ms -> 22.57 / 22.46 ms per step)."""
+    import os
+    return os.environ.get("FHB_HEAD_COMPOSE", "1") == "1"
+
+
+def _compose_heads(W: WeightSet, g: Geometry, hs: Dict[str, int], n: int):
+    """LayerWiseProjHead (modules/module.py:649-661) is ConvTranspose1d(k=2,s=2) followed by Linear with nothing in
+    between: for output phase p,  pred[2t+p] = x[t] (Wup_p Wlin^T) + (bup Wlin^T + blin).  Fold the two weights once per
+    step (two tiny batched GEMMs + two 1-row GEMMs for the bias) and the 12 heads run as ONE [B*Ts, E] x [E, 2D] GEMM
+    instead of [B*Ts, E] x [E, 2E] followed by [B*2Ts, E] x [E, D]: 38 % fewer head FLOPs forward and backward, the
+    [n, B, 2Ts, E] intermediate is never written, and one bf16 rounding of the activations disappears.
+    Returns Wc [n, 2, D, E] bf16 (K-major [2D, E] per head) and bc [n, 2D] fp32."""
+    E, D = g.E, g.d_out
+    dev = W["h0.wlin"].device
+    Wc = torch.empty(n, 2, D, E, device=dev, dtype=bf16)
+    bc = torch.empty(n, 2 * D, device=dev, dtype=f32)
+    wlin3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+    bup3 = L.tensor3(data_ptr=W["h0.bup16"].data_ptr(), dim=(E, 1, n), stride=(E, hs["bup16"]))
+    for p in range(2):
+        # Wc[h, p] [D x E_in] = Wlin[h] [D x E_out] (K-major) x Wup[h, p] (rows = E_out, E_in contiguous: MN-major B)
+        wup3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr() + 2 * p * E * E, dim=(E, E, n), stride=(E, hs["wup"]))
+        K.gemm_raw(wlin3, wup3, Wc, D, E, E, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E,
+                   d_hi_stride=2 * D * E, d_offset_elems=p * D * E)
+        # bc[h, p*D:(p+1)*D] = bup[h] Wlin[h]^T + blin[h]   (M = 1)
+        K.gemm_raw(bup3, wlin3, bc, 1, D, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=2 * D,
+                   d_hi_stride=2 * D, d_offset_elems=p * D, flags=L.EPI_BIAS, bias=W["h0.blin"],
+                   bias_hi_stride=hs["blin"])
+    return Wc, bc
+
+
 def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], *, train: bool,
                     heads: str = "all", want_lr: bool = False, pred_buf=None, drop: Optional[DropCfg] = None):
     """Student forward (reference modules/model.py:420-552).  heads: 'all' (12 LayerWiseProjHeads),
@@ -591,7 +624,17 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     if idx:
         if pred_buf is None:
             pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=bf16)
-        if c.heads_batched:
+        c.Wc = None
+        if c.heads_batched and head_compose_enabled():
+            hs["bup16"] = W.head_stride("bup16")
+            c.Wc, bc = _compose_heads(W, g, hs, n)
+            a3 = L.tensor3(data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
+            b3 = L.tensor3(data_ptr=c.Wc.data_ptr(), dim=(E, 2 * D, n), stride=(E, 2 * D * E))
+            K.gemm_raw(a3, b3, pred_buf, B * Ts, 2 * D, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
+                       d_ld=2 * D, d_hi_stride=B * Ts * 2 * D, flags=L.EPI_BIAS, bias=bc, bias_hi_stride=2 * D)
+            c.z = None
+            c.head_strides = hs
+        elif c.heads_batched:
             # all n heads as TWO batched GEMMs (ob = head): 12x the tiles per launch, no per-head launch tails
             z = torch.empty(n, B * Tq, E, device=dev, dtype=bf16)
             a3 = L.tensor3(data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
@@ -620,6 +663,65 @@ def _head_name(P, i):
     return f"proj_head.{i}." if f"proj_head.{i}.lin_proj.bias" in P else "final_proj."
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def side_stream(dev) -> "torch.cuda.Stream":
+    """One extra stream per device for work that is off the step's critical path (FHB_STREAMS)."""
+    idx = torch.device(dev).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[idx]
+
+
+def stream_mode() -> int:
+    """FHB_STREAMS bit mask (default 1).  1 = the frozen teacher's forward runs on the side stream beside the student's
+    forward (they only meet in the loss); 2 = the transformer layers' weight-gradient GEMMs and bias column sums run on
+    the side stream beside the dgrad chain; 4 = the conv stack's weight-gradient GEMMs too.  Interleaved A/B on B200
+    (profiles/r01z_streams_compose_ab.log, r01z_streams2_ab.log): bit 1 saves 0.15 - 0.4 ms of a 23 ms step in every
+    pair, bits 2 and 4 are within the noise (every GEMM is a persistent one-CTA-per-SM kernel, so two of them never
+    share an SM and only launch tails overlap) and stay off."""
+    import os
+    return int(os.environ.get("FHB_STREAMS", "1"))
+
+
+class _OffPath:
+    """`with aside(t1, t2, ...):` runs the enclosed launches on the side stream after everything queued so far on the
+    current stream.  The tensors named are main-stream temporaries the side-stream kernels read: they are kept alive
+    until join() (after which the main stream has waited for the side stream), so the caching allocator never hands
+    their blocks out early and - unlike record_stream - the allocation pattern is the same every step.
+    Disabled: a no-op context, everything stays in order."""
+
+    def __init__(self, dev, enabled: bool):
+        self.side = side_stream(dev) if enabled else None
+        self._keep: List[torch.Tensor] = []
+        self._ctx = None
+
+    def __call__(self, *tensors):
+        if self.side is not None:
+            self._keep.extend(t for t in tensors if t is not None)
+        return self
+
+    def __enter__(self):
+        if self.side is None:
+            return self
+        self.side.wait_stream(torch.cuda.current_stream())
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.side is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._keep.clear()
+
+
 def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc: int, num_cb=1, a_cb=0, b_cb=0,
            a_c1_off=0, b_c1_off=0):
     """out[M][N] (fp32, accumulated) += sum over contraction of dy^T x; both MN-major."""
@@ -640,6 +742,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     gv = G_.view
     dx = None  # gradient wrt the current layer's output [B*Ts, E]
     n = g.n_layers
+    mode = stream_mode()
+    aside = _OffPath(dev, bool(mode & 2))       # transformer-layer wgrads / bias column sums
+    aside_conv = _OffPath(dev, bool(mode & 4))  # conv-stack wgrads
     gs = G_.head_stride() if getattr(c, "heads_batched", False) else None
     dx_head = None
     if g.n_split:
@@ -670,6 +775,35 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         # lin_proj.bias += colsum(dpred); upsampler.bias += colsum(dpred) @ Wlin (= colsum of dz below, never re-read)
         K.head_bias_grads(dpred_colsum, W["h0.wlin"], hs["wlin"], G_.from_("proj_head.0.lin_proj.bias"),
                           G_.from_("proj_head.0.upsampler.bias"), gs, n, D, E)
+    if gs is not None and getattr(c, "Wc", None) is not None:
+        # ---- folded heads (see _compose_heads): dWc = dpred^T x, dx = dpred Wc, then the chain rule back to the two
+        #      original weights (four small batched GEMMs) and the rank-1 term of the folded bias
+        rows = B * Ts
+        dWc = torch.empty(n, D, 2, E, device=dev, dtype=bf16)  # [h][d][p][i]
+        a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(2 * D, rows, n), stride=(2 * D, rows * 2 * D))
+        x3 = L.tensor3(data_ptr=c.lay.data_ptr(), dim=(E, rows, n), stride=(E, rows * E))
+        K.gemm_raw(a3, x3, dWc, D, E, rows, a_major=1, b_major=1, num_ob=2 * n, ob_mod=2, a_coord=(D, 1, 0, 0),
+                   b_coord=(0, 1, 0, 0), d_ld=2 * E, d_lo_stride=E, d_hi_stride=D * 2 * E)
+        dx_head = torch.empty(n, rows, E, device=dev, dtype=bf16)
+        b3 = L.tensor3(data_ptr=c.Wc.data_ptr(), dim=(E, 2 * D, n), stride=(E, 2 * D * E))
+        K.gemm_raw(a3, b3, dx_head, rows, E, 2 * D, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
+                   d_ld=E, d_hi_stride=rows * E)
+        wlin3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+        for ph in range(2):
+            dwc3 = L.tensor3(data_ptr=dWc.data_ptr() + 2 * ph * E, dim=(E, D, n), stride=(2 * E, D * 2 * E))
+            wup3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr() + 2 * ph * E * E, dim=(E, E, n), stride=(E, hs["wup"]))
+            # dWlin[h] [D x E_out] += dWc[h, :, ph, :] [D x E_in] x Wup[h, ph] ([E_out][E_in]: K-major B)
+            K.gemm_raw(dwc3, wup3, G_.from_("proj_head.0.lin_proj.weight"), D, E, E, num_ob=n, a_coord=(0, 1, 0, 0),
+                       b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD)
+            # dWup[h, ph] [E_out x E_in] += Wlin[h]^T [E_out x D] x dWc[h, :, ph, :] [D x E_in]   (both MN-major)
+            K.gemm_raw(wlin3, dwc3, G_.from_("proj_head.0.upsampler.weight"), E, E, D, a_major=1, b_major=1, num_ob=n,
+                       a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, d_offset_elems=ph * E * E,
+                       flags=L.EPI_ATOMIC_ADD)
+        # z = x Wup + bup feeds lin_proj: dWlin += colsum(dpred) (x) bup   (n x D x E fp32 elements, one pass)
+        glin = G_.from_("proj_head.0.lin_proj.weight").as_strided((n, D, E), (gs, E, 1))
+        bup = W["h0.bup"].as_strided((n, 1, E), (hs["bup"], E, 1))
+        glin.addcmul_(dpred_colsum.view(n, D, 1), bup)
+    elif gs is not None:
         a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, B * Tq, n), stride=(D, B * Tq * D))
         z3 = L.tensor3(data_ptr=c.z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
         K.gemm_raw(a3, z3, G_.from_("proj_head.0.lin_proj.weight"), D, E, B * Tq, a_major=1, b_major=1, num_ob=n,
@@ -729,10 +863,12 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
                         dy2=dx2, dx_drop=dy2m if d3 is not None else None, drop=d3)
         # FFN (fc2 bias gradient = column sums of dy2m: accumulated by the LayerNorm backward above; the saved
         # s.u = gelu'(u) * activation-dropout mask, s.h = dropped activations)
-        K.linear_wgrad(dy2m, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
+        with aside(dy2m):
+            K.linear_wgrad(dy2m, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
         du = K.linear_dgrad(dy2m, W[f"l{l}.w2"].view(E, F), mul_aux=s.u)
-        K.colsum(du, gv(p + "fc1.bias"))
-        K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
+        with aside(du):
+            K.colsum(du, gv(p + "fc1.bias"))
+            K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
         dx1 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2)
         # attention LayerNorm (same scheme for dropout1 on the out_proj branch)
         dy1 = torch.empty_like(dx1)
@@ -742,18 +878,21 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
                         gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"),
                         dxsum=gv(p + "self_attn.out_proj.bias"), dx_drop=dy1m if d1 is not None else None, drop=d1)
         # attention block (out_proj bias gradient: accumulated by the LayerNorm backward above)
-        K.linear_wgrad(dy1m, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
+        with aside(dy1m):
+            K.linear_wgrad(dy1m, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
         dattn = K.linear_dgrad(dy1m, W[f"l{l}.wo"].view(E, E))
         dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
         delta = torch.empty(B, H, Ts, device=dev, dtype=f32)
         dq_ws = torch.empty(B * Ts, E, device=dev, dtype=f32) if d in (40, 64) else None
         K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5, drop=dl(DropCfg.ATTN),
                    dq_ws=dq_ws)
-        K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
-        K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
-                       accumulate=True)
+        with aside(dqkv):
+            K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
+            K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
+                           accumulate=True)
         dx = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1)
     if dx is None:
+        aside.join()
         return
     if g.tr:
         # ---- time-reduction conv backward
@@ -828,8 +967,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         # wgrad: dW2[co][(j,ci)] += sum_{b,t} dU[b,t,co] * X[b, s*t + j, ci]
         dy3 = L.tensor3(data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
         x3 = L.tensor3(data_ptr=xin.data_ptr() + 2 * in_halo * cin, dim=(k * cin, To, B), stride=(s * cin, in_rows * cin))
-        _wgrad(dy3, x3, gv(f"feature_extractor.conv_layers.{i}.0.weight").view(co, k * cin), co, k * cin, To,
-               num_cb=B, a_cb=1, b_cb=1)
+        with aside_conv(du):
+            _wgrad(dy3, x3, gv(f"feature_extractor.conv_layers.{i}.0.weight").view(co, k * cin), co, k * cin, To,
+                   num_cb=B, a_cb=1, b_cb=1)
         # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1}) (layer 0 included: its forward saved gelu' of the GroupNorm output)
         dprev = torch.empty(B, in_rows, cin, device=dev, dtype=bf16)
         flags, uprev = L.EPI_MUL_AUX, c.u[i - 1]
@@ -877,3 +1017,5 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     else:
         acc = torch.empty(B, C0, 12, device=dev, dtype=f32)
         K.conv0_bwd(c.wave, wv, gm, bt, T0, c.stat, c.mean0, c.rstd0, du, acc, gw, gg, gb, True, dy_is_dz=True)
+    aside.join()
+    aside_conv.join()

@@ -820,3 +820,23 @@ def test_cfg5_w2v2_teacher_30s_and_step(F):
     losses = [float(step.training_step({"x": xb, "padding_mask": pmb})) for _ in range(3)]
     assert all(l == l and l < 1e4 for l in losses)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_unfolded_heads_match_reference_fixture(F, path, monkeypatch):
+    """The default path folds ConvTranspose1d + Linear of every LayerWiseProjHead into one weight per step
+    (engine._compose_heads; test_model_matches_reference_fixture checks projections, loss and the gradients of BOTH
+    original weights and biases through the fold).  FHB_HEAD_COMPOSE=0 keeps the two-GEMM form: same fixture, same
+    tolerances."""
+    monkeypatch.setenv("FHB_HEAD_COMPOSE", "0")
+    test_model_matches_reference_fixture(F, path)
+
+
+@pytest.mark.parametrize("streams,compose", [("7", "0"), ("3", "1"), ("7", "1")])
+def test_side_streams_and_folded_heads_fused_step(F, monkeypatch, streams, compose):
+    """FHB_STREAMS (teacher forward / weight-gradient GEMMs on a side stream) must not change results: the fused step
+    still equals the autograd path and the oracle-checked fixture."""
+    monkeypatch.setenv("FHB_STREAMS", streams)
+    monkeypatch.setenv("FHB_HEAD_COMPOSE", compose)
+    test_fused_step_equals_autograd_path_and_updates_weights(F)
+    test_model_matches_reference_fixture(F, GOLDEN[-1])

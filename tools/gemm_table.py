@@ -29,6 +29,7 @@ def one():
 for _ in range(3):
     one()
 steps = 5
+os.environ["FHB_STREAMS"] = "0"  # one stream: each event pair brackets exactly one kernel
 K.enable_gemm_timing(True)
 for _ in range(steps):
     one()
