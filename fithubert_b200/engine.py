@@ -285,8 +285,9 @@ class GradStore:
                 plain(p + f"self_attn.{nm}_proj.weight")
             for nm in "qkv":
                 plain(p + f"self_attn.{nm}_proj.bias")
-            for pn in ("self_attn.out_proj.weight", "self_attn.out_proj.bias", "self_attn_layer_norm.weight",
-                       "self_attn_layer_norm.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias",
+            # out_proj / fc1 / fc2 weights adjacent: when F == E (FitHuBERT) their three wgrads run as ONE batched GEMM
+            for pn in ("self_attn.out_proj.weight", "fc1.weight", "fc2.weight", "self_attn.out_proj.bias",
+                       "self_attn_layer_norm.weight", "self_attn_layer_norm.bias", "fc1.bias", "fc2.bias",
                        "final_layer_norm.weight", "final_layer_norm.bias"):
                 plain(p + pn)
         if g.n_split and "proj_head.2.weight" in params:
@@ -471,18 +472,23 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
     dev = x.device
     s = SimpleNamespace(x=x)
     qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
-    attn = torch.empty(B * T, E, device=dev, dtype=bf16)
+    # training with F == E: the inputs of out_proj / fc1 / fc2 (attn, x1, h) share one [3, M, E] buffer so that their three
+    # weight-gradient GEMMs run as one batched launch in the backward (wgrad_batch_enabled)
+    xs = torch.empty(3, B * T, E, device=dev, dtype=bf16) if (save and F == E and wgrad_batch_enabled()) else None
+    attn = xs[0] if xs is not None else torch.empty(B * T, E, device=dev, dtype=bf16)
     lse = torch.empty(B, H, T, device=dev, dtype=f32) if save else None
     dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
     K.attn_fwd(qkv, valid_t, attn, lse, B, T, H, d, d ** -0.5, drop=dl(DropCfg.ATTN))
     y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"], residual=x, drop=dl(DropCfg.DROP1))
-    x1 = torch.empty_like(y1)
+    x1 = xs[1] if xs is not None else torch.empty_like(y1)
     s.mean1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
     s.rstd1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
     K.layernorm_fwd(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1,
                     s.mean1, s.rstd1)
     u = torch.empty(B * T, F, device=dev, dtype=bf16) if save else None
-    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u, drop=dl(DropCfg.ACT))
+    h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u, drop=dl(DropCfg.ACT),
+                 out=None if xs is None else xs[2])
+    s.xs = xs
     lr = torch.empty(B * T, E, device=dev, dtype=bf16) if want_lr else None
     y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr, drop=dl(DropCfg.DROP3))
     x2 = out if out is not None else torch.empty_like(y2)
@@ -528,6 +534,12 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
 # =============================================================================================
 # student
 # =============================================================================================
+def wgrad_batch_enabled() -> bool:
+    """FHB_WGRAD_BATCH=0 keeps one weight-gradient launch per Linear (see layer_fwd / student_backward)."""
+    import os
+    return os.environ.get("FHB_WGRAD_BATCH", "1") == "1"
+
+
 def head_compose_enabled() -> bool:
     """Run each LayerWiseProjHead as ONE GEMM against the folded weight (see _compose_heads); FHB_HEAD_COMPOSE=0 keeps
     the two-GEMM form (A/B on B200, profiles/r01z_streams_ab.log: 22.96 / 23.26 ms -> 22.57 / 22.46 ms per step)."""
@@ -855,31 +867,54 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         # fc2 branch (wgrad, dgrad, bias gradient), the plain dy2 continues down the residual.
         drop = getattr(c, "drop", None)
         dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
-        dy2 = torch.empty_like(dx)
+        xs = getattr(s, "xs", None)
+        dys = torch.empty_like(xs) if xs is not None else None  # [dy1m, du, dy2m]: A operands of the batched wgrad
         d3 = dl(DropCfg.DROP3)
-        dy2m = torch.empty_like(dx) if d3 is not None else dy2
+        if dys is not None:
+            dy2m = dys[2]
+            dy2 = torch.empty_like(dx) if d3 is not None else dy2m
+        else:
+            dy2 = torch.empty_like(dx)
+            dy2m = torch.empty_like(dx) if d3 is not None else dy2
         K.layernorm_bwd(dx, s.y2, P[p + "final_layer_norm.weight"], s.mean2, s.rstd2, dy2,
                         gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"), dxsum=gv(p + "fc2.bias"),
                         dy2=dx2, dx_drop=dy2m if d3 is not None else None, drop=d3)
         # FFN (fc2 bias gradient = column sums of dy2m: accumulated by the LayerNorm backward above; the saved
         # s.u = gelu'(u) * activation-dropout mask, s.h = dropped activations)
-        with aside(dy2m):
-            K.linear_wgrad(dy2m, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
-        du = K.linear_dgrad(dy2m, W[f"l{l}.w2"].view(E, F), mul_aux=s.u)
+        if dys is None:
+            with aside(dy2m):
+                K.linear_wgrad(dy2m, s.h, out=gv(p + "fc2.weight").view(E, F), accumulate=True)
+        du = K.linear_dgrad(dy2m, W[f"l{l}.w2"].view(E, F), mul_aux=s.u, out=None if dys is None else dys[1])
         with aside(du):
             K.colsum(du, gv(p + "fc1.bias"))
-            K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
+            if dys is None:
+                K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
         dx1 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2)
         # attention LayerNorm (same scheme for dropout1 on the out_proj branch)
-        dy1 = torch.empty_like(dx1)
         d1 = dl(DropCfg.DROP1)
-        dy1m = torch.empty_like(dx1) if d1 is not None else dy1
+        if dys is not None:
+            dy1m = dys[0]
+            dy1 = torch.empty_like(dx1) if d1 is not None else dy1m
+        else:
+            dy1 = torch.empty_like(dx1)
+            dy1m = torch.empty_like(dx1) if d1 is not None else dy1
         K.layernorm_bwd(dx1, s.y1, P[p + "self_attn_layer_norm.weight"], s.mean1, s.rstd1, dy1,
                         gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"),
                         dxsum=gv(p + "self_attn.out_proj.bias"), dx_drop=dy1m if d1 is not None else None, drop=d1)
         # attention block (out_proj bias gradient: accumulated by the LayerNorm backward above)
-        with aside(dy1m):
-            K.linear_wgrad(dy1m, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
+        with aside(dys if dys is not None else dy1m):
+            if dys is not None:
+                # dW[j] += dys[j]^T xs[j] for j = out_proj, fc1, fc2: one batched split-K launch (ob = j); the three
+                # gradient segments are adjacent in the flat buffer (GradStore order)
+                M_ = B * Ts
+                a3 = L.tensor3(data_ptr=dys.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
+                b3 = L.tensor3(data_ptr=xs.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
+                assert G_.entries[p + "fc1.weight"][0] - G_.entries[p + "self_attn.out_proj.weight"][0] == E * E and \
+                    G_.entries[p + "fc2.weight"][0] - G_.entries[p + "fc1.weight"][0] == E * E
+                K.gemm_raw(a3, b3, G_.from_(p + "self_attn.out_proj.weight"), E, E, M_, a_major=1, b_major=1, num_ob=3,
+                           a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=E * E, flags=L.EPI_ATOMIC_ADD)
+            else:
+                K.linear_wgrad(dy1m, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
         dattn = K.linear_dgrad(dy1m, W[f"l{l}.wo"].view(E, E))
         dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
         delta = torch.empty(B, H, Ts, device=dev, dtype=f32)

@@ -840,3 +840,10 @@ def test_side_streams_and_folded_heads_fused_step(F, monkeypatch, streams, compo
     monkeypatch.setenv("FHB_HEAD_COMPOSE", compose)
     test_fused_step_equals_autograd_path_and_updates_weights(F)
     test_model_matches_reference_fixture(F, GOLDEN[-1])
+
+
+def test_per_linear_wgrad_launches_match_oracle(F, monkeypatch):
+    """Default: the out_proj / fc1 / fc2 weight gradients of a layer run as one batched split-K GEMM (F == E; covered
+    by every gradient check above).  FHB_WGRAD_BATCH=0 keeps one launch per Linear: same oracle comparison."""
+    monkeypatch.setenv("FHB_WGRAD_BATCH", "0")
+    test_oracle_parity_fithubert_group_geometry(F)
