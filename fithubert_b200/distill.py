@@ -189,22 +189,43 @@ class W2V2Distil(nn.Module):
         (rec_loss_weight * rec + sim_loss_weight * sim per layer): their sum is the step's total loss."""
         sm, tm = self.student_model, self.teacher_model.model
         dev = sm.post_extract_proj.weight.device
-        x = x.to(dev, non_blocking=True).float().contiguous()
-        if lengths is None:
-            lengths = _lengths_from_mask(padding_mask)
-        elif all(n == x.shape[1] for n in lengths):
-            lengths = None
+        chunks = None
+        if not x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.shape[0] >= 4:
+            # host batch (what a DataLoader hands over): copied in batch slices on a copy stream; conv layer 0 of the
+            # teacher and of the student start on the first slice while the others are still in flight
+            x, chunks = E.h2d_chunked(x, dev)
+        else:
+            x = x.to(dev, non_blocking=True).float().contiguous()
         Ld = x.shape[1]
         T = E.conv_frames(Ld, tm._conv_layers)[-1]
-        # teacher mask (M3 for HuBERT: applied whenever a mask exists; M1 for wav2vec2)
-        if padding_mask is None and lengths is None:
-            t_valid = None
-        elif tm.kind == "hubert":
-            from .model import hubert_mask_lengths
-            t_valid = hubert_mask_lengths(lengths if lengths is not None else [Ld] * x.shape[0], Ld, T)
-        else:
-            t_valid = None if lengths is None else conv_out_lengths(lengths, tm._conv_layers)
-        s_valid = None if lengths is None else conv_out_lengths(lengths, sm._conv_layers)
+        memo = {}
+
+        def host_lengths():
+            # resolved lazily, AFTER the first conv stack has been queued: scanning a host padding mask takes ~0.7 ms
+            # for 32 x 250k samples, and nothing before the positional conv needs the result
+            if "l" not in memo:
+                ls = lengths
+                if ls is None:
+                    ls = _lengths_from_mask(padding_mask)
+                elif all(n == Ld for n in ls):
+                    ls = None
+                memo["l"] = ls
+            return memo["l"]
+
+        def t_valid():
+            # teacher mask (M3 for HuBERT: applied whenever a mask exists; M1 for wav2vec2)
+            ls = host_lengths()
+            if padding_mask is None and ls is None:
+                return None
+            if tm.kind == "hubert":
+                from .model import hubert_mask_lengths
+                return hubert_mask_lengths(ls if ls is not None else [Ld] * x.shape[0], Ld, T)
+            return None if ls is None else conv_out_lengths(ls, tm._conv_layers)
+
+        def s_valid():
+            ls = host_lengths()
+            return None if ls is None else conv_out_lengths(ls, sm._conv_layers)
+
         n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
         Pt, Wt = tm.engine_state()
         if self._tgt_buf is None or self._tgt_buf.shape[1:3] != (B, T):
@@ -216,12 +237,16 @@ class W2V2Distil(nn.Module):
             main, side = torch.cuda.current_stream(), E.side_stream(dev)
             side.wait_stream(main)  # the H2D copy of x, the previous step's readers of the target buffer
             with torch.cuda.stream(side):
-                tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots)
-            c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
+                tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
+                                           wave_chunks=chunks)
+            c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
+                                  wave_chunks=chunks)
             main.wait_stream(side)
         else:
-            tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots)
-            c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg())
+            tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
+                                       wave_chunks=chunks)
+            c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
+                                  wave_chunks=chunks)
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
         # gradient written in place over the projections (they are not needed again)
         # the loss kernel also produces the column sums of the gradient it writes: both head bias gradients follow

@@ -375,7 +375,7 @@ def _valid_tensor(valid: Optional[List[int]], device) -> Optional[torch.Tensor]:
     return torch.tensor(valid, dtype=torch.int32).to(device, non_blocking=True)
 
 
-def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool):
+def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool, wave_chunks=None):
     """Conv feature extractor (reference modules/module.py:94-102).  Returns ctx with the last
     activation [B, T, C] (contiguous view) and, when `save`, everything backward needs.
     When saving for backward, the output of every k=3,s=2 layer is stored as [B, T_i + 2, C_i] with one
@@ -393,8 +393,15 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool)
     c.rstd0 = torch.empty(B, C0, device=dev, dtype=f32)
     y = torch.empty(B, T0, C0, device=dev, dtype=bf16)
     gp0 = torch.empty(B, T0, C0, device=dev, dtype=bf16) if save else None
-    K.conv0_fwd(wave, P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
-                P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat, c.mean0, c.rstd0, y, gp_out=gp0)
+    # layer 0 is per-sample work (GroupNorm statistics are per sample and channel): when the waveform is still arriving
+    # from the host in batch slices (wave_chunks = [(first, last, event)], see h2d_chunked) each slice is processed as
+    # soon as its copy has landed, so the rest of the H2D transfer hides under it
+    for (b0, b1, ev) in (wave_chunks or [(0, B, None)]):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        K.conv0_fwd(wave[b0:b1], P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
+                    P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat[b0:b1], c.mean0[b0:b1], c.rstd0[b0:b1], y[b0:b1],
+                    gp_out=None if gp0 is None else gp0[b0:b1])
     c.y = [y]
     c.u = [gp0]  # per layer: gelu'(pre-activation), saved by the forward epilogue (the backward multiplier)
     # (buffer, rows allocated per sample, first data row)
@@ -421,12 +428,18 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool)
     return c
 
 
-def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid_t: Optional[torch.Tensor], save: bool,
-                 drop: Optional[DropCfg] = None):
+def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
+                 drop: Optional[DropCfg] = None, wave_chunks=None):
     """conv stack -> LayerNorm -> post_extract_proj -> (mask, pos-conv, +x, LayerNorm)
     = reference modules/model.py:428-489 + modules/module.py:273-281."""
-    c = conv_stack_fwd(P, W, g, wave, save)
+    c = conv_stack_fwd(P, W, g, wave, save, wave_chunks)
     B, T, dev = c.B, c.T, wave.device
+    # `valid` (per-sample valid frame counts, or None) may be a callable: the conv stack above does not need it, so a
+    # caller that still has to derive the lengths from a host padding mask does that scan while the GPU already works
+    if callable(valid):
+        valid = valid()
+    valid_t = _valid_tensor(valid, dev)
+    c.valid, c.valid_t = valid, valid_t
     E, Cf = g.E, g.c_feat
     feat = c.out
     f_ln = torch.empty(B, T, Cf, device=dev, dtype=bf16)
@@ -504,14 +517,15 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
 # =============================================================================================
 # teacher
 # =============================================================================================
-def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None, slots=None):
+def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None, slots=None,
+                    wave_chunks=None):
     """Frozen teacher forward (reference utils/utils.py:80-99 around fairseq HubertModel /
     Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] bf16, features [B, T, E]).
     slots: optional list mapping teacher layer -> row of out_buf (None = not a distillation target: that layer's
     output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather."""
     W.ensure_fresh()
-    valid_t = _valid_tensor(valid, wave.device)
-    c = frontend_fwd(P, W, g, wave, valid_t, save=False)
+    c = frontend_fwd(P, W, g, wave, valid, save=False, wave_chunks=wave_chunks)
+    valid_t = c.valid_t
     B, T, E = c.B, c.T, g.E
     if out_buf is None:
         n_out = g.n_layers if slots is None else 1 + max(s for s in slots if s is not None)
@@ -573,17 +587,18 @@ def _compose_heads(W: WeightSet, g: Geometry, hs: Dict[str, int], n: int):
 
 
 def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], *, train: bool,
-                    heads: str = "all", want_lr: bool = False, pred_buf=None, drop: Optional[DropCfg] = None):
+                    heads: str = "all", want_lr: bool = False, pred_buf=None, drop: Optional[DropCfg] = None,
+                    wave_chunks=None):
     """Student forward (reference modules/model.py:420-552).  heads: 'all' (12 LayerWiseProjHeads),
     'last' (after _disable_projection_heads: final_proj on the last layer), 'none'.
     Returns ctx: .layers [n_layers][B*Ts, E], .tr [B*Ts, E], .preds [n_layers or 1, B, T', D], .feats."""
     W.ensure_fresh()
     dev = wave.device
-    valid_t = _valid_tensor(valid, dev)
-    valid_s = _valid_tensor(None if valid is None else [v // 2 for v in valid], dev)
     if drop is not None and not drop.any():
         drop = None
-    c = frontend_fwd(P, W, g, wave, valid_t, save=train, drop=drop)
+    c = frontend_fwd(P, W, g, wave, valid, save=train, drop=drop, wave_chunks=wave_chunks)
+    valid, valid_t = c.valid, c.valid_t  # `valid` may have been a callable (resolved after the conv stack was queued)
+    valid_s = _valid_tensor(None if valid is None else [v // 2 for v in valid], dev)
     B, T, E = c.B, c.T, g.E
     if g.tr:
         Ts = T // 2
@@ -685,6 +700,37 @@ def side_stream(dev) -> "torch.cuda.Stream":
     if idx not in _SIDE_STREAMS:
         _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
     return _SIDE_STREAMS[idx]
+
+
+_COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def h2d_chunked(x_host: torch.Tensor, dev, n_chunks: int = 0):
+    """Host -> device copy of a [B, L] fp32 batch in `n_chunks` batch slices on a copy stream.  Returns (x_dev,
+    [(first, last, event)]): consumers wait for a slice's event before touching it (conv_stack_fwd does, slice by slice),
+    so only the first slice's transfer is exposed.  True DMA overlap needs pinned host memory; pageable memory works but
+    is staged by the driver."""
+    if n_chunks <= 0:
+        import os
+        n_chunks = int(os.environ.get("FHB_H2D_CHUNKS", "4"))
+    idx = torch.device(dev).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _COPY_STREAMS:
+        _COPY_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    cs = _COPY_STREAMS[idx]
+    B = x_host.shape[0]
+    x = torch.empty(x_host.shape, device=dev, dtype=f32)
+    cs.wait_stream(torch.cuda.current_stream())  # the block may have been released by work still queued on this stream
+    step = -(-B // max(1, min(n_chunks, B)))
+    chunks = []
+    with torch.cuda.stream(cs):
+        for b0 in range(0, B, step):
+            b1 = min(B, b0 + step)
+            x[b0:b1].copy_(x_host[b0:b1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            chunks.append((b0, b1, ev))
+    return x, chunks
 
 
 def stream_mode() -> int:
