@@ -389,6 +389,14 @@ def main():
     groups = K.gemm_timing_groups(classify)
     K.enable_gemm_timing(False)
 
+    # ---- host side of one step: how long the CPU needs to ENQUEUE a step (no synchronisation inside).  If this is close
+    # to the device time, the end-to-end number below - which synchronises every step - is launch-bound, not copy-bound
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_step()
+    host_enqueue_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+
     # ---- end to end through the public API with host buffers
     for _ in range(2):
         e2e_step()
@@ -431,6 +439,7 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4 + 4 * B, "d2h_bytes_per_step": 4,
                 "api": "W2V2Distil.training_step({'x','padding_mask'}) with pinned host tensors"},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": {"bound": "tensor", "kernel": "fhb_gemm_kernel (tcgen05, all variants)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": peak_src, "launches_per_step": gemm_calls / max(1, args.steps),

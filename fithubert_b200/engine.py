@@ -393,35 +393,40 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool,
     c.rstd0 = torch.empty(B, C0, device=dev, dtype=f32)
     y = torch.empty(B, T0, C0, device=dev, dtype=bf16)
     gp0 = torch.empty(B, T0, C0, device=dev, dtype=bf16) if save else None
-    # layer 0 is per-sample work (GroupNorm statistics are per sample and channel): when the waveform is still arriving
-    # from the host in batch slices (wave_chunks = [(first, last, event)], see h2d_chunked) each slice is processed as
-    # soon as its copy has landed, so the rest of the H2D transfer hides under it
-    for (b0, b1, ev) in (wave_chunks or [(0, B, None)]):
-        if ev is not None:
-            torch.cuda.current_stream().wait_event(ev)
-        K.conv0_fwd(wave[b0:b1], P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
-                    P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat[b0:b1], c.mean0[b0:b1], c.rstd0[b0:b1], y[b0:b1],
-                    gp_out=None if gp0 is None else gp0[b0:b1])
     c.y = [y]
     c.u = [gp0]  # per layer: gelu'(pre-activation), saved by the forward epilogue (the backward multiplier)
-    # (buffer, rows allocated per sample, first data row)
-    x_buf, x_rows, x_row0, cin, T = y, T0, 0, C0, T0
     for i, (co, k, s) in enumerate(g.conv_layers):
         if i == 0:
             continue
-        To = frames[i]
-        halo = halos[i]
-        rows = To + 2 * halo
-        yb = torch.empty(B, rows, co, device=dev, dtype=bf16)
-        ub = torch.empty(B, rows, co, device=dev, dtype=bf16) if save else None
-        a3 = L.tensor3(data_ptr=x_buf.data_ptr() + 2 * x_row0 * cin, dim=(k * cin, To, B), stride=(s * cin, x_rows * cin))
-        b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
-        K.gemm_raw(a3, b3, yb, To, co, k * cin, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=co, d_hi_stride=rows * co,
-                   d_offset_elems=halo * co,
-                   flags=L.EPI_GELU | ((L.EPI_STORE_PREACT | L.EPI_AUX_DGELU) if save else 0), aux_out=ub)
-        c.y.append(yb)
-        c.u.append(ub)
-        x_buf, x_rows, x_row0, cin, T = yb, rows, halo, co, To
+        rows = frames[i] + 2 * halos[i]
+        c.y.append(torch.empty(B, rows, co, device=dev, dtype=bf16))
+        c.u.append(torch.empty(B, rows, co, device=dev, dtype=bf16) if save else None)
+    # Nothing in the extractor couples samples (GroupNorm statistics are per sample and channel), so when the waveform is
+    # still arriving from the host in batch slices (wave_chunks = [(first, last, event)], see h2d_chunked) the WHOLE
+    # stack runs slice by slice, each as soon as its copy has landed: the rest of the transfer hides under it.
+    for (b0, b1, ev) in (wave_chunks or [(0, B, None)]):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        nb = b1 - b0
+        K.conv0_fwd(wave[b0:b1], P["feature_extractor.conv_layers.0.0.weight"], P["feature_extractor.conv_layers.0.2.weight"],
+                    P["feature_extractor.conv_layers.0.2.bias"], T0, c.stat[b0:b1], c.mean0[b0:b1], c.rstd0[b0:b1], y[b0:b1],
+                    gp_out=None if gp0 is None else gp0[b0:b1])
+        # (buffer, rows allocated per sample, first data row)
+        x_buf, x_rows, x_row0, cin, T = y, T0, 0, C0, T0
+        for i, (co, k, s) in enumerate(g.conv_layers):
+            if i == 0:
+                continue
+            To = frames[i]
+            halo = halos[i]
+            rows = To + 2 * halo
+            yb, ub = c.y[i], c.u[i]
+            a3 = L.tensor3(data_ptr=x_buf.data_ptr() + 2 * (b0 * x_rows + x_row0) * cin, dim=(k * cin, To, nb),
+                           stride=(s * cin, x_rows * cin))
+            b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
+            K.gemm_raw(a3, b3, yb, To, co, k * cin, num_ob=nb, a_coord=(0, 1, 0, 0), d_ld=co, d_hi_stride=rows * co,
+                       d_offset_elems=(b0 * rows + halo) * co,
+                       flags=L.EPI_GELU | ((L.EPI_STORE_PREACT | L.EPI_AUX_DGELU) if save else 0), aux_out=ub)
+            x_buf, x_rows, x_row0, cin, T = yb, rows, halo, co, To
     c.T = T
     assert halos[-1] == 0, "the last conv layer must not be k=3,s=2 (its output feeds a dense LayerNorm)"
     c.out = x_buf

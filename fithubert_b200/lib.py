@@ -152,6 +152,9 @@ def tensor3(t: torch.Tensor | None = None, *, data_ptr=None, dim=None, stride=No
     elif t is not None:
         data_ptr = t.data_ptr()
     r.ptr = data_ptr
-    r.dim = (C.c_int64 * 3)(*dim)
-    r.stride = (C.c_int64 * 2)(*stride)
+    # element-wise stores into the embedded arrays: building (c_int64 * 3)(*dim) objects costs 3x as much, and this
+    # runs twice per GEMM launch
+    d, st = r.dim, r.stride
+    d[0], d[1], d[2] = dim
+    st[0], st[1] = stride
     return r
