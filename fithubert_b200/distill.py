@@ -9,6 +9,7 @@ raises NotImplementedError.
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Dict, List, Optional
 
@@ -267,7 +268,12 @@ class W2V2Distil(nn.Module):
                            grad_scale * self.rec_loss_weight, dbias=dcs, dbias_layer_stride=D if fused else 0)
             if self.rec_loss_weight != 1.0:
                 layer_loss = layer_loss * self.rec_loss_weight
-        E.student_backward(P, W, sm._geom, G, c, c.preds, dpred_colsum=dcs)
+        hook = None
+        if self.reducer is not None and self.reducer.enabled and self._micro == self.accumulate - 1 and \
+                os.environ.get("FHB_EARLY_REDUCE", "0") == "1" and not self.split_head:
+            first = G.entries[f"encoder.layers.{1 if sm._geom.tr else 0}.self_attn.q_proj.weight"][0]
+            hook = lambda: self.reducer.reduce_tail(G.flat, first)  # noqa: E731
+        E.student_backward(P, W, sm._geom, G, c, c.preds, dpred_colsum=dcs, on_layers_done=hook)
         return layer_loss
 
     def training_step(self, batch, batch_idx=0):

@@ -657,7 +657,7 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         if pred_buf is None:
             pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=bf16)
         c.Wc = None
-        if c.heads_batched and head_compose_enabled():
+        if c.heads_batched and head_compose_enabled() and W.head_stride("bup16") is not None:
             hs["bup16"] = W.head_stride("bup16")
             c.Wc, bc = _compose_heads(W, g, hs, n)
             a3 = L.tensor3(data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
@@ -794,7 +794,7 @@ def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc:
 
 def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torch.Tensor,
                      dlayers: Optional[List[Optional[torch.Tensor]]] = None,
-                     dpred_colsum: Optional[torch.Tensor] = None):
+                     dpred_colsum: Optional[torch.Tensor] = None, on_layers_done=None):
     """Backward of student_forward(train=True, heads='all').  dpred: [n_layers, B, T', D] bf16 gradient of
     the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer.
     dpred_colsum: fp32 [n_layers, D] column sums of dpred over (B, T') if the loss kernel already produced them
@@ -977,6 +977,11 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
                            accumulate=True)
         dx = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1)
+    if on_layers_done is not None:
+        # every gradient of the heads and of the transformer layers is final from here on (85 % of the bytes): the
+        # data-parallel exchange of that part can start under the front-end / conv-stack backward below
+        aside.join()
+        on_layers_done()
     if dx is None:
         aside.join()
         return

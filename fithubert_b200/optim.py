@@ -85,23 +85,39 @@ class GradAllReduce:
         self.stream = torch.cuda.Stream() if (self.enabled and torch.cuda.is_available()) else None
         self._handles = []
 
-    def bucket_bounds(self, numel: int):
+    def bucket_bounds(self, numel: int, start: int = 0):
+        """Bucket boundaries over flat[start:numel]; bucket size = ceil(total / n_buckets) whatever the range."""
         step = -(-numel // self.n_buckets)
         step = (step + 3) // 4 * 4
-        return [(a, min(a + step, numel)) for a in range(0, numel, step)]
+        return [(a, min(a + step, numel)) for a in range(start, numel, step)]
 
-    def reduce_all(self, flat: torch.Tensor):
-        """All buckets, issued back to front (the order backward completes them)."""
-        if not self.enabled:
-            return
+    def _issue(self, flat: torch.Tensor, lo: int, hi: int):
+        bounds = [(a, b) for (a, b) in self.bucket_bounds(hi, lo)]
         if self.stream is None:  # gloo / CPU tests
-            for (a, b) in reversed(self.bucket_bounds(flat.numel())):
+            for (a, b) in reversed(bounds):
                 dist.all_reduce(flat[a:b])
             return
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
-            for (a, b) in reversed(self.bucket_bounds(flat.numel())):
+            for (a, b) in reversed(bounds):
                 dist.all_reduce(flat[a:b])
+
+    def reduce_tail(self, flat: torch.Tensor, start: int):
+        """flat[start:] is final (the transformer layers' and heads' gradients, once the backward has passed the
+        encoder): reduce it now, under the rest of the backward.  reduce_all() then only sends flat[:start]."""
+        if not self.enabled:
+            return
+        start = start // 4 * 4
+        self._issue(flat, start, flat.numel())
+        self._tail_from = start
+
+    def reduce_all(self, flat: torch.Tensor):
+        """Every bucket not sent yet, issued back to front (the order backward completes them)."""
+        if not self.enabled:
+            return
+        hi = getattr(self, "_tail_from", None)
+        self._tail_from = None
+        self._issue(flat, 0, flat.numel() if hi is None else hi)
 
     def wait(self):
         if self.enabled and self.stream is not None:

@@ -51,8 +51,18 @@ def _worker(rank, world, port, q):
     bounds = red.bucket_bounds(flat.numel())
     assert bounds[0][0] == 0 and bounds[-1][1] == flat.numel()
     assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+    split = flat.clone()
     red.reduce_all(flat)
     red.wait()
+    # two-phase exchange (reduce_tail as soon as the layers' / heads' gradients are final, the rest after the backward):
+    # every element is reduced exactly once, whatever the split point
+    cut = (flat.numel() // 3) + 1
+    red.reduce_tail(split, cut)
+    red.reduce_all(split)
+    red.wait()
+    assert torch.equal(split, flat)
+    red.reduce_all(split)  # the next step starts from a clean state: a full exchange again
+    assert torch.allclose(split, flat * world)
     flat = flat / red.world  # the AdamW kernel's grad_scale = 1/world
     _, ref, _ = grads(x_all, pm_all, tgt_all)
     err = float((flat - ref).abs().max() / ref.abs().max())
