@@ -78,7 +78,10 @@ class GradAllReduce:
     heads -> layers -> front-end), the optimizer waits on the last bucket.  Averaging (1/world) is folded
     into the AdamW kernel's grad_scale."""
 
-    def __init__(self, n_buckets: int = 6):
+    def __init__(self, n_buckets: int = 0):
+        if n_buckets <= 0:
+            import os
+            n_buckets = int(os.environ.get("FHB_REDUCE_BUCKETS", "6"))
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.enabled else 1
         self.n_buckets = n_buckets
