@@ -7,7 +7,12 @@ frozen HuBERT-Base teacher forward + student forward/backward + layer-wise loss 
 all-reduce (N > 1) + fused AdamW.  Workload at every N: cfg-2 of BASELINE.json per GPU
 (32 x 15.6 s, LibriSpeech-bucket lengths, random-init teacher/student), i.e. weak scaling
 (global batch 32*N; at N = 8 this is BASELINE configs[2]'s global batch 256).
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  Keys beyond the contract: `roofline` (live CUDA-event time of every tcgen05 GEMM launch
+against the measured sustained bf16 peak, per group), `cpu_baseline` (the oracle port on the host cores, bounded
+sample), `host_enqueue_ms_per_step` (CPU time to queue one step), `student_fwd` (N = 1: the second half of
+BASELINE.json's metric, cfg-4 = the s3prl UpstreamExpert forward on 64 wavs U[5 s, 10 s]).
+Other BASELINE configurations: --workload cfg4 (that expert forward alone), --workload cfg5 (FitW2V2: wav2vec 2.0 Base
+teacher, 16 mixed-length utterances U[10 s, 30 s]).
 """
 from __future__ import annotations
 
