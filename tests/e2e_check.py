@@ -1,5 +1,5 @@
 """Stage-by-stage GPU check of the engine against the golden fixtures (reference outputs).
-Usage: python tools/e2e_check.py [fixture-name ...]"""
+Usage: python tests/e2e_check.py [fixture-name ...]"""
 import glob
 import os
 import sys

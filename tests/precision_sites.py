@@ -1,5 +1,7 @@
 """Which bf16 rounding site dominates the deep-layer deviation?  Emulates the CUDA path's storage roundings in the
-student's 12 encoder layers (weights bf16, fp32 accumulate) and toggles sites off one at a time."""
+student's 12 encoder layers (weights bf16, fp32 accumulate) and toggles sites off one at a time.
+Analysis script (checker side: it runs the oracle, hence it lives under tests/; not collected by pytest).
+Usage: python tests/precision_sites.py   -> profiles/r01final_precision_sites.txt"""
 import sys, torch, torch.nn.functional as F
 sys.path.insert(0, 'oracle'); sys.path.insert(0, '.')
 import fhb_oracle as O
