@@ -103,3 +103,33 @@ def test_mask_rules_suffix_and_lengths():
         m3 = O.mask_m3(pm, T)
         chunk = (L - L % T) // T
         assert O.valid_lengths(m3, T, 2)[1] == min(T, -(-n // chunk))
+
+
+def test_head_fold_algebra_matches_the_oracle_head():
+    """engine._compose_heads runs LayerWiseProjHead (modules/module.py:649-661: ConvTranspose1d(k=2,s=2) then Linear)
+    as one GEMM against Wc_p = Wlin Wup_p^T, bias bc = Wlin bup + blin, and returns to the original parameters by the
+    chain rule.  The same formulas in fp64 torch against autograd through the oracle's own head: prediction and the
+    gradients of all four parameters."""
+    torch.manual_seed(0)
+    E, D, B, Ts = 24, 40, 2, 7
+    x = torch.randn(B, Ts, E, dtype=torch.float64)
+    wup = torch.randn(E, E, 2, dtype=torch.float64, requires_grad=True)   # ConvTranspose1d weight [in, out, k]
+    bup = torch.randn(E, dtype=torch.float64, requires_grad=True)
+    wlin = torch.randn(D, E, dtype=torch.float64, requires_grad=True)
+    blin = torch.randn(D, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv_transpose1d(x.transpose(1, 2), wup, bup, stride=2)
+    pred = torch.nn.functional.linear(y.transpose(1, 2), wlin, blin)      # [B, 2Ts, D] (the oracle's head())
+    dpred = torch.randn_like(pred)
+    pred.backward(dpred)
+    with torch.no_grad():
+        wc = torch.stack([wlin @ wup[:, :, p].t() for p in range(2)])     # [2, D, E_in]
+        bc = wlin @ bup + blin
+        folded = torch.stack([x @ wc[p].t() + bc for p in range(2)], 2).reshape(B, 2 * Ts, D)
+        assert torch.allclose(folded, pred, atol=1e-10)
+        dp = dpred.reshape(B, Ts, 2, D)
+        dwc = torch.stack([dp[:, :, p].reshape(-1, D).t() @ x.reshape(-1, E) for p in range(2)])  # dpred_p^T x
+        cs = dpred.reshape(-1, D).sum(0)
+        dwlin = sum(dwc[p] @ wup[:, :, p] for p in range(2)) + torch.outer(cs, bup)
+        dwup = torch.stack([(wlin.t() @ dwc[p]).t() for p in range(2)], 2)                        # [in, out, k]
+        assert torch.allclose(dwlin, wlin.grad, atol=1e-9) and torch.allclose(dwup, wup.grad, atol=1e-9)
+        assert torch.allclose(cs, blin.grad, atol=1e-9) and torch.allclose(cs @ wlin, bup.grad, atol=1e-9)
