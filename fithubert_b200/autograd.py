@@ -12,20 +12,27 @@ class _StudentFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, source, valid, *params):
         P, W, G = model.engine_state(True)
-        c = E.student_forward(P, W, model._geom, source, valid, train=True, heads="all", want_lr=False,
+        # after _disable_projection_heads (the s3prl expert: fithubert/expert.py:44) only final_proj is left
+        heads = "all" if model.proj_head is not None else ("last" if model.final_proj is not None else "none")
+        c = E.student_forward(P, W, model._geom, source, valid, train=True, heads=heads, want_lr=False,
                               drop=model.drop_cfg())
         ctx.model, ctx.c, ctx.names = model, c, [n for n, _ in model.named_parameters()]
+        ctx.set_materialize_grads(False)  # outputs the loss never touched arrive as None, not as zero tensors
         model._last_ctx = c
-        return (c.preds, *c.layers)
+        preds = c.preds if c.preds is not None else source.new_zeros(0)
+        return (preds, *c.layers)
 
     @staticmethod
     def backward(ctx, dpreds, *dlayers):
         model, c = ctx.model, ctx.c
         P, W, G = model.engine_state(True)
         G.zero_()
-        if dpreds is None:
+        if c.preds is None:
+            dpreds = None
+        elif dpreds is None:
             dpreds = torch.zeros_like(c.preds)
-        dpreds = dpreds.to(torch.bfloat16).contiguous()
+        if dpreds is not None:
+            dpreds = dpreds.to(torch.bfloat16).contiguous()
         dl = [None if d is None else d.to(torch.bfloat16).contiguous() for d in dlayers]
         E.student_backward(P, W, model._geom, G, c, dpreds, dl)
         grads = G.export()
@@ -35,7 +42,8 @@ class _StudentFn(torch.autograd.Function):
 def student_apply(model, source, valid):
     params = [p for _, p in model.named_parameters()]
     outs = _StudentFn.apply(model, source, valid, *params)
-    return model._last_ctx, outs[0], list(outs[1:])
+    c = model._last_ctx
+    return c, (outs[0] if c.preds is not None else None), list(outs[1:])
 
 
 class _DistillLossFn(torch.autograd.Function):

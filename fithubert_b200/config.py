@@ -126,5 +126,9 @@ class CustomStudentModelConfig:
         for (_, k, s) in layers[1:]:
             if (k, s) not in ((1, 1), (2, 2), (3, 2)):
                 raise NotImplementedError(f"conv layer (k={k}, s={s}) is not implemented")
+        if layers[-1][0] == self.encoder_embed_dim:
+            # modules/model.py:298-302 then builds NO post_extract_proj (state-dict keys and arithmetic differ)
+            raise NotImplementedError("conv output width == encoder_embed_dim (the reference drops post_extract_proj) "
+                                      "is not implemented")
         assert self.encoder_embed_dim % self.encoder_attention_heads == 0
         assert self.encoder_embed_dim % self.conv_pos_groups == 0

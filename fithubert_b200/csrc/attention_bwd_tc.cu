@@ -407,12 +407,10 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
     if (rc) return rc;
   }
   FHB_CUDA_CHECK(cudaMemsetAsync(dq_ws, 0, sizeof(float) * (size_t)B * T * E, s));
-  static bool attr_set = false;
-  if (!attr_set) {
+  FHB_ONCE_PER_DEVICE({
     FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  });
   dim3 grid((T + kT - 1) / kT, H, B);
   if (drop_p > 0.f)
     FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, true>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,

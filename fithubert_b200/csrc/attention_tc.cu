@@ -330,12 +330,10 @@ int launch_fwd(const void* qkv, const int32_t* valid, void* out, float* lse, int
   const int64_t stride[2] = {3LL * H * HD, 3LL * H * HD * T};
   int rc = fhb_make_tmap_bf16_3d(&tm, qkv, dim, stride, 64, kTQ, "qkv");
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  FHB_ONCE_PER_DEVICE({
     FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     FHB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
-  }
+  });
   dim3 grid((T + kTQ - 1) / kTQ, H, B);
   if (drop_p > 0.f)
     FHB_CUDA_CHECK(fhb_launch((attn_fwd_tc_kernel<HD, true>), dim3(grid), dim3(288), kSmem, s, tm, valid, static_cast<__nv_bfloat16*>(out), lse, T, H, scale,

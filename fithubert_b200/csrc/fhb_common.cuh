@@ -32,16 +32,33 @@ void fhb_set_error(const char* fmt, ...);
 int fhb_make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, const int64_t dim[3], const int64_t stride[2],
                           uint32_t box0, uint32_t box1, const char* name);
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 static inline int fhb_num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
   }
   return n;
 }
+
+// Runs `stmt` the first time this call site is reached on each device (function attributes such as the dynamic
+// shared-memory limit are per device, not per process).
+#define FHB_ONCE_PER_DEVICE(stmt)                                                   \
+  do {                                                                              \
+    static unsigned long long _fhb_done = 0ull;                                     \
+    int _fhb_dev = 0;                                                               \
+    cudaGetDevice(&_fhb_dev);                                                       \
+    const unsigned long long _fhb_bit = 1ull << (_fhb_dev & 63);                    \
+    if (!(__atomic_load_n(&_fhb_done, __ATOMIC_ACQUIRE) & _fhb_bit)) {              \
+      stmt;                                                                         \
+      __atomic_fetch_or(&_fhb_done, _fhb_bit, __ATOMIC_RELEASE);                    \
+    }                                                                               \
+  } while (0)
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)

@@ -49,7 +49,7 @@ struct GemmParams {
   long long d_ld, d_hi_stride, d_lo_stride, bias_hi_stride;
   void* d;
   const float* bias;
-  const __nv_bfloat16* residual;
+  const void* residual;  // bf16, or fp32 with FHB_EPI_RES_F32
   const __nv_bfloat16* aux_in;
   __nv_bfloat16* aux_out;
   const int* row_valid;
@@ -375,24 +375,42 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
           }
           if (flags & FHB_EPI_RESIDUAL) {
-            uint32_t uu[8];
-            if (ring && !ring_is_aux) {
+            if (flags & FHB_EPI_RES_F32) {
+              // fp32 residual stream: 16 floats per thread, through the ring when D is fp32 too (same slab geometry)
+              if (ring && !ring_is_aux) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) uu[j] = ring[j];
-            } else if (col_ok) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
-              const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-              uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w;
-              uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+                for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(ring[j]);
+              } else if (col_ok) {
+                const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 f = __ldg(rp + j);
+                  v[4 * j] += f.x;
+                  v[4 * j + 1] += f.y;
+                  v[4 * j + 2] += f.z;
+                  v[4 * j + 3] += f.w;
+                }
+              }
             } else {
+              uint32_t uu[8];
+              if (ring && !ring_is_aux) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) uu[j] = 0u;
-            }
+                for (int j = 0; j < 8; ++j) uu[j] = ring[j];
+              } else if (col_ok) {
+                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + c);
+                const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+                uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w;
+                uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+              } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack_bf16(uu[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+                for (int j = 0; j < 8; ++j) uu[j] = 0u;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = unpack_bf16(uu[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
             }
           }
           if ((flags & FHB_EPI_SQDIFF) && col_ok) {
@@ -686,12 +704,8 @@ int pick_bn(int n, long long row_tiles, bool split_k) {
 template <int A_MN, int B_MN, int EPI_IN>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
             const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBytes));
-    attr_set = true;
-  }
+  FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN>,
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
   const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
   // "small" = at most ~200 k-blocks per SM: the student's GEMMs and the teacher's encoder GEMMs, not the conv stacks
   // (swept on B200, profiles/r01y_pdl_ab.log: 7 104 -> 23.61 ms, 30 000 -> 23.55 ms, 150 000 -> 23.68 ms, none -> 23.94 ms)
@@ -764,6 +778,8 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   const int flags = a->flags;
   FHB_ARG_CHECK(!(flags & FHB_EPI_BIAS) || a->bias, "gemm: FHB_EPI_BIAS without bias");
   FHB_ARG_CHECK(!(flags & FHB_EPI_RESIDUAL) || a->residual, "gemm: FHB_EPI_RESIDUAL without residual");
+  FHB_ARG_CHECK(!(flags & FHB_EPI_RES_F32) || (flags & FHB_EPI_RESIDUAL), "gemm: FHB_EPI_RES_F32 needs FHB_EPI_RESIDUAL");
+  FHB_ARG_CHECK(!(flags & FHB_EPI_STORE_PREACT) || !(flags & FHB_EPI_OUT_F32), "gemm: a second output needs a bf16 D");
   FHB_ARG_CHECK(!(flags & FHB_EPI_ROWZERO) || a->row_valid, "gemm: FHB_EPI_ROWZERO without row_valid");
   FHB_ARG_CHECK(!(flags & FHB_EPI_STORE_PREACT) || a->aux_out, "gemm: FHB_EPI_STORE_PREACT without aux_out");
   FHB_ARG_CHECK(!(flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) || a->aux_in, "gemm: FHB_EPI_MUL_DGELU/MUL_AUX without aux_in");
@@ -811,7 +827,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.d = a->d;
   p.bias_hi_stride = a->bias_hi_stride;
   p.bias = a->bias;
-  p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  p.residual = a->residual;
   p.aux_in = static_cast<const __nv_bfloat16*>(a->aux_in);
   p.aux_out = static_cast<__nv_bfloat16*>(a->aux_out);
   p.row_valid = a->row_valid;
@@ -853,10 +869,13 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.use_tma_store = force_direct ? 0 : 1;
   const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
   // the [m][n] epilogue input (aux_in if used, else the residual) is staged through a TMA ring when D is bf16
-  const void* ring_src = (flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) ? a->aux_in
-                         : ((flags & FHB_EPI_RESIDUAL) ? a->residual : nullptr);
+  const bool ring_aux = (flags & (FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX)) != 0;
+  const void* ring_src = ring_aux ? a->aux_in : ((flags & FHB_EPI_RESIDUAL) ? a->residual : nullptr);
+  // the ring's slabs have the geometry of D's: usable when the staged operand has D's element type (aux_in is always
+  // bf16; the residual is bf16 or, with FHB_EPI_RES_F32, fp32); otherwise that operand is read from global memory
+  const bool ring_f32 = !ring_aux && (flags & FHB_EPI_RES_F32) != 0;
   p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 2 : 0;
-  p.n_in = (p.use_tma_store && ring_src && !out_f32) ? kInRing : 0;
+  p.n_in = (p.use_tma_store && ring_src && ring_f32 == out_f32) ? kInRing : 0;
   p.stages = (14 - 2 - p.n_auxout - p.n_in) / 3;
   if (p.stages > kStages) p.stages = kStages;
   if (p.use_tma_store) {
@@ -872,7 +891,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
         return rc;
     }
     if (p.n_in) {
-      if ((rc = make_out_tmap(&ti, const_cast<void*>(ring_src), false, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride,
+      if ((rc = make_out_tmap(&ti, const_cast<void*>(ring_src), ring_f32, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride,
                               a->d_hi_stride, "epilogue input")) != 0)
         return rc;
     }

@@ -18,24 +18,39 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
       make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
+__device__ __forceinline__ void load8f(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8f(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// IN_F32: x is the fp32 pre-LayerNorm sum written by the out_proj / fc2 GEMM epilogue (the residual stream is never
+// rounded to bf16 on its way through a layer).  y (bf16) is the next GEMM's A operand; y32 (optional) the fp32 copy the
+// next residual add reads.  sub32 / diff_out (optional): diff_out = bf16(x - sub32), i.e. the FFN branch output
+// `layer_result` of modules/module.py:577-580 recovered from the sum and its residual operand.
+template <bool IN_F32>
 __global__ void __launch_bounds__(256)
-layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, long long rows, int C, float eps) {
+layernorm_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ sub32,
+                     __nv_bfloat16* __restrict__ diff_out, long long rows, int C, float eps) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = C >> 3;
   for (long long row = warp_global; row < rows; row += nwarps) {
-    const __nv_bfloat16* xr = x + row * C;
     float v[kMaxVec][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        load8(xr + vi * 8, v[i]);
+        if (IN_F32) load8f(static_cast<const float*>(x_) + row * C + vi * 8, v[i]);
+        else load8(static_cast<const __nv_bfloat16*>(x_) + row * C + vi * 8, v[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i][j];
       }
@@ -58,12 +73,18 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
       mean_out[row] = mu;
       rstd_out[row] = rs;
     }
-    __nv_bfloat16* yr = y + row * C;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         float o[8];
+        if (diff_out) {
+          float r[8];
+          load8f(sub32 + row * C + vi * 8, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = v[i][j] - r[j];
+          store8(diff_out + row * C + vi * 8, o);
+        }
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)),
                      g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)),
@@ -72,7 +93,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
         const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
-        store8(yr + vi * 8, o);
+        store8(y + row * C + vi * 8, o);
+        if (y32) store8f(y32 + row * C + vi * 8, o);
       }
     }
   }
@@ -90,11 +112,14 @@ __device__ __forceinline__ void cvt8(const uint4& u, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-template <int NV, bool DXSUM>
+// F32: the gradient arrives as dy32 (fp32, optional: the residual stream of the backward pass) and / or dy2 (bf16: a
+// projection head's or autograd's contribution), x is the fp32 pre-LayerNorm sum; dx32 (fp32) is the un-masked gradient
+// that continues down the residual, dx / dx_drop the bf16 copies the dgrad / wgrad GEMMs consume.
+template <int NV, bool DXSUM, bool F32>
 __global__ void __launch_bounds__(256, 2)
-layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
-                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+layernorm_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ dy2,
+                     const void* __restrict__ x_, const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dx32,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
                      __nv_bfloat16* __restrict__ dx_drop, uint32_t drop_seed, uint32_t drop_thr, float drop_scale,
                      long long rows, int C) {
@@ -110,27 +135,48 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   __syncwarp();
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   for (long long row = warp_global; row < rows; row += nwarps) {
-    uint4 rx[NV], rd[NV], rd2[NV], rr[NV];
+    float xh[NV][8], dxh[NV][8];
+    uint4 rd2[NV], rr[NV];
+    if (F32) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + 32 * i;
-      rx[i] = rd[i] = rd2[i] = rr[i] = zero4;
-      if (vi < nvec) {
-        rx[i] = *reinterpret_cast<const uint4*>(x + row * C + vi * 8);
-        rd[i] = *reinterpret_cast<const uint4*>(dy + row * C + vi * 8);
-        if (dy2) rd2[i] = *reinterpret_cast<const uint4*>(dy2 + row * C + vi * 8);
-        if (dres) rr[i] = *reinterpret_cast<const uint4*>(dres + row * C + vi * 8);
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        rd2[i] = rr[i] = zero4;
+        if (vi < nvec) {
+          load8f(static_cast<const float*>(x_) + row * C + vi * 8, xh[i]);
+          if (dy_) load8f(static_cast<const float*>(dy_) + row * C + vi * 8, dxh[i]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dxh[i][j] = 0.f;
+          }
+          if (dy2) rd2[i] = *reinterpret_cast<const uint4*>(dy2 + row * C + vi * 8);
+        }
+      }
+    } else {
+      uint4 rx[NV], rd[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        rx[i] = rd[i] = rd2[i] = rr[i] = zero4;
+        if (vi < nvec) {
+          rx[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x_) + row * C + vi * 8);
+          rd[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(dy_) + row * C + vi * 8);
+          if (dy2) rd2[i] = *reinterpret_cast<const uint4*>(dy2 + row * C + vi * 8);
+          if (dres) rr[i] = *reinterpret_cast<const uint4*>(dres + row * C + vi * 8);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        cvt8(rx[i], xh[i]);
+        cvt8(rd[i], dxh[i]);
       }
     }
     const float mu = mean[row], rs = rstd[row];
-    float xh[NV][8], dxh[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        cvt8(rx[i], xh[i]);
-        cvt8(rd[i], dxh[i]);
         if (dy2) {  // two gradient streams meet here (layer above + this layer's projection head)
           float t2[8];
           cvt8(rd2[i], t2);
@@ -164,7 +210,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         cvt8(rr[i], o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += rs * (dxh[i][j] - s1 - xh[i][j] * s2);
-        store8(dx + row * C + vi * 8, o);
+        if (dx) store8(dx + row * C + vi * 8, o);
+        if (F32 && dx32) store8f(dx32 + row * C + vi * 8, o);
         if (dx_drop) {
           // gradient through nn.Dropout on the branch that produced x (residual + dropout(branch)): the masked
           // copy feeds the branch's dgrad / wgrad / bias gradient, the plain dx continues down the residual
@@ -207,25 +254,35 @@ int ln_grid(long long rows, int rows_per_warp_target) {
 
 }  // namespace
 
-extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
-                                 float* rstd, int64_t rows, int32_t C, float eps, fhb_stream_t stream) {
+namespace {
+int ln_fwd_launch(bool in_f32, const void* x, const float* gamma, const float* beta, void* y, float* y32, float* mean,
+                  float* rstd, const float* sub32, void* diff_out, int64_t rows, int32_t C, float eps, fhb_stream_t stream) {
   FHB_ARG_CHECK(x && gamma && beta && y, "layernorm_fwd: null pointer");
   FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_fwd: C=%d must be a multiple of 8, <= %d",
                 C, kMaxVec * 256);
   FHB_ARG_CHECK((mean == nullptr) == (rstd == nullptr), "layernorm_fwd: mean and rstd go together");
+  FHB_ARG_CHECK((sub32 == nullptr) == (diff_out == nullptr), "layernorm_fwd: sub32 and diff_out go together");
   if (rows == 0) return 0;
   fhb_pdl_hint(rows * C <= 16LL << 20);
-  FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel, dim3(ln_grid(rows, 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, rows, C, eps));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (in_f32)
+    FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel<true>, dim3(ln_grid(rows, 1)), dim3(256), 0, s, x, gamma, beta,
+                              static_cast<__nv_bfloat16*>(y), y32, mean, rstd, sub32, static_cast<__nv_bfloat16*>(diff_out),
+                              rows, C, eps));
+  else
+    FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel<false>, dim3(ln_grid(rows, 1)), dim3(256), 0, s, x, gamma, beta,
+                              static_cast<__nv_bfloat16*>(y), y32, mean, rstd, sub32, static_cast<__nv_bfloat16*>(diff_out),
+                              rows, C, eps));
   FHB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x, const float* gamma, const float* mean,
-                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                                 float* dxsum, void* dx_drop, uint32_t drop_seed, float drop_p, int64_t rows, int32_t C,
-                                 fhb_stream_t stream) {
-  FHB_ARG_CHECK(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+int ln_bwd_launch(bool f32, const void* dy, const void* dy2, const void* x, const float* gamma, const float* mean,
+                  const float* rstd, const void* dres, void* dx, float* dx32, float* dgamma, float* dbeta, float* dxsum,
+                  void* dx_drop, uint32_t drop_seed, float drop_p, int64_t rows, int32_t C, fhb_stream_t stream) {
+  FHB_ARG_CHECK(x && gamma && mean && rstd && dgamma && dbeta, "layernorm_bwd: null pointer");
+  FHB_ARG_CHECK(f32 ? (dy || dy2) && (dx || dx32 || dx_drop) && !dres : (dy && dx && !dx32),
+                "layernorm_bwd: missing gradient input / output");
   FHB_ARG_CHECK(!dx_drop || (drop_p >= 0.f && drop_p < 1.f && rows * C < (1LL << 32)), "layernorm_bwd: bad dropout arguments");
   FHB_ARG_CHECK(rows >= 0 && C > 0 && C % 8 == 0 && C <= kMaxVec * 256, "layernorm_bwd: bad C=%d", C);
   if (rows == 0) return 0;
@@ -236,26 +293,52 @@ extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x,
   const int nv = (C / 8 + 31) / 32;
   const size_t sm = 8 * (dxsum ? 3 : 2) * C * sizeof(float);  // [8 warps][NS][C]
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define FHB_LN_BWD(NV, DX)                                                                                          \
-  do {                                                                                                              \
-    static bool attr_set = false;                                                                                   \
-    if (!attr_set) {                                                                                                \
-      FHB_CUDA_CHECK(cudaFuncSetAttribute(layernorm_bwd_kernel<NV, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          8 * 3 * kMaxVec * 256 * (int)sizeof(float)));                             \
-      attr_set = true;                                                                                              \
-    }                                                                                                               \
-    FHB_CUDA_CHECK(fhb_launch((layernorm_bwd_kernel<NV, DX>), dim3((unsigned)blocks), dim3(256), sm, s,             \
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dy2),                               \
-      static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,                                                      \
-      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum,              \
+#define FHB_LN_BWD(NV, DX, F)                                                                                        \
+  do {                                                                                                               \
+    FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute((layernorm_bwd_kernel<NV, DX, F>),                        \
+        cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * kMaxVec * 256 * (int)sizeof(float))));                  \
+    FHB_CUDA_CHECK(fhb_launch((layernorm_bwd_kernel<NV, DX, F>), dim3((unsigned)blocks), dim3(256), sm, s, dy,       \
+      static_cast<const __nv_bfloat16*>(dy2), x, gamma, mean, rstd,                                                  \
+      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dx32, dgamma, dbeta, dxsum,          \
       static_cast<__nv_bfloat16*>(dx_drop), drop_seed, fhb_dropout_thr16(drop_p), fhb_dropout_scale(drop_p), rows, C)); \
   } while (0)
-  if (dxsum) {
-    if (nv == 1) FHB_LN_BWD(1, true); else if (nv == 2) FHB_LN_BWD(2, true); else FHB_LN_BWD(3, true);
+#define FHB_LN_BWD_NV(DX, F) \
+  do { if (nv == 1) FHB_LN_BWD(1, DX, F); else if (nv == 2) FHB_LN_BWD(2, DX, F); else FHB_LN_BWD(3, DX, F); } while (0)
+  if (f32) {
+    if (dxsum) FHB_LN_BWD_NV(true, true); else FHB_LN_BWD_NV(false, true);
   } else {
-    if (nv == 1) FHB_LN_BWD(1, false); else if (nv == 2) FHB_LN_BWD(2, false); else FHB_LN_BWD(3, false);
+    if (dxsum) FHB_LN_BWD_NV(true, false); else FHB_LN_BWD_NV(false, false);
   }
+#undef FHB_LN_BWD_NV
 #undef FHB_LN_BWD
   FHB_LAUNCH_CHECK();
   return 0;
+}
+}  // namespace
+
+extern "C" int fhb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                 float* rstd, int64_t rows, int32_t C, float eps, fhb_stream_t stream) {
+  return ln_fwd_launch(false, x, gamma, beta, y, nullptr, mean, rstd, nullptr, nullptr, rows, C, eps, stream);
+}
+
+extern "C" int fhb_layernorm_fwd32(const float* x32, const float* gamma, const float* beta, void* y, float* y32,
+                                   float* mean, float* rstd, const float* sub32, void* diff_out, int64_t rows, int32_t C,
+                                   float eps, fhb_stream_t stream) {
+  return ln_fwd_launch(true, x32, gamma, beta, y, y32, mean, rstd, sub32, diff_out, rows, C, eps, stream);
+}
+
+extern "C" int fhb_layernorm_bwd(const void* dy, const void* dy2, const void* x, const float* gamma, const float* mean,
+                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 float* dxsum, void* dx_drop, uint32_t drop_seed, float drop_p, int64_t rows, int32_t C,
+                                 fhb_stream_t stream) {
+  return ln_bwd_launch(false, dy, dy2, x, gamma, mean, rstd, dres, dx, nullptr, dgamma, dbeta, dxsum, dx_drop, drop_seed,
+                       drop_p, rows, C, stream);
+}
+
+extern "C" int fhb_layernorm_bwd32(const float* dy32, const void* dy2, const float* x32, const float* gamma,
+                                   const float* mean, const float* rstd, void* dx, float* dx32, float* dgamma,
+                                   float* dbeta, float* dxsum, void* dx_drop, uint32_t drop_seed, float drop_p,
+                                   int64_t rows, int32_t C, fhb_stream_t stream) {
+  return ln_bwd_launch(true, dy32, dy2, x32, gamma, mean, rstd, nullptr, dx, dx32, dgamma, dbeta, dxsum, dx_drop,
+                       drop_seed, drop_p, rows, C, stream);
 }

@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(256)
 posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ valid,
                           const __nv_bfloat16* __restrict__ conv, const float* __restrict__ bias,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                          __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                          float* __restrict__ rstd_out, int B, int T, int C, int G, int cp, float eps, int delta,
-                          int rows_per_warp) {
+                          __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int B, int T, int C, int G, int cp,
+                          float eps, int delta, int rows_per_warp) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -265,6 +265,10 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
 #pragma unroll
         for (int j = 0; j < VEC; ++j) o[j] = (hv[i][j] - mu) * rs * gv[j] + bv[j];
         stv<VEC>(y + row * C + c, o);
+        if (y32) {  // fp32 copy: the residual operand of the first transformer layer's out_proj epilogue
+#pragma unroll
+          for (int j = 0; j < VEC; j += 2) *reinterpret_cast<float2*>(y32 + row * C + c + j) = make_float2(o[j], o[j + 1]);
+        }
       }
     }
   }
@@ -502,10 +506,10 @@ extern "C" int fhb_posconv_wn_prep(const float* v, const float* g, void* w_fwd, 
 template <int VEC>
 int launch_finish_fwd(int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, const int32_t* valid, const __nv_bfloat16* conv,
                       const float* bias, const float* gamma, const float* beta, __nv_bfloat16* h_out, __nv_bfloat16* y,
-                      float* mean, float* rstd, int B, int T, int C, int G, int cp, float eps, int delta, int rpw) {
+                      float* y32, float* mean, float* rstd, int B, int T, int C, int G, int cp, float eps, int delta, int rpw) {
 #define FHB_FF(NV)                                                                                                        \
   FHB_CUDA_CHECK(fhb_launch((posconv_finish_fwd_kernel<VEC, NV>), grid, dim3(256), 0, s, x, valid, conv, bias, gamma, beta, \
-                            h_out, y, mean, rstd, B, T, C, G, cp, eps, delta, rpw))
+                            h_out, y, y32, mean, rstd, B, T, C, G, cp, eps, delta, rpw))
   if constexpr (VEC == 8) {
     if (nv <= 1) FHB_FF(1); else if (nv == 2) FHB_FF(2); else FHB_FF(3);
   } else {
@@ -516,9 +520,9 @@ int launch_finish_fwd(int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x,
 }
 
 extern "C" int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const void* conv, const float* bias,
-                                      const float* gamma, const float* beta, void* h_out, void* y, float* mean,
-                                      float* rstd, int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps,
-                                      int32_t delta, fhb_stream_t stream) {
+                                      const float* gamma, const float* beta, void* h_out, void* y, float* y32,
+                                      float* mean, float* rstd, int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp,
+                                      float eps, int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(x && conv && bias && gamma && beta && y && delta >= 1, "posconv_finish_fwd: null pointer");
   FHB_ARG_CHECK(C <= 768 && C % G == 0 && (C / G) % 2 == 0, "posconv_finish_fwd: C=%d must be <= 768 with an even group width", C);
   const long long rows = (long long)B * T;
@@ -529,10 +533,10 @@ extern "C" int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const
   if (cg % 8 == 0)
     return launch_finish_fwd<8>((C / 8 + 31) / 32, grid, s, static_cast<const __nv_bfloat16*>(x), valid,
                                 static_cast<const __nv_bfloat16*>(conv), bias, gamma, beta, static_cast<__nv_bfloat16*>(h_out),
-                                static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta, rpw);
+                                static_cast<__nv_bfloat16*>(y), y32, mean, rstd, B, T, C, G, cp, eps, delta, rpw);
   return launch_finish_fwd<2>((C / 2 + 31) / 32, grid, s, static_cast<const __nv_bfloat16*>(x), valid,
                               static_cast<const __nv_bfloat16*>(conv), bias, gamma, beta, static_cast<__nv_bfloat16*>(h_out),
-                              static_cast<__nv_bfloat16*>(y), mean, rstd, B, T, C, G, cp, eps, delta, rpw);
+                              static_cast<__nv_bfloat16*>(y), y32, mean, rstd, B, T, C, G, cp, eps, delta, rpw);
 }
 
 template <int VEC>
@@ -542,8 +546,8 @@ int launch_finish_bwd(int nv, dim3 grid, size_t smem, cudaStream_t s, const __nv
                       int G, int cp, int pad_l, int Tp, int rpw, int delta) {
 #define FHB_FB(NV)                                                                                                       \
   do {                                                                                                                   \
-    FHB_CUDA_CHECK(cudaFuncSetAttribute(posconv_finish_bwd_kernel<VEC, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                        8 * 3 * 768 * (int)sizeof(float)));                                              \
+    FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute((posconv_finish_bwd_kernel<VEC, NV>),                        \
+        cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * (int)sizeof(float))));                               \
     FHB_CUDA_CHECK(fhb_launch((posconv_finish_bwd_kernel<VEC, NV>), grid, dim3(256), smem, s, dy, h, conv, bias, gamma,   \
                               mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, C, G, cp, pad_l, Tp, rpw, delta));         \
   } while (0)

@@ -130,7 +130,9 @@ def shard_indices(n: int, rank: int, world: int, shuffle: bool, seed: int, epoch
         idx = list(range(n))
     if world > 1:
         total = -(-n // world) * world
-        idx += idx[:total - n]
+        pad = total - n
+        if pad > 0 and n > 0:  # DistributedSampler repeats the list when the padding is longer than the list itself
+            idx += (idx * -(-pad // n))[:pad]
         idx = idx[rank:total:world]
     return idx
 
@@ -153,27 +155,45 @@ class BucketLoader:
     def __len__(self) -> int:
         return len(shard_indices(len(self.dataset), self.rank, self.world, False, 0, 0))
 
-    def _produce(self, order: Sequence[int], out: "queue.Queue") -> None:
+    @staticmethod
+    def _put(out: "queue.Queue", item, stop: "threading.Event") -> bool:
+        """Blocking put that gives up once the consumer has gone away (early break / exception in the training loop)."""
+        while not stop.is_set():
+            try:
+                out.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _produce(self, order: Sequence[int], out: "queue.Queue", stop: "threading.Event") -> None:
         try:
             for i in order:
+                if stop.is_set():
+                    return
                 item = self.dataset[i]
                 if self.pin:
                     item = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in item.items()}
-                out.put(item)
-            out.put(None)
+                if not self._put(out, item, stop):
+                    return
+            self._put(out, None, stop)
         except BaseException as e:  # noqa: BLE001 - handed to the consumer
-            out.put(e)
+            self._put(out, e, stop)
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         order = shard_indices(len(self.dataset), self.rank, self.world, self.shuffle, self.seed, self.epoch)
         q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
-        t = threading.Thread(target=self._produce, args=(order, q), daemon=True)
+        stop = threading.Event()
+        t = threading.Thread(target=self._produce, args=(order, q, stop), daemon=True)
         t.start()
-        while True:
-            item = q.get()
-            if item is None:
-                break
-            if isinstance(item, BaseException):
-                raise item
-            yield item
-        t.join()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:  # also reached when the consumer stops early (break, exception, generator close)
+            stop.set()
+            t.join()

@@ -342,7 +342,10 @@ class W2V2Distil(nn.Module):
         else:
             K.distill_loss(c.preds, tgt, self.layer_weights, rec, None, n, B, c.Tq, T, D, lt, 0.0)
             per = rec * self.rec_loss_weight
-        loss = per[n - 1] if (self.train_cfg["distil_random_layer"] > 0 and not self.split_head) else per.sum()
+        # train.py:198-199: with random-layer distillation the monitored value is the last layer's own (un-weighted)
+        # feature loss, not the weighted total
+        loss = (rec[n - 1] if not self.sim_loss_weight else rec[n - 1] + sim[n - 1]) \
+            if (self.train_cfg["distil_random_layer"] > 0 and not self.split_head) else per.sum()
         return {"v_loss": loss}
 
     def optimizer_step(self):

@@ -296,7 +296,10 @@ class GradStore:
         for i in range(g.n_layers if not g.n_split else 0):
             p = f"proj_head.{i}."
             if p + "upsampler.weight" not in params:
-                continue
+                if i == g.n_layers - 1 and "final_proj.upsampler.weight" in params:
+                    p = "final_proj."  # after _disable_projection_heads: the last head under its new name
+                else:
+                    continue
             # grad stored as dWup[(j, co)][ci]; param element (ci, co, j)
             order.append((p + "upsampler.weight", (E, E, 2), (1, E, E * E)))
             plain(p + "upsampler.bias")
@@ -434,7 +437,7 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool,
 
 
 def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
-                 drop: Optional[DropCfg] = None, wave_chunks=None):
+                 drop: Optional[DropCfg] = None, wave_chunks=None, want_enc32: bool = False):
     """conv stack -> LayerNorm -> post_extract_proj -> (mask, pos-conv, +x, LayerNorm)
     = reference modules/model.py:428-489 + modules/module.py:273-281."""
     c = conv_stack_fwd(P, W, g, wave, save, wave_chunks)
@@ -473,10 +476,14 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
     c.h = torch.empty(B * T, E, device=dev, dtype=bf16) if save else None
     c.mean_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
     c.rstd_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
-    K.posconv_finish_fwd(feats, valid_t, conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"],
-                         P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp, delta=dl)
-    c.Tp, c.R = Tp, R
     d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
+    # fp32 copy of the encoder input: the residual operand of layer 0 when no GEMM sits in between (no TR layer) and no
+    # dropout follows (the dropped tensor is bf16 anyway)
+    c.enc_in32 = torch.empty(B * T, E, device=dev, dtype=f32) if (want_enc32 and d_pro is None) else None
+    K.posconv_finish_fwd(feats, valid_t, conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"],
+                         P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp, delta=dl,
+                         y32=c.enc_in32)
+    c.Tp, c.R = Tp, R
     if d_pro is not None:  # F.dropout after the encoder LayerNorm (modules/module.py:294)
         K.dropout(enc, enc, *d_pro)
     c.enc_in = enc
@@ -484,38 +491,51 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
 
 
 def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, T, save: bool, want_lr: bool,
-              out: Optional[torch.Tensor] = None, drop: Optional[DropCfg] = None):
-    """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E]."""
+              out: Optional[torch.Tensor] = None, drop: Optional[DropCfg] = None, x32: Optional[torch.Tensor] = None,
+              out32: Optional[torch.Tensor] = None):
+    """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E].
+    The residual stream never passes through bf16: x32 is the fp32 copy of x (None for the first layer, whose input is
+    the bf16 output of a GEMM / LayerNorm anyway), the out_proj / fc2 epilogues add it in fp32 and write the sums y1 / y2
+    in fp32, the LayerNorms read those and emit the bf16 GEMM operand together with the next fp32 copy (out32)."""
     E, F, H, d = g.E, g.F, g.H, g.d
     dev = x.device
     s = SimpleNamespace(x=x)
+    M = B * T
     qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
     # training with F == E: the inputs of out_proj / fc1 / fc2 (attn, x1, h) share one [3, M, E] buffer so that their three
     # weight-gradient GEMMs run as one batched launch in the backward (wgrad_batch_enabled)
-    xs = torch.empty(3, B * T, E, device=dev, dtype=bf16) if (save and F == E and wgrad_batch_enabled()) else None
-    attn = xs[0] if xs is not None else torch.empty(B * T, E, device=dev, dtype=bf16)
+    xs = torch.empty(3, M, E, device=dev, dtype=bf16) if (save and F == E and wgrad_batch_enabled()) else None
+    attn = xs[0] if xs is not None else torch.empty(M, E, device=dev, dtype=bf16)
     lse = torch.empty(B, H, T, device=dev, dtype=f32) if save else None
     dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
     K.attn_fwd(qkv, valid_t, attn, lse, B, T, H, d, d ** -0.5, drop=dl(DropCfg.ATTN))
-    y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"], residual=x, drop=dl(DropCfg.DROP1))
-    x1 = xs[1] if xs is not None else torch.empty_like(y1)
-    s.mean1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
-    s.rstd1 = torch.empty(B * T, device=dev, dtype=f32) if save else None
-    K.layernorm_fwd(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1,
-                    s.mean1, s.rstd1)
-    u = torch.empty(B * T, F, device=dev, dtype=bf16) if save else None
+    y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"],
+                  residual=x32 if x32 is not None else x, drop=dl(DropCfg.DROP1), out_dtype=f32)
+    x1 = xs[1] if xs is not None else torch.empty(M, E, device=dev, dtype=bf16)
+    x1_32 = torch.empty(M, E, device=dev, dtype=f32)
+    s.mean1 = torch.empty(M, device=dev, dtype=f32) if save else None
+    s.rstd1 = torch.empty(M, device=dev, dtype=f32) if save else None
+    K.layernorm_fwd32(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1, x1_32,
+                      s.mean1, s.rstd1)
+    u = torch.empty(M, F, device=dev, dtype=bf16) if save else None
     h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u, drop=dl(DropCfg.ACT),
                  out=None if xs is None else xs[2])
     s.xs = xs
-    lr = torch.empty(B * T, E, device=dev, dtype=bf16) if want_lr else None
-    y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr, drop=dl(DropCfg.DROP3))
-    x2 = out if out is not None else torch.empty_like(y2)
-    s.mean2 = torch.empty(B * T, device=dev, dtype=f32) if save else None
-    s.rstd2 = torch.empty(B * T, device=dev, dtype=f32) if save else None
-    K.layernorm_fwd(y2, P[prefix + "final_layer_norm.weight"], P[prefix + "final_layer_norm.bias"], x2, s.mean2, s.rstd2)
+    d3 = dl(DropCfg.DROP3)
+    y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1_32, drop=d3, out_dtype=f32)
+    lr = torch.empty(M, E, device=dev, dtype=bf16) if want_lr else None
+    if want_lr and d3 is not None:
+        # `layer_result` is the fc2 output BEFORE dropout3 (modules/module.py:577-578); y2 - x1 would be the dropped one
+        K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], out=lr)
+    x2 = out if out is not None else torch.empty(M, E, device=dev, dtype=bf16)
+    s.mean2 = torch.empty(M, device=dev, dtype=f32) if save else None
+    s.rstd2 = torch.empty(M, device=dev, dtype=f32) if save else None
+    recover = want_lr and d3 is None
+    K.layernorm_fwd32(y2, P[prefix + "final_layer_norm.weight"], P[prefix + "final_layer_norm.bias"], x2, out32, s.mean2,
+                      s.rstd2, sub32=x1_32 if recover else None, diff_out=lr if recover else None)
     if save:
         s.qkv, s.attn, s.lse, s.y1, s.x1, s.u, s.h, s.y2 = qkv, attn, lse, y1, x1, u, h, y2
-    s.out, s.lr = x2, lr
+    s.out, s.lr, s.out32 = x2, lr, out32
     return s
 
 
@@ -523,20 +543,22 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
 # teacher
 # =============================================================================================
 def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None, slots=None,
-                    wave_chunks=None):
+                    wave_chunks=None, want_lr: bool = False):
     """Frozen teacher forward (reference utils/utils.py:80-99 around fairseq HubertModel /
     Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] bf16, features [B, T, E]).
     slots: optional list mapping teacher layer -> row of out_buf (None = not a distillation target: that layer's
     output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather."""
     W.ensure_fresh()
-    c = frontend_fwd(P, W, g, wave, valid, save=False, wave_chunks=wave_chunks)
+    c = frontend_fwd(P, W, g, wave, valid, save=False, wave_chunks=wave_chunks, want_enc32=True)
     valid_t = c.valid_t
     B, T, E = c.B, c.T, g.E
     if out_buf is None:
         n_out = g.n_layers if slots is None else 1 + max(s for s in slots if s is not None)
         out_buf = torch.empty(n_out, B, T, E, device=wave.device, dtype=bf16)
-    x = c.enc_in
+    x, x32 = c.enc_in, c.enc_in32
     scratch = None
+    lrs = []
+    ping = [torch.empty(B * T, E, device=wave.device, dtype=f32) for _ in range(2)]  # fp32 copies of the layer outputs
     last = g.n_layers if slots is None else 1 + max(l for l, s in enumerate(slots) if s is not None)
     for l in range(last):  # layers above the highest target are never needed
         slot = l if slots is None else slots[l]
@@ -545,8 +567,12 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
             dst = scratch[l & 1]
         else:
             dst = out_buf[slot].view(B * T, E)
-        s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=False, out=dst)
-        x = s.out
+        s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=want_lr, out=dst, x32=x32,
+                      out32=ping[l & 1] if l + 1 < last else None)
+        x, x32 = s.out, s.out32
+        lrs.append(s.lr)
+    if want_lr:  # the hook output of every layer is (x, (attn, layer_result)), utils/utils.py:65-78
+        return out_buf, c.feats.view(B, T, E), lrs
     return out_buf, c.feats.view(B, T, E)
 
 
@@ -593,15 +619,19 @@ def _compose_heads(W: WeightSet, g: Geometry, hs: Dict[str, int], n: int):
 
 def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], *, train: bool,
                     heads: str = "all", want_lr: bool = False, pred_buf=None, drop: Optional[DropCfg] = None,
-                    wave_chunks=None):
+                    wave_chunks=None, n_run: Optional[int] = None):
     """Student forward (reference modules/model.py:420-552).  heads: 'all' (12 LayerWiseProjHeads),
     'last' (after _disable_projection_heads: final_proj on the last layer), 'none'.
+    n_run: transformer layers to execute (the reference's `layer=` early exit, modules/module.py:335-340); the heads then
+    see the last executed layer's output.
     Returns ctx: .layers [n_layers][B*Ts, E], .tr [B*Ts, E], .preds [n_layers or 1, B, T', D], .feats."""
     W.ensure_fresh()
+    n_run = g.n_layers if n_run is None else max(0, min(int(n_run), g.n_layers))
+    assert n_run == g.n_layers or (not train and heads != "all"), "early exit is an inference-time option without heads"
     dev = wave.device
     if drop is not None and not drop.any():
         drop = None
-    c = frontend_fwd(P, W, g, wave, valid, save=train, drop=drop, wave_chunks=wave_chunks)
+    c = frontend_fwd(P, W, g, wave, valid, save=train, drop=drop, wave_chunks=wave_chunks, want_enc32=not g.tr)
     valid, valid_t = c.valid, c.valid_t  # `valid` may have been a callable (resolved after the conv stack was queued)
     valid_s = _valid_tensor(None if valid is None else [v // 2 for v in valid], dev)
     B, T, E = c.B, c.T, g.E
@@ -618,14 +648,17 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         Ts, tr, valid_s, off = T, None, valid_t, 0
     c.Ts, c.valid_t, c.valid_s, c.drop = Ts, valid_t, valid_s, drop
     c.tr = tr
-    x = tr if tr is not None else c.enc_in
+    x, x32 = (tr, None) if tr is not None else (c.enc_in, c.enc_in32)
     c.layer_ctx = []
     lay = torch.empty(g.n_layers, B * Ts, E, device=dev, dtype=bf16)  # stacked layer outputs (batched heads)
-    for l in range(g.n_layers):
+    ping = [torch.empty(B * Ts, E, device=dev, dtype=f32) for _ in range(2)]  # fp32 copies of the layer outputs
+    c.x_last = x
+    for l in range(n_run):
         s = layer_fwd(P, W, g, f"encoder.layers.{l + off}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l],
-                      drop=drop)
+                      drop=drop, x32=x32, out32=ping[l & 1] if l + 1 < n_run else None)
         c.layer_ctx.append(s)
-        x = s.out
+        x, x32 = s.out, s.out32
+    c.x_last = x  # output of the last executed layer (the TR conv / prologue output when n_run == 0)
     c.lay = lay
     c.layers = [s.out for s in c.layer_ctx]
     c.lrs = [s.lr for s in c.layer_ctx]
@@ -638,7 +671,7 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         if heads == "all":
             N, inter = g.n_split, g.inter
             c.sp_u = torch.empty(B * Ts, N * inter, device=dev, dtype=bf16) if train else None
-            c.sp_h = K.linear(c.layers[-1], W["sp.w1"].view(N * inter, E), P["proj_head.0.bias"], gelu=True, dgelu_out=c.sp_u)
+            c.sp_h = K.linear(c.x_last, W["sp.w1"].view(N * inter, E), P["proj_head.0.bias"], gelu=True, dgelu_out=c.sp_u)
             if pred_buf is None:
                 pred_buf = torch.empty(N, B, Ts, D, device=dev, dtype=bf16)
             a3 = L.tensor3(data_ptr=c.sp_h.data_ptr(), dim=(inter, B * Ts, N), stride=(N * inter, inter))
@@ -682,7 +715,8 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         else:
             c.z = []
             for j, i in enumerate(idx):
-                z = K.linear(c.layers[i], W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"])
+                src = c.layers[i] if i < n_run else c.x_last  # `layer=` early exit: final_proj sees the last executed layer
+                z = K.linear(src, W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"])
                 K.linear(z.view(B * Tq, E), W[f"h{i}.wlin"].view(D, E), P[_head_name(P, i) + "lin_proj.bias"],
                          out=pred_buf[j].view(B * Tq, D))
                 c.z.append(z if train else None)
@@ -801,7 +835,7 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     (batched-heads path only); both head bias gradients are derived from them (fhb_head_bias_grads)."""
     E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
     B, T, Ts, Tq = c.B, c.T, c.Ts, c.Tq
-    dev = dpred.device
+    dev = c.lay.device
     gv = G_.view
     dx = None  # gradient wrt the current layer's output [B*Ts, E]
     n = g.n_layers
@@ -884,17 +918,24 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         K.gemm_raw(a3, b3, dx_head, B * Ts, E, 2 * E, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=E, d_hi_stride=B * Ts * E)
     off = 1 if g.tr else 0
+    # The gradient of the residual stream is carried in fp32 (dx32), like the stream itself in the forward: the dgrad
+    # epilogues add an fp32 residual and write fp32, the LayerNorm backward reads that and emits the bf16 GEMM operand
+    # next to the fp32 copy that continues down the residual.  dxb: bf16 contributions entering at this layer's output
+    # (its projection head, autograd's dlayers), summed inside the LayerNorm backward.
+    dx32 = None
+    dxb = dx  # the split head's gradient wrt the last layer (bf16) or None
+    dx = None
     for l in range(g.n_layers - 1, -1, -1):
         s = c.layer_ctx[l]
         p = f"encoder.layers.{l + off}."
-        hp = f"proj_head.{l}."
-        dx2 = None  # second gradient stream into this layer's output (summed inside the LayerNorm backward)
+        hp = _head_name(P, l)
+
+        def add_b(t, cur):
+            return t if cur is None else K.add_bf16(cur, t, torch.empty_like(t))
+
         if dx_head is not None:
-            if dx is None:
-                dx = dx_head[l]
-            else:
-                dx2 = dx_head[l]
-        elif l in c.head_idx:
+            dxb = add_b(dx_head[l], dxb)
+        elif l in c.head_idx and not g.n_split:
             j = c.head_idx.index(l)
             dp = dpred[j].view(B * Tq, D)
             z = c.z[j].view(B * Tq, E)
@@ -904,32 +945,26 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.colsum(dz, gv(hp + "upsampler.bias"))
             dz2 = dz.view(B * Ts, 2 * E)
             K.linear_wgrad(dz2, s.out, out=gv(hp + "upsampler.weight").view(2 * E, E), accumulate=True)
-            dx = K.linear_dgrad(dz2, W[f"h{l}.wup"].view(2 * E, E), residual=dx)
+            dxb = add_b(K.linear_dgrad(dz2, W[f"h{l}.wup"].view(2 * E, E)), dxb)
         if dlayers is not None and dlayers[l] is not None:
-            if dx is None:
-                dx = dlayers[l]
-            elif dx2 is None:
-                dx2 = dlayers[l]
-            else:
-                dx2 = K.add_bf16(dx2, dlayers[l], torch.empty_like(dx))
-        if dx is None:
+            dxb = add_b(dlayers[l], dxb)
+        if dx32 is None and dxb is None:
             continue
-        # final LayerNorm.  With dropout3 active the LayerNorm backward also writes dy2 * mask: that copy feeds the
-        # fc2 branch (wgrad, dgrad, bias gradient), the plain dy2 continues down the residual.
+        M_ = B * Ts
+        # final LayerNorm.  With dropout3 active the bf16 copy is dy2 * mask: it feeds the fc2 branch (wgrad, dgrad, bias
+        # gradient), the un-masked fp32 dy2 continues down the residual.
         drop = getattr(c, "drop", None)
         dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
         xs = getattr(s, "xs", None)
         dys = torch.empty_like(xs) if xs is not None else None  # [dy1m, du, dy2m]: A operands of the batched wgrad
         d3 = dl(DropCfg.DROP3)
-        if dys is not None:
-            dy2m = dys[2]
-            dy2 = torch.empty_like(dx) if d3 is not None else dy2m
-        else:
-            dy2 = torch.empty_like(dx)
-            dy2m = torch.empty_like(dx) if d3 is not None else dy2
-        K.layernorm_bwd(dx, s.y2, P[p + "final_layer_norm.weight"], s.mean2, s.rstd2, dy2,
-                        gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"), dxsum=gv(p + "fc2.bias"),
-                        dy2=dx2, dx_drop=dy2m if d3 is not None else None, drop=d3)
+        dy2m = dys[2] if dys is not None else torch.empty(M_, E, device=dev, dtype=bf16)
+        dy2_32 = torch.empty(M_, E, device=dev, dtype=f32)
+        K.layernorm_bwd32(dx32, s.y2, P[p + "final_layer_norm.weight"], s.mean2, s.rstd2,
+                          gv(p + "final_layer_norm.weight"), gv(p + "final_layer_norm.bias"), dy2=dxb,
+                          dx=None if d3 is not None else dy2m, dx32=dy2_32, dxsum=gv(p + "fc2.bias"),
+                          dx_drop=dy2m if d3 is not None else None, drop=d3)
+        dxb = None
         # FFN (fc2 bias gradient = column sums of dy2m: accumulated by the LayerNorm backward above; the saved
         # s.u = gelu'(u) * activation-dropout mask, s.h = dropped activations)
         if dys is None:
@@ -940,24 +975,20 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.colsum(du, gv(p + "fc1.bias"))
             if dys is None:
                 K.linear_wgrad(du, s.x1, out=gv(p + "fc1.weight").view(F, E), accumulate=True)
-        dx1 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2)
+        dx1_32 = K.linear_dgrad(du, W[f"l{l}.w1"].view(F, E), residual=dy2_32, out_dtype=f32)
         # attention LayerNorm (same scheme for dropout1 on the out_proj branch)
         d1 = dl(DropCfg.DROP1)
-        if dys is not None:
-            dy1m = dys[0]
-            dy1 = torch.empty_like(dx1) if d1 is not None else dy1m
-        else:
-            dy1 = torch.empty_like(dx1)
-            dy1m = torch.empty_like(dx1) if d1 is not None else dy1
-        K.layernorm_bwd(dx1, s.y1, P[p + "self_attn_layer_norm.weight"], s.mean1, s.rstd1, dy1,
-                        gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"),
-                        dxsum=gv(p + "self_attn.out_proj.bias"), dx_drop=dy1m if d1 is not None else None, drop=d1)
+        dy1m = dys[0] if dys is not None else torch.empty(M_, E, device=dev, dtype=bf16)
+        dy1_32 = dy2_32  # its last reader (the fc1 dgrad epilogue above) is queued before this writer
+        K.layernorm_bwd32(dx1_32, s.y1, P[p + "self_attn_layer_norm.weight"], s.mean1, s.rstd1,
+                          gv(p + "self_attn_layer_norm.weight"), gv(p + "self_attn_layer_norm.bias"),
+                          dx=None if d1 is not None else dy1m, dx32=dy1_32, dxsum=gv(p + "self_attn.out_proj.bias"),
+                          dx_drop=dy1m if d1 is not None else None, drop=d1)
         # attention block (out_proj bias gradient: accumulated by the LayerNorm backward above)
         with aside(dys if dys is not None else dy1m):
             if dys is not None:
                 # dW[j] += dys[j]^T xs[j] for j = out_proj, fc1, fc2: one batched split-K launch (ob = j); the three
                 # gradient segments are adjacent in the flat buffer (GradStore order)
-                M_ = B * Ts
                 a3 = L.tensor3(data_ptr=dys.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
                 b3 = L.tensor3(data_ptr=xs.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
                 assert G_.entries[p + "fc1.weight"][0] - G_.entries[p + "self_attn.out_proj.weight"][0] == E * E and \
@@ -967,16 +998,20 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             else:
                 K.linear_wgrad(dy1m, s.attn, out=gv(p + "self_attn.out_proj.weight").view(E, E), accumulate=True)
         dattn = K.linear_dgrad(dy1m, W[f"l{l}.wo"].view(E, E))
-        dqkv = torch.empty(B * Ts, 3 * E, device=dev, dtype=bf16)
+        dqkv = torch.empty(M_, 3 * E, device=dev, dtype=bf16)
         delta = torch.empty(B, H, Ts, device=dev, dtype=f32)
-        dq_ws = torch.empty(B * Ts, E, device=dev, dtype=f32) if d in (40, 64) else None
+        dq_ws = torch.empty(M_, E, device=dev, dtype=f32) if d in (40, 64) else None
         K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5, drop=dl(DropCfg.ATTN),
                    dq_ws=dq_ws)
         with aside(dqkv):
             K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
             K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
                            accumulate=True)
-        dx = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1)
+        if l > 0:
+            dx32 = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1_32, out_dtype=f32)
+        else:  # what leaves the encoder layers feeds bf16 GEMM operands (TR conv / prologue backward)
+            dx = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1_32)
+            dx32 = None
     if on_layers_done is not None:
         # every gradient of the heads and of the transformer layers is final from here on (85 % of the bytes): the
         # data-parallel exchange of that part can start under the front-end / conv-stack backward below

@@ -33,9 +33,9 @@ class UpstreamExpert(nn.Module):
     def get_downsample_rates(self, key: str):
         return 320
 
-    @torch.no_grad()
     def forward(self, wavs):
-        """fithubert/expert.py:52-75.  The reference pads the wavs and builds `padding_mask = ~(arange(Lmax) < len)`, from
+        """fithubert/expert.py:52-75 (differentiable like the reference's: with grad enabled and trainable parameters the
+        hand-written backward runs behind torch.autograd, so s3prl's upstream fine-tuning works).  The reference pads the wavs and builds `padding_mask = ~(arange(Lmax) < len)`, from
         which the model recovers `len` again (modules/model.py:449-472); here the lengths go to the model directly and
         the zero-padded batch is assembled in HBM (one async copy per wav - DMA straight from the caller's buffer when
         it is pinned or already on the device), so no [B, Lmax] mask or padded host copy is ever made."""

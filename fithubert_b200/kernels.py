@@ -78,6 +78,9 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
     for name, t in (("residual", residual), ("aux_in", aux_in), ("aux_out", aux_out), ("loss_target", loss_target)):
         # "laid out like D": same element offset as the output
         setattr(g, name, None if t is None else t.data_ptr() + d_offset_elems * t.element_size())
+    if residual is not None and residual.dtype == torch.float32:
+        flags |= L.EPI_RES_F32  # the fp32 copy of the residual stream (layernorm_fwd32 / layernorm_bwd32)
+        g.flags = flags
     g.loss_weight, g.grad_scale = loss_weight, grad_scale
     g.bias_hi_stride = bias_hi_stride
     if drop is not None and drop[1] > 0.0:  # (seed, p)
@@ -134,12 +137,12 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, dgelu_of=None, mul_aux=None, residual=None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, out_dtype=bf16) -> torch.Tensor:
     """dx[M,K] = dy[M,N] @ w[N,K]  (w consumed MN-major: no transposed copy), optionally * gelu'(dgelu_of)
-    or * mul_aux (a saved gelu'), + residual."""
+    or * mul_aux (a saved gelu'), + residual (bf16 or fp32)."""
     M, N = dy.shape
     K = w.shape[1]
-    dx = out if out is not None else torch.empty(M, K, device=dy.device, dtype=bf16)
+    dx = out if out is not None else torch.empty(M, K, device=dy.device, dtype=out_dtype)
     assert dgelu_of is None or mul_aux is None
     flags = (L.EPI_MUL_DGELU if dgelu_of is not None else 0) | (L.EPI_MUL_AUX if mul_aux is not None else 0) | \
         (L.EPI_RESIDUAL if residual is not None else 0)
@@ -219,6 +222,31 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
     return y
 
 
+def layernorm_fwd32(x32, gamma, beta, y, y32=None, mean=None, rstd=None, sub32=None, diff_out=None, eps=1e-5):
+    """LayerNorm of the fp32 pre-LN sum: y bf16 (GEMM operand), y32 the fp32 copy the next residual add reads;
+    diff_out = bf16(x32 - sub32) (the FFN branch output the reference returns as `layer_result`)."""
+    assert x32.dtype == torch.float32 and (y32 is None or y32.dtype == torch.float32)
+    rows, Cd = x32.numel() // x32.shape[-1], x32.shape[-1]
+    L.check(L.lib().fhb_layernorm_fwd32(L.ptr(x32), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(y32), L.ptr(mean),
+                                        L.ptr(rstd), L.ptr(sub32), L.ptr(diff_out), C.c_int64(rows), Cd, _f(eps),
+                                        L.stream_ptr()), "fhb_layernorm_fwd32")
+    return y
+
+
+def layernorm_bwd32(dy32, x32, gamma, mean, rstd, dgamma, dbeta, *, dy2=None, dx=None, dx32=None, dxsum=None,
+                    dx_drop=None, drop=None):
+    """Backward of layernorm_fwd32.  Gradient in = dy32 (fp32, optional) + dy2 (bf16, optional); out = dx32 (fp32,
+    the backward residual stream), dx (bf16) and / or dx_drop (bf16, dropout-masked, with drop=(seed, p))."""
+    assert x32.dtype == torch.float32 and (dy32 is None or dy32.dtype == torch.float32)
+    assert dy2 is None or dy2.dtype == bf16
+    rows, Cd = x32.numel() // x32.shape[-1], x32.shape[-1]
+    seed, p = (drop[0] & 0xFFFFFFFF, drop[1]) if (drop is not None and dx_drop is not None) else (0, 0.0)
+    L.check(L.lib().fhb_layernorm_bwd32(L.ptr(dy32), L.ptr(dy2), L.ptr(x32), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
+                                        L.ptr(dx), L.ptr(dx32), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dxsum), L.ptr(dx_drop),
+                                        C.c_uint32(seed), _f(p), C.c_int64(rows), Cd, L.stream_ptr()),
+            "fhb_layernorm_bwd32")
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=None, dy2=None, dx_drop=None,
                   drop=None):
     """dxsum (fp32 [C], accumulated): column sums of dx = bias gradient of the linear layer that produced x.
@@ -243,10 +271,11 @@ def posconv_wn_prep(v, g, w_fwd, w_bwd, ws, Cd, G, Kt, cp, delta=1):
                                         L.stream_ptr()), "fhb_posconv_wn_prep")
 
 
-def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5, delta=1):
+def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5, delta=1,
+                       y32=None):
     L.check(L.lib().fhb_posconv_finish_fwd(L.ptr(x), L.ptr(valid), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(beta),
-                                           L.ptr(h_out), L.ptr(y), L.ptr(mean), L.ptr(rstd), B, T, Cd, G, cp, _f(eps),
-                                           delta, L.stream_ptr()), "fhb_posconv_finish_fwd")
+                                           L.ptr(h_out), L.ptr(y), L.ptr(y32), L.ptr(mean), L.ptr(rstd), B, T, Cd, G, cp,
+                                           _f(eps), delta, L.stream_ptr()), "fhb_posconv_finish_fwd")
 
 
 def posconv_finish_bwd(dy, h, conv, bias, gamma, mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, Cd, G, cp, pad_l, Tp,

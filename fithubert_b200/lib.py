@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfhb_sm100a.so")
 
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROWZERO = 1, 2, 4, 8
 EPI_STORE_PREACT, EPI_MUL_DGELU, EPI_OUT_F32, EPI_ATOMIC_ADD, EPI_SQDIFF = 16, 32, 64, 128, 256
-EPI_AUX_DGELU, EPI_MUL_AUX, EPI_DROPOUT = 512, 1024, 2048
+EPI_AUX_DGELU, EPI_MUL_AUX, EPI_DROPOUT, EPI_RES_F32 = 512, 1024, 2048, 4096
 
 
 class FhbError(RuntimeError):
@@ -101,7 +101,7 @@ def _declare(l):
 # every symbol include/fhb.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
     "fhb_last_error", "fhb_abi_version", "fhb_set_pdl", "fhb_gemm", "fhb_conv0_gn_gelu_fwd", "fhb_conv0_gn_gelu_bwd", "fhb_conv0_im2col", "fhb_conv0_bwd_finalize",
-    "fhb_layernorm_fwd", "fhb_layernorm_bwd", "fhb_posconv_pack", "fhb_posconv_wn_prep",
+    "fhb_layernorm_fwd", "fhb_layernorm_bwd", "fhb_layernorm_fwd32", "fhb_layernorm_bwd32", "fhb_posconv_pack", "fhb_posconv_wn_prep",
     "fhb_posconv_finish_fwd", "fhb_posconv_finish_bwd", "fhb_posconv_unpack_bwd", "fhb_posconv_wn_bwd",
     "fhb_attn_fwd", "fhb_attn_bwd", "fhb_distill_loss_fwd_bwd", "fhb_distill_loss_sim_fwd_bwd", "fhb_adamw_multi", "fhb_prep_multi",
     "fhb_colsum", "fhb_colsum_batched", "fhb_head_bias_grads", "fhb_add_bf16", "fhb_mul_dgelu", "fhb_mul_bf16", "fhb_dropout", "fhb_mask_lengths", "fhb_memset2d",

@@ -304,13 +304,20 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
 
     # ---- engine plumbing -----------------------------------------------------------------
     def engine_state(self, train: bool):
+        """(parameters, bf16 shadows, flat gradient buffer).  The gradient buffer (and with it the optimizer's moments,
+        which are laid out like it) only depends on the parameter tensors: an eval-mode forward between two training
+        steps (validation) re-uses the training shadows - they are a superset - and never resets anything."""
         P = _named_param_dict(self)
-        _require_cuda(next(iter(P.values())), "CustomStudentModel")
-        if self._weights is None or self._weights.train != train or self._weights.device != next(iter(P.values())).device \
-                or any(self._weights.params[k] is not v and self._weights.params[k].data_ptr() != v.data_ptr()
-                       for k, v in P.items()):
+        first = next(iter(P.values()))
+        _require_cuda(first, "CustomStudentModel")
+        W = self._weights
+        stale = W is None or W.device != first.device or any(
+            W.params[k] is not v and W.params[k].data_ptr() != v.data_ptr() for k, v in P.items())
+        if stale:
             self._weights = E.WeightSet(P, self._geom, train)
             self._grads = None
+        elif train and not W.train:
+            self._weights = E.WeightSet(P, self._geom, True)  # adds the dgrad-layout shadows; gradients untouched
         if train and self._grads is None:
             self._grads = E.GradStore(P, self._geom)
         return P, self._weights, self._grads
@@ -319,8 +326,6 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
         """Reference modules/model.py:420-552.  `lengths` (not in the reference signature, optional): the per-sample
         un-padded lengths the caller already knows, i.e. (~padding_mask).sum(-1); when given, the [B, L] mask is
         neither needed nor scanned (UpstreamExpert builds its mask from these very numbers)."""
-        if layer is not None:
-            raise NotImplementedError("`layer` early exit is not implemented on the B200 path")
         dev = self.post_extract_proj.weight.device
         _require_cuda(self.post_extract_proj.weight, "CustomStudentModel")
         source = source.to(dev, non_blocking=True).float().contiguous()
@@ -334,16 +339,26 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
                 lengths = None  # no sample is padded: the reference runs mask-free (modules/model.py:449,471-472)
         valid = None if lengths is None else conv_out_lengths(lengths, self._conv_layers)
         heads = "all" if self.proj_head is not None else ("last" if self.final_proj is not None else "none")
+        n_run = None
+        if layer is not None:
+            # modules/module.py:300-340: `layer` indexes encoder.layers (entry 0 is the time-reduction conv when enabled);
+            # the loop breaks after that entry, so entries 0..layer run
+            n_run = max(0, min(self._geom.n_layers, int(layer) + (0 if self.enable_tr_layer else 1)))
+            if n_run < self._geom.n_layers and heads == "all" and self.layerwise_proj:
+                # the reference indexes layer_results[i] for every head (modules/model.py:493-499)
+                raise IndexError("list index out of range")
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad and n_run is not None and n_run < self._geom.n_layers:
+            raise NotImplementedError("the `layer` early exit has no backward on the B200 path (inference-time option)")
         if needs_grad:
-            if heads != "all":
-                raise NotImplementedError("training without the layer-wise projection heads is not implemented")
+            if not self.layerwise_proj and heads != "all":
+                raise NotImplementedError("fine-tuning the SplitLinear recipe without its head is not implemented")
             from .autograd import student_apply
             c, preds, layers_out = student_apply(self, source, valid)
         else:
             P, W, _ = self.engine_state(False)
             c = E.student_forward(P, W, self._geom, source, valid, train=False, heads=heads, want_lr=True,
-                                  drop=self.drop_cfg())
+                                  drop=self.drop_cfg(), n_run=n_run)
             preds, layers_out = c.preds, c.layers
         B, T, Ts, Em = c.B, c.T, c.Ts, self._geom.E
         mask = _frame_mask(valid, T, dev)
@@ -353,14 +368,14 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
         if not self.layerwise_proj:
             # reference modules/model.py:504-518: x stays the encoder output, projections is ONE [B, N, T, D] tensor
             projections = None if preds is None else preds.permute(1, 0, 2, 3)
-            x = layers_out[-1].view(B, Ts, Em)
+            x = c.x_last.view(B, Ts, Em)
         elif heads == "all":
             projections = [preds[i] for i in range(preds.shape[0])]
             x = projections[-1]
         elif heads == "last":
             projections, x = None, preds[0]
         else:
-            projections, x = None, layers_out[-1].view(B, Ts, Em)
+            projections, x = None, c.x_last.view(B, Ts, Em)
         return {
             "x": x,
             "padding_mask": mask,
@@ -419,28 +434,32 @@ class TeacherModel(_ParamCacheMixin, nn.Module):
         return None if lengths is None else conv_out_lengths(lengths, self._conv_layers)
 
     @torch.no_grad()
-    def extract_features(self, source, padding_mask=None, mask=None, out_buf=None):
+    def extract_features(self, source, padding_mask=None, mask=None, out_buf=None, want_lr=False):
         dev = self.post_extract_proj.weight.device
         source = source.to(dev, non_blocking=True).float().contiguous()
         P, W = self.engine_state()
         T = E.conv_frames(source.shape[1], self._conv_layers)[-1]
         valid = self.frame_valid(padding_mask, source.shape[1], T)
-        layers, feats = E.teacher_forward(P, W, self._geom, source, valid, out_buf=out_buf)
-        return layers, feats, valid
+        res = E.teacher_forward(P, W, self._geom, source, valid, out_buf=out_buf, want_lr=want_lr)
+        return (*res, valid) if want_lr else (*res, None, valid)
 
 
 class TeacherWrapper(nn.Module):
     """Same contract as reference utils/utils.py:51-99: extract_features(source, padding_mask) ->
-    {'layer_results': [(x [T,B,C], (None, None))] * n_layers, 'x': [B,T,C], 'features': [post_extract_proj out]}."""
+    {'layer_results': [(x [T,B,C], (None, layer_result [T,B,C]))] * n_layers, 'x': [B,T,C],
+    'features': [post_extract_proj out]} - each entry is what the forward hook on an encoder layer captures
+    (utils/utils.py:65-78: the layer returns (x, (attn, layer_result)), attn None with need_weights=False)."""
 
     def __init__(self, model: TeacherModel):
         super().__init__()
         self.model = model
 
     def extract_features(self, source, padding_mask=None, out_buf=None):
-        layers, feats, valid = self.model.extract_features(source, padding_mask, out_buf=out_buf)
+        layers, feats, lrs, valid = self.model.extract_features(source, padding_mask, out_buf=out_buf, want_lr=True)
+        B, T, C = layers.shape[1:]
         res = {
-            "layer_results": [(layers[i].transpose(0, 1), (None, None)) for i in range(layers.shape[0])],
+            "layer_results": [(layers[i].transpose(0, 1), (None, lrs[i].view(B, T, C).transpose(0, 1)))
+                              for i in range(layers.shape[0])],
             "x": layers[-1],
             "features": [feats],
         }

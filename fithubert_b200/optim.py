@@ -32,10 +32,18 @@ class FusedAdamW:
 
     def _build(self):
         P, W, G = self.model.engine_state(True)
-        self.P, self.W, self.G = P, W, G
         dev = G.flat.device
-        self.m = torch.zeros(G.numel, device=dev, dtype=torch.float32)
-        self.v = torch.zeros(G.numel, device=dev, dtype=torch.float32)
+        layout = tuple((pn, e[0], e[1]) for pn, e in G.entries.items())
+        if getattr(self, "m", None) is not None and self.m.device == dev and layout == getattr(self, "_layout", None):
+            pass  # same gradient layout (a rebuilt buffer, moved parameters): the moments stay
+        elif self.step_count > 0 and getattr(self, "m", None) is not None:
+            raise L.FhbError("the student's parameter set changed after optimizer steps were taken: Adam moments cannot "
+                             "be carried over (build a new optimizer, or restore one from a checkpoint)")
+        else:
+            self.m = torch.zeros(G.numel, device=dev, dtype=torch.float32)
+            self.v = torch.zeros(G.numel, device=dev, dtype=torch.float32)
+        self._layout = layout
+        self.P, self.W, self.G = P, W, G
         entries, mx = [], 1
         for pn, (off, n, dims, gs) in G.entries.items():
             e = L.AdamwTensor()
@@ -61,6 +69,7 @@ class FusedAdamW:
         P, W, G = self.model.engine_state(True)
         if self._table is None or G is not self.G or self._ptrs != tuple(P[pn].data_ptr() for pn in G.entries):
             self._build()
+        self.W = W
         self.step_count += 1
         b1, b2 = self.betas
         K.adamw_multi(self._table, self._n, self._max_n, self.current_lr(), b1, b2, self.eps, self.wd,

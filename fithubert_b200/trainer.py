@@ -78,6 +78,22 @@ def restore(model, path: str) -> Dict:
     return state
 
 
+def _global_mean(total, count: int, world: int) -> float:
+    """sum(total) / sum(count) over all ranks (one small all-reduce; NaN when no rank saw a batch)."""
+    if world > 1:
+        dev = total.device if isinstance(total, torch.Tensor) else (
+            torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+        pair = torch.zeros(2, dtype=torch.float64, device=dev)
+        if total is not None:
+            pair[0] = float(total) if not isinstance(total, torch.Tensor) else total.detach().double()
+        pair[1] = float(count)
+        dist.all_reduce(pair)
+        total, count = pair[0], float(pair[1])
+    if total is None or count <= 0:
+        return float("nan")
+    return float(total) / float(count)
+
+
 def fit(model, train_loader, val_loader=None, num_epochs: Optional[int] = None, output_dir: Optional[str] = None,
         ckpt_path: Optional[str] = None, save_top_k: int = 3, patience: int = 15, log_every: int = 0) -> Dict:
     """trainer.fit(model, ckpt_path=...) of train.py:492-509.  `model` is a W2V2Distil; the loaders are BucketLoaders
@@ -109,7 +125,10 @@ def fit(model, train_loader, val_loader=None, num_epochs: Optional[int] = None, 
             if log_every and rank == 0 and (i + 1) % log_every == 0:
                 print(f"epoch {epoch} step {i + 1}: loss {float(loss):.5f} lr {model.optimizer.current_lr():.3e}", flush=True)
         model.training_epoch_end()
-        train_loss = float(run / max(1, nb)) if run is not None else float("nan")
+        # every rank sees only its shard: the monitored values are (sum, count) pairs reduced over the ranks, so all
+        # ranks rank checkpoints and hit EarlyStopping on the same epoch (Lightning syncs both; a rank-local decision
+        # would leave the others blocked in the next gradient all-reduce)
+        train_loss = _global_mean(run, nb, world)
         v_loss = float("nan")
         if val_loader is not None:
             model.student_model.eval()
@@ -118,7 +137,7 @@ def fit(model, train_loader, val_loader=None, num_epochs: Optional[int] = None, 
                 v = model.validation_step(batch, i)["v_loss"] * batch["x"].shape[0]
                 tot = v if tot is None else tot + v
                 cnt += batch["x"].shape[0]
-            v_loss = float(tot / max(1, cnt)) if tot is not None else float("nan")
+            v_loss = _global_mean(tot, cnt, world)
         history.append((epoch, train_loss, v_loss))
         monitor = v_loss if val_loader is not None else train_loss
         if saver is not None:

@@ -60,9 +60,11 @@ enum {
   FHB_EPI_SQDIFF = 256,     /* fused distillation loss, see fhb_gemm_args.loss_*             */
   FHB_EPI_AUX_DGELU = 512,  /* with STORE_PREACT: aux_out = gelu'(value before GELU) instead  */
   FHB_EPI_MUL_AUX = 1024,   /* * aux_in[m][n] (e.g. a gelu' saved by FHB_EPI_AUX_DGELU)       */
-  FHB_EPI_DROPOUT = 2048    /* nn.Dropout(drop_p) after bias/GELU, before the residual; the    */
+  FHB_EPI_DROPOUT = 2048,   /* nn.Dropout(drop_p) after bias/GELU, before the residual; the    */
                             /* mask of element (ob, m, n) is a hash of (drop_seed, index), see  */
                             /* fhb_dropout; with AUX_DGELU the saved gelu' is masked the same   */
+  FHB_EPI_RES_F32 = 4096    /* the residual is fp32 (the high-precision copy of the residual    */
+                            /* stream the LayerNorm kernels keep next to the bf16 GEMM operand) */
 };
 
 typedef struct {
@@ -147,6 +149,22 @@ int fhb_layernorm_bwd(const void* dy, const void* dy2 /* optional: gradient = dy
                       const float* gamma, const float* mean, const float* rstd,
                       const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, void* dx_drop,
                       uint32_t drop_seed, float drop_p, int64_t rows, int32_t C, fhb_stream_t stream);
+/* The residual stream of the post-LN transformer layers (modules/module.py:557-580: x = LN(x + branch(x))) is carried in
+ * fp32 next to the bf16 GEMM operands: the out_proj / fc2 epilogues add an fp32 residual (FHB_EPI_RES_F32) and write the
+ * sum in fp32 (FHB_EPI_OUT_F32); these variants read that sum.
+ *  fwd32: x32 fp32 [rows][C] -> y (bf16, the next GEMM's A operand), y32 (optional fp32 copy, the next residual operand);
+ *         sub32 + diff_out (optional, together): diff_out = bf16(x32 - sub32) = the FFN branch output `layer_result`
+ *         the reference returns per layer (modules/module.py:577-580, modules/model.py:493-499).
+ *  bwd32: gradient = dy32 (fp32, optional) + dy2 (bf16, optional), at least one; x32 = the saved fp32 sum; outputs
+ *         dx32 (optional fp32, continues down the residual), dx (optional bf16), dx_drop (optional bf16, dx * the
+ *         dropout mask of (drop_seed, drop_p)); dgamma / dbeta / dxsum ACCUMULATED as in fhb_layernorm_bwd (dxsum sums
+ *         dx_drop when given, else dx). */
+int fhb_layernorm_fwd32(const float* x32, const float* gamma, const float* beta, void* y, float* y32, float* mean,
+                        float* rstd, const float* sub32, void* diff_out, int64_t rows, int32_t C, float eps,
+                        fhb_stream_t stream);
+int fhb_layernorm_bwd32(const float* dy32, const void* dy2, const float* x32, const float* gamma, const float* mean,
+                        const float* rstd, void* dx, float* dx32, float* dgamma, float* dbeta, float* dxsum,
+                        void* dx_drop, uint32_t drop_seed, float drop_p, int64_t rows, int32_t C, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ positional conv (K5) helpers
  * The grouped Conv1d(k=128, pad=64, groups=16) of modules/module.py:186-200,276-278 runs as a batched
@@ -167,9 +185,10 @@ int fhb_posconv_pack(const void* x, const int32_t* valid, void* xg, int32_t B, i
  * 1 / ||v[:, :, j]|| (the inv_norm argument of fhb_posconv_wn_bwd).  Group width C / G must be even, K | 256. */
 int fhb_posconv_wn_prep(const float* v, const float* g, void* w_fwd, void* w_bwd, float* ws, int32_t C, int32_t G,
                         int32_t K, int32_t cp, int32_t delta, fhb_stream_t stream);
+/* y32 (optional): fp32 copy of y, the residual operand of the first transformer layer (see fhb_layernorm_fwd32) */
 int fhb_posconv_finish_fwd(const void* x, const int32_t* valid, const void* conv, const float* bias,
-                           const float* gamma, const float* beta, void* h_out, void* y, float* mean, float* rstd,
-                           int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps, int32_t delta,
+                           const float* gamma, const float* beta, void* h_out, void* y, float* y32, float* mean,
+                           float* rstd, int32_t B, int32_t T, int32_t C, int32_t G, int32_t cp, float eps, int32_t delta,
                            fhb_stream_t stream);
 /* dh = LN-bwd(dy) and dcg[b][g][t+pad_l][cp] = dh * gelu'(conv + bias) (group-major, time-padded: the
  * A operand of the dgrad GEMM and the B operand of the wgrad GEMM) in one pass; dgamma/dbeta/dbias are

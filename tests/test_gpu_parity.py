@@ -2,9 +2,11 @@
 kernels through the C ABI (libfhb_sm100a.so) and compares with (a) the golden fixtures produced by the
 unmodified reference, (b) the CPU oracle on seeded inputs, (c) size-independent properties at full size.
 
-Tolerances (BASELINE.json north_star): bf16 path 2e-2 max-abs / max|ref| for hidden states and loss;
-integer outputs (masks, lengths) bit-exact.  Parameter gradients are compared at 4e-2: they are sums of
-bf16-rounded products over up to 25k rows (the reference's own bf16-autocast gradients deviate as much).
+Tolerances (BASELINE.json north_star): bf16 path 2e-2 max-abs / max|ref| for hidden states, loss and every
+parameter gradient (at every depth: the residual stream and its gradient are carried in fp32 next to the bf16 GEMM
+operands, tests/precision_emul.py); integer outputs (masks, lengths) bit-exact.  The one exception is a gradient that
+is mathematically zero (k_proj.bias: a constant shift of every key leaves the softmax unchanged), skipped below a
+1e-9 absolute reference like tests/test_oracle_golden.py does.
 """
 import glob
 import os
@@ -18,8 +20,8 @@ import fhb_oracle as O
 pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "tiny_*.pt")))
 TOL = 2e-2
-GTOL = 4e-2
-DEEP_TOL = 4e-2  # raw hidden states of the deeper layers at the real 12-layer depth (see the cfg-4 test)
+GTOL = 2e-2
+DEEP_TOL = 2e-2  # raw hidden states of every layer at the real 12-layer depth (cfg-4 / cfg-5 / full-geometry tests)
 
 
 def rel(a, b):
@@ -92,6 +94,19 @@ def test_gemm_variants(F):
         ref = (dy2.float() @ w3.float()) * gp.float()
         assert rel(K.linear_dgrad(dy2, w3, mul_aux=gp), ref) < 1e-2
         assert rel(K.linear_dgrad(dy2, w3, mul_aux=gp, residual=r2), ref + r2.float()) < 1e-2
+    # fp32 residual stream: fp32 residual + fp32 output (TMA ring with fp32 slabs), and the mixed cases (direct reads)
+    for (M, N, Kd) in [(700, 480, 480), (1000, 768, 3072), (130, 96, 96)]:
+        x, w, b = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev)
+        r32, r16 = torch.randn(M, N, device=dev), rnd(M, N)
+        ref = x.float() @ w.float().t() + b
+        y = K.linear(x, w, b, residual=r32, out_dtype=torch.float32)
+        assert y.dtype == torch.float32 and rel(y, ref + r32) < 1e-5
+        assert rel(K.linear(x, w, b, residual=r16, out_dtype=torch.float32), ref + r16.float()) < 1e-5
+        assert rel(K.linear(x, w, b, residual=r32), ref + r32) < 1e-2
+        w2 = rnd(Kd, N, sc=0.05)  # dgrad: dx = dy @ w2 + residual
+        dyy = rnd(M, Kd)
+        assert rel(K.linear_dgrad(dyy, w2, residual=r32, out_dtype=torch.float32), dyy.float() @ w2.float() + r32) < 1e-5
+        assert rel(K.linear_dgrad(dyy, w2, residual=r32), dyy.float() @ w2.float() + r32) < 1e-2
     dy, xx = rnd(5000, 480, sc=0.1), rnd(5000, 960)
     assert rel(K.linear_wgrad(dy, xx), dy.float().t() @ xx.float()) < 2e-3
     # k=3,s=2 convolution as an overlapping-row TMA view
@@ -131,6 +146,31 @@ def test_layernorm_fwd_bwd(F):
         K.layernorm_bwd(dya, x, g, mean, rstd, dx2, dg2, db2, dxsum=dsum, dy2=dyb)
         assert rel(dx2, xr.grad) < 1.5e-2 and rel(dg2, gr.grad) < 5e-3 and rel(db2, br.grad) < 5e-3
         assert rel(dsum, xr.grad.sum(0)) < 5e-3  # fp32 sums of the un-rounded dx
+        # fp32 residual-stream variants: fp32 sum in -> bf16 operand + fp32 copy (+ x - sub as bf16) out, and back
+        x32 = torch.randn(1000, C, device="cuda") * 2 + 0.3
+        sub = torch.randn(1000, C, device="cuda")
+        y16, y32, df = torch.empty_like(x), torch.empty_like(x32), torch.empty_like(x)
+        K.layernorm_fwd32(x32, g, b, y16, y32, mean, rstd, sub32=sub, diff_out=df)
+        xr = x32.clone().requires_grad_(True)
+        ref = Fn.layer_norm(xr, (C,), gr, br, 1e-5)
+        assert rel(y32, ref) < 1e-5 and rel(y16, ref) < 1e-2 and rel(df, x32 - sub) < 1e-2
+        assert torch.equal(y16, y32.bfloat16())
+        gr.grad = br.grad = None
+        d32, d16 = torch.randn(1000, C, device="cuda"), torch.randn(1000, C, device="cuda").bfloat16()
+        ref.backward(d32 + d16.float())
+        o16, o32, od = torch.empty_like(x), torch.empty_like(x32), torch.empty_like(x)
+        dg, db, dsum = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        K.layernorm_bwd32(d32, x32, g, mean, rstd, dg, db, dy2=d16, dx=o16, dx32=o32, dxsum=dsum)
+        assert rel(o32, xr.grad) < 1e-5 and torch.equal(o16, o32.bfloat16())
+        assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4 and rel(dsum, xr.grad.sum(0)) < 1e-4
+        dg.zero_(), db.zero_(), dsum.zero_()
+        K.layernorm_bwd32(None, x32, g, mean, rstd, dg, db, dy2=d16, dx32=o32, dx_drop=od, dxsum=dsum, drop=(1234, 0.25))
+        xr.grad = None
+        Fn.layer_norm(xr, (C,), g, b, 1e-5).backward(d16.float())
+        assert rel(o32, xr.grad) < 1e-5
+        keep = od.float() != 0
+        assert 0.70 < float(keep.float().mean()) < 0.80 and rel(od.float()[keep], (o32 / 0.75)[keep]) < 1e-2
+        assert rel(dsum, od.float().sum(0)) < 1e-3
 
 
 def test_conv0_groupnorm_gelu_fwd_bwd(F):
@@ -486,7 +526,7 @@ def test_oracle_parity_fithubert_group_geometry(F):
     for n, p in student.named_parameters():
         if p.grad is None or ref_sd[n].grad is None or ref_sd[n].grad.abs().max() < 1e-8:
             continue
-        assert rel(p.grad, ref_sd[n].grad) < 6e-2, n
+        assert rel(p.grad, ref_sd[n].grad) < GTOL, n
 
 
 @pytest.mark.parametrize("loss_type", ["l1", "mse"])
@@ -595,7 +635,7 @@ def test_split_head_recipe_matches_reference_fixture(F):
         ref = g["grads"][n]
         if ref.abs().max() < 1e-9:
             continue
-        assert p.grad is not None and rel(p.grad, ref) < 6e-2, n  # L1's sign gradient is bf16-noise sensitive
+        assert p.grad is not None and rel(p.grad, ref) < GTOL, n
     # fused training step: same loss, parameters move
     step.configure_optimizers(total_steps=100)
     before = student.state_dict()["proj_head.2.weight"].clone()
@@ -765,12 +805,10 @@ def test_cfg4_expert_full_model_matches_oracle(F):
             errs[f"l{l}[{b}]"] = rel(out["hidden_states"][l][0][:v, b], ref["layer_results"][l][0][:v, j])
             assert torch.isfinite(out["hidden_states"][l][0][:, b].float()).all()
     print("cfg-4 full-depth parity, valid frames (max|diff| / max|ref|):", {n: round(e, 4) for n, e in errs.items()})
-    # north_star's bf16 budget (2e-2) holds for last_hidden_state and the lower layers; the bf16 rounding of the
-    # residual stream accumulates with depth, which is inside what the reference's own bf16-autocast run deviates from
-    # its fp32 run (1.5 - 2.7e-2), so the deeper raw hidden states are held to DEEP_TOL.
+    # north_star's bf16 budget (2e-2) at every depth: the residual stream is carried in fp32, so the deviation no
+    # longer grows with the layer index (round 1: 2.2 - 3.4e-2 at layers 9-11)
     for n, e in errs.items():
-        deep = n.startswith("l") and int(n[1:n.index("[")]) >= 4
-        assert e < (DEEP_TOL if deep else TOL), (n, errs)
+        assert e < TOL, (n, errs)
 
 
 def test_cfg5_w2v2_teacher_30s_and_step(F):
@@ -798,7 +836,7 @@ def test_cfg5_w2v2_teacher_30s_and_step(F):
     assert torch.isfinite(tr["_stacked"].float()).all()
     print("cfg-5 teacher full-depth parity, valid frames (max|diff| / max|ref|):", {l: round(e, 4) for l, e in errs.items()})
     for l, e in errs.items():
-        assert e < (DEEP_TOL if l >= 4 else TOL), (l, errs)
+        assert e < TOL, (l, errs)
     del teacher, tr
     cfg = bench.yaml_cfg()
     cfg["teacher"]["teacher_model"] = "wav2vec_small.pt"
@@ -847,3 +885,233 @@ def test_per_linear_wgrad_launches_match_oracle(F, monkeypatch):
     by every gradient check above).  FHB_WGRAD_BATCH=0 keeps one launch per Linear: same oracle comparison."""
     monkeypatch.setenv("FHB_WGRAD_BATCH", "0")
     test_oracle_parity_fithubert_group_geometry(F)
+
+
+# ----------------------------------------------------------------------------- round 2: the real geometry, every gradient
+def _dump(name, rows):
+    """Per-tensor deviation table next to the gpurun logs (read back into profiles/ by hand)."""
+    d = os.path.join(os.path.dirname(__file__), "..", "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, name), "w") as f:
+            for k, v in rows:
+                f.write(f"{v:.5f}  {k}\n")
+
+
+def test_full_geometry_step_matches_oracle(F):
+    """One distillation step at FitHuBERT's REAL geometry - 12 layers, D = 480, H = 12, twelve 480 -> 768 heads, HuBERT-Base
+    teacher with mask rule M3 at T = 779 - on B = 2 utterances of cfg-2's lengths (15.6 s) against the CPU oracle: all 12
+    teacher layers, all 12 student hidden states and projections, the loss, and EVERY parameter gradient at 2e-2."""
+    from fithubert_b200.autograd import _DistillLossFn
+    scfg, tcfg = O.student_config(), O.teacher_config()
+    ssd, tsd = O.init_student_state(scfg, 0, perturb=True), O.init_teacher_state(tcfg, 1, perturb=True)
+    Lmax = 249600
+    lens = [Lmax, 243187]
+    x, pm = O.synth_batch(2, Lmax, lens, seed=21)
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+    with torch.no_grad():
+        t_ref = O.teacher_forward(tsd, tcfg, x, pm)
+    s_ref = O.student_forward(ref_sd, scfg, x, pm)
+    w = O.layer_weights(12, 0.1)
+    loss_ref, per_ref = O.distill_loss(s_ref["projections"], t_ref["layer_results"], w)
+    loss_ref.backward()
+    teacher = F.TeacherModel(kind="hubert")
+    teacher.load_state_dict(tsd)
+    teacher = F.TeacherWrapper(teacher.cuda())
+    student = F.CustomStudentModel(full_student_cfg(F, dict(pred_layer_id="[11]")))
+    student.load_state_dict(ssd)
+    student = student.cuda().eval()
+    tr = teacher.extract_features(x.cuda(), pm)
+    T = 779
+    tv = (~t_ref["padding_mask"]).sum(-1).tolist()
+    assert tr["_valid"] == tv and tr["x"].shape == (2, T, 768)
+    rows = []
+    for l in range(12):
+        rows.append((f"teacher layer {l}", max(rel(tr["layer_results"][l][0][:tv[b], b], t_ref["layer_results"][l][0][:tv[b], b])
+                                               for b in range(2))))
+        # the hook output of a teacher layer is (x, (attn, layer_result)) (utils/utils.py:65-78)
+        lr = tr["layer_results"][l][1][1]
+        assert tr["layer_results"][l][1][0] is None and lr.shape == (T, 2, 768)
+        rows.append((f"teacher layer_result {l}", max(rel(lr[:tv[b], b], t_ref["layer_results"][l][1][1][:tv[b], b]) for b in range(2))))
+    sr = student(x.cuda(), pm)
+    assert torch.equal(sr["padding_mask"].cpu(), s_ref["padding_mask"])
+    sv = [v // 2 for v in (~s_ref["padding_mask"]).sum(-1).tolist()]
+    for l in range(12):
+        rows.append((f"student layer {l}", max(rel(sr["layer_results"][l][0][:sv[b], b], s_ref["layer_results"][l][0][:sv[b], b])
+                                               for b in range(2))))
+        rows.append((f"projection {l}", max(rel(sr["projections"][l][b, :2 * sv[b]], s_ref["projections"][l][b, :2 * sv[b]])
+                                            for b in range(2))))
+    loss, per_layer = _DistillLossFn.apply(sr["projections"][0]._base, tr["_stacked"], torch.tensor(w, device="cuda"), 0)
+    loss.backward()
+    grows = []
+    for n, p in student.named_parameters():
+        if p.grad is None or ref_sd[n].grad is None or ref_sd[n].grad.abs().max() < 1e-9:
+            continue
+        grows.append((n, rel(p.grad, ref_sd[n].grad)))
+    _dump("r02_full_geometry_parity.txt", rows + [("loss", abs(float(loss) - float(loss_ref)) / float(loss_ref))] +
+          sorted(grows, key=lambda r: -r[1]))
+    print("full geometry: worst activations", sorted(rows, key=lambda r: -r[1])[:3], "worst grads",
+          sorted(grows, key=lambda r: -r[1])[:5])
+    assert abs(float(loss) - float(loss_ref)) < 1e-2 * float(loss_ref) and rel(per_layer, per_ref) < 1e-2
+    for k, e in rows:
+        assert e < TOL, (k, e)
+    assert len(grows) >= 255
+    for k, e in grows:
+        assert e < GTOL, (k, e)
+
+
+def test_host_batch_chunked_path_matches_device_path_and_oracle(F):
+    """What bench.py's `e2e` measures: a pinned HOST batch with B >= 4 is copied in batch slices on a copy stream and
+    both conv stacks run slice by slice (distill.py / engine.h2d_chunked).  Same step with the batch already resident
+    in HBM: identical per-layer losses, gradients equal up to the order of the fp32 split-K atomics; and both agree
+    with the oracle."""
+    import bench
+    s_over = dict(conv_feature_layers="[(16, 10, 5)] + [(32, 1, 1)] + [(32, 3, 2)] * 4 + [(64, 1, 1)] + [(64, 2, 2)] * 2",
+                  encoder_layers=3, encoder_embed_dim=96, encoder_ffn_embed_dim=96, encoder_attention_heads=4,
+                  conv_pos=16, conv_pos_groups=4, pred_head_final_dim=64)
+    t_over = dict(conv_feature_layers="[(32,10,5)] + [(32,3,2)] * 4 + [(32,2,2)] * 2", encoder_layers=3,
+                  encoder_embed_dim=64, encoder_ffn_embed_dim=128, encoder_attention_heads=4, conv_pos=16, conv_pos_groups=4)
+    scfg, tcfg = O.student_config(**s_over), O.teacher_config(**t_over)
+    ssd, tsd = O.init_student_state(scfg, 5, perturb=True), O.init_teacher_state(tcfg, 6, perturb=True)
+    lens = [24000, 22100, 19000, 16001, 12345]
+    x, pm = O.synth_batch(5, 24000, lens, seed=3)
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+    with torch.no_grad():
+        t_ref = O.teacher_forward(tsd, tcfg, x, pm)
+    s_ref = O.student_forward(ref_sd, scfg, x, pm)
+    w = O.layer_weights(3, 0.1)
+    loss_ref, per_ref = O.distill_loss(s_ref["projections"], t_ref["layer_results"], w)
+    loss_ref.backward()
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(s_over)
+    cfg["distiller"]["pred_layer_id"] = "[2]"
+    cfg["train"]["distil_random_layer"] = 2
+    teacher = F.TeacherModel(kind="hubert", **t_over)
+    teacher.load_state_dict(tsd)
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    step.student_model.load_state_dict(ssd)
+    step.student_model.eval()
+    step.configure_optimizers(total_steps=100)
+    outs = []
+    for host in (False, True):
+        xb = x.pin_memory() if host else x.cuda()
+        pmb = pm.pin_memory() if host else pm
+        step.optimizer.zero_grad()
+        ll = step.fused_forward_backward(xb, pmb)
+        _, _, G = step.student_model.engine_state(True)
+        outs.append((ll.clone(), {k: v.clone() for k, v in G.export().items()}))
+    (l_dev, g_dev), (l_host, g_host) = outs
+    assert torch.equal(l_dev, l_host)
+    assert rel(l_host, per_ref) < 1e-2 and abs(float(l_host.sum()) - float(loss_ref)) < 1e-2 * float(loss_ref)
+    for n, gr in g_host.items():
+        if ref_sd[n].grad is None or ref_sd[n].grad.abs().max() < 1e-9:
+            continue
+        assert rel(gr, g_dev[n]) < 1e-4, n
+        assert rel(gr, ref_sd[n].grad) < GTOL, n
+
+
+def test_layer_early_exit_and_expert_finetune_gradients(F):
+    """`layer=` of CustomStudentModel.forward / extract_features (modules/model.py:491,554-558; modules/module.py:335-340)
+    after _disable_projection_heads, against the oracle's layer outputs; and UpstreamExpert.forward is differentiable
+    like the reference's (fithubert/expert.py:52): gradients of a loss on its outputs reach the student parameters and
+    match autograd through the oracle."""
+    g = torch.load(GOLDEN[1])
+    scfg = O.student_config(**g["student_cfg"])
+    ssd = g["student_state"]
+    cfg = {"distiller": dict(extractor_mode="default", layerwise_proj=True, enable_tr_layer=True, tr_layer_index=0,
+                             tr_layer_type="conv1d", required_seq_len_multiple=1, pred_layer_id="[2]", **g["student_cfg"])}
+    ck = {"state_dict": {"student_model." + k: v for k, v in ssd.items()}}
+    ex = F.UpstreamExpert(ck, cfg).cuda().eval()
+    x, pm = g["source"], g["padding_mask"]
+    with torch.no_grad():
+        ref = O.student_forward(ssd, scfg, x, pm, heads=False)
+        full = ex.model(x.cuda(), pm)
+        assert rel(full["x"], ref["x"]) < TOL
+        for k in (0, 1, 2, 3):  # entry 0 of encoder.layers is the time-reduction conv
+            out = ex.model.extract_features(x.cuda(), pm, layer=k)
+            assert len(out["layer_results"]) == k
+            hid = ref["tr_layer_results"][0] if k == 0 else ref["layer_results"][k - 1][0]
+            # x = final_proj(output of entry k), modules/model.py:500-502
+            want = torch.nn.functional.conv_transpose1d(hid.permute(1, 2, 0), ssd["proj_head.2.upsampler.weight"],
+                                                        ssd["proj_head.2.upsampler.bias"], stride=2).transpose(1, 2)
+            want = torch.nn.functional.linear(want, ssd["proj_head.2.lin_proj.weight"], ssd["proj_head.2.lin_proj.bias"])
+            assert out["x"].shape == want.shape and rel(out["x"], want) < TOL, k
+    # with every head present the reference indexes layer_results[i] for each of them and fails
+    _, student = build_pair(F, g)
+    with torch.no_grad(), pytest.raises(IndexError):
+        student(x.cuda(), pm, layer=1)
+    # fine-tuning through the expert: d(sum of squares of last_hidden_state + hidden_states[1]) / d(parameters)
+    ex.train()
+    for p in ex.parameters():
+        p.requires_grad_(True)
+    ex.model._drop_p = dict(p_input=0.0, p_drop=0.0, p_attn=0.0, p_act=0.0)  # parity at p = 0
+    lens = (~pm).sum(-1).tolist()
+    out = ex([x[i, :n].cuda() for i, n in enumerate(lens)])
+    loss = out["last_hidden_state"].float().pow(2).mean() + out["hidden_states"][1][0].float().pow(2).mean()
+    loss.backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+    r = O.student_forward(ref_sd, scfg, x, pm, heads=False)
+    (r["x"].pow(2).mean() + r["layer_results"][1][0].pow(2).mean()).backward()
+    seen = 0
+    for n, p in ex.model.named_parameters():
+        rn = n.replace("final_proj.", "proj_head.2.")
+        if ref_sd[rn].grad is None or ref_sd[rn].grad.abs().max() < 1e-9:
+            continue
+        assert p.grad is not None and rel(p.grad, ref_sd[rn].grad) < GTOL, n
+        seen += 1
+    assert seen > 40
+
+
+def _ddp_worker(rank, world, port, cfg, ssd, tsd, t_over, x, pm, out):
+    import torch.distributed as dist
+    import fithubert_b200 as F
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    teacher = F.TeacherModel(kind="hubert", **t_over)
+    teacher.load_state_dict(tsd)
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    step.student_model.load_state_dict(ssd)
+    step.student_model.eval()
+    step.configure_optimizers(total_steps=100)
+    step.optimizer.zero_grad()
+    n = x.shape[0] // world
+    step.fused_forward_backward(x[rank * n:(rank + 1) * n].cuda(), pm[rank * n:(rank + 1) * n])
+    _, _, G = step.student_model.engine_state(True)
+    step.reducer.reduce_all(G.flat)
+    step.reducer.wait()
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save((G.flat / world).cpu(), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_nccl_step_equals_one_process_on_the_concatenated_batch(F, tmp_path):
+    """N ranks, each on its contiguous slice of the batch, per-rank mean loss, NCCL all-reduce of
+    the flat gradient buffer and the 1 / world scale = one process on the whole batch (equal-shape shards)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import bench
+    import torch.multiprocessing as mp
+    g = torch.load(GOLDEN[0])
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"]["pred_layer_id"] = "[2]"
+    cfg["train"]["distil_random_layer"] = 2
+    tc = dict(g["teacher_cfg"])
+    tc.pop("kind")
+    x, pm = O.synth_batch(4, 9000, [9000, 8000, 7000, 6000], seed=5)
+    out = str(tmp_path / "flat.pt")
+    mp.start_processes(_ddp_worker, args=(2, 29533, cfg, g["student_state"], g["teacher_state"], tc, x, pm, out), nprocs=2,
+                       start_method="spawn")
+    flat2 = torch.load(out)
+    teacher = F.TeacherModel(kind="hubert", **tc)
+    teacher.load_state_dict(g["teacher_state"])
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    step.student_model.load_state_dict(g["student_state"])
+    step.student_model.eval()
+    step.configure_optimizers(total_steps=100)
+    step.optimizer.zero_grad()
+    step.fused_forward_backward(x.cuda(), pm)
+    _, _, G = step.student_model.engine_state(True)
+    assert rel(flat2, G.flat) < 2e-3  # same arithmetic, different tile / atomic order
