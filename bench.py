@@ -209,6 +209,9 @@ def measure_student_fwd(dev, B, Lmax, Lmin, steps, warmup, seed, world):
     from fithubert_b200 import kernels as K
     torch.manual_seed(0)
     ex = F.UpstreamExpert(None, {"distiller": yaml_cfg()["distiller"]}).to(dev).eval()
+    for p_ in ex.parameters():  # feature extraction (s3prl's frozen-upstream mode): the forward is differentiable like
+        p_.requires_grad_(False)  # the reference's, so gradients are switched off here, at the caller
+    torch.set_grad_enabled(False)
     lengths = synth_lengths_uniform(B, Lmin, Lmax, seed)
     g = torch.Generator().manual_seed(seed)
     host = [(0.1 * torch.randn(n, generator=g)).pin_memory() for n in lengths]
@@ -245,6 +248,7 @@ def measure_student_fwd(dev, B, Lmax, Lmin, steps, warmup, seed, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
+    torch.set_grad_enabled(True)
     flops = CFG4["flop_per_utt"] * (Lmax / CFG4["Lmax"]) * B
     return {
         "metric": "student fwd audio-sec/sec", "value": audio_s * world * steps / (ms / 1e3), "unit": "audio-s/s",

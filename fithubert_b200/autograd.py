@@ -7,6 +7,12 @@ import torch
 
 from . import engine as E
 
+# Loss scale of the fp16 gradient that _DistillLossFn.backward has just handed to autograd: consumed by the next
+# _StudentFn.backward (the chain between the two is linear - views, stacks, permutes - so the scale survives it),
+# which divides the exported parameter gradients by it.  Gradients of any other loss arrive un-scaled (scale 1):
+# callers that feed fp16 outputs into their own loss scale it themselves, as under torch.cuda.amp.
+_PENDING_SCALE = [1.0]
+
 
 class _StudentFn(torch.autograd.Function):
     @staticmethod
@@ -19,8 +25,17 @@ class _StudentFn(torch.autograd.Function):
         ctx.model, ctx.c, ctx.names = model, c, [n for n, _ in model.named_parameters()]
         ctx.set_materialize_grads(False)  # outputs the loss never touched arrive as None, not as zero tensors
         model._last_ctx = c
-        preds = c.preds if c.preds is not None else source.new_zeros(0)
-        return (preds, *c.layers)
+        outs = (c.preds if c.preds is not None else source.new_zeros(0), *c.layers)
+        # autograd stamps the RETURNED tensor objects with this node's grad_fn.  The context the backward keeps must not
+        # hold those same objects, or node -> ctx -> c -> tensor -> node is a reference cycle no collector sees (every
+        # call's saved activations would stay allocated): keep detached aliases instead.
+        if c.preds is not None:
+            c.preds = c.preds.detach()
+        c.layers = [t.detach() for t in c.layers]
+        for s_, t in zip(c.layer_ctx, c.layers):
+            s_.out = t
+        c.x_last = c.x_last.detach()
+        return outs
 
     @staticmethod
     def backward(ctx, dpreds, *dlayers):
@@ -31,11 +46,13 @@ class _StudentFn(torch.autograd.Function):
             dpreds = None
         elif dpreds is None:
             dpreds = torch.zeros_like(c.preds)
+        scale, _PENDING_SCALE[0] = _PENDING_SCALE[0], 1.0
         if dpreds is not None:
-            dpreds = dpreds.to(torch.bfloat16).contiguous()
-        dl = [None if d is None else d.to(torch.bfloat16).contiguous() for d in dlayers]
+            dpreds = dpreds.to(torch.float16).contiguous()
+        dl = [None if d is None else (d.float() * scale).to(torch.float16).contiguous() if scale != 1.0 else
+              d.to(torch.float16).contiguous() for d in dlayers]
         E.student_backward(P, W, model._geom, G, c, dpreds, dl)
-        grads = G.export()
+        grads = G.export(scale=scale)
         return (None, None, None, *[grads.get(n) for n in ctx.names])
 
 
@@ -49,22 +66,24 @@ def student_apply(model, source, valid):
 class _DistillLossFn(torch.autograd.Function):
     """Fused K10: per-layer weighted MSE/L1 (+ optional cosine, train.py:302-314) between projections and teacher
     layers + d(loss)/d(pred) in one pass (reference train.py:250-314).
-    apply(preds, tgt, weights, loss_type[, rec_weight=1, sim_weight=0]) -> (total, per-layer rec[, per-layer sim]);
-    total = rec_weight * sum(rec) + sim_weight * sum(sim)."""
+    apply(preds, tgt, weights, loss_type[, rec_weight=1, sim_weight=0, loss_scale=auto]) -> (total, per-layer rec
+    [, per-layer sim]); total = rec_weight * sum(rec) + sim_weight * sum(sim).  The fp16 gradient handed back to autograd
+    is multiplied by loss_scale (see _PENDING_SCALE)."""
 
     @staticmethod
     def forward(ctx, preds, tgt, weights, loss_type, *extra):
-        rec_weight, sim_weight = (tuple(extra) + (1.0, 0.0)[len(extra):])[:2]
+        rec_weight, sim_weight, scale = (tuple(extra) + (1.0, 0.0, 0.0)[len(extra):])[:3]
         n, B, Tq, D = preds.shape
+        ctx.scale = float(scale) if scale else E.loss_scale_for(B * Tq * D)
         Tt = tgt.shape[2]
         ctx.n_in = 4 + len(extra)
         rec = torch.zeros(n, device=preds.device, dtype=torch.float32)
         dpred = torch.empty_like(preds)
         ctx.args = (preds, tgt, weights, n, B, Tq, Tt, D, loss_type, float(rec_weight), float(sim_weight))
-        sim = _run_loss(ctx.args, rec, dpred, 1.0)
+        sim = _run_loss(ctx.args, rec, dpred, ctx.scale)
         ctx.save_for_backward(dpred)
         total = rec.sum() * rec_weight  # 12-element reductions; the heavy lifting is the kernel above
-        if sim is None:
+        if not sim_weight:
             ctx.mark_non_differentiable(rec)
             return total, rec
         ctx.mark_non_differentiable(rec, sim)
@@ -76,7 +95,8 @@ class _DistillLossFn(torch.autograd.Function):
         scale = float(gtotal)  # one scalar D2H; 1.0 unless the caller rescales the loss (grad accumulation)
         if scale != 1.0:
             scratch = torch.zeros(ctx.args[3], device=dpred.device, dtype=torch.float32)
-            _run_loss(ctx.args, scratch, dpred, scale)
+            _run_loss(ctx.args, scratch, dpred, scale * ctx.scale)
+        _PENDING_SCALE[0] = ctx.scale
         return (dpred,) + (None,) * (ctx.n_in - 1)
 
 

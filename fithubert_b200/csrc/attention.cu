@@ -1,4 +1,4 @@
-// K7: flash-style masked self-attention, forward + backward, bf16 in / fp32 softmax statistics.
+// K7: flash-style masked self-attention, forward + backward, fp16 in / fp32 softmax statistics.
 // Reference: fairseq MultiheadAttention manual path reached from modules/module.py:558-564
 // (bmm QK^T -> masked_fill(-inf on padded keys) -> fp32 softmax -> bmm PV); the T x T score matrix is
 // never materialised here.  Padded QUERY rows are computed like any other row (their outputs enter the
@@ -26,11 +26,19 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t&
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+// F16: fp16 operands (every 16-bit tensor of the library; gradients carry a loss scale); false: bf16
+template <bool F16 = true>
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if constexpr (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
   const int sz = pred ? 16 : 0;
@@ -58,7 +66,7 @@ __device__ __forceinline__ void zero_pad_cols(__nv_bfloat16* s, int d) {
   if (padc <= 0) return;
   for (int i = threadIdx.x; i < kTile * padc; i += blockDim.x) {
     const int r = i / padc, c = d + (i - r * padc);
-    s[r * (DP + 8) + c] = __float2bfloat16(0.f);
+    s[r * (DP + 8) + c] = __float2bfloat16(0.f);  // all-zero bits in either 16-bit format
   }
 }
 
@@ -72,7 +80,7 @@ __device__ __forceinline__ void load_a_frags(const __nv_bfloat16* s, int warp, i
   }
 }
 // acc[8][4] (16 x 64) += A(frags, 16 x DP) * B^T where B tile is [64 rows (n)][DP (k)] in smem
-template <int DP>
+template <int DP, bool F16 = true>
 __device__ __forceinline__ void mma_a_bt(float (*acc)[4], const uint32_t (*af)[4], const __nv_bfloat16* bs, int lane) {
 #pragma unroll
   for (int kk = 0; kk < DP / 16; ++kk) {
@@ -83,13 +91,13 @@ __device__ __forceinline__ void mma_a_bt(float (*acc)[4], const uint32_t (*af)[4
       const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3);
       const int col = kk * 16 + ((lane >> 3) & 1) * 8;
       ldsm_x4(smem_u32(bs + row * (DP + 8) + col), b0, b1, b2, b3);
-      mma16816(acc[2 * np], af[kk], b0, b1);
-      mma16816(acc[2 * np + 1], af[kk], b2, b3);
+      mma16816<F16>(acc[2 * np], af[kk], b0, b1);
+      mma16816<F16>(acc[2 * np + 1], af[kk], b2, b3);
     }
   }
 }
 // acc[DP/8][4] (16 x DP) += P(frags pf[4][4], 16 x 64) * B where B tile is [64 rows (k)][DP (n)] in smem
-template <int DP>
+template <int DP, bool F16 = true>
 __device__ __forceinline__ void mma_p_b(float (*acc)[4], const uint32_t (*pf)[4], const __nv_bfloat16* bs, int lane) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
@@ -100,18 +108,19 @@ __device__ __forceinline__ void mma_p_b(float (*acc)[4], const uint32_t (*pf)[4]
       const int row = kk * 16 + (lane & 15);
       const int col = np * 16 + (lane >> 4) * 8;
       ldsm_x4_t(smem_u32(bs + row * (DP + 8) + col), b0, b1, b2, b3);
-      mma16816(acc[2 * np], pf[kk], b0, b1);
-      mma16816(acc[2 * np + 1], pf[kk], b2, b3);
+      mma16816<F16>(acc[2 * np], pf[kk], b0, b1);
+      mma16816<F16>(acc[2 * np + 1], pf[kk], b2, b3);
     }
   }
 }
+template <bool F16 = true>
 __device__ __forceinline__ void acc_to_frags(const float (*s)[4], uint32_t (*pf)[4]) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    pf[kk][0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-    pf[kk][1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-    pf[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pf[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    pf[kk][0] = pack16(s[2 * kk][0], s[2 * kk][1], F16);
+    pf[kk][1] = pack16(s[2 * kk][2], s[2 * kk][3], F16);
+    pf[kk][2] = pack16(s[2 * kk + 1][0], s[2 * kk + 1][1], F16);
+    pf[kk][3] = pack16(s[2 * kk + 1][2], s[2 * kk + 1][3], F16);
   }
 }
 
@@ -155,7 +164,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ v
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    mma_a_bt<DP>(s, qf, Ks, lane);
+    mma_a_bt<DP>(s, qf, Ks, lane);  // fp16 q, k
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -207,7 +216,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ v
       o[i][3] *= alpha[1];
     }
     uint32_t pf[4][4];
-    acc_to_frags(s, pf);
+    acc_to_frags(s, pf);  // probabilities -> fp16
     mma_p_b<DP>(o, pf, Vs, lane);
   }
 #pragma unroll
@@ -225,7 +234,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ v
 #pragma unroll
     for (int i = 0; i < DP / 8; ++i) {
       const int col = i * 8 + 2 * tq;
-      if (col < d) *reinterpret_cast<uint32_t*>(orow + col) = pack_bf16(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
+      if (col < d) *reinterpret_cast<uint32_t*>(orow + col) = pack_f16(o[i][2 * r] * inv, o[i][2 * r + 1] * inv);
     }
     if (lse && tq == 0) lse[((long long)b * H + h) * T + row] = (m_i[r] + log2f(l_i[r])) * kLn2;
   }
@@ -249,7 +258,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
     const uint32_t au[4] = {a.x, a.y, a.z, a.w}, eu[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 x = unpack_bf16(au[j]), y = unpack_bf16(eu[j]);
+      const float2 x = unpack_f16(au[j]), y = unpack_f16(eu[j]);
       s += x.x * y.x + x.y * y.y;
     }
   }
@@ -318,7 +327,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict
         dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
       }
       mma_a_bt<DP>(st, kf, Qs, lane);  // S^T[key][q]
-      mma_a_bt<DP>(dp, vf, Ds, lane);  // dP^T[key][q] = V dO^T
+      mma_a_bt<DP>(dp, vf, Ds, lane);        // dP^T[key][q] = V dO^T
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -339,7 +348,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict
       acc_to_frags(st, pf);
       mma_p_b<DP>(dv, pf, Ds, lane);  // dV += P^T dO
       acc_to_frags(dp, pf);
-      mma_p_b<DP>(dk, pf, Qs, lane);  // dK += dS^T Q
+      mma_p_b<DP>(dk, pf, Qs, lane);  // dK += dS^T Q 
     }
   }
 #pragma unroll
@@ -352,8 +361,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict
     for (int i = 0; i < DP / 8; ++i) {
       const int col = i * 8 + 2 * tq;
       if (col < d) {
-        *reinterpret_cast<uint32_t*>(krow + col) = pack_bf16(dk[i][2 * r], dk[i][2 * r + 1]);
-        *reinterpret_cast<uint32_t*>(vrow + col) = pack_bf16(dv[i][2 * r], dv[i][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(krow + col) = pack_f16(dk[i][2 * r], dk[i][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(vrow + col) = pack_f16(dv[i][2 * r], dv[i][2 * r + 1]);
       }
     }
   }
@@ -414,8 +423,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict_
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
-    mma_a_bt<DP>(s, qf, Ks, lane);    // S = Q K^T
-    mma_a_bt<DP>(dp, dof, Vs, lane);  // dP = dO V^T
+    mma_a_bt<DP>(s, qf, Ks, lane);            // S = Q K^T
+    mma_a_bt<DP>(dp, dof, Vs, lane);   // dP = dO V^T 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -433,7 +442,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict_
     }
     uint32_t pf[4][4];
     acc_to_frags(dp, pf);
-    mma_p_b<DP>(dq, pf, Ks, lane);  // dQ += dS K
+    mma_p_b<DP>(dq, pf, Ks, lane);  // dQ += dS K 
   }
   __nv_bfloat16* dbase = dqkv + (long long)b * T * ld;
 #pragma unroll
@@ -444,7 +453,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict_
 #pragma unroll
     for (int i = 0; i < DP / 8; ++i) {
       const int col = i * 8 + 2 * tq;
-      if (col < d) *reinterpret_cast<uint32_t*>(qrow + col) = pack_bf16(dq[i][2 * r], dq[i][2 * r + 1]);
+      if (col < d) *reinterpret_cast<uint32_t*>(qrow + col) = pack_f16(dq[i][2 * r], dq[i][2 * r + 1]);
     }
   }
 }

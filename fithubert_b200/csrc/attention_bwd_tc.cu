@@ -12,8 +12,8 @@
 //   warps 0-15: thread = (key row, 32-query quarter).  S^T / dP^T out of TMEM in one batch, then
 //        P^T = 2^(S^T*scale*log2e - lse_q), Pd^T = P^T o dropmask, dS^T = P^T o (dP^T o dropmask - delta_q)  [the
 //        softmax scale is applied once to dK at the final store and to dQ in dq_convert, not per element],
-//        both written as bf16 A operands (128B-swizzled);  dQ_i is drained TMEM -> smem -> TMA reduce-add (fp32)
-//        into a [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to bf16 afterwards.
+//        both written as fp16 A operands (128B-swizzled);  dQ_i is drained TMEM -> smem -> TMA reduce-add (fp32)
+//        into a [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to fp16 afterwards.
 // S^T_{i+1} / dP^T_{i+1} are issued as soon as the compute warps hold tile i in registers, so the tensor pipe
 // works ahead of the exponentials.  Ragged edges are trimmed: the last query tile issues N = ceil16(valid
 // queries) and contracts over that many queries only; warps whose queries or keys are all out of range skip
@@ -137,21 +137,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_load_3d(&tm_qkv, kv_full, smem + S::kV, 2 * HDall + h * HD, k0, b);
       load_qd(0);
       if (nq > 1) load_qd(1);
-      const uint32_t id_kv = umma_idesc_bf16(128, DK, 0, 1);   // dV / dK: A K-major (queries), B MN-major
-      const uint32_t id_dq = umma_idesc_bf16(128, DK, 1, 1);   // dQ: A = dS^T read MN-major, B = K MN-major
+      // every operand is fp16 (tcgen05 kind::f16 needs A and B in ONE format: mixing fp16 with bf16 is an illegal
+      // instruction on sm_100a)
+      const uint32_t id_dv = umma_idesc_16(128, DK, 0, 1, 0, 0);   // dV / dK: A K-major (queries), B MN-major
+      const uint32_t id_dk = id_dv;
+      const uint32_t id_dq = umma_idesc_16(128, DK, 1, 1, 0, 0);   // dQ: A = dS^T read MN-major, B = K MN-major
       const uint32_t ka = smem_u32(smem + S::kK), va = smem_u32(smem + S::kV);
       const uint32_t pa = smem_u32(smem + S::kP), dsa = smem_u32(smem + S::kDS);
       auto nq16 = [&](int i) { return (min(kT, T - i * kT) + 15) & ~15; };  // valid queries of tile i, rounded to 16
       auto issue_s = [&](int i) {
         const uint32_t qa = smem_u32(smem + S::kQ + (i & 1) * kTileBytes);
         const uint32_t da = smem_u32(smem + S::kDO + (i & 1) * kTileBytes);
-        const uint32_t id_s = umma_idesc_bf16(128, (uint32_t)nq16(i), 0, 0);  // both operands K-major over d
+        const uint32_t id_s = umma_idesc_16(128, (uint32_t)nq16(i), 0, 0, 0, 0);   // both operands K-major over d
+        const uint32_t id_p = umma_idesc_16(128, (uint32_t)nq16(i), 0, 0, 0, 0);
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k)
           tc_mma_bf16(tm_s, umma_desc_sw128(ka + k * 32, 0, 1024), umma_desc_sw128(qa + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k)
-          tc_mma_bf16(tm_dp, umma_desc_sw128(va + k * 32, 0, 1024), umma_desc_sw128(da + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
+          tc_mma_bf16(tm_dp, umma_desc_sw128(va + k * 32, 0, 1024), umma_desc_sw128(da + k * 32, 0, 1024), id_p, k > 0 ? 1u : 0u);
         tc_commit(s_full);
       };
       if (HD % 16) mbar_wait(kv_ready, 0); else mbar_wait(kv_full, 0);
@@ -173,12 +177,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const int ksteps = nq16(i) / 16;  // contraction over the valid queries of this tile only
         for (int k = 0; k < ksteps; ++k) {  // A atoms of 64 queries, B 16 query rows = 2 KiB per step
           const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
-          tc_mma_bf16(tm_dv, umma_desc_sw128(pa + aoff, 0, 1024), umma_desc_sw128(da + k * 2048, 0, 1024), id_kv,
+          tc_mma_bf16(tm_dv, umma_desc_sw128(pa + aoff, 0, 1024), umma_desc_sw128(da + k * 2048, 0, 1024), id_dv,
                       (i > 0 || k > 0) ? 1u : 0u);
         }
         for (int k = 0; k < ksteps; ++k) {
           const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
-          tc_mma_bf16(tm_dk, umma_desc_sw128(dsa + aoff, 0, 1024), umma_desc_sw128(qa + k * 2048, 0, 1024), id_kv,
+          tc_mma_bf16(tm_dk, umma_desc_sw128(dsa + aoff, 0, 1024), umma_desc_sw128(qa + k * 2048, 0, 1024), id_dk,
                       (i > 0 || k > 0) ? 1u : 0u);
         }
         if (i > 0) {
@@ -311,10 +315,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             unpack2(mul2(p2, add2(dp2, pack2(nd[e], nd[e + 1]))), ds[e], ds[e + 1]);
           }
           const uint32_t ch = ch0 + (uint32_t)(c >> 3);
-          st_shared_v4(prow + ((ch ^ rsw) << 4), pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]),
-                       pack_bf16(pd[6], pd[7]));
-          st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
-                       pack_bf16(ds[6], ds[7]));
+          st_shared_v4(prow + ((ch ^ rsw) << 4), pack_f16(pd[0], pd[1]), pack_f16(pd[2], pd[3]), pack_f16(pd[4], pd[5]),
+                       pack_f16(pd[6], pd[7]));
+          st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_f16(ds[0], ds[1]), pack_f16(ds[2], ds[3]), pack_f16(ds[4], ds[5]),
+                       pack_f16(ds[6], ds[7]));
         }
       } else if (cols_live) {
         // every key of this warp is masked: P = dS = 0 (the dQ contraction reads these rows)
@@ -331,7 +335,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     mbar_wait(mma_done, (nq - 1) & 1);
     drain_dq(nq - 1);
-    // ---- dK, dV: TMEM -> bf16 -> global.  Thread = key row, columns [16 quad, 16 quad + 16)
+    // ---- dK, dV: TMEM -> fp16 -> global.  Thread = key row, columns [16 quad, 16 quad + 16)
     tc_fence_after();
     if (c16 < DK) {
       __nv_bfloat16* krow = dqkv + ((long long)b * T + key) * ld + HDall + h * HD;
@@ -352,11 +356,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           const uint32_t* a = rk + 8 * q8;
           const uint32_t* v = rv + 8 * q8;
           *reinterpret_cast<uint4*>(krow + c16 + 8 * q8) =
-              make_uint4(pack_bf16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_bf16(__uint_as_float(a[2]), __uint_as_float(a[3])),
-                         pack_bf16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_bf16(__uint_as_float(a[6]), __uint_as_float(a[7])));
+              make_uint4(pack_f16(__uint_as_float(a[0]), __uint_as_float(a[1])), pack_f16(__uint_as_float(a[2]), __uint_as_float(a[3])),
+                         pack_f16(__uint_as_float(a[4]), __uint_as_float(a[5])), pack_f16(__uint_as_float(a[6]), __uint_as_float(a[7])));
           *reinterpret_cast<uint4*>(vrow + c16 + 8 * q8) =
-              make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_bf16(__uint_as_float(v[2]), __uint_as_float(v[3])),
-                         pack_bf16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_bf16(__uint_as_float(v[6]), __uint_as_float(v[7])));
+              make_uint4(pack_f16(__uint_as_float(v[0]), __uint_as_float(v[1])), pack_f16(__uint_as_float(v[2]), __uint_as_float(v[3])),
+                         pack_f16(__uint_as_float(v[4]), __uint_as_float(v[5])), pack_f16(__uint_as_float(v[6]), __uint_as_float(v[7])));
         }
       }
     }
@@ -370,7 +374,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
 }
 
-// dqkv[row][0:E] = bf16(scale * dq_acc[row][0:E])   (the softmax scale the fused kernel left out of dS)
+// dqkv[row][0:E] = fp16(scale * dq_acc[row][0:E])   (the softmax scale the fused kernel left out of dS)
 __global__ void __launch_bounds__(256)
 dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int E8, long long ld,
                   float scale) {
@@ -382,8 +386,8 @@ dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqk
     const float4 a = *reinterpret_cast<const float4*>(acc + r * (E8 * 8) + c);
     const float4 b2 = *reinterpret_cast<const float4*>(acc + r * (E8 * 8) + c + 4);
     *reinterpret_cast<uint4*>(dqkv + r * ld + c) =
-        make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale),
-                   pack_bf16(b2.x * scale, b2.y * scale), pack_bf16(b2.z * scale, b2.w * scale));
+        make_uint4(pack_f16(a.x * scale, a.y * scale), pack_f16(a.z * scale, a.w * scale),
+                   pack_f16(b2.x * scale, b2.y * scale), pack_f16(b2.z * scale, b2.w * scale));
   }
 }
 

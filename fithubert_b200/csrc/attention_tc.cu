@@ -9,7 +9,7 @@
 //                              tcgen05.mma issue:  S_j = Q K_j^T (128x128xd)  and  O += P_j V_j (128xdx128)
 //   warps 0-7: thread = (query row, 64-key half).  S_j is pulled out of TMEM in one batch of tcgen05.ld (which
 //              frees the S columns for S_{j+1} while the exponentials run), online softmax in registers - the two
-//              halves of a row only exchange their maxima through smem once per key tile - and P_j -> bf16 ->
+//              halves of a row only exchange their maxima through smem once per key tile - and P_j -> fp16 ->
 //              swizzled smem (A operand of the second MMA).  16 softmax warps per SM hide the TMEM / MUFU latency.
 //   Ragged edges are trimmed: the last key tile issues N = ceil16(valid keys) and contracts over that many keys
 //   only; warps whose 32 query rows are all >= T skip the exponentials.
@@ -120,12 +120,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
       tma_load_3d(&tm_qkv, q_full, sQ, h * HD, q0, b);
       load_kv(0);
       if (nt > 1) load_kv(1);
-      const uint32_t idesc_o = umma_idesc_bf16(128, DK, 0, 1);   // O: A = P (K-major), B = V (MN-major)
+      const uint32_t idesc_o = umma_idesc_16(128, DK, 0, 1, 0, 0);   // O: A = P (K-major), B = V (MN-major), both fp16
       const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
       auto nk16 = [&](int j) { return (min(kTK, nvalid - j * kTK) + 15) & ~15; };  // valid keys of tile j, rounded
       auto issue_s = [&](int j) {
         const uint32_t ka = smem_u32(sK + (j & 1) * kTileBytes);
-        const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)nk16(j), 0, 0);  // S: A = Q, B = K, both K-major
+        const uint32_t idesc_s = umma_idesc_16(128, (uint32_t)nk16(j), 0, 0, 0, 0);  // S: A = Q, B = K, both K-major, fp16
 #pragma unroll
         for (int k = 0; k < DK / 16; ++k)
           tc_mma_bf16(tmem_s, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024), idesc_s,
@@ -247,7 +247,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
         }
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");  // xch may be rewritten by the next tile only after both halves read it
-      // probabilities -> bf16 -> swizzled smem (K-major A operand: this half's 64-key atom)
+      // probabilities -> fp16 (at most 2^8 after the lazy rescale: in range) -> swizzled smem (K-major A operand: this half's 64-key atom)
       if (work) {
         float ls4[4] = {0.f, 0.f, 0.f, 0.f};
         const float neg_m = -m_i;
@@ -276,10 +276,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
               }
             }
             const uint32_t ch = (uint32_t)(c >> 3);
-            st_shared_v4(prow + (((ch) ^ rsw) << 4), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]),
-                         pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
-            st_shared_v4(prow + (((ch + 1) ^ rsw) << 4), pack_bf16(pv[8], pv[9]), pack_bf16(pv[10], pv[11]),
-                         pack_bf16(pv[12], pv[13]), pack_bf16(pv[14], pv[15]));
+            st_shared_v4(prow + (((ch) ^ rsw) << 4), pack_f16(pv[0], pv[1]), pack_f16(pv[2], pv[3]),
+                         pack_f16(pv[4], pv[5]), pack_f16(pv[6], pv[7]));
+            st_shared_v4(prow + (((ch + 1) ^ rsw) << 4), pack_f16(pv[8], pv[9]), pack_f16(pv[10], pv[11]),
+                         pack_f16(pv[12], pv[13]), pack_f16(pv[14], pv[15]));
           }
         }
         l_i += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
@@ -307,9 +307,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int* __rest
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(o[i]) * inv;
       if (row < T) {
         uint4* op = reinterpret_cast<uint4*>(orow + c);
-        op[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        op[0] = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
         if (c + 8 < HD)
-          op[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          op[1] = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
       }
     }
     if (lse && half == 0 && row < T) lse[((long long)b * H + h) * T + row] = (m_i + log2f(l_row)) * kLn2;

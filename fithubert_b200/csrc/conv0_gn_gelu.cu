@@ -133,7 +133,7 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
     }
     uint32_t pk[CPT / 2];
 #pragma unroll
-    for (int i = 0; i < CPT / 2; ++i) pk[i] = pack_bf16(y[2 * i], y[2 * i + 1]);
+    for (int i = 0; i < CPT / 2; ++i) pk[i] = pack_f16(y[2 * i], y[2 * i + 1]);
     if (CPT == 8) {
       *reinterpret_cast<uint4*>(o + (long long)t * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     } else {
@@ -141,7 +141,7 @@ conv0_fwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
     }
     if (gp_out) {  // gelu'(z): the backward multiplier (applied by the dgrad epilogue of the next layer)
 #pragma unroll
-      for (int i = 0; i < CPT / 2; ++i) pk[i] = pack_bf16(gp[2 * i], gp[2 * i + 1]);
+      for (int i = 0; i < CPT / 2; ++i) pk[i] = pack_f16(gp[2 * i], gp[2 * i + 1]);
       __nv_bfloat16* og = gp_out + ((long long)b * T0 + t_begin) * C + c0 + (long long)t * C;
       if (CPT == 8) *reinterpret_cast<uint4*>(og) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       else *reinterpret_cast<uint2*>(og) = make_uint2(pk[0], pk[1]);
@@ -283,11 +283,11 @@ conv0_fwd_mma_kernel(const float* __restrict__ wave, long long ld, int T0, int C
       for (int row = 0; row < 2; ++row) {
         if (row == 0 ? r0 : r1) {
           const long long off = row * row8 + 32 * grp;
-          *reinterpret_cast<uint4*>(op + off) = make_uint4(pack_bf16(y[row][0], y[row][1]), pack_bf16(y[row][2], y[row][3]),
-                                                              pack_bf16(y[row][4], y[row][5]), pack_bf16(y[row][6], y[row][7]));
+          *reinterpret_cast<uint4*>(op + off) = make_uint4(pack_f16(y[row][0], y[row][1]), pack_f16(y[row][2], y[row][3]),
+                                                              pack_f16(y[row][4], y[row][5]), pack_f16(y[row][6], y[row][7]));
           if (GP)
-            *reinterpret_cast<uint4*>(gpp + off) = make_uint4(pack_bf16(gp[row][0], gp[row][1]), pack_bf16(gp[row][2], gp[row][3]),
-                                                                pack_bf16(gp[row][4], gp[row][5]), pack_bf16(gp[row][6], gp[row][7]));
+            *reinterpret_cast<uint4*>(gpp + off) = make_uint4(pack_f16(gp[row][0], gp[row][1]), pack_f16(gp[row][2], gp[row][3]),
+                                                                pack_f16(gp[row][4], gp[row][5]), pack_f16(gp[row][6], gp[row][7]));
         }
       }
     }
@@ -354,7 +354,7 @@ conv0_bwd_kernel(const float* __restrict__ wave, long long ld, int T0, int C, in
 #pragma unroll
       for (int j = 0; j < kK; ++j) v[j] = xs[t * kS + j];
       const uint2 raw = __ldg(reinterpret_cast<const uint2*>(d + (long long)t * C));
-      const float2 d01 = unpack_bf16(raw.x), d23 = unpack_bf16(raw.y);
+      const float2 d01 = unpack_f16(raw.x), d23 = unpack_f16(raw.y);
       const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
       if (dy_is_dz) {
         // dy already carries gelu'(z) (saved by the forward, multiplied in by the producing dgrad epilogue):
@@ -443,7 +443,7 @@ conv0_bwd_dz_kernel(const float* __restrict__ wave, long long ld, int T0, int C,
         float v[kK];
 #pragma unroll
         for (int j = 0; j < kK; ++j) v[j] = xs[t * kS + j];
-        const float2 d01 = unpack_bf16(raw[u].x), d23 = unpack_bf16(raw[u].y);
+        const float2 d01 = unpack_f16(raw[u].x), d23 = unpack_f16(raw[u].y);
         const float dv[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
@@ -528,14 +528,14 @@ conv0_im2col_kernel(const float* __restrict__ wave, long long ld, int T0, __nv_b
 #pragma unroll
   for (int j = 0; j < kK; ++j) {
     const float v = __ldg(x + j);
-    hi[j] = __bfloat162float(__float2bfloat16(v));
+    hi[j] = __half2float(__float2half_rn(v));
     lo[j] = v - hi[j];
   }
   uint4* o = reinterpret_cast<uint4*>(xcol + ((long long)b * T0 + t) * 32);
-  o[0] = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-  o[1] = make_uint4(pack_bf16(hi[8], hi[9]), pack_bf16(1.0f, 0.f), 0u, 0u);
-  o[2] = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-  o[3] = make_uint4(pack_bf16(lo[8], lo[9]), 0u, 0u, 0u);
+  o[0] = make_uint4(pack_f16(hi[0], hi[1]), pack_f16(hi[2], hi[3]), pack_f16(hi[4], hi[5]), pack_f16(hi[6], hi[7]));
+  o[1] = make_uint4(pack_f16(hi[8], hi[9]), pack_f16(1.0f, 0.f), 0u, 0u);
+  o[2] = make_uint4(pack_f16(lo[0], lo[1]), pack_f16(lo[2], lo[3]), pack_f16(lo[4], lo[5]), pack_f16(lo[6], lo[7]));
+  o[3] = make_uint4(pack_f16(lo[8], lo[9]), 0u, 0u, 0u);
 }
 
 // dW[c][j], dgamma[c], dbeta[c] from the GEMM accumulators acc32[b][c][32] (layout of xcol's columns); same algebra

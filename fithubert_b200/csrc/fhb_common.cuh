@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -236,6 +237,23 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// ---------------------------------------------------------------- 16-bit storage formats
+// Every 16-bit tensor of the library is fp16: weights, activations, saved gelu' multipliers, attention probabilities,
+// projections, teacher targets - all bounded - and the gradients, which carry a power-of-two LOSS SCALE (applied by the
+// loss kernel, removed by the AdamW kernel) like the reference's own AMP recipe (data/conf/fithubert.yaml: use_fp16).
+// fp16's 11-bit significand is 8x finer than bf16's 8 bits at the same tensor-pipe rate and the same bytes.  (tcgen05
+// kind::f16 has separate format fields for A and B, but mixing fp16 with bf16 raises an illegal-instruction fault on
+// sm_100a, so one format has to serve forward AND backward.)  Conversions saturate instead of producing inf.
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool f16) { return f16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+__device__ __forceinline__ float2 unpack16(uint32_t u, bool f16) { return f16 ? unpack_f16(u) : unpack_bf16(u); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -353,11 +371,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;
   return d;
 }
-// UMMA instruction descriptor, kind::f16, bf16 x bf16 -> fp32.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+// UMMA instruction descriptor, kind::f16 -> fp32 accumulate.  a_bf16 / b_bf16: operand format (0 = fp16, 1 = bf16).
+__host__ __device__ constexpr uint32_t umma_idesc_16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                     uint32_t a_bf16, uint32_t b_bf16) {
   return (1u << 4)                 // D format fp32
-         | (1u << 7)               // A format bf16
-         | (1u << 10)              // B format bf16
+         | (a_bf16 << 7)           // A format: 0 fp16, 1 bf16
+         | (b_bf16 << 10)          // B format
          | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return umma_idesc_16(M, N, a_mn_major, b_mn_major, 1, 1);
 }
 #endif  // __CUDACC__

@@ -49,13 +49,13 @@ struct GemmParams {
   long long d_ld, d_hi_stride, d_lo_stride, bias_hi_stride;
   void* d;
   const float* bias;
-  const void* residual;  // bf16, or fp32 with FHB_EPI_RES_F32
-  const __nv_bfloat16* aux_in;
-  __nv_bfloat16* aux_out;
+  const void* residual;  // fp16, bf16 (FHB_EPI_RES_BF16) or fp32 (FHB_EPI_RES_F32)
+  const __half* aux_in;  // always fp16 (a forward-pass quantity: a saved gelu' or pre-activation)
+  void* aux_out;         // fp16 (with FHB_EPI_AUX_DGELU: always; else the type of D)
   const int* row_valid;
-  const __nv_bfloat16* loss_target;
+  const __half* loss_target;
   float* loss_acc;
-  float loss_weight, grad_scale;
+  float loss_weight, grad_scale, alpha;
   uint32_t drop_seed, drop_thr;
   float drop_scale;
   int flags;
@@ -190,7 +190,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const Tile t = decode_tile(p, tile);
         // the last n-block of a row may be narrower: issue only the columns that exist (multiple of 16)
         const int n_eff = min(p.bn, (p.n - t.n0 + 15) & ~15);
-        const uint32_t idesc = umma_idesc_bf16(kBM, (uint32_t)n_eff, A_MN, B_MN);
+        const uint32_t idesc = umma_idesc_16(kBM, (uint32_t)n_eff, A_MN, B_MN, (p.flags & FHB_GEMM_A_BF16) ? 1u : 0u,
+                                             (p.flags & FHB_GEMM_B_BF16) ? 1u : 0u);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);
@@ -220,6 +221,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // ------------------------------------------------------------ epilogue (warps 0-7)
     const int flags = p.flags;
     const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
+    const bool out_f16 = (flags & FHB_EPI_OUT_BF16) == 0;                            // 16-bit D: fp16 unless flagged bf16
+    const bool aux_f16 = out_f16 || (flags & FHB_EPI_AUX_DGELU) != 0;                 // a saved gelu' is always fp16
     const bool two_out = (flags & FHB_EPI_STORE_PREACT) != 0;
     const bool in_tma = EPI_IN && p.n_in > 0;
     // which [m][n] operand travels through the TMA input ring: aux_in if it is used, else the residual
@@ -290,6 +293,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       // fused epilogue math on 16 consecutive columns starting at tile column c.  `ring`: this thread's 16
       // values of the TMA-staged input operand (nullptr = read every [m][n] operand from global memory).
       auto math16 = [&](float* v, float* pre, int c, const uint32_t* ring) {
+        if (flags & FHB_EPI_ALPHA) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
+        }
         if (flags & FHB_EPI_BIAS) {
           const float4* bp = reinterpret_cast<const float4*>(bs + c);
 #pragma unroll
@@ -361,14 +368,14 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (flags & FHB_EPI_MUL_DGELU) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float2 f = unpack_bf16(uu[j]);
+                const float2 f = unpack_f16(uu[j]);
                 v[2 * j] *= gelu_erf_grad(f.x);
                 v[2 * j + 1] *= gelu_erf_grad(f.y);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float2 f = unpack_bf16(uu[j]);
+                const float2 f = unpack_f16(uu[j]);
                 v[2 * j] *= f.x;
                 v[2 * j + 1] *= f.y;
               }
@@ -397,7 +404,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) uu[j] = ring[j];
               } else if (col_ok) {
-                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + c);
+                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + off + c);
                 const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
                 uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w;
                 uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
@@ -405,9 +412,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) uu[j] = 0u;
               }
+              const bool res_f16 = (flags & FHB_EPI_RES_BF16) == 0;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float2 f = unpack_bf16(uu[j]);
+                const float2 f = unpack16(uu[j], res_f16);
                 v[2 * j] += f.x;
                 v[2 * j + 1] += f.y;
               }
@@ -419,7 +427,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack_bf16(uu[j]);
+              const float2 f = unpack_f16(uu[j]);
               const float d0 = v[2 * j] - f.x, d1 = v[2 * j + 1] - f.y;
               loss_local += d0 * d0 + d1 * d1;
               v[2 * j] = d0 * p.grad_scale;
@@ -484,12 +492,12 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 2; ++q) {  // 2 chunks of 8 bf16
               const uint32_t ch = (uint32_t)(half * 4 + gq * 2 + q);
-              st_shared_v4(drow + ((ch ^ rsw) << 4), pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+              st_shared_v4(drow + ((ch ^ rsw) << 4), pack16(v[8 * q], v[8 * q + 1], out_f16), pack16(v[8 * q + 2], v[8 * q + 3], out_f16),
+                           pack16(v[8 * q + 4], v[8 * q + 5], out_f16), pack16(v[8 * q + 6], v[8 * q + 7], out_f16));
               if (two_out)
-                st_shared_v4(arow + ((ch ^ rsw) << 4), pack_bf16(pre[8 * q], pre[8 * q + 1]),
-                             pack_bf16(pre[8 * q + 2], pre[8 * q + 3]), pack_bf16(pre[8 * q + 4], pre[8 * q + 5]),
-                             pack_bf16(pre[8 * q + 6], pre[8 * q + 7]));
+                st_shared_v4(arow + ((ch ^ rsw) << 4), pack16(pre[8 * q], pre[8 * q + 1], aux_f16),
+                             pack16(pre[8 * q + 2], pre[8 * q + 3], aux_f16), pack16(pre[8 * q + 4], pre[8 * q + 5], aux_f16),
+                             pack16(pre[8 * q + 6], pre[8 * q + 7], aux_f16));
             }
           }
         }
@@ -524,10 +532,11 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         math16(v, pre, c, nullptr);
         if (!row_ok || t.n0 + c >= p.n) continue;
         if (flags & FHB_EPI_STORE_PREACT) {
-          uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off + c);
-          ap[0] = make_uint4(pack_bf16(pre[0], pre[1]), pack_bf16(pre[2], pre[3]), pack_bf16(pre[4], pre[5]), pack_bf16(pre[6], pre[7]));
-          ap[1] = make_uint4(pack_bf16(pre[8], pre[9]), pack_bf16(pre[10], pre[11]), pack_bf16(pre[12], pre[13]),
-                             pack_bf16(pre[14], pre[15]));
+          uint4* ap = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.aux_out) + off + c);
+          ap[0] = make_uint4(pack16(pre[0], pre[1], aux_f16), pack16(pre[2], pre[3], aux_f16), pack16(pre[4], pre[5], aux_f16),
+                             pack16(pre[6], pre[7], aux_f16));
+          ap[1] = make_uint4(pack16(pre[8], pre[9], aux_f16), pack16(pre[10], pre[11], aux_f16), pack16(pre[12], pre[13], aux_f16),
+                             pack16(pre[14], pre[15], aux_f16));
         }
         if (out_f32) {
           float* dp = reinterpret_cast<float*>(p.d) + off + c;
@@ -540,10 +549,11 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         } else {
-          uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.d) + off + c);
-          dp[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          dp[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                             pack_bf16(v[14], v[15]));
+          uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.d) + off + c);
+          dp[0] = make_uint4(pack16(v[0], v[1], out_f16), pack16(v[2], v[3], out_f16), pack16(v[4], v[5], out_f16),
+                             pack16(v[6], v[7], out_f16));
+          dp[1] = make_uint4(pack16(v[8], v[9], out_f16), pack16(v[10], v[11], out_f16), pack16(v[12], v[13], out_f16),
+                             pack16(v[14], v[15], out_f16));
         }
       }
       tc_fence_before();
@@ -778,7 +788,11 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   const int flags = a->flags;
   FHB_ARG_CHECK(!(flags & FHB_EPI_BIAS) || a->bias, "gemm: FHB_EPI_BIAS without bias");
   FHB_ARG_CHECK(!(flags & FHB_EPI_RESIDUAL) || a->residual, "gemm: FHB_EPI_RESIDUAL without residual");
-  FHB_ARG_CHECK(!(flags & FHB_EPI_RES_F32) || (flags & FHB_EPI_RESIDUAL), "gemm: FHB_EPI_RES_F32 needs FHB_EPI_RESIDUAL");
+  FHB_ARG_CHECK(!(flags & (FHB_EPI_RES_F32 | FHB_EPI_RES_BF16)) || (flags & FHB_EPI_RESIDUAL), "gemm: FHB_EPI_RES_* needs FHB_EPI_RESIDUAL");
+  FHB_ARG_CHECK((flags & (FHB_EPI_RES_F32 | FHB_EPI_RES_BF16)) != (FHB_EPI_RES_F32 | FHB_EPI_RES_BF16), "gemm: one residual type");
+  FHB_ARG_CHECK((flags & (FHB_EPI_OUT_F32 | FHB_EPI_OUT_BF16)) != (FHB_EPI_OUT_F32 | FHB_EPI_OUT_BF16), "gemm: one output type");
+  FHB_ARG_CHECK(!(flags & FHB_GEMM_A_BF16) == !(flags & FHB_GEMM_B_BF16),
+                "gemm: A and B must share one 16-bit format (tcgen05 kind::f16 faults on fp16 x bf16)");
   FHB_ARG_CHECK(!(flags & FHB_EPI_STORE_PREACT) || !(flags & FHB_EPI_OUT_F32), "gemm: a second output needs a bf16 D");
   FHB_ARG_CHECK(!(flags & FHB_EPI_ROWZERO) || a->row_valid, "gemm: FHB_EPI_ROWZERO without row_valid");
   FHB_ARG_CHECK(!(flags & FHB_EPI_STORE_PREACT) || a->aux_out, "gemm: FHB_EPI_STORE_PREACT without aux_out");
@@ -828,13 +842,14 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.bias_hi_stride = a->bias_hi_stride;
   p.bias = a->bias;
   p.residual = a->residual;
-  p.aux_in = static_cast<const __nv_bfloat16*>(a->aux_in);
-  p.aux_out = static_cast<__nv_bfloat16*>(a->aux_out);
+  p.aux_in = static_cast<const __half*>(a->aux_in);
+  p.aux_out = a->aux_out;
   p.row_valid = a->row_valid;
-  p.loss_target = static_cast<const __nv_bfloat16*>(a->loss_target);
+  p.loss_target = static_cast<const __half*>(a->loss_target);
   p.loss_acc = a->loss_acc;
   p.loss_weight = a->loss_weight;
   p.grad_scale = a->grad_scale;
+  p.alpha = a->alpha;
   if (flags & FHB_EPI_DROPOUT) {
     FHB_ARG_CHECK(a->drop_p >= 0.f && a->drop_p < 1.f, "gemm: drop_p=%f must be in [0, 1)", (double)a->drop_p);
     FHB_ARG_CHECK((long long)num_ob * a->m * a->n < (1LL << 32) && a->n % 2 == 0, "gemm: dropout index space exceeds 32 bits");

@@ -8,14 +8,29 @@ namespace {
 
 constexpr int kMaxVec = 3;  // C <= 3*32*8 = 768
 
+// forward activations are fp16, gradients bf16 (fhb_common.cuh)
+__device__ __forceinline__ void load8h(const __half* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8h(__half* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7]));
+}
+__device__ __forceinline__ void cvt8h(const uint4& u, float* f) {
+  float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
-  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) =
-      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+      make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7]));
 }
 
 __device__ __forceinline__ void load8f(const float* p, float* f) {
@@ -34,9 +49,9 @@ __device__ __forceinline__ void store8f(float* p, const float* f) {
 template <bool IN_F32>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                     const float* __restrict__ beta, __half* __restrict__ y, float* __restrict__ y32,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ sub32,
-                     __nv_bfloat16* __restrict__ diff_out, long long rows, int C, float eps) {
+                     __half* __restrict__ diff_out, long long rows, int C, float eps) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -50,7 +65,7 @@ layernorm_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ gamm
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         if (IN_F32) load8f(static_cast<const float*>(x_) + row * C + vi * 8, v[i]);
-        else load8(static_cast<const __nv_bfloat16*>(x_) + row * C + vi * 8, v[i]);
+        else load8h(static_cast<const __half*>(x_) + row * C + vi * 8, v[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i][j];
       }
@@ -83,7 +98,7 @@ layernorm_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ gamm
           load8f(sub32 + row * C + vi * 8, r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = v[i][j] - r[j];
-          store8(diff_out + row * C + vi * 8, o);
+          store8h(diff_out + row * C + vi * 8, o);
         }
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)),
                      g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
@@ -93,7 +108,7 @@ layernorm_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ gamm
         const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
-        store8(y + row * C + vi * 8, o);
+        store8h(y + row * C + vi * 8, o);
         if (y32) store8f(y32 + row * C + vi * 8, o);
       }
     }
@@ -108,7 +123,7 @@ layernorm_fwd_kernel(const void* __restrict__ x_, const float* __restrict__ gamm
 // global atomic per column per block.  All 16-byte loads of a row are issued before the first use.
 // NV = 16-byte vectors per lane.
 __device__ __forceinline__ void cvt8(const uint4& u, float* f) {
-  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  float2 a = unpack_f16(u.x), b = unpack_f16(u.y), c = unpack_f16(u.z), d = unpack_f16(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
@@ -159,7 +174,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restri
         const int vi = lane + 32 * i;
         rx[i] = rd[i] = rd2[i] = rr[i] = zero4;
         if (vi < nvec) {
-          rx[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x_) + row * C + vi * 8);
+          rx[i] = *reinterpret_cast<const uint4*>(static_cast<const __half*>(x_) + row * C + vi * 8);
           rd[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(dy_) + row * C + vi * 8);
           if (dy2) rd2[i] = *reinterpret_cast<const uint4*>(dy2 + row * C + vi * 8);
           if (dres) rr[i] = *reinterpret_cast<const uint4*>(dres + row * C + vi * 8);
@@ -167,7 +182,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restri
       }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        cvt8(rx[i], xh[i]);
+        cvt8h(rx[i], xh[i]);  // the saved forward input: fp16
         cvt8(rd[i], dxh[i]);
       }
     }
@@ -267,11 +282,11 @@ int ln_fwd_launch(bool in_f32, const void* x, const float* gamma, const float* b
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (in_f32)
     FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel<true>, dim3(ln_grid(rows, 1)), dim3(256), 0, s, x, gamma, beta,
-                              static_cast<__nv_bfloat16*>(y), y32, mean, rstd, sub32, static_cast<__nv_bfloat16*>(diff_out),
+                              static_cast<__half*>(y), y32, mean, rstd, sub32, static_cast<__half*>(diff_out),
                               rows, C, eps));
   else
     FHB_CUDA_CHECK(fhb_launch(layernorm_fwd_kernel<false>, dim3(ln_grid(rows, 1)), dim3(256), 0, s, x, gamma, beta,
-                              static_cast<__nv_bfloat16*>(y), y32, mean, rstd, sub32, static_cast<__nv_bfloat16*>(diff_out),
+                              static_cast<__half*>(y), y32, mean, rstd, sub32, static_cast<__half*>(diff_out),
                               rows, C, eps));
   FHB_LAUNCH_CHECK();
   return 0;

@@ -43,7 +43,7 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
     uint32_t out[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 p = unpack_bf16(pa[j]), q = unpack_bf16(ta[j]);
+      const float2 p = unpack_f16(pa[j]), q = unpack_f16(ta[j]);  // forward tensors: fp16; the gradient below: bf16
       const float d0 = p.x - q.x, d1 = p.y - q.y;
       float g0, g1;
       if (loss_type == 0) {
@@ -55,8 +55,8 @@ distill_loss_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloat16*
         g0 = d0 > 0.f ? gs : (d0 < 0.f ? -gs : 0.f);
         g1 = d1 > 0.f ? gs : (d1 < 0.f ? -gs : 0.f);
       }
-      out[j] = pack_bf16(g0, g1);
-      const float2 gr = unpack_bf16(out[j]);  // sum what the downstream GEMMs will read
+      out[j] = pack_f16(g0, g1);
+      const float2 gr = unpack_f16(out[j]);  // sum what the downstream GEMMs will read
       cs[2 * j] += gr.x;
       cs[2 * j + 1] += gr.y;
     }
@@ -136,7 +136,7 @@ distill_loss_sim_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloa
       const uint32_t pa[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w}, qa[4] = {qu[i].x, qu[i].y, qu[i].z, qu[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16(pa[j]), c = unpack_bf16(qa[j]);
+        const float2 a = unpack_f16(pa[j]), c = unpack_f16(qa[j]);
         p[i][2 * j] = a.x; p[i][2 * j + 1] = a.y;
         q[i][2 * j] = c.x; q[i][2 * j + 1] = c.y;
       }
@@ -178,8 +178,8 @@ distill_loss_sim_kernel(const __nv_bfloat16* __restrict__ pred, const __nv_bfloa
             const float grec = loss_type == 0 ? gr * d : (d > 0.f ? gr : (d < 0.f ? -gr : 0.f));
             g2[e] = grec + k_q * qv + k_p * pv;
           }
-          o[j] = pack_bf16(g2[0], g2[1]);
-          const float2 gb = unpack_bf16(o[j]);  // sum what the downstream GEMMs will read
+          o[j] = pack_f16(g2[0], g2[1]);
+          const float2 gb = unpack_f16(o[j]);  // sum what the downstream GEMMs will read
           cs[i][2 * j] += gb.x;
           cs[i][2 * j + 1] += gb.y;
         }
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* 
     uint2* d2p = reinterpret_cast<uint2*>(e.dst);
     for (long long i = i0; i < (n >> 2); i += step) {
       const float4 v = __ldg(s4 + i);
-      d2p[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      d2p[i] = make_uint2(pack_f16(v.x, v.y), pack_f16(v.z, v.w));
     }
     return;
   }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const fhb_prep_tensor* 
     if (e.dst_is_f32)
       static_cast<float*>(e.dst)[i] = e.accumulate ? static_cast<float*>(e.dst)[i] + v : v;
     else
-      static_cast<__nv_bfloat16*>(e.dst)[i] = __float2bfloat16(v);
+      static_cast<__half*>(e.dst)[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
   }
 }
 
@@ -313,7 +313,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, long l
       const uint32_t a[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(a[j]);
+        const float2 f = unpack_f16(a[j]);
         acc[2 * j] += f.x;
         acc[2 * j + 1] += f.y;
       }
@@ -357,7 +357,7 @@ head_bias_grads_kernel(const float* __restrict__ cs, long long cs_stride, const 
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll 16
   for (int d = 0; d < nd; ++d) {
-    const float2 f = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(w + (long long)d * E)));
+    const float2 f = unpack_f16(__ldg(reinterpret_cast<const uint32_t*>(w + (long long)d * E)));
     a0 = fmaf(cs_s[d], f.x, a0);
     a1 = fmaf(cs_s[d], f.y, a1);
   }
@@ -376,8 +376,8 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(bb[j]);
-      o[j] = pack_bf16(p.x + q.x, p.y + q.y);
+      const float2 p = unpack_f16(aa[j]), q = unpack_f16(bb[j]);
+      o[j] = pack_f16(p.x + q.x, p.y + q.y);
     }
     reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -398,8 +398,8 @@ mul_dgelu_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, const __
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(cc[j]);
-      o[j] = pack_bf16(p.x * gelu_erf_grad(q.x), p.y * gelu_erf_grad(q.y));
+      const float2 p = unpack_f16(aa[j]), q = unpack_f16(cc[j]);
+      o[j] = pack_f16(p.x * gelu_erf_grad(q.x), p.y * gelu_erf_grad(q.y));
     }
     o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -420,16 +420,16 @@ mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long a_bs, const __nv_
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 p = unpack_bf16(aa[j]), q = unpack_bf16(cc[j]);
-      o[j] = pack_bf16(alpha * p.x * q.x, alpha * p.y * q.y);
+      const float2 p = unpack_f16(aa[j]), q = unpack_f16(cc[j]);  // gradient (bf16) x saved gelu' (fp16)
+      o[j] = pack_f16(alpha * p.x * q.x, alpha * p.y * q.y);
     }
     o4[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 __global__ void __launch_bounds__(256)
-dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long nvec, uint32_t seed,
-               uint32_t thr, float scale) {
+dropout_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, long long nvec, uint32_t seed,
+               uint32_t thr, float scale, bool f16) {
   pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 a = reinterpret_cast<const uint4*>(x)[i];
@@ -439,8 +439,8 @@ dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
     for (int j = 0; j < 4; ++j) {
       float m0, m1;
       dropout_pair(seed, (uint32_t)(i * 4 + j), thr, scale, m0, m1);
-      const float2 p = unpack_bf16(aa[j]);
-      o[j] = pack_bf16(p.x * m0, p.y * m1);
+      const float2 p = unpack16(aa[j], f16);
+      o[j] = pack16(p.x * m0, p.y * m1, f16);
     }
     reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -626,14 +626,15 @@ extern "C" int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int
   return 0;
 }
 
-extern "C" int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, float p, fhb_stream_t stream) {
+extern "C" int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, float p, int32_t is_f16,
+                           fhb_stream_t stream) {
   FHB_ARG_CHECK(x && y && n % 8 == 0 && n < (1LL << 32), "dropout: n must be a multiple of 8 and < 2^32");
   FHB_ARG_CHECK(p >= 0.f && p < 1.f, "dropout: p=%f must be in [0, 1)", (double)p);
   if (n == 0) return 0;
   fhb_pdl_hint(n <= 16LL << 20);
   FHB_CUDA_CHECK(fhb_launch(dropout_kernel, dim3(grid_x(n / 8, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n / 8, seed, fhb_dropout_thr16(p),
-      fhb_dropout_scale(p)));
+      static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), n / 8, seed, fhb_dropout_thr16(p),
+      fhb_dropout_scale(p), is_f16 != 0));
   FHB_LAUNCH_CHECK();
   return 0;
 }

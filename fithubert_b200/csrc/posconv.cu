@@ -14,12 +14,12 @@ __device__ __forceinline__ void ldv(const __nv_bfloat16* p, float* f) {
     const uint32_t a[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 t = unpack_bf16(a[j]);
+      const float2 t = unpack_f16(a[j]);
       f[2 * j] = t.x;
       f[2 * j + 1] = t.y;
     }
   } else {
-    const float2 t = unpack_bf16(*reinterpret_cast<const uint32_t*>(p));
+    const float2 t = unpack_f16(*reinterpret_cast<const uint32_t*>(p));
     f[0] = t.x;
     f[1] = t.y;
   }
@@ -28,9 +28,19 @@ template <int VEC>
 __device__ __forceinline__ void stv(__nv_bfloat16* p, const float* f) {
   if constexpr (VEC == 8) {
     *reinterpret_cast<uint4*>(p) =
-        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7]));
   } else {
-    *reinterpret_cast<uint32_t*>(p) = pack_bf16(f[0], f[1]);
+    *reinterpret_cast<uint32_t*>(p) = pack_f16(f[0], f[1]);
+  }
+}
+// fp16 twins (forward activations are fp16, gradients bf16: fhb_common.cuh)
+template <int VEC>
+__device__ __forceinline__ void stvh(__nv_bfloat16* p, const float* f) {
+  if constexpr (VEC == 8) {
+    *reinterpret_cast<uint4*>(p) =
+        make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7]));
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = pack_f16(f[0], f[1]);
   }
 }
 template <int VEC>
@@ -64,7 +74,17 @@ template <int VEC>
 __device__ __forceinline__ void cvtraw(const RawVec<VEC>& r, float* f) {
 #pragma unroll
   for (int j = 0; j < VEC / 2; ++j) {
-    const float2 t = unpack_bf16(r.w[j]);
+    const float2 t = unpack_f16(r.w[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void cvtrawh(const RawVec<VEC>& r, float* f) {
+#pragma unroll
+  for (int j = 0; j < VEC / 2; ++j) {
+    const float2 t = unpack_f16(r.w[j]);
     f[2 * j] = t.x;
     f[2 * j + 1] = t.y;
   }
@@ -171,7 +191,7 @@ posconv_wn_layout_kernel(const float* __restrict__ v, const float* __restrict__ 
   const int half = cg >> 1;  // cg is even (host check): consecutive threads write consecutive bf16 pairs of one tap row
   for (int i = threadIdx.x; i < K * half; i += blockDim.x) {
     const int j = i / half, kk = (i - j * half) * 2;
-    const uint32_t pk = pack_bf16(sc[j] * tile[kk * (K + 1) + j], sc[j] * tile[(kk + 1) * (K + 1) + j]);
+    const uint32_t pk = pack_f16(sc[j] * tile[kk * (K + 1) + j], sc[j] * tile[(kk + 1) * (K + 1) + j]);
     const int jj = flip ? K - 1 - j : j;
     for (int dl = 0; dl < delta; ++dl)
       *reinterpret_cast<uint32_t*>(w_out + ((long long)((g * delta + dl) * cp + r) * Kx + jj + dl) * cp + kk) = pk;
@@ -227,8 +247,8 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
       if (coff[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
         float xv[VEC], cv[VEC], bv[VEC];
-        cvtraw<VEC>(rx[i], xv);
-        cvtraw<VEC>(rc[i], cv);
+        cvtrawh<VEC>(rx[i], xv);
+        cvtrawh<VEC>(rc[i], cv);
         ldf<VEC>(bias + c, bv);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -258,13 +278,13 @@ posconv_finish_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __rest
     for (int i = 0; i < NV; ++i) {
       if (coff[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
-        if (h_out) stv<VEC>(h_out + row * C + c, hv[i]);
+        if (h_out) stvh<VEC>(h_out + row * C + c, hv[i]);
         float gv[VEC], bv[VEC], o[VEC];
         ldf<VEC>(gamma + c, gv);
         ldf<VEC>(beta + c, bv);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) o[j] = (hv[i][j] - mu) * rs * gv[j] + bv[j];
-        stv<VEC>(y + row * C + c, o);
+        stvh<VEC>(y + row * C + c, o);
         if (y32) {  // fp32 copy: the residual operand of the first transformer layer's out_proj epilogue
 #pragma unroll
           for (int j = 0; j < VEC; j += 2) *reinterpret_cast<float2*>(y32 + row * C + c + j) = make_float2(o[j], o[j + 1]);
@@ -329,7 +349,7 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
       if (gcc[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
         float gv[VEC];
-        cvtraw<VEC>(rh[i], xh[i]);
+        cvtrawh<VEC>(rh[i], xh[i]);  // saved forward sum h: fp16
         cvtraw<VEC>(rd[i], dv[i]);
         ldf<VEC>(gamma + c, gv);
 #pragma unroll
@@ -350,7 +370,7 @@ posconv_finish_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
       if (gcc[i] >= 0) {
         const int c = (lane + 32 * i) * VEC;
         float cv[VEC], bv[VEC], d[VEC], dc[VEC];
-        cvtraw<VEC>(rc[i], cv);
+        cvtrawh<VEC>(rc[i], cv);  // forward conv output: fp16
         ldf<VEC>(bias + c, bv);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {

@@ -22,7 +22,7 @@ from .config import CustomStudentModelConfig
 from .model import CustomStudentModel, TeacherModel, TeacherWrapper, conv_out_lengths, freeze_model, _lengths_from_mask
 from .optim import FusedAdamW, GradAllReduce
 
-bf16 = torch.bfloat16
+f16 = torch.float16
 
 
 def load_model_and_config(teacher_model: str, device=None):
@@ -126,6 +126,7 @@ class W2V2Distil(nn.Module):
         self.reducer: Optional[GradAllReduce] = None
         self._micro = 0
         self._tgt_buf = None
+        self._loss_scale: Optional[float] = None
 
     # ------------------------------------------------------------------ reference-style API (autograd)
     def forward(self, x, padding_mask=None):
@@ -152,12 +153,13 @@ class W2V2Distil(nn.Module):
                     base._base.shape[0] == len(student_results["projections"]):
                 preds = base._base  # the engine's stacked [n, B, T', D] buffer: no copy
         lt = 0 if self.rec_loss_type == "mse" else 1
+        S = self.loss_scale(preds.shape[1] * preds.shape[2] * preds.shape[3])
         if self.sim_loss_weight:
             total, rec, sim = _DistillLossFn.apply(preds, tgt, self.layer_weights, lt,
-                                                   float(self.rec_loss_weight), float(self.sim_loss_weight))
+                                                   float(self.rec_loss_weight), float(self.sim_loss_weight), S)
             per_layer = rec + sim  # train.py:316 feat_loss = rec_layer_loss + sim_layer_loss (un-weighted sum)
         else:
-            total, per_layer = _DistillLossFn.apply(preds, tgt, self.layer_weights, lt, float(self.rec_loss_weight))
+            total, per_layer = _DistillLossFn.apply(preds, tgt, self.layer_weights, lt, float(self.rec_loss_weight), 0.0, S)
         losses = self._loss_dict(per_layer)
         return total, losses
 
@@ -175,6 +177,21 @@ class W2V2Distil(nn.Module):
         return losses
 
     # ------------------------------------------------------------------ fused training path
+    def loss_scale(self, n_elems: int) -> float:
+        """The loss scale of this module (train_cfg['loss_scale'] if given, else engine.loss_scale_for of the first
+        training batch, the minimum over the ranks): constant afterwards, so that accumulated micro-batches and the
+        ranks of a data-parallel job all add gradients of ONE scale into the flat buffer."""
+        if self._loss_scale is None:
+            S = float(self.train_cfg.get("loss_scale", 0) or E.loss_scale_for(n_elems))
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                t = torch.tensor([S], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                S = float(t[0])
+            self._loss_scale = S
+            self.student_model._loss_scale = S
+        return self._loss_scale
+
     def configure_optimizers(self, total_steps: int = 0):
         o = self.yaml_cfg["optimizer"]
         lr = float(o["lr"]) if not isinstance(o["lr"], str) else float(eval(o["lr"], {"__builtins__": {}}))
@@ -230,7 +247,7 @@ class W2V2Distil(nn.Module):
         n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
         Pt, Wt = tm.engine_state()
         if self._tgt_buf is None or self._tgt_buf.shape[1:3] != (B, T):
-            self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=bf16)
+            self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=f16)
         P, W, G = sm.engine_state(True)
         if E.stream_mode() & 1:
             # the frozen teacher's forward and the student's forward only meet in the loss: run them on two streams so
@@ -249,7 +266,11 @@ class W2V2Distil(nn.Module):
             c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
                                   wave_chunks=chunks)
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
-        # gradient written in place over the projections (they are not needed again)
+        # gradient written in place over the projections (they are not needed again).  fp16 gradients carry the loss
+        # scale: fixed at the first training batch (and agreed on by all ranks), removed by the AdamW kernel
+        dpred = c.preds
+        S = self.loss_scale(B * c.Tq * D)
+        grad_scale = grad_scale * S
         # the loss kernel also produces the column sums of the gradient it writes: both head bias gradients follow
         # (batched heads only; the per-head fallback path computes its own column sums)
         fused = getattr(c, "heads_batched", False) and G.head_stride() is not None
@@ -259,12 +280,12 @@ class W2V2Distil(nn.Module):
         lt = 0 if self.rec_loss_type == "mse" else 1
         if self.sim_loss_weight:
             sim_loss = torch.zeros(n, device=dev, dtype=torch.float32)
-            K.distill_loss_sim(c.preds, tgt, self.layer_weights, layer_loss, sim_loss, c.preds, n, B, c.Tq, T, D, lt,
+            K.distill_loss_sim(c.preds, tgt, self.layer_weights, layer_loss, sim_loss, dpred, n, B, c.Tq, T, D, lt,
                                grad_scale * self.rec_loss_weight, grad_scale * self.sim_loss_weight,
                                dbias=dcs, dbias_layer_stride=D if fused else 0)
             layer_loss = layer_loss * self.rec_loss_weight + sim_loss * self.sim_loss_weight
         else:
-            K.distill_loss(c.preds, tgt, self.layer_weights, layer_loss, c.preds, n, B, c.Tq, T, D, lt,
+            K.distill_loss(c.preds, tgt, self.layer_weights, layer_loss, dpred, n, B, c.Tq, T, D, lt,
                            grad_scale * self.rec_loss_weight, dbias=dcs, dbias_layer_stride=D if fused else 0)
             if self.rec_loss_weight != 1.0:
                 layer_loss = layer_loss * self.rec_loss_weight
@@ -273,7 +294,8 @@ class W2V2Distil(nn.Module):
                 os.environ.get("FHB_EARLY_REDUCE", "0") == "1" and not self.split_head:
             first = G.entries[f"encoder.layers.{1 if sm._geom.tr else 0}.self_attn.q_proj.weight"][0]
             hook = lambda: self.reducer.reduce_tail(G.flat, first)  # noqa: E731
-        E.student_backward(P, W, sm._geom, G, c, c.preds, dpred_colsum=dcs, on_layers_done=hook)
+        E.student_backward(P, W, sm._geom, G, c, dpred, dpred_colsum=dcs, on_layers_done=hook)
+        G.loss_scale = S
         return layer_loss
 
     def training_step(self, batch, batch_idx=0):
@@ -352,4 +374,4 @@ class W2V2Distil(nn.Module):
         _, _, G = self.student_model.engine_state(True)
         self.reducer.reduce_all(G.flat)
         self.reducer.wait()
-        self.optimizer.step(grad_scale=1.0 / self.reducer.world)
+        self.optimizer.step(grad_scale=1.0 / (self.reducer.world * (self._loss_scale or 1.0)))

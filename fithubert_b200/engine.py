@@ -2,9 +2,9 @@
 into the teacher forward, the student forward and the student backward.
 
 Layout decisions:
-  * activations bf16 channel-last [B, T, C]; every contraction is a tcgen05 GEMM over a (possibly
+  * every 16-bit tensor is fp16 (gradients carry a power-of-two loss scale, include/fhb.h), channel-last [B, T, C]; every contraction is a tcgen05 GEMM over a (possibly
     overlapping-row) strided view - no im2col, no permute copies;
-  * fp32 master parameters live in the nn.Module; bf16 GEMM-layout shadows are re-derived by ONE
+  * fp32 master parameters live in the nn.Module; fp16 GEMM-layout shadows are re-derived by ONE
     multi-tensor kernel whenever the parameters change;
   * parameter gradients accumulate in ONE flat fp32 buffer, in the layout the wgrad GEMM produces
     (the fused AdamW kernel reads them through a 3-D stride; the buffer is what NCCL all-reduces).
@@ -21,7 +21,16 @@ import torch
 from . import kernels as K
 from . import lib as L
 
-bf16 = torch.bfloat16
+f16 = torch.float16    # every 16-bit tensor: weights, activations, saved gelu', projections, targets and gradients
+bf16 = f16             # (old name, kept as an alias in the backward code: gradients are fp16 WITH a loss scale)
+
+
+def loss_scale_for(n_elems: int) -> float:
+    """Power-of-two loss scale for fp16 gradients (the reference trains under fp16 AMP with a GradScaler,
+    data/conf/fithubert.yaml: use_fp16).  d(loss)/d(pred) = 2 w (pred - tgt) / n_elems per element; 2^(ceil(log2 n) + 2)
+    puts it at 8 ... 16 x w x (pred - tgt): three decades above fp16's normal minimum, three below its maximum.  The
+    scale is applied by the loss kernel and removed by the AdamW kernel (or on export to .grad); conversions saturate."""
+    return float(2.0 ** min(24, max(0, math.ceil(math.log2(max(1, n_elems))) + 2)))
 f32 = torch.float32
 
 
@@ -93,7 +102,7 @@ class Geometry:
 
 
 # =============================================================================================
-# bf16 / fp32 shadows of the master parameters
+# fp16 / fp32 shadows of the master parameters
 # =============================================================================================
 class WeightSet:
     """GEMM-layout shadows for one model on one device."""
@@ -119,24 +128,24 @@ class WeightSet:
             if i == 0:
                 continue
             pn = f"feature_extractor.conv_layers.{i}.0.weight"
-            add(f"conv{i}.w", bf16, (c, k, cin), [(pn, 0, (cin * k, 1, k), 0)])
+            add(f"conv{i}.w", f16, (c, k, cin), [(pn, 0, (cin * k, 1, k), 0)])
             if self.train and (k, s) == (3, 2):
-                add(f"conv{i}.wd_even", bf16, (cin, 2, c), [(pn, 2, (k, -2, cin * k), 0)])
-                add(f"conv{i}.wd_odd", bf16, (cin, 1, c), [(pn, 1, (k, 0, cin * k), 0)])
+                add(f"conv{i}.wd_even", f16, (cin, 2, c), [(pn, 2, (k, -2, cin * k), 0)])
+                add(f"conv{i}.wd_odd", f16, (cin, 1, c), [(pn, 1, (k, 0, cin * k), 0)])
             cin = c
         E, F = g.E, g.F
 
         def lin(name, pn, n, kd):
-            add(name, bf16, (n, 1, kd), [(pn, 0, (kd, 0, 1), 0)])
+            add(name, f16, (n, 1, kd), [(pn, 0, (kd, 0, 1), 0)])
 
         lin("pp.w", "post_extract_proj.weight", E, g.c_feat)
         off = 0
         if g.tr:
-            add("tr.w", bf16, (E, 2, E), [("encoder.layers.0.weight", 0, (2 * E, 1, 2), 0)])
+            add("tr.w", f16, (E, 2, E), [("encoder.layers.0.weight", 0, (2 * E, 1, 2), 0)])
             off = 1
         for l in range(g.n_layers):
             p = f"encoder.layers.{l + off}."
-            add(f"l{l}.wqkv", bf16, (3 * E, 1, E),
+            add(f"l{l}.wqkv", f16, (3 * E, 1, E),
                 [(p + f"self_attn.{nm}_proj.weight", 0, (E, 0, 1), j * E * E) for j, nm in enumerate("qkv")])
             add(f"l{l}.bqkv", f32, (3 * E, 1, 1),
                 [(p + f"self_attn.{nm}_proj.bias", 0, (1, 0, 0), j * E) for j, nm in enumerate("qkv")])
@@ -147,7 +156,7 @@ class WeightSet:
             # DistilHuBERT head (modules/module.py:585-619): Linear(E, N * inter) and the SplitLinear weight
             # [N][inter][D] transposed per task to the K-major [D][inter] the forward GEMM consumes
             lin("sp.w1", "proj_head.0.weight", g.n_split * g.inter, E)
-            add("sp.w2", bf16, (g.n_split, g.d_out, g.inter), [("proj_head.2.weight", 0, (g.inter * g.d_out, 1, g.d_out), 0)])
+            add("sp.w2", f16, (g.n_split, g.d_out, g.inter), [("proj_head.2.weight", 0, (g.inter * g.d_out, 1, g.d_out), 0)])
         elif g.student:
             for i in range(g.n_layers):
                 p = f"proj_head.{i}."
@@ -156,21 +165,21 @@ class WeightSet:
                         p = "final_proj."
                     else:
                         continue
-                add(f"h{i}.wup", bf16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
+                add(f"h{i}.wup", f16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
                 add(f"h{i}.bup", f32, (2, E, 1), [(p + "upsampler.bias", 0, (0, 1, 0), 0)])
-                add(f"h{i}.bup16", bf16, (E, 1, 1), [(p + "upsampler.bias", 0, (1, 0, 0), 0)])  # A operand of the bias fold
+                add(f"h{i}.bup16", f16, (E, 1, 1), [(p + "upsampler.bias", 0, (1, 0, 0), 0)])  # A operand of the bias fold
                 lin(f"h{i}.wlin", p + "lin_proj.weight", g.d_out, E)
                 add(f"h{i}.blin", f32, (g.d_out, 1, 1), [(p + "lin_proj.bias", 0, (1, 0, 0), 0)])
         self.spec = spec
-        nb = sum(math.prod(d) for (_, t, d, _) in spec if t == bf16)
+        nb = sum(math.prod(d) for (_, t, d, _) in spec if t == f16)
         nf = sum(math.prod(d) for (_, t, d, _) in spec if t == f32)
         pc = g.G * g.pdelta * g.cp * g.kpx * g.cp
-        self.buf16 = torch.empty(round_up(nb, 64) + 64 * len(spec) + 2 * round_up(pc, 64) + 128, device=self.device, dtype=bf16)
+        self.buf16 = torch.empty(round_up(nb, 64) + 64 * len(spec) + 2 * round_up(pc, 64) + 128, device=self.device, dtype=f16)
         self.buf32 = torch.empty(nf + 8 * len(spec) + 2 * g.kpos + 64, device=self.device, dtype=f32)
         o16 = o32 = 0
         for (name, t, dims, _) in spec:
             n = math.prod(dims)
-            if t == bf16:
+            if t == f16:
                 self.views[name] = self.buf16[o16:o16 + n]
                 o16 += round_up(n, 64)  # keep every shadow 128-byte aligned (TMA base alignment)
             else:
@@ -313,6 +322,7 @@ class GradStore:
             self.entries[pn] = (off, n, dims, gs)
             off += round_up(n, 4)  # 16-byte alignment for vector / TMA-free fp32 stores
         self.numel = off
+        self.loss_scale = 1.0  # scale of the gradients currently in the buffer (set by the fused step)
         self.flat = torch.zeros(off, device=self.device, dtype=f32)
         self.no_grad = [pn for pn in params if pn not in self.entries]  # the dead `upsampler.*`
 
@@ -327,6 +337,7 @@ class GradStore:
 
     def zero_(self):
         K.zero_(self.flat)
+        self.loss_scale = 1.0
 
     def head_stride(self) -> Optional[int]:
         """Float stride between consecutive projection heads' gradient blocks, if uniform."""
@@ -347,8 +358,11 @@ class GradStore:
         """Flat view from the start of `pn` to the end of the buffer (base pointer of a strided batch)."""
         return self.flat[self.entries[pn][0]:]
 
-    def export(self, accumulate=False) -> Dict[str, torch.Tensor]:
-        """Gradients in PARAMETER layout (what autograd would have produced)."""
+    def export(self, accumulate=False, scale: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """Gradients in PARAMETER layout (what autograd would have produced); `scale`: the loss scale the backward ran
+        with (default: the one the fused step recorded in .loss_scale); the exported gradients are divided by it."""
+        scale = self.loss_scale if scale is None else scale
+        assert not (accumulate and scale != 1.0)
         out = {}
         entries = []
         mx = 1
@@ -366,6 +380,8 @@ class GradStore:
         table = L.table_to_device(entries, self.device)
         K.prep_multi(table, len(entries), mx)
         self._keepalive = table
+        if scale != 1.0:
+            torch._foreach_mul_(list(out.values()), 1.0 / scale)
         return out
 
 
@@ -394,16 +410,16 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool,
     c.stat = torch.empty(B, 65, device=dev, dtype=torch.float64)
     c.mean0 = torch.empty(B, C0, device=dev, dtype=f32)
     c.rstd0 = torch.empty(B, C0, device=dev, dtype=f32)
-    y = torch.empty(B, T0, C0, device=dev, dtype=bf16)
-    gp0 = torch.empty(B, T0, C0, device=dev, dtype=bf16) if save else None
+    y = torch.empty(B, T0, C0, device=dev, dtype=f16)
+    gp0 = torch.empty(B, T0, C0, device=dev, dtype=f16) if save else None
     c.y = [y]
     c.u = [gp0]  # per layer: gelu'(pre-activation), saved by the forward epilogue (the backward multiplier)
     for i, (co, k, s) in enumerate(g.conv_layers):
         if i == 0:
             continue
         rows = frames[i] + 2 * halos[i]
-        c.y.append(torch.empty(B, rows, co, device=dev, dtype=bf16))
-        c.u.append(torch.empty(B, rows, co, device=dev, dtype=bf16) if save else None)
+        c.y.append(torch.empty(B, rows, co, device=dev, dtype=f16))
+        c.u.append(torch.empty(B, rows, co, device=dev, dtype=f16) if save else None)
     # Nothing in the extractor couples samples (GroupNorm statistics are per sample and channel), so when the waveform is
     # still arriving from the host in batch slices (wave_chunks = [(first, last, event)], see h2d_chunked) the WHOLE
     # stack runs slice by slice, each as soon as its copy has landed: the rest of the transfer hides under it.
@@ -423,9 +439,9 @@ def conv_stack_fwd(P, W: WeightSet, g: Geometry, wave: torch.Tensor, save: bool,
             halo = halos[i]
             rows = To + 2 * halo
             yb, ub = c.y[i], c.u[i]
-            a3 = L.tensor3(data_ptr=x_buf.data_ptr() + 2 * (b0 * x_rows + x_row0) * cin, dim=(k * cin, To, nb),
+            a3 = L.tensor3(x_buf, data_ptr=x_buf.data_ptr() + 2 * (b0 * x_rows + x_row0) * cin, dim=(k * cin, To, nb),
                            stride=(s * cin, x_rows * cin))
-            b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
+            b3 = L.tensor3(W[f"conv{i}.w"], data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
             K.gemm_raw(a3, b3, yb, To, co, k * cin, num_ob=nb, a_coord=(0, 1, 0, 0), d_ld=co, d_hi_stride=rows * co,
                        d_offset_elems=(b0 * rows + halo) * co,
                        flags=L.EPI_GELU | ((L.EPI_STORE_PREACT | L.EPI_AUX_DGELU) if save else 0), aux_out=ub)
@@ -450,7 +466,7 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
     c.valid, c.valid_t = valid, valid_t
     E, Cf = g.E, g.c_feat
     feat = c.out
-    f_ln = torch.empty(B, T, Cf, device=dev, dtype=bf16)
+    f_ln = torch.empty(B, T, Cf, device=dev, dtype=f16)
     c.mean_f = torch.empty(B * T, device=dev, dtype=f32) if save else None
     c.rstd_f = torch.empty(B * T, device=dev, dtype=f32) if save else None
     K.layernorm_fwd(feat, P["layer_norm.weight"], P["layer_norm.bias"], f_ln, c.mean_f, c.rstd_f)
@@ -464,21 +480,21 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
     G, cp, kp, dl = g.G, g.cp, g.kpos, g.pdelta
     R = (T + dl - 1) // dl                   # GEMM rows per (sample, group): one row = dl consecutive frames
     Tp = dl * R + g.kpx                      # padded time extent every overlapped row window stays inside
-    xg = torch.empty(B * G, Tp, cp, device=dev, dtype=bf16)
+    xg = torch.empty(B * G, Tp, cp, device=dev, dtype=f16)
     K.posconv_pack(feats, valid_t, xg, B, T, E, G, cp, kp // 2, Tp)
-    conv = torch.empty(B * R, G * dl * cp, device=dev, dtype=bf16)  # [b][r][g][dl][cp]
-    a3 = L.tensor3(data_ptr=xg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
-    b3 = L.tensor3(data_ptr=W["pc.w"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))
+    conv = torch.empty(B * R, G * dl * cp, device=dev, dtype=f16)  # [b][r][g][dl][cp]
+    a3 = L.tensor3(xg, data_ptr=xg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    b3 = L.tensor3(W["pc.w"], data_ptr=W["pc.w"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))
     K.gemm_raw(a3, b3, conv, R, dl * cp, g.kpx * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
                d_ld=G * dl * cp, d_hi_stride=R * G * dl * cp, d_lo_stride=dl * cp)
     c.xg, c.conv = (xg, conv) if save else (None, conv)
-    enc = torch.empty(B * T, E, device=dev, dtype=bf16)
-    c.h = torch.empty(B * T, E, device=dev, dtype=bf16) if save else None
+    enc = torch.empty(B * T, E, device=dev, dtype=f16)
+    c.h = torch.empty(B * T, E, device=dev, dtype=f16) if save else None
     c.mean_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
     c.rstd_e = torch.empty(B * T, device=dev, dtype=f32) if save else None
     d_pro = drop.site(DropCfg.SITE_PROLOGUE, drop.p_drop) if drop is not None else None
     # fp32 copy of the encoder input: the residual operand of layer 0 when no GEMM sits in between (no TR layer) and no
-    # dropout follows (the dropped tensor is bf16 anyway)
+    # dropout follows (the dropped tensor is fp16 anyway)
     c.enc_in32 = torch.empty(B * T, E, device=dev, dtype=f32) if (want_enc32 and d_pro is None) else None
     K.posconv_finish_fwd(feats, valid_t, conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"],
                          P["encoder.layer_norm.bias"], c.h, enc, c.mean_e, c.rstd_e, B, T, E, G, cp, delta=dl,
@@ -494,9 +510,9 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
               out: Optional[torch.Tensor] = None, drop: Optional[DropCfg] = None, x32: Optional[torch.Tensor] = None,
               out32: Optional[torch.Tensor] = None):
     """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E].
-    The residual stream never passes through bf16: x32 is the fp32 copy of x (None for the first layer, whose input is
-    the bf16 output of a GEMM / LayerNorm anyway), the out_proj / fc2 epilogues add it in fp32 and write the sums y1 / y2
-    in fp32, the LayerNorms read those and emit the bf16 GEMM operand together with the next fp32 copy (out32)."""
+    The residual stream never passes through 16 bits: x32 is the fp32 copy of x (None for the first layer, whose input is
+    the fp16 output of a GEMM anyway), the out_proj / fc2 epilogues add it in fp32 and write the sums y1 / y2 in fp32, the
+    LayerNorms read those and emit the fp16 GEMM operand together with the next fp32 copy (out32)."""
     E, F, H, d = g.E, g.F, g.H, g.d
     dev = x.device
     s = SimpleNamespace(x=x)
@@ -504,30 +520,30 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
     qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
     # training with F == E: the inputs of out_proj / fc1 / fc2 (attn, x1, h) share one [3, M, E] buffer so that their three
     # weight-gradient GEMMs run as one batched launch in the backward (wgrad_batch_enabled)
-    xs = torch.empty(3, M, E, device=dev, dtype=bf16) if (save and F == E and wgrad_batch_enabled()) else None
-    attn = xs[0] if xs is not None else torch.empty(M, E, device=dev, dtype=bf16)
+    xs = torch.empty(3, M, E, device=dev, dtype=f16) if (save and F == E and wgrad_batch_enabled()) else None
+    attn = xs[0] if xs is not None else torch.empty(M, E, device=dev, dtype=f16)
     lse = torch.empty(B, H, T, device=dev, dtype=f32) if save else None
     dl = (lambda which: drop.layer(l, which)) if drop is not None else (lambda which: None)
     K.attn_fwd(qkv, valid_t, attn, lse, B, T, H, d, d ** -0.5, drop=dl(DropCfg.ATTN))
     y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"],
                   residual=x32 if x32 is not None else x, drop=dl(DropCfg.DROP1), out_dtype=f32)
-    x1 = xs[1] if xs is not None else torch.empty(M, E, device=dev, dtype=bf16)
+    x1 = xs[1] if xs is not None else torch.empty(M, E, device=dev, dtype=f16)
     x1_32 = torch.empty(M, E, device=dev, dtype=f32)
     s.mean1 = torch.empty(M, device=dev, dtype=f32) if save else None
     s.rstd1 = torch.empty(M, device=dev, dtype=f32) if save else None
     K.layernorm_fwd32(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1, x1_32,
                       s.mean1, s.rstd1)
-    u = torch.empty(M, F, device=dev, dtype=bf16) if save else None
+    u = torch.empty(M, F, device=dev, dtype=f16) if save else None
     h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True, dgelu_out=u, drop=dl(DropCfg.ACT),
                  out=None if xs is None else xs[2])
     s.xs = xs
     d3 = dl(DropCfg.DROP3)
     y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1_32, drop=d3, out_dtype=f32)
-    lr = torch.empty(M, E, device=dev, dtype=bf16) if want_lr else None
+    lr = torch.empty(M, E, device=dev, dtype=f16) if want_lr else None
     if want_lr and d3 is not None:
         # `layer_result` is the fc2 output BEFORE dropout3 (modules/module.py:577-578); y2 - x1 would be the dropped one
         K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], out=lr)
-    x2 = out if out is not None else torch.empty(M, E, device=dev, dtype=bf16)
+    x2 = out if out is not None else torch.empty(M, E, device=dev, dtype=f16)
     s.mean2 = torch.empty(M, device=dev, dtype=f32) if save else None
     s.rstd2 = torch.empty(M, device=dev, dtype=f32) if save else None
     recover = want_lr and d3 is None
@@ -545,7 +561,7 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
 def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None, slots=None,
                     wave_chunks=None, want_lr: bool = False):
     """Frozen teacher forward (reference utils/utils.py:80-99 around fairseq HubertModel /
-    Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] bf16, features [B, T, E]).
+    Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] fp16, features [B, T, E]).
     slots: optional list mapping teacher layer -> row of out_buf (None = not a distillation target: that layer's
     output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather."""
     W.ensure_fresh()
@@ -554,7 +570,7 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     B, T, E = c.B, c.T, g.E
     if out_buf is None:
         n_out = g.n_layers if slots is None else 1 + max(s for s in slots if s is not None)
-        out_buf = torch.empty(n_out, B, T, E, device=wave.device, dtype=bf16)
+        out_buf = torch.empty(n_out, B, T, E, device=wave.device, dtype=f16)
     x, x32 = c.enc_in, c.enc_in32
     scratch = None
     lrs = []
@@ -563,7 +579,7 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     for l in range(last):  # layers above the highest target are never needed
         slot = l if slots is None else slots[l]
         if slot is None:
-            scratch = [torch.empty(B * T, E, device=wave.device, dtype=bf16) for _ in range(2)] if scratch is None else scratch
+            scratch = [torch.empty(B * T, E, device=wave.device, dtype=f16) for _ in range(2)] if scratch is None else scratch
             dst = scratch[l & 1]
         else:
             dst = out_buf[slot].view(B * T, E)
@@ -597,17 +613,17 @@ def _compose_heads(W: WeightSet, g: Geometry, hs: Dict[str, int], n: int):
     between: for output phase p,  pred[2t+p] = x[t] (Wup_p Wlin^T) + (bup Wlin^T + blin).  Fold the two weights once per
     step (two tiny batched GEMMs + two 1-row GEMMs for the bias) and the 12 heads run as ONE [B*Ts, E] x [E, 2D] GEMM
     instead of [B*Ts, E] x [E, 2E] followed by [B*2Ts, E] x [E, D]: 38 % fewer head FLOPs forward and backward, the
-    [n, B, 2Ts, E] intermediate is never written, and one bf16 rounding of the activations disappears.
-    Returns Wc [n, 2, D, E] bf16 (K-major [2D, E] per head) and bc [n, 2D] fp32."""
+    [n, B, 2Ts, E] intermediate is never written, and one 16-bit rounding of the activations disappears.
+    Returns Wc [n, 2, D, E] fp16 (K-major [2D, E] per head) and bc [n, 2D] fp32."""
     E, D = g.E, g.d_out
     dev = W["h0.wlin"].device
-    Wc = torch.empty(n, 2, D, E, device=dev, dtype=bf16)
+    Wc = torch.empty(n, 2, D, E, device=dev, dtype=f16)
     bc = torch.empty(n, 2 * D, device=dev, dtype=f32)
-    wlin3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
-    bup3 = L.tensor3(data_ptr=W["h0.bup16"].data_ptr(), dim=(E, 1, n), stride=(E, hs["bup16"]))
+    wlin3 = L.tensor3(W["h0.wlin"], data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+    bup3 = L.tensor3(W["h0.bup16"], data_ptr=W["h0.bup16"].data_ptr(), dim=(E, 1, n), stride=(E, hs["bup16"]))
     for p in range(2):
         # Wc[h, p] [D x E_in] = Wlin[h] [D x E_out] (K-major) x Wup[h, p] (rows = E_out, E_in contiguous: MN-major B)
-        wup3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr() + 2 * p * E * E, dim=(E, E, n), stride=(E, hs["wup"]))
+        wup3 = L.tensor3(W["h0.wup"], data_ptr=W["h0.wup"].data_ptr() + 2 * p * E * E, dim=(E, E, n), stride=(E, hs["wup"]))
         K.gemm_raw(wlin3, wup3, Wc, D, E, E, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E,
                    d_hi_stride=2 * D * E, d_offset_elems=p * D * E)
         # bc[h, p*D:(p+1)*D] = bup[h] Wlin[h]^T + blin[h]   (M = 1)
@@ -638,9 +654,9 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     if g.tr:
         Ts = T // 2
         # time-reduction Conv1d(k=2, s=2) (modules/module.py:317-321): reshaped-view GEMM, drops an odd tail frame
-        tr = torch.empty(B * Ts, E, device=dev, dtype=bf16)
-        a3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
-        b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
+        tr = torch.empty(B * Ts, E, device=dev, dtype=f16)
+        a3 = L.tensor3(c.enc_in, data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
+        b3 = L.tensor3(W["tr.w"], data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
         K.gemm_raw(a3, b3, tr, Ts, E, 2 * E, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=Ts * E,
                    flags=L.EPI_BIAS, bias=P["encoder.layers.0.bias"])
         off = 1
@@ -650,7 +666,7 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     c.tr = tr
     x, x32 = (tr, None) if tr is not None else (c.enc_in, c.enc_in32)
     c.layer_ctx = []
-    lay = torch.empty(g.n_layers, B * Ts, E, device=dev, dtype=bf16)  # stacked layer outputs (batched heads)
+    lay = torch.empty(g.n_layers, B * Ts, E, device=dev, dtype=f16)  # stacked layer outputs (batched heads)
     ping = [torch.empty(B * Ts, E, device=dev, dtype=f32) for _ in range(2)]  # fp32 copies of the layer outputs
     c.x_last = x
     for l in range(n_run):
@@ -670,12 +686,12 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         c.Tq, c.head_idx, c.heads_batched, c.preds = Ts, [], False, None
         if heads == "all":
             N, inter = g.n_split, g.inter
-            c.sp_u = torch.empty(B * Ts, N * inter, device=dev, dtype=bf16) if train else None
+            c.sp_u = torch.empty(B * Ts, N * inter, device=dev, dtype=f16) if train else None
             c.sp_h = K.linear(c.x_last, W["sp.w1"].view(N * inter, E), P["proj_head.0.bias"], gelu=True, dgelu_out=c.sp_u)
             if pred_buf is None:
-                pred_buf = torch.empty(N, B, Ts, D, device=dev, dtype=bf16)
-            a3 = L.tensor3(data_ptr=c.sp_h.data_ptr(), dim=(inter, B * Ts, N), stride=(N * inter, inter))
-            b3 = L.tensor3(data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
+                pred_buf = torch.empty(N, B, Ts, D, device=dev, dtype=f16)
+            a3 = L.tensor3(c.sp_h, data_ptr=c.sp_h.data_ptr(), dim=(inter, B * Ts, N), stride=(N * inter, inter))
+            b3 = L.tensor3(W["sp.w2"], data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
             K.gemm_raw(a3, b3, pred_buf, B * Ts, D, inter, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=D,
                        d_hi_stride=B * Ts * D, flags=L.EPI_BIAS, bias=P["proj_head.2.bias"], bias_hi_stride=D)
             c.preds = pred_buf
@@ -688,26 +704,26 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     c.heads_batched = bool(idx) and heads == "all" and all(v is not None for v in hs.values())
     if idx:
         if pred_buf is None:
-            pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=bf16)
+            pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=f16)
         c.Wc = None
         if c.heads_batched and head_compose_enabled() and W.head_stride("bup16") is not None:
             hs["bup16"] = W.head_stride("bup16")
             c.Wc, bc = _compose_heads(W, g, hs, n)
-            a3 = L.tensor3(data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
-            b3 = L.tensor3(data_ptr=c.Wc.data_ptr(), dim=(E, 2 * D, n), stride=(E, 2 * D * E))
+            a3 = L.tensor3(lay, data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
+            b3 = L.tensor3(c.Wc, data_ptr=c.Wc.data_ptr(), dim=(E, 2 * D, n), stride=(E, 2 * D * E))
             K.gemm_raw(a3, b3, pred_buf, B * Ts, 2 * D, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                        d_ld=2 * D, d_hi_stride=B * Ts * 2 * D, flags=L.EPI_BIAS, bias=bc, bias_hi_stride=2 * D)
             c.z = None
             c.head_strides = hs
         elif c.heads_batched:
             # all n heads as TWO batched GEMMs (ob = head): 12x the tiles per launch, no per-head launch tails
-            z = torch.empty(n, B * Tq, E, device=dev, dtype=bf16)
-            a3 = L.tensor3(data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
-            b3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
+            z = torch.empty(n, B * Tq, E, device=dev, dtype=f16)
+            a3 = L.tensor3(lay, data_ptr=lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
+            b3 = L.tensor3(W["h0.wup"], data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
             K.gemm_raw(a3, b3, z, B * Ts, 2 * E, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=2 * E,
                        d_hi_stride=B * Ts * 2 * E, flags=L.EPI_BIAS, bias=W["h0.bup"], bias_hi_stride=hs["bup"])
-            a3 = L.tensor3(data_ptr=z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
-            b3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+            a3 = L.tensor3(z, data_ptr=z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
+            b3 = L.tensor3(W["h0.wlin"], data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
             K.gemm_raw(a3, b3, pred_buf, B * Tq, D, E, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=D,
                        d_hi_stride=B * Tq * D, flags=L.EPI_BIAS, bias=W["h0.blin"], bias_hi_stride=hs["blin"])
             c.z = z if train else None
@@ -850,13 +866,13 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         N, inter, rows = g.n_split, g.inter, B * Ts
         if dpred_colsum is None:
             K.colsum_batched(dpred.view(N, rows, D), gv("proj_head.2.bias"), D)
-        a3 = L.tensor3(data_ptr=c.sp_h.data_ptr(), dim=(inter, rows, N), stride=(N * inter, inter))
-        b3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, rows, N), stride=(D, rows * D))
+        a3 = L.tensor3(c.sp_h, data_ptr=c.sp_h.data_ptr(), dim=(inter, rows, N), stride=(N * inter, inter))
+        b3 = L.tensor3(dpred, data_ptr=dpred.data_ptr(), dim=(D, rows, N), stride=(D, rows * D))
         K.gemm_raw(a3, b3, gv("proj_head.2.weight"), inter, D, rows, a_major=1, b_major=1, num_ob=N, a_coord=(0, 1, 0, 0),
                    b_coord=(0, 1, 0, 0), d_ld=D, d_hi_stride=inter * D, flags=L.EPI_ATOMIC_ADD)
         dh = torch.empty(rows, N * inter, device=dev, dtype=bf16)  # d(pre-GELU): x gelu'(u) in the epilogue
-        a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, rows, N), stride=(D, rows * D))
-        b3 = L.tensor3(data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
+        a3 = L.tensor3(dpred, data_ptr=dpred.data_ptr(), dim=(D, rows, N), stride=(D, rows * D))
+        b3 = L.tensor3(W["sp.w2"], data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
         K.gemm_raw(a3, b3, dh, rows, inter, D, b_major=1, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=N * inter, d_hi_stride=inter, flags=L.EPI_MUL_AUX, aux_in=c.sp_u)
         K.colsum(dh, gv("proj_head.0.bias"))
@@ -876,45 +892,48 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         # ---- folded heads (see _compose_heads): dWc = dpred^T x, dx = dpred Wc, then the chain rule back to the two
         #      original weights (four small batched GEMMs) and the rank-1 term of the folded bias
         rows = B * Ts
+        # dWc sums (loss-scaled) products over all B*Ts rows: x 2^-ceil(log2 rows) keeps it inside fp16's range (the
+        # chain GEMMs below multiply it back while accumulating into the fp32 gradient buffer)
+        down = 2.0 ** -math.ceil(math.log2(max(2, rows)))
         dWc = torch.empty(n, D, 2, E, device=dev, dtype=bf16)  # [h][d][p][i]
-        a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(2 * D, rows, n), stride=(2 * D, rows * 2 * D))
-        x3 = L.tensor3(data_ptr=c.lay.data_ptr(), dim=(E, rows, n), stride=(E, rows * E))
+        a3 = L.tensor3(dpred, data_ptr=dpred.data_ptr(), dim=(2 * D, rows, n), stride=(2 * D, rows * 2 * D))
+        x3 = L.tensor3(c.lay, data_ptr=c.lay.data_ptr(), dim=(E, rows, n), stride=(E, rows * E))
         K.gemm_raw(a3, x3, dWc, D, E, rows, a_major=1, b_major=1, num_ob=2 * n, ob_mod=2, a_coord=(D, 1, 0, 0),
-                   b_coord=(0, 1, 0, 0), d_ld=2 * E, d_lo_stride=E, d_hi_stride=D * 2 * E)
+                   b_coord=(0, 1, 0, 0), d_ld=2 * E, d_lo_stride=E, d_hi_stride=D * 2 * E, alpha=down)
         dx_head = torch.empty(n, rows, E, device=dev, dtype=bf16)
-        b3 = L.tensor3(data_ptr=c.Wc.data_ptr(), dim=(E, 2 * D, n), stride=(E, 2 * D * E))
+        b3 = L.tensor3(c.Wc, data_ptr=c.Wc.data_ptr(), dim=(E, 2 * D, n), stride=(E, 2 * D * E))
         K.gemm_raw(a3, b3, dx_head, rows, E, 2 * D, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=E, d_hi_stride=rows * E)
-        wlin3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+        wlin3 = L.tensor3(W["h0.wlin"], data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
         for ph in range(2):
-            dwc3 = L.tensor3(data_ptr=dWc.data_ptr() + 2 * ph * E, dim=(E, D, n), stride=(2 * E, D * 2 * E))
-            wup3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr() + 2 * ph * E * E, dim=(E, E, n), stride=(E, hs["wup"]))
+            dwc3 = L.tensor3(dWc, data_ptr=dWc.data_ptr() + 2 * ph * E, dim=(E, D, n), stride=(2 * E, D * 2 * E))
+            wup3 = L.tensor3(W["h0.wup"], data_ptr=W["h0.wup"].data_ptr() + 2 * ph * E * E, dim=(E, E, n), stride=(E, hs["wup"]))
             # dWlin[h] [D x E_out] += dWc[h, :, ph, :] [D x E_in] x Wup[h, ph] ([E_out][E_in]: K-major B)
             K.gemm_raw(dwc3, wup3, G_.from_("proj_head.0.lin_proj.weight"), D, E, E, num_ob=n, a_coord=(0, 1, 0, 0),
-                       b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD)
+                       b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD, alpha=1.0 / down)
             # dWup[h, ph] [E_out x E_in] += Wlin[h]^T [E_out x D] x dWc[h, :, ph, :] [D x E_in]   (both MN-major)
             K.gemm_raw(wlin3, dwc3, G_.from_("proj_head.0.upsampler.weight"), E, E, D, a_major=1, b_major=1, num_ob=n,
                        a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, d_offset_elems=ph * E * E,
-                       flags=L.EPI_ATOMIC_ADD)
+                       flags=L.EPI_ATOMIC_ADD, alpha=1.0 / down)
         # z = x Wup + bup feeds lin_proj: dWlin += colsum(dpred) (x) bup   (n x D x E fp32 elements, one pass)
         glin = G_.from_("proj_head.0.lin_proj.weight").as_strided((n, D, E), (gs, E, 1))
         bup = W["h0.bup"].as_strided((n, 1, E), (hs["bup"], E, 1))
         glin.addcmul_(dpred_colsum.view(n, D, 1), bup)
     elif gs is not None:
-        a3 = L.tensor3(data_ptr=dpred.data_ptr(), dim=(D, B * Tq, n), stride=(D, B * Tq * D))
-        z3 = L.tensor3(data_ptr=c.z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
+        a3 = L.tensor3(dpred, data_ptr=dpred.data_ptr(), dim=(D, B * Tq, n), stride=(D, B * Tq * D))
+        z3 = L.tensor3(c.z, data_ptr=c.z.data_ptr(), dim=(E, B * Tq, n), stride=(E, B * Tq * E))
         K.gemm_raw(a3, z3, G_.from_("proj_head.0.lin_proj.weight"), D, E, B * Tq, a_major=1, b_major=1, num_ob=n,
                    a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD)
         dz = torch.empty(n, B * Tq, E, device=dev, dtype=bf16)
-        b3 = L.tensor3(data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
+        b3 = L.tensor3(W["h0.wlin"], data_ptr=W["h0.wlin"].data_ptr(), dim=(E, D, n), stride=(E, hs["wlin"]))
         K.gemm_raw(a3, b3, dz, B * Tq, E, D, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E,
                    d_hi_stride=B * Tq * E)
-        a3 = L.tensor3(data_ptr=dz.data_ptr(), dim=(2 * E, B * Ts, n), stride=(2 * E, B * Ts * 2 * E))
-        x3 = L.tensor3(data_ptr=c.lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
+        a3 = L.tensor3(dz, data_ptr=dz.data_ptr(), dim=(2 * E, B * Ts, n), stride=(2 * E, B * Ts * 2 * E))
+        x3 = L.tensor3(c.lay, data_ptr=c.lay.data_ptr(), dim=(E, B * Ts, n), stride=(E, B * Ts * E))
         K.gemm_raw(a3, x3, G_.from_("proj_head.0.upsampler.weight"), 2 * E, E, B * Ts, a_major=1, b_major=1, num_ob=n,
                    a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=E, d_hi_stride=gs, flags=L.EPI_ATOMIC_ADD)
         dx_head = torch.empty(n, B * Ts, E, device=dev, dtype=bf16)
-        b3 = L.tensor3(data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
+        b3 = L.tensor3(W["h0.wup"], data_ptr=W["h0.wup"].data_ptr(), dim=(E, 2 * E, n), stride=(E, hs["wup"]))
         K.gemm_raw(a3, b3, dx_head, B * Ts, E, 2 * E, b_major=1, num_ob=n, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=E, d_hi_stride=B * Ts * E)
     off = 1 if g.tr else 0
@@ -989,8 +1008,8 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             if dys is not None:
                 # dW[j] += dys[j]^T xs[j] for j = out_proj, fc1, fc2: one batched split-K launch (ob = j); the three
                 # gradient segments are adjacent in the flat buffer (GradStore order)
-                a3 = L.tensor3(data_ptr=dys.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
-                b3 = L.tensor3(data_ptr=xs.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
+                a3 = L.tensor3(dys, data_ptr=dys.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
+                b3 = L.tensor3(xs, data_ptr=xs.data_ptr(), dim=(E, M_, 3), stride=(E, M_ * E))
                 assert G_.entries[p + "fc1.weight"][0] - G_.entries[p + "self_attn.out_proj.weight"][0] == E * E and \
                     G_.entries[p + "fc2.weight"][0] - G_.entries[p + "fc1.weight"][0] == E * E
                 K.gemm_raw(a3, b3, G_.from_(p + "self_attn.out_proj.weight"), E, E, M_, a_major=1, b_major=1, num_ob=3,
@@ -1023,14 +1042,14 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     if g.tr:
         # ---- time-reduction conv backward
         K.colsum(dx, gv("encoder.layers.0.bias"))
-        dy3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
-        x3 = L.tensor3(data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
+        dy3 = L.tensor3(dx, data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
+        x3 = L.tensor3(c.enc_in, data_ptr=c.enc_in.data_ptr(), dim=(2 * E, Ts, B), stride=(2 * E, T * E))
         _wgrad(dy3, x3, gv("encoder.layers.0.weight").view(E, 2 * E), E, 2 * E, Ts, num_cb=B, a_cb=1, b_cb=1)
         denc = torch.empty(B * T, E, device=dev, dtype=bf16)
         if T % 2:  # the odd tail frame was dropped by the TR conv: zero gradient
             K.zero_rows(denc, (T - 1) * E, T * E, E, B)
-        a3 = L.tensor3(data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
-        b3 = L.tensor3(data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
+        a3 = L.tensor3(dx, data_ptr=dx.data_ptr(), dim=(E, Ts, B), stride=(E, Ts * E))
+        b3 = L.tensor3(W["tr.w"], data_ptr=W["tr.w"].data_ptr(), dim=(2 * E, E, 1), stride=(2 * E, 2 * E * E))
         K.gemm_raw(a3, b3, denc, Ts, 2 * E, E, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * E, d_hi_stride=T * E)
     else:
         denc = dx  # no TR layer: the first transformer layer reads the prologue output directly
@@ -1050,15 +1069,15 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
                          c.rstd_e, dh, dcg, gv("encoder.layer_norm.weight"), gv("encoder.layer_norm.bias"),
                          gv("encoder.pos_conv.0.bias"), B, T, E, G, cp, pad_b, Tp, delta=dl)
     dxc = torch.empty(B * R, G * dl * cp, device=dev, dtype=bf16)  # [b][r][g][dl][cp], like the forward output
-    a3 = L.tensor3(data_ptr=dcg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
-    b3 = L.tensor3(data_ptr=W["pc.wt"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))
+    a3 = L.tensor3(dcg, data_ptr=dcg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    b3 = L.tensor3(W["pc.wt"], data_ptr=W["pc.wt"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))
     K.gemm_raw(a3, b3, dxc, R, dl * cp, g.kpx * cp, num_ob=B * G, ob_mod=G, a_coord=(0, G, 1, 0), b_coord=(0, 0, 1, 0),
                d_ld=G * dl * cp, d_hi_stride=R * G * dl * cp, d_lo_stride=dl * cp)
     # wgrad, time-blocked like the forward: dwt'[g][(j',ci)][(dl,co)] = sum_{b,r} xg[b,g,dl_*r + j',ci] *
     # dcg[b,g,dl_*r + dl + pad_b,co]  (N = dl_*cp instead of cp); posconv_wn_bwd folds the dl_ shifted partials
     dwt = torch.empty(G, g.kpx * cp, dl * cp, device=dev, dtype=f32)
-    a3 = L.tensor3(data_ptr=c.xg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
-    b3 = L.tensor3(data_ptr=dcg.data_ptr() + 2 * pad_b * cp, dim=(dl * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    a3 = L.tensor3(c.xg, data_ptr=c.xg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
+    b3 = L.tensor3(dcg, data_ptr=dcg.data_ptr() + 2 * pad_b * cp, dim=(dl * cp, R, B * G), stride=(dl * cp, Tp * cp))
     K.gemm_raw(a3, b3, dwt, g.kpx * cp, dl * cp, R, a_major=1, b_major=1, num_ob=G, ob_mod=G, num_cb=B,
                a_coord=(0, 0, 1, G), b_coord=(0, 0, 1, G), d_ld=dl * cp, d_lo_stride=g.kpx * cp * dl * cp, split_k=1)
     K.posconv_wn_bwd(dwt, P["encoder.pos_conv.0.weight_v"], P["encoder.pos_conv.0.weight_g"], W["pc.inv"],
@@ -1091,8 +1110,8 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         xin = c.y[i - 1]
         du_data = du.data_ptr() + 2 * halo * co
         # wgrad: dW2[co][(j,ci)] += sum_{b,t} dU[b,t,co] * X[b, s*t + j, ci]
-        dy3 = L.tensor3(data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
-        x3 = L.tensor3(data_ptr=xin.data_ptr() + 2 * in_halo * cin, dim=(k * cin, To, B), stride=(s * cin, in_rows * cin))
+        dy3 = L.tensor3(du, data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
+        x3 = L.tensor3(xin, data_ptr=xin.data_ptr() + 2 * in_halo * cin, dim=(k * cin, To, B), stride=(s * cin, in_rows * cin))
         with aside_conv(du):
             _wgrad(dy3, x3, gv(f"feature_extractor.conv_layers.{i}.0.weight").view(co, k * cin), co, k * cin, To,
                    num_cb=B, a_cb=1, b_cb=1)
@@ -1107,18 +1126,18 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.zero_rows(dprev, (in_halo + covered) * cin, in_rows * cin, (Tin - covered) * cin, B)
         if (k, s) == (1, 1) or (k, s) == (2, 2):
             # dA[b,t,(j,ci)] = dU[b,t,:] W2[:, (j,ci)]  ==  dX[b, s*t + j, ci]   (W2 consumed MN-major)
-            a3 = L.tensor3(data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
-            b3 = L.tensor3(data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
+            a3 = L.tensor3(du, data_ptr=du_data, dim=(co, To, B), stride=(co, rows * co))
+            b3 = L.tensor3(W[f"conv{i}.w"], data_ptr=W[f"conv{i}.w"].data_ptr(), dim=(k * cin, co, 1), stride=(k * cin, k * cin * co))
             K.gemm_raw(a3, b3, dprev, To, k * cin, co, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=k * cin,
                        d_hi_stride=in_rows * cin, d_offset_elems=in_halo * cin, flags=flags, aux_in=uprev)
         else:  # (3, 2): even input frames see taps (2, 0) of outputs (u-1, u); odd frames tap 1 of output u
             n_even, n_odd = (Tin + 1) // 2, Tin // 2
-            a3 = L.tensor3(data_ptr=du.data_ptr(), dim=(2 * co, n_even, B), stride=(co, rows * co))
-            b3 = L.tensor3(data_ptr=W[f"conv{i}.wd_even"].data_ptr(), dim=(2 * co, cin, 1), stride=(2 * co, 2 * co * cin))
+            a3 = L.tensor3(du, data_ptr=du.data_ptr(), dim=(2 * co, n_even, B), stride=(co, rows * co))
+            b3 = L.tensor3(W[f"conv{i}.wd_even"], data_ptr=W[f"conv{i}.wd_even"].data_ptr(), dim=(2 * co, cin, 1), stride=(2 * co, 2 * co * cin))
             K.gemm_raw(a3, b3, dprev, n_even, cin, 2 * co, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * cin,
                        d_hi_stride=in_rows * cin, d_offset_elems=in_halo * cin, flags=flags, aux_in=uprev)
-            a3 = L.tensor3(data_ptr=du_data, dim=(co, n_odd, B), stride=(co, rows * co))
-            b3 = L.tensor3(data_ptr=W[f"conv{i}.wd_odd"].data_ptr(), dim=(co, cin, 1), stride=(co, co * cin))
+            a3 = L.tensor3(du, data_ptr=du_data, dim=(co, n_odd, B), stride=(co, rows * co))
+            b3 = L.tensor3(W[f"conv{i}.wd_odd"], data_ptr=W[f"conv{i}.wd_odd"].data_ptr(), dim=(co, cin, 1), stride=(co, co * cin))
             K.gemm_raw(a3, b3, dprev, n_odd, cin, co, num_ob=B, a_coord=(0, 1, 0, 0), d_ld=2 * cin,
                        d_hi_stride=in_rows * cin, d_offset_elems=(in_halo + 1) * cin, flags=flags, aux_in=uprev)
         du = dprev
@@ -1135,8 +1154,8 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         xcol = torch.empty(B, T0, 32, device=dev, dtype=bf16)
         K.conv0_im2col(c.wave, T0, xcol)
         acc32 = torch.zeros(B, C0, 32, device=dev, dtype=f32)
-        a3 = L.tensor3(data_ptr=du.data_ptr(), dim=(C0, T0, B), stride=(C0, T0 * C0))
-        b3 = L.tensor3(data_ptr=xcol.data_ptr(), dim=(32, T0, B), stride=(32, T0 * 32))
+        a3 = L.tensor3(du, data_ptr=du.data_ptr(), dim=(C0, T0, B), stride=(C0, T0 * C0))
+        b3 = L.tensor3(xcol, data_ptr=xcol.data_ptr(), dim=(32, T0, B), stride=(32, T0 * 32))
         K.gemm_raw(a3, b3, acc32, C0, 32, T0, a_major=1, b_major=1, num_ob=B, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=32, d_hi_stride=C0 * 32, flags=L.EPI_ATOMIC_ADD)
         K.conv0_bwd_finalize(acc32, c.wave, wv, gm, bt, T0, c.stat, c.mean0, c.rstd0, gw, gg, gb, True)

@@ -9,7 +9,8 @@ import torch
 
 from . import lib as L
 
-bf16 = torch.bfloat16
+f16 = torch.float16     # every 16-bit tensor: weights, activations, saved gelu', projections, targets, and the
+bf16 = f16              # gradients (which carry the loss scale, engine.loss_scale_for); the old name stays as an alias
 
 
 def _cuda(t: torch.Tensor) -> torch.Tensor:
@@ -57,7 +58,7 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
              d_ld: int, d_hi_stride=0, d_lo_stride=0, flags=0, split_k=0, bias=None, residual=None,
              aux_in=None, aux_out=None, row_valid=None, loss_target=None, loss_acc=None,
              loss_weight=0.0, grad_scale=0.0, d_offset_elems=0, a_c1_off=0, b_c1_off=0, bias_hi_stride=0,
-             drop=None) -> None:
+             drop=None, alpha=None) -> None:
     g = L.GemmArgs()
     g.a, g.b = a, b
     g.a_major, g.b_major = a_major, b_major
@@ -68,19 +69,28 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
     g.a_c1_off, g.b_c1_off = a_c1_off, b_c1_off
     g.d = d.data_ptr() + d_offset_elems * d.element_size()
     g.d_ld, g.d_hi_stride, g.d_lo_stride = d_ld, d_hi_stride, d_lo_stride
+    # operand / output formats travel in the flags: fp16 (forward tensors) unless flagged bf16 (gradients) or fp32
+    assert not a.bf16 and not b.bf16, "operands are fp16 (tcgen05 cannot mix fp16 with bf16; gradients carry a loss scale)"
     if d.dtype == torch.float32:
         flags |= L.EPI_OUT_F32
     else:
-        assert d.dtype == bf16
+        assert d.dtype == f16, d.dtype
+    assert aux_in is None or aux_in.dtype == f16, "aux_in is a forward quantity (fp16)"
+    assert loss_target is None or loss_target.dtype == f16
+    if aux_out is not None:
+        assert aux_out.dtype == (f16 if (flags & L.EPI_AUX_DGELU) else d.dtype), (aux_out.dtype, d.dtype)
+    if alpha is not None and alpha != 1.0:
+        flags |= L.EPI_ALPHA
+        g.alpha = alpha
     g.flags, g.split_k = flags, split_k
     for name, t in (("bias", bias), ("row_valid", row_valid), ("loss_acc", loss_acc)):
         setattr(g, name, None if t is None else t.data_ptr())
     for name, t in (("residual", residual), ("aux_in", aux_in), ("aux_out", aux_out), ("loss_target", loss_target)):
         # "laid out like D": same element offset as the output
         setattr(g, name, None if t is None else t.data_ptr() + d_offset_elems * t.element_size())
-    if residual is not None and residual.dtype == torch.float32:
-        flags |= L.EPI_RES_F32  # the fp32 copy of the residual stream (layernorm_fwd32 / layernorm_bwd32)
-        g.flags = flags
+    if residual is not None:  # fp32: the high-precision copy of the residual stream (layernorm_fwd32 / layernorm_bwd32)
+        flags |= {torch.float32: L.EPI_RES_F32, f16: 0}[residual.dtype]
+    g.flags = flags
     g.loss_weight, g.grad_scale = loss_weight, grad_scale
     g.bias_hi_stride = bias_hi_stride
     if drop is not None and drop[1] > 0.0:  # (seed, p)
@@ -100,9 +110,9 @@ def gemm_raw(a: L.Tensor3, b: L.Tensor3, d: torch.Tensor, m: int, n: int, k: int
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, gelu=False,
-           residual=None, row_valid=None, rows_per_batch=0, preact_out=None, dgelu_out=None, out_dtype=bf16,
+           residual=None, row_valid=None, rows_per_batch=0, preact_out=None, dgelu_out=None, out_dtype=f16,
            out: Optional[torch.Tensor] = None, drop=None) -> torch.Tensor:
-    """y[M,N] = epi(x[M,K] @ w[N,K]^T).  x, w bf16 row-major (x may be a strided 2-D view).
+    """y[M,N] = epi(x[M,K] @ w[N,K]^T).  x, w fp16 row-major (x may be a strided 2-D view); y fp16 (or fp32).
     preact_out: also store the value before GELU / residual; dgelu_out: store gelu'(that value) instead
     (what the backward epilogue multiplies by: FHB_EPI_MUL_AUX)."""
     _cuda(x)
@@ -139,14 +149,14 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, dgelu_of=None, mul_aux=None, residual=None,
                  out: Optional[torch.Tensor] = None, out_dtype=bf16) -> torch.Tensor:
     """dx[M,K] = dy[M,N] @ w[N,K]  (w consumed MN-major: no transposed copy), optionally * gelu'(dgelu_of)
-    or * mul_aux (a saved gelu'), + residual (bf16 or fp32)."""
+    or * mul_aux (a saved gelu'), + residual (fp16 or fp32); dx fp16 (or fp32)."""
     M, N = dy.shape
     K = w.shape[1]
     dx = out if out is not None else torch.empty(M, K, device=dy.device, dtype=out_dtype)
     assert dgelu_of is None or mul_aux is None
     flags = (L.EPI_MUL_DGELU if dgelu_of is not None else 0) | (L.EPI_MUL_AUX if mul_aux is not None else 0) | \
         (L.EPI_RESIDUAL if residual is not None else 0)
-    b3 = L.tensor3(data_ptr=w.data_ptr(), dim=(K, N, 1), stride=(w.stride(0), w.stride(0) * N))
+    b3 = L.tensor3(w, data_ptr=w.data_ptr(), dim=(K, N, 1), stride=(w.stride(0), w.stride(0) * N))
     gemm_raw(L.tensor3(dy), b3, dx, M, K, N, b_major=1, d_ld=dx.stride(0), flags=flags,
              aux_in=dgelu_of if dgelu_of is not None else mul_aux, residual=residual)
     return dx
@@ -154,15 +164,15 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, dgelu_of=None, mul_aux=No
 
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
                  accumulate=False) -> torch.Tensor:
-    """dw[N,K] (fp32) = dy[M,N]^T @ x[M,K]; both operands MN-major, split-K with fp32 atomics."""
+    """dw[N,K] (fp32) = dy[M,N]^T @ x[M,K] ; both operands MN-major, split-K with fp32 atomics."""
     M, N = dy.shape
     K = x.shape[1]
     if out is None:
         out = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
     elif not accumulate:
         out.zero_()
-    a3 = L.tensor3(data_ptr=dy.data_ptr(), dim=(N, M, 1), stride=(dy.stride(0), dy.stride(0) * M))
-    b3 = L.tensor3(data_ptr=x.data_ptr(), dim=(K, M, 1), stride=(x.stride(0), x.stride(0) * M))
+    a3 = L.tensor3(dy, data_ptr=dy.data_ptr(), dim=(N, M, 1), stride=(dy.stride(0), dy.stride(0) * M))
+    b3 = L.tensor3(x, data_ptr=x.data_ptr(), dim=(K, M, 1), stride=(x.stride(0), x.stride(0) * M))
     gemm_raw(a3, b3, out, N, K, M, a_major=1, b_major=1, d_ld=out.stride(0), flags=L.EPI_ATOMIC_ADD)
     return out
 
@@ -173,6 +183,7 @@ def _f(x):
 
 
 def conv0_fwd(wave, weight, gamma, beta, T0, stat, mean, rstd, out, eps=1e-5, gp_out=None):
+    assert out.dtype == f16 and (gp_out is None or gp_out.dtype == f16)
     a = L.Conv0Args()
     B, Ld = wave.shape
     a.wave, a.wave_ld = wave.data_ptr(), wave.stride(0)
@@ -216,6 +227,7 @@ def conv0_bwd_finalize(acc32, wave, weight, gamma, beta, T0, stat, mean, rstd, d
 
 
 def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-5):
+    assert x.dtype == f16 and y.dtype == f16
     rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
     L.check(L.lib().fhb_layernorm_fwd(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(mean), L.ptr(rstd),
                                       C.c_int64(rows), Cd, _f(eps), L.stream_ptr()), "fhb_layernorm_fwd")
@@ -226,6 +238,7 @@ def layernorm_fwd32(x32, gamma, beta, y, y32=None, mean=None, rstd=None, sub32=N
     """LayerNorm of the fp32 pre-LN sum: y bf16 (GEMM operand), y32 the fp32 copy the next residual add reads;
     diff_out = bf16(x32 - sub32) (the FFN branch output the reference returns as `layer_result`)."""
     assert x32.dtype == torch.float32 and (y32 is None or y32.dtype == torch.float32)
+    assert y.dtype == f16 and (diff_out is None or diff_out.dtype == f16)
     rows, Cd = x32.numel() // x32.shape[-1], x32.shape[-1]
     L.check(L.lib().fhb_layernorm_fwd32(L.ptr(x32), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ptr(y32), L.ptr(mean),
                                         L.ptr(rstd), L.ptr(sub32), L.ptr(diff_out), C.c_int64(rows), Cd, _f(eps),
@@ -239,6 +252,7 @@ def layernorm_bwd32(dy32, x32, gamma, mean, rstd, dgamma, dbeta, *, dy2=None, dx
     the backward residual stream), dx (bf16) and / or dx_drop (bf16, dropout-masked, with drop=(seed, p))."""
     assert x32.dtype == torch.float32 and (dy32 is None or dy32.dtype == torch.float32)
     assert dy2 is None or dy2.dtype == bf16
+    assert (dx is None or dx.dtype == bf16) and (dx_drop is None or dx_drop.dtype == bf16)
     rows, Cd = x32.numel() // x32.shape[-1], x32.shape[-1]
     seed, p = (drop[0] & 0xFFFFFFFF, drop[1]) if (drop is not None and dx_drop is not None) else (0, 0.0)
     L.check(L.lib().fhb_layernorm_bwd32(L.ptr(dy32), L.ptr(dy2), L.ptr(x32), L.ptr(gamma), L.ptr(mean), L.ptr(rstd),
@@ -252,6 +266,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dxsum=
     """dxsum (fp32 [C], accumulated): column sums of dx = bias gradient of the linear layer that produced x.
     dy2: optional second gradient stream, summed with dy on load.  dx_drop + drop=(seed, p): also write
     dx * dropout-mask (the gradient entering a `residual + dropout(branch)` branch; dxsum then sums that)."""
+    assert dy.dtype == bf16 and x.dtype == f16 and dx.dtype == bf16, "16-bit tensors are fp16"
     rows, Cd = x.numel() // x.shape[-1], x.shape[-1]
     seed, p = (drop[0] & 0xFFFFFFFF, drop[1]) if (drop is not None and dx_drop is not None) else (0, 0.0)
     L.check(L.lib().fhb_layernorm_bwd(L.ptr(dy), L.ptr(dy2), L.ptr(x), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(dres),
@@ -273,6 +288,7 @@ def posconv_wn_prep(v, g, w_fwd, w_bwd, ws, Cd, G, Kt, cp, delta=1):
 
 def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, B, T, Cd, G, cp, eps=1e-5, delta=1,
                        y32=None):
+    assert x.dtype == f16 and conv.dtype == f16 and y.dtype == f16 and (h_out is None or h_out.dtype == f16)
     L.check(L.lib().fhb_posconv_finish_fwd(L.ptr(x), L.ptr(valid), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(beta),
                                            L.ptr(h_out), L.ptr(y), L.ptr(y32), L.ptr(mean), L.ptr(rstd), B, T, Cd, G, cp,
                                            _f(eps), delta, L.stream_ptr()), "fhb_posconv_finish_fwd")
@@ -280,6 +296,7 @@ def posconv_finish_fwd(x, valid, conv, bias, gamma, beta, h_out, y, mean, rstd, 
 
 def posconv_finish_bwd(dy, h, conv, bias, gamma, mean, rstd, dh, dcg, dgamma, dbeta, dbias, B, T, Cd, G, cp, pad_l, Tp,
                        delta=1):
+    assert dy.dtype == bf16 and h.dtype == f16 and conv.dtype == f16 and dh.dtype == bf16 and dcg.dtype == bf16
     L.check(L.lib().fhb_posconv_finish_bwd(L.ptr(dy), L.ptr(h), L.ptr(conv), L.ptr(bias), L.ptr(gamma), L.ptr(mean),
                                            L.ptr(rstd), L.ptr(dh), L.ptr(dcg), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dbias),
                                            B, T, Cd, G, cp, pad_l, Tp, delta, L.stream_ptr()), "fhb_posconv_finish_bwd")
@@ -301,12 +318,14 @@ def _drop(drop):
 
 def attn_fwd(qkv, valid, out, lse, B, T, H, d, scale, drop=None):
     """drop = (seed, p): attention dropout on the probabilities (same pair passed to attn_bwd)."""
+    assert qkv.dtype == f16 and out.dtype == f16
     L.check(L.lib().fhb_attn_fwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(lse), B, T, H, d, _f(scale), *_drop(drop),
                                  L.stream_ptr()), "fhb_attn_fwd")
 
 
 def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale, drop=None, dq_ws=None):
     """dq_ws (fp32 [B, T, H*d]): enables the fused tcgen05 backward for d in {40, 64}."""
+    assert qkv.dtype == f16 and out.dtype == f16 and dout.dtype == bf16 and dqkv.dtype == bf16
     L.check(L.lib().fhb_attn_bwd(L.ptr(qkv), L.ptr(valid), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv),
                                  L.ptr(delta_ws), L.ptr(dq_ws), B, T, H, d, _f(scale), *_drop(drop), L.stream_ptr()),
             "fhb_attn_bwd")
@@ -314,6 +333,7 @@ def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale, drop
 
 def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0,
                  dbias=None, dbias_layer_stride=0):
+    assert pred.dtype == f16 and tgt.dtype == f16 and (dpred is None or dpred.dtype == bf16)
     L.check(L.lib().fhb_distill_loss_fwd_bwd(L.ptr(pred), L.ptr(tgt), L.ptr(weights), L.ptr(layer_loss), L.ptr(dpred),
                                              L.ptr(dbias), C.c_int64(dbias_layer_stride), n_layers, B, Tp, Tt, D,
                                              loss_type, _f(grad_scale), L.stream_ptr()), "fhb_distill_loss_fwd_bwd")
@@ -322,6 +342,7 @@ def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, 
 def distill_loss_sim(pred, tgt, weights, rec_layer_loss, sim_layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0,
                      rec_grad_scale=1.0, sim_grad_scale=1.0, dbias=None, dbias_layer_stride=0):
     """Reconstruction (mse / l1) + cosine (-logsigmoid(cos)) hint loss and its gradient in one pass (train.py:282-314)."""
+    assert pred.dtype == f16 and tgt.dtype == f16 and (dpred is None or dpred.dtype == bf16)
     L.check(L.lib().fhb_distill_loss_sim_fwd_bwd(L.ptr(pred), L.ptr(tgt), L.ptr(weights), L.ptr(rec_layer_loss),
                                                  L.ptr(sim_layer_loss), L.ptr(dpred), L.ptr(dbias),
                                                  C.c_int64(dbias_layer_stride), n_layers, B, Tp, Tt, D, loss_type,
@@ -339,6 +360,7 @@ def prep_multi(table, n_tensors, max_n):
 
 
 def colsum(x2d, out):
+    assert x2d.dtype == bf16, "16-bit tensors are fp16"
     rows, Cd = x2d.shape
     L.check(L.lib().fhb_colsum(L.ptr(x2d), C.c_int64(rows), Cd, C.c_int64(x2d.stride(0)), L.ptr(out), L.stream_ptr()),
             "fhb_colsum")
@@ -347,6 +369,7 @@ def colsum(x2d, out):
 def colsum_batched(x3d, out, out_bstride):
     """x3d [n, rows, C] (contiguous), out: fp32 view whose batch b lives at out + b * out_bstride elements."""
     n, rows, Cd = x3d.shape
+    assert x3d.dtype == bf16
     L.check(L.lib().fhb_colsum_batched(L.ptr(x3d), C.c_int64(rows), Cd, C.c_int64(x3d.stride(1)),
                                        C.c_int64(x3d.stride(0)), L.ptr(out), C.c_int64(out_bstride), n, L.stream_ptr()),
             "fhb_colsum_batched")
@@ -360,6 +383,7 @@ def head_bias_grads(cs, wlin, wlin_stride, dlin_bias, dup_bias, grad_stride, n_h
 
 
 def add_bf16(a, b, y):
+    assert a.dtype == bf16 and b.dtype == bf16 and y.dtype == bf16
     L.check(L.lib().fhb_add_bf16(L.ptr(a), L.ptr(b), L.ptr(y), C.c_int64(a.numel()), L.stream_ptr()), "fhb_add_bf16")
     return y
 
@@ -372,14 +396,16 @@ def mul_dgelu(dy, dy_bs, u, u_bs, out, out_bs, B, n, *, u_off=0, out_off=0):
 
 def mul_bf16(a, a_bs, m, m_bs, out, out_bs, B, n, alpha=1.0):
     """out = alpha * a * m (alpha: fairseq GradMultiply's scale, modules/model.py:428-431)."""
+    assert a.dtype == bf16 and m.dtype == f16 and out.dtype == bf16, "16-bit tensors are fp16"
     L.check(L.lib().fhb_mul_bf16(L.ptr(a), C.c_int64(a_bs), L.ptr(m), C.c_int64(m_bs), L.ptr(out), C.c_int64(out_bs), B,
                                  C.c_int64(n), _f(alpha), L.stream_ptr()), "fhb_mul_bf16")
 
 
 def dropout(x, y, seed, p):
     """y = nn.Dropout(p)(x) with the library's counter-based mask (also its own backward); y may alias x."""
+    assert x.dtype == f16 and y.dtype == f16
     L.check(L.lib().fhb_dropout(L.ptr(x), L.ptr(y), C.c_int64(x.numel()), C.c_uint32(seed & 0xFFFFFFFF), _f(p),
-                                L.stream_ptr()), "fhb_dropout")
+                                int(x.dtype == f16), L.stream_ptr()), "fhb_dropout")
     return y
 
 

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfhb_sm100a.so")
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROWZERO = 1, 2, 4, 8
 EPI_STORE_PREACT, EPI_MUL_DGELU, EPI_OUT_F32, EPI_ATOMIC_ADD, EPI_SQDIFF = 16, 32, 64, 128, 256
 EPI_AUX_DGELU, EPI_MUL_AUX, EPI_DROPOUT, EPI_RES_F32 = 512, 1024, 2048, 4096
+GEMM_A_BF16, GEMM_B_BF16, EPI_OUT_BF16, EPI_RES_BF16, EPI_ALPHA = 8192, 16384, 32768, 65536, 131072
 
 
 class FhbError(RuntimeError):
@@ -40,7 +41,7 @@ class GemmArgs(C.Structure):
         ("loss_target", C.c_void_p), ("loss_acc", C.c_void_p),
         ("loss_weight", C.c_float), ("grad_scale", C.c_float),
         ("bias_hi_stride", C.c_int64),
-        ("drop_seed", C.c_uint32), ("drop_p", C.c_float),
+        ("drop_seed", C.c_uint32), ("drop_p", C.c_float), ("alpha", C.c_float),
     ]
 
 
@@ -135,12 +136,20 @@ def ptr(t) -> C.c_void_p | None:
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def tensor3(t: torch.Tensor | None = None, *, data_ptr=None, dim=None, stride=None) -> Tensor3:
-    """Describe a bf16 operand.  With `t` given (1-3 D, last dim contiguous) the description is
-    derived; otherwise dim/stride (elements, dim[0] contiguous) are taken verbatim."""
+def tensor3(t: torch.Tensor | None = None, *, data_ptr=None, dim=None, stride=None, offset=0, bf16=None) -> Tensor3:
+    """Describe a 16-bit GEMM operand.  With `t` given (1-3 D, last dim contiguous) the description is derived;
+    otherwise dim/stride (elements, dim[0] contiguous) are taken verbatim, starting `offset` elements into `t`.
+    The operand FORMAT travels with the description as `.bf16` (True: bf16, a gradient; False: fp16, a forward tensor):
+    taken from t.dtype, or from the `bf16` argument when only a raw pointer is given."""
     r = Tensor3()
+    if t is not None:
+        assert t.dtype in (torch.bfloat16, torch.float16), t.dtype
+        r.bf16 = t.dtype == torch.bfloat16
+    else:
+        assert bf16 is not None, "a raw-pointer operand needs its format"
+        r.bf16 = bool(bf16)
     if t is not None and dim is None:
-        assert t.dtype == torch.bfloat16 and t.stride(-1) == 1, (t.dtype, t.stride())
+        assert t.stride(-1) == 1, (t.dtype, t.stride())
         if t.dim() == 2:
             dim = (t.shape[1], t.shape[0], 1)
             stride = (t.stride(0), t.stride(0) * t.shape[0])
@@ -149,8 +158,8 @@ def tensor3(t: torch.Tensor | None = None, *, data_ptr=None, dim=None, stride=No
             dim = (t.shape[2], t.shape[1], t.shape[0])
             stride = (t.stride(1), t.stride(0))
         data_ptr = t.data_ptr()
-    elif t is not None:
-        data_ptr = t.data_ptr()
+    elif t is not None and data_ptr is None:
+        data_ptr = t.data_ptr() + 2 * offset
     r.ptr = data_ptr
     # element-wise stores into the embedded arrays: building (c_int64 * 3)(*dim) objects costs 3x as much, and this
     # runs twice per GEMM launch

@@ -7,8 +7,14 @@
  * Conventions: plain pointers + sizes, no torch types.  All pointers are DEVICE pointers unless
  * a name ends in _host.  Every function enqueues work on `stream` and returns immediately:
  * 0 = ok, FHB_ERR_ARG (<0) = bad argument, >0 = cudaError_t.  fhb_last_error() gives the text.
- * No function allocates device memory or synchronises.  Activations are bf16 channel-last
- * [batch, time, channels]; statistics, losses, gradients of parameters and optimizer state fp32.
+ * No function allocates device memory or synchronises.  Every 16-bit tensor is fp16, channel-last
+ * [batch, time, channels]: weight shadows, activations, saved gelu' multipliers, projections, teacher targets, and the
+ * gradients, which carry a power-of-two LOSS SCALE (the caller multiplies it into the grad_scale of the loss kernel
+ * and divides it out in the grad_scale of fhb_adamw_multi) - the precision the reference's own AMP recipe trains in
+ * (data/conf/fithubert.yaml: use_fp16; Lightning GradScaler).  fp16's significand is 8x finer than bf16's at the
+ * same tensor-pipe rate; tcgen05 kind::f16 cannot mix the two formats in one product (illegal instruction on
+ * sm_100a), so one format serves forward and backward.  Conversions to fp16 saturate.  The residual stream of the
+ * transformer layers and its gradient are fp32.  Statistics, losses, parameter gradients, optimizer state: fp32.
  */
 #ifndef FHB_H_
 #define FHB_H_
@@ -37,7 +43,8 @@ int fhb_set_pdl(int mode);
  * projections and fc1/fc2 (:557-579 -> fairseq MultiheadAttention), LayerWiseProjHead (:649-661),
  * and the dgrad / wgrad contractions autograd derives from them.
  *
- * Operands are 3-D strided bf16 tensors (dim[0] contiguous; strides in ELEMENTS, multiples of 8;
+ * Operands are 3-D strided fp16 tensors (FHB_GEMM_A_BF16 + FHB_GEMM_B_BF16 together select bf16 x bf16; the two
+ * formats cannot be mixed; dim[0] contiguous; strides in ELEMENTS, multiples of 8;
  * rows may overlap, i.e. stride[0] < dim[0] is legal and is how k>1 convolutions are expressed).
  *   major 0 (K-major):  dim = {K, rows(M or N), batches}
  *   major 1 (MN-major): dim = {M or N, contraction rows, contraction batches}
@@ -51,20 +58,26 @@ typedef struct {
 enum {
   FHB_EPI_BIAS = 1,         /* + bias[n] (fp32)                                              */
   FHB_EPI_GELU = 2,         /* exact erf GELU                                                */
-  FHB_EPI_RESIDUAL = 4,     /* + residual[m][n] (bf16, laid out like D)                      */
+  FHB_EPI_RESIDUAL = 4,     /* + residual[m][n] (laid out like D; fp16, or see RES_BF16/F32) */
   FHB_EPI_ROWZERO = 8,      /* rows m >= row_valid[ob_hi] are written as 0                   */
-  FHB_EPI_STORE_PREACT = 16,/* aux_out[m][n] = value before GELU (bf16, laid out like D)     */
-  FHB_EPI_MUL_DGELU = 32,   /* * gelu'(aux_in[m][n])  (backward through a fused GELU)        */
-  FHB_EPI_OUT_F32 = 64,     /* D is fp32 (default bf16)                                      */
+  FHB_EPI_STORE_PREACT = 16,/* aux_out[m][n] = value before GELU (D's 16-bit type, like D)   */
+  FHB_EPI_MUL_DGELU = 32,   /* * gelu'(aux_in[m][n])  (aux_in fp16: a saved pre-activation)  */
+  FHB_EPI_OUT_F32 = 64,     /* D is fp32 (default fp16; FHB_EPI_OUT_BF16: bf16, a gradient)  */
   FHB_EPI_ATOMIC_ADD = 128, /* D += (fp32 atomics; required when split_k > 1)                */
   FHB_EPI_SQDIFF = 256,     /* fused distillation loss, see fhb_gemm_args.loss_*             */
-  FHB_EPI_AUX_DGELU = 512,  /* with STORE_PREACT: aux_out = gelu'(value before GELU) instead  */
-  FHB_EPI_MUL_AUX = 1024,   /* * aux_in[m][n] (e.g. a gelu' saved by FHB_EPI_AUX_DGELU)       */
+  FHB_EPI_AUX_DGELU = 512,  /* with STORE_PREACT: aux_out = gelu'(value before GELU), ALWAYS fp16 */
+  FHB_EPI_MUL_AUX = 1024,   /* * aux_in[m][n] (fp16: a gelu' saved by FHB_EPI_AUX_DGELU)      */
   FHB_EPI_DROPOUT = 2048,   /* nn.Dropout(drop_p) after bias/GELU, before the residual; the    */
                             /* mask of element (ob, m, n) is a hash of (drop_seed, index), see  */
                             /* fhb_dropout; with AUX_DGELU the saved gelu' is masked the same   */
-  FHB_EPI_RES_F32 = 4096    /* the residual is fp32 (the high-precision copy of the residual    */
-                            /* stream the LayerNorm kernels keep next to the bf16 GEMM operand) */
+  FHB_EPI_RES_F32 = 4096,   /* the residual is fp32 (the high-precision copy of the residual    */
+                            /* stream the LayerNorm kernels keep next to the 16-bit GEMM operand) */
+  FHB_GEMM_A_BF16 = 8192,   /* A holds bf16; default fp16 (set both or neither)                */
+  FHB_GEMM_B_BF16 = 16384,  /* B holds bf16; default fp16                                      */
+  FHB_EPI_OUT_BF16 = 32768, /* D (and a plain STORE_PREACT aux_out) is bf16                    */
+  FHB_EPI_RES_BF16 = 65536, /* the residual is bf16                                            */
+  FHB_EPI_ALPHA = 131072    /* accumulator x alpha first (keeps sums over many rows, e.g. the  */
+                            /* gradient of a folded weight, inside fp16's range)               */
 };
 
 typedef struct {
@@ -94,6 +107,7 @@ typedef struct {
   int64_t bias_hi_stride;   /* elements: batch ob_hi reads bias + ob_hi * bias_hi_stride (0 = shared bias)  */
   uint32_t drop_seed;       /* FHB_EPI_DROPOUT                                                 */
   float drop_p;
+  float alpha;              /* FHB_EPI_ALPHA                                                   */
 } fhb_gemm_args;
 
 int fhb_gemm(const fhb_gemm_args* args, fhb_stream_t stream);
@@ -307,7 +321,8 @@ int fhb_mul_bf16(const void* a, int64_t a_bstride, const void* m, int64_t m_bstr
  * hash of (j * 0x9E3779B1 + seed); element keeps iff its 16-bit half >= round(p * 65536).  Every fused dropout
  * in this library (GEMM epilogue, LayerNorm backward, attention) generates the same mask for the same index.
  * Replaces nn.Dropout / F.dropout at modules/model.py:489, modules/module.py:294,566,573,578. */
-int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, float p, fhb_stream_t stream);
+int fhb_dropout(const void* x, void* y, int64_t n, uint32_t seed, float p, int32_t is_f16 /* 1: fp16 (what the
+                library uses), 0: bf16 */, fhb_stream_t stream);
 /* zero `height` runs of `width_bytes` bytes, `pitch_bytes` apart (halo rows / borders of strided buffers);
  * a cudaMemset2DAsync, no kernel */
 int fhb_memset2d(void* ptr, int64_t pitch_bytes, int64_t width_bytes, int64_t height, fhb_stream_t stream);

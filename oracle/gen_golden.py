@@ -195,12 +195,15 @@ def main():
     import yaml
     with open(os.path.join(REF, "data/conf/fithubert.yaml")) as f:
         ycfg = yaml.safe_load(f)["distiller"]
-    run_case("tiny_hubert_pad", TINY_STUDENT, TINY_TEACHER, 3, 9000, [9000, 7411, 5000], ycfg)
-    run_case("tiny_hubert_nopad", TINY_STUDENT, TINY_TEACHER, 2, 6500, [6500, 6500], ycfg)
-    run_case("tiny_w2v2_pad_oddT", TINY_STUDENT, TINY_TEACHER, 2, 8100, [8100, 4321], ycfg, kind="wav2vec2")
+    # 1.5 - 2 s utterances (75 - 99 frames): parameter gradients are sums over frames, and with the 0.5 s / 27-frame
+    # utterances of round 1 the max-norm deviation of a bf16 run on the smallest tensors (conv layer 0, GroupNorm) was
+    # dominated by that handful of frames rather than by the arithmetic under test
+    run_case("tiny_hubert_pad", TINY_STUDENT, TINY_TEACHER, 3, 32000, [32000, 27411, 21000], ycfg)
+    run_case("tiny_hubert_nopad", TINY_STUDENT, TINY_TEACHER, 2, 24000, [24000, 24000], ycfg)
+    run_case("tiny_w2v2_pad_oddT", TINY_STUDENT, TINY_TEACHER, 2, 28100, [28100, 17321], ycfg, kind="wav2vec2")
     with open(os.path.join(REF, "data/conf/ex.yaml")) as f:
         ecfg = yaml.safe_load(f)["distiller"]
-    run_case_split("split_hubert_pad", TINY_SPLIT_STUDENT, TINY_TEACHER, 3, 9000, [9000, 7411, 5000], ecfg)
+    run_case_split("split_hubert_pad", TINY_SPLIT_STUDENT, TINY_TEACHER, 3, 32000, [32000, 27411, 21000], ecfg)
 
 
 if __name__ == "__main__":

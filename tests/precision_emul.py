@@ -18,13 +18,18 @@ def q16(t):
     return t.bfloat16().float()
 
 
+def qh(t):
+    return t.half().float()
+
+
 class RQ(torch.autograd.Function):
-    """value rounded to bf16 in the forward (f) and / or gradient rounded in the backward (b)"""
+    """value rounded to bf16 (f = True) or fp16 (f = "h") in the forward and / or gradient rounded to bf16 in the
+    backward (b)"""
 
     @staticmethod
     def forward(ctx, t, f, b):
         ctx.b = b
-        return q16(t) if f else t.clone()
+        return qh(t) if f == "h" else (q16(t) if f else t.clone())
 
     @staticmethod
     def backward(ctx, g):
@@ -40,7 +45,7 @@ class GeluSaved(torch.autograd.Function):
             p = pre.detach().requires_grad_(True)
             y = F.gelu(p)
             (gp,) = torch.autograd.grad(y.sum(), p)
-        ctx.save_for_backward(q16(gp) if rounded else gp)
+        ctx.save_for_backward(qh(gp) if rounded == "h" else (q16(gp) if rounded else gp))
         return y.detach()
 
     @staticmethod
@@ -80,14 +85,19 @@ class AttnCore(torch.autograd.Function):
 
 
 class Sites:
-    def __init__(self, fwd, bwd):
-        self.fwd, self.bwd = set(fwd), set(bwd)
+    """fwd / bwd: sites stored in 16 bits; f16: the forward sites among them that use fp16 instead of bf16"""
+
+    def __init__(self, fwd, bwd, f16=()):
+        self.fwd, self.bwd, self.f16 = set(fwd), set(bwd), set(f16)
+
+    def fmt(self, f):
+        return ("h" if f in self.f16 else True) if f in self.fwd else False
 
     def r(self, t, f=None, b=None):
-        return RQ.apply(t, f in self.fwd, b in self.bwd)
+        return RQ.apply(t, self.fmt(f), b in self.bwd)
 
     def w(self, w):
-        return RQ.apply(w, "w" in self.fwd, False)
+        return RQ.apply(w, self.fmt("w"), False)
 
 
 # every bf16 storage site of the round-1 CUDA path
@@ -107,7 +117,7 @@ def conv_stack(S, sd, x, conv_layers):
         else:
             x = F.conv1d(x, S.w(w), None, stride=s)
         x = S.r(x, None, "dconv")  # dU = (dgrad) * gelu' is stored in bf16
-        x = GeluSaved.apply(x, "conv_u" in S.fwd)
+        x = GeluSaved.apply(x, S.fmt("conv_u"))
         x = S.r(x, "conv_y", None)
     return x
 
@@ -127,7 +137,7 @@ def layer(S, sd, p, x, bias, H):
     x1 = S.r(F.layer_norm(y1, (E,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], 1e-5), "ln", "dln")
     x1o = S.r(x1, "lnop", "dlnop")
     u = S.r(F.linear(x1o, S.w(sd[p + "fc1.weight"]), sd[p + "fc1.bias"]), None, "du")
-    h = S.r(GeluSaved.apply(u, "ffu" in S.fwd), "ffh", None)
+    h = S.r(GeluSaved.apply(u, S.fmt("ffu")), "ffh", None)
     y2 = S.r(x1 + S.r(F.linear(h, S.w(sd[p + "fc2.weight"]), sd[p + "fc2.bias"]), None, "dyop"), "y", "dx")
     return S.r(F.layer_norm(y2, (E,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5), "ln", "dln")
 
