@@ -508,7 +508,7 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
 
 def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, T, save: bool, want_lr: bool,
               out: Optional[torch.Tensor] = None, drop: Optional[DropCfg] = None, x32: Optional[torch.Tensor] = None,
-              out32: Optional[torch.Tensor] = None):
+              out32: Optional[torch.Tensor] = None, stream32: bool = True):
     """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E].
     The residual stream never passes through 16 bits: x32 is the fp32 copy of x (None for the first layer, whose input is
     the fp16 output of a GEMM anyway), the out_proj / fc2 epilogues add it in fp32 and write the sums y1 / y2 in fp32, the
@@ -517,6 +517,24 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
     dev = x.device
     s = SimpleNamespace(x=x)
     M = B * T
+    if not stream32:
+        # forward-only variant with the residual stream in fp16 (the frozen teacher, FHB_TEACHER_STREAM32=0): half the
+        # bytes through the out_proj / fc2 epilogues and the LayerNorms; fp16's 11-bit significand keeps the 12-layer
+        # deviation at a few 1e-3 (profiles/r02*_teacher_stream16.txt)
+        assert not save
+        qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
+        attn = torch.empty(M, E, device=dev, dtype=f16)
+        K.attn_fwd(qkv, valid_t, attn, None, B, T, H, d, d ** -0.5)
+        y1 = K.linear(attn, W[f"l{l}.wo"].view(E, E), P[prefix + "self_attn.out_proj.bias"], residual=x)
+        x1 = torch.empty(M, E, device=dev, dtype=f16)
+        K.layernorm_fwd(y1, P[prefix + "self_attn_layer_norm.weight"], P[prefix + "self_attn_layer_norm.bias"], x1)
+        h = K.linear(x1, W[f"l{l}.w1"].view(F, E), P[prefix + "fc1.bias"], gelu=True)
+        lr = torch.empty(M, E, device=dev, dtype=f16) if want_lr else None
+        y2 = K.linear(h, W[f"l{l}.w2"].view(E, F), P[prefix + "fc2.bias"], residual=x1, preact_out=lr)
+        x2 = out if out is not None else torch.empty(M, E, device=dev, dtype=f16)
+        K.layernorm_fwd(y2, P[prefix + "final_layer_norm.weight"], P[prefix + "final_layer_norm.bias"], x2)
+        s.out, s.lr, s.out32 = x2, lr, None
+        return s
     qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
     # training with F == E: the inputs of out_proj / fc1 / fc2 (attn, x1, h) share one [3, M, E] buffer so that their three
     # weight-gradient GEMMs run as one batched launch in the backward (wgrad_batch_enabled)
@@ -565,7 +583,12 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     slots: optional list mapping teacher layer -> row of out_buf (None = not a distillation target: that layer's
     output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather."""
     W.ensure_fresh()
-    c = frontend_fwd(P, W, g, wave, valid, save=False, wave_chunks=wave_chunks, want_enc32=True)
+    import os
+    # the frozen teacher carries its residual stream in fp16 by default (A/B on B200, profiles/r02i_teacher_stream16_ab.txt:
+    # 24.0 / 24.6 ms -> 23.7 / 23.6 ms per step; teacher layers deviate 3.1e-3 instead of 1.4e-3 from the fp32 oracle,
+    # student gradients unchanged at 2.0e-3); FHB_TEACHER_STREAM32=1 gives it the student's fp32 stream
+    stream32 = os.environ.get("FHB_TEACHER_STREAM32", "0") == "1"
+    c = frontend_fwd(P, W, g, wave, valid, save=False, wave_chunks=wave_chunks, want_enc32=stream32)
     valid_t = c.valid_t
     B, T, E = c.B, c.T, g.E
     if out_buf is None:
@@ -584,7 +607,7 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         else:
             dst = out_buf[slot].view(B * T, E)
         s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=want_lr, out=dst, x32=x32,
-                      out32=ping[l & 1] if l + 1 < last else None)
+                      out32=ping[l & 1] if (l + 1 < last and stream32) else None, stream32=stream32)
         x, x32 = s.out, s.out32
         lrs.append(s.lr)
     if want_lr:  # the hook output of every layer is (x, (attn, layer_result)), utils/utils.py:65-78
