@@ -135,6 +135,73 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+def reference_root():
+    """Where the reference's own Python files can be imported from (they run unmodified through oracle/fairseq_stub):
+    FHB_REFERENCE, /root/reference (the build container) or baseline/_ref; None on a box that has neither."""
+    for r in (os.environ.get("FHB_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if r and os.path.isfile(os.path.join(r, "modules", "model.py")):
+            return r
+    return None
+
+
+def cpu_reference_classes_step_fn(ref, n_utts, Lmax, seed=1234):
+    """cpu_baseline.kind = "reference": the reference's OWN classes (modules/model.py CustomStudentModel, and its
+    ConvFeatureExtractionModel / TransformerEncoder wired as HuBERT-Base, oracle/gen_golden.RefTeacher) imported
+    unmodified through the fairseq stub, the restated loss and optimizer step around them (train.py / s3prl cannot be
+    imported: Lightning and s3prl are absent).  Same workload and weights-by-key as the port."""
+    import torch
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "fairseq_stub"), ref, os.path.join(ROOT, "oracle")]
+    os.environ["FHB_REFERENCE"] = ref
+    import fhb_oracle as O
+    import gen_golden as GG  # imports the reference modules
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ycfg = yaml_cfg()["distiller"]
+    student = GG.CustomStudentModel(GG.CustomStudentModelConfig(**ycfg))
+    student.load_state_dict(O.init_student_state(O.student_config(), 0))
+    tcfg = O.teacher_config()
+    teacher = GG.RefTeacher(tcfg)
+    teacher.load_state_dict(O.init_teacher_state(tcfg, 1))
+    student.eval()  # dropout identity, like the port
+    teacher.eval()
+    lengths = synth_lengths(CFG2["B"], Lmax, seed)[:n_utts]
+    lengths[0] = Lmax
+    x, pm = O.synth_batch(n_utts, Lmax, lengths, seed)
+    w = O.layer_weights(12, 0.1)
+    params = {k: p for k, p in student.named_parameters()}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in params.items()}
+    state = {"step": 0}
+
+    def step():
+        with torch.no_grad():
+            t = teacher(x, pm)
+        s_ = student(source=x, padding_mask=pm)
+        loss, _ = O.distill_loss(s_["projections"], t["layer_results"], w)
+        loss.backward()
+        state["step"] += 1
+        with torch.no_grad():
+            for k, p in params.items():
+                if p.grad is None:
+                    continue
+                O.adamw_step(p, p.grad, m[k], v2[k], state["step"], 5e-4)
+                p.grad = None
+        return float(loss)
+
+    return step, sum(lengths) / SR, torch.get_num_threads()
+
+
+def cpu_arm(n_utts, Lmax):
+    """(step fn, audio seconds per step, cores, kind)"""
+    ref = reference_root()
+    if ref is not None:
+        try:
+            return (*cpu_reference_classes_step_fn(ref, n_utts, Lmax), "reference")
+        except Exception as e:  # noqa: BLE001 - the port is always available
+            sys.stderr.write(f"bench: reference classes unavailable ({type(e).__name__}: {e}); timing the oracle port\n")
+    return (*cpu_reference_step_fn(n_utts, Lmax), "port")
+
+
 def cpu_reference_step_fn(n_utts, Lmax, seed=1234):
     """The reference's algorithm for this path, restated (oracle/fhb_oracle.py), fp32 on the host cores:
     teacher fwd + student fwd/bwd + loss + AdamW for `n_utts` utterances of the cfg-2 length distribution."""
@@ -176,7 +243,7 @@ def run_reference(args):
     if rank != 0:
         return
     n_utts = 2
-    step, audio_s, cores = cpu_reference_step_fn(n_utts, CFG2["Lmax"])
+    step, audio_s, cores, kind = cpu_arm(n_utts, CFG2["Lmax"])
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -191,7 +258,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg-2: FitHuBERT distillation step, 32 x 15.6 s per GPU (bounded CPU sample)",
                    "per_gpu_batch": 32, "utterance_s": 15.6},
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -266,6 +333,142 @@ def measure_student_fwd(dev, B, Lmax, Lmin, steps, warmup, seed, world):
     }
 
 
+def measure_membound(dev, step_obj, peak_gbs):
+    """HBM-bound kernels of the step at their cfg-2 shapes, each timed ALONE with CUDA events (L2 flushed before every
+    launch by writing a 512 MB buffer): algorithmic bytes, microseconds, GB/s and the fraction of the
+    measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)."""
+    import torch
+    from fithubert_b200 import kernels as K, lib as L
+    f16, f32 = torch.float16, torch.float32
+    flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
+    rows_t, Et, rows_s, Es = 32 * 779, 768, 32 * 389, 480
+    rnd = lambda *sh, dt=f16: torch.randn(*sh, device=dev, dtype=f32).to(dt)
+    out = []
+
+    def run(name, nbytes, fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = sorted(ts)[len(ts) // 2]
+        gbs = nbytes / us / 1e3
+        out.append({"kernel": name, "bytes": int(nbytes), "us": round(us, 1), "gbs": round(gbs, 1),
+                    "frac": round(gbs / peak_gbs, 3)})
+
+    g, b = torch.ones(Et, device=dev), torch.zeros(Et, device=dev)
+    x, y = rnd(rows_t, Et), torch.empty(rows_t, Et, device=dev, dtype=f16)
+    run("layernorm_fwd (teacher 24928 x 768, fp16 in/out)", 4 * rows_t * Et, lambda: K.layernorm_fwd(x, g, b, y))
+    gs, bs = torch.ones(Es, device=dev), torch.zeros(Es, device=dev)
+    x32, y16, y32 = rnd(rows_s, Es, dt=f32), torch.empty(rows_s, Es, device=dev, dtype=f16), torch.empty(rows_s, Es, device=dev)
+    mean, rstd = torch.empty(rows_s, device=dev), torch.empty(rows_s, device=dev)
+    run("layernorm_fwd32 (student 12448 x 480, fp32 in, fp16 + fp32 out)", 10 * rows_s * Es,
+        lambda: K.layernorm_fwd32(x32, gs, bs, y16, y32, mean, rstd))
+    d32, d16 = rnd(rows_s, Es, dt=f32), rnd(rows_s, Es)
+    o16, o32 = torch.empty_like(d16), torch.empty_like(d32)
+    dg, db, dsum = (torch.zeros(Es, device=dev) for _ in range(3))
+    run("layernorm_bwd32 (student, fp32 + fp16 grads in, fp16 + fp32 out)", 16 * rows_s * Es,
+        lambda: K.layernorm_bwd32(d32, x32, gs, mean, rstd, dg, db, dy2=d16, dx=o16, dx32=o32, dxsum=dsum))
+    del x, y, x32, y16, y32, d32, d16, o16, o32
+    # conv layer 0 (+ GroupNorm + GELU): teacher C = 512, student C = 128 with the saved gelu'
+    Bq, Lq = 32, 249600
+    T0 = (Lq - 10) // 5 + 1
+    wave = 0.1 * torch.randn(Bq, Lq, device=dev)
+    for C0, gp, name in ((512, False, "teacher"), (128, True, "student, + saved gelu'")):
+        w0, gm, bt = torch.randn(C0, 1, 10, device=dev) * 0.3, torch.ones(C0, device=dev), torch.zeros(C0, device=dev)
+        stat = torch.empty(Bq, 65, device=dev, dtype=torch.float64)
+        m0, r0 = torch.empty(Bq, C0, device=dev), torch.empty(Bq, C0, device=dev)
+        yo = torch.empty(Bq, T0, C0, device=dev, dtype=f16)
+        go = torch.empty_like(yo) if gp else None
+        nb = 2 * Bq * Lq * 4 + Bq * T0 * C0 * 2 * (2 if gp else 1)
+        run(f"conv0_gn_gelu_fwd ({name}: stats + normalise, {C0} ch)", nb,
+            lambda: K.conv0_fwd(wave, w0, gm, bt, T0, stat, m0, r0, yo, gp_out=go), reps=3)
+        del yo, go
+    # loss + gradient over the 12 stacked projections
+    n, Tq, D = 12, 778, 768
+    pred, tgt = rnd(n, Bq, Tq, D), rnd(n, Bq, 779, D)
+    wl, ll = torch.full((n,), 0.1, device=dev), torch.zeros(n, device=dev)
+    dcs = torch.zeros(n, D, device=dev)
+    run("distill_loss_fwd_bwd (12 x 32 x 778 x 768: read pred + tgt, write dpred)", 3 * n * Bq * Tq * D * 2,
+        lambda: K.distill_loss(pred, tgt, wl, ll, pred, n, Bq, Tq, 779, D, 0, 1.0, dbias=dcs, dbias_layer_stride=D), reps=3)
+    del pred, tgt
+    # AdamW over the student's own flat buffers
+    opt = step_obj.optimizer
+    opt.step_count += 0
+    P_, W_, G_ = step_obj.student_model.engine_state(True)
+    if opt._table is None:
+        opt._build()
+    m_keep, v_keep = opt.m.clone(), opt.v.clone()  # lr = 0, wd = 0: parameters stay, the moments are restored
+    run("adamw_multi (31.2 M parameters: p, g, m, v)", 28 * G_.numel,
+        lambda: K.adamw_multi(opt._table, opt._n, opt._max_n, 0.0, 0.9, 0.98, 1e-6, 0.0, 1, 0, 1.0), reps=3)
+    opt.m.copy_(m_keep)
+    opt.v.copy_(v_keep)
+    gcol = rnd(rows_s, 3 * Es)
+    cs = torch.zeros(3 * Es, device=dev)
+    run("colsum (12448 x 1440 fp16 -> fp32 bias gradient)", rows_s * 3 * Es * 2, lambda: K.colsum(gcol, cs))
+    return out
+
+
+def measure_gpu_eager(dev, B, Lmax, lengths_seed):
+    """The bar SURVEY 2.2 names: the same distillation step in plain PyTorch eager on this GPU (cuDNN / cuBLAS /
+    torch SDPA-free manual attention exactly as the reference computes it), fp16 autocast like the reference's AMP
+    recipe.  The restated reference arithmetic (oracle/fhb_oracle.py) runs on CUDA tensors; one warm-up + two timed
+    steps, outside every other timed region.  A reported baseline, like cpu_baseline."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fhb_oracle as O
+    scfg, tcfg = O.student_config(), O.teacher_config()
+    ssd = {k: v.to(dev).requires_grad_(k not in ("upsampler.weight", "upsampler.bias"))
+           for k, v in O.init_student_state(scfg, 0).items()}
+    tsd = {k: v.to(dev) for k, v in O.init_teacher_state(tcfg, 1).items()}
+    lengths = synth_lengths(B, Lmax, lengths_seed)
+    x, pm = O.synth_batch(B, Lmax, lengths, lengths_seed)
+    x, pm = x.to(dev), pm.to(dev)
+    w = O.layer_weights(12, 0.1)
+    opt = torch.optim.AdamW([p for p in ssd.values() if p.requires_grad], lr=5e-4, betas=(0.9, 0.98), eps=1e-6,
+                            weight_decay=1e-6, fused=True)
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 16)
+    # the oracle's mask helpers build CPU tensors: give them the device through torch's default
+    prev = torch.get_default_device() if hasattr(torch, "get_default_device") else None
+    torch.set_default_device(dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.float16):
+            with torch.no_grad():
+                t = O.teacher_forward(tsd, tcfg, x, pm)
+            s_ = O.student_forward(ssd, scfg, x, pm)
+            loss, _ = O.distill_loss(s_["projections"], t["layer_results"], w)
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        return loss
+
+    try:
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        n = 2
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+    finally:
+        torch.set_default_device(prev if prev is not None else "cpu")
+    del ssd, tsd, opt
+    torch.cuda.empty_cache()
+    return {"value": sum(lengths) / SR / (ms / 1e3), "unit": "audio-s/s", "ms_per_step": ms, "dtype": "fp16 autocast (torch.amp)",
+            "what": "restated reference arithmetic in PyTorch eager (cuDNN conv1d, cuBLAS linear / bmm, fused AdamW) on the "
+                    "same GPU and batch; 1 warm-up + 2 timed steps"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -274,6 +477,8 @@ def main():
     ap.add_argument("--impl", default="fhb")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-student-fwd", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager GPU baseline leg")
+    ap.add_argument("--no-membound", action="store_true", help="skip the per-kernel HBM table")
     ap.add_argument("--profile", action="store_true", help="2 device steps then exit (for ncu launch lists)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
                     help="cfg2 (default, the bench line): distillation step 32 x 15.6 s; cfg4: UpstreamExpert "
@@ -298,6 +503,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the overlapped gradient all-reduce shares the GPU with the backward: a handful of NCCL CTAs is plenty for
+        # 125 MB over NVLink, and the persistent kernels leave exactly that many SMs free (FHB_COMM_SMS)
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("FHB_COMM_SMS", "8"))
         dist.init_process_group("nccl", device_id=dev)
     import fithubert_b200 as F
     from fithubert_b200 import kernels as K
@@ -310,7 +518,7 @@ def main():
         out = measure_student_fwd(dev, B, Lmax, CFG4["Lmin"], args.steps, max(args.warmup, 3), 1234 + rank, world)
         if rank == 0:
             out.update({"n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                        "dtype": "bf16", "data": "synthetic"})
+                        "dtype": "fp16", "data": "synthetic"})
             print(json.dumps(out))
         if world > 1:
             dist.destroy_process_group()
@@ -357,6 +565,7 @@ def main():
         time.sleep(0.3)  # let nvidia-smi come up; the rows kept are those taken under load (see stop())
     barrier()  # after rank 0's sleep: no rank may enter the timed region while another is still outside it
     K.reset_counters()
+    step_obj.comm_events = [] if world > 1 else None  # CUDA-event pairs around the main stream's wait for the all-reduce
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     for _ in range(args.steps):
@@ -364,6 +573,8 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    comm_ms = sum(a.elapsed_time(b) for a, b in (step_obj.comm_events or [])) / max(1, args.steps)
+    step_obj.comm_events = None
     launches = K.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(ll.sum())
@@ -416,10 +627,10 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_s * 1e3, comm_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, comm_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -437,7 +648,9 @@ def main():
     out = {
         "metric": "distill-step audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "precision": "fp16 storage (weights, activations, loss-scaled gradients), fp32 accumulate, fp32 student residual "
+                     "stream / statistics / parameter gradients / optimizer state",
         "config": {"workload": f"{wl_name} + student fwd/bwd + "
                                f"loss + allreduce + AdamW), {B} x {Lmax / SR:.1f} s per GPU, random-init weights",
                    "per_gpu_batch": B, "global_batch": B * world, "utterance_s": Lmax / SR,
@@ -448,6 +661,7 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4 + 4 * B, "d2h_bytes_per_step": 4,
                 "api": "W2V2Distil.training_step({'x','padding_mask'}) with pinned host tensors"},
         "gpu_launches": launches,
+        "comm_exposed_ms": comm_ms if world > 1 else 0.0,  # main-stream time spent waiting for the gradient all-reduce
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": {"bound": "tensor", "kernel": "fhb_gemm_kernel (tcgen05, all variants)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
@@ -465,18 +679,31 @@ def main():
         sf = measure_student_fwd(dev, CFG4["B"], CFG4["Lmax"], CFG4["Lmin"], args.steps, 3, 1234, 1)
         out["student_fwd"] = {k: sf[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches")}
         out["student_fwd"]["workload"] = sf["config"]["workload"]
+    if args.workload == "cfg2" and world == 1 and not args.no_membound:
+        try:
+            hbm = float(peaks.get("hbm_gbs", 6545.0))
+            out["membound"] = {"peak_gbs": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
+                               "kernels": measure_membound(dev, step_obj, hbm)}
+        except Exception as e:  # noqa: BLE001 - a diagnostic table must not cost the bench line
+            out["membound"] = {"error": f"{type(e).__name__}: {e}"}
+    if args.workload == "cfg2" and world == 1 and not args.no_eager:
+        try:
+            out["gpu_eager_baseline"] = measure_gpu_eager(dev, B, Lmax, 1234)
+        except Exception as e:  # noqa: BLE001
+            out["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
     if not args.no_cpu_baseline:
         n_utts = 2
-        stepf, a_s, cores = cpu_reference_step_fn(n_utts, Lmax)
+        stepf, a_s, cores, kind = cpu_arm(n_utts, Lmax)
         stepf()
         t0 = time.perf_counter()
         n = 3
         for _ in range(n):
             stepf()
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": a_s * n / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                               "sample": f"{n_utts} of the {B} utterances ({Lmax / SR:.1f} s each), fp32 oracle, "
-                                         f"1 warm-up + {n} timed full steps"}
+        out["cpu_baseline"] = {"value": a_s * n / dt, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                               "sample": f"{n_utts} of the {B} utterances ({Lmax / SR:.1f} s each), fp32 "
+                                         f"{'reference classes through the fairseq stub' if kind == 'reference' else 'oracle port'}"
+                                         f", 1 warm-up + {n} timed full steps"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

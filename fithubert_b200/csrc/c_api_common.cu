@@ -38,3 +38,14 @@ extern "C" int fhb_set_pdl(int mode) {
   g_pdl = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return prev;
 }
+
+// SMs the persistent kernels leave alone (fhb_num_sms() = device SMs - reserved): while a gradient all-reduce runs
+// beside the backward, NCCL's few CTAs get SMs of their own instead of delaying CTAs of a statically scheduled GEMM.
+// Process-wide launch configuration like the PDL mode above (the data path itself holds no mutable state).
+static int g_reserved_sms = 0;
+int fhb_reserved_sms() { return g_reserved_sms; }
+extern "C" int fhb_set_reserved_sms(int n) {
+  const int prev = g_reserved_sms;
+  g_reserved_sms = n < 0 ? 0 : (n > 64 ? 64 : n);
+  return prev;
+}

@@ -33,7 +33,8 @@ void fhb_set_error(const char* fmt, ...);
 int fhb_make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, const int64_t dim[3], const int64_t stride[2],
                           uint32_t box0, uint32_t box1, const char* name);
 
-// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
+int fhb_reserved_sms();  // c_api_common.cu (fhb_set_reserved_sms)
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs) minus the reserved ones
 static inline int fhb_num_sms() {
   static int cache[64] = {0};
   int dev = 0;
@@ -44,7 +45,8 @@ static inline int fhb_num_sms() {
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
     n = v > 0 ? v : 148;
   }
-  return n;
+  const int r = fhb_reserved_sms();
+  return n - r > 8 ? n - r : n;
 }
 
 // Runs `stmt` the first time this call site is reached on each device (function attributes such as the dynamic

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from . import engine as E
 from . import kernels as K
+from . import lib as L
 from .config import CustomStudentModelConfig
 from .model import CustomStudentModel, TeacherModel, TeacherWrapper, conv_out_lengths, freeze_model, _lengths_from_mask
 from .optim import FusedAdamW, GradAllReduce
@@ -289,12 +290,23 @@ class W2V2Distil(nn.Module):
                            grad_scale * self.rec_loss_weight, dbias=dcs, dbias_layer_stride=D if fused else 0)
             if self.rec_loss_weight != 1.0:
                 layer_loss = layer_loss * self.rec_loss_weight
+        # data-parallel: the gradient all-reduce runs UNDER the backward by default (Lightning DDP's overlap,
+        # train.py:494).  Buckets are issued on a side stream as the backward finalises them - heads, then every second
+        # transformer layer, the front end last (optimizer_step) - and the persistent kernels leave a few SMs to NCCL's
+        # CTAs (fhb_set_reserved_sms) so that neither side waits for the other's SMs.  FHB_EARLY_REDUCE=0: one exchange
+        # after the backward.
         hook = None
-        if self.reducer is not None and self.reducer.enabled and self._micro == self.accumulate - 1 and \
-                os.environ.get("FHB_EARLY_REDUCE", "0") == "1" and not self.split_head:
-            first = G.entries[f"encoder.layers.{1 if sm._geom.tr else 0}.self_attn.q_proj.weight"][0]
-            hook = lambda: self.reducer.reduce_tail(G.flat, first)  # noqa: E731
-        E.student_backward(P, W, sm._geom, G, c, dpred, dpred_colsum=dcs, on_layers_done=hook)
+        overlap = self.reducer is not None and self.reducer.enabled and self._micro == self.accumulate - 1 and \
+            os.environ.get("FHB_EARLY_REDUCE", "1") == "1" and not self.split_head
+        if overlap:
+            self.reducer._full = G.flat.numel()
+            hook = lambda off: self.reducer.reduce_tail(G.flat, off)  # noqa: E731
+            prev_reserved = L.lib().fhb_set_reserved_sms(int(os.environ.get("FHB_COMM_SMS", "8")))
+        try:
+            E.student_backward(P, W, sm._geom, G, c, dpred, dpred_colsum=dcs, on_progress=hook)
+        finally:
+            if overlap:
+                L.lib().fhb_set_reserved_sms(prev_reserved)
         G.loss_scale = S
         return layer_loss
 
@@ -370,8 +382,17 @@ class W2V2Distil(nn.Module):
             if (self.train_cfg["distil_random_layer"] > 0 and not self.split_head) else per.sum()
         return {"v_loss": loss}
 
+    comm_events = None  # bench.py: a list collecting (start, end) CUDA events of the exposed all-reduce wait
+
     def optimizer_step(self):
         _, _, G = self.student_model.engine_state(True)
+        ev = None
+        if self.comm_events is not None and self.reducer.enabled:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         self.reducer.reduce_all(G.flat)
         self.reducer.wait()
+        if ev is not None:
+            ev[1].record()
+            self.comm_events.append(ev)
         self.optimizer.step(grad_scale=1.0 / (self.reducer.world * (self._loss_scale or 1.0)))

@@ -867,11 +867,14 @@ def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc:
 
 def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torch.Tensor,
                      dlayers: Optional[List[Optional[torch.Tensor]]] = None,
-                     dpred_colsum: Optional[torch.Tensor] = None, on_layers_done=None):
+                     dpred_colsum: Optional[torch.Tensor] = None, on_layers_done=None, on_progress=None):
     """Backward of student_forward(train=True, heads='all').  dpred: [n_layers, B, T', D] bf16 gradient of
     the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer.
     dpred_colsum: fp32 [n_layers, D] column sums of dpred over (B, T') if the loss kernel already produced them
-    (batched-heads path only); both head bias gradients are derived from them (fhb_head_bias_grads)."""
+    (batched-heads path only); both head bias gradients are derived from them (fhb_head_bias_grads).
+    on_progress(offset): called whenever flat[offset:] of the gradient buffer has become final - after the heads and
+    then after every second transformer layer (the buffer is laid out front end, layers 0..n-1, heads, and the backward
+    walks it from the end) - so that a data-parallel caller can start reducing that part under the rest of the pass."""
     E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
     B, T, Ts, Tq = c.B, c.T, c.Ts, c.Tq
     dev = c.lay.device
@@ -1049,6 +1052,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
             K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
                            accumulate=True)
+        if on_progress is not None and (l % 2 == 0 or l == g.n_layers - 1):
+            aside.join()
+            on_progress(G_.entries[p + "self_attn.q_proj.weight"][0])
         if l > 0:
             dx32 = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1_32, out_dtype=f32)
         else:  # what leaves the encoder layers feeds bf16 GEMM operands (TR conv / prologue backward)

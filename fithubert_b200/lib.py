@@ -101,7 +101,7 @@ def _declare(l):
 
 # every symbol include/fhb.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "fhb_last_error", "fhb_abi_version", "fhb_set_pdl", "fhb_gemm", "fhb_conv0_gn_gelu_fwd", "fhb_conv0_gn_gelu_bwd", "fhb_conv0_im2col", "fhb_conv0_bwd_finalize",
+    "fhb_last_error", "fhb_abi_version", "fhb_set_pdl", "fhb_set_reserved_sms", "fhb_gemm", "fhb_conv0_gn_gelu_fwd", "fhb_conv0_gn_gelu_bwd", "fhb_conv0_im2col", "fhb_conv0_bwd_finalize",
     "fhb_layernorm_fwd", "fhb_layernorm_bwd", "fhb_layernorm_fwd32", "fhb_layernorm_bwd32", "fhb_posconv_pack", "fhb_posconv_wn_prep",
     "fhb_posconv_finish_fwd", "fhb_posconv_finish_bwd", "fhb_posconv_unpack_bwd", "fhb_posconv_wn_bwd",
     "fhb_attn_fwd", "fhb_attn_bwd", "fhb_distill_loss_fwd_bwd", "fhb_distill_loss_sim_fwd_bwd", "fhb_adamw_multi", "fhb_prep_multi",

@@ -376,10 +376,16 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             projections, x = None, preds[0]
         else:
             projections, x = None, c.x_last.view(B, Ts, Em)
+        feats = c.feats.view(B, T, Em)
+        if mask is not None and not (self.training and self._drop_p["p_input"] > 0.0):
+            # `features` aliases the encoder's input in the reference (modules/model.py:483,489): when dropout_input is an
+            # identity, the encoder's in-place index_put(x, padding_mask, 0) (modules/module.py:273-274) zeroes the padded
+            # frames of the returned tensor too; with dropout live it is a copy and they stay as computed
+            feats = feats.masked_fill(mask.unsqueeze(-1), 0.0)
         return {
             "x": x,
             "padding_mask": mask,
-            "features": c.feats.view(B, T, Em),
+            "features": feats,
             "layer_results": layer_results,
             "tr_layer_results": [] if c.tr is None else [c.tr.view(B, Ts, Em).transpose(0, 1)],
             "projections": projections,

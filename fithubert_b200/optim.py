@@ -98,8 +98,8 @@ class GradAllReduce:
         self._handles = []
 
     def bucket_bounds(self, numel: int, start: int = 0):
-        """Bucket boundaries over flat[start:numel]; bucket size = ceil(total / n_buckets) whatever the range."""
-        step = -(-numel // self.n_buckets)
+        """Bucket boundaries over flat[start:numel]; bucket size = ceil(buffer size / n_buckets) whatever the range."""
+        step = -(-max(numel, getattr(self, "_full", numel)) // self.n_buckets)
         step = (step + 3) // 4 * 4
         return [(a, min(a + step, numel)) for a in range(start, numel, step)]
 
@@ -115,12 +115,17 @@ class GradAllReduce:
                 dist.all_reduce(flat[a:b])
 
     def reduce_tail(self, flat: torch.Tensor, start: int):
-        """flat[start:] is final (the transformer layers' and heads' gradients, once the backward has passed the
-        encoder): reduce it now, under the rest of the backward.  reduce_all() then only sends flat[:start]."""
+        """flat[start:] is final (backward fills the buffer from its end: heads, then layers 12..1, then the front end):
+        reduce the part not sent yet, flat[start : previous start], now - under the rest of the backward.  reduce_all()
+        sends what is left."""
         if not self.enabled:
             return
         start = start // 4 * 4
-        self._issue(flat, start, flat.numel())
+        hi = getattr(self, "_tail_from", None)
+        hi = flat.numel() if hi is None else hi
+        if start >= hi:
+            return
+        self._issue(flat, start, hi)
         self._tail_from = start
 
     def reduce_all(self, flat: torch.Tensor):
@@ -129,7 +134,8 @@ class GradAllReduce:
             return
         hi = getattr(self, "_tail_from", None)
         self._tail_from = None
-        self._issue(flat, 0, flat.numel() if hi is None else hi)
+        if hi is None or hi > 0:
+            self._issue(flat, 0, flat.numel() if hi is None else hi)
 
     def wait(self):
         if self.enabled and self.stream is not None:

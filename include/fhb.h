@@ -34,6 +34,9 @@ int fhb_abi_version(void);
  * overlaps its prologue with the previous kernel's tail and waits (griddepcontrol.wait) before its first global-memory
  * access.  Returns the previous mode.  Per-kernel event timing switches it off. */
 int fhb_set_pdl(int mode);
+/* Leave `n` SMs (0 ... 64) out of the grids of the persistent kernels (GEMM, LayerNorm, ...): room for the few CTAs of a
+ * gradient all-reduce that overlaps the backward pass (Lightning DDP's overlap, train.py:494).  Returns the previous n. */
+int fhb_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
  * D[ob][m][n] = epilogue( sum_{cb,k} A[ob,cb][m][k] * B[ob,cb][n][k] )        bf16 x bf16 -> fp32

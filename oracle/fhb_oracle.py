@@ -7,9 +7,10 @@ package fithubert_b200/ never does (it fails loudly without its CUDA library).
 
 Parity pin: the reference ships no tests or golden vectors, so
 this oracle is pinned against the *reference's own files executed unmodified* through
-oracle/fairseq_stub (oracle/gen_golden.py -> tests/golden/*.pt, and the live check in
-tests/test_oracle_vs_reference.py when /root/reference is present), and the teacher
-additionally against torchaudio.models.hubert_base.  The optimizer (s3prl, source not
+oracle/fairseq_stub (oracle/gen_golden.py -> tests/golden/*.pt, and the live check
+tests/test_oracle_pins.py::test_oracle_matches_the_reference_classes_live when
+/root/reference is present), and the teacher additionally against
+torchaudio.models.hubert_base (tests/test_oracle_pins.py).  The optimizer (s3prl, source not
 available anywhere in this image) is restated from its published algorithm:
 "parity unpinned" for that one function.  calculate_loss (train.py:236-405) cannot be
 executed either (train.py imports Lightning and s3prl at module level): distill_loss /
@@ -214,7 +215,11 @@ def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
     feats = F.layer_norm(feats, (C,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
     mask = mask_m1(padding_mask, T, conv_layers)
     feats = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
-    features_to_distill = feats
+    # modules/model.py:483,489: `features_to_distill = features` is an ALIAS, and with dropout_input an identity (eval
+    # mode, or p = 0: nn.Dropout then returns its input) the encoder's in-place index_put(x, padding_mask, 0)
+    # (modules/module.py:273-274) writes through it: the returned `features` have their padded frames zeroed.  (In
+    # training mode with p > 0 dropout makes a copy and `features` stay un-zeroed; this oracle restates dropout = identity.)
+    features_to_distill = feats if mask is None else feats.masked_fill(mask.unsqueeze(-1), 0.0)
     x = encoder_prologue(sd, feats, mask, cfg).transpose(0, 1)  # [T,B,C]
     tr = bool(cfg.get("enable_tr_layer", True))
     tr_layer_results = []

@@ -64,7 +64,11 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "distill-step audio-sec/sec" and line["unit"] == "audio-s/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" when the reference's own classes are importable here (/root/reference, through the fairseq stub),
+    # "port" (the oracle restatement) on a box without them
+    import bench
+    assert line["cpu_baseline"]["kind"] == ("reference" if bench.reference_root() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

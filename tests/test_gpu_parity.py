@@ -490,6 +490,8 @@ def test_model_matches_reference_fixture(F, path):
     else:
         assert torch.equal(sr["padding_mask"].cpu(), g["student_mask"])
     assert rel(sr["tr_layer_results"][0], g["student_tr"]) < TOL
+    # `features` alias the encoder input: padded frames come back zeroed when dropout_input is an identity (model.py)
+    assert rel(sr["features"], g["student_features"]) < TOL
     for i, ref in enumerate(g["student_layers"]):
         assert sr["layer_results"][i][0].shape == ref.shape  # [Ts, B, C] time-major like the reference
         assert rel(sr["layer_results"][i][0], ref) < TOL

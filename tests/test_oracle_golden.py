@@ -34,6 +34,7 @@ def test_oracle_matches_reference_fixture(path):
     for i, ref in enumerate(g["student_layers"]):
         assert relerr(s["layer_results"][i][0], ref) < 1e-5
     assert relerr(s["tr_layer_results"][0], g["student_tr"]) < 1e-5
+    assert relerr(s["features"], g["student_features"]) < 1e-5  # padded frames zeroed through the alias (see the oracle)
     for i, ref in enumerate(g["projections"]):
         assert relerr(s["projections"][i], ref) < 1e-5
     loss, per_layer = O.distill_loss(s["projections"], t["layer_results"], g["layer_weights"])
