@@ -33,6 +33,8 @@ void fhb_set_error(const char* fmt, ...);
 int fhb_make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, const int64_t dim[3], const int64_t stride[2],
                           uint32_t box0, uint32_t box1, const char* name);
 
+int fhb_make_tmap_bf16_4d(CUtensorMap* tm, const void* ptr, const int64_t dim[4], const int64_t stride[3], uint32_t box0,
+                          uint32_t box2, const char* name);
 int fhb_reserved_sms();  // c_api_common.cu (fhb_set_reserved_sms)
 // SM count of the CURRENT device (cached per device: one process may drive several GPUs) minus the reserved ones
 static inline int fhb_num_sms() {

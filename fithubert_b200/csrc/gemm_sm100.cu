@@ -747,6 +747,34 @@ int fhb_make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, const int64_t dim[3]
   return make_tmap(tm, t, box0, box1, name);
 }
 
+// 16-bit 4-D map {d0, d1, d2, d3} (strides in elements for d1..d3), box {box0, 1, box2, 1}, 128B swizzle.  box0 may
+// exceed d0: the out-of-range columns are zero-filled by TMA (attention_tc.cu loads 40-wide heads into 64-wide tiles).
+int fhb_make_tmap_bf16_4d(CUtensorMap* tm, const void* ptr, const int64_t dim[4], const int64_t stride[3], uint32_t box0,
+                          uint32_t box2, const char* name) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  for (int i = 0; i < 4; ++i) key.d[i] = dim[i];
+  for (int i = 0; i < 3; ++i) key.s[i] = stride[i];
+  key.box0 = box0; key.box1 = box2; key.kind = 5;
+  if (tmap_lookup(key, tm)) return 0;
+  EncodeTiledFn enc = get_encode_fn();
+  FHB_ARG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  FHB_ARG_CHECK(ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && stride[0] % 8 == 0 && stride[1] % 8 == 0 &&
+                    stride[2] % 8 == 0 && box0 * 2 <= 128 && box2 <= 256,
+                "tensor map %s: 16-bit maps need 16-byte aligned base / strides and a box row of at most 128 bytes", name);
+  cuuint64_t dims[4] = {(cuuint64_t)dim[0], (cuuint64_t)dim[1], (cuuint64_t)dim[2], (cuuint64_t)dim[3]};
+  cuuint64_t strides[3] = {(cuuint64_t)stride[0] * 2, (cuuint64_t)stride[1] * 2, (cuuint64_t)stride[2] * 2};
+  cuuint32_t box[4] = {box0, 1, box2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FHB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", name, (int)r);
+  tmap_insert(key, *tm);
+  return 0;
+}
+
 // fp32, no swizzle: dense [box1][box0] smem rows (TMA reduce-add of partial results, attention_bwd_tc.cu)
 int fhb_make_tmap_f32_3d(CUtensorMap* tm, void* ptr, const int64_t dim[3], const int64_t stride[2], uint32_t box0,
                          uint32_t box1, const char* name) {

@@ -290,6 +290,30 @@ def test_attention_fwd_bwd(F, d, T, amp, short):
         assert rel(dqkv2, q3.grad) < 2e-2
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,T,B,H", [(64, 300, 24, 12), (40, 389, 32, 12), (64, 256, 40, 8)])
+def test_attention_fwd_many_items_per_cta(F, d, T, B, H):
+    """More (query tile, head, sample) items than resident CTAs: the persistent forward pipelines loads and products
+    across item boundaries; ragged lengths leave key halves / tiles empty (valid <= 64, == 128, == 129 ...)."""
+    from fithubert_b200 import kernels as K
+    g = torch.Generator().manual_seed(11)
+    qkv = (1.5 * torch.randn(B, T, 3 * H * d, generator=g)).half().cuda()
+    valid = torch.randint(1, T + 1, (B,), generator=g).tolist()
+    for i, v in enumerate([T, 1, 17, 64, 65, 128, 129, T - 1]):
+        valid[i] = min(v, T)
+    vt = torch.tensor(valid, device="cuda", dtype=torch.int32)
+    out = torch.full((B * T, H * d), float("nan"), device="cuda", dtype=torch.float16)
+    lse = torch.empty(B, H, T, device="cuda")
+    K.attn_fwd(qkv, vt, out, lse, B, T, H, d, d ** -0.5)
+    q, k, v = (t.reshape(B, T, H, d).transpose(1, 2) for t in qkv.float().chunk(3, dim=-1))
+    mask = (torch.arange(T, device="cuda")[None] >= vt[:, None])[:, None, None, :]
+    s = ((q @ k.transpose(-1, -2)) * d ** -0.5).masked_fill(mask, float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, H * d)
+    err = (out.view(B, T, -1).float() - ref).abs().amax(dim=(1, 2)) / ref.abs().amax()
+    assert float(err.max()) < 1e-2, err.tolist()
+    assert float((lse - torch.logsumexp(s, -1)).abs().max()) < 2e-2
+
+
 # ----------------------------------------------------------------------------- dropout (K13)
 def _fmix32(x):
     x = x & 0xFFFFFFFF

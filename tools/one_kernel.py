@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from fithubert_b200 import kernels as K
 
-dev, bf = "cuda", torch.bfloat16
+dev, bf = "cuda", torch.float16
 case = sys.argv[1]
 rnd = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc).to(bf)
 if case == "attn64":
