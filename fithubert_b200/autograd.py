@@ -25,12 +25,17 @@ class _StudentFn(torch.autograd.Function):
         ctx.model, ctx.c, ctx.names = model, c, [n for n, _ in model.named_parameters()]
         ctx.set_materialize_grads(False)  # outputs the loss never touched arrive as None, not as zero tensors
         model._last_ctx = c
-        outs = (c.preds if c.preds is not None else source.new_zeros(0), *c.layers)
+        feats = c.cnn_out if c.cnn_out is not None else c.feats  # the returned `features` (features_to_distill)
+        outs = (c.preds if c.preds is not None else source.new_zeros(0), feats, *c.layers)
         # autograd stamps the RETURNED tensor objects with this node's grad_fn.  The context the backward keeps must not
         # hold those same objects, or node -> ctx -> c -> tensor -> node is a reference cycle no collector sees (every
         # call's saved activations would stay allocated): keep detached aliases instead.
         if c.preds is not None:
             c.preds = c.preds.detach()
+        if c.cnn_out is not None:
+            c.cnn_out = c.cnn_out.detach()
+        else:
+            c.feats = c.feats.detach()
         c.layers = [t.detach() for t in c.layers]
         for s_, t in zip(c.layer_ctx, c.layers):
             s_.out = t
@@ -38,7 +43,7 @@ class _StudentFn(torch.autograd.Function):
         return outs
 
     @staticmethod
-    def backward(ctx, dpreds, *dlayers):
+    def backward(ctx, dpreds, dfeat, *dlayers):
         model, c = ctx.model, ctx.c
         P, W, G = model.engine_state(True)
         G.zero_()
@@ -51,7 +56,10 @@ class _StudentFn(torch.autograd.Function):
             dpreds = dpreds.to(torch.float16).contiguous()
         dl = [None if d is None else (d.float() * scale).to(torch.float16).contiguous() if scale != 1.0 else
               d.to(torch.float16).contiguous() for d in dlayers]
-        E.student_backward(P, W, model._geom, G, c, dpreds, dl)
+        if dfeat is not None:
+            pre_scaled, _FEAT_GRAD_SCALED[0] = _FEAT_GRAD_SCALED[0], False
+            dfeat = ((dfeat.float() * scale) if (scale != 1.0 and not pre_scaled) else dfeat).to(torch.float16).contiguous()
+        E.student_backward(P, W, model._geom, G, c, dpreds, dl, dfeatures=dfeat)
         grads = G.export(scale=scale)
         return (None, None, None, *[grads.get(n) for n in ctx.names])
 
@@ -60,7 +68,7 @@ def student_apply(model, source, valid):
     params = [p for _, p in model.named_parameters()]
     outs = _StudentFn.apply(model, source, valid, *params)
     c = model._last_ctx
-    return c, (outs[0] if c.preds is not None else None), list(outs[1:])
+    return c, (outs[0] if c.preds is not None else None), list(outs[2:]), outs[1]
 
 
 class _DistillLossFn(torch.autograd.Function):
@@ -98,6 +106,42 @@ class _DistillLossFn(torch.autograd.Function):
             _run_loss(ctx.args, scratch, dpred, scale * ctx.scale)
         _PENDING_SCALE[0] = ctx.scale
         return (dpred,) + (None,) * (ctx.n_in - 1)
+
+
+class _FeatureL1Fn(torch.autograd.Function):
+    """CNN-feature loss (train.py:241-246): mean |features - teacher features| and its (loss-scaled) fp16 gradient from
+    the same kernel as the layer losses, run with one "layer".  apply(features [B, T, D], teacher_features, loss_scale)."""
+
+    @staticmethod
+    def forward(ctx, feats, tgt, scale):
+        from . import kernels as K
+        B, T, D = feats.shape
+        assert tgt.shape == feats.shape, "CNN-feature loss: student and teacher features differ in shape"
+        feats, tgt = feats.contiguous(), tgt.contiguous()
+        ctx.scale = float(scale)
+        rec = torch.zeros(1, device=feats.device, dtype=torch.float32)
+        dpred = torch.empty_like(feats)
+        ctx.args = (feats, tgt, B, T, D)
+        K.distill_loss(feats.view(1, B, T, D), tgt.view(1, B, T, D), torch.ones(1, device=feats.device), rec,
+                       dpred.view(1, B, T, D), 1, B, T, T, D, 1, ctx.scale)
+        ctx.save_for_backward(dpred)
+        return rec[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import kernels as K
+        (dpred,) = ctx.saved_tensors
+        w = float(g)  # cnn_loss_weight (x any caller rescaling)
+        if w != 1.0:
+            feats, tgt, B, T, D = ctx.args
+            K.distill_loss(feats.view(1, B, T, D), tgt.view(1, B, T, D), torch.ones(1, device=feats.device),
+                           torch.zeros(1, device=feats.device), dpred.view(1, B, T, D), 1, B, T, T, D, 1, ctx.scale * w)
+        _PENDING_SCALE[0] = ctx.scale
+        _FEAT_GRAD_SCALED[0] = True
+        return dpred, None, None
+
+
+_FEAT_GRAD_SCALED = [False]  # the features gradient about to reach _StudentFn.backward already carries the loss scale
 
 
 def _run_loss(args, rec, dpred, scale):

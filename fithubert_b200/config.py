@@ -99,9 +99,6 @@ class CustomStudentModelConfig:
                 raise NotImplementedError("layerwise_proj=True without a time-reduction layer is not implemented")
         else:
             # DistilHuBERT-style recipe (data/conf/ex.yaml): Linear -> GELU -> SplitLinear on the last layer, no TR layer
-            if self.enable_tr_layer:
-                raise NotImplementedError("layerwise_proj=False with a TR layer (shared upsampler, modules/model.py:"
-                                          "504-505) is not implemented")
             if len(parse_int_list(self.pred_layer_id)) < 2:
                 raise NotImplementedError("the SplitLinear head needs at least two pred_layer_id entries")
         if self.enable_tr_layer:

@@ -4,8 +4,8 @@ Same surface for the hot path: forward(x, padding_mask) -> (student_results, tea
 calculate_loss(student_results, teacher_results, labels=None) -> (total_loss, losses),
 training_step(batch, batch_idx) -> loss, configure_optimizers().  training_step is the FUSED path:
 teacher forward -> student forward -> loss+gradient kernel -> explicit backward, no autograd.
-CTC / attention-map / value-relation / CNN losses are out of scope: requesting them
-raises NotImplementedError.
+The CNN-feature L1 loss (train.py:241-246) is built; CTC / attention-map / value-relation losses are out of scope
+(SURVEY 2.1): requesting them raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -66,8 +66,7 @@ class W2V2Distil(nn.Module):
         self.rec_loss_type, self.sim_loss_weight = t["rec_loss_type"], t["sim_loss_weight"]
         self.attn_loss_weight, self.v_rel_loss_weight = t["attn_loss_weight"], t["v_rel_loss_weight"]
         self.random_layer_weight = t["random_layer_weight"]
-        for name, w in (("cnn_loss_weight", self.cnn_loss_weight), ("attn_loss_weight", self.attn_loss_weight),
-                        ("v_rel_loss_weight", self.v_rel_loss_weight)):
+        for name, w in (("attn_loss_weight", self.attn_loss_weight), ("v_rel_loss_weight", self.v_rel_loss_weight)):
             if w:
                 raise NotImplementedError(f"{name} > 0 is outside the B200 hot path (SURVEY 2.1 / 8f)")
         if self.sim_loss_weight and t["distil_random_layer"] > 0:
@@ -162,6 +161,12 @@ class W2V2Distil(nn.Module):
         else:
             total, per_layer = _DistillLossFn.apply(preds, tgt, self.layer_weights, lt, float(self.rec_loss_weight), 0.0, S)
         losses = self._loss_dict(per_layer)
+        if self.cnn_loss_weight > 0:
+            # CNN post projection loss (train.py:241-246): plain L1 mean between `features` and the teacher's
+            from .autograd import _FeatureL1Fn
+            cnn_loss = _FeatureL1Fn.apply(student_results["features"], teacher_results["features"][0], S)
+            losses = {"cnn_loss": cnn_loss, **losses}
+            total = total + self.cnn_loss_weight * cnn_loss
         return total, losses
 
     def _loss_dict(self, per_layer: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -256,14 +261,14 @@ class W2V2Distil(nn.Module):
             main, side = torch.cuda.current_stream(), E.side_stream(dev)
             side.wait_stream(main)  # the H2D copy of x, the previous step's readers of the target buffer
             with torch.cuda.stream(side):
-                tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
-                                           wave_chunks=chunks)
+                tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
+                                                 wave_chunks=chunks)
             c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
                                   wave_chunks=chunks)
             main.wait_stream(side)
         else:
-            tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
-                                       wave_chunks=chunks)
+            tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
+                                             wave_chunks=chunks)
             c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
                                   wave_chunks=chunks)
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -302,8 +307,26 @@ class W2V2Distil(nn.Module):
             self.reducer._full = G.flat.numel()
             hook = lambda off: self.reducer.reduce_tail(G.flat, off)  # noqa: E731
             prev_reserved = L.lib().fhb_set_reserved_sms(int(os.environ.get("FHB_COMM_SMS", "8")))
+        dfeatures = None
+        self.last_cnn_loss = None
+        if self.cnn_loss_weight > 0:
+            # CNN-feature loss (train.py:241-246,372-378): L1 mean between features_to_distill and the teacher's
+            # post_extract_proj output; the same loss kernel with one "layer", gradient written over the features
+            if c.cnn_out is None:
+                raise NotImplementedError("cnn_loss_weight > 0 without a cnn_proj_head (pred_head_final_dim == "
+                                          "encoder_embed_dim) is only available through calculate_loss / autograd")
+            Dc = c.cnn_out.shape[-1]
+            if Dc != t_feats.shape[-1]:
+                raise ValueError("CNN-feature loss: student features and teacher features differ in width")
+            cnn = torch.zeros(1, device=dev, dtype=torch.float32)
+            one = torch.ones(1, device=dev, dtype=torch.float32)
+            K.distill_loss(c.cnn_out.view(1, B, T, Dc), t_feats.reshape(1, B, T, Dc), one, cnn, c.cnn_out.view(1, B, T, Dc),
+                           1, B, T, T, Dc, 1, grad_scale * self.cnn_loss_weight)
+            dfeatures = c.cnn_out
+            self.last_cnn_loss = cnn[0]
+            layer_loss = torch.cat([layer_loss, cnn * self.cnn_loss_weight])
         try:
-            E.student_backward(P, W, sm._geom, G, c, dpred, dpred_colsum=dcs, on_progress=hook)
+            E.student_backward(P, W, sm._geom, G, c, dpred, dpred_colsum=dcs, on_progress=hook, dfeatures=dfeatures)
         finally:
             if overlap:
                 L.lib().fhb_set_reserved_sms(prev_reserved)
@@ -323,7 +346,7 @@ class W2V2Distil(nn.Module):
         if self._micro == self.accumulate:
             self._micro = 0
             self.optimizer_step()
-        self.last_layer_losses = layer_loss
+        self.last_layer_losses = layer_loss[:self.n_pred]  # (a trailing slot, if present, is cnn_loss_weight * cnn_loss)
         return layer_loss.sum()
 
     def training_epoch_end(self, training_step_outputs=None):
@@ -361,7 +384,7 @@ class W2V2Distil(nn.Module):
         s_valid = None if lengths is None else conv_out_lengths(lengths, sm._conv_layers)
         n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
         Pt, Wt = tm.engine_state()
-        tgt, _ = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, slots=self.tgt_slots)
+        tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, slots=self.tgt_slots)
         was_training = sm.training
         sm.eval()
         P, W, _ = sm.engine_state(sm._weights.train if sm._weights is not None else False)
@@ -376,6 +399,12 @@ class W2V2Distil(nn.Module):
         else:
             K.distill_loss(c.preds, tgt, self.layer_weights, rec, None, n, B, c.Tq, T, D, lt, 0.0)
             per = rec * self.rec_loss_weight
+        if self.cnn_loss_weight > 0 and c.cnn_out is not None:
+            cnn = torch.zeros(1, device=dev, dtype=torch.float32)
+            Dc = c.cnn_out.shape[-1]
+            K.distill_loss(c.cnn_out.view(1, B, T, Dc), t_feats.reshape(1, B, T, Dc), torch.ones(1, device=dev), cnn, None,
+                           1, B, T, T, Dc, 1, 0.0)
+            per = torch.cat([per, cnn * self.cnn_loss_weight])
         # train.py:198-199: with random-layer distillation the monitored value is the last layer's own (un-weighted)
         # feature loss, not the weighted total
         loss = (rec[n - 1] if not self.sim_loss_weight else rec[n - 1] + sim[n - 1]) \

@@ -139,6 +139,8 @@ class WeightSet:
             add(name, f16, (n, 1, kd), [(pn, 0, (kd, 0, 1), 0)])
 
         lin("pp.w", "post_extract_proj.weight", E, g.c_feat)
+        if g.student and "cnn_proj_head.1.weight" in self.params:  # CNN-feature head (modules/model.py:304-310)
+            lin("cnn.w", "cnn_proj_head.1.weight", self.params["cnn_proj_head.1.weight"].shape[0], E)
         off = 0
         if g.tr:
             add("tr.w", f16, (E, 2, E), [("encoder.layers.0.weight", 0, (2 * E, 1, 2), 0)])
@@ -152,6 +154,10 @@ class WeightSet:
             lin(f"l{l}.wo", p + "self_attn.out_proj.weight", E, E)
             lin(f"l{l}.w1", p + "fc1.weight", F, E)
             lin(f"l{l}.w2", p + "fc2.weight", E, F)
+        if g.student and g.n_split and g.tr and "upsampler.weight" in self.params:
+            # shared upsampler in front of the DistilHuBERT head (modules/model.py:341-348,402-404,504-505)
+            add("up.wup", f16, (2, E, E), [("upsampler.weight", 0, (1, 2, 2 * E), 0)])
+            add("up.bup", f32, (2, E, 1), [("upsampler.bias", 0, (0, 1, 0), 0)])
         if g.student and g.n_split and "proj_head.2.weight" in self.params:
             # DistilHuBERT head (modules/module.py:585-619): Linear(E, N * inter) and the SplitLinear weight
             # [N][inter][D] transposed per task to the K-major [D][inter] the forward GEMM consumes
@@ -283,6 +289,9 @@ class GradStore:
                    "encoder.pos_conv.0.bias", "encoder.pos_conv.0.weight_g", "encoder.pos_conv.0.weight_v",
                    "encoder.layer_norm.weight", "encoder.layer_norm.bias"):
             plain(pn)
+        if "cnn_proj_head.1.weight" in params:
+            plain("cnn_proj_head.1.weight")
+            plain("cnn_proj_head.1.bias")
         off = 0
         if g.tr:
             order.append(("encoder.layers.0.weight", (E, E, 2), (2 * E, 1, E)))
@@ -300,6 +309,10 @@ class GradStore:
                        "final_layer_norm.weight", "final_layer_norm.bias"):
                 plain(p + pn)
         if g.n_split and "proj_head.2.weight" in params:
+            if g.tr and "upsampler.weight" in params:
+                # grad stored as dWup[(j, co)][ci]; param element (ci, co, j)
+                order.append(("upsampler.weight", (E, E, 2), (1, E, E * E)))
+                plain("upsampler.bias")
             for pn in ("proj_head.0.weight", "proj_head.0.bias", "proj_head.2.weight", "proj_head.2.bias"):
                 plain(pn)
         for i in range(g.n_layers if not g.n_split else 0):
@@ -471,7 +484,16 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
     c.rstd_f = torch.empty(B * T, device=dev, dtype=f32) if save else None
     K.layernorm_fwd(feat, P["layer_norm.weight"], P["layer_norm.bias"], f_ln, c.mean_f, c.rstd_f)
     c.f_ln = f_ln
-    feats = K.linear(f_ln.view(B * T, Cf), W["pp.w"].view(E, Cf), P["post_extract_proj.bias"])
+    c.cnn_out = c.cnn_g = None
+    if g.student and "cnn.w" in W.views:
+        # CNN-feature head (modules/model.py:304-310,486-487): features_to_distill = Linear(GELU(features)).  ONE GEMM gives
+        # both gelu(features) (D) and the features themselves (the stored pre-activation); the backward recomputes gelu'
+        feats = torch.empty(B * T, E, device=dev, dtype=f16)
+        c.cnn_g = K.linear(f_ln.view(B * T, Cf), W["pp.w"].view(E, Cf), P["post_extract_proj.bias"], gelu=True, preact_out=feats)
+        Dc = P["cnn_proj_head.1.weight"].shape[0]
+        c.cnn_out = K.linear(c.cnn_g, W["cnn.w"].view(Dc, E), P["cnn_proj_head.1.bias"])  # [B*T, Dc]
+    else:
+        feats = K.linear(f_ln.view(B * T, Cf), W["pp.w"].view(E, Cf), P["post_extract_proj.bias"])
     c.feats = feats  # [B*T, E], padded frames NOT zeroed (reference `features_to_distill`)
     d_in = drop.site(DropCfg.SITE_INPUT, drop.p_input) if drop is not None else None
     if d_in is not None:  # dropout_input (modules/model.py:489); `features_to_distill` above stays un-dropped
@@ -706,17 +728,26 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     if g.n_split:
         # DistilHuBERT head on the last layer (modules/model.py:504-518): Linear(E, N * inter) -> GELU -> SplitLinear
         # (modules/module.py:585-619) = one GEMM + one GEMM batched over the N tasks; preds [N, B, T, D]
-        c.Tq, c.head_idx, c.heads_batched, c.preds = Ts, [], False, None
+        c.head_idx, c.heads_batched, c.preds = [], False, None
+        c.x_up = None
+        Tq = Ts
+        if g.tr and "up.wup" in W.views:
+            # shared upsampler (modules/model.py:402-404,504-505): ConvTranspose1d(k=2,s=2) on the encoder output =
+            # GEMM to [B*Ts, 2E] = [B*2Ts, E]; `x` of the result dict is this upsampled tensor
+            Tq = 2 * Ts
+            c.x_up = K.linear(c.x_last, W["up.wup"].view(2 * E, E), W["up.bup"]).view(B * Tq, E)
+        c.Tq = Tq
         if heads == "all":
             N, inter = g.n_split, g.inter
-            c.sp_u = torch.empty(B * Ts, N * inter, device=dev, dtype=f16) if train else None
-            c.sp_h = K.linear(c.x_last, W["sp.w1"].view(N * inter, E), P["proj_head.0.bias"], gelu=True, dgelu_out=c.sp_u)
+            xin = c.x_up if c.x_up is not None else c.x_last
+            c.sp_u = torch.empty(B * Tq, N * inter, device=dev, dtype=f16) if train else None
+            c.sp_h = K.linear(xin, W["sp.w1"].view(N * inter, E), P["proj_head.0.bias"], gelu=True, dgelu_out=c.sp_u)
             if pred_buf is None:
-                pred_buf = torch.empty(N, B, Ts, D, device=dev, dtype=f16)
-            a3 = L.tensor3(c.sp_h, data_ptr=c.sp_h.data_ptr(), dim=(inter, B * Ts, N), stride=(N * inter, inter))
+                pred_buf = torch.empty(N, B, Tq, D, device=dev, dtype=f16)
+            a3 = L.tensor3(c.sp_h, data_ptr=c.sp_h.data_ptr(), dim=(inter, B * Tq, N), stride=(N * inter, inter))
             b3 = L.tensor3(W["sp.w2"], data_ptr=W["sp.w2"].data_ptr(), dim=(inter, D, N), stride=(inter, D * inter))
-            K.gemm_raw(a3, b3, pred_buf, B * Ts, D, inter, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=D,
-                       d_hi_stride=B * Ts * D, flags=L.EPI_BIAS, bias=P["proj_head.2.bias"], bias_hi_stride=D)
+            K.gemm_raw(a3, b3, pred_buf, B * Tq, D, inter, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0), d_ld=D,
+                       d_hi_stride=B * Tq * D, flags=L.EPI_BIAS, bias=P["proj_head.2.bias"], bias_hi_stride=D)
             c.preds = pred_buf
         return c
     # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E]
@@ -867,14 +898,17 @@ def _wgrad(dy3: L.Tensor3, x3: L.Tensor3, out: torch.Tensor, M: int, N: int, Kc:
 
 def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torch.Tensor,
                      dlayers: Optional[List[Optional[torch.Tensor]]] = None,
-                     dpred_colsum: Optional[torch.Tensor] = None, on_layers_done=None, on_progress=None):
+                     dpred_colsum: Optional[torch.Tensor] = None, on_layers_done=None, on_progress=None,
+                     dfeatures: Optional[torch.Tensor] = None):
     """Backward of student_forward(train=True, heads='all').  dpred: [n_layers, B, T', D] bf16 gradient of
     the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer.
     dpred_colsum: fp32 [n_layers, D] column sums of dpred over (B, T') if the loss kernel already produced them
     (batched-heads path only); both head bias gradients are derived from them (fhb_head_bias_grads).
     on_progress(offset): called whenever flat[offset:] of the gradient buffer has become final - after the heads and
     then after every second transformer layer (the buffer is laid out front end, layers 0..n-1, heads, and the backward
-    walks it from the end) - so that a data-parallel caller can start reducing that part under the rest of the pass."""
+    walks it from the end) - so that a data-parallel caller can start reducing that part under the rest of the pass.
+    dfeatures: fp16 gradient wrt the returned `features` (features_to_distill, train.py:241-246): [B*T, D_cnn] when the
+    model has a cnn_proj_head, else [B*T, E]."""
     E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
     B, T, Ts, Tq = c.B, c.T, c.Ts, c.Tq
     dev = c.lay.device
@@ -889,7 +923,7 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     if g.n_split:
         # ---- DistilHuBERT head backward: SplitLinear (batched over the N tasks), GELU, Linear.  dpred [N, B, T, D];
         #      the SplitLinear bias gradient (column sums of dpred) was accumulated by the loss kernel or is summed here
-        N, inter, rows = g.n_split, g.inter, B * Ts
+        N, inter, rows = g.n_split, g.inter, B * Tq
         if dpred_colsum is None:
             K.colsum_batched(dpred.view(N, rows, D), gv("proj_head.2.bias"), D)
         a3 = L.tensor3(c.sp_h, data_ptr=c.sp_h.data_ptr(), dim=(inter, rows, N), stride=(N * inter, inter))
@@ -902,8 +936,15 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         K.gemm_raw(a3, b3, dh, rows, inter, D, b_major=1, num_ob=N, a_coord=(0, 1, 0, 0), b_coord=(0, 1, 0, 0),
                    d_ld=N * inter, d_hi_stride=inter, flags=L.EPI_MUL_AUX, aux_in=c.sp_u)
         K.colsum(dh, gv("proj_head.0.bias"))
-        K.linear_wgrad(dh, c.layers[-1], out=gv("proj_head.0.weight").view(N * inter, E), accumulate=True)
+        xin = c.x_up if getattr(c, "x_up", None) is not None else c.layers[-1]
+        K.linear_wgrad(dh, xin, out=gv("proj_head.0.weight").view(N * inter, E), accumulate=True)
         dx = K.linear_dgrad(dh, W["sp.w1"].view(N * inter, E))
+        if getattr(c, "x_up", None) is not None:
+            # shared upsampler backward: dz [B*2Ts, E] == [B*Ts, 2E]
+            K.colsum(dx, gv("upsampler.bias"))
+            dz2 = dx.view(B * Ts, 2 * E)
+            K.linear_wgrad(dz2, c.layers[-1], out=gv("upsampler.weight").view(2 * E, E), accumulate=True)
+            dx = K.linear_dgrad(dz2, W["up.wup"].view(2 * E, E))
     if gs is not None:
         # ---- all n projection heads at once (ob = head): 2 wgrad + 2 dgrad batched GEMMs, 1-2 column sums
         hs = c.head_strides
@@ -1116,6 +1157,18 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     d_in = drop.site(DropCfg.SITE_INPUT, drop.p_input) if drop is not None else None
     if d_in is not None:
         K.dropout(dfeat, dfeat, *d_in)
+    if dfeatures is not None:
+        # gradient of the CNN-feature loss (train.py:241-246) joins the gradient of `features` AFTER the input dropout
+        # (features_to_distill is taken before it, modules/model.py:483-489)
+        if getattr(c, "cnn_out", None) is not None:
+            Dc = dfeatures.shape[-1]
+            dfe = dfeatures.view(B * T, Dc)
+            K.colsum(dfe, gv("cnn_proj_head.1.bias"))
+            K.linear_wgrad(dfe, c.cnn_g, out=gv("cnn_proj_head.1.weight").view(Dc, E), accumulate=True)
+            dfe = K.linear_dgrad(dfe, W["cnn.w"].view(Dc, E), dgelu_of=c.feats)  # x gelu'(features)
+        else:
+            dfe = dfeatures.view(B * T, E)
+        dfeat = K.add_bf16(dfeat, dfe, torch.empty_like(dfeat))
     # ---- post_extract_proj + LayerNorm(C_feat)
     Cf = g.c_feat
     K.colsum(dfeat, gv("post_extract_proj.bias"))

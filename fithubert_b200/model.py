@@ -215,7 +215,10 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
         self.embed = layers[-1][0]
         self.feature_extractor = ConvFeatureExtractionModel(layers, 0.0, cfg.extractor_mode, cfg.conv_bias)
         self.post_extract_proj = nn.Linear(self.embed, cfg.encoder_embed_dim)
+        # CNN distillation for encoder dimension mismatch (reference modules/model.py:304-310)
         self.cnn_proj_head = None
+        if cfg.pred_head_final_dim != cfg.encoder_embed_dim and cfg._cnn_weight > 0:
+            self.cnn_proj_head = nn.Sequential(nn.GELU(), nn.Linear(cfg.encoder_embed_dim, cfg.pred_head_final_dim))
         self.crop_seq_to_multiple = cfg.crop_seq_to_multiple
         self.feature_grad_mult = cfg.feature_grad_mult
         self.encoder = TransformerEncoder(cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim,
@@ -354,12 +357,13 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             if not self.layerwise_proj and heads != "all":
                 raise NotImplementedError("fine-tuning the SplitLinear recipe without its head is not implemented")
             from .autograd import student_apply
-            c, preds, layers_out = student_apply(self, source, valid)
+            c, preds, layers_out, feats_out = student_apply(self, source, valid)
         else:
             P, W, _ = self.engine_state(False)
             c = E.student_forward(P, W, self._geom, source, valid, train=False, heads=heads, want_lr=True,
                                   drop=self.drop_cfg(), n_run=n_run)
             preds, layers_out = c.preds, c.layers
+            feats_out = c.cnn_out if c.cnn_out is not None else c.feats
         B, T, Ts, Em = c.B, c.T, c.Ts, self._geom.E
         mask = _frame_mask(valid, T, dev)
         layer_results = [(lo.view(B, Ts, Em).transpose(0, 1), None,
@@ -368,7 +372,8 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
         if not self.layerwise_proj:
             # reference modules/model.py:504-518: x stays the encoder output, projections is ONE [B, N, T, D] tensor
             projections = None if preds is None else preds.permute(1, 0, 2, 3)
-            x = c.x_last.view(B, Ts, Em)
+            # with a TR layer the encoder output goes through the shared upsampler first (modules/model.py:504-505)
+            x = c.x_up.view(B, 2 * Ts, Em) if getattr(c, "x_up", None) is not None else c.x_last.view(B, Ts, Em)
         elif heads == "all":
             projections = [preds[i] for i in range(preds.shape[0])]
             x = projections[-1]
@@ -376,8 +381,10 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             projections, x = None, preds[0]
         else:
             projections, x = None, c.x_last.view(B, Ts, Em)
-        feats = c.feats.view(B, T, Em)
-        if mask is not None and not (self.training and self._drop_p["p_input"] > 0.0):
+        feats = feats_out.view(B, T, -1)
+        if c.cnn_out is not None:
+            pass  # cnn_proj_head(features) is a new tensor (modules/model.py:486-487): the in-place zeroing never reaches it
+        elif mask is not None and not (self.training and self._drop_p["p_input"] > 0.0):
             # `features` aliases the encoder's input in the reference (modules/model.py:483,489): when dropout_input is an
             # identity, the encoder's in-place index_put(x, padding_mask, 0) (modules/module.py:273-274) zeroes the padded
             # frames of the returned tensor too; with dropout live it is a copy and they stay as computed

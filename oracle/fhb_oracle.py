@@ -220,6 +220,10 @@ def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
     # (modules/module.py:273-274) writes through it: the returned `features` have their padded frames zeroed.  (In
     # training mode with p > 0 dropout makes a copy and `features` stay un-zeroed; this oracle restates dropout = identity.)
     features_to_distill = feats if mask is None else feats.masked_fill(mask.unsqueeze(-1), 0.0)
+    if "cnn_proj_head.1.weight" in sd:
+        # modules/model.py:304-310,486-487: Sequential(GELU, Linear) applied BEFORE the encoder call - a new tensor, so
+        # the encoder's in-place zeroing never reaches it (padded frames stay as computed)
+        features_to_distill = F.linear(F.gelu(feats), sd["cnn_proj_head.1.weight"], sd["cnn_proj_head.1.bias"])
     x = encoder_prologue(sd, feats, mask, cfg).transpose(0, 1)  # [T,B,C]
     tr = bool(cfg.get("enable_tr_layer", True))
     tr_layer_results = []
@@ -237,15 +241,19 @@ def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
         layer_results.append((x, None, lr))
 
     if not cfg.get("layerwise_proj", True):
-        assert not tr, "the shared-upsampler variant (layerwise_proj=False with a TR layer) is not restated"
         out = x.transpose(0, 1)  # [B, T, E]
+        if tr:
+            # shared upsampler (modules/model.py:341-348,402-404,504-505): ConvTranspose1d(k = s = tr_reduce_factor) on the
+            # encoder output, in front of the head; `x` of the result is the upsampled tensor
+            out = F.conv_transpose1d(out.transpose(1, 2), sd["upsampler.weight"], sd["upsampler.bias"],
+                                     stride=cfg["tr_reduce_factor"]).transpose(1, 2)
         projections = None
         if heads:
             n = sd["proj_head.2.weight"].shape[0]
             h = F.gelu(F.linear(out, sd["proj_head.0.weight"], sd["proj_head.0.bias"]))
-            h = h.reshape(B, T, n, 1, -1)
+            h = h.reshape(B, out.shape[1], n, 1, -1)
             pred = torch.einsum("...klm,kmn->...kln", h, sd["proj_head.2.weight"]).squeeze(3) + sd["proj_head.2.bias"]
-            projections = pred.reshape(B, T, n, -1).permute(0, 2, 1, 3)  # B x N x T x D
+            projections = pred.reshape(B, out.shape[1], n, -1).permute(0, 2, 1, 3)  # B x N x T x D
         return {"x": out, "padding_mask": mask, "features": features_to_distill,
                 "layer_results": layer_results, "tr_layer_results": tr_layer_results, "projections": projections}
 
@@ -448,9 +456,18 @@ def init_student_state(cfg: dict, seed: int = 0, perturb: bool = False) -> State
             sd[f"proj_head.{i}.upsampler.bias"] = uni(E, bound=bt)
             sd[f"proj_head.{i}.lin_proj.weight"] = uni(D, E, bound=1 / math.sqrt(E))
             sd[f"proj_head.{i}.lin_proj.bias"] = uni(D, bound=1 / math.sqrt(E))
+    if cfg.get("_cnn_weight", 0) > 0 and D != E:  # cnn_proj_head = Sequential(GELU, Linear(E, D)), modules/model.py:304-310
+        sd["cnn_proj_head.1.weight"] = uni(D, E, bound=1 / math.sqrt(E))
+        sd["cnn_proj_head.1.bias"] = uni(D, bound=1 / math.sqrt(E))
     if perturb:
         _perturb(sd, gen)
     return sd
+
+
+def cnn_feature_loss(student_features: Tensor, teacher_features: Tensor) -> Tensor:
+    """W2V2Distil.calculate_loss CNN branch, train.py:241-246: plain L1 mean between the student's `features`
+    (features_to_distill) and the teacher's post_extract_proj output."""
+    return F.l1_loss(student_features.float(), teacher_features.float(), reduction="none").mean()
 
 
 def init_teacher_state(cfg: dict, seed: int = 1, perturb: bool = False) -> State:

@@ -191,6 +191,70 @@ def run_case_split(name, s_over, t_over, B, Lmax, lengths, yaml_distiller):
     print(name, "loss", float(loss), "bytes", os.path.getsize(path))
 
 
+TINY_UP_STUDENT = dict(  # layerwise_proj False WITH a TR layer (shared upsampler) + CNN-feature head (D != E, _cnn_weight > 0)
+    conv_feature_layers="[(16, 10, 5)] + [(32, 3, 2)] * 4 + [(32, 2, 2)] * 2",
+    encoder_layers=2, encoder_embed_dim=96, encoder_ffn_embed_dim=96, encoder_attention_heads=4,
+    conv_pos=16, conv_pos_groups=4, pred_head_final_dim=64, pred_layer_id="[0, 2]",
+    init_conv_layers=False, init_encoder_layers=0, enable_tr_layer=True,
+)
+CNN_LOSS_WEIGHT = 0.5
+
+
+def run_case_upsampler_cnn(name, s_over, t_over, B, Lmax, lengths, yaml_distiller):
+    """ex.yaml family with enable_tr_layer True: the encoder output goes through the model's shared `upsampler`
+    (modules/model.py:341-348,402-404,504-505) before the DistilHuBERT head, and - pred_head_final_dim != encoder_embed_dim,
+    _cnn_weight > 0 - `features` come out of cnn_proj_head (modules/model.py:304-310,486-487).  Loss = L1 + cosine over
+    pred_layer_id (train.py:268-314) + cnn_loss_weight * L1(features, teacher features[0]) (train.py:241-246,372-378),
+    restated inline like the other cases.
+    The batch is un-padded on purpose: with a padding mask and dropout_input an identity (eval mode / p = 0) the reference's
+    OWN backward raises - the encoder's in-place index_put (modules/module.py:273-274) overwrites the tensor cnn_proj_head's
+    GELU saved ("modified by an inplace operation"); it only trains with dropout_input live, whose mask cannot be replayed."""
+    torch.manual_seed(0)
+    cfg = ref_student_cfg(yaml_distiller, **s_over)
+    cfg._cnn_weight = CNN_LOSS_WEIGHT  # train.py:43
+    assert not cfg.layerwise_proj and cfg.enable_tr_layer
+    student = CustomStudentModel(cfg)
+    assert student.cnn_proj_head is not None and student.upsampler is not None
+    teacher = RefTeacher(O.teacher_config(**t_over, kind="hubert"))
+    perturb_(student, 31)
+    perturb_(teacher, 32)
+    student.eval()
+    teacher.eval()
+    x, pm = O.synth_batch(B, Lmax, lengths, seed=2468)
+    with torch.no_grad():
+        t_res = teacher(x, pm)
+    s_res = student(source=x, padding_mask=pm)
+    ids = eval(cfg.pred_layer_id)
+    tgt = torch.stack([t_res["layer_results"][i][0].transpose(0, 1) for i in ids], 1)
+    pred = s_res["projections"]
+    tgt = tgt.narrow(2, 0, pred.shape[2])
+    rec = torch.nn.functional.l1_loss(pred, tgt, reduction="none")
+    sim = -torch.nn.functional.logsigmoid(torch.nn.functional.cosine_similarity(pred, tgt, dim=-1))
+    cnn = torch.nn.functional.l1_loss(s_res["features"], t_res["features"][0], reduction="none").mean()
+    loss = 1.0 * rec.mean() + 1.0 * sim.mean() + CNN_LOSS_WEIGHT * cnn
+    loss.backward()
+    out = {
+        "student_cfg": dict(s_over, layerwise_proj=False, feature_grad_mult=cfg.feature_grad_mult),
+        "teacher_cfg": dict(t_over, kind="hubert"), "cnn_loss_weight": CNN_LOSS_WEIGHT,
+        "student_state": {k: v.detach().clone() for k, v in student.state_dict().items()},
+        "teacher_state": {k: v.detach().clone() for k, v in teacher.state_dict().items()},
+        "source": x, "padding_mask": pm, "pred_layer_id": ids,
+        "student_mask": s_res["padding_mask"], "teacher_mask": t_res["padding_mask"],
+        "student_features": s_res["features"].detach(), "teacher_features": t_res["features"][0].detach(),
+        "student_layers": [lr[0].detach() for lr in s_res["layer_results"]],
+        "student_tr": s_res["tr_layer_results"][0].detach(),
+        "x": s_res["x"].detach(), "projections": pred.detach(),
+        "teacher_layers": [lr[0].detach() for lr in t_res["layer_results"]],
+        "loss": loss.detach(), "rec_layer": rec.mean((0, 2, 3)).detach(), "sim_layer": sim.mean((0, 2)).detach(),
+        "cnn_loss": cnn.detach(),
+        "grads": {n: p.grad.detach().clone() for n, p in student.named_parameters() if p.grad is not None},
+        "no_grad_params": [n for n, p in student.named_parameters() if p.grad is None],
+    }
+    path = os.path.join(HERE, "..", "tests", "golden", name + ".pt")
+    torch.save(out, path)
+    print(name, "loss", float(loss), "cnn", float(cnn), "bytes", os.path.getsize(path))
+
+
 def main():
     import yaml
     with open(os.path.join(REF, "data/conf/fithubert.yaml")) as f:
@@ -204,6 +268,7 @@ def main():
     with open(os.path.join(REF, "data/conf/ex.yaml")) as f:
         ecfg = yaml.safe_load(f)["distiller"]
     run_case_split("split_hubert_pad", TINY_SPLIT_STUDENT, TINY_TEACHER, 3, 32000, [32000, 27411, 21000], ecfg)
+    run_case_upsampler_cnn("upsampler_cnn_hubert_nopad", TINY_UP_STUDENT, TINY_TEACHER, 2, 28000, [28000, 28000], ecfg)
 
 
 if __name__ == "__main__":

@@ -704,6 +704,65 @@ def test_split_head_recipe_matches_reference_fixture(F):
     assert out["projections"] is None and out["x"].shape == g["x"].shape
 
 
+def test_shared_upsampler_and_cnn_feature_loss_match_reference_fixture(F):
+    """layerwise_proj False WITH a TR layer - the model's shared `upsampler` in front of the DistilHuBERT head
+    (modules/model.py:341-348,402-404,504-505) - plus cnn_proj_head and the CNN-feature L1 loss (modules/model.py:304-310,
+    486-487; train.py:241-246,372-378), against the fixture the unmodified reference produced: hidden states, the upsampled
+    `x`, projections, `features`, the three loss terms, every parameter gradient (upsampler.* and cnn_proj_head.* included)
+    through the autograd API, and the fused training step."""
+    import bench
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "upsampler_cnn_hubert_nopad.pt"))
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"].update(init_conv_layers=False, init_encoder_layers=0)
+    cfg["train"].update(distil_random_layer=0, random_layer_weight=0, rec_loss_type="l1", rec_loss_weight=1.0,
+                        sim_loss_weight=1.0, cnn_loss_weight=g["cnn_loss_weight"])
+    tc = dict(g["teacher_cfg"])
+    teacher = F.TeacherModel(kind=tc.pop("kind"), **tc)
+    teacher.load_state_dict(g["teacher_state"])
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    student = step.student_model
+    assert set(student.state_dict()) == set(g["student_state"])  # upsampler.*, cnn_proj_head.1.*, proj_head.{0,2}.*
+    student.load_state_dict(g["student_state"])
+    student.eval()
+    x, pm = g["source"], g["padding_mask"]
+    with torch.no_grad():
+        sr = student(x.cuda(), pm)
+        tr = step.teacher_model.extract_features(x.cuda(), pm)
+    assert sr["padding_mask"] is None
+    for i, ref in enumerate(g["student_layers"]):
+        assert sr["layer_results"][i][0].shape == ref.shape and rel(sr["layer_results"][i][0], ref) < TOL
+    assert rel(sr["tr_layer_results"][0], g["student_tr"]) < TOL
+    assert sr["x"].shape == g["x"].shape and rel(sr["x"], g["x"]) < TOL
+    assert sr["projections"].shape == g["projections"].shape and rel(sr["projections"], g["projections"]) < TOL
+    assert sr["features"].shape == g["student_features"].shape and rel(sr["features"], g["student_features"]) < TOL
+    assert rel(tr["features"][0], g["teacher_features"]) < TOL
+    # reference-style API: forward -> calculate_loss -> backward
+    s_res, t_res = step(x.cuda(), pm)
+    total, losses = step.calculate_loss(s_res, t_res)
+    ids = g["pred_layer_id"]
+    assert set(losses) == {"cnn_loss"} | {f"layer{i}" for i in ids}
+    assert abs(float(losses["cnn_loss"]) - float(g["cnn_loss"])) < 2e-2 * float(g["cnn_loss"])
+    assert abs(float(total) - float(g["loss"])) < 2e-2 * float(g["loss"])
+    total.backward()
+    grads = [(n, p.grad) for n, p in student.named_parameters()]
+    assert all(gr is not None for n, gr in grads if n.startswith(("upsampler.", "cnn_proj_head.")))
+    check_grads(grads, g["grads"], "upsampler_cnn", min_count=40)
+    # fused training step: same loss, the new parameters move
+    step.configure_optimizers(total_steps=100)
+    before = {k: student.state_dict()[k].clone() for k in ("upsampler.weight", "cnn_proj_head.1.weight")}
+    loss = step.training_step({"x": x, "padding_mask": pm})
+    assert abs(float(loss) - float(total)) < 1e-3 * float(total)
+    assert abs(float(step.last_cnn_loss) - float(g["cnn_loss"])) < 2e-2 * float(g["cnn_loss"])
+    for k, v in before.items():
+        assert not torch.equal(student.state_dict()[k], v), k
+    # after _disable_projection_heads the expert-style forward still upsamples the encoder output
+    student._disable_projection_heads()
+    with torch.no_grad():
+        out = student(x.cuda(), pm)
+    assert out["projections"] is None and out["x"].shape == g["x"].shape and student.cnn_proj_head is None
+
+
 def test_fit_loop_trains_checkpoints_and_resumes(F, tmp_path):
     """trainer.fit (the Lightning Trainer features the reference uses, train.py:475-509) on a tiny student / teacher and
     synthetic length-bucketed data: the loss goes down, validation runs, Lightning-shaped checkpoints are written,

@@ -83,6 +83,40 @@ def test_oracle_matches_reference_fixture_split_head():
     assert relerr(ssd2[k].grad * 0.1, g["grads"][k]) < 1e-4
 
 
+def test_oracle_matches_reference_fixture_shared_upsampler_and_cnn_loss():
+    """layerwise_proj False WITH a TR layer (the model's shared `upsampler` in front of the DistilHuBERT head,
+    modules/model.py:402-404,504-505) + cnn_proj_head / CNN-feature L1 loss (modules/model.py:304-310, train.py:241-246);
+    fixture from the unmodified reference (oracle/gen_golden.py::run_case_upsampler_cnn; un-padded on purpose, see there)."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "upsampler_cnn_hubert_nopad.pt"))
+    scfg = O.student_config(**g["student_cfg"])
+    tcfg = O.teacher_config(**g["teacher_cfg"])
+    ssd = {k: v.clone().requires_grad_(True) for k, v in g["student_state"].items()}
+    assert set(ssd) == set(O.init_student_state(dict(scfg, pred_layer_id=g["pred_layer_id"], _cnn_weight=g["cnn_loss_weight"])))
+    s = O.student_forward(ssd, scfg, g["source"], g["padding_mask"])
+    with torch.no_grad():
+        t = O.teacher_forward(g["teacher_state"], tcfg, g["source"], g["padding_mask"])
+    assert s["padding_mask"] is None and g["student_mask"] is None
+    for i, ref in enumerate(g["student_layers"]):
+        assert relerr(s["layer_results"][i][0], ref) < 1e-5
+    assert relerr(s["tr_layer_results"][0], g["student_tr"]) < 1e-5
+    assert s["x"].shape == g["x"].shape and relerr(s["x"], g["x"]) < 1e-5          # the UPSAMPLED encoder output
+    assert relerr(s["projections"], g["projections"]) < 1e-5
+    assert s["features"].shape == g["student_features"].shape and relerr(s["features"], g["student_features"]) < 1e-5
+    assert relerr(t["features"][0], g["teacher_features"]) < 1e-5
+    ids = g["pred_layer_id"]
+    preds = {i: s["projections"][:, n] for n, i in enumerate(ids)}
+    loss, rec, sim = O.distill_loss_sim(preds, t["layer_results"], ids, "l1", 1.0, 1.0)
+    cnn = O.cnn_feature_loss(s["features"], t["features"][0])
+    assert abs(float(cnn) - float(g["cnn_loss"])) < 1e-5 * float(g["cnn_loss"])
+    loss = loss + g["cnn_loss_weight"] * cnn
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert g["no_grad_params"] == [] and "upsampler.weight" in g["grads"] and "cnn_proj_head.1.weight" in g["grads"]
+    for n, ref in g["grads"].items():
+        assert ssd[n].grad is not None, n
+        assert float((ssd[n].grad - ref).abs().max()) < 2e-4 * float(ref.abs().max()) + 1e-8, n
+
+
 def test_conv_layer_string_parser():
     assert O.parse_conv_layers(O.FITHUBERT_CONV) == [(128, 10, 5), (256, 1, 1)] + [(256, 3, 2)] * 4 + [(512, 1, 1)] + [(512, 2, 2)] * 2
     assert len(O.parse_conv_layers(O.HUBERT_CONV)) == 7
