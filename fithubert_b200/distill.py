@@ -213,11 +213,11 @@ class W2V2Distil(nn.Module):
         (rec_loss_weight * rec + sim_loss_weight * sim per layer): their sum is the step's total loss."""
         sm, tm = self.student_model, self.teacher_model.model
         dev = sm.post_extract_proj.weight.device
-        chunks = None
+        chunks = x_done = None
         if not x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.shape[0] >= 4:
-            # host batch (what a DataLoader hands over): copied in batch slices on a copy stream; conv layer 0 of the
-            # teacher and of the student start on the first slice while the others are still in flight
-            x, chunks = E.h2d_chunked(x, dev)
+            # host batch (what a DataLoader hands over): copied on a copy stream into a double buffer - under the previous
+            # step when the GPU is still busy with it, else in batch slices that the conv stacks consume as they land
+            x, chunks, x_done = E.h2d_chunked(x, dev)
         else:
             x = x.to(dev, non_blocking=True).float().contiguous()
         Ld = x.shape[1]
@@ -303,10 +303,21 @@ class W2V2Distil(nn.Module):
         hook = None
         overlap = self.reducer is not None and self.reducer.enabled and self._micro == self.accumulate - 1 and \
             os.environ.get("FHB_EARLY_REDUCE", "1") == "1" and not self.split_head
+        prev_reserved = 0
         if overlap:
             self.reducer._full = G.flat.numel()
-            hook = lambda off: self.reducer.reduce_tail(G.flat, off)  # noqa: E731
-            prev_reserved = L.lib().fhb_set_reserved_sms(int(os.environ.get("FHB_COMM_SMS", "8")))
+            comm_sms = int(os.environ.get("FHB_COMM_SMS", "8"))
+            windowed = os.environ.get("FHB_COMM_WINDOW", "1") == "1"
+            prev_reserved = L.lib().fhb_set_reserved_sms(0 if windowed else comm_sms)
+
+            def hook(off):
+                # off: flat[off:] is final -> send it, and leave NCCL its SMs for the next layer's worth of kernels (an
+                # exchange of two layers' gradients is over well within that); None: one layer later -> all SMs back
+                if off is not None:
+                    self.reducer.reduce_tail(G.flat, off)
+                    L.lib().fhb_set_reserved_sms(comm_sms)
+                elif windowed:
+                    L.lib().fhb_set_reserved_sms(0)
         dfeatures = None
         self.last_cnn_loss = None
         if self.cnn_loss_weight > 0:
@@ -331,6 +342,8 @@ class W2V2Distil(nn.Module):
             if overlap:
                 L.lib().fhb_set_reserved_sms(prev_reserved)
         G.loss_scale = S
+        if x_done is not None:
+            x_done.record()  # last reader of the waveform buffer (conv layer 0's backward) is queued
         return layer_loss
 
     def training_step(self, batch, batch_idx=0):

@@ -814,11 +814,19 @@ def side_stream(dev) -> "torch.cuda.Stream":
 _COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
+_H2D_BUFS: Dict[tuple, list] = {}
+
+
 def h2d_chunked(x_host: torch.Tensor, dev, n_chunks: int = 0):
-    """Host -> device copy of a [B, L] fp32 batch in `n_chunks` batch slices on a copy stream.  Returns (x_dev,
-    [(first, last, event)]): consumers wait for a slice's event before touching it (conv_stack_fwd does, slice by slice),
-    so only the first slice's transfer is exposed.  True DMA overlap needs pinned host memory; pageable memory works but
-    is staged by the driver."""
+    """Host -> device copy of a [B, L] fp32 batch on a copy stream, into one of two persistent device buffers per shape
+    (a prefetching loader's double buffer).  Returns (x_dev, chunks, done): consumers wait for a chunk's event before
+    touching it (conv_stack_fwd does, slice by slice), and record `done` on their stream after the last use of x_dev so
+    that the buffer is not overwritten two steps later before they are finished.
+      * GPU still busy with the previous step (the caller does not synchronise every step): ONE copy, issued at once - it
+        does not wait for the queued work, so it runs under the previous step's kernels and the conv stacks run un-sliced;
+      * GPU idle (the caller reads the loss back every step): `n_chunks` batch slices, the conv stacks start on the first
+        one while the others are in flight, so only the first slice's transfer is exposed.
+    True DMA overlap needs pinned host memory; pageable memory works but is staged by the driver."""
     if n_chunks <= 0:
         import os
         n_chunks = int(os.environ.get("FHB_H2D_CHUNKS", "4"))
@@ -827,10 +835,20 @@ def h2d_chunked(x_host: torch.Tensor, dev, n_chunks: int = 0):
     if idx not in _COPY_STREAMS:
         _COPY_STREAMS[idx] = torch.cuda.Stream(device=idx)
     cs = _COPY_STREAMS[idx]
+    key = (idx, tuple(x_host.shape))
+    if key not in _H2D_BUFS:
+        if len(_H2D_BUFS) > 8:  # shapes change with every bucket of a real loader: keep the cache small
+            _H2D_BUFS.clear()
+        _H2D_BUFS[key] = [0, [torch.empty(x_host.shape, device=dev, dtype=f32) for _ in range(2)],
+                          [torch.cuda.Event(), torch.cuda.Event()]]
+    ent = _H2D_BUFS[key]
+    ent[0] ^= 1
+    x, done = ent[1][ent[0]], ent[2][ent[0]]
+    main = torch.cuda.current_stream()
+    busy = not main.query()
+    cs.wait_event(done)  # the step that used this buffer two calls ago (a never-recorded event is complete)
     B = x_host.shape[0]
-    x = torch.empty(x_host.shape, device=dev, dtype=f32)
-    cs.wait_stream(torch.cuda.current_stream())  # the block may have been released by work still queued on this stream
-    step = -(-B // max(1, min(n_chunks, B)))
+    step = B if busy else -(-B // max(1, min(n_chunks, B)))
     chunks = []
     with torch.cuda.stream(cs):
         for b0 in range(0, B, step):
@@ -839,7 +857,7 @@ def h2d_chunked(x_host: torch.Tensor, dev, n_chunks: int = 0):
             ev = torch.cuda.Event()
             ev.record(cs)
             chunks.append((b0, b1, ev))
-    return x, chunks
+    return x, chunks, done
 
 
 def stream_mode() -> int:
@@ -904,9 +922,10 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     the loss wrt every projection (zeros where unused).  Accumulates into the flat gradient buffer.
     dpred_colsum: fp32 [n_layers, D] column sums of dpred over (B, T') if the loss kernel already produced them
     (batched-heads path only); both head bias gradients are derived from them (fhb_head_bias_grads).
-    on_progress(offset): called whenever flat[offset:] of the gradient buffer has become final - after the heads and
-    then after every second transformer layer (the buffer is laid out front end, layers 0..n-1, heads, and the backward
-    walks it from the end) - so that a data-parallel caller can start reducing that part under the rest of the pass.
+    on_progress(offset): called with an offset whenever flat[offset:] of the gradient buffer has become final - after the
+    heads and then after every second transformer layer (the buffer is laid out front end, layers 0..n-1, heads, and the
+    backward walks it from the end) - so that a data-parallel caller can start reducing that part under the rest of the
+    pass; called with None after the layers in between and once the prologue backward is queued (progress ticks).
     dfeatures: fp16 gradient wrt the returned `features` (features_to_distill, train.py:241-246): [B*T, D_cnn] when the
     model has a cnn_proj_head, else [B*T, E]."""
     E, F, H, d, D = g.E, g.F, g.H, g.d, g.d_out
@@ -1093,9 +1112,14 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
             K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),
                            accumulate=True)
-        if on_progress is not None and (l % 2 == 0 or l == g.n_layers - 1):
-            aside.join()
-            on_progress(G_.entries[p + "self_attn.q_proj.weight"][0])
+        if on_progress is not None:
+            # every second layer (and after the last one, whose call also covers the heads) a new part of the buffer is
+            # handed over; the calls in between only tell the caller that one more layer's worth of kernels has been
+            # queued since (it stops reserving SMs for the exchange it started a layer ago)
+            issue = l % 2 == 0 or l == g.n_layers - 1
+            if issue:
+                aside.join()
+            on_progress(G_.entries[p + "self_attn.q_proj.weight"][0] if issue else None)
         if l > 0:
             dx32 = K.linear_dgrad(dqkv, W[f"l{l}.wqkv"].view(3 * E, E), residual=dy1_32, out_dtype=f32)
         else:  # what leaves the encoder layers feeds bf16 GEMM operands (TR conv / prologue backward)
@@ -1138,6 +1162,8 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     K.posconv_finish_bwd(denc, c.h, c.conv, P["encoder.pos_conv.0.bias"], P["encoder.layer_norm.weight"], c.mean_e,
                          c.rstd_e, dh, dcg, gv("encoder.layer_norm.weight"), gv("encoder.layer_norm.bias"),
                          gv("encoder.pos_conv.0.bias"), B, T, E, G, cp, pad_b, Tp, delta=dl)
+    if on_progress is not None:
+        on_progress(None)
     dxc = torch.empty(B * R, G * dl * cp, device=dev, dtype=bf16)  # [b][r][g][dl][cp], like the forward output
     a3 = L.tensor3(dcg, data_ptr=dcg.data_ptr(), dim=(g.kpx * cp, R, B * G), stride=(dl * cp, Tp * cp))
     b3 = L.tensor3(W["pc.wt"], data_ptr=W["pc.wt"].data_ptr(), dim=(g.kpx * cp, dl * cp, G), stride=(g.kpx * cp, dl * cp * g.kpx * cp))

@@ -93,6 +93,17 @@ elif case in ("conv0_fwd_t", "conv0_fwd_s"):
     out = torch.empty(B, T0, Cd, device=dev, dtype=bf)
     gp = torch.empty(B, T0, Cd, device=dev, dtype=bf) if Cd == 128 else None
     fn = lambda: K.conv0_fwd(wave, w, g, b, T0, stat, mean, rstd, out, gp_out=gp)
+elif case == "ln_fwd_t":
+    rows, Cd = 32 * 779, 768
+    x = rnd(rows, Cd); y = torch.empty_like(x)
+    g, b = torch.randn(Cd, device=dev), torch.randn(Cd, device=dev)
+    fn = lambda: K.layernorm_fwd(x, g, b, y)
+elif case == "ln_fwd32_s":
+    rows, Cd = 32 * 389, 480
+    x = torch.randn(rows, Cd, device=dev); y = torch.empty(rows, Cd, device=dev, dtype=bf); y32 = torch.empty_like(x)
+    g, b = torch.randn(Cd, device=dev), torch.randn(Cd, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    fn = lambda: K.layernorm_fwd32(x, g, b, y, y32, mean, rstd)
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
