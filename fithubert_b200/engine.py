@@ -1205,6 +1205,9 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     dyl = torch.empty(B * T, Cf, device=dev, dtype=bf16)
     K.layernorm_bwd(dfl, c.out, P["layer_norm.weight"], c.mean_f, c.rstd_f, dyl, gv("layer_norm.weight"),
                     gv("layer_norm.bias"))
+    if on_progress is not None:
+        # everything behind the conv stack in the buffer is final: it goes out under the conv-stack backward
+        on_progress(G_.entries["layer_norm.weight"][0])
     # dU_last = dY * gelu'(U_last)   (c.u holds the saved gelu' values)
     du = torch.empty(B, T, Cf, device=dev, dtype=bf16)
     K.mul_bf16(dyl, T * Cf, c.u[last], T * Cf, du, T * Cf, B, T * Cf, alpha=g.grad_mult)  # x feature_grad_mult
@@ -1223,6 +1226,10 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         with aside_conv(du):
             _wgrad(dy3, x3, gv(f"feature_extractor.conv_layers.{i}.0.weight").view(co, k * cin), co, k * cin, To,
                    num_cb=B, a_cb=1, b_cb=1)
+        if on_progress is not None and not (mode & 4):
+            # the two widest layers (half of the stack's parameters) and then the layers down to 3 are handed over as
+            # soon as their weight gradients are queued; only ~1 MB (layers 2, 1, 0) is left for after the backward
+            on_progress(G_.entries[f"feature_extractor.conv_layers.{i}.0.weight"][0] if i in (last - 1, 3) else None)
         # dU_{i-1} = dX_{i-1} * gelu'(U_{i-1}) (layer 0 included: its forward saved gelu' of the GroupNorm output)
         dprev = torch.empty(B, in_rows, cin, device=dev, dtype=bf16)
         flags, uprev = L.EPI_MUL_AUX, c.u[i - 1]
