@@ -93,6 +93,12 @@ elif case in ("conv0_fwd_t", "conv0_fwd_s"):
     out = torch.empty(B, T0, Cd, device=dev, dtype=bf)
     gp = torch.empty(B, T0, Cd, device=dev, dtype=bf) if Cd == 128 else None
     fn = lambda: K.conv0_fwd(wave, w, g, b, T0, stat, mean, rstd, out, gp_out=gp)
+elif case == "sfc_res32":
+    M, N, Kd = 32 * 389, 480, 480
+    x, w, b = rnd(M, Kd), rnd(N, Kd, sc=0.05), torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.float32)
+    fn = lambda: K.linear(x, w, b, out=out, residual=res, out_dtype=torch.float32)
 elif case == "ln_fwd_t":
     rows, Cd = 32 * 779, 768
     x = rnd(rows, Cd); y = torch.empty_like(x)
