@@ -25,6 +25,9 @@ def main(argv=None):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized():
+        # the gradient all-reduce runs under the backward: NCCL is capped at the SMs the persistent kernels leave it
+        # (W2V2Distil.fused_forward_backward, FHB_COMM_SMS) - 125 MB over NVLink need no more
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("FHB_COMM_SMS", "8"))
         dist.init_process_group("nccl", device_id=dev)
     from . import BucketLoader, LibriDataset, W2V2Distil, fit
     model = W2V2Distil(cfg, device=dev)
