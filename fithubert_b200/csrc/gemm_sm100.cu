@@ -10,6 +10,11 @@
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile schedule (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs of one wave
 // share the A tile in L2).
+// PAIR MODE (K-major operands, p.pair = 1): the grid is launched as clusters of two CTAs that work on two vertically
+// adjacent row blocks of the SAME n-block.  Each CTA loads its own A tile and HALF of the shared B tile, multicast into
+// both CTAs' shared memory (cp.async.bulk.tensor ... .multicast::cluster): the L2 -> SM operand traffic of B halves
+// (48 -> 32 KB per k-block and CTA at BN = 256).  A stage is free again once BOTH CTAs' MMAs have consumed it
+// (tcgen05.commit ... .multicast::cluster onto empty barriers of count 2).
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -65,13 +70,36 @@ struct GemmParams {
   int stages;    // smem pipeline depth: 4, 3 or 2 depending on how many epilogue staging buffers are needed
   int n_auxout;  // 0 / 2 staging buffers for the second output
   int n_in;      // 0 / kInRing staging buffers for the TMA-loaded epilogue input (residual or aux_in)
+  int pair;      // 1: clusters of two CTAs share the B tile by TMA multicast (num_m_blk then counts PAIRS of row blocks)
 };
 
 struct Tile {
   int ob_hi, ob_lo, m0, n0, kb_begin, kb_end;
 };
 
-__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load multicast to the CTAs of `mask`: lands at the same shared-memory offset in each and completes bytes on the
+// barrier at the same offset in each
+__device__ __forceinline__ void tma_load_3d_mc(const void* desc, uint64_t* bar, void* smem, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int pair_rank = 0) {
   Tile t;
   const int nb = tile % p.num_n_blk;
   tile /= p.num_n_blk;
@@ -81,7 +109,7 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
   const int ob = tile / p.split_k;
   t.ob_hi = ob / p.ob_mod;
   t.ob_lo = ob % p.ob_mod;
-  t.m0 = mb * kBM;
+  t.m0 = (p.pair ? 2 * mb + pair_rank : mb) * kBM;  // pair mode: mb counts pairs of row blocks (a row block past m is all clipped)
   t.n0 = nb * p.bn;
   t.kb_begin = sp * p.kb_per_split;
   t.kb_end = min(t.kb_begin + p.kb_per_split, p.kb_total);
@@ -94,6 +122,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_aux,
                 const __grid_constant__ CUtensorMap tm_in, const GemmParams p) {
+  // pair mode: tm_b's box is HALF the B tile (bn / 2 rows); this CTA's rank in its cluster picks the half it loads
+  const int pair_rank = p.pair ? (int)cluster_ctarank() : 0;
+  const int first_tile = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nstages = p.stages;
   uint8_t* smem_a = smem;
@@ -121,7 +153,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     tma_prefetch_desc(&tm_d);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], p.pair ? 2 : 1);  // pair mode: both CTAs' MMAs release a stage (the peer multicasts into it)
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -135,6 +167,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.pair) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 8) {
@@ -142,8 +175,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const Tile t = decode_tile(p, tile);
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_stride) {
+        const Tile t = decode_tile(p, tile, pair_rank);
         const int a_c2 = t.ob_hi * p.a_hi_c2 + t.ob_lo * p.a_lo_c2;
         const int b_c2 = t.ob_hi * p.b_hi_c2 + t.ob_lo * p.b_lo_c2;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
@@ -166,6 +199,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int i = 0; i < atoms; ++i)
               tma_load_3d(&tm_b, &full[stage], sb + i * (kBK * 128), t.n0 + i * 64 + t.ob_lo * p.b_lo_c0, kr + p.b_c1_off,
                           b_c2 + cb * p.b_cb_c2);
+          } else if (p.pair) {
+            const int half_rows = p.bn >> 1;
+            tma_load_3d_mc(&tm_b, &full[stage], sb + pair_rank * half_rows * 128, kb * kBK + t.ob_lo * p.b_lo_c0,
+                           t.n0 + pair_rank * half_rows, b_c2, (uint16_t)3);
           } else {
             tma_load_3d(&tm_b, &full[stage], sb, kb * kBK + t.ob_lo * p.b_lo_c0, t.n0, b_c2);
           }
@@ -186,8 +223,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const Tile t = decode_tile(p, tile);
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_stride, ++it) {
+        const Tile t = decode_tile(p, tile, pair_rank);
         // the last n-block of a row may be narrower: issue only the columns that exist (multiple of 16)
         const int n_eff = min(p.bn, (p.n - t.n0 + 15) & ~15);
         const uint32_t idesc = umma_idesc_16(kBM, (uint32_t)n_eff, A_MN, B_MN, (p.flags & FHB_GEMM_A_BF16) ? 1u : 0u,
@@ -208,7 +245,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint64_t db = umma_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
             tc_mma_bf16(tmem_d, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (p.pair) tc_commit_mc(&empty[stage], (uint16_t)3);  // ... in BOTH CTAs: the peer's B half lands in this slot too
+          else tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -237,7 +275,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       return p.use_tma_store ? (min(p.bn, p.n - t.n0) + slab_cols - 1) / slab_cols : 0;
     };
     // ---- input-ring prefetcher (thread 0): walks the (tile, slab) sequence kInRing-1 slabs ahead
-    int pf_tile = blockIdx.x, pf_sidx = 0, pf_ns = 0;
+    int pf_tile = first_tile, pf_sidx = 0, pf_ns = 0;
     uint32_t pf_ctr = 0;
     Tile pf_t = {0, 0, 0, 0, 0, 0};
     auto prefetch_one = [&]() {
@@ -249,9 +287,9 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       ++pf_ctr;
       if (++pf_sidx == pf_ns) {
         pf_sidx = 0;
-        pf_tile += gridDim.x;
+        pf_tile += tile_stride;
         if (pf_tile < p.total_tiles) {
-          pf_t = decode_tile(p, pf_tile);
+          pf_t = decode_tile(p, pf_tile, pair_rank);
           pf_ns = tile_slabs(pf_t);
         }
       }
@@ -259,7 +297,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (in_tma && threadIdx.x == 0) {
       tma_prefetch_desc(&tm_in);
       if (pf_tile < p.total_tiles) {
-        pf_t = decode_tile(p, pf_tile);
+        pf_t = decode_tile(p, pf_tile, pair_rank);
         pf_ns = tile_slabs(pf_t);
       }
       for (int i = 0; i < kInRing - 1; ++i) prefetch_one();
@@ -267,8 +305,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     int it = 0;
     uint32_t slab_ctr = 0;
     float loss_local = 0.f;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const Tile t = decode_tile(p, tile);
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_stride, ++it) {
+      const Tile t = decode_tile(p, tile, pair_rank);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       // stage this tile's bias slice (double buffered by tile parity; the slab barriers order it)
@@ -568,6 +606,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();  // the peer may still be arriving on this CTA's empty barriers
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -716,12 +755,61 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
             const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
   FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN>,
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
-  const int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
+  int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
+  if (p.pair) {
+    // clusters of two CTAs: as many as can be co-resident (one CTA per SM; a GPC with an odd number of free SMs strands one)
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& mc = max_clusters[dev & 63];
+    if (mc == 0) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(2 * 148);
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, &q) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = 64;
+      }
+      mc = n;
+    }
+    int clusters = mc < fhb_num_sms() / 2 ? mc : fhb_num_sms() / 2;
+    if (clusters > p.total_tiles) clusters = p.total_tiles;
+    grid = 2 * clusters;
+  }
   // "small" = at most ~200 k-blocks per SM: the student's GEMMs and the teacher's encoder GEMMs, not the conv stacks
   // (swept on B200, profiles/r01y_pdl_ab.log: 7 104 -> 23.61 ms, 30 000 -> 23.55 ms, 150 000 -> 23.68 ms, none -> 23.94 ms)
   static const long long pdl_limit = getenv("FHB_PDL_GEMM_LIMIT") ? atoll(getenv("FHB_PDL_GEMM_LIMIT")) : 30000;
   fhb_pdl_hint((long long)p.total_tiles * (p.kb_per_split < 1 ? 1 : p.kb_per_split) <= pdl_limit);
-  FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
+  if (p.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = fhb_pdl_enabled() ? 2 : 1;
+    FHB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, ta, tb, td, tx, ti, p));
+  } else {
+    FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
+  }
   FHB_LAUNCH_CHECK();
   return 0;
 }
@@ -843,6 +931,19 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.num_m_blk = (a->m + kBM - 1) / kBM;
   p.bn = pick_bn(a->n, (long long)p.num_m_blk * num_ob, (flags & FHB_EPI_ATOMIC_ADD) != 0);
   p.num_n_blk = (a->n + p.bn - 1) / p.bn;
+  // Pair mode (see the kernel header): forward-shaped GEMMs (both operands K-major, no split-K) with at least two row
+  // blocks run as clusters of two CTAs that share the B tile by TMA multicast.  Opt-in (FHB_GEMM_PAIR=1): measured on
+  // B200 it changes nothing - 12 448 x 480 x 480 and 12 448 x 1440 x 480 to 0.1 us, the teacher-encoder group 4.16 vs
+  // 4.14 ms per step (profiles/r02zz_gemm_pair_ab.txt) - i.e. these GEMMs are NOT bound by L2 -> SM operand traffic.
+  static const bool pair_on = getenv("FHB_GEMM_PAIR") && getenv("FHB_GEMM_PAIR")[0] == '1';
+  const int m_blocks = p.num_m_blk;
+  if (pair_on && a->a_major == 0 && a->b_major == 0 && !(flags & FHB_EPI_ATOMIC_ADD) && a->split_k <= 1 && m_blocks >= 2 &&
+      p.bn % 16 == 0 && (long long)((m_blocks + 1) / 2) * p.num_n_blk * num_ob >= fhb_num_sms() / 2) {
+    p.pair = 1;
+    p.num_m_blk = (m_blocks + 1) / 2;  // decode_tile counts PAIRS of row blocks
+  }
+  static const bool dbg = getenv("FHB_GEMM_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "fhb_gemm m=%d n=%d k=%d bn=%d a_major=%d b_major=%d ob=%d pair=%d\n", a->m, a->n, a->k, p.bn, a->a_major, a->b_major, num_ob, p.pair);
   p.num_ob = num_ob;
   p.ob_mod = ob_mod;
   p.kb_per_cb = (a->k + kBK - 1) / kBK;
@@ -896,7 +997,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
     if ((rc = make_tmap(&ta, a->a, 64, kBK, "A")) != 0) return rc;
   }
   if (a->b_major == 0) {
-    if ((rc = make_tmap(&tb, a->b, kBK, (uint32_t)p.bn, "B")) != 0) return rc;
+    if ((rc = make_tmap(&tb, a->b, kBK, (uint32_t)(p.pair ? p.bn / 2 : p.bn), "B")) != 0) return rc;
     p.stage_tx_bytes = kABytes + (uint32_t)p.bn * kBK * 2;
   } else {
     if ((rc = make_tmap(&tb, a->b, 64, kBK, "B")) != 0) return rc;

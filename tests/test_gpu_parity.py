@@ -148,6 +148,39 @@ def test_gemm_variants(F):
     assert rel(y, refc) < 1e-2
 
 
+def test_gemm_pair_mode_cluster_multicast(F):
+    """FHB_GEMM_PAIR=1 (read once per process, hence the subprocess): K-major GEMMs run as clusters of two CTAs that share
+    the B tile by TMA multicast.  Odd and even row-block counts, a narrow last n-block, bias / GELU / fp32 residual
+    epilogues, a batched problem - against fp32 torch."""
+    import subprocess
+    import sys
+    code = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from fithubert_b200 import kernels as K
+torch.manual_seed(5)
+worst = 0.0
+for (M, N, Kd) in ((12448, 480, 480), (24928, 768, 768), (129 * 148, 1440, 480), (128 * 149, 256, 200)):
+    x = torch.randn(M, Kd, device="cuda").half(); w = (0.05 * torch.randn(N, Kd, device="cuda")).half()
+    b = torch.randn(N, device="cuda"); res = torch.randn(M, N, device="cuda")
+    ref = x.float() @ w.float().t() + b
+    y = K.linear(x, w, b)
+    worst = max(worst, float((y.float() - ref).abs().max() / ref.abs().max()))
+    y = K.linear(x, w, b, gelu=True)
+    g = torch.nn.functional.gelu(ref)
+    worst = max(worst, float((y.float() - g).abs().max() / g.abs().max()))
+    y = K.linear(x, w, b, residual=res, out_dtype=torch.float32)
+    worst = max(worst, float((y - (ref + res)).abs().max() / (ref + res).abs().max()))
+print("WORST", worst)
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FHB_GEMM_PAIR="1", FHB_GEMM_DEBUG="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "pair=1" in r.stderr, "pair mode did not engage"
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst < 2e-3, worst
+
+
 def test_layernorm_fwd_bwd(F):
     from fithubert_b200 import kernels as K
     torch.manual_seed(1)
