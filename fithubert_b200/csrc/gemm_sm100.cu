@@ -99,6 +99,42 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
+// ---- cta_group::2 (p.pair == 2): the two CTAs of a cluster run ONE UMMA of M = 256: each holds its 128 rows of A and
+// HALF of the B tile in its own shared memory (the instruction reads both), each accumulates its 128 rows in its own
+// TMEM.  Per CTA and k-block the tensor pipe then reads 16 KB A + bn/2 x 128 B of B instead of the whole B tile, and TMA
+// writes as little: the shared-memory bandwidth that caps a one-CTA UMMA at ~2/3 of the tensor peak is no longer the bound.
+// Only the leader (cluster rank 0) issues MMAs; both CTAs' loads complete on the LEADER's full barrier.
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;  // shared::cluster address -> same offset in the even CTA of the pair
+__device__ __forceinline__ void tma_load_3d_cg2(const void* desc, uint32_t bar_addr, void* smem, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(desc), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
 __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int pair_rank = 0) {
   Tile t;
   const int nb = tile % p.num_n_blk;
@@ -117,7 +153,9 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int p
 }
 
 // EPI_IN = 1: the epilogue reads [m][n] operands (residual / aux_in / loss target) laid out like D
-template <int A_MN, int B_MN, int EPI_IN>
+// CG2 = 1: the cta_group::2 instantiation.  A kernel that contains cta_group::2 instructions can only be launched as
+// clusters of two ("cluster misconfiguration" otherwise), so the pair-of-SMs path is a separate instantiation.
+template <int A_MN, int B_MN, int EPI_IN, int CG2 = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_aux,
@@ -126,6 +164,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int pair_rank = p.pair ? (int)cluster_ctarank() : 0;
   const int first_tile = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_stride = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool cg2 = CG2 != 0;  // (the host launches this instantiation iff p.pair == 2)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nstages = p.stages;
   uint8_t* smem_a = smem;
@@ -153,16 +192,19 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     tma_prefetch_desc(&tm_d);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], p.pair ? 2 : 1);  // pair mode: both CTAs' MMAs release a stage (the peer multicasts into it)
+      mbar_init(&empty[i], p.pair == 1 ? 2 : 1);  // multicast pairs: both CTAs' MMAs release a stage (the peer writes into it)
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiThreads);
+      mbar_init(&acc_empty[i], p.pair == 2 ? 2 * kEpiThreads : kEpiThreads);  // cta_group::2: both CTAs' epilogues release the leader
     }
     for (int i = 0; i < kInRing; ++i) mbar_init(&in_full[i], 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) {
+    if constexpr (CG2) tmem_alloc_cg2(tmem_slot, 512);  // collective: one warp of each CTA of the pair
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -181,6 +223,21 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int b_c2 = t.ob_hi * p.b_hi_c2 + t.ob_lo * p.b_lo_c2;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if constexpr (CG2) {
+            // both CTAs' bytes complete on the leader's barrier; the leader arms it with the sum
+            const uint32_t lbar = smem_u32(&full[stage]) & kLeaderMask;
+            if (pair_rank == 0) mbar_expect_tx(&full[stage], p.stage_tx_bytes + kABytes);  // 2 x A + the two halves of B
+            tma_load_3d_cg2(&tm_a, lbar, smem_a + stage * kABytes, kb * kBK + t.ob_lo * p.a_lo_c0, t.m0,
+                            t.ob_hi * p.a_hi_c2 + t.ob_lo * p.a_lo_c2);
+            const int n_eff2 = min(p.bn, (p.n - t.n0 + 15) & ~15) >> 1;  // this n-block's rows of B per CTA
+            tma_load_3d_cg2(&tm_b, lbar, smem_b + stage * kBBytes, kb * kBK + t.ob_lo * p.b_lo_c0, t.n0 + pair_rank * n_eff2,
+                            t.ob_hi * p.b_hi_c2 + t.ob_lo * p.b_lo_c2);
+            if (++stage == nstages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_expect_tx(&full[stage], p.stage_tx_bytes);
           const int cb = kb / p.kb_per_cb;
           const int kr = (kb - cb * p.kb_per_cb) * kBK;
@@ -199,7 +256,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int i = 0; i < atoms; ++i)
               tma_load_3d(&tm_b, &full[stage], sb + i * (kBK * 128), t.n0 + i * 64 + t.ob_lo * p.b_lo_c0, kr + p.b_c1_off,
                           b_c2 + cb * p.b_cb_c2);
-          } else if (p.pair) {
+          } else if (p.pair == 1) {
             const int half_rows = p.bn >> 1;
             tma_load_3d_mc(&tm_b, &full[stage], sb + pair_rank * half_rows * 128, kb * kBK + t.ob_lo * p.b_lo_c0,
                            t.n0 + pair_rank * half_rows, b_c2, (uint16_t)3);
@@ -214,8 +271,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------ MMA issuer (cta_group::2: the leader CTA only)
+    if (elect_one() && !(cg2 && pair_rank != 0)) {
       // K-major: 8-row groups 1024 B apart (SBO); MN-major: 64-element atoms kBK*128 B apart (LBO),
       // 8-k-row groups 1024 B apart (SBO).
       const uint32_t a_lbo = A_MN ? kBK * 128 : 0, b_lbo = B_MN ? kBK * 128 : 0;
@@ -227,7 +284,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const Tile t = decode_tile(p, tile, pair_rank);
         // the last n-block of a row may be narrower: issue only the columns that exist (multiple of 16)
         const int n_eff = min(p.bn, (p.n - t.n0 + 15) & ~15);
-        const uint32_t idesc = umma_idesc_16(kBM, (uint32_t)n_eff, A_MN, B_MN, (p.flags & FHB_GEMM_A_BF16) ? 1u : 0u,
+        const uint32_t idesc = umma_idesc_16(cg2 ? 2 * kBM : kBM, (uint32_t)n_eff, A_MN, B_MN, (p.flags & FHB_GEMM_A_BF16) ? 1u : 0u,
                                              (p.flags & FHB_GEMM_B_BF16) ? 1u : 0u);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -243,16 +300,19 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
             const uint64_t db = umma_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            tc_mma_bf16(tmem_d, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            if constexpr (CG2) tc_mma_cg2(tmem_d, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
           }
-          if (p.pair) tc_commit_mc(&empty[stage], (uint16_t)3);  // ... in BOTH CTAs: the peer's B half lands in this slot too
+          if constexpr (CG2) tc_commit_cg2(&empty[stage], (uint16_t)3);        // both CTAs' stage slots were read by these MMAs
+          else if (p.pair) tc_commit_mc(&empty[stage], (uint16_t)3);  // ... in BOTH CTAs: the peer's B half lands in this slot too
           else tc_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&acc_full[as]);
+        if constexpr (CG2) tc_commit_cg2(&acc_full[as], (uint16_t)3);  // each CTA's epilogue drains its own 128 rows
+        else tc_commit(&acc_full[as]);
       }
     }
   } else {
@@ -595,7 +655,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[as]);
+      if (cg2) mbar_arrive_cluster(smem_u32(&acc_empty[as]) & kLeaderMask);  // the leader's MMA warp waits for both epilogues
+      else mbar_arrive(&acc_empty[as]);
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (EPI_IN && (flags & FHB_EPI_SQDIFF)) {
@@ -609,7 +670,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (p.pair) cluster_sync_all();  // the peer may still be arriving on this CTA's empty barriers
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -750,10 +812,10 @@ int pick_bn(int n, long long row_tiles, bool split_k) {
   return best;
 }
 
-template <int A_MN, int B_MN, int EPI_IN>
+template <int A_MN, int B_MN, int EPI_IN, int CG2 = 0>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
             const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
-  FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN>,
+  FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>,
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
   int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
   if (p.pair) {
@@ -776,7 +838,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
       q.attrs = qa;
       q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, &q) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>, &q) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = 64;
       }
@@ -806,9 +868,9 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = fhb_pdl_enabled() ? 2 : 1;
-    FHB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fhb_gemm_kernel<A_MN, B_MN, EPI_IN>, ta, tb, td, tx, ti, p));
+    FHB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>, ta, tb, td, tx, ti, p));
   } else {
-    FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
+    FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
   }
   FHB_LAUNCH_CHECK();
   return 0;
@@ -817,8 +879,11 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
 template <int A_MN, int B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
            const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
-  if (p.flags & (FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX | FHB_EPI_SQDIFF))
-    return launch2<A_MN, B_MN, 1>(ta, tb, td, tx, ti, p, s);
+  const bool epi_in = (p.flags & (FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX | FHB_EPI_SQDIFF)) != 0;
+  if constexpr (A_MN == 0 && B_MN == 0) {
+    if (p.pair == 2) return epi_in ? launch2<0, 0, 1, 1>(ta, tb, td, tx, ti, p, s) : launch2<0, 0, 0, 1>(ta, tb, td, tx, ti, p, s);
+  }
+  if (epi_in) return launch2<A_MN, B_MN, 1>(ta, tb, td, tx, ti, p, s);
   return launch2<A_MN, B_MN, 0>(ta, tb, td, tx, ti, p, s);
 }
 
@@ -931,15 +996,22 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.num_m_blk = (a->m + kBM - 1) / kBM;
   p.bn = pick_bn(a->n, (long long)p.num_m_blk * num_ob, (flags & FHB_EPI_ATOMIC_ADD) != 0);
   p.num_n_blk = (a->n + p.bn - 1) / p.bn;
-  // Pair mode (see the kernel header): forward-shaped GEMMs (both operands K-major, no split-K) with at least two row
-  // blocks run as clusters of two CTAs that share the B tile by TMA multicast.  Opt-in (FHB_GEMM_PAIR=1): measured on
-  // B200 it changes nothing - 12 448 x 480 x 480 and 12 448 x 1440 x 480 to 0.1 us, the teacher-encoder group 4.16 vs
-  // 4.14 ms per step (profiles/r02zz_gemm_pair_ab.txt) - i.e. these GEMMs are NOT bound by L2 -> SM operand traffic.
-  static const bool pair_on = getenv("FHB_GEMM_PAIR") && getenv("FHB_GEMM_PAIR")[0] == '1';
+  // Pair modes (see the kernel header): forward-shaped GEMMs (both operands K-major, no split-K) with at least two row
+  // blocks run as clusters of two CTAs.  FHB_GEMM_PAIR=1: the B tile is shared by TMA multicast (L2 -> SM traffic of B
+  // halved); FHB_GEMM_PAIR=2: cta_group::2 - one UMMA of M = 256 over the pair, B split between the two CTAs (shared-
+  // memory traffic per CTA halved as well).  Both are OPT-IN: measured on B200 (profiles/r02zz_gemm_pair_ab.txt) multicast
+  // changes nothing (12 448-row GEMMs to 0.1 us, teacher-encoder group 4.16 vs 4.14 ms per step) and cta_group::2 is
+  // slower (teacher encoder 4.39 vs 4.13-4.20 ms, conv stacks 6.30 vs 6.07-6.12, the 12 448-row GEMMs +3 us each): operand
+  // delivery - from L2 or from shared memory - is not what bounds these GEMMs.
+  static const int pair_mode = getenv("FHB_GEMM_PAIR") ? atoi(getenv("FHB_GEMM_PAIR")) : 0;
+  const bool pair_on = pair_mode == 1 || pair_mode == 2;
   const int m_blocks = p.num_m_blk;
   if (pair_on && a->a_major == 0 && a->b_major == 0 && !(flags & FHB_EPI_ATOMIC_ADD) && a->split_k <= 1 && m_blocks >= 2 &&
       p.bn % 16 == 0 && (long long)((m_blocks + 1) / 2) * p.num_n_blk * num_ob >= fhb_num_sms() / 2) {
-    p.pair = 1;
+    p.pair = pair_mode;
+    // cta_group::2 needs 32 <= N <= 256 for every n-block (the last one may be narrower)
+    const int last_n = a->n - (p.num_n_blk - 1) * p.bn;
+    if (p.pair == 2 && (((last_n + 15) & ~15) < 32 || p.bn < 32)) p.pair = 1;
     p.num_m_blk = (m_blocks + 1) / 2;  // decode_tile counts PAIRS of row blocks
   }
   static const bool dbg = getenv("FHB_GEMM_DEBUG") != nullptr;

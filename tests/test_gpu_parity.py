@@ -148,10 +148,11 @@ def test_gemm_variants(F):
     assert rel(y, refc) < 1e-2
 
 
-def test_gemm_pair_mode_cluster_multicast(F):
-    """FHB_GEMM_PAIR=1 (read once per process, hence the subprocess): K-major GEMMs run as clusters of two CTAs that share
-    the B tile by TMA multicast.  Odd and even row-block counts, a narrow last n-block, bias / GELU / fp32 residual
-    epilogues, a batched problem - against fp32 torch."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_gemm_pair_mode_cluster_multicast(F, mode):
+    """FHB_GEMM_PAIR (read once per process, hence the subprocess): K-major GEMMs run as clusters of two CTAs - 1: the B
+    tile shared by TMA multicast, 2: cta_group::2 (one UMMA of M = 256 over the pair, B split between the CTAs).  Odd and
+    even row-block counts, a narrow last n-block, bias / GELU / fp32 residual epilogues - against fp32 torch."""
     import subprocess
     import sys
     code = r"""
@@ -173,10 +174,10 @@ for (M, N, Kd) in ((12448, 480, 480), (24928, 768, 768), (129 * 148, 1440, 480),
     worst = max(worst, float((y - (ref + res)).abs().max() / (ref + res).abs().max()))
 print("WORST", worst)
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, FHB_GEMM_PAIR="1", FHB_GEMM_DEBUG="1")
+    env = dict(os.environ, FHB_GEMM_PAIR=mode, FHB_GEMM_DEBUG="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
-    assert "pair=1" in r.stderr, "pair mode did not engage"
+    assert f"pair={mode}" in r.stderr, "pair mode did not engage"
     worst = float(r.stdout.strip().split("WORST")[-1])
     assert worst < 2e-3, worst
 
