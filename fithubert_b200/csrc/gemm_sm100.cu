@@ -29,7 +29,7 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int kMaxBN = 256;
-constexpr int kStages = 4;
+constexpr int kStages = 6;   // barrier slots; the pipeline depth is p.stages (<= 4 with whole B tiles, <= 6 with cta_group::2 half tiles)
 constexpr int kAccStages = 2;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -168,8 +168,11 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nstages = p.stages;
   uint8_t* smem_a = smem;
+  // cta_group::2: a stage holds A and HALF a B tile (32 KiB instead of 48): the freed shared memory deepens the pipeline -
+  // 4 x 48 KiB in flight cover ~1.1 us of L2 latency at the full MMA rate, 6 x 32 KiB at half the bytes per CTA ~1.6 us
+  constexpr uint32_t kBSlot = CG2 ? kBBytes / 2 : kBBytes;
   uint8_t* smem_b = smem + nstages * kABytes;
-  uint8_t* smem_out = smem + nstages * kStageBytes;            // 2 x 16 KiB staging buffers for TMA stores of D
+  uint8_t* smem_out = smem + nstages * (kABytes + kBSlot);     // 2 x 16 KiB staging buffers for TMA stores of D
   uint8_t* smem_auxo = smem_out + 2 * kStoreBytes;             // 0 / 2 buffers for the second output
   uint8_t* smem_in = smem_auxo + p.n_auxout * kStoreBytes;     // 0 / 3 buffers for the TMA-loaded epilogue input
   uint8_t* smem_tail = smem + 14 * kStoreBytes;
@@ -196,7 +199,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], p.pair == 2 ? 2 * kEpiThreads : kEpiThreads);  // cta_group::2: both CTAs' epilogues release the leader
+      mbar_init(&acc_empty[i], p.pair == 2 ? 2 : kEpiThreads);  // cta_group::2: one arrival per CTA of the pair (see the epilogue)
     }
     for (int i = 0; i < kInRing; ++i) mbar_init(&in_full[i], 1);
     fence_mbar_init();
@@ -230,7 +233,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             tma_load_3d_cg2(&tm_a, lbar, smem_a + stage * kABytes, kb * kBK + t.ob_lo * p.a_lo_c0, t.m0,
                             t.ob_hi * p.a_hi_c2 + t.ob_lo * p.a_lo_c2);
             const int n_eff2 = min(p.bn, (p.n - t.n0 + 15) & ~15) >> 1;  // this n-block's rows of B per CTA
-            tma_load_3d_cg2(&tm_b, lbar, smem_b + stage * kBBytes, kb * kBK + t.ob_lo * p.b_lo_c0, t.n0 + pair_rank * n_eff2,
+            tma_load_3d_cg2(&tm_b, lbar, smem_b + stage * kBSlot, kb * kBK + t.ob_lo * p.b_lo_c0, t.n0 + pair_rank * n_eff2,
                             t.ob_hi * p.b_hi_c2 + t.ob_lo * p.b_lo_c2);
             if (++stage == nstages) {
               stage = 0;
@@ -242,7 +245,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           const int cb = kb / p.kb_per_cb;
           const int kr = (kb - cb * p.kb_per_cb) * kBK;
           uint8_t* sa = smem_a + stage * kABytes;
-          uint8_t* sb = smem_b + stage * kBBytes;
+          uint8_t* sb = smem_b + stage * kBSlot;
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < kBM / 64; ++i)
@@ -295,7 +298,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kBSlot);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
@@ -655,8 +658,14 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
       tc_fence_before();
-      if (cg2) mbar_arrive_cluster(smem_u32(&acc_empty[as]) & kLeaderMask);  // the leader's MMA warp waits for both epilogues
-      else mbar_arrive(&acc_empty[as]);
+      if (cg2) {
+        // the leader's MMA warp waits for both CTAs' epilogues: ONE (remote) arrival per CTA behind a block barrier instead of
+        // 256 arrivals across the cluster
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) mbar_arrive_cluster(smem_u32(&acc_empty[as]) & kLeaderMask);
+      } else {
+        mbar_arrive(&acc_empty[as]);
+      }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (EPI_IN && (flags & FHB_EPI_SQDIFF)) {
@@ -843,6 +852,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
         n = 64;
       }
       mc = n;
+      if (getenv("FHB_GEMM_DEBUG")) fprintf(stderr, "fhb_gemm: %d co-resident 2-CTA clusters\n", n);
     }
     int clusters = mc < fhb_num_sms() / 2 ? mc : fhb_num_sms() / 2;
     if (clusters > p.total_tiles) clusters = p.total_tiles;
@@ -998,12 +1008,19 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.num_n_blk = (a->n + p.bn - 1) / p.bn;
   // Pair modes (see the kernel header): forward-shaped GEMMs (both operands K-major, no split-K) with at least two row
   // blocks run as clusters of two CTAs.  FHB_GEMM_PAIR=1: the B tile is shared by TMA multicast (L2 -> SM traffic of B
-  // halved); FHB_GEMM_PAIR=2: cta_group::2 - one UMMA of M = 256 over the pair, B split between the two CTAs (shared-
-  // memory traffic per CTA halved as well).  Both are OPT-IN: measured on B200 (profiles/r02zz_gemm_pair_ab.txt) multicast
-  // changes nothing (12 448-row GEMMs to 0.1 us, teacher-encoder group 4.16 vs 4.14 ms per step) and cta_group::2 is
-  // slower (teacher encoder 4.39 vs 4.13-4.20 ms, conv stacks 6.30 vs 6.07-6.12, the 12 448-row GEMMs +3 us each): operand
-  // delivery - from L2 or from shared memory - is not what bounds these GEMMs.
-  static const int pair_mode = getenv("FHB_GEMM_PAIR") ? atoi(getenv("FHB_GEMM_PAIR")) : 0;
+  // halved); FHB_GEMM_PAIR=2: cta_group::2 - one UMMA of M = 256 over the pair, B split between the two CTAs, and the
+  // shared memory that frees buys a 6-stage pipeline; 0: one CTA per tile.  Default (unset): cta_group::2 for the LARGE
+  // GEMMs only.  Measured on B200 (profiles/r02zz_gemm_pair_ab.txt): multicast changes nothing; cta_group::2 with 4 stages is
+  // slower (teacher encoder 4.39 vs 4.13-4.20 ms), with 6 stages and one arrival per CTA faster (4.10-4.13 vs 4.18-4.26 ms,
+  // conv stacks 5.97 vs 6.04-6.09, step -0.3 ms) - what bounds the big GEMMs is how much L2 latency the bytes in flight
+  // cover, not operand bandwidth; the 12 448-row GEMMs lose 3 us each to the cluster barriers and stay on one CTA.
+  static const int pair_env = getenv("FHB_GEMM_PAIR") ? atoi(getenv("FHB_GEMM_PAIR")) : -1;
+  int pair_mode = pair_env < 0 ? 2 : pair_env;
+  if (pair_env < 0) {
+    const long long pair_tiles = (long long)((p.num_m_blk + 1) / 2) * p.num_n_blk * num_ob;
+    const long long kb = (long long)((a->k + kBK - 1) / kBK) * num_cb;
+    if (pair_tiles * kb <= 40LL * (fhb_num_sms() / 2)) pair_mode = 0;  // fewer than ~40 k-blocks per cluster: not worth it
+  }
   const bool pair_on = pair_mode == 1 || pair_mode == 2;
   const int m_blocks = p.num_m_blk;
   if (pair_on && a->a_major == 0 && a->b_major == 0 && !(flags & FHB_EPI_ATOMIC_ADD) && a->split_k <= 1 && m_blocks >= 2 &&
@@ -1093,7 +1110,11 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 2 : 0;
   p.n_in = (p.use_tma_store && ring_src && ring_f32 == out_f32) ? kInRing : 0;
   p.stages = (14 - 2 - p.n_auxout - p.n_in) / 3;
-  if (p.stages > kStages) p.stages = kStages;
+  if (p.stages > 4) p.stages = 4;
+  if (p.pair == 2) {  // half B tiles: 2 units of 16 KiB per stage
+    p.stages = (14 - 2 - p.n_auxout - p.n_in) / 2;
+    if (p.stages > kStages) p.stages = kStages;
+  }
   if (p.use_tma_store) {
     const int n_hi = (num_ob + ob_mod - 1) / ob_mod;
     if ((rc = make_out_tmap(&td, a->d, out_f32, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride, a->d_hi_stride,
