@@ -39,7 +39,7 @@ constexpr uint32_t kBBytes = kMaxBN * kBK * 2;  // 32 KiB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kStoreBytes = kBM * 128;  // one output slab: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
 constexpr uint32_t kBiasBytes = 2 * kMaxBN * 4;
-constexpr int kInRing = 3;  // epilogue-input slabs in flight (prefetch distance 2)
+constexpr int kInRing = 6;  // most epilogue-input slabs in flight (the ring depth is p.n_in: 3, or 4 with cta_group::2)
 constexpr uint32_t kBarBytes = 256;
 // 14 units of 16 KiB: 3 per pipeline stage + 2 output slabs (+ 2 second-output slabs) (+ 3 epilogue-input slabs)
 constexpr uint32_t kSmemBytes = 14 * kStoreBytes + kBiasBytes + kBarBytes;
@@ -69,7 +69,7 @@ struct GemmParams {
   int use_tma_store;
   int stages;    // smem pipeline depth: 4, 3 or 2 depending on how many epilogue staging buffers are needed
   int n_auxout;  // 0 / 2 staging buffers for the second output
-  int n_in;      // 0 / kInRing staging buffers for the TMA-loaded epilogue input (residual or aux_in)
+  int n_in;      // 0 / 3 / 4 staging buffers (<= kInRing) for the TMA-loaded epilogue input (residual or aux_in)
   int pair;      // 1: clusters of two CTAs share the B tile by TMA multicast (num_m_blk then counts PAIRS of row blocks)
 };
 
@@ -339,11 +339,13 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     };
     // ---- input-ring prefetcher (thread 0): walks the (tile, slab) sequence kInRing-1 slabs ahead
     int pf_tile = first_tile, pf_sidx = 0, pf_ns = 0;
-    uint32_t pf_ctr = 0;
+    uint32_t pf_ctr = 0, pf_slot = 0;
+    uint32_t in_slot = 0, in_phase = 0;  // consumer side of the input ring
     Tile pf_t = {0, 0, 0, 0, 0, 0};
     auto prefetch_one = [&]() {
       if (pf_tile >= p.total_tiles) return;
-      const uint32_t slot = pf_ctr % kInRing;
+      const uint32_t slot = pf_slot;
+      if (++pf_slot == (uint32_t)p.n_in) pf_slot = 0;
       mbar_expect_tx(&in_full[slot], kStoreBytes);
       tma_load_4d(&tm_in, &in_full[slot], in_u32 + slot * kStoreBytes, pf_t.n0 + pf_sidx * slab_cols, pf_t.m0, pf_t.ob_lo,
                   pf_t.ob_hi);
@@ -363,7 +365,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         pf_t = decode_tile(p, pf_tile, pair_rank);
         pf_ns = tile_slabs(pf_t);
       }
-      for (int i = 0; i < kInRing - 1; ++i) prefetch_one();
+      for (int i = 0; i < p.n_in - 1; ++i) prefetch_one();
     }
     int it = 0;
     uint32_t slab_ctr = 0;
@@ -563,8 +565,12 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (!out_f32) tmem_ld16(taddr + c0 + 16, r + 16);
         uint32_t ring[16];
         if (in_tma) {
-          const uint32_t slot = slab_ctr % kInRing;
-          mbar_wait(&in_full[slot], (slab_ctr / kInRing) & 1u);
+          const uint32_t slot = in_slot;
+          mbar_wait(&in_full[slot], in_phase);
+          if (++in_slot == (uint32_t)p.n_in) {
+            in_slot = 0;
+            in_phase ^= 1u;
+          }
           const uint32_t irow = in_u32 + slot * kStoreBytes + row_in_tile * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1009,18 +1015,16 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   // Pair modes (see the kernel header): forward-shaped GEMMs (both operands K-major, no split-K) with at least two row
   // blocks run as clusters of two CTAs.  FHB_GEMM_PAIR=1: the B tile is shared by TMA multicast (L2 -> SM traffic of B
   // halved); FHB_GEMM_PAIR=2: cta_group::2 - one UMMA of M = 256 over the pair, B split between the two CTAs, and the
-  // shared memory that frees buys a 6-stage pipeline; 0: one CTA per tile.  Default (unset): cta_group::2 for the LARGE
-  // GEMMs only.  Measured on B200 (profiles/r02zz_gemm_pair_ab.txt): multicast changes nothing; cta_group::2 with 4 stages is
-  // slower (teacher encoder 4.39 vs 4.13-4.20 ms), with 6 stages and one arrival per CTA faster (4.10-4.13 vs 4.18-4.26 ms,
-  // conv stacks 5.97 vs 6.04-6.09, step -0.3 ms) - what bounds the big GEMMs is how much L2 latency the bytes in flight
-  // cover, not operand bandwidth; the 12 448-row GEMMs lose 3 us each to the cluster barriers and stay on one CTA.
+  // shared memory that frees buys a 6-stage pipeline; 0: one CTA per tile.  Default (unset): cta_group::2 for LONG
+  // contractions only (K >= 1536).  Measured per shape inside the step (profiles/r02zz_gemm_pair_ab.txt): cta_group::2 wins
+  // where the main loop dominates - fc2 K = 3072: 111.6 -> 100.1 us, the teacher's k=3 conv layers K = 1536: 1001 -> 899 us,
+  // pos-conv K = 4224 / 6336: -25 % - because a 6 x 32 KB ring covers ~1.6 us of L2 latency at the full MMA rate where
+  // 4 x 48 KB cover 1.1 us; it loses 5-10 % on short contractions and heavy epilogues (fc1 + GELU N = 3072, out_proj K = 768,
+  // every HBM-bound conv layer), where the pair's lock step and cluster barriers cost more than the ring buys.  TMA
+  // multicast alone changes nothing: operand bandwidth is not the bound.
   static const int pair_env = getenv("FHB_GEMM_PAIR") ? atoi(getenv("FHB_GEMM_PAIR")) : -1;
   int pair_mode = pair_env < 0 ? 2 : pair_env;
-  if (pair_env < 0) {
-    const long long pair_tiles = (long long)((p.num_m_blk + 1) / 2) * p.num_n_blk * num_ob;
-    const long long kb = (long long)((a->k + kBK - 1) / kBK) * num_cb;
-    if (pair_tiles * kb <= 40LL * (fhb_num_sms() / 2)) pair_mode = 0;  // fewer than ~40 k-blocks per cluster: not worth it
-  }
+  if (pair_env < 0 && (a->k + kBK - 1) / kBK < 24) pair_mode = 0;
   const bool pair_on = pair_mode == 1 || pair_mode == 2;
   const int m_blocks = p.num_m_blk;
   if (pair_on && a->a_major == 0 && a->b_major == 0 && !(flags & FHB_EPI_ATOMIC_ADD) && a->split_k <= 1 && m_blocks >= 2 &&
@@ -1108,7 +1112,10 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   // bf16; the residual is bf16 or, with FHB_EPI_RES_F32, fp32); otherwise that operand is read from global memory
   const bool ring_f32 = !ring_aux && (flags & FHB_EPI_RES_F32) != 0;
   p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 2 : 0;
-  p.n_in = (p.use_tma_store && ring_src && ring_f32 == out_f32) ? kInRing : 0;
+  // ring depth: 3 slabs (2 in flight); cta_group::2 stages are 2 units, so a 4th slab fits beside 4 pipeline stages - the
+  // teacher's out_proj (K = 768: a tile's 64 KB of residual against 3.2 us of MMA) is bound by this ring
+  static const int ring_cg2 = getenv("FHB_GEMM_RING") ? atoi(getenv("FHB_GEMM_RING")) : 4;
+  p.n_in = (p.use_tma_store && ring_src && ring_f32 == out_f32) ? (p.pair == 2 ? (ring_cg2 < 3 ? 3 : (ring_cg2 > kInRing ? kInRing : ring_cg2)) : 3) : 0;
   p.stages = (14 - 2 - p.n_auxout - p.n_in) / 3;
   if (p.stages > 4) p.stages = 4;
   if (p.pair == 2) {  // half B tiles: 2 units of 16 KiB per stage
