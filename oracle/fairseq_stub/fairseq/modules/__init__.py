@@ -82,6 +82,8 @@ class MultiheadAttention(nn.Module):
         self.v_proj = nn.Linear(embed_dim, embed_dim, bias=True)
         self.q_proj = nn.Linear(embed_dim, embed_dim, bias=True)
         self.out_proj = nn.Linear(embed_dim, embed_dim, bias=True)
+        # fairseq's FairseqDropout: the attention-map recipe calls it directly (reference utils/utils.py:224)
+        self.dropout_module = nn.Dropout(dropout)
         self.skip_embed_dim_check = False
         self.reset_parameters()
 
@@ -96,7 +98,7 @@ class MultiheadAttention(nn.Module):
         nn.init.constant_(self.out_proj.bias, 0.0)
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights=False,
-                attn_mask=None, **kw):
+                attn_mask=None, before_softmax=False, **kw):
         tgt_len, bsz, embed_dim = query.size()
         q = self.q_proj(query) * self.scaling
         k = self.k_proj(query)
@@ -111,6 +113,10 @@ class MultiheadAttention(nn.Module):
             w = w.view(bsz, H, tgt_len, tgt_len)
             w = w.masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2).to(torch.bool), float("-inf"))
             w = w.view(bsz * H, tgt_len, tgt_len)
+        if before_softmax:
+            # fairseq multihead_attention.py (commit 1b61bbad): `if before_softmax: return attn_weights, v` right after
+            # the key-padding masked_fill - the un-normalised logits [B*H, T, T] and the value heads [B*H, T, d]
+            return w, v
         w_float = F.softmax(w, dim=-1, dtype=torch.float32)
         w = w_float.type_as(w)
         p = F.dropout(w, p=self.dropout_p, training=self.training)

@@ -153,9 +153,8 @@ def pos_conv(sd: State, prefix: str, x_btc: Tensor, k: int, groups: int) -> Tens
     return F.gelu(y).transpose(1, 2)
 
 
-def mha(sd: State, p: str, x_tbc: Tensor, key_mask: Optional[Tensor], H: int) -> Tensor:
-    """[EXT] fairseq MultiheadAttention manual path (SURVEY App. B.1): q scaled after
-    bias, -inf on padded keys, fp32 softmax, out_proj."""
+def _mha_heads(sd: State, p: str, x_tbc: Tensor, key_mask: Optional[Tensor], H: int):
+    """q (scaled after bias), k, v as [B*H, T, d] and the masked logits [B*H, T, T] of fairseq's manual path."""
     T, B, E = x_tbc.shape
     d = E // H
     q = F.linear(x_tbc, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"]) * d ** -0.5
@@ -165,19 +164,42 @@ def mha(sd: State, p: str, x_tbc: Tensor, key_mask: Optional[Tensor], H: int) ->
     w = torch.bmm(q, k.transpose(1, 2))
     if key_mask is not None:
         w = w.view(B, H, T, T).masked_fill(key_mask[:, None, None, :], float("-inf")).view(B * H, T, T)
+    return w, v
+
+
+def mha(sd: State, p: str, x_tbc: Tensor, key_mask: Optional[Tensor], H: int, return_attn: bool = False):
+    """[EXT] fairseq MultiheadAttention manual path (SURVEY App. B.1): q scaled after
+    bias, -inf on padded keys, fp32 softmax, out_proj.
+    return_attn: the attention-map recipe (utils/utils.py:190-232, `rtrn_attn_forward` bound over every layer's forward
+    when attn_loss_weight > 0, train.py:64-77): fairseq's `before_softmax=True` hands back the masked logits and the
+    value heads, the layer finishes the attention itself and also returns (logits, v_rel) with
+    v_rel = bmm(v * scaling, v^T) (un-masked, :229)."""
+    T, B, E = x_tbc.shape
+    d = E // H
+    w, v = _mha_heads(sd, p, x_tbc, key_mask, H)
     a = torch.bmm(torch.softmax(w.float(), -1), v)
     a = a.transpose(0, 1).reshape(T, B, E)
-    return F.linear(a, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+    out = F.linear(a, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+    if return_attn:
+        return out, (w, torch.bmm(v * d ** -0.5, v.transpose(1, 2)))
+    return out
 
 
-def encoder_layer(sd: State, p: str, x: Tensor, key_mask, H: int) -> Tuple[Tensor, Tensor]:
-    """modules/module.py:557-580, post-LN branch, dropout = identity."""
+def encoder_layer(sd: State, p: str, x: Tensor, key_mask, H: int, return_attn: bool = False):
+    """modules/module.py:557-580, post-LN branch, dropout = identity.  return_attn: utils/utils.py:233-258 (the same layer
+    with the logits / value-relation pair in place of the `None` attention weights)."""
     E = x.shape[-1]
-    x = x + mha(sd, p + "self_attn.", x, key_mask, H)
+    a = mha(sd, p + "self_attn.", x, key_mask, H, return_attn)
+    attn = None
+    if return_attn:
+        a, attn = a
+    x = x + a
     x = F.layer_norm(x, (E,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], 1e-5)
     h = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
     lr = F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
     x = F.layer_norm(x + lr, (E,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5)
+    if return_attn:
+        return x, attn, lr
     return x, lr
 
 
@@ -199,14 +221,16 @@ def grad_multiply(x: Tensor, scale: float) -> Tensor:
 
 
 def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional[Tensor] = None,
-                    heads: bool = True) -> dict:
+                    heads: bool = True, return_attn: bool = False) -> dict:
     """CustomStudentModel.forward, modules/model.py:420-552 (n_mels=0, transformer, dropout identity) for the two
     shipped recipes:
       * fithubert.yaml: layerwise_proj=True, conv1d TR layer at index 0 -> 12 LayerWiseProjHeads, x = last projection;
       * ex.yaml: layerwise_proj=False, enable_tr_layer=False, feature_grad_mult < 1 -> DistilHuBERT head
         Linear -> GELU -> SplitLinear on the last layer (:504-518, modules/module.py:585-619), projections a
         [B, N, T, D] tensor, x = the encoder output.
-    heads=False mirrors the state after _disable_projection_heads() (:393-399,500-502)."""
+    heads=False mirrors the state after _disable_projection_heads() (:393-399,500-502).
+    return_attn=True: every layer runs `rtrn_attn_forward` (train.py:64-77 with attn_loss_weight > 0): layer_results[i] =
+    (x, (attn_logits, v_rel), layer_result) (modules/module.py:331-334 appends (x, z, lr) with z the layer's second output)."""
     conv_layers = parse_conv_layers(cfg["conv_feature_layers"])
     H = cfg["encoder_attention_heads"]
     feats = conv_extractor(sd, "feature_extractor.", source, conv_layers)
@@ -236,7 +260,15 @@ def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
         rmask = mask_m2(mask, cfg["tr_reduce_factor"])
     layer_results = []
     off = 1 if tr else 0
+    if return_attn and tr:
+        # train.py:70-77 calls `layer.self_attn._set_skip_embed_dim_check()` on every entry of encoder.layers; entry 0 is
+        # the time-reduction nn.Conv1d (modules/module.py:230-236)
+        raise AttributeError("'Conv1d' object has no attribute 'self_attn'")
     for i in range(cfg["encoder_layers"]):
+        if return_attn:
+            x, attn, lr = encoder_layer(sd, f"encoder.layers.{i + off}.", x, rmask, H, True)
+            layer_results.append((x, attn, lr))
+            continue
         x, lr = encoder_layer(sd, f"encoder.layers.{i + off}.", x, rmask, H)
         layer_results.append((x, None, lr))
 
@@ -274,7 +306,8 @@ def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
 
 
 # --------------------------------------------------------------------------- teacher
-def teacher_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional[Tensor] = None) -> dict:
+def teacher_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional[Tensor] = None,
+                    return_attn: bool = False) -> dict:
     """TeacherWrapper.extract_features (utils/utils.py:80-99) around [EXT]
     HubertModel / Wav2Vec2Model.extract_features(mask=None), eval mode."""
     conv_layers = parse_conv_layers(cfg["conv_feature_layers"])
@@ -290,6 +323,10 @@ def teacher_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
     x = encoder_prologue(sd, feats, mask, cfg).transpose(0, 1)
     layer_results = []
     for i in range(cfg["encoder_layers"]):
+        if return_attn:  # the hook captures (x, ((attn_logits, v_rel), layer_result)), utils/utils.py:65-78,258
+            x, attn, lr = encoder_layer(sd, f"encoder.layers.{i}.", x, mask, H, True)
+            layer_results.append((x, (attn, lr)))
+            continue
         x, lr = encoder_layer(sd, f"encoder.layers.{i}.", x, mask, H)
         layer_results.append((x, (None, lr)))
     return {"layer_results": layer_results, "x": layer_results[-1][0].transpose(0, 1),
@@ -468,6 +505,39 @@ def cnn_feature_loss(student_features: Tensor, teacher_features: Tensor) -> Tens
     """W2V2Distil.calculate_loss CNN branch, train.py:241-246: plain L1 mean between the student's `features`
     (features_to_distill) and the teacher's post_extract_proj output."""
     return F.l1_loss(student_features.float(), teacher_features.float(), reduction="none").mean()
+
+
+def attn_map_loss(pred: Tensor, target: Tensor, loss_type: str = "kldiv", nan_like_reference: bool = True) -> Tensor:
+    """Attention distribution transfer loss, train.py:327-353.  pred / target: the student's and the teacher's LAST-layer
+    attention logits [B*H, T, T], -inf at padded keys (each side's own mask rule).
+      mse   (:331-341): squared differences; inf (one side masked) and nan (both masked) entries are zeroed in place and
+            left out of the mean - the count is taken per (b*h, key) column (`torch.any(.., 1)` reduces the QUERY axis);
+      kldiv (:342-349): F.kl_div(log_softmax(pred), softmax(target), 'none'), inf entries (student-masked key with
+            teacher mass) zeroed, sum over keys, mean over all B*H*T query rows (padded queries included).
+    Reference quirk: in the kldiv branch a key masked on BOTH sides gives 0 * -inf = nan, and nan is NOT patched there
+    (only inf is, :348): with a padded batch the reference's kldiv loss is nan.  nan_like_reference=False restates the
+    evidently intended value (such keys contribute nothing), which is what the CUDA path computes."""
+    pred, target = pred.float(), target.float()
+    if loss_type == "mse":
+        loss = F.mse_loss(pred, target, reduction="none")
+        inf_count = torch.any(loss.isinf(), 1).count_nonzero() * loss.size(-1)
+        nan_count = torch.any(loss.isnan(), 1).count_nonzero() * loss.size(-1)
+        loss = loss.masked_fill(loss.isinf() | loss.isnan(), 0.0)
+        return loss.sum() / (loss.numel() - inf_count - nan_count)
+    if loss_type == "kldiv":
+        loss = F.kl_div(F.log_softmax(pred, dim=-1), F.softmax(target, dim=-1), reduction="none")
+        loss = loss.masked_fill(loss.isinf(), 0.0)
+        if not nan_like_reference:
+            loss = loss.masked_fill(loss.isnan(), 0.0)
+        return loss.sum(dim=-1).mean()
+    raise NotImplementedError("attn_loss_type must be one of 'mse', 'kldiv'.")
+
+
+def value_relation_loss(pred: Tensor, target: Tensor) -> Tensor:
+    """Value relation transfer loss, train.py:355-368: KL(softmax(teacher v_rel) || softmax(student v_rel)) per row of
+    the un-masked [B*H, T, T] value-relation maps, summed over the last axis, mean over rows."""
+    loss = F.kl_div(F.log_softmax(pred.float(), dim=-1), F.softmax(target.float(), dim=-1), reduction="none")
+    return loss.sum(dim=-1).mean()
 
 
 def init_teacher_state(cfg: dict, seed: int = 1, perturb: bool = False) -> State:

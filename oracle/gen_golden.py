@@ -80,7 +80,9 @@ class RefTeacher(nn.Module):
             mask = O.mask_m1(padding_mask, T, self.conv_layers)
         f = self.post_extract_proj(f)
         x, layer_results, _ = self.encoder(f.clone(), padding_mask=mask)
-        return {"layer_results": [(lr[0], (None, lr[2])) for lr in layer_results],
+        # the forward hook on every encoder layer captures its output (x, (attn, layer_result)), utils/utils.py:65-78;
+        # `attn` is None on the stock layer and (attn_logits, v_rel) once rtrn_attn_forward is bound (train.py:64-69)
+        return {"layer_results": [(lr[0], (lr[1], lr[2])) for lr in layer_results],
                 "features": [f], "padding_mask": mask}
 
 
@@ -255,8 +257,74 @@ def run_case_upsampler_cnn(name, s_over, t_over, B, Lmax, lengths, yaml_distille
     print(name, "loss", float(loss), "cnn", float(cnn), "bytes", os.path.getsize(path))
 
 
+TINY_ATTN_STUDENT = dict(  # ex.yaml family (no TR layer: the attention-map recipe needs matching frame rates and heads)
+    conv_feature_layers="[(32,10,5)] + [(32,3,2)] * 4 + [(32,2,2)] * 2",
+    encoder_layers=2, encoder_embed_dim=96, encoder_ffn_embed_dim=128, encoder_attention_heads=4,
+    conv_pos=16, conv_pos_groups=4, pred_head_final_dim=64, pred_layer_id="[0, 2]",
+    init_conv_layers=False, init_encoder_layers=0,
+)
+
+
+def run_case_attn(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, yaml_train, attn_loss_type, attn_w, vrel_w):
+    """Attention-map / value-relation distillation: ex.yaml recipe (L1 + cosine over pred_layer_id) with
+    attn_loss_weight / v_rel_loss_weight > 0.  As train.py:64-77 does, `rtrn_attn_forward` - compiled from the unmodified
+    utils/utils.py (oracle/ref_extract.py) - is bound over every teacher and student encoder layer; the loss is the
+    reference's OWN `W2V2Distil.calculate_loss` (train.py:236-405), compiled the same way and called on the two result
+    dicts, so nothing in this fixture is builder-restated arithmetic."""
+    import ref_extract as R
+    torch.manual_seed(0)
+    cfg = ref_student_cfg(yaml_distiller, **s_over)
+    assert not cfg.layerwise_proj and not cfg.enable_tr_layer
+    student = CustomStudentModel(cfg)
+    teacher = RefTeacher(O.teacher_config(**t_over, kind="hubert"))
+    perturb_(student, 41)
+    perturb_(teacher, 42)
+    R.bind_attn_forward(teacher.encoder.layers)
+    R.bind_attn_forward(student.encoder.layers)
+    student.eval()
+    teacher.eval()
+    x, pm = O.synth_batch(B, Lmax, lengths, seed=1357)
+    with torch.no_grad():
+        t_res = teacher(x, pm)
+    s_res = student(source=x, padding_mask=pm)
+    ids = eval(cfg.pred_layer_id)
+    train_cfg = dict(yaml_train, attn_loss_weight=attn_w, attn_loss_type=attn_loss_type, v_rel_loss_weight=vrel_w)
+    loss, losses = R.ref_calculate_loss(s_res, t_res, train_cfg=train_cfg, model_cfg=dict(yaml_distiller, **s_over),
+                                        pred_layer_id=ids, num_encoders=cfg.encoder_layers)
+    loss.backward()
+    s_attn, s_vrel = s_res["layer_results"][-1][1]
+    t_attn, t_vrel = t_res["layer_results"][-1][1][0]
+    out = {
+        "student_cfg": dict(s_over, layerwise_proj=False, enable_tr_layer=False, feature_grad_mult=cfg.feature_grad_mult),
+        "teacher_cfg": dict(t_over, kind="hubert"),
+        "train_cfg": {k: train_cfg[k] for k in ("cnn_loss_weight", "rec_loss_weight", "rec_loss_type", "sim_loss_weight",
+                                                "attn_loss_weight", "attn_loss_type", "v_rel_loss_weight",
+                                                "distil_random_layer", "random_layer_weight")},
+        "student_state": {k: v.detach().clone() for k, v in student.state_dict().items()},
+        "teacher_state": {k: v.detach().clone() for k, v in teacher.state_dict().items()},
+        "source": x, "padding_mask": pm, "pred_layer_id": ids,
+        "student_mask": s_res["padding_mask"], "teacher_mask": t_res["padding_mask"],
+        "student_layers": [lr[0].detach() for lr in s_res["layer_results"]],
+        "x": s_res["x"].detach(), "projections": s_res["projections"].detach(),
+        "teacher_layers": [lr[0].detach() for lr in t_res["layer_results"]],
+        "student_attn": s_attn.detach(), "student_vrel": s_vrel.detach(),
+        "teacher_attn": t_attn.detach(), "teacher_vrel": t_vrel.detach(),
+        "loss": loss.detach(), "losses": {k: v.detach() for k, v in losses.items()},
+        "grads": {n: p.grad.detach().clone() for n, p in student.named_parameters() if p.grad is not None},
+        "no_grad_params": [n for n, p in student.named_parameters() if p.grad is None],
+    }
+    path = os.path.join(HERE, "..", "tests", "golden", name + ".pt")
+    torch.save(out, path)
+    print(name, "loss", float(loss), {k: round(float(v), 6) for k, v in losses.items()}, "bytes", os.path.getsize(path))
+
+
 def main():
     import yaml
+    only = sys.argv[1:]  # optional: names of the cases to (re)generate
+    if only:
+        for fn_name in ("run_case", "run_case_split", "run_case_upsampler_cnn", "run_case_attn"):
+            fn = globals()[fn_name]
+            globals()[fn_name] = (lambda f: lambda name, *a, **k: f(name, *a, **k) if name in only else None)(fn)
     with open(os.path.join(REF, "data/conf/fithubert.yaml")) as f:
         ycfg = yaml.safe_load(f)["distiller"]
     # 1.5 - 2 s utterances (75 - 99 frames): parameter gradients are sums over frames, and with the 0.5 s / 27-frame
@@ -269,6 +337,14 @@ def main():
         ecfg = yaml.safe_load(f)["distiller"]
     run_case_split("split_hubert_pad", TINY_SPLIT_STUDENT, TINY_TEACHER, 3, 32000, [32000, 27411, 21000], ecfg)
     run_case_upsampler_cnn("upsampler_cnn_hubert_nopad", TINY_UP_STUDENT, TINY_TEACHER, 2, 28000, [28000, 28000], ecfg)
+    with open(os.path.join(REF, "data/conf/ex.yaml")) as f:
+        etrain = yaml.safe_load(f)["train"]
+    # mse on a padded batch (HuBERT teacher: the two sides mask different key columns); kldiv + value relation un-padded
+    # (with padding the reference's kldiv branch is nan, see oracle attn_map_loss)
+    run_case_attn("attn_mse_hubert_pad", TINY_ATTN_STUDENT, TINY_TEACHER, 3, 20000, [20000, 17411, 13000], ecfg, etrain,
+                  "mse", 200.0, 300.0)
+    run_case_attn("attn_kldiv_hubert_nopad", TINY_ATTN_STUDENT, TINY_TEACHER, 2, 18000, [18000, 18000], ecfg, etrain,
+                  "kldiv", 500.0, 300.0)
 
 
 if __name__ == "__main__":

@@ -112,3 +112,82 @@ def test_oracle_matches_the_reference_classes_live():
     for l in range(3):
         assert rel(to["layer_results"][l][0], tr["layer_results"][l][0]) < 1e-5
         assert rel(to["layer_results"][l][1][1], tr["layer_results"][l][1][1]) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="needs /root/reference")
+def test_loss_restatements_match_the_reference_calculate_loss_live():
+    """The oracle's loss functions against the reference's OWN `W2V2Distil.calculate_loss` (train.py:236-405), compiled from
+    the unmodified source by oracle/ref_extract.py (train.py itself cannot be imported: Lightning / s3prl are absent) and
+    called on synthetic result dicts: the random-layer MSE recipe (fithubert.yaml), L1 + cosine over pred_layer_id
+    (ex.yaml), the CNN-feature L1 term, and the attention-map (mse, kldiv) / value-relation terms."""
+    import ref_extract as R
+    g = torch.Generator().manual_seed(3)
+    B, n, T, D, H = 2, 4, 13, 24, 3
+    proj = [torch.randn(B, T - 1, D, generator=g) for _ in range(n)]
+    t_layers = [torch.randn(T, B, D, generator=g) for _ in range(n)]
+
+    def attn_pair(valid):
+        a = torch.randn(B * H, T, T, generator=g)
+        for b, v in enumerate(valid):
+            a[b * H:(b + 1) * H, :, v:] = float("-inf")
+        return a, torch.randn(B * H, T, T, generator=g)
+
+    s_attn, s_vrel = attn_pair([T, T - 4])
+    t_attn, t_vrel = attn_pair([T, T - 3])  # HuBERT's mask rule keeps one more frame than the student's
+    feats, t_feats = torch.randn(B, T, D, generator=g), torch.randn(B, T, D, generator=g)
+    s_res = {"projections": proj, "features": feats, "layer_results": [(None, None, None)] * (n - 1) + [(None, (s_attn, s_vrel), None)]}
+    t_res = {"layer_results": [(t_layers[i], (None, None)) for i in range(n - 1)] + [(t_layers[-1], ((t_attn, t_vrel), None))],
+             "features": [t_feats]}
+    base = dict(cnn_loss_weight=0, rec_loss_weight=1.0, rec_loss_type="mse", sim_loss_weight=0, attn_loss_weight=0,
+                attn_loss_type="kldiv", v_rel_loss_weight=0, distil_random_layer=0, random_layer_weight=0)
+    # (1) fithubert.yaml: every lower layer picked at random_layer_weight, the last at 1
+    rand_l = [2, 0, 1]
+    tc = dict(base, distil_random_layer=n - 1, random_layer_weight=0.1)
+    ref, ref_losses = R.ref_calculate_loss(s_res, t_res, train_cfg=tc, model_cfg={"layerwise_proj": True},
+                                           pred_layer_id=[n - 1], rand_l=rand_l, num_encoders=n)
+    ours, per = O.distill_loss(proj, t_res["layer_results"], O.layer_weights(n, 0.1))
+    assert abs(float(ours) - float(ref)) < 1e-6 * float(ref)
+    for i, l in enumerate(rand_l):  # logged in the permuted order of rand_l (train.py:319-321)
+        assert abs(float(per[l]) - float(ref_losses[f"rand_l{i}"])) < 1e-6
+    assert abs(float(per[-1]) - float(ref_losses[f"l{n - 1}"])) < 1e-6
+    # (2) ex.yaml: L1 + cosine over pred_layer_id, plus the CNN-feature term
+    ids = [0, 2]
+    tc = dict(base, rec_loss_type="l1", sim_loss_weight=0.7, rec_loss_weight=1.3, cnn_loss_weight=0.5)
+    ref, ref_losses = R.ref_calculate_loss(s_res, t_res, train_cfg=tc, model_cfg={"layerwise_proj": True}, pred_layer_id=ids,
+                                           num_encoders=n)
+    ours, rec, sim = O.distill_loss_sim(proj, t_res["layer_results"], ids, "l1", 1.3, 0.7)
+    cnn = O.cnn_feature_loss(feats, t_feats)
+    assert abs(float(ours + 0.5 * cnn) - float(ref)) < 1e-6 * float(ref)
+    assert abs(float(cnn) - float(ref_losses["cnn_loss"])) < 1e-6
+    for k, i in enumerate(ids):
+        assert abs(float(rec[k] + sim[k]) - float(ref_losses[f"layer{i}"])) < 1e-6
+    # (3) attention map (mse on padded logits) + value relation
+    tc = dict(base, attn_loss_weight=2.0, attn_loss_type="mse", v_rel_loss_weight=3.0)
+    ref, ref_losses = R.ref_calculate_loss(s_res, t_res, train_cfg=tc, model_cfg={"layerwise_proj": True}, pred_layer_id=ids,
+                                           num_encoders=n)
+    rec_only, _, _ = O.distill_loss_sim(proj, t_res["layer_results"], ids, "mse", 1.0, 0.0)
+    a, v = O.attn_map_loss(s_attn, t_attn, "mse"), O.value_relation_loss(s_vrel, t_vrel)
+    assert abs(float(a) - float(ref_losses["attn_loss"])) < 1e-6 * float(a)
+    assert abs(float(v) - float(ref_losses["v_rel_loss"])) < 1e-6 * float(v)
+    assert abs(float(rec_only + 2.0 * a + 3.0 * v) - float(ref)) < 1e-6 * float(ref)
+    # the mean runs over the keys neither side masks: B*H*T * min(valid) columns
+    d2 = (s_attn - t_attn)[..., :T - 4].pow(2)
+    expect = (d2[:H].sum() + (s_attn - t_attn)[:H, :, T - 4:].pow(2).sum() + d2[H:].sum()) / (H * T * (T + T - 4))
+    assert abs(float(a) - float(expect)) < 1e-6 * float(a)
+    # (4) kldiv: nan on a padded batch in the reference (documented quirk), equal on an un-padded one
+    tc = dict(base, attn_loss_weight=1.0, attn_loss_type="kldiv")
+    ref, ref_losses = R.ref_calculate_loss(s_res, t_res, train_cfg=tc, model_cfg={"layerwise_proj": True}, pred_layer_id=ids,
+                                           num_encoders=n)
+    assert torch.isnan(ref_losses["attn_loss"]) and torch.isnan(O.attn_map_loss(s_attn, t_attn, "kldiv"))
+    s2, t2 = torch.randn(B * H, T, T, generator=g), torch.randn(B * H, T, T, generator=g)
+    s_res["layer_results"][-1] = (None, (s2, s_vrel), None)
+    t_res["layer_results"][-1] = (t_layers[-1], ((t2, t_vrel), None))
+    ref, ref_losses = R.ref_calculate_loss(s_res, t_res, train_cfg=tc, model_cfg={"layerwise_proj": True}, pred_layer_id=ids,
+                                           num_encoders=n)
+    a = O.attn_map_loss(s2, t2, "kldiv")
+    assert abs(float(a) - float(ref_losses["attn_loss"])) < 1e-6 * float(a)
+    # v_rel_loss_weight > 0 without attn_loss_weight: the stock layers return None where the pair would be
+    s_res["layer_results"][-1] = (None, None, None)
+    with pytest.raises(TypeError):
+        R.ref_calculate_loss(s_res, t_res, train_cfg=dict(base, v_rel_loss_weight=1.0), model_cfg={"layerwise_proj": True},
+                             pred_layer_id=ids, num_encoders=n)
