@@ -27,6 +27,12 @@ class _StudentFn(torch.autograd.Function):
         model._last_ctx = c
         feats = c.cnn_out if c.cnn_out is not None else c.feats  # the returned `features` (features_to_distill)
         outs = (c.preds if c.preds is not None else source.new_zeros(0), feats, *c.layers)
+        ctx.n_layers_out = len(c.layers)
+        if getattr(model, "_return_attn", False):
+            # attention-map recipe: the last layer's (attn_logits, v_rel), fp32 [B*H, T, pitch] (train.py:64-77)
+            g = model._geom
+            maps = E.attn_maps(c.layer_ctx[-1].qkv, c.valid_s, c.B, c.Ts, g.H, g.d)
+            outs = outs + (maps["attn"], maps["vrel"])
         # autograd stamps the RETURNED tensor objects with this node's grad_fn.  The context the backward keeps must not
         # hold those same objects, or node -> ctx -> c -> tensor -> node is a reference cycle no collector sees (every
         # call's saved activations would stay allocated): keep detached aliases instead.
@@ -43,8 +49,9 @@ class _StudentFn(torch.autograd.Function):
         return outs
 
     @staticmethod
-    def backward(ctx, dpreds, dfeat, *dlayers):
+    def backward(ctx, dpreds, dfeat, *rest):
         model, c = ctx.model, ctx.c
+        dlayers, dmaps = rest[:ctx.n_layers_out], rest[ctx.n_layers_out:]
         P, W, G = model.engine_state(True)
         G.zero_()
         if c.preds is None:
@@ -59,6 +66,21 @@ class _StudentFn(torch.autograd.Function):
         if dfeat is not None:
             pre_scaled, _FEAT_GRAD_SCALED[0] = _FEAT_GRAD_SCALED[0], False
             dfeat = ((dfeat.float() * scale) if (scale != 1.0 and not pre_scaled) else dfeat).to(torch.float16).contiguous()
+        c.attn_grad = []
+        if any(d is not None for d in dmaps):
+            # gradients wrt the last layer's maps -> fp16 operands of the head-gradient kernels, centred in fp16's range
+            # by a power of two that `alpha` takes out again (one scalar D2H per map: this is the autograd API path)
+            pre_scaled, _MAP_GRAD_SCALED[0] = _MAP_GRAD_SCALED[0], False
+            sc = 1.0 if pre_scaled else scale
+            for kind, d in zip(("qk", "vv"), dmaps):
+                if d is None:
+                    continue
+                d = torch.nan_to_num(d.float(), nan=0.0, posinf=0.0, neginf=0.0)
+                amax = float(d.abs().max())
+                if amax == 0.0:
+                    continue
+                boost = E._pow2_near(256.0 / (amax * sc))
+                c.attn_grad.append((kind, (d * (sc * boost)).to(torch.float16).contiguous(), model._geom.d ** -0.5 / boost))
         E.student_backward(P, W, model._geom, G, c, dpreds, dl, dfeatures=dfeat)
         grads = G.export(scale=scale)
         return (None, None, None, *[grads.get(n) for n in ctx.names])
@@ -68,7 +90,9 @@ def student_apply(model, source, valid):
     params = [p for _, p in model.named_parameters()]
     outs = _StudentFn.apply(model, source, valid, *params)
     c = model._last_ctx
-    return c, (outs[0] if c.preds is not None else None), list(outs[2:]), outs[1]
+    n = len(c.layers)
+    maps = tuple(outs[2 + n:]) if len(outs) > 2 + n else None
+    return c, (outs[0] if c.preds is not None else None), list(outs[2:2 + n]), outs[1], maps
 
 
 class _DistillLossFn(torch.autograd.Function):
@@ -141,6 +165,49 @@ class _FeatureL1Fn(torch.autograd.Function):
         return dpred, None, None
 
 
+class _AttnMapLossFn(torch.autograd.Function):
+    """Attention distribution transfer / value relation transfer loss on [B*H, T, T] maps (train.py:327-368) and its
+    gradient wrt the student's map from one kernel.
+    apply(pred, target, valid_s, valid_t (device int32 or None), H, mode (0 mse, 1 kldiv), loss_mult, loss_scale)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, valid_s, valid_t, H, mode, loss_mult, scale):
+        from . import kernels as K
+        BH, T = pred.shape[0], pred.shape[1]
+
+        def pitched(t):  # rows of a multiple of 8 floats (what the engine's maps are views of); else a padded copy
+            if t.dtype == torch.float32 and t.stride(2) == 1 and t.stride(1) % 8 == 0 and t.stride(0) == T * t.stride(1) \
+                    and t.data_ptr() % 16 == 0:
+                return t.as_strided((BH, T, t.stride(1)), (T * t.stride(1), t.stride(1), 1))
+            p = torch.empty(BH, T, (T + 7) // 8 * 8, device=t.device, dtype=torch.float32)
+            p[..., :T] = t
+            return p
+
+        s_, t_ = pitched(pred.detach()), pitched(target.detach())
+        if s_.shape != t_.shape:
+            t2 = torch.empty_like(s_)
+            t2[..., :T] = t_[..., :T]
+            t_ = t2
+        ctx.scale = float(scale)
+        loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+        G = torch.empty(s_.shape, device=pred.device, dtype=torch.float16)
+        base = ctx.scale * loss_mult
+        ctx.boost = E._pow2_near((1.0 if mode == 0 else 0.25 * T) / base)
+        K.attn_map_loss(s_, t_, valid_s, valid_t, G, loss, BH // H, T, H, mode, loss_mult, base * ctx.boost)
+        ctx.save_for_backward(G)
+        ctx.T = T
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (G,) = ctx.saved_tensors
+        w = float(g)  # the loss weight (x any caller rescaling)
+        _PENDING_SCALE[0] = ctx.scale
+        _MAP_GRAD_SCALED[0] = True
+        return (G[..., :ctx.T].float() * (w / ctx.boost),) + (None,) * 7
+
+
+_MAP_GRAD_SCALED = [False]  # the map gradients about to reach _StudentFn.backward already carry the loss scale
 _FEAT_GRAD_SCALED = [False]  # the features gradient about to reach _StudentFn.backward already carries the loss scale
 
 

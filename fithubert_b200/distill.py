@@ -66,9 +66,20 @@ class W2V2Distil(nn.Module):
         self.rec_loss_type, self.sim_loss_weight = t["rec_loss_type"], t["sim_loss_weight"]
         self.attn_loss_weight, self.v_rel_loss_weight = t["attn_loss_weight"], t["v_rel_loss_weight"]
         self.random_layer_weight = t["random_layer_weight"]
-        for name, w in (("attn_loss_weight", self.attn_loss_weight), ("v_rel_loss_weight", self.v_rel_loss_weight)):
-            if w:
-                raise NotImplementedError(f"{name} > 0 is outside the B200 hot path (SURVEY 2.1 / 8f)")
+        self.attn_loss_type = t.get("attn_loss_type", "kldiv")
+        if self.attn_loss_weight > 0:
+            # Attention-map distillation (train.py:64-77): the reference re-binds the forward of EVERY entry of
+            # encoder.layers to utils/utils.py `rtrn_attn_forward` after touching its `.self_attn`; with a time-reduction
+            # layer entry 0 is an nn.Conv1d (modules/module.py:230-236) and construction fails - same error here
+            if self.student_model.enable_tr_layer:
+                raise AttributeError("'Conv1d' object has no attribute 'self_attn'")
+            if self.attn_loss_type not in ("mse", "kldiv"):
+                raise NotImplementedError("attn_loss_type must be one of 'mse', 'kldiv'.")
+            self.student_model._return_attn = True
+            self.teacher_model.model._return_attn = True
+        elif self.v_rel_loss_weight > 0:
+            # train.py:357-358 subscripts layer_results[-1][1], which is None unless the attention recipe is bound
+            raise TypeError("'NoneType' object is not subscriptable")
         if self.sim_loss_weight and t["distil_random_layer"] > 0:
             # train.py:304-306 reduces the 3-D cosine loss over dim 3 in this branch and cannot execute
             raise NotImplementedError("sim_loss_weight > 0 needs distil_random_layer = 0 (the reference's random-layer "
@@ -167,6 +178,31 @@ class W2V2Distil(nn.Module):
             cnn_loss = _FeatureL1Fn.apply(student_results["features"], teacher_results["features"][0], S)
             losses = {"cnn_loss": cnn_loss, **losses}
             total = total + self.cnn_loss_weight * cnn_loss
+        if self.attn_loss_weight > 0:
+            # attention distribution transfer / value relation transfer (train.py:327-378) on the last layer's maps
+            from .autograd import _AttnMapLossFn
+            pred, v_pred = student_results["layer_results"][-1][1]
+            target, v_target = teacher_results["layer_results"][-1][1][0]
+            if pred.shape != target.shape:
+                raise RuntimeError(f"The size of tensor a {tuple(pred.shape)} must match the size of tensor b "
+                                   f"{tuple(target.shape)}")
+            BH, T = pred.shape[:2]
+            H = self.student_model._geom.H
+            B = BH // H
+            vs, vt = student_results.get("_valid"), teacher_results.get("_valid")
+            dev = pred.device
+            vs_d, vt_d = E._valid_tensor(vs, dev), E._valid_tensor(vt, dev)
+            if self.attn_loss_type == "mse":
+                count = H * T * sum(min(a, b, T) for a, b in zip(vs or [T] * B, vt or [T] * B))
+                attn_loss = _AttnMapLossFn.apply(pred, target, vs_d, vt_d, H, 0, 1.0 / count, S)
+            else:
+                attn_loss = _AttnMapLossFn.apply(pred, target, vs_d, vt_d, H, 1, 1.0 / (BH * T), S)
+            losses["attn_loss"] = attn_loss
+            total = total + self.attn_loss_weight * attn_loss
+            if self.v_rel_loss_weight > 0:
+                v_rel_loss = _AttnMapLossFn.apply(v_pred, v_target, None, None, H, 1, 1.0 / (BH * T), S)
+                losses["v_rel_loss"] = v_rel_loss
+                total = total + self.v_rel_loss_weight * v_rel_loss
         return total, losses
 
     def _loss_dict(self, per_layer: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -252,6 +288,7 @@ class W2V2Distil(nn.Module):
 
         n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
         Pt, Wt = tm.engine_state()
+        t_extras = {} if self.attn_loss_weight > 0 else None  # the teacher's last-layer q | k | v (attention-map recipe)
         if self._tgt_buf is None or self._tgt_buf.shape[1:3] != (B, T):
             self._tgt_buf = torch.empty(n, B, T, tm._geom.E, device=dev, dtype=f16)
         P, W, G = sm.engine_state(True)
@@ -262,13 +299,13 @@ class W2V2Distil(nn.Module):
             side.wait_stream(main)  # the H2D copy of x, the previous step's readers of the target buffer
             with torch.cuda.stream(side):
                 tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
-                                                 wave_chunks=chunks)
+                                                 wave_chunks=chunks, extras=t_extras)
             c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
                                   wave_chunks=chunks)
             main.wait_stream(side)
         else:
             tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, out_buf=self._tgt_buf, slots=self.tgt_slots,
-                                             wave_chunks=chunks)
+                                             wave_chunks=chunks, extras=t_extras)
             c = E.student_forward(P, W, sm._geom, x, s_valid, train=True, heads="all", drop=sm.drop_cfg(),
                                   wave_chunks=chunks)
         layer_loss = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -336,6 +373,16 @@ class W2V2Distil(nn.Module):
             dfeatures = c.cnn_out
             self.last_cnn_loss = cnn[0]
             layer_loss = torch.cat([layer_loss, cnn * self.cnn_loss_weight])
+        self.last_attn_losses = None
+        if self.attn_loss_weight > 0:
+            # attention distribution transfer + value relation transfer on the LAST layer's maps (train.py:327-378); the
+            # gradients wrt the student's maps wait in c.attn_grad for the last layer's attention backward
+            al = E.attn_transfer_losses(c, sm._geom, t_extras, tm._geom, loss_type=self.attn_loss_type,
+                                        w_attn=float(self.attn_loss_weight), w_vrel=float(self.v_rel_loss_weight),
+                                        grad_scale=grad_scale, valid_s=c.valid, valid_t=t_extras["valid_host"])
+            self.last_attn_losses = al
+            wv = torch.tensor([float(self.attn_loss_weight), float(self.v_rel_loss_weight)], device=dev)
+            layer_loss = torch.cat([layer_loss, al * wv])
         try:
             E.student_backward(P, W, sm._geom, G, c, dpred, dpred_colsum=dcs, on_progress=hook, dfeatures=dfeatures)
         finally:
@@ -359,7 +406,8 @@ class W2V2Distil(nn.Module):
         if self._micro == self.accumulate:
             self._micro = 0
             self.optimizer_step()
-        self.last_layer_losses = layer_loss[:self.n_pred]  # (a trailing slot, if present, is cnn_loss_weight * cnn_loss)
+        # trailing slots, if present: cnn_loss_weight * cnn_loss, then attn_loss_weight * attn_loss, v_rel_loss_weight * v_rel_loss
+        self.last_layer_losses = layer_loss[:self.n_pred]
         return layer_loss.sum()
 
     def training_epoch_end(self, training_step_outputs=None):

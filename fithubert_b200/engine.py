@@ -530,7 +530,7 @@ def frontend_fwd(P, W: WeightSet, g: Geometry, wave, valid, save: bool,
 
 def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, T, save: bool, want_lr: bool,
               out: Optional[torch.Tensor] = None, drop: Optional[DropCfg] = None, x32: Optional[torch.Tensor] = None,
-              out32: Optional[torch.Tensor] = None, stream32: bool = True):
+              out32: Optional[torch.Tensor] = None, stream32: bool = True, keep_qkv: bool = False):
     """One post-LN transformer layer (reference modules/module.py:557-580) on x [B*T, E].
     The residual stream never passes through 16 bits: x32 is the fp32 copy of x (None for the first layer, whose input is
     the fp16 output of a GEMM anyway), the out_proj / fc2 epilogues add it in fp32 and write the sums y1 / y2 in fp32, the
@@ -556,8 +556,12 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
         x2 = out if out is not None else torch.empty(M, E, device=dev, dtype=f16)
         K.layernorm_fwd(y2, P[prefix + "final_layer_norm.weight"], P[prefix + "final_layer_norm.bias"], x2)
         s.out, s.lr, s.out32 = x2, lr, None
+        if keep_qkv:
+            s.qkv = qkv
         return s
     qkv = K.linear(x, W[f"l{l}.wqkv"].view(3 * E, E), W[f"l{l}.bqkv"])
+    if keep_qkv:
+        s.qkv = qkv
     # training with F == E: the inputs of out_proj / fc1 / fc2 (attn, x1, h) share one [3, M, E] buffer so that their three
     # weight-gradient GEMMs run as one batched launch in the backward (wgrad_batch_enabled)
     xs = torch.empty(3, M, E, device=dev, dtype=f16) if (save and F == E and wgrad_batch_enabled()) else None
@@ -596,14 +600,108 @@ def layer_fwd(P, W: WeightSet, g: Geometry, prefix: str, l: int, x, valid_t, B, 
 
 
 # =============================================================================================
+# attention-map / value-relation distillation
+# =============================================================================================
+def attn_maps(qkv: torch.Tensor, valid_dev, B: int, T: int, H: int, d: int, want=("attn", "vrel"), out=None):
+    """What `rtrn_attn_forward` (reference utils/utils.py:190-232) returns next to a layer's output: the un-normalised
+    attention logits bmm(q * scaling, k^T) with -inf at padded keys, and v_rel = bmm(v * scaling, v^T); each fp32
+    [B*H, T, pitch] (pitch = T rounded up to 8; the columns beyond T are padding).  qkv: that layer's fused projection
+    output [B*T, 3*H*d] fp16.  out: optional dict of buffers to write into."""
+    E = H * d
+    q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+    res = {}
+    if "attn" in want:
+        res["attn"] = K.attn_scores(q, k, valid_dev, B, T, H, d, d ** -0.5, out=None if out is None else out.get("attn"))
+    if "vrel" in want:
+        res["vrel"] = K.attn_scores(v, v, None, B, T, H, d, d ** -0.5, out=None if out is None else out.get("vrel"))
+    return res
+
+
+def _pow2_near(x: float) -> float:
+    return 2.0 ** max(-40, min(40, round(math.log2(max(x, 1e-30)))))
+
+
+def attn_transfer_losses(c, g: Geometry, t_extras: dict, gt: Geometry, *, loss_type: str, w_attn: float, w_vrel: float,
+                         grad_scale: float, valid_s: Optional[List[int]], valid_t: Optional[List[int]]):
+    """Attention distribution transfer + value relation transfer losses of the LAST layer (reference train.py:327-368) and
+    their gradients wrt the student's maps, for the fused training step.  Returns fp32 [2] (attn_loss, v_rel_loss,
+    un-weighted); stores c.attn_grad = [(kind, G fp16 [B*H, T, pitch], alpha)]: student_backward adds
+    alpha * (G k, G^T q) to (dq, dk) for kind 'qk' and alpha * (G + G^T) v to dv for kind 'vv'.
+    grad_scale: the loss scale of the fp16 gradients (x 1/accumulation ...).  G additionally carries a power of two that
+    centres it in fp16's range; alpha takes it out again in fp32."""
+    B, T, H, d = c.B, c.Ts, g.H, g.d
+    if g.tr:
+        # train.py:70-77 touches `.self_attn` of every encoder.layers entry; entry 0 is the time-reduction nn.Conv1d
+        raise AttributeError("'Conv1d' object has no attribute 'self_attn'")
+    if t_extras["T"] != T or gt.H != H or t_extras["B"] != B:
+        raise RuntimeError(f"The size of tensor a ({B * H}, {T}, {T}) must match the size of tensor b "
+                           f"({t_extras['B'] * gt.H}, {t_extras['T']}, {t_extras['T']}): the attention maps of student and "
+                           "teacher need the same head count and frame rate")
+    if loss_type not in ("mse", "kldiv"):
+        raise NotImplementedError("attn_loss_type must be one of 'mse', 'kldiv'.")
+    dev = c.lay.device
+    s_qkv, t_qkv = c.layer_ctx[-1].qkv, t_extras["qkv"]
+    rows = B * H * T
+    losses = torch.zeros(2, device=dev, dtype=f32)
+    c.attn_grad = []
+    bufs = None
+    if w_attn > 0:
+        S_s = attn_maps(s_qkv, c.valid_s, B, T, H, d, ("attn",))["attn"]
+        S_t = attn_maps(t_qkv, t_extras["valid_t"], B, T, gt.H, gt.d, ("attn",))["attn"]
+        bufs = (S_s, S_t)
+        if loss_type == "mse":
+            vs = valid_s if valid_s is not None else [T] * B
+            vt = valid_t if valid_t is not None else [T] * B
+            loss_mult = 1.0 / (H * T * sum(min(a, b, T) for a, b in zip(vs, vt)))
+            boost = _pow2_near(1.0 / (grad_scale * w_attn * loss_mult))
+        else:
+            loss_mult = 1.0 / rows
+            boost = _pow2_near(0.25 * T / (grad_scale * w_attn * loss_mult))
+        G = torch.empty(S_s.shape, device=dev, dtype=f16)
+        K.attn_map_loss(S_s, S_t, c.valid_s, t_extras["valid_t"], G, losses[0:1], B, T, H, 0 if loss_type == "mse" else 1,
+                        loss_mult, grad_scale * w_attn * loss_mult * boost)
+        c.attn_grad.append(("qk", G, d ** -0.5 / boost))
+    if w_vrel > 0:
+        out = None if bufs is None else {"vrel": bufs[0]}
+        R_s = attn_maps(s_qkv, None, B, T, H, d, ("vrel",), out)["vrel"]
+        out = None if bufs is None else {"vrel": bufs[1]}
+        R_t = attn_maps(t_qkv, None, B, T, gt.H, gt.d, ("vrel",), out)["vrel"]
+        loss_mult = 1.0 / rows
+        boost = _pow2_near(0.25 * T / (grad_scale * w_vrel * loss_mult))
+        G = torch.empty(R_s.shape, device=dev, dtype=f16)
+        K.attn_map_loss(R_s, R_t, None, None, G, losses[1:2], B, T, H, 1, loss_mult, grad_scale * w_vrel * loss_mult * boost)
+        c.attn_grad.append(("vv", G, d ** -0.5 / boost))
+    return losses
+
+
+def attn_transfer_backward(c, g: Geometry, qkv: torch.Tensor, dqkv: torch.Tensor):
+    """Adds the gradients of the last layer's attention-map / value-relation terms to dqkv [B*Ts, 3E] (after the flash
+    attention backward has written it): logits = scaling * q k^T -> dq += scaling * dS k, dk += scaling * dS^T q;
+    v_rel = scaling * v v^T -> dv += scaling * (dR + dR^T) v."""
+    B, T, H, d = c.B, c.Ts, g.H, g.d
+    E = H * d
+    q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+    dq, dk, dv = dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:]
+    for kind, G, alpha in c.attn_grad:
+        if kind == "qk":
+            K.attn_scores_bwd(G, k, dq, B, T, H, d, alpha, trans=0)
+            K.attn_scores_bwd(G, q, dk, B, T, H, d, alpha, trans=1)
+        else:
+            K.attn_scores_bwd(G, v, dv, B, T, H, d, alpha, trans=0)
+            K.attn_scores_bwd(G, v, dv, B, T, H, d, alpha, trans=1)
+
+
+# =============================================================================================
 # teacher
 # =============================================================================================
 def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], out_buf=None, slots=None,
-                    wave_chunks=None, want_lr: bool = False):
+                    wave_chunks=None, want_lr: bool = False, extras: Optional[dict] = None):
     """Frozen teacher forward (reference utils/utils.py:80-99 around fairseq HubertModel /
     Wav2Vec2Model.extract_features).  Returns (layers [n_layers, B, T, E] fp16, features [B, T, E]).
     slots: optional list mapping teacher layer -> row of out_buf (None = not a distillation target: that layer's
-    output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather."""
+    output goes to a scratch buffer), so the loss kernel finds the pred_layer_id targets stacked without a gather.
+    extras: a dict to fill with what the attention-map recipe needs from the LAST layer (utils/utils.py:190-232 bound over the
+    teacher's layers, train.py:64-69): 'qkv' [B*T, 3E] fp16, 'valid_t' (device int32 or None), 'B', 'T'."""
     W.ensure_fresh()
     import os
     # the frozen teacher carries its residual stream in fp16 by default (A/B on B200, profiles/r02i_teacher_stream16_ab.txt:
@@ -620,7 +718,7 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     scratch = None
     lrs = []
     ping = [torch.empty(B * T, E, device=wave.device, dtype=f32) for _ in range(2)]  # fp32 copies of the layer outputs
-    last = g.n_layers if slots is None else 1 + max(l for l, s in enumerate(slots) if s is not None)
+    last = g.n_layers if (slots is None or extras is not None) else 1 + max(l for l, s in enumerate(slots) if s is not None)
     for l in range(last):  # layers above the highest target are never needed
         slot = l if slots is None else slots[l]
         if slot is None:
@@ -629,9 +727,12 @@ def teacher_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
         else:
             dst = out_buf[slot].view(B * T, E)
         s = layer_fwd(P, W, g, f"encoder.layers.{l}.", l, x, valid_t, B, T, save=False, want_lr=want_lr, out=dst, x32=x32,
-                      out32=ping[l & 1] if (l + 1 < last and stream32) else None, stream32=stream32)
+                      out32=ping[l & 1] if (l + 1 < last and stream32) else None, stream32=stream32,
+                      keep_qkv=extras is not None and l == g.n_layers - 1)
         x, x32 = s.out, s.out32
         lrs.append(s.lr)
+        if extras is not None and l == g.n_layers - 1:
+            extras.update(qkv=s.qkv, valid_t=valid_t, valid_host=c.valid, B=B, T=T)
     if want_lr:  # the hook output of every layer is (x, (attn, layer_result)), utils/utils.py:65-78
         return out_buf, c.feats.view(B, T, E), lrs
     return out_buf, c.feats.view(B, T, E)
@@ -680,7 +781,7 @@ def _compose_heads(W: WeightSet, g: Geometry, hs: Dict[str, int], n: int):
 
 def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int]], *, train: bool,
                     heads: str = "all", want_lr: bool = False, pred_buf=None, drop: Optional[DropCfg] = None,
-                    wave_chunks=None, n_run: Optional[int] = None):
+                    wave_chunks=None, n_run: Optional[int] = None, keep_qkv_last: bool = False):
     """Student forward (reference modules/model.py:420-552).  heads: 'all' (12 LayerWiseProjHeads),
     'last' (after _disable_projection_heads: final_proj on the last layer), 'none'.
     n_run: transformer layers to execute (the reference's `layer=` early exit, modules/module.py:335-340); the heads then
@@ -716,7 +817,8 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
     c.x_last = x
     for l in range(n_run):
         s = layer_fwd(P, W, g, f"encoder.layers.{l + off}.", l, x, valid_s, B, Ts, save=train, want_lr=want_lr, out=lay[l],
-                      drop=drop, x32=x32, out32=ping[l & 1] if l + 1 < n_run else None)
+                      drop=drop, x32=x32, out32=ping[l & 1] if l + 1 < n_run else None,
+                      keep_qkv=keep_qkv_last and l == g.n_layers - 1)
         c.layer_ctx.append(s)
         x, x32 = s.out, s.out32
     c.x_last = x  # output of the last executed layer (the TR conv / prologue output when n_run == 0)
@@ -1108,6 +1210,8 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
         dq_ws = torch.empty(M_, E, device=dev, dtype=f32) if d in (40, 64) else None
         K.attn_bwd(s.qkv, c.valid_s, s.attn, dattn, s.lse, dqkv, delta, B, Ts, H, d, d ** -0.5, drop=dl(DropCfg.ATTN),
                    dq_ws=dq_ws)
+        if l == g.n_layers - 1 and getattr(c, "attn_grad", None):
+            attn_transfer_backward(c, g, s.qkv, dqkv)  # attention-map / value-relation terms (train.py:327-368)
         with aside(dqkv):
             K.colsum(dqkv, G_.span(p + "self_attn.q_proj.bias", p + "self_attn.v_proj.bias"))
             K.linear_wgrad(dqkv, s.x, out=G_.span(p + "self_attn.q_proj.weight", p + "self_attn.v_proj.weight").view(3 * E, E),

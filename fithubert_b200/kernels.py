@@ -331,6 +331,35 @@ def attn_bwd(qkv, valid, out, dout, lse, dqkv, delta_ws, B, T, H, d, scale, drop
             "fhb_attn_bwd")
 
 
+def attn_scores(a, b, valid, B, T, H, d, scale, out=None):
+    """Un-normalised attention logits / value relation of one layer (reference utils/utils.py:190-232): a, b = two head
+    blocks of the fused [B*T, 3*H*d] projection output (strided views q | k | v).  Returns fp32 [B*H, T, pitch]."""
+    assert a.dtype == f16 and b.dtype == f16 and a.stride(0) == b.stride(0) and a.stride(1) == 1
+    pitch = (T + 7) // 8 * 8
+    if out is None:
+        out = torch.empty(B * H, T, pitch, device=a.device, dtype=torch.float32)
+    L.check(L.lib().fhb_attn_scores(L.ptr(a), L.ptr(b), C.c_int64(a.stride(0)), L.ptr(valid), L.ptr(out), C.c_int64(pitch),
+                                    B, T, H, d, _f(scale), L.stream_ptr()), "fhb_attn_scores")
+    return out
+
+
+def attn_map_loss(s, t, valid_s, valid_t, ds, loss, B, T, H, mode, loss_mult, grad_mult):
+    """mode 0: mse over the keys neither side masks; 1: KL(softmax(t) || softmax(s)) per row (train.py:327-368).
+    loss (fp32 [1]) is accumulated; ds (fp16, laid out like s) receives grad_mult * d(row terms)/d(s)."""
+    assert s.dtype == torch.float32 and t.dtype == torch.float32 and ds.dtype == f16 and s.shape == t.shape == ds.shape
+    L.check(L.lib().fhb_attn_map_loss(L.ptr(s), L.ptr(t), C.c_int64(s.shape[-1]), L.ptr(valid_s), L.ptr(valid_t), L.ptr(ds),
+                                      L.ptr(loss), B, T, H, mode, _f(loss_mult), _f(grad_mult), L.stream_ptr()),
+            "fhb_attn_map_loss")
+
+
+def attn_scores_bwd(g, m, out, B, T, H, d, alpha, trans, accumulate=True):
+    """out head block (+)= alpha * (g or g^T) @ m head block: the gradient of attn_scores back into q / k / v."""
+    assert g.dtype == f16 and m.dtype == f16 and out.dtype == f16 and m.stride(1) == 1 and out.stride(1) == 1
+    L.check(L.lib().fhb_attn_scores_bwd(L.ptr(g), C.c_int64(g.shape[-1]), L.ptr(m), C.c_int64(m.stride(0)), L.ptr(out),
+                                        C.c_int64(out.stride(0)), B, T, H, d, _f(alpha), int(trans), int(accumulate),
+                                        L.stream_ptr()), "fhb_attn_scores_bwd")
+
+
 def distill_loss(pred, tgt, weights, layer_loss, dpred, n_layers, B, Tp, Tt, D, loss_type=0, grad_scale=1.0,
                  dbias=None, dbias_layer_stride=0):
     assert pred.dtype == f16 and tgt.dtype == f16 and (dpred is None or dpred.dtype == bf16)

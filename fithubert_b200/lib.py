@@ -104,7 +104,7 @@ EXPORTS = [
     "fhb_last_error", "fhb_abi_version", "fhb_set_pdl", "fhb_set_reserved_sms", "fhb_gemm", "fhb_conv0_gn_gelu_fwd", "fhb_conv0_gn_gelu_bwd", "fhb_conv0_im2col", "fhb_conv0_bwd_finalize",
     "fhb_layernorm_fwd", "fhb_layernorm_bwd", "fhb_layernorm_fwd32", "fhb_layernorm_bwd32", "fhb_posconv_pack", "fhb_posconv_wn_prep",
     "fhb_posconv_finish_fwd", "fhb_posconv_finish_bwd", "fhb_posconv_unpack_bwd", "fhb_posconv_wn_bwd",
-    "fhb_attn_fwd", "fhb_attn_bwd", "fhb_distill_loss_fwd_bwd", "fhb_distill_loss_sim_fwd_bwd", "fhb_adamw_multi", "fhb_prep_multi",
+    "fhb_attn_fwd", "fhb_attn_bwd", "fhb_attn_scores", "fhb_attn_map_loss", "fhb_attn_scores_bwd", "fhb_distill_loss_fwd_bwd", "fhb_distill_loss_sim_fwd_bwd", "fhb_adamw_multi", "fhb_prep_multi",
     "fhb_colsum", "fhb_colsum_batched", "fhb_head_bias_grads", "fhb_add_bf16", "fhb_mul_dgelu", "fhb_mul_bf16", "fhb_dropout", "fhb_mask_lengths", "fhb_memset2d",
 ]
 

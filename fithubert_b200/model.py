@@ -256,6 +256,7 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
                                 cfg.conv_pos_groups, cfg.conv_pos, cfg.encoder_layers, cfg.pred_head_final_dim, True,
                                 tr=cfg.enable_tr_layer, n_split=0 if cfg.layerwise_proj else self.n_tasks, inter=inter,
                                 grad_mult=cfg.feature_grad_mult)
+        self._return_attn = False  # attention-map recipe (train.py:64-77): the last layer also returns (logits, v_rel)
         self._weights = None
         self._grads = None
         self._conv_layers = layers
@@ -357,18 +358,28 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             if not self.layerwise_proj and heads != "all":
                 raise NotImplementedError("fine-tuning the SplitLinear recipe without its head is not implemented")
             from .autograd import student_apply
-            c, preds, layers_out, feats_out = student_apply(self, source, valid)
+            c, preds, layers_out, feats_out, maps = student_apply(self, source, valid)
         else:
             P, W, _ = self.engine_state(False)
             c = E.student_forward(P, W, self._geom, source, valid, train=False, heads=heads, want_lr=True,
-                                  drop=self.drop_cfg(), n_run=n_run)
+                                  drop=self.drop_cfg(), n_run=n_run, keep_qkv_last=self._return_attn)
             preds, layers_out = c.preds, c.layers
             feats_out = c.cnn_out if c.cnn_out is not None else c.feats
+            maps = None
+            if self._return_attn and len(c.layer_ctx) == self._geom.n_layers:
+                maps = E.attn_maps(c.layer_ctx[-1].qkv, c.valid_s, c.B, c.Ts, self._geom.H, self._geom.d)
+                maps = (maps["attn"], maps["vrel"])
         B, T, Ts, Em = c.B, c.T, c.Ts, self._geom.E
         mask = _frame_mask(valid, T, dev)
         layer_results = [(lo.view(B, Ts, Em).transpose(0, 1), None,
                           None if lr is None else lr.view(B, Ts, Em).transpose(0, 1))
                          for lo, lr in zip(layers_out, c.lrs)]
+        if maps is not None:
+            # utils/utils.py:190-258 bound over the layers (train.py:70-77): a layer's second output is (attn_logits, v_rel)
+            # instead of None.  The reference returns the pair for every layer and reads the LAST one (train.py:329,357);
+            # only that one is materialised here ([B*H, T, T] fp32 each - the other layers keep the flash kernels)
+            x_, _, lr_ = layer_results[-1]
+            layer_results[-1] = (x_, (maps[0][..., :Ts], maps[1][..., :Ts]), lr_)
         if not self.layerwise_proj:
             # reference modules/model.py:504-518: x stays the encoder output, projections is ONE [B, N, T, D] tensor
             projections = None if preds is None else preds.permute(1, 0, 2, 3)
@@ -396,6 +407,7 @@ class CustomStudentModel(_ParamCacheMixin, nn.Module):
             "layer_results": layer_results,
             "tr_layer_results": [] if c.tr is None else [c.tr.view(B, Ts, Em).transpose(0, 1)],
             "projections": projections,
+            "_valid": valid,  # (not in the reference) per-sample valid frame counts behind `padding_mask`, host ints
         }
 
     def extract_features(self, source, padding_mask, layer=None):
@@ -422,6 +434,7 @@ class TeacherModel(_ParamCacheMixin, nn.Module):
                                           encoder_layers, conv_pos, conv_pos_groups, tr_layer=False)
         self._geom = E.Geometry(layers, encoder_embed_dim, encoder_ffn_embed_dim, encoder_attention_heads,
                                 conv_pos_groups, conv_pos, encoder_layers, 0, False)
+        self._return_attn = False
         self._weights = None
 
     def engine_state(self):
@@ -453,7 +466,13 @@ class TeacherModel(_ParamCacheMixin, nn.Module):
         P, W = self.engine_state()
         T = E.conv_frames(source.shape[1], self._conv_layers)[-1]
         valid = self.frame_valid(padding_mask, source.shape[1], T)
-        res = E.teacher_forward(P, W, self._geom, source, valid, out_buf=out_buf, want_lr=want_lr)
+        extras = {} if self._return_attn else None
+        res = E.teacher_forward(P, W, self._geom, source, valid, out_buf=out_buf, want_lr=want_lr, extras=extras)
+        self._last_maps = None
+        if extras is not None:
+            g = self._geom
+            m = E.attn_maps(extras["qkv"], extras["valid_t"], extras["B"], extras["T"], g.H, g.d)
+            self._last_maps = (m["attn"][..., :extras["T"]], m["vrel"][..., :extras["T"]])
         return (*res, valid) if want_lr else (*res, None, valid)
 
 
@@ -470,9 +489,14 @@ class TeacherWrapper(nn.Module):
     def extract_features(self, source, padding_mask=None, out_buf=None):
         layers, feats, lrs, valid = self.model.extract_features(source, padding_mask, out_buf=out_buf, want_lr=True)
         B, T, C = layers.shape[1:]
+        maps = getattr(self.model, "_last_maps", None)
+        n = layers.shape[0]
         res = {
-            "layer_results": [(layers[i].transpose(0, 1), (None, lrs[i].view(B, T, C).transpose(0, 1)))
-                              for i in range(layers.shape[0])],
+            # with the attention-map recipe bound (train.py:64-69) the hook's `attn` slot of the LAST layer holds
+            # (attn_logits, v_rel) [B*H, T, T] (utils/utils.py:229-258); see CustomStudentModel.forward
+            "layer_results": [(layers[i].transpose(0, 1),
+                               (maps if (maps is not None and i == n - 1) else None, lrs[i].view(B, T, C).transpose(0, 1)))
+                              for i in range(n)],
             "x": layers[-1],
             "features": [feats],
         }

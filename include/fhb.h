@@ -241,6 +241,38 @@ int fhb_attn_bwd(const void* qkv, const int32_t* valid, const void* out, const v
                  void* dqkv, float* delta_ws, float* dq_ws, int32_t B, int32_t T, int32_t H, int32_t d, float scale,
                  uint32_t drop_seed, float drop_p, fhb_stream_t stream);
 
+/* ------------------------------------------------------------------ attention-map / value-relation distillation
+ * The reference's optional recipe (attn_loss_weight / v_rel_loss_weight > 0): train.py:64-77 re-binds every encoder layer's
+ * forward to utils/utils.py:190-258 `rtrn_attn_forward`, which asks fairseq's MultiheadAttention for its un-normalised
+ * logits (before_softmax=True: bmm(q * scaling, k^T) with -inf at padded keys) and also returns the value relation
+ * v_rel = bmm(v * scaling, v^T); train.py:327-368 compares the LAST layer's maps of student and teacher.
+ * Only that layer materialises T x T maps here: fp32 [B*H][T][pitch], pitch a multiple of 8 (>= T).
+ *
+ * fhb_attn_scores: out[b*H+h][i][j] = scale * sum_c a[(b*T+i)*ld + h*d + c] * b[(b*T+j)*ld + h*d + c], -inf where
+ *   j >= valid[b] (valid optional).  a / b: fp16 head blocks of the fused [B*T][3*H*d] projection output (q and k for the
+ *   logits; v and v, valid = NULL, for the value relation).  d: multiple of 8, <= 64. */
+int fhb_attn_scores(const void* a, const void* b, int64_t ld, const int32_t* valid, float* out, int64_t pitch,
+                    int32_t B, int32_t T, int32_t H, int32_t d, float scale, fhb_stream_t stream);
+/* loss[0] += loss_mult * sum over the B*H*T query rows of
+ *   mode 0 (train.py:331-341): sum_{j < min(vs, vt)} (s - t)^2  - keys either side masks are inf / nan in the reference
+ *           and dropped from sum and count (the caller passes loss_mult = 1 / (H * T * sum_b min(vs_b, vt_b)));
+ *   mode 1 (train.py:342-349,357-364): sum_j p_j (log p_j - log q_j), p = softmax_j(t), q = softmax_j(s) over each side's
+ *           un-masked keys, summed over the keys both keep (loss_mult = 1 / (B*H*T): F.kl_div(..).sum(-1).mean()).
+ *           A key masked on BOTH sides is nan in the reference (0 * -inf, only inf is patched); here it contributes 0.
+ * ds: fp16 [B*H][T][pitch], grad_mult * d(row term)/d(s), every column written (0 at masked keys / row padding);
+ * grad_mult carries loss_mult, the loss weight and the loss scale of the fp16 gradients. */
+int fhb_attn_map_loss(const float* s, const float* t, int64_t pitch, const int32_t* valid_s, const int32_t* valid_t,
+                      void* ds, float* loss, int32_t B, int32_t T, int32_t H, int32_t mode, float loss_mult,
+                      float grad_mult, fhb_stream_t stream);
+/* Gradient of fhb_attn_scores back into a head block:
+ *   trans = 0: out[(b*T+r)*ld_out + h*d + :] (+)= alpha * sum_c g[b*H+h][r][c] * m[(b*T+c)*ld_m + h*d + :]
+ *   trans = 1: the same with g[b*H+h][c][r]
+ * (dq = dS k, dk = dS^T q, dv = (dR + dR^T) v; alpha = the score scale, divided by any power of two the caller folded
+ * into g to centre it in fp16's range).  g: fp16 as written by fhb_attn_map_loss; out: fp16, accumulate != 0 adds to it. */
+int fhb_attn_scores_bwd(const void* g, int64_t pitch, const void* m, int64_t ld_m, void* out, int64_t ld_out, int32_t B,
+                        int32_t T, int32_t H, int32_t d, float alpha, int32_t trans, int32_t accumulate,
+                        fhb_stream_t stream);
+
 /* ------------------------------------------------------------------ distillation loss + gradient (K10)
  * loss_l = w_l * mean_{b,t,d} (pred_l - tgt_l)^2 ; dpred_l = 2 w_l (pred_l - tgt_l) / (B*T'*D)
  * Replaces train.py:250-267 (two torch.stack copies), :282-293 (mse, weighting, mean).  pred: bf16

@@ -1248,3 +1248,163 @@ def test_two_rank_nccl_step_equals_one_process_on_the_concatenated_batch(F, tmp_
     step.fused_forward_backward(x.cuda(), pm)
     _, _, G = step.student_model.engine_state(True)
     assert rel(flat2, G.flat / G.loss_scale) < 2e-3  # same arithmetic, different tile / atomic order
+
+
+# ----------------------------------------------------------------------------- attention-map / value-relation distillation
+@pytest.mark.parametrize("d,T,B,H,valid_s,valid_t", [(24, 49, 3, 4, [49, 40, 33], [49, 41, 34]), (40, 130, 2, 3, None, None),
+                                                     (64, 203, 2, 2, [203, 150], [203, 150]), (16, 64, 2, 2, [64, 9], [64, 64])])
+def test_attention_map_kernels_vs_torch(F, d, T, B, H, valid_s, valid_t):
+    """fhb_attn_scores / fhb_attn_map_loss / fhb_attn_scores_bwd against fp32 torch + the oracle's loss restatement
+    (reference utils/utils.py:190-232, train.py:327-368)."""
+    from fithubert_b200 import kernels as K, engine as E
+    g_ = torch.Generator().manual_seed(d * 1000 + T)
+    E_ = H * d
+    qkv = (torch.randn(B * T, 3 * E_, generator=g_) * 0.7).cuda().half()
+    tqkv = (torch.randn(B * T, 3 * E_, generator=g_) * 0.7).cuda().half()
+    dev = qkv.device
+    vs_d, vt_d = E._valid_tensor(valid_s, dev), E._valid_tensor(valid_t, dev)
+    scale = d ** -0.5
+
+    def heads(x):  # [B*T, E] -> [B*H, T, d] fp32
+        return x.float().view(B, T, H, d).permute(0, 2, 1, 3).reshape(B * H, T, d)
+
+    def ref_logits(x, valid):
+        q, k = heads(x[:, :E_]), heads(x[:, E_:2 * E_])
+        w = torch.bmm(q * scale, k.transpose(1, 2))
+        if valid is not None:
+            km = torch.arange(T, device=dev)[None, :] >= torch.tensor(valid, device=dev)[:, None]
+            w = w.view(B, H, T, T).masked_fill(km[:, None, None, :], float("-inf")).view(B * H, T, T)
+        return w
+
+    S_s = K.attn_scores(qkv[:, :E_], qkv[:, E_:2 * E_], vs_d, B, T, H, d, scale)
+    S_t = K.attn_scores(tqkv[:, :E_], tqkv[:, E_:2 * E_], vt_d, B, T, H, d, scale)
+    pitch = S_s.shape[-1]
+    assert pitch % 8 == 0 and pitch >= T
+    for mine, x, valid in ((S_s, qkv, valid_s), (S_t, tqkv, valid_t)):
+        ref = ref_logits(x, valid)
+        assert torch.equal(mine[..., :T].isinf(), ref.isinf())
+        fin = ~ref.isinf()
+        assert float((mine[..., :T][fin] - ref[fin]).abs().max()) < 2e-3 * float(ref[fin].abs().max())
+    v = heads(qkv[:, 2 * E_:])
+    R_s = K.attn_scores(qkv[:, 2 * E_:], qkv[:, 2 * E_:], None, B, T, H, d, scale)
+    assert rel(R_s[..., :T], torch.bmm(v * scale, v.transpose(1, 2))) < 2e-3
+    # losses + gradient wrt the student map, both modes
+    for mode, name in ((0, "mse"), (1, "kldiv")):
+        s_ref = S_s[..., :T].clone().requires_grad_(True)
+        t_ref = S_t[..., :T].clone()
+        want = O.attn_map_loss(s_ref, t_ref, name, nan_like_reference=False)
+        want.backward()
+        if mode == 0:
+            count = H * T * sum(min(a, b) for a, b in zip(valid_s or [T] * B, valid_t or [T] * B))
+            loss_mult = 1.0 / count
+        else:
+            loss_mult = 1.0 / (B * H * T)
+        G = torch.empty(S_s.shape, device=dev, dtype=torch.float16)
+        loss = torch.zeros(1, device=dev)
+        boost = 2.0 ** round(torch.log2(torch.tensor((1.0 if mode == 0 else 0.25 * T) / loss_mult)).item())
+        K.attn_map_loss(S_s, S_t, vs_d, vt_d, G, loss, B, T, H, mode, loss_mult, loss_mult * boost)
+        assert abs(float(loss) - float(want)) < 1e-4 * abs(float(want)), (name, float(loss), float(want))
+        gref = torch.nan_to_num(s_ref.grad, nan=0.0)
+        assert float(G[..., T:].float().abs().max() if pitch > T else 0.0) == 0.0
+        assert rel(G[..., :T].float() / boost, gref) < 2e-3, name
+        # back into the heads: dq = scale * G k, dk = scale * G^T q (fp16 operands, fp32 accumulate)
+        q, k = heads(qkv[:, :E_]), heads(qkv[:, E_:2 * E_])
+        Gf = G[..., :T].float()
+        dq_ref = torch.bmm(Gf, k) * scale
+        dk_ref = torch.bmm(Gf.transpose(1, 2), q) * scale
+        base = (torch.randn(B * T, 3 * E_, generator=g_) * 0.1).cuda().half()
+        dqkv = base.clone()
+        K.attn_scores_bwd(G, qkv[:, E_:2 * E_], dqkv[:, :E_], B, T, H, d, scale, trans=0)
+        K.attn_scores_bwd(G, qkv[:, :E_], dqkv[:, E_:2 * E_], B, T, H, d, scale, trans=1)
+        K.attn_scores_bwd(G, qkv[:, 2 * E_:], dqkv[:, 2 * E_:], B, T, H, d, scale, trans=0, accumulate=False)
+
+        def unheads(x):
+            return x.view(B, H, T, d).permute(0, 2, 1, 3).reshape(B * T, E_)
+
+        assert rel(dqkv[:, :E_].float() - base[:, :E_].float(), unheads(dq_ref)) < 5e-3, name
+        assert rel(dqkv[:, E_:2 * E_].float() - base[:, E_:2 * E_].float(), unheads(dk_ref)) < 5e-3, name
+        assert rel(dqkv[:, 2 * E_:].float(), unheads(torch.bmm(Gf, v) * scale)) < 5e-3, name
+
+
+@pytest.mark.parametrize("name", ["attn_mse_hubert_pad", "attn_kldiv_hubert_nopad"])
+def test_attention_map_recipe_matches_reference_fixture(F, name):
+    """Attention-map + value-relation distillation on the ex.yaml recipe against fixtures that hold
+    what the reference's own `rtrn_attn_forward` and `calculate_loss` produced: the last layer's (attn_logits, v_rel) of
+    student and teacher, every loss term, the total, every parameter gradient - through the reference-style API
+    (forward -> calculate_loss -> backward) AND through the fused training step."""
+    import bench
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"))
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    cfg["distiller"].update(init_conv_layers=False, init_encoder_layers=0)
+    cfg["train"].update(g["train_cfg"])
+    tc = dict(g["teacher_cfg"])
+    teacher = F.TeacherModel(kind=tc.pop("kind"), **tc)
+    teacher.load_state_dict(g["teacher_state"])
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    student = step.student_model
+    student.load_state_dict(g["student_state"])
+    student.eval()
+    x, pm = g["source"], g["padding_mask"]
+
+    def check_maps(pair, ref_attn, ref_vrel, tag):
+        attn, vrel = pair
+        assert attn.shape == ref_attn.shape and vrel.shape == ref_vrel.shape
+        assert torch.equal(attn.isinf().cpu(), ref_attn.isinf()), tag  # -inf at exactly the reference's padded keys
+        fin = ~ref_attn.isinf()
+        assert float((attn.cpu()[fin] - ref_attn[fin]).abs().max()) < TOL * float(ref_attn[fin].abs().max()), tag
+        assert rel(vrel, ref_vrel) < TOL, tag
+
+    with torch.no_grad():
+        s_res, t_res = step(x.cuda(), pm)
+    assert all(lr[1] is None for lr in s_res["layer_results"][:-1])  # only the last layer's pair is materialised
+    check_maps(s_res["layer_results"][-1][1], g["student_attn"], g["student_vrel"], "student")
+    check_maps(t_res["layer_results"][-1][1][0], g["teacher_attn"], g["teacher_vrel"], "teacher")
+    # reference-style API with autograd
+    s_res, t_res = step(x.cuda(), pm)
+    total, losses = step.calculate_loss(s_res, t_res)
+    assert set(losses) == set(g["losses"])
+    for k, ref in g["losses"].items():
+        assert abs(float(losses[k]) - float(ref)) < TOL * abs(float(ref)), (k, float(losses[k]), float(ref))
+    assert abs(float(total) - float(g["loss"])) < 1e-2 * float(g["loss"])
+    total.backward()
+    ref_grads = dict(g["grads"])
+    if g["train_cfg"]["attn_loss_type"] == "kldiv":
+        # every term that sees the logits is a softmax: a constant shift of all keys changes nothing and k_proj.bias has a
+        # mathematically zero gradient (the fixture holds 9e-8 of rounding noise): absolute check, like test_oracle_golden
+        for k in [k for k in ref_grads if k.endswith("k_proj.bias")]:
+            ref_grads.pop(k)
+            assert float(dict(student.named_parameters())[k].grad.abs().max()) < 1e-4, k
+    check_grads([(n, p.grad) for n, p in student.named_parameters()], ref_grads, f"{name}_api", min_count=30)
+    # fused training path: same terms, same gradients
+    _, _, G = student.engine_state(True)
+    G.zero_()
+    parts = step.fused_forward_backward(x, pm)
+    assert abs(float(parts.sum()) - float(g["loss"])) < 1e-2 * float(g["loss"])
+    al = step.last_attn_losses
+    assert abs(float(al[0]) - float(g["losses"]["attn_loss"])) < TOL * float(g["losses"]["attn_loss"])
+    assert abs(float(al[1]) - float(g["losses"]["v_rel_loss"])) < TOL * float(g["losses"]["v_rel_loss"])
+    grads = G.export()
+    check_grads(list(grads.items()), ref_grads, f"{name}_fused", min_count=30)
+    # and a whole training step moves the attention projections
+    step.configure_optimizers(total_steps=100)
+    before = student.state_dict()["encoder.layers.1.self_attn.q_proj.weight"].clone()
+    loss = step.training_step({"x": x, "padding_mask": pm})
+    assert abs(float(loss) - float(total)) < 1e-3 * float(total)
+    assert not torch.equal(student.state_dict()["encoder.layers.1.self_attn.q_proj.weight"], before)
+
+
+def test_attention_map_recipe_error_behaviour(F):
+    """The reference fails at construction when the student has a time-reduction layer (train.py:70-77 touches `.self_attn`
+    of encoder.layers[0], an nn.Conv1d) and at the first loss when only v_rel_loss_weight is set (train.py:357-358)."""
+    import bench
+    g = torch.load(GOLDEN[1])
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    teacher, _ = build_pair(F, g)
+    cfg["train"].update(attn_loss_weight=1.0)
+    with pytest.raises(AttributeError):
+        F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+    cfg["train"].update(attn_loss_weight=0, v_rel_loss_weight=1.0)
+    with pytest.raises(TypeError):
+        F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
