@@ -677,6 +677,15 @@ def main():
         peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
     value = audio_s * world * args.steps / (ms / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM bytes per fhb_gemm launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 225 launches of one
+    # cfg-2 step, from the committed ncu capture profiles/gemm_traffic.json; null for other workloads / when absent)
+    traffic = traffic_src = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic.json")
+    if args.workload == "cfg2" and os.path.isfile(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/gemm_traffic.json: " + tj["source"]
+
     out = {
         "metric": "distill-step audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -698,7 +707,8 @@ def main():
         "comm_exposed_ms": comm_ms if world > 1 else 0.0,  # main-stream time spent waiting for the gradient all-reduce
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": {"bound": "tensor", "kernel": "fhb_gemm_kernel (tcgen05, all variants)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "launches_per_step": gemm_calls / max(1, args.steps),
                      "gemm_ms_per_step": gemm_ms / args.steps,
                      "groups": {g: {"tflops": (f / (ms / 1e3) / 1e12) if ms > 0 else 0.0,

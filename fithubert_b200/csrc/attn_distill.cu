@@ -194,6 +194,80 @@ __global__ void __launch_bounds__(256) attn_map_loss_kernel(const float* __restr
   }
 }
 
+// KL mode with the whole row in registers (T <= 32 * NT): one read of s and t, one write of ds.  exp through ex2.approx on
+// pre-scaled arguments (2 ulp), the same arithmetic as the streaming kernel above otherwise.
+template <int NT>
+__global__ void __launch_bounds__(256) attn_map_kl_rows_kernel(const float* __restrict__ s, const float* __restrict__ t, long long pitch,
+                                                               const int* __restrict__ valid_s, const int* __restrict__ valid_t,
+                                                               __half* __restrict__ ds, float* __restrict__ loss, long long rows,
+                                                               int T, int H, float loss_mult, float grad_mult) {
+  pdl_sync();
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  float local = 0.f;
+  if (row < rows) {
+    const int bi = (int)(row / ((long long)T * H));
+    const int vs = valid_s ? min(valid_s[bi], T) : T;
+    const int vt = valid_t ? min(valid_t[bi], T) : T;
+    const int vk = min(vs, vt);
+    const float* sr = s + row * pitch;
+    const float* tr = t + row * pitch;
+    float sv[NT], tv[NT];
+    float ms = -INFINITY, mt = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int j = lane + 32 * i;
+      sv[i] = j < vs ? __ldg(sr + j) : -INFINITY;
+      tv[i] = j < vt ? __ldg(tr + j) : -INFINITY;
+      ms = fmaxf(ms, sv[i]);
+      mt = fmaxf(mt, tv[i]);
+    }
+    ms = warp_max(ms);
+    mt = warp_max(mt);
+    float zs = 0.f, zt = 0.f, ek = 0.f, et = 0.f;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int j = lane + 32 * i;
+      const float d = tv[i] - sv[i];                        // only used where both are finite (j < vk)
+      const float es = ex2_approx((sv[i] - ms) * kLog2e);   // exp(-inf) = 0 at masked keys
+      const float e = ex2_approx((tv[i] - mt) * kLog2e);
+      zs += es;
+      zt += e;
+      if (j < vk) {
+        ek += e;
+        et += e * d;
+      }
+      sv[i] = es;
+      tv[i] = e;
+    }
+    zs = warp_sum(zs);
+    zt = warp_sum(zt);
+    ek = warp_sum(ek);
+    et = warp_sum(et);
+    const float inv_zs = 1.f / zs, inv_zt = 1.f / zt;
+    const float pk = ek * inv_zt;
+    if (lane == 0) local = et * inv_zt + pk * (ms - mt + kLn2 * (log2f(zs) - log2f(zt)));
+    __half* dr = ds + row * pitch;
+    const float a = inv_zs * pk * grad_mult, b = inv_zt * grad_mult;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int j = lane + 32 * i;
+      if (j < (int)pitch) dr[j] = __float2half_rn(j < vs ? sv[i] * a - tv[i] * b : 0.f);  // tv = 0 beyond vt
+    }
+  }
+  __shared__ float part[8];
+  local = warp_sum(local);
+  if (lane == 0) part[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += part[i];
+    if (v != 0.f) atomicAdd(loss, v * loss_mult);
+  }
+}
+
 // ------------------------------------------------------------------ gradient back into the heads
 // acc [64 r][DP] = sum_c A[r][c] * M[c][:], A = G tile (TRANS = 0) or its transpose (TRANS = 1)
 template <int DP, bool TRANS>
@@ -307,6 +381,22 @@ extern "C" int fhb_attn_map_loss(const float* s, const float* t, int64_t pitch, 
   const long long rows = (long long)B * H * T;
   FHB_ARG_CHECK((rows + 7) / 8 < (1LL << 31), "attn_map_loss: too many rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 1 && pitch <= 32 * 32) {
+    // rows of up to 1024 keys (every BASELINE configuration short of cfg-5's 30 s utterances) stay in registers
+    const dim3 grid((unsigned)((rows + 7) / 8));
+    if (pitch <= 32 * 8) {
+      FHB_CUDA_CHECK(fhb_launch(attn_map_kl_rows_kernel<8>, grid, dim3(256), 0, st, s, t, (long long)pitch, valid_s, valid_t,
+                                static_cast<__half*>(ds), loss, rows, T, H, loss_mult, grad_mult));
+    } else if (pitch <= 32 * 16) {
+      FHB_CUDA_CHECK(fhb_launch(attn_map_kl_rows_kernel<16>, grid, dim3(256), 0, st, s, t, (long long)pitch, valid_s, valid_t,
+                                static_cast<__half*>(ds), loss, rows, T, H, loss_mult, grad_mult));
+    } else {
+      FHB_CUDA_CHECK(fhb_launch(attn_map_kl_rows_kernel<32>, grid, dim3(256), 0, st, s, t, (long long)pitch, valid_s, valid_t,
+                                static_cast<__half*>(ds), loss, rows, T, H, loss_mult, grad_mult));
+    }
+    FHB_LAUNCH_CHECK();
+    return 0;
+  }
   FHB_CUDA_CHECK(fhb_launch(attn_map_loss_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, s, t, (long long)pitch, valid_s,
                             valid_t, static_cast<__half*>(ds), loss, rows, T, H, mode, loss_mult, grad_mult));
   FHB_LAUNCH_CHECK();

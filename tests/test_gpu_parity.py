@@ -1252,7 +1252,10 @@ def test_two_rank_nccl_step_equals_one_process_on_the_concatenated_batch(F, tmp_
 
 # ----------------------------------------------------------------------------- attention-map / value-relation distillation
 @pytest.mark.parametrize("d,T,B,H,valid_s,valid_t", [(24, 49, 3, 4, [49, 40, 33], [49, 41, 34]), (40, 130, 2, 3, None, None),
-                                                     (64, 203, 2, 2, [203, 150], [203, 150]), (16, 64, 2, 2, [64, 9], [64, 64])])
+                                                     (64, 203, 2, 2, [203, 150], [203, 150]), (16, 64, 2, 2, [64, 9], [64, 64]),
+                                                     # KL rows held in registers: 16 / 32 values per lane; streaming kernel beyond 1024 keys
+                                                     (40, 300, 1, 2, [280], [281]), (64, 779, 1, 2, None, None),
+                                                     (8, 1040, 1, 1, [1000], [1001])])
 def test_attention_map_kernels_vs_torch(F, d, T, B, H, valid_s, valid_t):
     """fhb_attn_scores / fhb_attn_map_loss / fhb_attn_scores_bwd against fp32 torch + the oracle's loss restatement
     (reference utils/utils.py:190-232, train.py:327-368)."""

@@ -2,7 +2,7 @@
 SplitLinear head over teacher layers 3 / 7 / 11, L1 + cosine) at the cfg-2 batch (B x 15.6 s), with and without the
 attention-map / value-relation terms (attn_loss_weight, v_rel_loss_weight > 0; train.py:64-77,327-378).
 Prints ms per training step (CUDA events) and the per-kernel share of the extra launches.
-usage: python tools/attn_recipe_bench.py [B] [steps]"""
+usage: python tools/attn_recipe_bench.py [B] [steps] [case index 0-3: only that case, 1 warm-up step (for ncu)]"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,7 +28,7 @@ def ex_cfg(attn_w, vrel_w, attn_type):
     return cfg
 
 
-def run(B, steps, attn_w, vrel_w, attn_type):
+def run(B, steps, attn_w, vrel_w, attn_type, warmup=3):
     torch.manual_seed(0)
     teacher = F.TeacherWrapper(F.TeacherModel(kind="hubert").cuda())
     step = F.W2V2Distil(ex_cfg(attn_w, vrel_w, attn_type), teacher_model=teacher, device="cuda")
@@ -41,7 +41,7 @@ def run(B, steps, attn_w, vrel_w, attn_type):
         x[b, n:] = 0
     x = x.cuda()
     batch = {"x": x, "padding_mask": None, "lengths": lens}
-    for _ in range(3):
+    for _ in range(warmup):
         loss = step.training_step(batch)
     torch.cuda.synchronize()
     L.reset_counters()
@@ -62,6 +62,10 @@ def run(B, steps, attn_w, vrel_w, attn_type):
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    for a, v, t in ((0, 0, "kldiv"), (1.0, 0, "kldiv"), (1.0, 1.0, "kldiv"), (1.0, 1.0, "mse")):
-        print(json.dumps(dict(run(B, steps, a, v, t), B=B)), flush=True)
+    cases = ((0, 0, "kldiv"), (1.0, 0, "kldiv"), (1.0, 1.0, "kldiv"), (1.0, 1.0, "mse"))
+    only = int(sys.argv[3]) if len(sys.argv) > 3 else None
+    for i, (a, v, t) in enumerate(cases):
+        if only is not None and i != only:
+            continue
+        print(json.dumps(dict(run(B, steps, a, v, t, warmup=3 if only is None else 1), B=B)), flush=True)
         torch.cuda.empty_cache()
