@@ -12,10 +12,15 @@ tests/test_oracle_pins.py::test_oracle_matches_the_reference_classes_live when
 /root/reference is present), and the teacher additionally against
 torchaudio.models.hubert_base (tests/test_oracle_pins.py).  The optimizer (s3prl, source not
 available anywhere in this image) is restated from its published algorithm:
-"parity unpinned" for that one function.  calculate_loss (train.py:236-405) cannot be
-executed either (train.py imports Lightning and s3prl at module level): distill_loss /
-distill_loss_sim are line-by-line transcriptions of its live branches built from the
-same torch calls (F.mse_loss, F.l1_loss, F.cosine_similarity, F.logsigmoid).
+"parity unpinned" for that one function.  train.py cannot be IMPORTED (Lightning and
+s3prl at module level), but `W2V2Distil.calculate_loss` (train.py:236-405) and
+`rtrn_attn_forward` (utils/utils.py:190-258) are self-contained: oracle/ref_extract.py
+compiles them straight out of the reference's unmodified source text (ast), and
+  * tests/test_oracle_pins.py::test_loss_restatements_match_the_reference_calculate_loss_live
+    pins distill_loss, distill_loss_sim, cnn_feature_loss, attn_map_loss and
+    value_relation_loss against that very method (live, where /root/reference exists);
+  * the attn_* fixtures under tests/golden/ hold what those two reference functions
+    produced (loss terms, total, gradients), so they also travel to the GPU box.
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root; [EXT] = fairseq @1b61bbad / s3prl @185e4b06, not vendored).
