@@ -71,6 +71,7 @@ struct GemmParams {
   int n_auxout;  // 0 / 2 staging buffers for the second output
   int n_in;      // 0 / 3 / 4 staging buffers (<= kInRing) for the TMA-loaded epilogue input (residual or aux_in)
   int pair;      // 1: clusters of two CTAs share the B tile by TMA multicast (num_m_blk then counts PAIRS of row blocks)
+  int two_bar;   // 1: the round-2 epilogue with two block barriers per output slab (FHB_GEMM_EPI2BAR, A/B only)
 };
 
 struct Tile {
@@ -365,7 +366,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         pf_t = decode_tile(p, pf_tile, pair_rank);
         pf_ns = tile_slabs(pf_t);
       }
-      for (int i = 0; i < p.n_in - 1; ++i) prefetch_one();
+      // one-barrier epilogue: the refill that used to open slab 0 happens here (all p.n_in slots start out free)
+      for (int i = 0; i < p.n_in - (p.two_bar ? 1 : 0); ++i) prefetch_one();
     }
     int it = 0;
     uint32_t slab_ctr = 0;
@@ -552,13 +554,19 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t abuf = auxo_u32 + (slab_ctr & 1u) * kStoreBytes;
         // the buffers we are about to overwrite must have been drained by the TMA stores of slab - 2
         // (one bulk group per slab, so at most one group may still be reading)
-        if (threadIdx.x == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          // every thread has finished reading ring slot (slab_ctr - 1) % kInRing (barrier at the end of the
-          // previous slab): refill it with the slab kInRing - 1 ahead
-          if (in_tma) prefetch_one();
+        // ONE block barrier per slab (at its end): it publishes "every thread's st.shared of this slab is done" together
+        // with "the TMA store of the previous slab has finished reading its staging buffer" (thread 0 waits for that just
+        // before arriving - the store has had this whole slab's math to drain), so the next slab can overwrite the
+        // other buffer without a barrier of its own.  (p.two_bar: the round-2 scheme with a second barrier here.)
+        if (p.two_bar) {
+          if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            // every thread has finished reading ring slot (slab_ctr - 1) % kInRing (barrier at the end of the
+            // previous slab): refill it with the slab kInRing - 1 ahead
+            if (in_tma) prefetch_one();
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int c0 = sidx * slab_cols + half * my_cols;  // first tile column of this warp's share
         uint32_t r[32];
         tmem_ld16(taddr + c0, r);
@@ -609,6 +617,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         fence_async_shared();
+        if (!p.two_bar && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 0) {
           const int cc = t.n0 + sidx * slab_cols;
@@ -623,6 +632,8 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"(&tm_aux), "r"(abuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // every thread has read this slab's ring slot (barrier above): refill it with the slab p.n_in ahead
+          if (!p.two_bar && in_tma) prefetch_one();
         }
         ++slab_ctr;
       }
@@ -1080,6 +1091,8 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
     p.drop_scale = fhb_dropout_scale(a->drop_p);
   }
   p.flags = flags;
+  static const int two_bar = getenv("FHB_GEMM_EPI2BAR") ? atoi(getenv("FHB_GEMM_EPI2BAR")) : 0;
+  p.two_bar = two_bar;
 
   CUtensorMap ta, tb;
   int rc;

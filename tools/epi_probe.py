@@ -52,3 +52,11 @@ case("T qkv              24928x2304x768", Mt, 2304, 768)
 case("T out+res16        24928x768x768", Mt, 768, 768, res=f16)
 case("T out (no res)     24928x768x768", Mt, 768, 768)
 case("T fc2+res16        24928x768x3072", Mt, 768, 3072, res=f16)
+if len(sys.argv) > 1 and sys.argv[1] == "conv":
+    Mc = 32 * 49919
+    print("-- student conv1 shape (1.6 M rows, K = 128): where the 0x212 forward epilogue's time goes")
+    case("C1 plain (no bias)  1597408x256x128", Mc, 256, 128, sets=2)
+    case("C1 gelu             1597408x256x128", Mc, 256, 128, gelu=True, sets=2)
+    case("C1 gelu + dgelu out 1597408x256x128", Mc, 256, 128, gelu=True, dg=True, sets=2)
+    case("C2 gelu + dgelu out 798688x256x768", 32 * 24959, 256, 768, gelu=True, dg=True, sets=2)
+    case("C2 plain            798688x256x768", 32 * 24959, 256, 768, sets=2)
