@@ -445,11 +445,12 @@ class W2V2Distil(nn.Module):
         s_valid = None if lengths is None else conv_out_lengths(lengths, sm._conv_layers)
         n, B, D = self.n_pred, x.shape[0], sm._geom.d_out
         Pt, Wt = tm.engine_state()
-        tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, slots=self.tgt_slots)
+        t_extras = {} if self.attn_loss_weight > 0 else None
+        tgt, t_feats = E.teacher_forward(Pt, Wt, tm._geom, x, t_valid, slots=self.tgt_slots, extras=t_extras)
         was_training = sm.training
         sm.eval()
         P, W, _ = sm.engine_state(sm._weights.train if sm._weights is not None else False)
-        c = E.student_forward(P, W, sm._geom, x, s_valid, train=False, heads="all")
+        c = E.student_forward(P, W, sm._geom, x, s_valid, train=False, heads="all", keep_qkv_last=t_extras is not None)
         sm.train(was_training)
         rec = torch.zeros(n, device=dev, dtype=torch.float32)
         lt = 0 if self.rec_loss_type == "mse" else 1
@@ -466,6 +467,13 @@ class W2V2Distil(nn.Module):
             K.distill_loss(c.cnn_out.view(1, B, T, Dc), t_feats.reshape(1, B, T, Dc), torch.ones(1, device=dev), cnn, None,
                            1, B, T, T, Dc, 1, 0.0)
             per = torch.cat([per, cnn * self.cnn_loss_weight])
+        if t_extras is not None:
+            # v_loss is calculate_loss's total (train.py:183-185): the attention-map / value-relation terms belong to it
+            al = E.attn_transfer_losses(c, sm._geom, t_extras, tm._geom, loss_type=self.attn_loss_type,
+                                        w_attn=float(self.attn_loss_weight), w_vrel=float(self.v_rel_loss_weight),
+                                        grad_scale=1.0, valid_s=c.valid, valid_t=t_extras["valid_host"])
+            c.attn_grad = None  # (the gradients the kernel also wrote are not needed here)
+            per = torch.cat([per, al * torch.tensor([float(self.attn_loss_weight), float(self.v_rel_loss_weight)], device=dev)])
         # train.py:198-199: with random-layer distillation the monitored value is the last layer's own (un-weighted)
         # feature loss, not the weighted total
         loss = (rec[n - 1] if not self.sim_loss_weight else rec[n - 1] + sim[n - 1]) \

@@ -1389,6 +1389,9 @@ def test_attention_map_recipe_matches_reference_fixture(F, name):
     assert abs(float(al[1]) - float(g["losses"]["v_rel_loss"])) < TOL * float(g["losses"]["v_rel_loss"])
     grads = G.export()
     check_grads(list(grads.items()), ref_grads, f"{name}_fused", min_count=30)
+    # validation_step's v_loss is calculate_loss's total, attention terms included (train.py:180-199)
+    v = step.validation_step({"x": x, "padding_mask": pm})["v_loss"]
+    assert abs(float(v) - float(g["loss"])) < 1e-2 * float(g["loss"])
     # and a whole training step moves the attention projections
     step.configure_optimizers(total_steps=100)
     before = student.state_dict()["encoder.layers.1.self_attn.q_proj.weight"].clone()
