@@ -94,9 +94,11 @@ class CustomStudentModelConfig:
         if self.pos_conv_depth != 1:
             raise NotImplementedError("pos_conv_depth > 1 is not implemented")
         if self.layerwise_proj:
-            # FitHuBERT recipe (data/conf/fithubert.yaml): 12 LayerWiseProjHeads behind a conv1d TR layer at index 0
-            if not self.enable_tr_layer:
-                raise NotImplementedError("layerwise_proj=True without a time-reduction layer is not implemented")
+            # FitHuBERT recipe (data/conf/fithubert.yaml): 12 LayerWiseProjHeads behind a conv1d TR layer at index 0;
+            # without a TR layer LayerWiseProjHead is its Linear alone (modules/module.py:633-646), and with equal widths
+            # it would be the identity (no parameters at all)
+            if not self.enable_tr_layer and self.pred_head_final_dim == self.encoder_embed_dim:
+                raise NotImplementedError("layer-wise heads without a TR layer need pred_head_final_dim != encoder_embed_dim")
         else:
             # DistilHuBERT-style recipe (data/conf/ex.yaml): Linear -> GELU -> SplitLinear on the last layer, no TR layer
             if len(parse_int_list(self.pred_layer_id)) < 2:

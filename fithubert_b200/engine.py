@@ -166,14 +166,15 @@ class WeightSet:
         elif g.student:
             for i in range(g.n_layers):
                 p = f"proj_head.{i}."
-                if p + "upsampler.weight" not in self.params:
-                    if i == g.n_layers - 1 and "final_proj.upsampler.weight" in self.params:
+                if p + "lin_proj.weight" not in self.params:
+                    if i == g.n_layers - 1 and "final_proj.lin_proj.weight" in self.params:
                         p = "final_proj."
                     else:
                         continue
-                add(f"h{i}.wup", f16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
-                add(f"h{i}.bup", f32, (2, E, 1), [(p + "upsampler.bias", 0, (0, 1, 0), 0)])
-                add(f"h{i}.bup16", f16, (E, 1, 1), [(p + "upsampler.bias", 0, (1, 0, 0), 0)])  # A operand of the bias fold
+                if g.tr:  # (no TR layer: LayerWiseProjHead is the Linear alone, modules/module.py:633-646)
+                    add(f"h{i}.wup", f16, (2, E, E), [(p + "upsampler.weight", 0, (1, 2, 2 * E), 0)])
+                    add(f"h{i}.bup", f32, (2, E, 1), [(p + "upsampler.bias", 0, (0, 1, 0), 0)])
+                    add(f"h{i}.bup16", f16, (E, 1, 1), [(p + "upsampler.bias", 0, (1, 0, 0), 0)])  # A operand of the bias fold
                 lin(f"h{i}.wlin", p + "lin_proj.weight", g.d_out, E)
                 add(f"h{i}.blin", f32, (g.d_out, 1, 1), [(p + "lin_proj.bias", 0, (1, 0, 0), 0)])
         self.spec = spec
@@ -317,14 +318,15 @@ class GradStore:
                 plain(pn)
         for i in range(g.n_layers if not g.n_split else 0):
             p = f"proj_head.{i}."
-            if p + "upsampler.weight" not in params:
-                if i == g.n_layers - 1 and "final_proj.upsampler.weight" in params:
+            if p + "lin_proj.weight" not in params:
+                if i == g.n_layers - 1 and "final_proj.lin_proj.weight" in params:
                     p = "final_proj."  # after _disable_projection_heads: the last head under its new name
                 else:
                     continue
-            # grad stored as dWup[(j, co)][ci]; param element (ci, co, j)
-            order.append((p + "upsampler.weight", (E, E, 2), (1, E, E * E)))
-            plain(p + "upsampler.bias")
+            if g.tr:
+                # grad stored as dWup[(j, co)][ci]; param element (ci, co, j)
+                order.append((p + "upsampler.weight", (E, E, 2), (1, E, E * E)))
+                plain(p + "upsampler.bias")
             plain(p + "lin_proj.weight")
             plain(p + "lin_proj.bias")
         self.entries = {}
@@ -852,12 +854,13 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
                        d_hi_stride=B * Tq * D, flags=L.EPI_BIAS, bias=P["proj_head.2.bias"], bias_hi_stride=D)
             c.preds = pred_buf
         return c
-    # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E]
-    Tq = 2 * Ts
+    # projection heads (modules/module.py:649-661): ConvTranspose1d(k=2,s=2) = GEMM to [B*Ts, 2E] = [B*2Ts, E], then the
+    # Linear; without a TR layer the head is the Linear alone (:633-646) at the encoder's own frame rate
+    Tq = 2 * Ts if g.tr else Ts
     idx = list(range(n)) if heads == "all" else ([n - 1] if heads == "last" else [])
     c.head_idx = idx
-    hs = {k: W.head_stride(k) for k in ("wup", "bup", "wlin", "blin")} if heads == "all" else {}
-    c.heads_batched = bool(idx) and heads == "all" and all(v is not None for v in hs.values())
+    hs = {k: W.head_stride(k) for k in ("wup", "bup", "wlin", "blin")} if (heads == "all" and g.tr) else {}
+    c.heads_batched = bool(idx) and heads == "all" and g.tr and all(v is not None for v in hs.values())
     if idx:
         if pred_buf is None:
             pred_buf = torch.empty(len(idx), B, Tq, D, device=dev, dtype=f16)
@@ -888,7 +891,7 @@ def student_forward(P, W: WeightSet, g: Geometry, wave, valid: Optional[List[int
             c.z = []
             for j, i in enumerate(idx):
                 src = c.layers[i] if i < n_run else c.x_last  # `layer=` early exit: final_proj sees the last executed layer
-                z = K.linear(src, W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"])
+                z = K.linear(src, W[f"h{i}.wup"].view(2 * E, E), W[f"h{i}.bup"]) if g.tr else src
                 K.linear(z.view(B * Tq, E), W[f"h{i}.wlin"].view(D, E), P[_head_name(P, i) + "lin_proj.bias"],
                          out=pred_buf[j].view(B * Tq, D))
                 c.z.append(z if train else None)
@@ -1149,10 +1152,13 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
             K.colsum(dp, gv(hp + "lin_proj.bias"))
             K.linear_wgrad(dp, z, out=gv(hp + "lin_proj.weight").view(D, E), accumulate=True)
             dz = K.linear_dgrad(dp, W[f"h{l}.wlin"].view(D, E))  # [B*Tq, E] == [B*Ts, 2E]
-            K.colsum(dz, gv(hp + "upsampler.bias"))
-            dz2 = dz.view(B * Ts, 2 * E)
-            K.linear_wgrad(dz2, s.out, out=gv(hp + "upsampler.weight").view(2 * E, E), accumulate=True)
-            dxb = add_b(K.linear_dgrad(dz2, W[f"h{l}.wup"].view(2 * E, E)), dxb)
+            if g.tr:
+                K.colsum(dz, gv(hp + "upsampler.bias"))
+                dz2 = dz.view(B * Ts, 2 * E)
+                K.linear_wgrad(dz2, s.out, out=gv(hp + "upsampler.weight").view(2 * E, E), accumulate=True)
+                dxb = add_b(K.linear_dgrad(dz2, W[f"h{l}.wup"].view(2 * E, E)), dxb)
+            else:  # the head is the Linear alone: z is the layer output itself
+                dxb = add_b(dz, dxb)
         if dlayers is not None and dlayers[l] is not None:
             dxb = add_b(dlayers[l], dxb)
         if dx32 is None and dxb is None:

@@ -117,7 +117,9 @@ class LayerWiseProjHead(nn.Module):
     def __init__(self, in_dim, out_dim, enable_tr_layer=True, tr_reduce_factor=2):
         super().__init__()
         self.in_dim, self.out_dim = in_dim, out_dim
-        self.upsampler = nn.ConvTranspose1d(in_dim, in_dim, kernel_size=tr_reduce_factor, stride=tr_reduce_factor)
+        # reference modules/module.py:633-646: the upsampler only exists behind a time-reduction layer
+        self.upsampler = nn.ConvTranspose1d(in_dim, in_dim, kernel_size=tr_reduce_factor, stride=tr_reduce_factor) \
+            if enable_tr_layer else None
         self.lin_proj = nn.Linear(in_dim, out_dim)
 
 

@@ -295,9 +295,11 @@ def student_forward(sd: State, cfg: dict, source: Tensor, padding_mask: Optional
                 "layer_results": layer_results, "tr_layer_results": tr_layer_results, "projections": projections}
 
     def head(i, h_tbc):  # LayerWiseProjHead.forward, modules/module.py:649-661
-        y = F.conv_transpose1d(h_tbc.permute(1, 2, 0), sd[f"proj_head.{i}.upsampler.weight"],
-                               sd[f"proj_head.{i}.upsampler.bias"], stride=cfg["tr_reduce_factor"])
-        return F.linear(y.transpose(1, 2), sd[f"proj_head.{i}.lin_proj.weight"], sd[f"proj_head.{i}.lin_proj.bias"])
+        y = h_tbc.transpose(0, 1)
+        if tr:  # `self.upsampler` only exists with a time-reduction layer (:633-640)
+            y = F.conv_transpose1d(h_tbc.permute(1, 2, 0), sd[f"proj_head.{i}.upsampler.weight"],
+                                   sd[f"proj_head.{i}.upsampler.bias"], stride=cfg["tr_reduce_factor"]).transpose(1, 2)
+        return F.linear(y, sd[f"proj_head.{i}.lin_proj.weight"], sd[f"proj_head.{i}.lin_proj.bias"])
 
     if heads:
         projections = [head(i, layer_results[i][0]) for i in range(cfg["encoder_layers"])]
@@ -494,8 +496,9 @@ def init_student_state(cfg: dict, seed: int = 0, perturb: bool = False) -> State
         sd["proj_head.2.bias"] = uni(1, 1, n, D, bound=inter ** -0.5)
     else:
         for i in range(cfg["encoder_layers"]):
-            sd[f"proj_head.{i}.upsampler.weight"] = uni(E, E, f, bound=bt)
-            sd[f"proj_head.{i}.upsampler.bias"] = uni(E, bound=bt)
+            if tr:
+                sd[f"proj_head.{i}.upsampler.weight"] = uni(E, E, f, bound=bt)
+                sd[f"proj_head.{i}.upsampler.bias"] = uni(E, bound=bt)
             sd[f"proj_head.{i}.lin_proj.weight"] = uni(D, E, bound=1 / math.sqrt(E))
             sd[f"proj_head.{i}.lin_proj.bias"] = uni(D, bound=1 / math.sqrt(E))
     if cfg.get("_cnn_weight", 0) > 0 and D != E:  # cnn_proj_head = Sequential(GELU, Linear(E, D)), modules/model.py:304-310

@@ -31,6 +31,8 @@ from modules.model import CustomStudentModel, CustomStudentModelConfig  # noqa: 
 from modules.module import ConvFeatureExtractionModel, TransformerEncoder  # noqa: E402  (reference)
 import fhb_oracle as O  # noqa: E402
 
+only_cases = []  # filled from argv by main(): when non-empty, only these fixtures are (re)generated
+
 TINY_STUDENT = dict(
     conv_feature_layers="[(16, 10, 5)] + [(32, 1, 1)] + [(32, 3, 2)] * 4 + [(64, 1, 1)] + [(64, 2, 2)] * 2",
     encoder_layers=3, encoder_embed_dim=96, encoder_ffn_embed_dim=96, encoder_attention_heads=4,
@@ -96,6 +98,8 @@ def perturb_(module, seed):
 
 
 def run_case(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, kind="hubert", grads=True):
+    if only_cases and name not in only_cases:
+        return
     torch.manual_seed(0)
     student = CustomStudentModel(ref_student_cfg(yaml_distiller, **s_over))
     tcfg = O.teacher_config(**t_over, kind=kind)
@@ -126,7 +130,7 @@ def run_case(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, kind="huber
         "student_mask": s_res["padding_mask"], "teacher_mask": t_res["padding_mask"],
         "student_features": s_res["features"].detach(),
         "student_layers": [lr[0].detach() for lr in s_res["layer_results"]],
-        "student_tr": s_res["tr_layer_results"][0].detach(),
+        "student_tr": s_res["tr_layer_results"][0].detach() if s_res["tr_layer_results"] else None,
         "projections": [p.detach() for p in s_res["projections"]],
         "teacher_layers": [lr[0].detach() for lr in t_res["layer_results"]],
         "teacher_features": t_res["features"][0].detach(),
@@ -152,6 +156,8 @@ TINY_SPLIT_STUDENT = dict(  # data/conf/ex.yaml family: teacher-shaped conv stac
 def run_case_split(name, s_over, t_over, B, Lmax, lengths, yaml_distiller):
     """ex.yaml recipe: layerwise_proj False, enable_tr_layer False, feature_grad_mult 0.1; loss = L1 + cosine over
     pred_layer_id (train.py:268-314, `distil_random_layer == 0` branch, restated inline like run_case's)."""
+    if only_cases and name not in only_cases:
+        return
     torch.manual_seed(0)
     cfg = ref_student_cfg(yaml_distiller, **s_over)
     assert not cfg.layerwise_proj and not cfg.enable_tr_layer and cfg.feature_grad_mult == 0.1
@@ -211,6 +217,8 @@ def run_case_upsampler_cnn(name, s_over, t_over, B, Lmax, lengths, yaml_distille
     The batch is un-padded on purpose: with a padding mask and dropout_input an identity (eval mode / p = 0) the reference's
     OWN backward raises - the encoder's in-place index_put (modules/module.py:273-274) overwrites the tensor cnn_proj_head's
     GELU saved ("modified by an inplace operation"); it only trains with dropout_input live, whose mask cannot be replayed."""
+    if only_cases and name not in only_cases:
+        return
     torch.manual_seed(0)
     cfg = ref_student_cfg(yaml_distiller, **s_over)
     cfg._cnn_weight = CNN_LOSS_WEIGHT  # train.py:43
@@ -271,6 +279,8 @@ def run_case_attn(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, yaml_t
     utils/utils.py (oracle/ref_extract.py) - is bound over every teacher and student encoder layer; the loss is the
     reference's OWN `W2V2Distil.calculate_loss` (train.py:236-405), compiled the same way and called on the two result
     dicts, so nothing in this fixture is builder-restated arithmetic."""
+    if only_cases and name not in only_cases:
+        return
     import ref_extract as R
     torch.manual_seed(0)
     cfg = ref_student_cfg(yaml_distiller, **s_over)
@@ -320,11 +330,7 @@ def run_case_attn(name, s_over, t_over, B, Lmax, lengths, yaml_distiller, yaml_t
 
 def main():
     import yaml
-    only = sys.argv[1:]  # optional: names of the cases to (re)generate
-    if only:
-        for fn_name in ("run_case", "run_case_split", "run_case_upsampler_cnn", "run_case_attn"):
-            fn = globals()[fn_name]
-            globals()[fn_name] = (lambda f: lambda name, *a, **k: f(name, *a, **k) if name in only else None)(fn)
+    only_cases.extend(sys.argv[1:])  # optional: names of the cases to (re)generate
     with open(os.path.join(REF, "data/conf/fithubert.yaml")) as f:
         ycfg = yaml.safe_load(f)["distiller"]
     # 1.5 - 2 s utterances (75 - 99 frames): parameter gradients are sums over frames, and with the 0.5 s / 27-frame
@@ -333,6 +339,10 @@ def main():
     run_case("tiny_hubert_pad", TINY_STUDENT, TINY_TEACHER, 3, 32000, [32000, 27411, 21000], ycfg)
     run_case("tiny_hubert_nopad", TINY_STUDENT, TINY_TEACHER, 2, 24000, [24000, 24000], ycfg)
     run_case("tiny_w2v2_pad_oddT", TINY_STUDENT, TINY_TEACHER, 2, 28100, [28100, 17321], ycfg, kind="wav2vec2")
+    # layer-wise heads WITHOUT a time-reduction layer: LayerWiseProjHead is the Linear alone (modules/module.py:633-646),
+    # the layers run at the full frame rate with mask rule M1 un-reduced, projections are [B, T, D] (no T' narrowing)
+    run_case("notr_layerwise_hubert_pad", dict(TINY_STUDENT, enable_tr_layer=False), TINY_TEACHER, 3, 24000, [24000, 20411, 15000],
+             ycfg)
     with open(os.path.join(REF, "data/conf/ex.yaml")) as f:
         ecfg = yaml.safe_load(f)["distiller"]
     run_case_split("split_hubert_pad", TINY_SPLIT_STUDENT, TINY_TEACHER, 3, 32000, [32000, 27411, 21000], ecfg)

@@ -1414,3 +1414,64 @@ def test_attention_map_recipe_error_behaviour(F):
     cfg["train"].update(attn_loss_weight=0, v_rel_loss_weight=1.0)
     with pytest.raises(TypeError):
         F.W2V2Distil(cfg, teacher_model=teacher, device="cuda")
+
+
+def test_layerwise_heads_without_tr_layer_match_reference_fixture(F):
+    """layerwise_proj True with enable_tr_layer False (LayerWiseProjHead = its Linear alone, modules/module.py:633-646; the
+    FitHuBERT family without time reduction): hidden states, projections [B, T, D], loss and every parameter gradient against
+    the fixture the unmodified reference produced - autograd API and fused step - and, on the same student, the
+    attention-map recipe's maps against the oracle (this is the layer-wise configuration that recipe can run on)."""
+    import bench
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "notr_layerwise_hubert_pad.pt"))
+    cfg = bench.yaml_cfg()
+    cfg["distiller"].update(g["student_cfg"])
+    n = g["student_cfg"]["encoder_layers"]
+    cfg["distiller"]["pred_layer_id"] = f"[{n - 1}]"
+    cfg["train"].update(distil_random_layer=n - 1, random_layer_weight=0.1)
+    tc = dict(g["teacher_cfg"])
+    teacher = F.TeacherModel(kind=tc.pop("kind"), **tc)
+    teacher.load_state_dict(g["teacher_state"])
+    step = F.W2V2Distil(cfg, teacher_model=F.TeacherWrapper(teacher.cuda()), device="cuda")
+    student = step.student_model
+    assert set(student.state_dict()) == set(g["student_state"])  # no upsampler anywhere, no TR conv
+    student.load_state_dict(g["student_state"])
+    student.eval()
+    x, pm = g["source"], g["padding_mask"]
+    with torch.no_grad():
+        sr = student(x.cuda(), pm)
+    assert torch.equal(sr["padding_mask"].cpu(), g["student_mask"]) and sr["tr_layer_results"] == []
+    for i, ref in enumerate(g["student_layers"]):
+        assert sr["layer_results"][i][0].shape == ref.shape and rel(sr["layer_results"][i][0], ref) < TOL
+    for i, ref in enumerate(g["projections"]):
+        assert sr["projections"][i].shape == ref.shape and rel(sr["projections"][i], ref) < TOL
+    s_res, t_res = step(x.cuda(), pm)
+    total, losses = step.calculate_loss(s_res, t_res)
+    assert abs(float(total) - float(g["loss"])) < 1e-2 * float(g["loss"])
+    total.backward()
+    check_grads([(k, p.grad) for k, p in student.named_parameters()], g["grads"], "notr_layerwise_api", min_count=40)
+    _, _, G = student.engine_state(True)
+    G.zero_()
+    parts = step.fused_forward_backward(x, pm)
+    assert abs(float(parts.sum()) - float(g["loss"])) < 1e-2 * float(g["loss"])
+    check_grads(list(G.export().items()), g["grads"], "notr_layerwise_fused", min_count=40)
+    # attention-map recipe on this student (4 heads like the tiny teacher, same frame rate): maps vs the oracle
+    cfg["train"].update(attn_loss_weight=1.0, attn_loss_type="mse", v_rel_loss_weight=1.0)
+    step2 = F.W2V2Distil(cfg, teacher_model=step.teacher_model, device="cuda")
+    step2.student_model.load_state_dict(g["student_state"])
+    step2.student_model.eval()
+    with torch.no_grad():
+        s2, t2 = step2(x.cuda(), pm)
+    scfg, tcfg = O.student_config(**g["student_cfg"]), O.teacher_config(**g["teacher_cfg"])
+    with torch.no_grad():
+        so = O.student_forward(g["student_state"], scfg, x, pm, return_attn=True)
+        to = O.teacher_forward(g["teacher_state"], tcfg, x, pm, return_attn=True)
+    for mine, ref in ((s2["layer_results"][-1][1], so["layer_results"][-1][1]), (t2["layer_results"][-1][1][0], to["layer_results"][-1][1][0])):
+        fin = ~ref[0].isinf()
+        assert torch.equal(mine[0].isinf().cpu(), ref[0].isinf())
+        assert float((mine[0].cpu()[fin] - ref[0][fin]).abs().max()) < TOL * float(ref[0][fin].abs().max())
+        assert rel(mine[1], ref[1]) < TOL
+    total2, losses2 = step2.calculate_loss(s2, t2)
+    want = O.attn_map_loss(so["layer_results"][-1][1][0], to["layer_results"][-1][1][0][0], "mse")
+    assert abs(float(losses2["attn_loss"]) - float(want)) < TOL * float(want)
+    want_v = O.value_relation_loss(so["layer_results"][-1][1][1], to["layer_results"][-1][1][0][1])
+    assert abs(float(losses2["v_rel_loss"]) - float(want_v)) < TOL * float(want_v)

@@ -179,6 +179,31 @@ def test_attention_recipe_needs_no_time_reduction_layer():
         O.student_forward(sd, scfg, x, None, return_attn=True)
 
 
+def test_oracle_matches_reference_fixture_layerwise_heads_without_tr_layer():
+    """layerwise_proj True with enable_tr_layer False: LayerWiseProjHead has no upsampler (modules/module.py:633-646), the
+    encoder layers run at the full frame rate under mask rule M1, projections are [B, T, D].  Fixture from the unmodified
+    reference (oracle/gen_golden.py::run_case, MSE with random-layer weights like fithubert.yaml)."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "notr_layerwise_hubert_pad.pt"))
+    scfg = O.student_config(**g["student_cfg"])
+    tcfg = O.teacher_config(**g["teacher_cfg"])
+    ssd = {k: v.clone().requires_grad_(True) for k, v in g["student_state"].items()}
+    assert set(ssd) == set(O.init_student_state(scfg)) and not any("upsampler" in k for k in ssd)
+    s = O.student_forward(ssd, scfg, g["source"], g["padding_mask"])
+    with torch.no_grad():
+        t = O.teacher_forward(g["teacher_state"], tcfg, g["source"], g["padding_mask"])
+    assert torch.equal(s["padding_mask"], g["student_mask"]) and s["tr_layer_results"] == [] and g["student_tr"] is None
+    for i, ref in enumerate(g["student_layers"]):
+        assert s["layer_results"][i][0].shape == ref.shape and relerr(s["layer_results"][i][0], ref) < 1e-5
+    for i, ref in enumerate(g["projections"]):
+        assert s["projections"][i].shape == ref.shape and relerr(s["projections"][i], ref) < 1e-5
+    loss, per_layer = O.distill_loss(s["projections"], t["layer_results"], g["layer_weights"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"])) and relerr(per_layer, g["per_layer"]) < 1e-5
+    loss.backward()
+    assert g["no_grad_params"] == []
+    for n, ref in g["grads"].items():
+        assert float((ssd[n].grad - ref).abs().max()) < 2e-4 * float(ref.abs().max()) + 1e-8, n
+
+
 def test_conv_layer_string_parser():
     assert O.parse_conv_layers(O.FITHUBERT_CONV) == [(128, 10, 5), (256, 1, 1)] + [(256, 3, 2)] * 4 + [(512, 1, 1)] + [(512, 2, 2)] * 2
     assert len(O.parse_conv_layers(O.HUBERT_CONV)) == 7
