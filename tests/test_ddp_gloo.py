@@ -85,3 +85,60 @@ def test_two_rank_bucketed_allreduce_matches_single_process():
     for rank, err, nb in res:
         assert err < 1e-5, (rank, err)
         assert nb == 5
+
+
+def _fit_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import types
+    from fithubert_b200.trainer import fit
+
+    class Shard:
+        """Stands in for W2V2Distil on one rank (fit only touches this surface).  Rank 0's validation shard keeps improving,
+        rank 1's gets worse: a rank-local EarlyStopping would fire on rank 1 alone and leave rank 0 blocked in the next
+        collective; the global mean (1 + 0.02 * epoch) gets worse from the start, so BOTH must stop after `patience` epochs."""
+
+        def __init__(self):
+            self.train_cfg = {"num_epochs": 40}
+            self.accumulate, self._micro, self.optimizer, self.epoch = 1, 0, None, 0
+            self.student_model = types.SimpleNamespace(train=lambda *a: None, eval=lambda: None)
+
+        def configure_optimizers(self, total_steps=0):
+            self.total_steps = total_steps
+
+        def training_step(self, batch, i):
+            return torch.tensor(2.0 + rank)
+
+        def training_epoch_end(self):
+            self.epoch += 1
+
+        def validation_step(self, batch, i):
+            return {"v_loss": torch.tensor(1.0 - 0.01 * self.epoch if rank == 0 else 1.0 + 0.05 * self.epoch)}
+
+    batches = [{"x": torch.zeros(2, 8)} for _ in range(3)]
+    res = fit(Shard(), batches, batches, patience=3)
+    q.put((rank, res["epochs_run"], res["stopped_early"], [round(h[2], 6) for h in res["history"]],
+           [round(h[1], 6) for h in res["history"]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fit_stops_on_the_same_epoch_on_every_rank():
+    """trainer.fit under world_size 2 (gloo): the monitored v_loss and the early-stop decision are reduced over the ranks
+    (Lightning does both), so ranks whose shards disagree still leave the loop together."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, e0, s0, v0, t0), (_, e1, s1, v1, t1) = res
+    assert e0 == e1 == 4 and s0 and s1          # best at epoch 0, then 3 epochs without improvement
+    assert v0 == v1 and t0 == t1                # every rank saw the same (global) numbers
+    assert abs(v0[0] - 1.02) < 1e-6 and abs(v0[1] - 1.04) < 1e-6 and abs(t0[0] - 2.5) < 1e-6  # global means
