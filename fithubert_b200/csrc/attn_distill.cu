@@ -298,8 +298,8 @@ template <int DP, bool TRANS>
 __global__ void __launch_bounds__(128) attn_scores_bwd_kernel(const __half* __restrict__ g, long long pitch, const __half* __restrict__ m,
                                                               long long ld_m, __half* __restrict__ out, long long ld_out, int T, int H,
                                                               int d, float alpha, int accumulate) {
-  __shared__ __align__(16) __half sg[kTile * (kTile + 8)];
-  __shared__ __align__(16) __half sm[kTile * (DP + 8)];
+  __shared__ __align__(16) __half sg[2][kTile * (kTile + 8)];
+  __shared__ __align__(16) __half sm[2][kTile * (DP + 8)];
   pdl_sync();
   const int r0 = blockIdx.x * kTile, bh = blockIdx.y;
   const int bi = bh / H, h = bh - bi * H;
@@ -309,13 +309,26 @@ __global__ void __launch_bounds__(128) attn_scores_bwd_kernel(const __half* __re
   float acc[DP / 8][4];
 #pragma unroll
   for (int i = 0; i < DP / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  for (int c0 = 0; c0 < T; c0 += kTile) {
-    // the loss kernel wrote every column up to the pitch (zeros in the padding): whole 16-byte chunks are readable
-    if (TRANS) load_tile<kTile>(sg, gb, pitch, c0, T, r0, (int)pitch);  // sg[c][r]
-    else load_tile<kTile>(sg, gb, pitch, r0, T, c0, (int)pitch);        // sg[r][c]
-    load_tile<DP>(sm, mb, ld_m, c0, T, 0, d);                            // sm[c][:]
-    cp_async_wait_all();
+  // contraction tiles stream through two shared buffers: tile c + 1 is in flight (cp.async) while tile c is multiplied.
+  // The loss kernel wrote every column of g up to the pitch (zeros in the padding): whole 16-byte chunks are readable.
+  auto load = [&](int buf, int c0) {
+    if (TRANS) load_tile<kTile>(sg[buf], gb, pitch, c0, T, r0, (int)pitch);  // sg[c][r]
+    else load_tile<kTile>(sg[buf], gb, pitch, r0, T, c0, (int)pitch);        // sg[r][c]
+    load_tile<DP>(sm[buf], mb, ld_m, c0, T, 0, d);                            // sm[c][:]
+    cp_async_commit();
+  };
+  const int nct = (T + kTile - 1) / kTile;
+  load(0, 0);
+  for (int ct = 0; ct < nct; ++ct) {
+    if (ct + 1 < nct) {
+      load((ct + 1) & 1, (ct + 1) * kTile);
+      cp_async_wait_group<1>();
+    } else {
+      cp_async_wait_group<0>();
+    }
     __syncthreads();
+    const __half* sgt = sg[ct & 1];
+    const __half* smt = sm[ct & 1];
 #pragma unroll
     for (int kk = 0; kk < kTile / 16; ++kk) {
       uint32_t af[4];
@@ -323,9 +336,9 @@ __global__ void __launch_bounds__(128) attn_scores_bwd_kernel(const __half* __re
         // A[r][c] = sg[c][r]: 8x8 blocks (r 0-7, c 0-7) (r 8-15, c 0-7) (r 0-7, c 8-15) (r 8-15, c 8-15), transposed on load
         const int c = kk * 16 + ((lane >> 4) << 3) + (lane & 7);
         const int r = warp * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4_t(smem_u32(sg + c * (kTile + 8) + r), af[0], af[1], af[2], af[3]);
+        ldsm_x4_t(smem_u32(sgt + c * (kTile + 8) + r), af[0], af[1], af[2], af[3]);
       } else {
-        ldsm_x4(smem_u32(sg + (warp * 16 + (lane & 15)) * (kTile + 8) + kk * 16 + (lane >> 4) * 8), af[0], af[1], af[2], af[3]);
+        ldsm_x4(smem_u32(sgt + (warp * 16 + (lane & 15)) * (kTile + 8) + kk * 16 + (lane >> 4) * 8), af[0], af[1], af[2], af[3]);
       }
 #pragma unroll
       for (int np = 0; np < DP / 16; ++np) {
@@ -333,12 +346,12 @@ __global__ void __launch_bounds__(128) attn_scores_bwd_kernel(const __half* __re
         // .trans matrices: (k 0-7, n 0-7) (k 8-15, n 0-7) (k 0-7, n 8-15) (k 8-15, n 8-15)
         const int row = kk * 16 + (lane & 15);
         const int col = np * 16 + (lane >> 4) * 8;
-        ldsm_x4_t(smem_u32(sm + row * (DP + 8) + col), b0, b1, b2, b3);
+        ldsm_x4_t(smem_u32(smt + row * (DP + 8) + col), b0, b1, b2, b3);
         mma16816(acc[2 * np], af, b0, b1);
         mma16816(acc[2 * np + 1], af, b2, b3);
       }
     }
-    __syncthreads();
+    __syncthreads();  // both buffers of tile ct are free before the prefetch two iterations ahead overwrites them
   }
   __half* ob = out + (long long)bi * T * ld_out + h * d;
 #pragma unroll
