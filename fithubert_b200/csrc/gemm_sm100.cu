@@ -68,7 +68,8 @@ struct GemmParams {
   int total_tiles;
   int use_tma_store;
   int stages;    // smem pipeline depth: 4, 3 or 2 depending on how many epilogue staging buffers are needed
-  int n_auxout;  // 0 / 2 staging buffers for the second output
+  int n_out;     // 2 .. 4 staging buffers for the TMA stores of D (deeper = more stores in flight behind the epilogue)
+  int n_auxout;  // 0 / n_out staging buffers for the second output
   int n_in;      // 0 / 3 / 4 staging buffers (<= kInRing) for the TMA-loaded epilogue input (residual or aux_in)
   int pair;      // 1: clusters of two CTAs share the B tile by TMA multicast (num_m_blk then counts PAIRS of row blocks)
   int two_bar;   // 1: the round-2 epilogue with two block barriers per output slab (FHB_GEMM_EPI2BAR, A/B only)
@@ -174,7 +175,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   constexpr uint32_t kBSlot = CG2 ? kBBytes / 2 : kBBytes;
   uint8_t* smem_b = smem + nstages * kABytes;
   uint8_t* smem_out = smem + nstages * (kABytes + kBSlot);     // 2 x 16 KiB staging buffers for TMA stores of D
-  uint8_t* smem_auxo = smem_out + 2 * kStoreBytes;             // 0 / 2 buffers for the second output
+  uint8_t* smem_auxo = smem_out + p.n_out * kStoreBytes;       // 0 / n_out buffers for the second output
   uint8_t* smem_in = smem_auxo + p.n_auxout * kStoreBytes;     // 0 / 3 buffers for the TMA-loaded epilogue input
   uint8_t* smem_tail = smem + 14 * kStoreBytes;
   float* bias_s = reinterpret_cast<float*>(smem_tail);  // [2][kMaxBN]
@@ -370,7 +371,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       for (int i = 0; i < p.n_in - (p.two_bar ? 1 : 0); ++i) prefetch_one();
     }
     int it = 0;
-    uint32_t slab_ctr = 0;
+    uint32_t slab_ctr = 0, obuf = 0;  // obuf: staging buffer of the current slab (round robin over p.n_out)
     float loss_local = 0.f;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_stride, ++it) {
       const Tile t = decode_tile(p, tile, pair_rank);
@@ -550,8 +551,9 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       //      tensor edge: TMA clips the store and zero-fills the load)
       for (int sidx = 0; sidx < n_slabs; ++sidx) {
         // double-buffered staging: D in out[0..1], the optional second output in auxo[0..1]
-        const uint32_t dbuf = out_u32 + (slab_ctr & 1u) * kStoreBytes;
-        const uint32_t abuf = auxo_u32 + (slab_ctr & 1u) * kStoreBytes;
+        const uint32_t dbuf = out_u32 + obuf * kStoreBytes;
+        const uint32_t abuf = auxo_u32 + obuf * kStoreBytes;
+        if (++obuf == (uint32_t)p.n_out) obuf = 0;
         // the buffers we are about to overwrite must have been drained by the TMA stores of slab - 2
         // (one bulk group per slab, so at most one group may still be reading)
         // ONE block barrier per slab (at its end): it publishes "every thread's st.shared of this slab is done" together
@@ -617,7 +619,13 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         fence_async_shared();
-        if (!p.two_bar && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // (the next slab writes the buffer last used n_out - 1 slabs ago: all but the n_out - 2 youngest store groups
+        // must have finished reading shared memory)
+        if (!p.two_bar && threadIdx.x == 0) {
+          if (p.n_out == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else if (p.n_out == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 0) {
           const int cc = t.n0 + sidx * slab_cols;
@@ -1124,17 +1132,21 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   // the ring's slabs have the geometry of D's: usable when the staged operand has D's element type (aux_in is always
   // bf16; the residual is bf16 or, with FHB_EPI_RES_F32, fp32); otherwise that operand is read from global memory
   const bool ring_f32 = !ring_aux && (flags & FHB_EPI_RES_F32) != 0;
-  p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? 2 : 0;
+  // staging depth of the output path: FHB_GEMM_NOUT = 2 | 3 | 4 (tuning; the pipeline keeps at least 2 stages)
+  static const int nout_env = getenv("FHB_GEMM_NOUT") ? atoi(getenv("FHB_GEMM_NOUT")) : 2;
+  p.n_out = p.two_bar ? 2 : (nout_env < 2 ? 2 : (nout_env > 4 ? 4 : nout_env));
+  p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? p.n_out : 0;
   // ring depth: 3 slabs (2 in flight); cta_group::2 stages are 2 units, so a 4th slab fits beside 4 pipeline stages - the
   // teacher's out_proj (K = 768: a tile's 64 KB of residual against 3.2 us of MMA) is bound by this ring
   static const int ring_cg2 = getenv("FHB_GEMM_RING") ? atoi(getenv("FHB_GEMM_RING")) : 4;
   p.n_in = (p.use_tma_store && ring_src && ring_f32 == out_f32) ? (p.pair == 2 ? (ring_cg2 < 3 ? 3 : (ring_cg2 > kInRing ? kInRing : ring_cg2)) : 3) : 0;
-  p.stages = (14 - 2 - p.n_auxout - p.n_in) / 3;
-  if (p.stages > 4) p.stages = 4;
-  if (p.pair == 2) {  // half B tiles: 2 units of 16 KiB per stage
-    p.stages = (14 - 2 - p.n_auxout - p.n_in) / 2;
-    if (p.stages > kStages) p.stages = kStages;
+  const int unit_per_stage = p.pair == 2 ? 2 : 3;  // cta_group::2: half B tiles, 2 units of 16 KiB per stage
+  while (p.n_out > 2 && (14 - p.n_out - p.n_auxout - p.n_in) / unit_per_stage < 2) {
+    --p.n_out;
+    if (p.n_auxout) p.n_auxout = p.n_out;
   }
+  p.stages = (14 - p.n_out - p.n_auxout - p.n_in) / unit_per_stage;
+  if (p.stages > (p.pair == 2 ? kStages : 4)) p.stages = p.pair == 2 ? kStages : 4;
   if (p.use_tma_store) {
     const int n_hi = (num_ob + ob_mod - 1) / ob_mod;
     if ((rc = make_out_tmap(&td, a->d, out_f32, a->n, a->m, ob_mod, n_hi, a->d_ld, a->d_lo_stride, a->d_hi_stride,
