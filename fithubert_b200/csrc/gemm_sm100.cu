@@ -44,6 +44,17 @@ constexpr uint32_t kBarBytes = 256;
 // 14 units of 16 KiB: 3 per pipeline stage + 2 output slabs (+ 2 second-output slabs) (+ 3 epilogue-input slabs)
 constexpr uint32_t kSmemBytes = 14 * kStoreBytes + kBiasBytes + kBarBytes;
 
+#ifdef FHB_GEMM_TRACE
+// tools/gemm_trace.py: clock64 stamps of the epilogue phases of CTA 0 (thread 0 and thread 255), 8 per slab
+__device__ long long* g_gemm_trace = nullptr;
+#define FHB_TRACE(slot)                                                                              \
+  do {                                                                                               \
+    if (trace_on && slab_ctr < 96u) g_gemm_trace[(trace_who * 96 + slab_ctr) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define FHB_TRACE(slot) do {} while (0)
+#endif
+
 struct GemmParams {
   int m, n, k, bn;
   int num_m_blk, num_n_blk, num_ob, ob_mod, split_k;
@@ -372,6 +383,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     int it = 0;
     uint32_t slab_ctr = 0, obuf = 0;  // obuf: staging buffer of the current slab (round robin over p.n_out)
+#ifdef FHB_GEMM_TRACE
+    const bool trace_on = g_gemm_trace != nullptr && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 255);
+    const int trace_who = threadIdx.x == 0 ? 0 : 1;
+#endif
     float loss_local = 0.f;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_stride, ++it) {
       const Tile t = decode_tile(p, tile, pair_rank);
@@ -383,9 +398,11 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int c = threadIdx.x;
         if (c < p.bn) bs[c] = (t.n0 + c < p.n) ? __ldg(p.bias + (long long)t.ob_hi * p.bias_hi_stride + t.n0 + c) : 0.f;
       }
+      FHB_TRACE(6);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
+      FHB_TRACE(7);
       const int row = t.m0 + row_in_tile;
       const bool row_ok = row < p.m;
       bool zero_row = false;
@@ -571,6 +588,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         const int c0 = sidx * slab_cols + half * my_cols;  // first tile column of this warp's share
         uint32_t r[32];
+        FHB_TRACE(0);
         tmem_ld16(taddr + c0, r);
         if (!out_f32) tmem_ld16(taddr + c0 + 16, r + 16);
         uint32_t ring[16];
@@ -589,6 +607,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         tmem_ld_wait();
+        FHB_TRACE(1);
         const uint32_t drow = dbuf + row_in_tile * 128;
         const uint32_t arow = abuf + row_in_tile * 128;
 #pragma unroll
@@ -618,6 +637,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
           }
         }
+        FHB_TRACE(2);
         fence_async_shared();
         // (the next slab writes the buffer last used n_out - 1 slabs ago: all but the n_out - 2 youngest store groups
         // must have finished reading shared memory)
@@ -626,7 +646,9 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           else if (p.n_out == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
         }
+        FHB_TRACE(3);
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        FHB_TRACE(4);
         if (threadIdx.x == 0) {
           const int cc = t.n0 + sidx * slab_cols;
           if (flags & FHB_EPI_ATOMIC_ADD) {
@@ -643,6 +665,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           // every thread has read this slab's ring slot (barrier above): refill it with the slab p.n_in ahead
           if (!p.two_bar && in_tma) prefetch_one();
         }
+        FHB_TRACE(5);
         ++slab_ctr;
       }
 
@@ -1174,3 +1197,11 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   if (a->a_major == 0 && a->b_major == 1) return launch<0, 1>(ta, tb, td, tx, ti, p, s);
   return launch<1, 1>(ta, tb, td, tx, ti, p, s);
 }
+
+#ifdef FHB_GEMM_TRACE
+// debug builds only (-DFHB_GEMM_TRACE, tools/gemm_trace.py): device buffer of 2 x 96 x 8 int64 clock stamps, or NULL
+extern "C" int fhb_gemm_set_trace_buffer(long long* buf) {
+  FHB_CUDA_CHECK(cudaMemcpyToSymbol(g_gemm_trace, &buf, sizeof(buf)));
+  return 0;
+}
+#endif
