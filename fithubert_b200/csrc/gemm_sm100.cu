@@ -2,12 +2,14 @@
 // (UMMA M=128, N<=256, K=16, accumulators in TMEM, double buffered) -> tcgen05.ld -> fused epilogue
 // -> 128B-swizzled smem slab -> TMA store (TMA reduce-add for split-K).
 //
-// One CTA per SM, 320 threads:
+// One CTA per SM, 352 threads:
 //   warps 0-7  epilogue: warp w owns TMEM lanes 32(w%4)..+31 (= tile rows) and column half (w/4) of
 //              every 128-byte output slab
 //   warp  8    TMA producer (one elected lane)
 //   warp  9    MMA issuer (one elected lane) + TMEM allocation
-// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
+//   warp 10    store warp (one elected lane): TMA stores of finished output slabs, refills of the epilogue-input ring
+// Four pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), staging-buffer full/empty
+// (epilogue <-> store warp: the epilogue warps meet at no block barrier inside a tile), static
 // round-robin tile schedule (tile = blockIdx.x + i * gridDim.x, n fastest so CTAs of one wave
 // share the A tile in L2).
 // PAIR MODE (K-major operands, p.pair = 1): the grid is launched as clusters of two CTAs that work on two vertically
@@ -33,7 +35,8 @@ constexpr int kStages = 6;   // barrier slots; the pipeline depth is p.stages (<
 constexpr int kAccStages = 2;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = kEpiThreads + 64;
+constexpr int kThreads = kEpiThreads + 96;  // + TMA producer warp, MMA warp, store warp
+constexpr int kMaxOut = 4;                  // most output staging buffers (p.n_out)
 constexpr uint32_t kABytes = kBM * kBK * 2;     // 16 KiB
 constexpr uint32_t kBBytes = kMaxBN * kBK * 2;  // 32 KiB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -83,7 +86,6 @@ struct GemmParams {
   int n_auxout;  // 0 / n_out staging buffers for the second output
   int n_in;      // 0 / 3 / 4 staging buffers (<= kInRing) for the TMA-loaded epilogue input (residual or aux_in)
   int pair;      // 1: clusters of two CTAs share the B tile by TMA multicast (num_m_blk then counts PAIRS of row blocks)
-  int two_bar;   // 1: the round-2 epilogue with two block barriers per output slab (FHB_GEMM_EPI2BAR, A/B only)
 };
 
 struct Tile {
@@ -196,7 +198,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* acc_full = bars + 2 * kStages;
   uint64_t* acc_empty = bars + 2 * kStages + kAccStages;
   uint64_t* in_full = bars + 2 * kStages + 2 * kAccStages;  // [kInRing]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages + kInRing);
+  uint64_t* out_full = in_full + kInRing;     // [kMaxOut] 256 arrivals: every epilogue thread has written its share of the slab
+  uint64_t* out_empty = out_full + kMaxOut;   // [kMaxOut] the store warp: the TMA store of that buffer has finished reading it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_empty + kMaxOut);
+  static_assert((2 * kStages + 2 * kAccStages + kInRing + 2 * kMaxOut) * 8 + 4 <= kBarBytes, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,6 +220,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(&acc_empty[i], p.pair == 2 ? 2 : kEpiThreads);  // cta_group::2: one arrival per CTA of the pair (see the epilogue)
     }
     for (int i = 0; i < kInRing; ++i) mbar_init(&in_full[i], 1);
+    for (int i = 0; i < kMaxOut; ++i) {
+      mbar_init(&out_full[i], kEpiThreads);
+      mbar_init(&out_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -331,6 +340,85 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         else tc_commit(&acc_full[as]);
       }
     }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ store warp (one elected lane)
+    // Takes every TMA out of the epilogue warps' path: it waits until all 256 epilogue threads have written (and fenced)
+    // their share of an output slab, issues the TMA store(s) of that staging buffer, refills the epilogue-input ring slot
+    // the slab has just released, and hands the buffer back once the store has finished reading it.  The epilogue warps
+    // therefore never meet at a block barrier inside a tile: a warp that is done with slab s starts slab s + 1 (the other
+    // buffer) at once.  (Measured before, profiles/r03_gemm_epilogue_trace.txt: per slab every epilogue thread waited
+    // 125 - 370 clk at the barrier plus 350 clk for thread 0 to issue the store.)
+    if (elect_one()) {
+      const int flags = p.flags;
+      const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
+      const bool two_out = (flags & FHB_EPI_STORE_PREACT) != 0;
+      const bool in_tma = EPI_IN && p.n_in > 0;
+      const int slab_cols = out_f32 ? 32 : 64;
+      const uint32_t out_u32 = smem_u32(smem_out), auxo_u32 = smem_u32(smem_auxo), in_u32 = smem_u32(smem_in);
+      auto tile_slabs = [&](const Tile& t) {
+        return p.use_tma_store ? (min(p.bn, p.n - t.n0) + slab_cols - 1) / slab_cols : 0;
+      };
+      // ---- input-ring prefetcher: walks the (tile, slab) sequence p.n_in slabs ahead of the consumers
+      int pf_tile = first_tile, pf_sidx = 0, pf_ns = 0;
+      uint32_t pf_slot = 0;
+      Tile pf_t = {0, 0, 0, 0, 0, 0};
+      auto prefetch_one = [&]() {
+        if (pf_tile >= p.total_tiles) return;
+        const uint32_t slot = pf_slot;
+        if (++pf_slot == (uint32_t)p.n_in) pf_slot = 0;
+        mbar_expect_tx(&in_full[slot], kStoreBytes);
+        tma_load_4d(&tm_in, &in_full[slot], in_u32 + slot * kStoreBytes, pf_t.n0 + pf_sidx * slab_cols, pf_t.m0, pf_t.ob_lo,
+                    pf_t.ob_hi);
+        if (++pf_sidx == pf_ns) {
+          pf_sidx = 0;
+          pf_tile += tile_stride;
+          if (pf_tile < p.total_tiles) {
+            pf_t = decode_tile(p, pf_tile, pair_rank);
+            pf_ns = tile_slabs(pf_t);
+          }
+        }
+      };
+      if (in_tma) {
+        tma_prefetch_desc(&tm_in);
+        if (pf_tile < p.total_tiles) {
+          pf_t = decode_tile(p, pf_tile, pair_rank);
+          pf_ns = tile_slabs(pf_t);
+        }
+        for (int i = 0; i < p.n_in; ++i) prefetch_one();  // all p.n_in slots start out free
+      }
+      uint32_t obuf = 0, ouse = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_stride) {
+        const Tile t = decode_tile(p, tile, pair_rank);
+        const int n_slabs = tile_slabs(t);
+        for (int sidx = 0; sidx < n_slabs; ++sidx) {
+          mbar_wait(&out_full[obuf], ouse & 1u);
+          const uint32_t dbuf = out_u32 + obuf * kStoreBytes;
+          const uint32_t abuf = auxo_u32 + obuf * kStoreBytes;
+          const int cc = t.n0 + sidx * slab_cols;
+          if (flags & FHB_EPI_ATOMIC_ADD) {
+            asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm_d), "r"(dbuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm_d), "r"(dbuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
+          }
+          if (two_out)
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&tm_aux), "r"(abuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // every epilogue thread has read this slab's ring slot (it arrived after doing so): refill it
+          if (in_tma) prefetch_one();
+          // hand the staging buffer(s) back as soon as the store has read them (the epilogue warps are busy with the
+          // next slab in the other buffer meanwhile)
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&out_empty[obuf]);
+          if (++obuf == (uint32_t)p.n_out) {
+            obuf = 0;
+            ++ouse;
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0-7)
     const int flags = p.flags;
@@ -350,39 +438,9 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     auto tile_slabs = [&](const Tile& t) {
       return p.use_tma_store ? (min(p.bn, p.n - t.n0) + slab_cols - 1) / slab_cols : 0;
     };
-    // ---- input-ring prefetcher (thread 0): walks the (tile, slab) sequence kInRing-1 slabs ahead
-    int pf_tile = first_tile, pf_sidx = 0, pf_ns = 0;
-    uint32_t pf_ctr = 0, pf_slot = 0;
-    uint32_t in_slot = 0, in_phase = 0;  // consumer side of the input ring
-    Tile pf_t = {0, 0, 0, 0, 0, 0};
-    auto prefetch_one = [&]() {
-      if (pf_tile >= p.total_tiles) return;
-      const uint32_t slot = pf_slot;
-      if (++pf_slot == (uint32_t)p.n_in) pf_slot = 0;
-      mbar_expect_tx(&in_full[slot], kStoreBytes);
-      tma_load_4d(&tm_in, &in_full[slot], in_u32 + slot * kStoreBytes, pf_t.n0 + pf_sidx * slab_cols, pf_t.m0, pf_t.ob_lo,
-                  pf_t.ob_hi);
-      ++pf_ctr;
-      if (++pf_sidx == pf_ns) {
-        pf_sidx = 0;
-        pf_tile += tile_stride;
-        if (pf_tile < p.total_tiles) {
-          pf_t = decode_tile(p, pf_tile, pair_rank);
-          pf_ns = tile_slabs(pf_t);
-        }
-      }
-    };
-    if (in_tma && threadIdx.x == 0) {
-      tma_prefetch_desc(&tm_in);
-      if (pf_tile < p.total_tiles) {
-        pf_t = decode_tile(p, pf_tile, pair_rank);
-        pf_ns = tile_slabs(pf_t);
-      }
-      // one-barrier epilogue: the refill that used to open slab 0 happens here (all p.n_in slots start out free)
-      for (int i = 0; i < p.n_in - (p.two_bar ? 1 : 0); ++i) prefetch_one();
-    }
+    uint32_t in_slot = 0, in_phase = 0;  // consumer side of the input ring (the store warp refills it)
     int it = 0;
-    uint32_t slab_ctr = 0, obuf = 0;  // obuf: staging buffer of the current slab (round robin over p.n_out)
+    uint32_t slab_ctr = 0, obuf = 0, ouse = 0;  // obuf: staging buffer of the current slab (round robin over p.n_out)
 #ifdef FHB_GEMM_TRACE
     const bool trace_on = g_gemm_trace != nullptr && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 255);
     const int trace_who = threadIdx.x == 0 ? 0 : 1;
@@ -567,24 +625,15 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       // ---- 128-byte slabs through shared memory + TMA (the last slab of a row of tiles may hang over the
       //      tensor edge: TMA clips the store and zero-fills the load)
       for (int sidx = 0; sidx < n_slabs; ++sidx) {
-        // double-buffered staging: D in out[0..1], the optional second output in auxo[0..1]
-        const uint32_t dbuf = out_u32 + obuf * kStoreBytes;
-        const uint32_t abuf = auxo_u32 + obuf * kStoreBytes;
-        if (++obuf == (uint32_t)p.n_out) obuf = 0;
-        // the buffers we are about to overwrite must have been drained by the TMA stores of slab - 2
-        // (one bulk group per slab, so at most one group may still be reading)
-        // ONE block barrier per slab (at its end): it publishes "every thread's st.shared of this slab is done" together
-        // with "the TMA store of the previous slab has finished reading its staging buffer" (thread 0 waits for that just
-        // before arriving - the store has had this whole slab's math to drain), so the next slab can overwrite the
-        // other buffer without a barrier of its own.  (p.two_bar: the round-2 scheme with a second barrier here.)
-        if (p.two_bar) {
-          if (threadIdx.x == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            // every thread has finished reading ring slot (slab_ctr - 1) % kInRing (barrier at the end of the
-            // previous slab): refill it with the slab kInRing - 1 ahead
-            if (in_tma) prefetch_one();
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+        // staging buffers (round robin): D in out[obuf], the optional second output in auxo[obuf].  The store warp hands a
+        // buffer back once the TMA store of its previous slab has read it (parity trick: the first use passes at once).
+        const uint32_t mybuf = obuf;
+        const uint32_t dbuf = out_u32 + mybuf * kStoreBytes;
+        const uint32_t abuf = auxo_u32 + mybuf * kStoreBytes;
+        mbar_wait(&out_empty[mybuf], (ouse & 1u) ^ 1u);
+        if (++obuf == (uint32_t)p.n_out) {
+          obuf = 0;
+          ++ouse;
         }
         const int c0 = sidx * slab_cols + half * my_cols;  // first tile column of this warp's share
         uint32_t r[32];
@@ -638,33 +687,10 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         FHB_TRACE(2);
-        fence_async_shared();
-        // (the next slab writes the buffer last used n_out - 1 slabs ago: all but the n_out - 2 youngest store groups
-        // must have finished reading shared memory)
-        if (!p.two_bar && threadIdx.x == 0) {
-          if (p.n_out == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else if (p.n_out == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-        }
+        fence_async_shared();  // this thread's shared-memory writes are visible to the async proxy (the TMA store) ...
         FHB_TRACE(3);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_arrive(&out_full[mybuf]);  // ... before the store warp sees the slab complete
         FHB_TRACE(4);
-        if (threadIdx.x == 0) {
-          const int cc = t.n0 + sidx * slab_cols;
-          if (flags & FHB_EPI_ATOMIC_ADD) {
-            asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(&tm_d), "r"(dbuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
-          } else {
-            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(&tm_d), "r"(dbuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
-          }
-          if (two_out)
-            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(&tm_aux), "r"(abuf), "r"(cc), "r"(t.m0), "r"(t.ob_lo), "r"(t.ob_hi) : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          // every thread has read this slab's ring slot (barrier above): refill it with the slab p.n_in ahead
-          if (!p.two_bar && in_tma) prefetch_one();
-        }
         FHB_TRACE(5);
         ++slab_ctr;
       }
@@ -715,7 +741,6 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         mbar_arrive(&acc_empty[as]);
       }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (EPI_IN && (flags & FHB_EPI_SQDIFF)) {
       loss_local = warp_sum(loss_local);
       if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_acc, loss_local * p.loss_weight);
@@ -1122,8 +1147,6 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
     p.drop_scale = fhb_dropout_scale(a->drop_p);
   }
   p.flags = flags;
-  static const int two_bar = getenv("FHB_GEMM_EPI2BAR") ? atoi(getenv("FHB_GEMM_EPI2BAR")) : 0;
-  p.two_bar = two_bar;
 
   CUtensorMap ta, tb;
   int rc;
@@ -1157,7 +1180,7 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   const bool ring_f32 = !ring_aux && (flags & FHB_EPI_RES_F32) != 0;
   // staging depth of the output path: FHB_GEMM_NOUT = 2 | 3 | 4 (tuning; the pipeline keeps at least 2 stages)
   static const int nout_env = getenv("FHB_GEMM_NOUT") ? atoi(getenv("FHB_GEMM_NOUT")) : 2;
-  p.n_out = p.two_bar ? 2 : (nout_env < 2 ? 2 : (nout_env > 4 ? 4 : nout_env));
+  p.n_out = nout_env < 2 ? 2 : (nout_env > 4 ? 4 : nout_env);
   p.n_auxout = (p.use_tma_store && (flags & FHB_EPI_STORE_PREACT)) ? p.n_out : 0;
   // ring depth: 3 slabs (2 in flight); cta_group::2 stages are 2 units, so a 4th slab fits beside 4 pipeline stages - the
   // teacher's out_proj (K = 768: a tile's 64 KB of residual against 3.2 us of MMA) is bound by this ring

@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfhb_sm100a.so")
+# FHB_LIB: another build of the same library (A/B runs of kernel variants on one box); default: the in-tree build
+LIB_PATH = os.environ.get("FHB_LIB") or os.path.join(_HERE, "libfhb_sm100a.so")
 
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_ROWZERO = 1, 2, 4, 8
 EPI_STORE_PREACT, EPI_MUL_DGELU, EPI_OUT_F32, EPI_ATOMIC_ADD, EPI_SQDIFF = 16, 32, 64, 128, 256
