@@ -170,7 +170,9 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile, int p
 // EPI_IN = 1: the epilogue reads [m][n] operands (residual / aux_in / loss target) laid out like D
 // CG2 = 1: the cta_group::2 instantiation.  A kernel that contains cta_group::2 instructions can only be launched as
 // clusters of two ("cluster misconfiguration" otherwise), so the pair-of-SMs path is a separate instantiation.
-template <int A_MN, int B_MN, int EPI_IN, int CG2 = 0>
+// FLAGS_CT >= 0: the epilogue flag set is a compile-time constant (the hot flag sets of the distillation step get their own
+// instantiation: the epilogue's ~15 runtime flag branches and the 25 KB of code behind them disappear); -1: p.flags at run time
+template <int A_MN, int B_MN, int EPI_IN, int CG2 = 0, int FLAGS_CT = -1>
 __global__ void __launch_bounds__(kThreads, 1)
 fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_aux,
@@ -349,7 +351,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // buffer) at once.  (Measured before, profiles/r03_gemm_epilogue_trace.txt: per slab every epilogue thread waited
     // 125 - 370 clk at the barrier plus 350 clk for thread 0 to issue the store.)
     if (elect_one()) {
-      const int flags = p.flags;
+      const int flags = FLAGS_CT >= 0 ? FLAGS_CT : p.flags;
       const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
       const bool two_out = (flags & FHB_EPI_STORE_PREACT) != 0;
       const bool in_tma = EPI_IN && p.n_in > 0;
@@ -421,7 +423,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 0-7)
-    const int flags = p.flags;
+    const int flags = FLAGS_CT >= 0 ? FLAGS_CT : p.flags;
     const bool out_f32 = (flags & FHB_EPI_OUT_F32) != 0;
     const bool out_f16 = (flags & FHB_EPI_OUT_BF16) == 0;                            // 16-bit D: fp16 unless flagged bf16
     const bool aux_f16 = out_f16 || (flags & FHB_EPI_AUX_DGELU) != 0;                 // a saved gelu' is always fp16
@@ -894,10 +896,10 @@ int pick_bn(int n, long long row_tiles, bool split_k) {
   return best;
 }
 
-template <int A_MN, int B_MN, int EPI_IN, int CG2 = 0>
+template <int A_MN, int B_MN, int EPI_IN, int CG2 = 0, int FLAGS_CT = -1>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
             const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
-  FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>,
+  FHB_ONCE_PER_DEVICE(FHB_CUDA_CHECK(cudaFuncSetAttribute(fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2, FLAGS_CT>,
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
   int grid = p.total_tiles < fhb_num_sms() ? p.total_tiles : fhb_num_sms();
   if (p.pair) {
@@ -920,7 +922,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
       q.attrs = qa;
       q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>, &q) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2, FLAGS_CT>, &q) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = 64;
       }
@@ -951,18 +953,80 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = fhb_pdl_enabled() ? 2 : 1;
-    FHB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>, ta, tb, td, tx, ti, p));
+    FHB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2, FLAGS_CT>, ta, tb, td, tx, ti, p));
   } else {
-    FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
+    FHB_CUDA_CHECK(fhb_launch((fhb_gemm_kernel<A_MN, B_MN, EPI_IN, CG2, FLAGS_CT>), dim3(grid), dim3(kThreads), kSmemBytes, s, ta, tb, td, tx, ti, p));
   }
   FHB_LAUNCH_CHECK();
   return 0;
 }
 
+constexpr int kEpiInFlags = FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX | FHB_EPI_SQDIFF;
+template <int A_MN, int B_MN, int CG2, int F>
+int launch_spec(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
+                const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
+  return launch2<A_MN, B_MN, (F & kEpiInFlags) != 0, CG2, F>(ta, tb, td, tx, ti, p, s);
+}
+#define FHB_SPEC_CASE(A, B, C, F) \
+  case F: return launch_spec<A, B, C, F>(ta, tb, td, tx, ti, p, s)
+
 template <int A_MN, int B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
            const CUtensorMap& ti, const GemmParams& p, cudaStream_t s) {
-  const bool epi_in = (p.flags & (FHB_EPI_RESIDUAL | FHB_EPI_MUL_DGELU | FHB_EPI_MUL_AUX | FHB_EPI_SQDIFF)) != 0;
+  // The flag sets the distillation step spends its time in (profiles/r03final_gemm_table.txt) run flag-specialised
+  // instantiations; every other combination takes the generic kernels below.  FHB_GEMM_NOSPEC=1: generic only.
+  static const bool nospec = getenv("FHB_GEMM_NOSPEC") != nullptr;
+  if (!nospec) {
+    constexpr int B_ = FHB_EPI_BIAS, G_ = FHB_EPI_GELU, R_ = FHB_EPI_RESIDUAL, P_ = FHB_EPI_STORE_PREACT, O32 = FHB_EPI_OUT_F32,
+                  AT = FHB_EPI_ATOMIC_ADD, DG = FHB_EPI_AUX_DGELU, MA = FHB_EPI_MUL_AUX, DR = FHB_EPI_DROPOUT, R32 = FHB_EPI_RES_F32,
+                  AL = FHB_EPI_ALPHA;
+    if constexpr (A_MN == 0 && B_MN == 0) {
+      if (p.pair == 2) {
+        switch (p.flags) {
+          FHB_SPEC_CASE(0, 0, 1, 0);        // positional-conv GEMMs (K = 4224 / 6336)
+          FHB_SPEC_CASE(0, 0, 1, G_);       // teacher conv stack (k = 3: K = 1536)
+          FHB_SPEC_CASE(0, 0, 1, B_ | R_);  // teacher fc2 + residual
+          default: break;
+        }
+      } else if (p.pair == 0) {
+        switch (p.flags) {
+          FHB_SPEC_CASE(0, 0, 0, 0);                       // plain products (k = 2 conv dgrads, head chain rule)
+          FHB_SPEC_CASE(0, 0, 0, B_);                      // q | k | v projections, heads
+          FHB_SPEC_CASE(0, 0, 0, B_ | G_);                 // teacher fc1
+          FHB_SPEC_CASE(0, 0, 0, G_);                      // conv layers, inference
+          FHB_SPEC_CASE(0, 0, 0, G_ | P_ | DG);            // student conv layers, training (saved gelu')
+          FHB_SPEC_CASE(0, 0, 0, B_ | G_ | P_ | DG);       // student fc1, p = 0
+          FHB_SPEC_CASE(0, 0, 0, B_ | G_ | P_ | DG | DR);  // student fc1 with activation dropout
+          FHB_SPEC_CASE(0, 0, 0, B_ | R_);                 // teacher out_proj + fp16 residual
+          FHB_SPEC_CASE(0, 0, 0, B_ | R_ | R32 | O32);       // student out_proj / fc2, fp32 stream
+          FHB_SPEC_CASE(0, 0, 0, B_ | R_ | R32 | O32 | DR);  // ... with dropout
+          FHB_SPEC_CASE(0, 0, 0, MA);                      // k = 1 conv dgrad x saved gelu'
+          default: break;
+        }
+      }
+    } else if constexpr (A_MN == 0 && B_MN == 1) {
+      if (p.pair == 0) {
+        switch (p.flags) {
+          FHB_SPEC_CASE(0, 1, 0, 0);               // plain dgrads
+          FHB_SPEC_CASE(0, 1, 0, MA);              // dgrad x saved gelu'
+          FHB_SPEC_CASE(0, 1, 0, R_ | R32 | O32);  // dgrad + fp32 residual gradient
+          FHB_SPEC_CASE(0, 1, 0, MA | R_ | R32 | O32);
+          default: break;
+        }
+      }
+    } else {
+      if (p.pair == 0) {
+        switch (p.flags) {
+          FHB_SPEC_CASE(1, 1, 0, AT | O32);  // weight gradients (split-K, fp32 reduce-add)
+          FHB_SPEC_CASE(1, 1, 0, O32);       // positional-conv weight gradient (one split)
+          FHB_SPEC_CASE(1, 1, 0, AL);        // folded-head weight gradient (fp16, scaled)
+          FHB_SPEC_CASE(1, 1, 0, AT | O32 | AL);
+          default: break;
+        }
+      }
+    }
+  }
+  const bool epi_in = (p.flags & kEpiInFlags) != 0;
   if constexpr (A_MN == 0 && B_MN == 0) {
     if (p.pair == 2) return epi_in ? launch2<0, 0, 1, 1>(ta, tb, td, tx, ti, p, s) : launch2<0, 0, 0, 1>(ta, tb, td, tx, ti, p, s);
   }
