@@ -226,7 +226,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const uint32_t prow = smem_u32(smem + S::kP) + col_off;
     const uint32_t dsrow = smem_u32(smem + S::kDS) + col_off;
     const uint32_t ch0 = (uint32_t)(quad & 1) * 4;  // first 16-byte chunk of this thread's 32 queries inside the atom
-    const uint32_t T2 = 2u * (uint32_t)((T + 1) >> 1);
     // dQ drain / final dK, dV store geometry: thread owns tile row `row`, column group [16 quad, 16 quad + 16)
     const int c16 = quad * 16;
     float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ);
@@ -274,58 +273,77 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const bool work = cols_live && warp_keys_live;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      uint32_t sr[32], dr[32];
-      if (work) {
-        tmem_ld32b(tm_s + lane_off + quad * 32, sr);
-        tmem_ld32b(tm_dp + lane_off + quad * 32, dr);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(s_free);
-      if (i > 0) mbar_wait(mma_done, (i - 1) & 1);  // smem P / dS free again
-      if (work) {
-        // P^T = 2^(S^T sc - lse), Pd^T = P^T o mask, dS^T = P^T o (dP^T o mask - delta)   (x scale folded into the dQ
-        // conversion and the dK store).  Two queries per FFMA2 / FMUL2; lse and delta come as 16-byte smem vectors.
-        const f32x2_t sc2 = pack2(sc, sc);
-        const float4* ls4 = reinterpret_cast<const float4*>(ls + quad * 32);
-        const float4* dl4 = reinterpret_cast<const float4*>(dl + quad * 32);
+      // Two passes of 16 query columns: 32 live accumulator registers instead of 64 (the 17-warp block caps a thread at
+      // 96 registers), so the hash constants stay in registers and nothing spills.  S^T / dP^T are released to the MMA
+      // warp after the second pass's loads.
+      const f32x2_t sc2 = pack2(sc, sc);
+      // Dropout bits: one 32-bit hash serves the key pair (2m, 2m + 1) of a query (fhb_common.cuh), and lanes 2m / 2m + 1
+      // of this warp own exactly those two key rows - so each lane hashes every second query of its 32 and the
+      // partner lane supplies the other half through one shuffle (the forward's pair index q * ceil(T / 2) + key / 2,
+      // advanced by a constant per query pair).  Even key rows read the low 16 bits, odd ones the high 16.
+      const bool odd = lane & 1;
+      const uint32_t lsh = odd ? 0u : 16u, thrhi = drop_thr << 16;
+      const uint32_t T2h = (uint32_t)((T + 1) >> 1);
+      const uint32_t xh = ((uint32_t)((b * H + h) * T + q0 + quad * 32 + (int)odd) * T2h + ((uint32_t)key >> 1)) * 0x9E3779B1u + drop_seed;
+      const uint32_t xstep = 2u * T2h * 0x9E3779B1u;
+      const float4* ls4 = reinterpret_cast<const float4*>(ls + quad * 32);
+      const float4* dl4 = reinterpret_cast<const float4*>(dl + quad * 32);
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          const float4 la = ls4[c >> 2], lb = ls4[(c >> 2) + 1], da = dl4[c >> 2], db = dl4[(c >> 2) + 1];
-          const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-          const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-          float pd[8], ds[8];
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float t0, t1;
-            unpack2(fma2(pack2(__uint_as_float(sr[c + e]), __uint_as_float(sr[c + e + 1])), sc2, pack2(nl[e], nl[e + 1])), t0, t1);
-            f32x2_t p2 = pack2(ex2_approx(t0), ex2_approx(t1));
-            if (masked_keys) p2 = mul2(p2, pack2(keymask, keymask));
-            f32x2_t dp2 = pack2(__uint_as_float(dr[c + e]), __uint_as_float(dr[c + e + 1]));
-            f32x2_t pd2 = p2;
-            if (DROP) {
-              const int ql = quad * 32 + c + e;  // query within the tile
-              const uint32_t qid = (uint32_t)((b * H + h) * T + q0 + ql);
-              const f32x2_t mk2 = pack2(dropout_one(drop_seed, qid * T2 + (uint32_t)key, drop_thr, drop_scale),
-                                        dropout_one(drop_seed, (qid + 1) * T2 + (uint32_t)key, drop_thr, drop_scale));
-              pd2 = mul2(p2, mk2);
-              dp2 = mul2(dp2, mk2);
-            }
-            unpack2(pd2, pd[e], pd[e + 1]);
-            unpack2(mul2(p2, add2(dp2, pack2(nd[e], nd[e + 1]))), ds[e], ds[e + 1]);
-          }
-          const uint32_t ch = ch0 + (uint32_t)(c >> 3);
-          st_shared_v4(prow + ((ch ^ rsw) << 4), pack_f16(pd[0], pd[1]), pack_f16(pd[2], pd[3]), pack_f16(pd[4], pd[5]),
-                       pack_f16(pd[6], pd[7]));
-          st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_f16(ds[0], ds[1]), pack_f16(ds[2], ds[3]), pack_f16(ds[4], ds[5]),
-                       pack_f16(ds[6], ds[7]));
+      for (int hp = 0; hp < 2; ++hp) {
+        uint32_t sr[16], dr[16];
+        if (work) {
+          tmem_ld16(tm_s + lane_off + quad * 32 + hp * 16, sr);
+          tmem_ld16(tm_dp + lane_off + quad * 32 + hp * 16, dr);
+          tmem_ld_wait();
         }
-      } else if (cols_live) {
-        // every key of this warp is masked: P = dS = 0 (the dQ contraction reads these rows)
+        if (hp == 1) {
+          tc_fence_before();
+          mbar_arrive(s_free);
+        } else if (i > 0) {
+          mbar_wait(mma_done, (i - 1) & 1);  // smem P / dS free again
+        }
+        if (work) {
+          // P^T = 2^(S^T sc - lse), Pd^T = P^T o mask, dS^T = P^T o (dP^T o mask - delta)   (x scale folded into the dQ
+          // conversion and the dK store).  Two queries per FFMA2 / FMUL2; lse and delta come as 16-byte smem vectors.
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          st_shared_v4(prow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
-          st_shared_v4(dsrow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+          for (int c8 = 0; c8 < 16; c8 += 8) {
+            const int c = hp * 16 + c8;  // first query column (of this thread's 32) of the group of eight
+            const float4 la = ls4[c >> 2], lb = ls4[(c >> 2) + 1], da = dl4[c >> 2], db = dl4[(c >> 2) + 1];
+            const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+            const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            float pd[8], ds[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              float t0, t1;
+              unpack2(fma2(pack2(__uint_as_float(sr[c8 + e]), __uint_as_float(sr[c8 + e + 1])), sc2, pack2(nl[e], nl[e + 1])), t0, t1);
+              f32x2_t p2 = pack2(ex2_approx(t0), ex2_approx(t1));
+              if (masked_keys) p2 = mul2(p2, pack2(keymask, keymask));
+              f32x2_t dp2 = pack2(__uint_as_float(dr[c8 + e]), __uint_as_float(dr[c8 + e + 1]));
+              f32x2_t pd2 = p2;
+              if (DROP) {
+                const uint32_t mine = fhb_hash32(xh + (uint32_t)((c + e) >> 1) * xstep);  // query c + e + odd
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);                // query c + e + 1 - odd
+                const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
+                const f32x2_t mk2 = pack2((b0 << lsh) >= thrhi ? drop_scale : 0.f, (b1 << lsh) >= thrhi ? drop_scale : 0.f);
+                pd2 = mul2(p2, mk2);
+                dp2 = mul2(dp2, mk2);
+              }
+              unpack2(pd2, pd[e], pd[e + 1]);
+              unpack2(mul2(p2, add2(dp2, pack2(nd[e], nd[e + 1]))), ds[e], ds[e + 1]);
+            }
+            const uint32_t ch = ch0 + (uint32_t)(c >> 3);
+            st_shared_v4(prow + ((ch ^ rsw) << 4), pack_f16(pd[0], pd[1]), pack_f16(pd[2], pd[3]), pack_f16(pd[4], pd[5]),
+                         pack_f16(pd[6], pd[7]));
+            st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_f16(ds[0], ds[1]), pack_f16(ds[2], ds[3]), pack_f16(ds[4], ds[5]),
+                         pack_f16(ds[6], ds[7]));
+          }
+        } else if (cols_live && hp == 0) {
+          // every key of this warp is masked: P = dS = 0 (the dQ contraction reads these rows)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            st_shared_v4(prow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+            st_shared_v4(dsrow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+          }
         }
       }
       tc_fence_before();

@@ -6,7 +6,7 @@ import torch
 from fithubert_b200 import kernels as K, lib as L
 
 dev = "cuda"
-bf = torch.bfloat16
+bf = torch.float16  # the library's 16-bit storage format
 sel = sys.argv[1:]
 
 
