@@ -31,19 +31,16 @@ constexpr int kT = 128;
 constexpr uint32_t kTileBytes = kT * 64 * 2;  // 16 KiB
 constexpr float kLog2e = 1.4426950408889634f;
 
-__device__ __forceinline__ void tmem_ld32b(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
 constexpr int kCT = 512;  // compute threads (16 warps)
+// Phase trace (tools/attn_bwd_trace.py): clock64 stamps of lane 0 of every compute warp ([warp * 64 + tile * 16 + slot])
+// and of the MMA thread ([1024 + tile * 16 + slot]) of CTA (0, 0, 0), compiled in only under -DFHB_BWD_TRACE (a separate
+// build of the library; exports fhb_attn_bwd_trace_read)
+#ifdef FHB_BWD_TRACE
+__device__ long long g_bwd_trace[2048];
+#define BWD_TR(slot) do { if (trace_on) g_bwd_trace[trace_base + (slot)] = clock64(); } while (0)
+#else
+#define BWD_TR(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <int HD>
@@ -51,7 +48,8 @@ struct Smem {
   static constexpr uint32_t kK = 0, kV = kTileBytes, kQ = 2 * kTileBytes, kDO = 4 * kTileBytes, kP = 6 * kTileBytes,
                             kDS = 8 * kTileBytes, kDQ = 10 * kTileBytes;
   static constexpr uint32_t kDQBytes = kT * HD * 4;
-  static constexpr uint32_t kStats = kDQ + kDQBytes;   // lse[2][128], delta[2][128] floats
+  static constexpr int kNDQ = 1;  // dQ staging buffers (2 fits for HD <= 48 and was measured 6 % SLOWER: profiles/r05_attnbwd2_ab.txt)
+  static constexpr uint32_t kStats = kDQ + kNDQ * kDQBytes;   // lse[2][128], delta[2][128] floats
   static constexpr uint32_t kBars = kStats + 4 * kT * 4;
   static constexpr uint32_t kTotal = kBars + 128;
 };
@@ -80,6 +78,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;
+#ifdef FHB_BWD_TRACE
+  const bool trace_on = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0;
+  const int trace_base = warp * 64;
+  if (threadIdx.x == 0 && trace_on) g_bwd_trace[2047] = clock64();
+#endif
   const int HDall = H * HD;
   const long long ld = 3LL * HDall;
   pdl_sync();  // before the first global read (valid[]) and before the early exit below
@@ -164,38 +167,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       issue_s(0);
       for (int i = 0; i < nq; ++i) {
         const int st = i & 1;
+        BWD_TR(16 * i + 0);
         if (i + 1 < nq) {
           mbar_wait(&qd_full[st ^ 1], ((i + 1) >> 1) & 1);
+          BWD_TR(16 * i + 1);
           mbar_wait(s_free, i & 1);
+          BWD_TR(16 * i + 2);
           tc_fence_after();
           issue_s(i + 1);
+          BWD_TR(16 * i + 3);
         }
         mbar_wait(p_full, i & 1);
+        BWD_TR(16 * i + 4);
         tc_fence_after();
         const uint32_t qa = smem_u32(smem + S::kQ + st * kTileBytes);
         const uint32_t da = smem_u32(smem + S::kDO + st * kTileBytes);
         const int ksteps = nq16(i) / 16;  // contraction over the valid queries of this tile only
-        for (int k = 0; k < ksteps; ++k) {  // A atoms of 64 queries, B 16 query rows = 2 KiB per step
+        // descriptors: base + constant (the 14-bit address field cannot overflow: shared memory ends below 256 KB), so
+        // the unrolled, predicated issue loops are a handful of instructions per MMA
+        const uint64_t d_p = umma_desc_sw128(pa, 0, 1024), d_ds = umma_desc_sw128(dsa, 0, 1024);
+        const uint64_t d_q = umma_desc_sw128(qa, 0, 1024), d_do = umma_desc_sw128(da, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < kT / 16; ++k) {  // A atoms of 64 queries, B 16 query rows = 2 KiB per step
           const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
-          tc_mma_bf16(tm_dv, umma_desc_sw128(pa + aoff, 0, 1024), umma_desc_sw128(da + k * 2048, 0, 1024), id_dv,
-                      (i > 0 || k > 0) ? 1u : 0u);
+          if (k < ksteps) tc_mma_bf16(tm_dv, d_p + (aoff >> 4), d_do + ((k * 2048) >> 4), id_dv, (i > 0 || k > 0) ? 1u : 0u);
         }
-        for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+        for (int k = 0; k < kT / 16; ++k) {
           const uint32_t aoff = (k >> 2) * kTileBytes + (k & 3) * 32;
-          tc_mma_bf16(tm_dk, umma_desc_sw128(dsa + aoff, 0, 1024), umma_desc_sw128(qa + k * 2048, 0, 1024), id_dk,
-                      (i > 0 || k > 0) ? 1u : 0u);
+          if (k < ksteps) tc_mma_bf16(tm_dk, d_ds + (aoff >> 4), d_q + ((k * 2048) >> 4), id_dk, (i > 0 || k > 0) ? 1u : 0u);
         }
+        BWD_TR(16 * i + 5);
         if (i > 0) {
           mbar_wait(dq_free, (i - 1) & 1);
           tc_fence_after();
         }
+        BWD_TR(16 * i + 6);
 #pragma unroll
         for (int k = 0; k < kT / 16; ++k)  // contraction over the 128 keys: dS^T rows are the K rows (MN-major A)
           tc_mma_bf16(tm_dqa, umma_desc_sw128(dsa + k * 2048, kTileBytes, 1024), umma_desc_sw128(ka + k * 2048, 0, 1024),
                       id_dq, k > 0 ? 1u : 0u);
         tc_commit(mma_done);
+        BWD_TR(16 * i + 7);
         if (i + 2 < nq) {
           mbar_wait(mma_done, i & 1);
+          BWD_TR(16 * i + 8);
           load_qd(i + 2);
         }
       }
@@ -228,11 +244,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     const uint32_t ch0 = (uint32_t)(quad & 1) * 4;  // first 16-byte chunk of this thread's 32 queries inside the atom
     // dQ drain / final dK, dV store geometry: thread owns tile row `row`, column group [16 quad, 16 quad + 16)
     const int c16 = quad * 16;
-    float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ);
     auto drain_dq = [&](int j) {
-      // staging buffer must have been read by the previous TMA reduce
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      bar_compute();
+      // two staging buffers: buffer j & 1's last reader, the TMA reduce of tile j - 2, was waited for by thread 0 before
+      // a block barrier every thread has passed since (top of the tile loop / before the last drain); one buffer: wait here
+      float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ + (j % S::kNDQ) * S::kDQBytes);
+      if (S::kNDQ == 1) {
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        bar_compute();
+      }
+      BWD_TR(16 * ((j + 1) & 3) + 11);
       tc_fence_after();
       if (c16 < DK) {
         uint32_t r[16];
@@ -249,29 +269,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tc_fence_before();
       mbar_arrive(dq_free);
       fence_async_shared();
+      BWD_TR(16 * ((j + 1) & 3) + 12);
       bar_compute();
+      BWD_TR(16 * ((j + 1) & 3) + 13);
       if (tid == 0) {
         asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
                      ::"l"(&tm_dq), "r"(smem_u32(dq_stage)), "r"(h * HD), "r"(j * kT), "r"(b) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
+    // lse / delta of a query tile: fetched one tile ahead as RAW values from a clamped address (nothing depends on the
+    // load before the block barrier that follows it, so its latency hides under the tile's math); negated / scaled /
+    // masked when they are stored to shared memory at the top of the next tile - the inner loop then reads them straight
+    // into packed FFMA2 addends
+    const float* stat_src = (tid < 128 ? lse : delta) + ((long long)b * H + h) * T;
+    auto load_stat = [&](int i) -> float {
+      return tid < 256 ? stat_src[min(i * kT + (tid & 127), T - 1)] : 0.f;
+    };
+    float stat = load_stat(0);
     for (int i = 0; i < nq; ++i) {
       const int q0 = i * kT;
       float* ls = lse_s + (i & 1) * kT;
       float* dl = delta_s + (i & 1) * kT;
-      if (tid < 256) {
-        const int q = q0 + (tid & 127);
-        const long long off = ((long long)b * H + h) * T + q;
-        // stored NEGATED: the inner loop then reads them straight into packed FFMA2 addends
-        if (tid < 128) ls[tid] = q < T ? -lse[off] * kLog2e : -INFINITY;
-        else dl[tid - 128] = q < T ? -delta[off] : 0.f;
-      }
+      BWD_TR(16 * i + 0);
+      if (tid < 128) ls[tid] = q0 + tid < T ? -stat * kLog2e : -INFINITY;
+      else if (tid < 256) dl[tid - 128] = q0 + tid - 128 < T ? -stat : 0.f;
+      if (i + 1 < nq) stat = load_stat(i + 1);
+      // the dQ staging buffer the drain below writes (tile i - 1) was last read by the reduce of tile i - 3
+      if (S::kNDQ == 2 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       bar_compute();
       const int nq16v = (min(kT, T - q0) + 15) & ~15;      // query columns the MMAs of this tile touch
       const bool cols_live = quad * 32 < nq16v;             // warp-uniform: this warp's queries exist
       const bool work = cols_live && warp_keys_live;
+      BWD_TR(16 * i + 1);
       mbar_wait(s_full, i & 1);
+      BWD_TR(16 * i + 2);
       tc_fence_after();
       // Two passes of 16 query columns: 32 live accumulator registers instead of 64 (the 17-warp block caps a thread at
       // 96 registers), so the hash constants stay in registers and nothing spills.  S^T / dP^T are released to the MMA
@@ -288,6 +320,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const uint32_t xstep = 2u * T2h * 0x9E3779B1u;
       const float4* ls4 = reinterpret_cast<const float4*>(ls + quad * 32);
       const float4* dl4 = reinterpret_cast<const float4*>(dl + quad * 32);
+      uint32_t held[8];
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
         uint32_t sr[16], dr[16];
@@ -296,11 +329,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           tmem_ld16(tm_dp + lane_off + quad * 32 + hp * 16, dr);
           tmem_ld_wait();
         }
+        BWD_TR(16 * i + 3 + 3 * hp);
         if (hp == 1) {
           tc_fence_before();
           mbar_arrive(s_free);
-        } else if (i > 0) {
-          mbar_wait(mma_done, (i - 1) & 1);  // smem P / dS free again
         }
         if (work) {
           // P^T = 2^(S^T sc - lse), Pd^T = P^T o mask, dS^T = P^T o (dP^T o mask - delta)   (x scale folded into the dQ
@@ -312,6 +344,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
             const float nd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
             float pd[8], ds[8];
+            if (hp == 0 && c8 == 8) {
+              // the previous tile's dV / dK / dQ MMAs still read the P / dS tiles while the first eight columns are being
+              // computed: wait for them only here, then store the eight columns held back in registers
+              if (i > 0) mbar_wait(mma_done, (i - 1) & 1);
+              BWD_TR(16 * i + 4);
+              const uint32_t chp = ch0 + (uint32_t)((hp * 16) >> 3);
+              st_shared_v4(prow + ((chp ^ rsw) << 4), held[0], held[1], held[2], held[3]);
+              st_shared_v4(dsrow + ((chp ^ rsw) << 4), held[4], held[5], held[6], held[7]);
+            }
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               float t0, t1;
@@ -332,26 +373,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
               unpack2(mul2(p2, add2(dp2, pack2(nd[e], nd[e + 1]))), ds[e], ds[e + 1]);
             }
             const uint32_t ch = ch0 + (uint32_t)(c >> 3);
-            st_shared_v4(prow + ((ch ^ rsw) << 4), pack_f16(pd[0], pd[1]), pack_f16(pd[2], pd[3]), pack_f16(pd[4], pd[5]),
-                         pack_f16(pd[6], pd[7]));
-            st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_f16(ds[0], ds[1]), pack_f16(ds[2], ds[3]), pack_f16(ds[4], ds[5]),
-                         pack_f16(ds[6], ds[7]));
+            if (hp == 0 && c8 == 0) {
+              held[0] = pack_f16(pd[0], pd[1]); held[1] = pack_f16(pd[2], pd[3]);
+              held[2] = pack_f16(pd[4], pd[5]); held[3] = pack_f16(pd[6], pd[7]);
+              held[4] = pack_f16(ds[0], ds[1]); held[5] = pack_f16(ds[2], ds[3]);
+              held[6] = pack_f16(ds[4], ds[5]); held[7] = pack_f16(ds[6], ds[7]);
+            } else {
+              st_shared_v4(prow + ((ch ^ rsw) << 4), pack_f16(pd[0], pd[1]), pack_f16(pd[2], pd[3]), pack_f16(pd[4], pd[5]),
+                           pack_f16(pd[6], pd[7]));
+              st_shared_v4(dsrow + ((ch ^ rsw) << 4), pack_f16(ds[0], ds[1]), pack_f16(ds[2], ds[3]), pack_f16(ds[4], ds[5]),
+                           pack_f16(ds[6], ds[7]));
+            }
           }
-        } else if (cols_live && hp == 0) {
-          // every key of this warp is masked: P = dS = 0 (the dQ contraction reads these rows)
+        } else if (hp == 0) {
+          if (i > 0) mbar_wait(mma_done, (i - 1) & 1);  // every thread: the drain below reads dQ_{i-1} out of TMEM
+          if (cols_live) {
+            // every key of this warp is masked: P = dS = 0 (the dQ contraction reads these rows)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            st_shared_v4(prow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
-            st_shared_v4(dsrow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+            for (int c = 0; c < 4; ++c) {
+              st_shared_v4(prow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+              st_shared_v4(dsrow + (((ch0 + c) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+            }
           }
         }
+        BWD_TR(16 * i + 5 + 3 * hp);
       }
       tc_fence_before();
       fence_async_shared();
       mbar_arrive(p_full);
+      BWD_TR(16 * i + 9);
       if (i > 0) drain_dq(i - 1);
+      BWD_TR(16 * i + 10);
     }
     mbar_wait(mma_done, (nq - 1) & 1);
+    if (S::kNDQ == 2) {
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the reduce of tile nq - 3 has read its buffer
+      bar_compute();
+    }
     drain_dq(nq - 1);
     // ---- dK, dV: TMEM -> fp16 -> global.  Thread = key row, columns [16 quad, 16 quad + 16)
     tc_fence_after();
@@ -452,6 +510,12 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
 }
 
 }  // namespace
+
+#ifdef FHB_BWD_TRACE
+extern "C" int fhb_attn_bwd_trace_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_bwd_trace, sizeof(long long) * (size_t)(n < 2048 ? n : 2048));
+}
+#endif
 
 // Called by fhb_attn_bwd (attention.cu) for head_dim 40 / 64 when a dQ workspace is supplied.
 int fhb_attn_bwd_tc(const void* qkv, const int32_t* valid, const void* dout, const float* lse, const float* delta,
