@@ -48,8 +48,8 @@ struct Smem {
   static constexpr uint32_t kK = 0, kV = kTileBytes, kQ = 2 * kTileBytes, kDO = 4 * kTileBytes, kP = 6 * kTileBytes,
                             kDS = 8 * kTileBytes, kDQ = 10 * kTileBytes;
   static constexpr uint32_t kDQBytes = kT * HD * 4;
-  static constexpr int kNDQ = 1;  // dQ staging buffers (2 fits for HD <= 48 and was measured 6 % SLOWER: profiles/r05_attnbwd2_ab.txt)
-  static constexpr uint32_t kStats = kDQ + kNDQ * kDQBytes;   // lse[2][128], delta[2][128] floats
+  // (one dQ staging buffer: two fit for HD <= 48 and were measured 6 % SLOWER, profiles/r05_attnbwd2_ab.txt)
+  static constexpr uint32_t kStats = kDQ + kDQBytes;   // lse[2][128], delta[2][128] floats
   static constexpr uint32_t kBars = kStats + 4 * kT * 4;
   static constexpr uint32_t kTotal = kBars + 128;
 };
@@ -245,13 +245,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // dQ drain / final dK, dV store geometry: thread owns tile row `row`, column group [16 quad, 16 quad + 16)
     const int c16 = quad * 16;
     auto drain_dq = [&](int j) {
-      // two staging buffers: buffer j & 1's last reader, the TMA reduce of tile j - 2, was waited for by thread 0 before
-      // a block barrier every thread has passed since (top of the tile loop / before the last drain); one buffer: wait here
-      float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ + (j % S::kNDQ) * S::kDQBytes);
-      if (S::kNDQ == 1) {
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        bar_compute();
-      }
+      // the staging buffer must have been read by the previous TMA reduce
+      float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ);
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      bar_compute();
       BWD_TR(16 * ((j + 1) & 3) + 11);
       tc_fence_after();
       if (c16 < DK) {
@@ -278,26 +275,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
-    // lse / delta of a query tile: fetched one tile ahead as RAW values from a clamped address (nothing depends on the
-    // load before the block barrier that follows it, so its latency hides under the tile's math); negated / scaled /
-    // masked when they are stored to shared memory at the top of the next tile - the inner loop then reads them straight
-    // into packed FFMA2 addends
+    // lse / delta of a query tile: fetched as RAW values from a clamped address well ahead of their use (nothing
+    // depends on the load before the block barrier that follows it, so its latency hides under a tile's math); negated /
+    // scaled / masked when they are stored to shared memory at the END of the previous tile, in front of the block
+    // barriers of the dQ drain - the tile loop has no barrier of its own.  The inner loop reads them straight into
+    // packed FFMA2 addends.
     const float* stat_src = (tid < 128 ? lse : delta) + ((long long)b * H + h) * T;
     auto load_stat = [&](int i) -> float {
       return tid < 256 ? stat_src[min(i * kT + (tid & 127), T - 1)] : 0.f;
     };
+    auto store_stat = [&](int i, float raw) {  // buffer i & 1: last read by the math of tile i - 2
+      if (tid < 128) lse_s[(i & 1) * kT + tid] = i * kT + tid < T ? -raw * kLog2e : -INFINITY;
+      else if (tid < 256) delta_s[(i & 1) * kT + tid - 128] = i * kT + tid - 128 < T ? -raw : 0.f;
+    };
     float stat = load_stat(0);
+    store_stat(0, stat);
+    if (nq > 1) stat = load_stat(1);
+    bar_compute();
     for (int i = 0; i < nq; ++i) {
       const int q0 = i * kT;
       float* ls = lse_s + (i & 1) * kT;
       float* dl = delta_s + (i & 1) * kT;
       BWD_TR(16 * i + 0);
-      if (tid < 128) ls[tid] = q0 + tid < T ? -stat * kLog2e : -INFINITY;
-      else if (tid < 256) dl[tid - 128] = q0 + tid - 128 < T ? -stat : 0.f;
-      if (i + 1 < nq) stat = load_stat(i + 1);
-      // the dQ staging buffer the drain below writes (tile i - 1) was last read by the reduce of tile i - 3
-      if (S::kNDQ == 2 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      bar_compute();
       const int nq16v = (min(kT, T - q0) + 15) & ~15;      // query columns the MMAs of this tile touch
       const bool cols_live = quad * 32 < nq16v;             // warp-uniform: this warp's queries exist
       const bool work = cols_live && warp_keys_live;
@@ -402,14 +401,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       fence_async_shared();
       mbar_arrive(p_full);
       BWD_TR(16 * i + 9);
-      if (i > 0) drain_dq(i - 1);
+      if (i + 1 < nq) {
+        store_stat(i + 1, stat);
+        if (i + 2 < nq) stat = load_stat(i + 2);
+      }
+      if (i > 0) drain_dq(i - 1);  // (its block barriers also publish the statistics stored above)
+      else bar_compute();
       BWD_TR(16 * i + 10);
     }
     mbar_wait(mma_done, (nq - 1) & 1);
-    if (S::kNDQ == 2) {
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the reduce of tile nq - 3 has read its buffer
-      bar_compute();
-    }
     drain_dq(nq - 1);
     // ---- dK, dV: TMEM -> fp16 -> global.  Thread = key row, columns [16 quad, 16 quad + 16)
     tc_fence_after();
