@@ -12,8 +12,8 @@
 //   warps 0-15: thread = (key row, 32-query quarter).  S^T / dP^T out of TMEM in one batch, then
 //        P^T = 2^(S^T*scale*log2e - lse_q), Pd^T = P^T o dropmask, dS^T = P^T o (dP^T o dropmask - delta_q)  [the
 //        softmax scale is applied once to dK at the final store and to dQ in dq_convert, not per element],
-//        both written as fp16 A operands (128B-swizzled);  dQ_i is drained TMEM -> smem -> TMA reduce-add (fp32)
-//        into a [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to fp16 afterwards.
+//        both written as fp16 A operands (128B-swizzled);  dQ_i is drained TMEM -> registers -> red.global.add.v4.f32
+//        into a fp32 [B, T, H*d] workspace (each key tile contributes its partial dQ), converted to fp16 afterwards.
 // S^T_{i+1} / dP^T_{i+1} are issued as soon as the compute warps hold tile i in registers, so the tensor pipe
 // works ahead of the exponentials.  Ragged edges are trimmed: the last query tile issues N = ceil16(valid
 // queries) and contracts over that many queries only; warps whose queries or keys are all out of range skip
@@ -21,9 +21,6 @@
 // out-of-range query rows are zero-filled by TMA and carry lse = +inf.  Dropout masks are regenerated from the
 // forward's (seed, index) hash.  head_dim 40: the 8 pad columns of K and V are zeroed in smem once per CTA.
 #include "fhb_common.cuh"
-
-int fhb_make_tmap_f32_3d(CUtensorMap* tm, void* ptr, const int64_t dim[3], const int64_t stride[2], uint32_t box0,
-                         uint32_t box1, const char* name);
 
 namespace {
 
@@ -46,10 +43,8 @@ __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" 
 template <int HD>
 struct Smem {
   static constexpr uint32_t kK = 0, kV = kTileBytes, kQ = 2 * kTileBytes, kDO = 4 * kTileBytes, kP = 6 * kTileBytes,
-                            kDS = 8 * kTileBytes, kDQ = 10 * kTileBytes;
-  static constexpr uint32_t kDQBytes = kT * HD * 4;
-  // (one dQ staging buffer: two fit for HD <= 48 and were measured 6 % SLOWER, profiles/r05_attnbwd2_ab.txt)
-  static constexpr uint32_t kStats = kDQ + kDQBytes;   // lse[2][128], delta[2][128] floats
+                            kDS = 8 * kTileBytes;
+  static constexpr uint32_t kStats = 10 * kTileBytes;   // lse[2][128], delta[2][128] floats
   static constexpr uint32_t kBars = kStats + 4 * kT * 4;
   static constexpr uint32_t kTotal = kBars + 128;
 };
@@ -57,7 +52,7 @@ struct Smem {
 template <int HD, bool DROP>
 __global__ void __launch_bounds__(kCT + 32, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                   const __grid_constant__ CUtensorMap tm_dq, const int* __restrict__ valid,
+                   float* __restrict__ dq_ws, const int* __restrict__ valid,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                    int T, int H, float scale, uint32_t drop_seed, uint32_t drop_thr, float drop_scale) {
   constexpr int DK = (HD + 15) / 16 * 16;
@@ -107,7 +102,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
-    tma_prefetch_desc(&tm_dq);
     mbar_init(kv_full, 1);
     mbar_init(kv_ready, kCT);
     mbar_init(&qd_full[0], 1);
@@ -245,35 +239,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // dQ drain / final dK, dV store geometry: thread owns tile row `row`, column group [16 quad, 16 quad + 16)
     const int c16 = quad * 16;
     auto drain_dq = [&](int j) {
-      // the staging buffer must have been read by the previous TMA reduce
-      float* dq_stage = reinterpret_cast<float*>(smem + S::kDQ);
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      bar_compute();
-      BWD_TR(16 * ((j + 1) & 3) + 11);
+      // dQ_j (this key tile's partial): TMEM -> registers -> vector reductions red.global.add.v4.f32 straight into the
+      // fp32 [B, T, H*d] workspace (thread = query row, 16 columns).  No shared-memory staging, no block barrier, no TMA:
+      // the staged TMA reduce-add this replaces cost every warp ~850 clk per tile (two block barriers around it,
+      // profiles/r05_attnbwd_trace_after.txt)
       tc_fence_after();
       if (c16 < DK) {
         uint32_t r[16];
         tmem_ld16(tm_dqa + lane_off + c16, r);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_free);
+        BWD_TR(16 * ((j + 1) & 3) + 11);
+        const int q = j * kT + row;
+        if (q < T) {
+          float* dst = dq_ws + ((long long)b * T + q) * HDall + h * HD + c16;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          if (c16 + 4 * q4 < HD)
-            *reinterpret_cast<float4*>(dq_stage + row * HD + c16 + 4 * q4) =
-                make_float4(__uint_as_float(r[4 * q4]), __uint_as_float(r[4 * q4 + 1]), __uint_as_float(r[4 * q4 + 2]),
-                            __uint_as_float(r[4 * q4 + 3]));
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (c16 + 4 * q4 < HD)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q4), "f"(__uint_as_float(r[4 * q4])),
+                           "f"(__uint_as_float(r[4 * q4 + 1])), "f"(__uint_as_float(r[4 * q4 + 2])),
+                           "f"(__uint_as_float(r[4 * q4 + 3])) : "memory");
+          }
         }
+      } else {
+        tc_fence_before();
+        mbar_arrive(dq_free);
       }
-      tc_fence_before();
-      mbar_arrive(dq_free);
-      fence_async_shared();
       BWD_TR(16 * ((j + 1) & 3) + 12);
-      bar_compute();
-      BWD_TR(16 * ((j + 1) & 3) + 13);
-      if (tid == 0) {
-        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
-                     ::"l"(&tm_dq), "r"(smem_u32(dq_stage)), "r"(h * HD), "r"(j * kT), "r"(b) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
     };
     // lse / delta of a query tile: fetched as RAW values from a clamped address well ahead of their use (nothing
     // depends on the load before the block barrier that follows it, so its latency hides under a tile's math); negated /
@@ -405,8 +398,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         store_stat(i + 1, stat);
         if (i + 2 < nq) stat = load_stat(i + 2);
       }
-      if (i > 0) drain_dq(i - 1);  // (its block barriers also publish the statistics stored above)
-      else bar_compute();
+      if (i > 0) drain_dq(i - 1);
+      bar_compute();  // the one block barrier of a tile: publishes the statistics stored above
       BWD_TR(16 * i + 10);
     }
     mbar_wait(mma_done, (nq - 1) & 1);
@@ -440,7 +433,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
       }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -473,7 +465,7 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
                cudaStream_t s) {
   using S = Smem<HD>;
   const int64_t E = (int64_t)H * HD;
-  CUtensorMap tq, td, ta;
+  CUtensorMap tq, td;
   {
     const int64_t dim[3] = {3 * E, T, B}, stride[2] = {3 * E, 3 * E * T};
     int rc = fhb_make_tmap_bf16_3d(&tq, qkv, dim, stride, 64, kT, "qkv");
@@ -483,8 +475,6 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
     const int64_t dim[3] = {E, T, B}, stride[2] = {E, E * T};
     int rc = fhb_make_tmap_bf16_3d(&td, dout, dim, stride, 64, kT, "dout");
     if (rc) return rc;
-    rc = fhb_make_tmap_f32_3d(&ta, dq_ws, dim, stride, HD, kT, "dq workspace");
-    if (rc) return rc;
   }
   FHB_CUDA_CHECK(cudaMemsetAsync(dq_ws, 0, sizeof(float) * (size_t)B * T * E, s));
   FHB_ONCE_PER_DEVICE({
@@ -493,11 +483,11 @@ int launch_bwd(const void* qkv, const int32_t* valid, const void* dout, const fl
   });
   dim3 grid((T + kT - 1) / kT, H, B);
   if (drop_p > 0.f)
-    FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, true>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
+    FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, true>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, dq_ws, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv), T,
                                                              H, scale, drop_seed, fhb_dropout_thr16(drop_p),
                                                              fhb_dropout_scale(drop_p)));
   else
-    FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, false>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, ta, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
+    FHB_CUDA_CHECK(fhb_launch((attn_bwd_tc_kernel<HD, false>), dim3(grid), dim3(kCT + 32), S::kTotal, s, tq, td, dq_ws, valid, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
                                                               T, H, scale, 0u, 0u, 1.f));
   FHB_LAUNCH_CHECK();
   const long long rows = (long long)B * T;

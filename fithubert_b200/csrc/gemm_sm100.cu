@@ -1075,32 +1075,6 @@ int fhb_make_tmap_bf16_4d(CUtensorMap* tm, const void* ptr, const int64_t dim[4]
   return 0;
 }
 
-// fp32, no swizzle: dense [box1][box0] smem rows (TMA reduce-add of partial results, attention_bwd_tc.cu)
-int fhb_make_tmap_f32_3d(CUtensorMap* tm, void* ptr, const int64_t dim[3], const int64_t stride[2], uint32_t box0,
-                         uint32_t box1, const char* name) {
-  TmapKey key;
-  memset(&key, 0, sizeof(key));
-  key.ptr = ptr;
-  key.d[0] = dim[0]; key.d[1] = dim[1]; key.d[2] = dim[2];
-  key.s[0] = stride[0]; key.s[1] = stride[1];
-  key.box0 = box0; key.box1 = box1; key.kind = 4;
-  if (tmap_lookup(key, tm)) return 0;
-  EncodeTiledFn enc = get_encode_fn();
-  FHB_ARG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-  FHB_ARG_CHECK(ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && stride[0] % 4 == 0 && stride[1] % 4 == 0 &&
-                    box0 % 4 == 0 && box0 <= 256 && box1 <= 256,
-                "tensor map %s: fp32 maps need 16-byte aligned base / strides / box rows", name);
-  cuuint64_t dims[3] = {(cuuint64_t)dim[0], (cuuint64_t)dim[1], (cuuint64_t)dim[2]};
-  cuuint64_t strides[2] = {(cuuint64_t)stride[0] * 4, (cuuint64_t)stride[1] * 4};
-  cuuint32_t box[3] = {box0, box1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FHB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", name, (int)r);
-  tmap_insert(key, *tm);
-  return 0;
-}
-
 extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   FHB_ARG_CHECK(a != nullptr, "gemm: null args");
   FHB_ARG_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "gemm: m,n,k must be positive (got %d,%d,%d)", a->m, a->n, a->k);
