@@ -251,15 +251,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tc_fence_before();
         mbar_arrive(dq_free);
         BWD_TR(16 * ((j + 1) & 3) + 11);
-        const int q = j * kT + row;
-        if (q < T) {
-          float* dst = dq_ws + ((long long)b * T + q) * HDall + h * HD + c16;
+        if constexpr (HD > 48) {
+          // 4 x 4 transpose of the 16-byte chunks inside every group of four lanes (two butterfly steps of shuffles): lane
+          // l then holds chunk l & 3 of the four rows 4 (l >> 2) .. + 3, so one reduction instruction of the warp covers
+          // 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.  d = 64, T = 779: 411 -> 389 us; at d = 40 (160-byte
+          // rows, 10 chunks) it measured 2 us SLOWER than the plain form below (profiles/r05_attnbwd_red_ab.txt)
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            if (c16 + 4 * q4 < HD)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q4), "f"(__uint_as_float(r[4 * q4])),
-                           "f"(__uint_as_float(r[4 * q4 + 1])), "f"(__uint_as_float(r[4 * q4 + 2])),
-                           "f"(__uint_as_float(r[4 * q4 + 3])) : "memory");
+          for (int bit = 0; bit < 2; ++bit) {
+            const bool up = (lane >> bit) & 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if ((c >> bit) & 1) continue;
+              const int lo = c, hi = c | (1 << bit);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const uint32_t send = up ? r[4 * lo + w] : r[4 * hi + w];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+                if (up) r[4 * lo + w] = recv;
+                else r[4 * hi + w] = recv;
+              }
+            }
+          }
+          const int cq = c16 + 4 * (lane & 3);                  // first column of this lane's chunk
+          const int qb = j * kT + quarter * 32 + (lane & ~3);   // first of its four query rows
+          float* dst = dq_ws + ((long long)b * T + qb) * HDall + h * HD + cq;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (qb + k < T && cq < HD)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (long long)k * HDall),
+                           "f"(__uint_as_float(r[4 * k])), "f"(__uint_as_float(r[4 * k + 1])), "f"(__uint_as_float(r[4 * k + 2])),
+                           "f"(__uint_as_float(r[4 * k + 3])) : "memory");
+          }
+        } else {
+          const int q = j * kT + row;
+          if (q < T) {
+            float* dst = dq_ws + ((long long)b * T + q) * HDall + h * HD + c16;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              if (c16 + 4 * q4 < HD)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q4), "f"(__uint_as_float(r[4 * q4])),
+                             "f"(__uint_as_float(r[4 * q4 + 1])), "f"(__uint_as_float(r[4 * q4 + 2])),
+                             "f"(__uint_as_float(r[4 * q4 + 3])) : "memory");
+            }
           }
         }
       } else {
