@@ -443,38 +443,44 @@ __device__ __forceinline__ float wn_dw(const float* __restrict__ dwt, int g, int
   return s;
 }
 
-// One block (1024 threads) per tap j.  Threads walk (g, ci, co) with co fastest: the dwt reads are contiguous runs
-// of cg floats; v / dv are touched at stride K either way (tap-fastest parameter layout).
-__global__ void __launch_bounds__(1024)
+// One block per (input channel ci, group g): the dW slab [co < cg][j < K] of that pair goes through shared memory, because
+// dwt is contiguous along co and v / dv along the tap j (tap-fastest parameter layout) - both sides are then read and
+// written in contiguous runs.  PHASE 0: tot[j] += sum_co dW * v (one atomic per tap and block).  PHASE 1 (second launch,
+// tot complete): dv, and dg by block (0, 0).  (r05: the one-block-per-tap version walked v at stride K twice: 119 us.)
+template <int PHASE>
+__global__ void __launch_bounds__(256)
 posconv_wn_bwd_kernel(const float* __restrict__ dwt, const float* __restrict__ v, const float* __restrict__ gain,
-                      const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg, int C, int G,
-                      int K, int cp, int accumulate, int delta) {
+                      const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg,
+                      float* __restrict__ tot, int C, int G, int K, int cp, int accumulate, int delta) {
+  extern __shared__ float wn_tile[];  // [cg][K + 1]
   pdl_sync();
-  const int j = blockIdx.x;
-  const int cg = C / G;
-  const int n = C * cg;
-  float s = 0.f;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int co = idx % cg, rest = idx / cg;
-    const int ci = rest % cg, g = rest / cg;
-    const long long i = (long long)(g * cg + co) * cg + ci;
-    s += wn_dw(dwt, g, j, ci, co, K, cp, delta) * __ldg(v + i * K + j);
+  const int ci = blockIdx.x, g = blockIdx.y;
+  const int cg = C / G, ld = K + 1, n = cg * K;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {  // co fastest: contiguous runs of dwt
+    const int co = idx % cg, j = idx / cg;
+    wn_tile[co * ld + j] = wn_dw(dwt, g, j, ci, co, K, cp, delta);
   }
-  __shared__ float red[32];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  float tot = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-  const float inv = inv_norm[j], gj = gain[j];
-  if (threadIdx.x == 0) dg[j] = (accumulate ? dg[j] : 0.f) + tot * inv;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int co = idx % cg, rest = idx / cg;
-    const int ci = rest % cg, g = rest / cg;
-    const long long vi = ((long long)(g * cg + co) * cg + ci) * K + j;
-    const float dw = wn_dw(dwt, g, j, ci, co, K, cp, delta);
-    const float val = gj * inv * (dw - __ldg(v + vi) * tot * inv * inv);
-    dv[vi] = (accumulate ? dv[vi] : 0.f) + val;
+  if (PHASE == 0) {
+    // thread = (tap j, a slice of the co's): v read in runs of K floats  (K <= blockDim.x, checked by the host)
+    const int slices = blockDim.x / K;
+    const int j = threadIdx.x % K, sl = threadIdx.x / K;
+    if (sl < slices) {
+      float acc = 0.f;
+      for (int co = sl; co < cg; co += slices)
+        acc += wn_tile[co * ld + j] * __ldg(v + ((long long)(g * cg + co) * cg + ci) * K + j);
+      atomicAdd(tot + j, acc);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {  // j fastest: contiguous runs of v / dv
+      const int j = idx % K, co = idx / K;
+      const long long vi = ((long long)(g * cg + co) * cg + ci) * K + j;
+      const float inv = __ldg(inv_norm + j), t = __ldg(tot + j);
+      const float val = __ldg(gain + j) * inv * (wn_tile[co * ld + j] - __ldg(v + vi) * t * inv * inv);
+      dv[vi] = (accumulate ? dv[vi] : 0.f) + val;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+      for (int j = threadIdx.x; j < K; j += blockDim.x) dg[j] = (accumulate ? dg[j] : 0.f) + __ldg(tot + j) * __ldg(inv_norm + j);
   }
 }
 
@@ -632,7 +638,18 @@ extern "C" int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float*
                                   float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate,
                                   int32_t delta, fhb_stream_t stream) {
   FHB_ARG_CHECK(dwt && v && g && inv_norm && dv && dg && delta >= 1, "posconv_wn_bwd: null pointer");
-  FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel, dim3(K), dim3(1024), 0, static_cast<cudaStream_t>(stream), dwt, v, g,
-                            inv_norm, dv, dg, C, G, K, cp, accumulate, delta));
+  FHB_ARG_CHECK(G > 0 && C % G == 0 && K > 0 && K <= 256, "posconv_wn_bwd: bad geometry (C=%d G=%d K=%d)", C, G, K);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cg = C / G;
+  const size_t smem = sizeof(float) * (size_t)cg * (K + 1);
+  FHB_ARG_CHECK(smem <= 48 * 1024, "posconv_wn_bwd: group width %d x %d taps does not fit 48 KB of shared memory", cg, K);
+  float* tot = nullptr;  // per-tap dot products: stream-ordered scratch, K floats
+  FHB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&tot), sizeof(float) * (size_t)K, s));
+  FHB_CUDA_CHECK(cudaMemsetAsync(tot, 0, sizeof(float) * (size_t)K, s));
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel<0>, dim3(cg, G), dim3(256), smem, s, dwt, v, g, inv_norm, dv, dg, tot, C, G, K,
+                            cp, accumulate, delta));
+  FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel<1>, dim3(cg, G), dim3(256), smem, s, dwt, v, g, inv_norm, dv, dg, tot, C, G, K,
+                            cp, accumulate, delta));
+  FHB_CUDA_CHECK(cudaFreeAsync(tot, s));
   return 0;
 }
