@@ -579,6 +579,20 @@ def main():
         for _ in range(2):
             dev_step()
         torch.cuda.synchronize()
+        if os.environ.get("FHB_GEMM_STEPLOG"):
+            # diagnostic (trace build of the library, tools/gemm_steplog.py): start / end of every GEMM launch of 3 more
+            # steps queued back to back, in GPU nanoseconds
+            import ctypes as C
+            from fithubert_b200 import lib as L
+            L.lib().fhb_gemm_steplog_read(None, 0, 1)
+            for _ in range(3):
+                dev_step()
+            host = (C.c_longlong * (6 * 8192))()
+            n = L.lib().fhb_gemm_steplog_read(host, 8192, 1)
+            with open(os.environ["FHB_GEMM_STEPLOG"], "w") as f:
+                for i in range(n):
+                    e = host[6 * i:6 * i + 6]
+                    f.write("%d %d %d %d %d %d %d\n" % (e[0], e[1], e[2] >> 32, e[2] & 0xFFFFFFFF, e[3] >> 32, e[3] & 0xFFFFFFFF, e[5] - e[4]))
         return
     sampler = ClockSampler(local)
     def measure_e2e():

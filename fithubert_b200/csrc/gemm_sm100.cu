@@ -54,8 +54,28 @@ __device__ long long* g_gemm_trace = nullptr;
   do {                                                                                               \
     if (trace_on && slab_ctr < 96u) g_gemm_trace[(trace_who * 96 + slab_ctr) * 8 + (slot)] = clock64(); \
   } while (0)
+// whole-kernel timeline of CTA 0 (one stamp per slot, written by whichever thread passes the point): [2 * 96 * 8 + slot]
+#define FHB_TL(slot)                                                                                  \
+  do {                                                                                                \
+    if (g_gemm_trace != nullptr && blockIdx.x == 0) g_gemm_trace[2 * 96 * 8 + (slot)] = clock64();   \
+  } while (0)
+// start / end of EVERY CTA in nanoseconds (%globaltimer): [2 * 96 * 8 + 32 + 2 * blockIdx.x + {0, 1}], up to 512 CTAs
+__device__ __forceinline__ long long fhb_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FHB_CTA_STAMP(which)                                                                                    \
+  do {                                                                                                          \
+    if (g_gemm_trace != nullptr && blockIdx.x < 512) g_gemm_trace[2 * 96 * 8 + 32 + 2 * blockIdx.x + (which)] = fhb_globaltimer(); \
+  } while (0)
+// log of every launch (CTA 0: start / end in ns, shape): tools/gemm_steplog.py reads it after a few training steps
+__device__ long long g_gemm_log[6 * 8192];
+__device__ unsigned int g_gemm_log_n = 0;
 #else
 #define FHB_TRACE(slot) do {} while (0)
+#define FHB_TL(slot) do {} while (0)
+#define FHB_CTA_STAMP(which) do {} while (0)
 #endif
 
 struct GemmParams {
@@ -207,6 +227,20 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) FHB_TL(0);  // kernel entry
+  if (threadIdx.x == 0) FHB_CTA_STAMP(0);
+#ifdef FHB_GEMM_TRACE
+  unsigned int log_slot = 0xFFFFFFFFu;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    log_slot = atomicAdd(&g_gemm_log_n, 1u);
+    if (log_slot < 8192u) {
+      g_gemm_log[6 * log_slot] = fhb_globaltimer();
+      g_gemm_log[6 * log_slot + 2] = ((long long)p.m << 32) | (unsigned int)p.n;
+      g_gemm_log[6 * log_slot + 3] = ((long long)p.k << 32) | (unsigned int)p.flags;
+      g_gemm_log[6 * log_slot + 4] = clock64();
+    }
+  }
+#endif
 
   if (warp == 8 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();  // 128B-swizzle atoms need a 1024-byte aligned base
@@ -237,7 +271,9 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (p.pair) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
+  if (threadIdx.x == 0) FHB_TL(1);  // barriers initialised, TMEM allocated
   pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) FHB_TL(2);  // predecessor grid complete
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
@@ -320,6 +356,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t tmem_d = tmem_base + as * kMaxBN;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (kb == t.kb_begin && it < 4) FHB_TL(4 + 4 * it);  // first stage of tile `it` has landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * kBSlot);
@@ -340,6 +377,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         if constexpr (CG2) tc_commit_cg2(&acc_full[as], (uint16_t)3);  // each CTA's epilogue drains its own 128 rows
         else tc_commit(&acc_full[as]);
+        if (it < 4) FHB_TL(5 + 4 * it);  // every MMA of tile `it` issued
       }
     }
   } else if (warp == 10) {
@@ -463,6 +501,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       FHB_TRACE(7);
+      if (threadIdx.x == 0 && it < 4) FHB_TL(6 + 4 * it);  // accumulator of tile `it` complete
       const int row = t.m0 + row_in_tile;
       const bool row_ok = row < p.m;
       bool zero_row = false;
@@ -733,6 +772,7 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                              pack16(v[14], v[15], out_f16));
         }
       }
+      if (threadIdx.x == 0 && it < 4) FHB_TL(7 + 4 * it);  // epilogue of tile `it` done (this thread)
       tc_fence_before();
       if (cg2) {
         // the leader's MMA warp waits for both CTAs' epilogues: ONE (remote) arrival per CTA behind a block barrier instead of
@@ -751,6 +791,14 @@ fhb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FHB_TL(3);  // every warp done (the store warp has issued and drained its last store)
+  if (threadIdx.x == 0) FHB_CTA_STAMP(1);
+#ifdef FHB_GEMM_TRACE
+  if (log_slot < 8192u) {
+    g_gemm_log[6 * log_slot + 1] = fhb_globaltimer();
+    g_gemm_log[6 * log_slot + 5] = clock64();
+  }
+#endif
   if (p.pair) cluster_sync_all();  // the peer may still be arriving on this CTA's empty barriers
   if (warp == 9) {
     tc_fence_after();
@@ -1261,6 +1309,19 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
 
 #ifdef FHB_GEMM_TRACE
 // debug builds only (-DFHB_GEMM_TRACE, tools/gemm_trace.py): device buffer of 2 x 96 x 8 int64 clock stamps, or NULL
+extern "C" int fhb_gemm_steplog_read(long long* host, int max_entries, int reset) {
+  unsigned int n = 0;
+  FHB_CUDA_CHECK(cudaDeviceSynchronize());
+  FHB_CUDA_CHECK(cudaMemcpyFromSymbol(&n, g_gemm_log_n, sizeof(n)));
+  if (n > 8192u) n = 8192u;
+  if ((int)n > max_entries) n = (unsigned int)max_entries;
+  if (host && n) FHB_CUDA_CHECK(cudaMemcpyFromSymbol(host, g_gemm_log, sizeof(long long) * 6 * n));
+  if (reset) {
+    const unsigned int zero = 0;
+    FHB_CUDA_CHECK(cudaMemcpyToSymbol(g_gemm_log_n, &zero, sizeof(zero)));
+  }
+  return (int)n;
+}
 extern "C" int fhb_gemm_set_trace_buffer(long long* buf) {
   FHB_CUDA_CHECK(cudaMemcpyToSymbol(g_gemm_trace, &buf, sizeof(buf)));
   return 0;
