@@ -634,22 +634,23 @@ extern "C" int fhb_posconv_unpack_bwd(const void* dh, const void* dxc, const int
   return 0;
 }
 
-extern "C" int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, const float* inv_norm, float* dv,
-                                  float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate,
-                                  int32_t delta, fhb_stream_t stream) {
-  FHB_ARG_CHECK(dwt && v && g && inv_norm && dv && dg && delta >= 1, "posconv_wn_bwd: null pointer");
+extern "C" int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, float* ws, float* dv, float* dg,
+                                  int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate, int32_t delta,
+                                  fhb_stream_t stream) {
+  FHB_ARG_CHECK(dwt && v && g && ws && dv && dg && delta >= 1, "posconv_wn_bwd: null pointer");
   FHB_ARG_CHECK(G > 0 && C % G == 0 && K > 0 && K <= 256, "posconv_wn_bwd: bad geometry (C=%d G=%d K=%d)", C, G, K);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cg = C / G;
   const size_t smem = sizeof(float) * (size_t)cg * (K + 1);
   FHB_ARG_CHECK(smem <= 48 * 1024, "posconv_wn_bwd: group width %d x %d taps does not fit 48 KB of shared memory", cg, K);
-  float* tot = nullptr;  // per-tap dot products: stream-ordered scratch, K floats
-  FHB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&tot), sizeof(float) * (size_t)K, s));
+  // ws is fhb_posconv_wn_prep's workspace: [K, 2K) holds 1 / ||v[:, :, j]||; [0, K) (its sums of squares, dead since
+  // the prep) takes the per-tap dot products.  (A stream-ordered cudaMallocAsync scratch cost 8 ms of HOST time per call.)
+  float* tot = ws;
+  const float* inv_norm = ws + K;
   FHB_CUDA_CHECK(cudaMemsetAsync(tot, 0, sizeof(float) * (size_t)K, s));
   FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel<0>, dim3(cg, G), dim3(256), smem, s, dwt, v, g, inv_norm, dv, dg, tot, C, G, K,
                             cp, accumulate, delta));
   FHB_CUDA_CHECK(fhb_launch(posconv_wn_bwd_kernel<1>, dim3(cg, G), dim3(256), smem, s, dwt, v, g, inv_norm, dv, dg, tot, C, G, K,
                             cp, accumulate, delta));
-  FHB_CUDA_CHECK(cudaFreeAsync(tot, s));
   return 0;
 }

@@ -1286,7 +1286,7 @@ def student_backward(P, W: WeightSet, g: Geometry, G_: GradStore, c, dpred: torc
     b3 = L.tensor3(dcg, data_ptr=dcg.data_ptr() + 2 * pad_b * cp, dim=(dl * cp, R, B * G), stride=(dl * cp, Tp * cp))
     K.gemm_raw(a3, b3, dwt, g.kpx * cp, dl * cp, R, a_major=1, b_major=1, num_ob=G, ob_mod=G, num_cb=B,
                a_coord=(0, 0, 1, G), b_coord=(0, 0, 1, G), d_ld=dl * cp, d_lo_stride=g.kpx * cp * dl * cp, split_k=1)
-    K.posconv_wn_bwd(dwt, P["encoder.pos_conv.0.weight_v"], P["encoder.pos_conv.0.weight_g"], W["pc.inv"],
+    K.posconv_wn_bwd(dwt, P["encoder.pos_conv.0.weight_v"], P["encoder.pos_conv.0.weight_g"], W["pc.ws"],
                      gv("encoder.pos_conv.0.weight_v"), gv("encoder.pos_conv.0.weight_g"), E, G, kp, cp, True, delta=dl)
     dfeat = torch.empty(B * T, E, device=dev, dtype=bf16)
     K.posconv_unpack_bwd(dh, dxc, c.valid_t, dfeat, B, T, E, G, cp, delta=dl)

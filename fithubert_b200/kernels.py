@@ -307,8 +307,10 @@ def posconv_unpack_bwd(dh, dxc, valid, dx, B, T, Cd, G, cp, delta=1):
                                            L.stream_ptr()), "fhb_posconv_unpack_bwd")
 
 
-def posconv_wn_bwd(dwt, v, g, inv_norm, dv, dg, Cd, G, Kt, cp, accumulate=True, delta=1):
-    L.check(L.lib().fhb_posconv_wn_bwd(L.ptr(dwt), L.ptr(v), L.ptr(g), L.ptr(inv_norm), L.ptr(dv), L.ptr(dg), Cd, G, Kt,
+def posconv_wn_bwd(dwt, v, g, ws, dv, dg, Cd, G, Kt, cp, accumulate=True, delta=1):
+    """ws: posconv_wn_prep's fp32 [2 * Kt] workspace (ws[Kt:] = 1 / norm is read, ws[:Kt] is scratch)."""
+    assert ws.numel() >= 2 * Kt and ws.dtype == torch.float32
+    L.check(L.lib().fhb_posconv_wn_bwd(L.ptr(dwt), L.ptr(v), L.ptr(g), L.ptr(ws), L.ptr(dv), L.ptr(dg), Cd, G, Kt,
                                        cp, int(accumulate), delta, L.stream_ptr()), "fhb_posconv_wn_bwd")
 
 

@@ -219,10 +219,11 @@ int fhb_posconv_unpack_bwd(const void* dh, const void* dxc, const int32_t* valid
                            int32_t C, int32_t G, int32_t cp, int32_t delta, fhb_stream_t stream);
 /* dv, dg from dwt (fp32 [G][K*cp][cp], the wgrad GEMM output: dW[g*cg+co][ci][j] = dwt[g][j*cp+ci][co]).
  * delta > 1: dwt is the time-blocked wgrad output [G][(K+delta)*cp][delta*cp] and
- * dW[g*cg+co][ci][j] = sum_dl dwt[g][(j+dl)*cp+ci][dl*cp+co]. */
-int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, const float* inv_norm, float* dv,
-                       float* dg, int32_t C, int32_t G, int32_t K, int32_t cp, int32_t accumulate, int32_t delta,
-                       fhb_stream_t stream);
+ * dW[g*cg+co][ci][j] = sum_dl dwt[g][(j+dl)*cp+ci][dl*cp+co].
+ * ws: the 2*K-float workspace fhb_posconv_wn_prep filled: ws[K..2K) = 1 / ||v[:, :, j]|| is read, ws[0..K) is
+ * overwritten (scratch for the per-tap dot products sum dW * v). */
+int fhb_posconv_wn_bwd(const float* dwt, const float* v, const float* g, float* ws, float* dv, float* dg, int32_t C,
+                       int32_t G, int32_t K, int32_t cp, int32_t accumulate, int32_t delta, fhb_stream_t stream);
 
 /* ------------------------------------------------------------------ masked attention (K7)
  * o = softmax(scale * q k^T + keymask) v per (sample, head); replaces fairseq MultiheadAttention's
