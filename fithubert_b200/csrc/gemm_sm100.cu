@@ -922,7 +922,10 @@ int make_out_tmap(CUtensorMap* tm, void* base, bool f32, int n, int m, int ob_mo
 // TMA).  Among {64,128,192,256} pick the width that minimises (rounds over the SMs) x (tile width + a fixed
 // per-tile cost worth ~48 columns): N = 480 on 98 row blocks runs as 192+192+96 (294 tiles, 2 rounds)
 // instead of 256+224 (196 tiles, still 2 rounds of wider tiles).
-int pick_bn(int n, long long row_tiles, bool split_k) {
+// `step`: the granularity of a multi-block tile width = the column count of one 128-byte output slab (64 for 16-bit
+// outputs; 32 for fp32 outputs, which lets N = 480 run as three EQUAL 160-column tiles: every CTA of the two-round
+// schedule then owns 320 columns instead of up to 384).
+int pick_bn(int n, long long row_tiles, bool split_k, int step = 64) {
   const int n16 = (n + 15) / 16 * 16;
   if (n16 <= 64) return n16;
   static const int forced = getenv("FHB_GEMM_BN") ? atoi(getenv("FHB_GEMM_BN")) : 0;  // tuning sweeps only
@@ -930,7 +933,7 @@ int pick_bn(int n, long long row_tiles, bool split_k) {
   const int sms = fhb_num_sms();
   int best = kMaxBN;
   double best_cost = 1e30;
-  for (int bn = kMaxBN; bn >= 64; bn -= 64) {
+  for (int bn = kMaxBN; bn >= 64; bn -= step) {
     const int nblk = (n + bn - 1) / bn;
     const int w = nblk == 1 ? n16 : bn;
     const long long tiles = row_tiles * nblk;
@@ -1163,7 +1166,9 @@ extern "C" int fhb_gemm(const fhb_gemm_args* a, fhb_stream_t stream) {
   p.n = a->n;
   p.k = a->k;
   p.num_m_blk = (a->m + kBM - 1) / kBM;
-  p.bn = pick_bn(a->n, (long long)p.num_m_blk * num_ob, (flags & FHB_EPI_ATOMIC_ADD) != 0);
+  static const bool bn32 = getenv("FHB_GEMM_BN32") == nullptr || atoi(getenv("FHB_GEMM_BN32")) != 0;  // A/B switch
+  const bool f32_slabs = bn32 && (flags & FHB_EPI_OUT_F32) && !(flags & (FHB_EPI_STORE_PREACT | FHB_EPI_ATOMIC_ADD));
+  p.bn = pick_bn(a->n, (long long)p.num_m_blk * num_ob, (flags & FHB_EPI_ATOMIC_ADD) != 0, f32_slabs ? 32 : 64);
   p.num_n_blk = (a->n + p.bn - 1) / p.bn;
   // Pair modes (see the kernel header): forward-shaped GEMMs (both operands K-major, no split-K) with at least two row
   // blocks run as clusters of two CTAs.  FHB_GEMM_PAIR=1: the B tile is shared by TMA multicast (L2 -> SM traffic of B
