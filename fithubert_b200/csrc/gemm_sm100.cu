@@ -39,7 +39,6 @@ constexpr int kThreads = kEpiThreads + 96;  // + TMA producer warp, MMA warp, st
 constexpr int kMaxOut = 4;                  // most output staging buffers (p.n_out)
 constexpr uint32_t kABytes = kBM * kBK * 2;     // 16 KiB
 constexpr uint32_t kBBytes = kMaxBN * kBK * 2;  // 32 KiB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kStoreBytes = kBM * 128;  // one output slab: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
 constexpr uint32_t kBiasBytes = 2 * kMaxBN * 4;
 constexpr int kInRing = 6;  // most epilogue-input slabs in flight (the ring depth is p.n_in: 3, or 4 with cta_group::2)
