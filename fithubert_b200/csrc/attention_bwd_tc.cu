@@ -339,7 +339,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       // partner lane supplies the other half through one shuffle (the forward's pair index q * ceil(T / 2) + key / 2,
       // advanced by a constant per query pair).  Even key rows read the low 16 bits, odd ones the high 16.
       const bool odd = lane & 1;
-      const uint32_t lsh = odd ? 0u : 16u, thrhi = drop_thr << 16;
+      const uint32_t psel = odd ? 0x3276u : 0x5410u, thrhi = drop_thr << 16;
       const uint32_t T2h = (uint32_t)((T + 1) >> 1);
       const uint32_t xh = ((uint32_t)((b * H + h) * T + q0 + quad * 32 + (int)odd) * T2h + ((uint32_t)key >> 1)) * 0x9E3779B1u + drop_seed;
       const uint32_t xstep = 2u * T2h * 0x9E3779B1u;
@@ -389,8 +389,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
               if (DROP) {
                 const uint32_t mine = fhb_hash32(xh + (uint32_t)((c + e) >> 1) * xstep);  // query c + e + odd
                 const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);                // query c + e + 1 - odd
-                const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
-                const f32x2_t mk2 = pack2((b0 << lsh) >= thrhi ? drop_scale : 0.f, (b1 << lsh) >= thrhi ? drop_scale : 0.f);
+                // one byte permute gathers the two 16-bit decisions of this lane: (query c + e | query c + e + 1) =
+                // even key rows (low halves): (mine | other), odd key rows (high halves): (other | mine)
+                const uint32_t w = __byte_perm(mine, other, psel);
+                const f32x2_t mk2 = pack2((w << 16) >= thrhi ? drop_scale : 0.f, w >= thrhi ? drop_scale : 0.f);
                 pd2 = mul2(p2, mk2);
                 dp2 = mul2(dp2, mk2);
               }
